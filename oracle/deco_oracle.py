@@ -1,0 +1,501 @@
+"""CPU/torch restatement of the DeCo hot path -- TEST INFRASTRUCTURE ONLY.
+
+This file is the *oracle*: a plain-PyTorch (fp32 by default) restatement of the
+reference algorithm for the path named in BASELINE.json.  Only `tests/`,
+`__graft_entry__.smoke()` and the `cpu_baseline` / `--impl reference` legs of
+`bench.py` may import it.  The product (`deco_b200/`) never does.
+
+Parity status: PINNED.  `oracle/validate_against_reference.py` (run in the build
+container, where /root/reference exists) checks every function below against the
+live reference modules on identical weights/inputs, and `tests/golden/make_golden.py`
+stores reference outputs as fixtures that the CPU test-suite re-checks.
+
+Everything is functional: parameters come in as a flat ``dict[str, Tensor]`` whose
+keys are the reference module's ``state_dict`` names (the checkpoint contract,
+SURVEY.md section 8a).  Using F.linear / F.layer_norm / F.scaled_dot_product_attention
+means `torch.autocast(..., dtype=torch.bfloat16)` reproduces the reference's
+mixed-precision rounding points exactly as well.
+
+Reference citations are `path:line` under /root/reference.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+Params = Dict[str, torch.Tensor]
+
+
+# --------------------------------------------------------------------------- config
+@dataclass(frozen=True)
+class DenoiserCfg:
+    """Constructor arguments of the class-conditional denoiser
+    (src/models/transformer/dit_c2i_DeCo.py:417-433)."""
+    in_channels: int = 3
+    num_groups: int = 16
+    hidden_size: int = 1152
+    hidden_size_x: int = 32
+    num_blocks: int = 31
+    num_cond_blocks: int = 28
+    patch_size: int = 16
+    num_classes: int = 1000
+    max_freqs: int = 8
+
+    @property
+    def head_dim(self) -> int:
+        return self.hidden_size // self.num_groups
+
+    @property
+    def ffn_hidden(self) -> int:
+        # FlattenDiTBlock: mlp_hidden_dim=int(hidden*4.0); FeedForward: int(2*h/3)
+        # (dit_c2i_DeCo.py:200-201, :108)
+        return int(2 * int(self.hidden_size * 4.0) / 3)
+
+    @property
+    def num_res_blocks(self) -> int:
+        return self.num_blocks - self.num_cond_blocks
+
+
+CFG_XL = DenoiserCfg()                                            # configs_c2i/DeCo_XL.yaml:44-55
+CFG_L = DenoiserCfg(hidden_size=1024, num_blocks=25, num_cond_blocks=22)  # configs_c2i/DeCo_large.yaml
+
+
+def param_shapes(cfg: DenoiserCfg) -> Dict[str, Tuple[int, ...]]:
+    """state_dict names and shapes of the reference module (SURVEY.md 8a contract)."""
+    H, Hx, p, C = cfg.hidden_size, cfg.hidden_size_x, cfg.patch_size, cfg.in_channels
+    d, ffn = cfg.head_dim, cfg.ffn_hidden
+    s: Dict[str, Tuple[int, ...]] = {
+        "x_embedder.embedder.0.weight": (Hx, C + cfg.max_freqs ** 2),
+        "x_embedder.embedder.0.bias": (Hx,),
+        "s_embedder.proj.weight": (H, C * p * p),
+        "s_embedder.proj.bias": (H,),
+        "t_embedder.mlp.0.weight": (H, 256),
+        "t_embedder.mlp.0.bias": (H,),
+        "t_embedder.mlp.2.weight": (H, H),
+        "t_embedder.mlp.2.bias": (H,),
+        "y_embedder.embedding_table.weight": (cfg.num_classes + 1, H),
+    }
+    for i in range(cfg.num_cond_blocks):
+        b = f"blocks.{i}."
+        s[b + "norm1.weight"] = (H,)
+        s[b + "attn.qkv.weight"] = (3 * H, H)
+        s[b + "attn.q_norm.weight"] = (d,)
+        s[b + "attn.k_norm.weight"] = (d,)
+        s[b + "attn.proj.weight"] = (H, H)
+        s[b + "attn.proj.bias"] = (H,)
+        s[b + "norm2.weight"] = (H,)
+        s[b + "mlp.w1.weight"] = (ffn, H)
+        s[b + "mlp.w3.weight"] = (ffn, H)
+        s[b + "mlp.w2.weight"] = (H, ffn)
+        s[b + "adaLN_modulation.0.weight"] = (6 * H, H)
+        s[b + "adaLN_modulation.0.bias"] = (6 * H,)
+    s["dec_net.cond_embed.weight"] = (p * p * Hx, H)
+    s["dec_net.cond_embed.bias"] = (p * p * Hx,)
+    s["dec_net.input_proj.weight"] = (Hx, Hx)
+    s["dec_net.input_proj.bias"] = (Hx,)
+    for j in range(cfg.num_res_blocks):
+        b = f"dec_net.res_blocks.{j}."
+        s[b + "in_ln.weight"] = (Hx,)
+        s[b + "in_ln.bias"] = (Hx,)
+        s[b + "mlp.0.weight"] = (Hx, Hx)
+        s[b + "mlp.0.bias"] = (Hx,)
+        s[b + "mlp.2.weight"] = (Hx, Hx)
+        s[b + "mlp.2.bias"] = (Hx,)
+        s[b + "adaLN_modulation.1.weight"] = (3 * Hx, Hx)
+        s[b + "adaLN_modulation.1.bias"] = (3 * Hx,)
+    s["dec_net.final_layer.linear.weight"] = (C, Hx)
+    s["dec_net.final_layer.linear.bias"] = (C,)
+    return s
+
+
+def seeded_params(cfg: DenoiserCfg, seed: int = 1234, device="cpu") -> Params:
+    """Deterministic, *fully non-zero* random weights keyed by parameter name.
+
+    The reference's default init zeroes the decoder output layers
+    (dit_c2i_DeCo.py:386-393) so parity on default init is vacuous.
+    Each tensor is drawn from its own generator seeded with (seed, name index) so the
+    same weights can be produced for the reference module, the oracle and the CUDA
+    module on any box without shipping a checkpoint.
+    """
+    out: Params = {}
+    for idx, (name, shape) in enumerate(sorted(param_shapes(cfg).items())):
+        g = torch.Generator().manual_seed(seed * 100003 + idx)
+        if len(shape) == 2 and not name.startswith("y_embedder"):
+            std = 1.0 / math.sqrt(shape[1])
+            if "adaLN_modulation" in name:
+                std *= 0.5
+            w = torch.randn(shape, generator=g) * std
+        elif name.startswith("y_embedder"):
+            w = torch.randn(shape, generator=g) * 0.5
+        elif name.endswith("norm.weight") or name.endswith("norm1.weight") or name.endswith("norm2.weight") \
+                or name.endswith("in_ln.weight"):
+            w = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        else:  # biases
+            w = 0.05 * torch.randn(shape, generator=g)
+        out[name] = w.to(device)
+    return out
+
+
+# --------------------------------------------------------------------------- tables
+def timestep_embedding(t: torch.Tensor, dim: int = 256, max_period: float = 10.0) -> torch.Tensor:
+    """[cos || sin] sinusoid with max_period 10 (dit_c2i_DeCo.py:43-53)."""
+    half = dim // 2
+    freqs = torch.exp(-math.log(max_period)
+                      * torch.arange(0, half, dtype=torch.float32, device=t.device) / half)
+    args = t[..., None].float() * freqs[None]
+    return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+
+
+def rope_table_2d(head_dim: int, height: int, width: int, theta: float = 10000.0,
+                  scale: float = 16.0) -> torch.Tensor:
+    """2-D axial RoPE angles, returned as real angles [L, head_dim/2] (pair 2k -> x, 2k+1 -> y)
+    (dit_c2i_DeCo.py:116-131: positions linspace(0,scale,W), freqs theta^(-4k/d))."""
+    x_pos = torch.linspace(0, scale, width)
+    y_pos = torch.linspace(0, scale, height)
+    y_pos, x_pos = torch.meshgrid(y_pos, x_pos, indexing="ij")
+    freqs = 1.0 / (theta ** (torch.arange(0, head_dim, 4)[: head_dim // 4].float() / head_dim))
+    xa = torch.outer(x_pos.reshape(-1), freqs).float()
+    ya = torch.outer(y_pos.reshape(-1), freqs).float()
+    return torch.stack([xa, ya], dim=-1).reshape(height * width, -1)
+
+
+def apply_rope(x: torch.Tensor, angles: torch.Tensor) -> torch.Tensor:
+    """x: [B, N, heads, d]; rotate consecutive pairs (2j, 2j+1) by angles[n, j]
+    (dit_c2i_DeCo.py:134-145, written with real arithmetic)."""
+    xf = x.float().reshape(*x.shape[:-1], -1, 2)
+    cos = torch.cos(angles)[None, :, None, :]
+    sin = torch.sin(angles)[None, :, None, :]
+    a, b = xf[..., 0], xf[..., 1]
+    out = torch.stack([a * cos - b * sin, a * sin + b * cos], dim=-1)
+    return out.flatten(3).type_as(x)
+
+
+def nerf_pos_table(patch_size: int, max_freqs: int = 8) -> torch.Tensor:
+    """Constant per-pixel positional table [p*p, max_freqs^2] (dit_c2i_DeCo.py:221-236)."""
+    pos = torch.linspace(0, 1, patch_size)
+    pos_y, pos_x = torch.meshgrid(pos, pos, indexing="ij")
+    pos_x = pos_x.reshape(-1, 1, 1)
+    pos_y = pos_y.reshape(-1, 1, 1)
+    freqs = torch.linspace(0, max_freqs, max_freqs)
+    fx, fy = freqs[None, :, None], freqs[None, None, :]
+    coeffs = (1 + fx * fy) ** -1
+    return (torch.cos(pos_x * fx * torch.pi) * torch.cos(pos_y * fy * torch.pi) * coeffs
+            ).view(-1, max_freqs ** 2)
+
+
+# --------------------------------------------------------------------------- layers
+def rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
+    """dit_c2i_DeCo.py:94-99 (fp32 statistics, cast back, then weight * x)."""
+    dt = x.dtype
+    xf = x.to(torch.float32)
+    xf = xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps)
+    return weight * xf.to(dt)
+
+
+def modulate(x, shift, scale):
+    """dit_c2i_DeCo.py:11-12."""
+    return x * (1 + scale) + shift
+
+
+def attention(P: Params, pre: str, x: torch.Tensor, angles: torch.Tensor, heads: int,
+              mask=None) -> torch.Tensor:
+    """RAttention.forward (dit_c2i_DeCo.py:174-190)."""
+    B, N, C = x.shape
+    d = C // heads
+    qkv = F.linear(x, P[pre + "qkv.weight"]).reshape(B, N, 3, heads, d).permute(2, 0, 1, 3, 4)
+    q, k, v = qkv[0], qkv[1], qkv[2]
+    q = rmsnorm(q, P[pre + "q_norm.weight"])
+    k = rmsnorm(k, P[pre + "k_norm.weight"])
+    q, k = apply_rope(q, angles), apply_rope(k, angles)
+    q, k, v = q.transpose(1, 2), k.transpose(1, 2).contiguous(), v.transpose(1, 2).contiguous()
+    o = F.scaled_dot_product_attention(q, k, v, attn_mask=mask, dropout_p=0.0)
+    o = o.transpose(1, 2).reshape(B, N, C)
+    return F.linear(o, P[pre + "proj.weight"], P[pre + "proj.bias"])
+
+
+def feed_forward(P: Params, pre: str, x: torch.Tensor) -> torch.Tensor:
+    """FeedForward.forward (dit_c2i_DeCo.py:112-114)."""
+    return F.linear(F.silu(F.linear(x, P[pre + "w1.weight"])) * F.linear(x, P[pre + "w3.weight"]),
+                    P[pre + "w2.weight"])
+
+
+def dit_block(P: Params, i: int, x, c, angles, heads, mask=None):
+    """FlattenDiTBlock.forward (dit_c2i_DeCo.py:206-210)."""
+    b = f"blocks.{i}."
+    mod = F.linear(c, P[b + "adaLN_modulation.0.weight"], P[b + "adaLN_modulation.0.bias"])
+    sh1, sc1, g1, sh2, sc2, g2 = mod.chunk(6, dim=-1)
+    x = x + g1 * attention(P, b + "attn.", modulate(rmsnorm(x, P[b + "norm1.weight"]), sh1, sc1),
+                           angles, heads, mask)
+    x = x + g2 * feed_forward(P, b + "mlp.", modulate(rmsnorm(x, P[b + "norm2.weight"]), sh2, sc2))
+    return x
+
+
+def pixel_decoder(P: Params, cfg: DenoiserCfg, x: torch.Tensor, s: torch.Tensor) -> torch.Tensor:
+    """SimpleMLPAdaLN.forward + ResBlock + decoder FinalLayer
+    (dit_c2i_DeCo.py:395-415, :313-317, :329-332).  x: [BL, p*p, Hx], s: [BL, H]."""
+    Hx = cfg.hidden_size_x
+    x = F.linear(x, P["dec_net.input_proj.weight"], P["dec_net.input_proj.bias"])
+    y = F.linear(s, P["dec_net.cond_embed.weight"], P["dec_net.cond_embed.bias"])
+    y = y.reshape(y.shape[0], cfg.patch_size ** 2, -1)
+    for j in range(cfg.num_res_blocks):
+        b = f"dec_net.res_blocks.{j}."
+        mod = F.linear(F.silu(y), P[b + "adaLN_modulation.1.weight"], P[b + "adaLN_modulation.1.bias"])
+        sh, sc, g = mod.chunk(3, dim=-1)
+        h = modulate(F.layer_norm(x, (Hx,), P[b + "in_ln.weight"], P[b + "in_ln.bias"], 1e-6), sh, sc)
+        h = F.linear(F.silu(F.linear(h, P[b + "mlp.0.weight"], P[b + "mlp.0.bias"])),
+                     P[b + "mlp.2.weight"], P[b + "mlp.2.bias"])
+        x = x + g * h
+    x = F.layer_norm(x, (Hx,), None, None, 1e-6)
+    return F.linear(x, P["dec_net.final_layer.linear.weight"], P["dec_net.final_layer.linear.bias"])
+
+
+def denoiser_forward(P: Params, cfg: DenoiserCfg, x: torch.Tensor, t: torch.Tensor, y: torch.Tensor,
+                     s: Optional[torch.Tensor] = None, mask=None, return_s: bool = False):
+    """PixNerDiT.forward (dit_c2i_DeCo.py:488-510).  x:[B,C,H,W] t:[B] y:[B] int64."""
+    B, _, Hh, Ww = x.shape
+    p, H = cfg.patch_size, cfg.hidden_size
+    angles = rope_table_2d(cfg.head_dim, Hh // p, Ww // p).to(x.device)
+    xp = F.unfold(x, kernel_size=p, stride=p).transpose(1, 2)                      # [B, L, C*p*p]
+    tf = timestep_embedding(t.view(-1))
+    te = F.linear(F.silu(F.linear(tf, P["t_embedder.mlp.0.weight"], P["t_embedder.mlp.0.bias"])),
+                  P["t_embedder.mlp.2.weight"], P["t_embedder.mlp.2.bias"]).view(B, -1, H)
+    ye = F.embedding(y, P["y_embedder.embedding_table.weight"]).view(B, 1, H)
+    c = F.silu(te + ye)
+    if s is None:
+        s = F.linear(xp, P["s_embedder.proj.weight"], P["s_embedder.proj.bias"])
+        for i in range(cfg.num_cond_blocks):
+            s = dit_block(P, i, s, c, angles, cfg.num_groups, mask)
+        s = F.silu(te + s)
+    Bn, L, _ = s.shape
+    px = xp.reshape(Bn * L, cfg.in_channels, p * p).transpose(1, 2)               # [BL, p*p, C]
+    sf = s.reshape(Bn * L, H)
+    tab = nerf_pos_table(p, cfg.max_freqs).to(device=px.device, dtype=px.dtype)
+    emb_in = torch.cat([px, tab[None].expand(Bn * L, -1, -1)], dim=-1)
+    px = F.linear(emb_in, P["x_embedder.embedder.0.weight"], P["x_embedder.embedder.0.bias"])
+    out = pixel_decoder(P, cfg, px, sf)                                            # [BL, p*p, C]
+    out = out.transpose(1, 2).reshape(Bn, L, -1)
+    out = F.fold(out.transpose(1, 2).contiguous(), (Hh, Ww), kernel_size=p, stride=p)
+    return (out, s) if return_s else out
+
+
+# --------------------------------------------------------------------------- scheduler / sampler
+def shift_respace(t, shift: float = 3.0):
+    """flow_matching/sampling.py:11-12."""
+    return t / (t + (1 - t) * shift)
+
+
+def make_timesteps(num_steps: int, timeshift: float = 1.0, last_step: Optional[float] = None) -> torch.Tensor:
+    """fp32 schedule linspace(0, 1-last, n) || 1.0, then timeshift (sampling.py:52-57)."""
+    if last_step is None or num_steps == 1:
+        last_step = 1.0 / num_steps
+    ts = torch.linspace(0.0, 1 - last_step, num_steps)
+    ts = torch.cat([ts, torch.tensor([1.0])], dim=0)
+    return shift_respace(ts, timeshift)
+
+
+def cfg_combine(out: torch.Tensor, g: float) -> torch.Tensor:
+    """simple_guidance_fn (base/guidance.py:3-6): rows [uncond || cond]."""
+    u, c = out.chunk(2, dim=0)
+    return u + g * (c - u)
+
+
+def euler_sample(net: Callable, noise: torch.Tensor, cond: torch.Tensor, uncond: torch.Tensor,
+                 num_steps: int, guidance: float, gmin: float = 0.0, gmax: float = 1.0,
+                 timeshift: float = 1.0, last_step: Optional[float] = None,
+                 return_trajs: bool = False):
+    """EulerSampler._impl_sampling with ode_step_fn and LinearScheduler
+    (flow_matching/sampling.py:66-107).  Guidance applies iff gmin < t <= gmax (:93)."""
+    steps = make_timesteps(num_steps, timeshift, last_step).to(noise.device, noise.dtype)
+    B = noise.shape[0]
+    cfg_c = torch.cat([uncond, cond], dim=0)
+    x = noise
+    xs, vs = [noise], []
+    for t_cur, t_next in zip(steps[:-1], steps[1:]):
+        dt = t_next - t_cur
+        out = net(torch.cat([x, x], 0), t_cur.repeat(2 * B), cfg_c)
+        g = guidance if (t_cur > gmin and t_cur <= gmax) else 1.0
+        v = cfg_combine(out, g)
+        x = x + v * dt
+        xs.append(x)
+        vs.append(v)
+    return (x, xs, vs) if return_trajs else x
+
+
+def heun_sample(net: Callable, noise, cond, uncond, num_steps: int, guidance: float,
+                gmin: float = 0.0, gmax: float = 1.0, timeshift: float = 1.0,
+                last_step: Optional[float] = None, exact_henu: bool = False):
+    """HeunSampler._impl_sampling, ODE step (flow_matching/sampling.py:230-296).
+    With exact_henu=False the corrector's velocity is reused as the next predictor."""
+    steps = make_timesteps(num_steps, timeshift, last_step).to(noise.device)
+    B = noise.shape[0]
+    cfg_c = torch.cat([uncond, cond], dim=0)
+    x = noise
+    v_hat = None
+    for i, (t_cur, t_next) in enumerate(zip(steps[:-1], steps[1:])):
+        dt = t_next - t_cur
+        g = guidance if (t_cur > gmin and t_cur <= gmax) else 1.0
+        if i == 0 or exact_henu:
+            v = cfg_combine(net(torch.cat([x, x], 0), t_cur.repeat(2 * B), cfg_c), g)
+        else:
+            v = v_hat
+        x_hat = x + v * dt
+        if i < num_steps - 1:
+            v_hat = cfg_combine(net(torch.cat([x_hat, x_hat], 0), t_next.repeat(2 * B), cfg_c), g)
+            v = (v + v_hat) / 2
+            x = x + v * dt
+        else:
+            x = x + v * dt
+    return x
+
+
+def lagrange_coeffs(order: int, ts: Sequence[float], t0: float, t1: float) -> Tuple[float, ...]:
+    """Normalised integrals of the Lagrange basis over [t0, t1] for the last `order` nodes of ts
+    (pre_integral.py:4-125, orders 1-4; evaluated here in closed form with float64 polynomials)."""
+    import numpy as np
+    order = min(order, len(ts))
+    nodes = [float(v) for v in ts[-order:]]
+    if order == 1:
+        return (1.0,)
+    ints = []
+    for j, tj in enumerate(nodes):
+        poly = np.poly1d([1.0])
+        den = 1.0
+        for m, tm in enumerate(nodes):
+            if m != j:
+                poly = poly * np.poly1d([1.0, -tm])
+                den *= (tj - tm)
+        ip = poly.integ()
+        ints.append((ip(t1) - ip(t0)) / den)
+    tot = sum(ints)
+    return tuple(v / tot for v in ints)
+
+
+def adam_coeffs(num_steps: int, order: int, timeshift: float, last_step: Optional[float] = None):
+    """AdamLMSampler.__init__/_reparameterize_coeffs (adam_sampling.py:60-84)."""
+    if last_step is None:
+        last_step = 1.0 / num_steps
+    ts = torch.linspace(0.0, 1 - last_step, num_steps)
+    ts = torch.cat([ts, torch.tensor([1.0])], dim=0)
+    ts = shift_respace(ts, timeshift)
+    deltas = ts[1:] - ts[:-1]
+    coeffs = []
+    for i in range(num_steps):
+        o = min(order, i + 1)
+        coeffs.append(lagrange_coeffs(o, [float(v) for v in ts[: i + 1]], float(ts[i]), float(ts[i + 1])))
+    return ts, deltas, coeffs
+
+
+def adam_sample(net: Callable, noise, cond, uncond, num_steps: int, guidance: float, order: int = 2,
+                gmin: float = 0.0, gmax: float = 1.0, timeshift: float = 1.0):
+    """AdamLMSampler._impl_sampling (adam_sampling.py:86-122); strict (gmin, gmax) window (:104)."""
+    ts, deltas, coeffs = adam_coeffs(num_steps, order, timeshift)
+    B = noise.shape[0]
+    cfg_c = torch.cat([uncond, cond], dim=0)
+    x = noise
+    preds: List[torch.Tensor] = []
+    t_cur = torch.zeros([B]).to(noise.device, noise.dtype)
+    for i in range(num_steps):
+        out = net(torch.cat([x, x], 0), t_cur.repeat(2), cfg_c)
+        g = guidance if (t_cur[0] > gmin and t_cur[0] < gmax) else 1.0
+        preds.append(cfg_combine(out, g))
+        o = len(coeffs[i])
+        v = torch.zeros_like(preds[-1])
+        for j in range(o):
+            v = v + coeffs[i][j] * preds[-o:][j]
+        x = x + v * deltas[i].to(x.device)
+        t_cur = t_cur + deltas[i].to(x.device)
+    return x
+
+
+def fp2uint8(x: torch.Tensor) -> torch.Tensor:
+    """src/models/autoencoder/base.py:32-34."""
+    return torch.clamp((x + 1) * 127.5 + 0.5, 0, 255).to(torch.uint8)
+
+
+# --------------------------------------------------------------------------- DCT / FM loss
+JPEG_LUMA = [
+    [16, 11, 10, 16, 24, 40, 51, 61], [12, 12, 14, 19, 26, 58, 60, 55],
+    [14, 13, 16, 24, 40, 57, 69, 56], [14, 17, 22, 29, 51, 87, 80, 62],
+    [18, 22, 37, 56, 68, 109, 103, 77], [24, 35, 55, 64, 81, 104, 113, 92],
+    [49, 64, 78, 87, 103, 121, 120, 101], [72, 92, 95, 98, 112, 100, 103, 99]]
+JPEG_CHROMA = [
+    [17, 18, 24, 47, 99, 99, 99, 99], [18, 21, 26, 66, 99, 99, 99, 99],
+    [24, 26, 56, 99, 99, 99, 99, 99], [47, 66, 99, 99, 99, 99, 99, 99],
+    [99] * 8, [99] * 8, [99] * 8, [99] * 8]
+
+
+def dct_matrix(n: int = 8) -> torch.Tensor:
+    """Orthonormal DCT-II matrix (training_repa_DeCo.py:95-104)."""
+    i = torch.arange(n, dtype=torch.float32)
+    k = i.unsqueeze(1)
+    C = torch.cos(math.pi * (2 * i + 1) * k / (2.0 * n))
+    a = torch.sqrt(torch.tensor(2.0) / n) * torch.ones(n)
+    a[0] = math.sqrt(1.0 / n)
+    return a.unsqueeze(1) * C
+
+
+def freq_weight(quality: int = 85, mode: str = "inv_gamma", gamma: float = 1.0) -> torch.Tensor:
+    """JPEG-table frequency weights [3,8,8] (training_repa_DeCo.py:138-195)."""
+    def scale_q(base):
+        q = max(1, min(100, int(quality)))
+        sc = 5000 / q if q < 50 else 200 - 2 * q
+        return torch.floor((torch.tensor(base, dtype=torch.float32) * sc + 50) / 100).clamp(1, 255)
+
+    def to_w(Q):
+        if mode == "inv":
+            w = 1.0 / Q
+        elif mode == "inv_gamma":
+            w = (Q.mean() / Q) ** gamma
+        else:
+            raise ValueError("mode must be 'inv' or 'inv_gamma'")
+        return w / w.mean()
+    wy, wc = to_w(scale_q(JPEG_LUMA)), to_w(scale_q(JPEG_CHROMA))
+    return torch.stack([wy, wc, wc], dim=0)
+
+
+def rgb2ycbcr(x: torch.Tensor) -> torch.Tensor:
+    """BT.601 full range without offsets (training_repa_DeCo.py:106-114)."""
+    r, g, b = x[:, 0:1], x[:, 1:2], x[:, 2:3]
+    return torch.cat([0.299 * r + 0.587 * g + 0.114 * b,
+                      -0.168736 * r - 0.331264 * g + 0.5 * b,
+                      0.5 * r - 0.418688 * g - 0.081312 * b], dim=1)
+
+
+def block_dct(x: torch.Tensor, bs: int = 8) -> torch.Tensor:
+    """8x8 block DCT -> [B,C,Bh,Bw,8,8], reflect padding for ragged sizes
+    (training_repa_DeCo.py:116-136)."""
+    B, C, H, W = x.shape
+    ph, pw = (-H) % bs, (-W) % bs
+    if ph or pw:
+        x = F.pad(x, (0, pw, 0, ph), mode="reflect")
+    B, C, H2, W2 = x.shape
+    blocks = x.unfold(2, bs, bs).unfold(3, bs, bs).contiguous().view(-1, bs, bs)
+    Cm = dct_matrix(bs).to(x.device, x.dtype)
+    d = torch.matmul(torch.matmul(Cm.unsqueeze(0), blocks), Cm.t().unsqueeze(0))
+    return d.view(B, C, H2 // bs, W2 // bs, bs, bs)
+
+
+def dct_fm_loss(out: torch.Tensor, v_t: torch.Tensor, freq_loss_weight: float = 1.0,
+                quality: int = 85, mode: str = "inv_gamma", gamma: float = 1.0) -> Dict[str, torch.Tensor]:
+    """loss = mean((out-v_t)^2) + freq_loss_weight * mean(freq_w * (dct(ycbcr(out)) - dct(ycbcr(v_t)))^2)
+    (training_repa_DeCo.py:273-285 and the original trainer)."""
+    fm = ((out - v_t) ** 2).mean()
+    w = freq_weight(quality, mode, gamma).to(out.device)[None, :, None, None]
+    fr = (w * (block_dct(rgb2ycbcr(out)) - block_dct(rgb2ycbcr(v_t))) ** 2).mean()
+    return dict(fm_loss=fm, fm_loss_freq=fr, loss=fm + freq_loss_weight * fr)
+
+
+def time_shift(t, timeshift: float = 1.0):
+    """training_repa_DeCo.py:39-40."""
+    return t / (t + (1 - t) * timeshift)
+
+
+def make_xt_vt(x: torch.Tensor, noise: torch.Tensor, t: torch.Tensor):
+    """LinearScheduler interpolation: x_t = t*x + (1-t)*eps, v_t = x - eps
+    (training_repa_DeCo.py:231-237, scheduling.py:6-14)."""
+    a = t.view(-1, 1, 1, 1)
+    return a * x + (1 - a) * noise, x - noise

@@ -1,0 +1,222 @@
+"""Generate golden fixtures by executing the UNMODIFIED reference (/root/reference) on CPU fp32,
+and pin the oracle (oracle/deco_oracle.py) against it in the same run.
+
+Run in the build container only (the reference does not exist on the GPU box):
+    python tests/golden/make_golden.py
+Writes tests/golden/*.npz.  Every fixture is reproducible from seeds: weights come from
+oracle.deco_oracle.seeded_params (name-keyed generators), inputs from torch.Generator seeds.
+"""
+import os
+import sys
+import types
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference")
+
+# training_repa_DeCo.py:3,10 import names from timm only; stub them
+timm = types.ModuleType("timm")
+timm_data = types.ModuleType("timm.data")
+timm_data.IMAGENET_DEFAULT_MEAN = (0.485, 0.456, 0.406)
+timm_data.IMAGENET_DEFAULT_STD = (0.229, 0.224, 0.225)
+timm.data = timm_data
+sys.modules["timm"] = timm
+sys.modules["timm.data"] = timm_data
+
+from src.models.transformer.dit_c2i_DeCo import PixNerDiT as RefDiT  # noqa: E402
+from src.diffusion.flow_matching.sampling import EulerSampler as RefEuler, HeunSampler as RefHeun, ode_step_fn  # noqa: E402
+from src.diffusion.flow_matching.adam_sampling import AdamLMSampler as RefAdam  # noqa: E402
+from src.diffusion.flow_matching.scheduling import LinearScheduler as RefSched  # noqa: E402
+from src.diffusion.base.guidance import simple_guidance_fn as ref_guidance  # noqa: E402
+from src.diffusion.flow_matching.training_repa_DeCo import REPATrainer as RefTrainer  # noqa: E402
+
+from oracle import deco_oracle as O  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+torch.set_grad_enabled(False)
+
+
+def rel_l2(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm())
+
+
+def build_ref(cfg: O.DenoiserCfg, seed=1234):
+    m = RefDiT(in_channels=cfg.in_channels, num_groups=cfg.num_groups, hidden_size=cfg.hidden_size,
+               hidden_size_x=cfg.hidden_size_x, num_blocks=cfg.num_blocks,
+               num_cond_blocks=cfg.num_cond_blocks, patch_size=cfg.patch_size,
+               num_classes=cfg.num_classes)
+    P = O.seeded_params(cfg, seed)
+    sd = m.state_dict()
+    assert set(sd.keys()) == set(P.keys()), set(sd.keys()) ^ set(P.keys())
+    for k in sd:
+        assert tuple(sd[k].shape) == tuple(P[k].shape), k
+    m.load_state_dict(P)
+    return m.eval(), P
+
+
+def seeded_noise(n, shape, seed0=0):
+    # src/data/dataset/randn.py:74-75: one CPU generator per sample
+    return torch.stack([torch.randn(shape, generator=torch.Generator().manual_seed(seed0 + i),
+                                    dtype=torch.float32) for i in range(n)])
+
+
+def golden_forward(name, cfg, B, res, seed):
+    m, P = build_ref(cfg)
+    x = seeded_noise(B, (cfg.in_channels, res, res), seed)
+    t = torch.linspace(0.05, 0.95, B)
+    y = torch.tensor([(7 * i + 3) % (cfg.num_classes + 1) for i in range(B)])
+    y[-1] = cfg.num_classes  # null label row
+    ref = m(x, t, y)
+    ora = O.denoiser_forward(P, cfg, x, t, y)
+    e = rel_l2(ora, ref)
+    print(f"[{name}] oracle vs reference forward rel-L2 = {e:.3e}")
+    assert e < 2e-6, e
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        ref_bf = m(x, t, y).float()
+    print(f"[{name}] reference bf16-autocast vs fp32 rel-L2 = {rel_l2(ref_bf, ref):.3e} (noise floor)")
+    np.savez_compressed(os.path.join(OUT, f"{name}.npz"), x=x.numpy(), t=t.numpy(), y=y.numpy(),
+                        out=ref.numpy(), cfg=np.array([cfg.in_channels, cfg.num_groups, cfg.hidden_size,
+                                                       cfg.hidden_size_x, cfg.num_blocks, cfg.num_cond_blocks,
+                                                       cfg.patch_size, cfg.num_classes]),
+                        bf16_floor=np.float64(rel_l2(ref_bf, ref)))
+
+
+def golden_samplers():
+    """Sampler control flow pinned with an analytic 'network' so the fixture is tiny."""
+    def toy_net(x, t, y):
+        # depends on x, t and the label so CFG order [uncond || cond] matters
+        return torch.tanh(x * (0.5 + t.view(-1, 1, 1, 1))) - 0.1 * y.view(-1, 1, 1, 1).float()
+    noise = seeded_noise(3, (3, 8, 8), 100)
+    cond = torch.tensor([1, 2, 3])
+    unc = torch.tensor([10, 10, 10])
+    out = {}
+    sch = RefSched()
+    for n, g, lo, hi, shift in [(10, 3.2, 0.1, 1.0, 1.0), (7, 2.0, 0.0, 0.6, 3.0)]:
+        s = RefEuler(scheduler=sch, w_scheduler=sch, guidance_fn=ref_guidance, num_steps=n, guidance=g,
+                     guidance_interval_min=lo, guidance_interval_max=hi, timeshift=shift, step_fn=ode_step_fn)
+        r = s(toy_net, noise, cond, unc)
+        o = O.euler_sample(toy_net, noise, cond, unc, n, g, lo, hi, shift)
+        assert torch.equal(O.make_timesteps(n, shift), s.timesteps)
+        assert rel_l2(o, r) < 1e-6, rel_l2(o, r)
+        out[f"euler_{n}"] = r.numpy()
+        out[f"euler_{n}_ts"] = s.timesteps.numpy()
+        h = RefHeun(scheduler=sch, w_scheduler=sch, guidance_fn=ref_guidance, num_steps=n, guidance=g,
+                    guidance_interval_min=lo, guidance_interval_max=hi, timeshift=shift, step_fn=ode_step_fn)
+        r = h(toy_net, noise, cond, unc)
+        o = O.heun_sample(toy_net, noise, cond, unc, n, g, lo, hi, shift)
+        assert rel_l2(o, r) < 1e-6, rel_l2(o, r)
+        out[f"heun_{n}"] = r.numpy()
+        h = RefHeun(scheduler=sch, w_scheduler=sch, guidance_fn=ref_guidance, num_steps=n, guidance=g,
+                    guidance_interval_min=lo, guidance_interval_max=hi, timeshift=shift, step_fn=ode_step_fn,
+                    exact_henu=True)
+        r = h(toy_net, noise, cond, unc)
+        o = O.heun_sample(toy_net, noise, cond, unc, n, g, lo, hi, shift, exact_henu=True)
+        assert rel_l2(o, r) < 1e-6, rel_l2(o, r)
+        out[f"heun_exact_{n}"] = r.numpy()
+    for n, order, shift, g in [(25, 2, 3.0, 4.0), (8, 3, 1.0, 2.0), (6, 4, 2.0, 1.5)]:
+        a = RefAdam(order=order, timeshift=shift, scheduler=sch, guidance_fn=ref_guidance, num_steps=n,
+                    guidance=g, guidance_interval_min=0.0, guidance_interval_max=1.0)
+        ts, deltas, coeffs = O.adam_coeffs(n, order, shift)
+        assert torch.equal(ts, a.timesteps)
+        for i in range(n):
+            rc = [float(c) for c in a.solver_coeffs[i]]
+            assert np.allclose(rc, coeffs[i], rtol=2e-4, atol=2e-5), (i, rc, coeffs[i])
+        r = a(toy_net, noise, cond, unc)
+        o = O.adam_sample(toy_net, noise, cond, unc, n, g, order, 0.0, 1.0, shift)
+        assert rel_l2(o, r) < 1e-4, rel_l2(o, r)
+        out[f"adam_{n}_{order}"] = r.numpy()
+        out[f"adam_{n}_{order}_coeffs"] = np.array(
+            [[float(c) for c in a.solver_coeffs[i]] + [0.0] * (4 - len(a.solver_coeffs[i])) for i in range(n)])
+        out[f"adam_{n}_{order}_ts"] = a.timesteps.numpy()
+    out["noise"] = noise.numpy()
+    np.savez_compressed(os.path.join(OUT, "samplers_toy.npz"), **out)
+    print("[samplers] euler/heun/adam oracle == reference")
+
+
+def golden_dct():
+    tr = RefTrainer(scheduler=RefSched(), encoder=torch.nn.Identity(), freq_loss_weight=1, freq_quality=85)
+    dct = RefTrainer._dct._torchdynamo_orig_callable if hasattr(RefTrainer._dct, "_torchdynamo_orig_callable") \
+        else RefTrainer._dct
+    assert torch.equal(tr.dct_mat, O.dct_matrix(8))
+    assert torch.allclose(tr.freq_w[0, :, 0, 0], O.freq_weight(85), rtol=0, atol=0)
+    res = {}
+    for name, shape, seed in [("256", (2, 3, 256, 256), 7), ("ragged", (3, 3, 36, 44), 8), ("one", (1, 3, 8, 8), 9)]:
+        g = torch.Generator().manual_seed(seed)
+        out = torch.randn(shape, generator=g)
+        v = torch.randn(shape, generator=g)
+        with torch.enable_grad():
+            o = out.clone().requires_grad_(True)
+            fm = ((o - v) ** 2).mean()
+            fr = (tr.freq_w * (dct(tr, tr._rgb2ycbcr(o)) - dct(tr, tr._rgb2ycbcr(v))) ** 2).mean()
+            loss = fm + tr.freq_loss_weight * fr
+            loss.backward()
+        with torch.enable_grad():
+            o2 = out.clone().requires_grad_(True)
+            d = O.dct_fm_loss(o2, v)
+            d["loss"].backward()
+        assert abs(float(d["loss"]) - float(loss)) < 1e-6 * abs(float(loss))
+        assert rel_l2(o2.grad, o.grad) < 1e-6
+        print(f"[dct {name}] fm={float(fm):.6f} freq={float(fr):.6f} loss={float(loss):.6f} "
+              f"|grad|={float(o.grad.norm()):.6e}")
+        res[f"{name}_seed"] = np.int64(seed)
+        res[f"{name}_shape"] = np.array(shape)
+        res[f"{name}_fm"] = np.float64(fm)
+        res[f"{name}_freq"] = np.float64(fr)
+        res[f"{name}_loss"] = np.float64(loss)
+        res[f"{name}_grad_norm"] = np.float64(o.grad.norm())
+        if name != "256":
+            res[f"{name}_grad"] = o.grad.numpy()
+        else:
+            res[f"{name}_grad_sub"] = o.grad[:, :, ::8, ::8].numpy()
+    res["freq_w"] = tr.freq_w[0, :, 0, 0].numpy()
+    res["dct_mat"] = tr.dct_mat.numpy()
+    np.savez_compressed(os.path.join(OUT, "dct_loss.npz"), **res)
+
+
+def golden_cfg1():
+    """BASELINE.json configs[0]: DeCo-L/16 256px, batch 4, 10 Euler steps, CFG 3.2 on (0.1,1], fp32 CPU."""
+    cfg = O.CFG_L
+    m, P = build_ref(cfg)
+    B = 4
+    noise = seeded_noise(B, (3, 256, 256), 0)
+    cond = torch.tensor([0, 250, 500, 750])
+    unc = torch.full((B,), 1000)
+    sch = RefSched()
+    s = RefEuler(scheduler=sch, w_scheduler=sch, guidance_fn=ref_guidance, num_steps=10, guidance=3.2,
+                 guidance_interval_min=0.1, guidance_interval_max=1.0, step_fn=ode_step_fn)
+    t0 = time.time()
+    x, xs, vs = s(m, noise, cond, unc, return_x_trajs=True, return_v_trajs=True)
+    el = time.time() - t0
+    print(f"[cfg1] reference L/16 10-step CFG sampling on {torch.get_num_threads()} threads: {el:.1f}s "
+          f"-> {B / el:.4f} img/s")
+    o = O.euler_sample(lambda a, b, c: O.denoiser_forward(P, cfg, a, b, c), noise, cond, unc, 10, 3.2, 0.1, 1.0)
+    e = rel_l2(o, x)
+    print(f"[cfg1] oracle vs reference 10-step trajectory rel-L2 = {e:.3e}")
+    assert e < 1e-5
+    # first forward of the trajectory: the CFG-batched network output at t=0
+    np.savez_compressed(os.path.join(OUT, "cfg1_L16_euler10.npz"),
+                        final_sub=x[:, :, ::4, ::4].numpy(), final_mean=np.float64(x.mean()),
+                        final_std=np.float64(x.std()),
+                        v0_sub=vs[0][:, :, ::4, ::4].numpy(),
+                        x_step_norms=np.array([float(v.norm()) for v in xs]),
+                        cond=cond.numpy(), ref_seconds=np.float64(el), ref_threads=np.int64(torch.get_num_threads()))
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["dct", "samplers", "tiny", "cfg1"]
+    if "dct" in which:
+        golden_dct()
+    if "samplers" in which:
+        golden_samplers()
+    if "tiny" in which:
+        # XL-like head_dim 72 (non power of two), L-like head_dim 64 with a ragged FFN width
+        golden_forward("fwd_d72", O.DenoiserCfg(num_groups=8, hidden_size=576, num_blocks=5, num_cond_blocks=3,
+                                                num_classes=10), B=4, res=64, seed=11)
+        golden_forward("fwd_d64", O.DenoiserCfg(num_groups=4, hidden_size=256, num_blocks=4, num_cond_blocks=2,
+                                                num_classes=10), B=2, res=96, seed=21)
+    if "cfg1" in which:
+        golden_cfg1()
