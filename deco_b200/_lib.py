@@ -1,0 +1,83 @@
+"""ctypes binding of the C-ABI library (include/deco_b200.h).
+
+There is deliberately NO fallback: if the library is missing or a call fails, the caller gets an exception.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_C", "libdeco_b200.so")
+
+_vp, _ll, _i, _f = C.c_void_p, C.c_longlong, C.c_int, C.c_float
+
+# name -> (restype, argtypes); mirrors include/deco_b200.h one to one (checked by tests/test_abi.py)
+SIGNATURES = {
+    "deco_last_error": (C.c_char_p, []),
+    "deco_abi_version": (_i, []),
+    "deco_gemm_bf16": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _vp, _vp, _ll, _vp, _ll, _i, _i, _vp]),
+    "deco_patchify": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "deco_timestep_freq": (_i, [_vp, _vp, _i, _i, _f, _vp]),
+    "deco_cond_combine": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "deco_rmsnorm_modulate": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _vp, _ll, _i, _f, _vp]),
+    "deco_qknorm_rope": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i, _i, _f, _vp]),
+    "deco_attention_fwd": (_i, [_vp, _ll, _vp, _vp, _ll, _i, _vp, _vp, _ll, _i, _vp, _ll, _i, _i, _i, _i, _f, _vp]),
+    "deco_silu_add_rows": (_i, [_vp, _vp, _vp, _ll, _i, _i, _vp]),
+    "deco_decoder_blob_bytes": (_i, [_i]),
+    "deco_pixel_decoder": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "deco_cfg_step": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _f, _f, _f, _f, _f, _f, _vp, _vp, _vp, _vp, _ll, _vp]),
+    "deco_fp2uint8": (_i, [_vp, _vp, _ll, _vp]),
+    "deco_dct_fm_loss": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),
+}
+
+_lib = None
+_lock = threading.Lock()
+launch_count = 0  # number of kernel-launching C-ABI calls made through `call` (bench.py reports it)
+
+
+class DecoLibraryError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load libdeco_b200.so (building nothing: use `python -m deco_b200.build` / __graft_entry__.build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise DecoLibraryError(
+                f"{LIB_PATH} not found: the CUDA extension is not built (run `python -m deco_b200.build`). "
+                "deco_b200 has no CPU or PyTorch fallback.")
+        lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the symbol is missing: fail loudly
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def call(name: str, *args) -> None:
+    """Invoke an int-returning entry point and raise on a non-zero status."""
+    global launch_count
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        msg = lib.deco_last_error()
+        raise DecoLibraryError(f"{name} failed with status {rc}: {msg.decode() if msg else ''}")
+    launch_count += 1
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_of(device=None):
+    import torch
+    return torch.cuda.current_stream(device).cuda_stream

@@ -1,0 +1,19 @@
+// Error reporting and version for the C-ABI library (include/deco_b200.h).
+#include "common.cuh"
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+static thread_local char g_err[512] = "";
+
+void deco_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* deco_last_error(void) { return g_err; }
+extern "C" int deco_abi_version(void) { return 1; }
+
+// Number of kernels the library has launched since load is not tracked here; bench.py counts launches on the host side.

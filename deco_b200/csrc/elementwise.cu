@@ -1,0 +1,286 @@
+// Memory-bound glue kernels of the denoiser forward (all HBM-bound; 128-bit accesses, one pass each).
+//
+// Replaces (reference, /root/reference/src/models/transformer/dit_c2i_DeCo.py):
+//   :491 F.unfold + transpose            -> patchify_kernel        (fp32 NCHW -> bf16 [B*L, C*p*p])
+//   :43-53 timestep_embedding            -> timestep_freq_kernel   (cos || sin, max_period 10)
+//   :493-494 y_embedder + silu(t + y)    -> cond_combine_kernel
+//   :94-99 RMSNorm + :11-12 modulate     -> rmsnorm_modulate_kernel
+//   :178-180 q_norm / k_norm + RoPE      -> qknorm_rope_kernel     (in place on the QKV GEMM output)
+//   :499 silu(t + s)                     -> silu_add_rows_kernel
+#include "common.cuh"
+
+namespace deco {
+
+// ---------------------------------------------------------------- patchify
+// out[(b*L + py*Wp + px)][c*p*p + ky*p + kx] = x[b][c][py*p+ky][px*p+kx]; p % 8 == 0
+__global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                       int C, int H, int W, int p, long long total8)
+{
+    const int Wp = W / p, Hp = H / p;
+    const int p8 = p / 8;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += stride) {
+        long long r = i;
+        const int kx8 = (int)(r % p8); r /= p8;
+        const int ky = (int)(r % p); r /= p;
+        const int c = (int)(r % C); r /= C;
+        const int px = (int)(r % Wp); r /= Wp;
+        const int py = (int)(r % Hp); r /= Hp;
+        const long long b = r;
+        const float* src = x + (((b * C + c) * H + (py * p + ky)) * (long long)W + px * p + kx8 * 8);
+        const float4 a = __ldg(reinterpret_cast<const float4*>(src));
+        const float4 d = __ldg(reinterpret_cast<const float4*>(src) + 1);
+        uint4 o;
+        o.x = pack_bf2(a.x, a.y); o.y = pack_bf2(a.z, a.w); o.z = pack_bf2(d.x, d.y); o.w = pack_bf2(d.z, d.w);
+        reinterpret_cast<uint4*>(out)[i] = o;   // i enumerates output 16-byte chunks in order
+    }
+}
+
+// ---------------------------------------------------------------- timestep sinusoid
+__global__ void timestep_freq_kernel(const float* __restrict__ t, __nv_bfloat16* __restrict__ out, int B, int dim,
+                                     float max_period)
+{
+    const int half = dim / 2;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * half) return;
+    const int b = i / half, k = i % half;
+    // fp32 evaluation order of the reference: exp(-log(max_period) * k / half), then t * freq
+    const float freq = expf(-logf(max_period) * (float)k / (float)half);
+    const float arg = t[b] * freq;
+    out[(size_t)b * dim + k] = f2bf(cosf(arg));
+    out[(size_t)b * dim + half + k] = f2bf(sinf(arg));
+}
+
+// ---------------------------------------------------------------- c = silu(t_emb + y_emb[label])
+__global__ void cond_combine_kernel(const __nv_bfloat16* __restrict__ temb, const float* __restrict__ table,
+                                    const long long* __restrict__ labels, __nv_bfloat16* __restrict__ c,
+                                    int B, int Hd, int num_rows)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * Hd) return;
+    const int b = i / Hd, h = i % Hd;
+    long long lab = labels[b];
+    if (lab < 0 || lab >= num_rows) lab = num_rows - 1;   // clamp: the reference would raise on the host
+    const float v = bf2f(temb[i]) + __ldg(table + lab * Hd + h);
+    c[i] = f2bf(silu_f(v));
+}
+
+// ---------------------------------------------------------------- h = rms(x) * w * (1 + scale) + shift
+// One warp per row; the row lives in registers between the two passes.  Hd % 8 == 0, Hd <= 2048.
+template <int kMaxChunks>
+__global__ void __launch_bounds__(256) rmsnorm_modulate_kernel(
+    const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
+    const __nv_bfloat16* __restrict__ shift, const __nv_bfloat16* __restrict__ scale, long long mod_row_stride,
+    int rows_per_mod, __nv_bfloat16* __restrict__ out, long long M, int Hd, float eps)
+{
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const int nch = Hd >> 3;
+    const uint4* xr = reinterpret_cast<const uint4*>(x + row * Hd);
+    float v[kMaxChunks][8];
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < kMaxChunks; ++j) {
+        const int ch = lane + j * 32;
+        if (ch < nch) {
+            const uint4 q = ld_stream16(xr + ch);
+            const float2 a = unpack_bf2(q.x), b = unpack_bf2(q.y), c = unpack_bf2(q.z), d = unpack_bf2(q.w);
+            v[j][0] = a.x; v[j][1] = a.y; v[j][2] = b.x; v[j][3] = b.y;
+            v[j][4] = c.x; v[j][5] = c.y; v[j][6] = d.x; v[j][7] = d.y;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) ss = fmaf(v[j][e], v[j][e], ss);
+        }
+    }
+    ss = warp_sum(ss);
+    const float rs = rsqrtf(ss / (float)Hd + eps);
+    const long long mrow = row / rows_per_mod;
+    const uint4* shr = reinterpret_cast<const uint4*>(shift + mrow * mod_row_stride);
+    const uint4* scr = reinterpret_cast<const uint4*>(scale + mrow * mod_row_stride);
+    uint4* orow = reinterpret_cast<uint4*>(out + row * Hd);
+#pragma unroll
+    for (int j = 0; j < kMaxChunks; ++j) {
+        const int ch = lane + j * 32;
+        if (ch < nch) {
+            const float4 w0 = __ldg(reinterpret_cast<const float4*>(w) + ch * 2);
+            const float4 w1 = __ldg(reinterpret_cast<const float4*>(w) + ch * 2 + 1);
+            const uint4 sh = __ldg(shr + ch), sc = __ldg(scr + ch);
+            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+            const uint32_t shw[4] = {sh.x, sh.y, sh.z, sh.w}, scw[4] = {sc.x, sc.y, sc.z, sc.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 s2 = unpack_bf2(shw[e]), c2 = unpack_bf2(scw[e]);
+                // reference rounding points: normalised value cast back to bf16 (:99), (1 + scale) is a bf16 op
+                const float n0 = wv[2 * e] * round_bf(v[j][2 * e] * rs);
+                const float n1 = wv[2 * e + 1] * round_bf(v[j][2 * e + 1] * rs);
+                o[e] = pack_bf2(fmaf(n0, round_bf(1.0f + c2.x), s2.x), fmaf(n1, round_bf(1.0f + c2.y), s2.y));
+            }
+            orow[ch] = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- per-head RMSNorm + 2-D RoPE, in place
+// qkv: [M, 3*heads*D] (q | k | v).  One thread per (token, q|k, head) vector of D elements.
+// rope: [L, D/2] float2 (cos, sin); token position = row % L.
+template <int D>
+__global__ void __launch_bounds__(128) qknorm_rope_kernel(__nv_bfloat16* __restrict__ qkv, const float* __restrict__ qw,
+                                                          const float* __restrict__ kw, const float2* __restrict__ rope,
+                                                          long long M, int heads, int L, float eps)
+{
+    const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int per_tok = 2 * heads;
+    if (item >= M * per_tok) return;
+    const long long tok = item / per_tok;
+    const int r = (int)(item % per_tok);
+    const int is_k = r / heads, head = r % heads;
+    __nv_bfloat16* p = qkv + tok * (3LL * heads * D) + (long long)is_k * heads * D + (long long)head * D;
+    const float* wv = is_k ? kw : qw;
+    const float2* rp = rope + (long long)(tok % L) * (D / 2);
+    float v[D];
+    float ss = 0.f;
+#pragma unroll
+    for (int c = 0; c < D / 8; ++c) {
+        const uint4 q = *reinterpret_cast<const uint4*>(p + c * 8);
+        const float2 a = unpack_bf2(q.x), b = unpack_bf2(q.y), cc = unpack_bf2(q.z), d = unpack_bf2(q.w);
+        v[c * 8 + 0] = a.x; v[c * 8 + 1] = a.y; v[c * 8 + 2] = b.x; v[c * 8 + 3] = b.y;
+        v[c * 8 + 4] = cc.x; v[c * 8 + 5] = cc.y; v[c * 8 + 6] = d.x; v[c * 8 + 7] = d.y;
+    }
+#pragma unroll
+    for (int e = 0; e < D; ++e) ss = fmaf(v[e], v[e], ss);
+    const float rs = rsqrtf(ss / (float)D + eps);
+#pragma unroll
+    for (int c = 0; c < D / 8; ++c) {
+        uint32_t o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int j = c * 4 + e;   // pair index
+            const float a = __ldg(wv + 2 * j) * round_bf(v[2 * j] * rs);
+            const float b = __ldg(wv + 2 * j + 1) * round_bf(v[2 * j + 1] * rs);
+            const float2 cs = __ldg(rp + j);
+            o[e] = pack_bf2(a * cs.x - b * cs.y, a * cs.y + b * cs.x);
+        }
+        *reinterpret_cast<uint4*>(p + c * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// ---------------------------------------------------------------- out[m, :] = silu(x[m, :] + row[m / rows_per][:])
+__global__ void __launch_bounds__(256) silu_add_rows_kernel(const __nv_bfloat16* __restrict__ x,
+                                                            const __nv_bfloat16* __restrict__ rowv,
+                                                            __nv_bfloat16* __restrict__ out, long long M, int Hd,
+                                                            int rows_per)
+{
+    const int nch = Hd >> 3;
+    const long long total = M * nch;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const long long m = i / nch;
+        const int ch = (int)(i % nch);
+        const uint4 a = reinterpret_cast<const uint4*>(x)[i];   // plain load: out may alias x
+        const uint4 b = __ldg(reinterpret_cast<const uint4*>(rowv + (m / rows_per) * Hd) + ch);
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 p = unpack_bf2(aw[e]), q = unpack_bf2(bw[e]);
+            o[e] = pack_bf2(silu_f(round_bf(p.x + q.x)), silu_f(round_bf(p.y + q.y)));
+        }
+        reinterpret_cast<uint4*>(out)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+static inline unsigned grid_for(long long work, int threads, int per_sm = 16) {
+    long long b = (work + threads - 1) / threads;
+    const long long cap = (long long)kNumSMs * per_sm;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (unsigned)b;
+}
+
+}  // namespace deco
+
+extern "C" int deco_patchify(const float* x, void* out_bf16, int B, int C, int H, int W, int p, void* stream) {
+    using namespace deco;
+    DECO_CHECK_ARG(x && out_bf16, "patchify: null pointer");
+    DECO_CHECK_ARG(B > 0 && C > 0 && p > 0 && p % 8 == 0 && H % p == 0 && W % p == 0,
+                   "patchify: unsupported shape B=%d C=%d H=%d W=%d p=%d (need p%%8==0, H,W%%p==0)", B, C, H, W, p);
+    const long long total8 = (long long)B * C * H * W / 8;
+    patchify_kernel<<<grid_for(total8, 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)out_bf16, C, H, W, p, total8);
+    DECO_CHECK_LAUNCH("patchify_kernel");
+    return DECO_OK;
+}
+
+extern "C" int deco_timestep_freq(const float* t, void* out_bf16, int B, int dim, float max_period, void* stream) {
+    using namespace deco;
+    DECO_CHECK_ARG(t && out_bf16 && B > 0 && dim > 0 && dim % 2 == 0, "timestep_freq: bad arguments");
+    const int n = B * (dim / 2);
+    timestep_freq_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(t, (__nv_bfloat16*)out_bf16, B, dim, max_period);
+    DECO_CHECK_LAUNCH("timestep_freq_kernel");
+    return DECO_OK;
+}
+
+extern "C" int deco_cond_combine(const void* temb_bf16, const float* table, const long long* labels, void* c_bf16,
+                                 int B, int hidden, int num_rows, void* stream) {
+    using namespace deco;
+    DECO_CHECK_ARG(temb_bf16 && table && labels && c_bf16 && B > 0 && hidden > 0 && num_rows > 0,
+                   "cond_combine: bad arguments");
+    const int n = B * hidden;
+    cond_combine_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)temb_bf16, table, labels, (__nv_bfloat16*)c_bf16, B, hidden, num_rows);
+    DECO_CHECK_LAUNCH("cond_combine_kernel");
+    return DECO_OK;
+}
+
+extern "C" int deco_rmsnorm_modulate(const void* x_bf16, const float* weight, const void* shift_bf16,
+                                     const void* scale_bf16, long long mod_row_stride, int rows_per_mod,
+                                     void* out_bf16, long long M, int hidden, float eps, void* stream) {
+    using namespace deco;
+    DECO_CHECK_ARG(x_bf16 && weight && shift_bf16 && scale_bf16 && out_bf16, "rmsnorm_modulate: null pointer");
+    DECO_CHECK_ARG(M > 0 && hidden % 8 == 0 && hidden <= 2048 && rows_per_mod > 0 && mod_row_stride % 8 == 0,
+                   "rmsnorm_modulate: unsupported M=%lld hidden=%d", M, hidden);
+    const int warps = 8;
+    const unsigned grid = (unsigned)((M + warps - 1) / warps);
+    if (hidden <= 1280)
+        rmsnorm_modulate_kernel<5><<<grid, warps * 32, 0, (cudaStream_t)stream>>>(
+            (const __nv_bfloat16*)x_bf16, weight, (const __nv_bfloat16*)shift_bf16, (const __nv_bfloat16*)scale_bf16,
+            mod_row_stride, rows_per_mod, (__nv_bfloat16*)out_bf16, M, hidden, eps);
+    else
+        rmsnorm_modulate_kernel<8><<<grid, warps * 32, 0, (cudaStream_t)stream>>>(
+            (const __nv_bfloat16*)x_bf16, weight, (const __nv_bfloat16*)shift_bf16, (const __nv_bfloat16*)scale_bf16,
+            mod_row_stride, rows_per_mod, (__nv_bfloat16*)out_bf16, M, hidden, eps);
+    DECO_CHECK_LAUNCH("rmsnorm_modulate_kernel");
+    return DECO_OK;
+}
+
+extern "C" int deco_qknorm_rope(void* qkv_bf16, const float* q_weight, const float* k_weight, const float* rope_cos_sin,
+                                long long M, int heads, int head_dim, int L, float eps, void* stream) {
+    using namespace deco;
+    DECO_CHECK_ARG(qkv_bf16 && q_weight && k_weight && rope_cos_sin, "qknorm_rope: null pointer");
+    DECO_CHECK_ARG(M > 0 && heads > 0 && L > 0, "qknorm_rope: bad shape");
+    const long long items = M * 2 * heads;
+    const unsigned grid = (unsigned)((items + 127) / 128);
+    if (head_dim == 72)
+        qknorm_rope_kernel<72><<<grid, 128, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)qkv_bf16, q_weight, k_weight,
+                                                                      (const float2*)rope_cos_sin, M, heads, L, eps);
+    else if (head_dim == 64)
+        qknorm_rope_kernel<64><<<grid, 128, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)qkv_bf16, q_weight, k_weight,
+                                                                      (const float2*)rope_cos_sin, M, heads, L, eps);
+    else {
+        deco_set_error("qknorm_rope: head_dim %d not built (64, 72)", head_dim);
+        return DECO_ERR_UNSUPPORTED;
+    }
+    DECO_CHECK_LAUNCH("qknorm_rope_kernel");
+    return DECO_OK;
+}
+
+extern "C" int deco_silu_add_rows(const void* x_bf16, const void* row_bf16, void* out_bf16, long long M, int hidden,
+                                  int rows_per, void* stream) {
+    using namespace deco;
+    DECO_CHECK_ARG(x_bf16 && row_bf16 && out_bf16 && M > 0 && hidden % 8 == 0 && rows_per > 0, "silu_add_rows: bad arguments");
+    const long long total = M * (hidden / 8);
+    silu_add_rows_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x_bf16, (const __nv_bfloat16*)row_bf16, (__nv_bfloat16*)out_bf16, M, hidden, rows_per);
+    DECO_CHECK_LAUNCH("silu_add_rows_kernel");
+    return DECO_OK;
+}

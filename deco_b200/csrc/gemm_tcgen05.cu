@@ -1,0 +1,430 @@
+// Persistent, warp-specialised bf16 GEMM for sm_100a:  D[M,N] = epilogue(A[M,K] . W[N,K]^T)
+//   * operands staged by TMA (cp.async.bulk.tensor, 128-byte swizzle) into a multi-stage shared-memory ring,
+//   * tcgen05.mma (cta_group::1, M=128, N=BN, K=16, kind::f16, bf16 in / fp32 accumulate) issued by one thread,
+//   * accumulators in TMEM, double buffered (2 x BN columns) so the epilogue of tile i overlaps the MMAs of tile i+1,
+//   * epilogue warps read TMEM with tcgen05.ld and fuse bias / SiLU / AdaLN gate + residual / SwiGLU.
+//
+// Replaces every nn.Linear on the hot path of /root/reference/src/models/transformer/dit_c2i_DeCo.py:
+//   s_embedder.proj (:496), t_embedder.mlp (:55-57), adaLN_modulation (:207, all blocks batched into one GEMM),
+//   attn.qkv (:176), attn.proj + gated residual (:188,:208), mlp.w1/w3 + SiLU-gate (:113), mlp.w2 + gated residual
+//   (:113,:209), dec_net.cond_embed (:404).
+//
+// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+// warps 4-7 = epilogue (warp w owns TMEM lanes 32*(w%4)..+31 = tile rows).
+#include "common.cuh"
+#include <cuda.h>
+#include <mutex>
+#include <cstdio>
+
+namespace deco {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;            // 64 bf16 = 128 bytes = one swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kGemmThreads = 256;
+constexpr int kEpiWarp0 = 4;
+constexpr int kAccStages = 2;
+
+enum GemmEpilogue : int {
+    EPI_BIAS = 0,           // out = acc + bias
+    EPI_BIAS_SILU = 1,      // out = silu(acc + bias)
+    EPI_GATE_RESIDUAL = 2,  // out = resid + gate[row / rows_per_gate] * (acc + bias)
+    EPI_SWIGLU = 3,         // columns interleaved in 16s: out[:, n/2 + i] = silu(acc[n + i]) * acc[n + 16 + i]
+};
+
+struct GemmParams {
+    void* out;                       // bf16 [M, ldo]
+    long long ldo;
+    const float* bias;               // [N] fp32 or null
+    const __nv_bfloat16* resid;      // [M, ldr] (EPI_GATE_RESIDUAL)
+    long long ldr;
+    const __nv_bfloat16* gate;       // [M / rows_per_gate, gate_stride]
+    long long gate_stride;
+    int rows_per_gate;
+    int M, N, K;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a trapped kernel (an error the host sees), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {   // ~2 s at 2 GHz
+            printf("deco gemm: mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n",
+                   (int)blockIdx.x, (int)threadIdx.x, bar, parity);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        :: "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" :: "l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_dst), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (unused for swizzled K-major, 1) |
+//   [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024 B -> 64) | [46,48) version = 1 | [61,64) layout = 2 (SW128)
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)64 << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 = 1 @4, a/b_format BF16 = 1 @7/@10,
+// a/b major K = 0 @15/@16, N >> 3 @17, M >> 4 @24
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <int BN> struct GemmCfg {
+    static constexpr int kStageBytesA = kBM * kBK * 2;
+    static constexpr int kStageBytesB = BN * kBK * 2;
+    static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
+    static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 192 ? 5 : 6);
+    static constexpr int kTmemCols = (kAccStages * BN > 256) ? 512 : 256;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// ------------------------------------------------------------------ epilogue math on one 32-column chunk
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& P, const uint32_t (&acc)[32], long long row, int n0) {
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
+    if (P.bias) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+            if (n0 + i < P.N) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(P.bias + n0 + i));
+                v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+            }
+        }
+    }
+    if (EPI == EPI_SWIGLU) {
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(P.out) + row * P.ldo + (n0 >> 1);
+        if (n0 < P.N) {
+            uint32_t w[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                w[i] = pack_bf2(silu_f(v[2 * i]) * v[16 + 2 * i], silu_f(v[2 * i + 1]) * v[16 + 2 * i + 1]);
+            *reinterpret_cast<uint4*>(o) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4*>(o + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+        }
+        return;
+    }
+    if (EPI == EPI_BIAS_SILU) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = silu_f(v[i]);
+    }
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(P.out) + row * P.ldo + n0;
+    if (EPI == EPI_GATE_RESIDUAL) {
+        const __nv_bfloat16* r = P.resid + row * P.ldr + n0;
+        const __nv_bfloat16* gt = P.gate + (row / P.rows_per_gate) * P.gate_stride + n0;
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+            if (n0 + i < P.N) {
+                const uint4 rv = *reinterpret_cast<const uint4*>(r + i);
+                const uint4 gv = __ldg(reinterpret_cast<const uint4*>(gt + i));
+                const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w}, gw[4] = {gv.x, gv.y, gv.z, gv.w};
+                uint32_t w[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 rr = unpack_bf2(rw[e]), gg = unpack_bf2(gw[e]);
+                    w[e] = pack_bf2(fmaf(gg.x, v[i + 2 * e], rr.x), fmaf(gg.y, v[i + 2 * e + 1], rr.y));
+                }
+                *reinterpret_cast<uint4*>(o + i) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        }
+        return;
+    }
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+        if (n0 + i < P.N) {
+            *reinterpret_cast<uint4*>(o + i) = make_uint4(pack_bf2(v[i], v[i + 1]), pack_bf2(v[i + 2], v[i + 3]),
+                                                          pack_bf2(v[i + 4], v[i + 5]), pack_bf2(v[i + 6], v[i + 7]));
+        }
+    }
+}
+
+// ------------------------------------------------------------------ kernel
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         const GemmParams P)
+{
+    using Cfg = GemmCfg<BN>;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // 1024-byte alignment is required by the 128-byte swizzle atom (8 rows x 128 B)
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + kAccStages + s); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::kStages + 2 * kAccStages);
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_m = (P.M + kBM - 1) / kBM, num_n = (P.N + BN - 1) / BN;
+    const int num_tiles = num_m * num_n;
+    const int num_k = (P.K + kBK - 1) / kBK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < kAccStages; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_blk = tile / num_n, n_blk = tile % num_n;
+                for (int kb = 0; kb < num_k; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+                    const uint32_t sb = sa + Cfg::kStageBytesA;
+                    mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+                    tma_load_2d(sa, &tmap_a, full_bar(stage), kb * kBK, m_blk * kBM);
+                    tma_load_2d(sb, &tmap_b, full_bar(stage), kb * kBK, n_blk * BN);
+                    if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(kBM, BN);
+            int stage = 0; uint32_t phase = 0;
+            int as = 0; uint32_t aphase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(tempty_bar(as), aphase ^ 1);   // epilogue has drained this accumulator stage
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+                for (int kb = 0; kb < num_k; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+                    const uint64_t da = make_sw128_desc(sa), db = make_sw128_desc(sa + Cfg::kStageBytesA);
+#pragma unroll
+                    for (int k = 0; k < kBK / kUmmaK; ++k) {
+                        // advance 16 elements = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
+                        umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar(stage));       // frees the smem stage once these MMAs retire
+                    if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(tfull_bar(as));              // accumulator complete -> epilogue
+                if (++as == kAccStages) { as = 0; aphase ^= 1; }
+            }
+        }
+    } else if (warp >= kEpiWarp0) {
+        // ===================== epilogue =====================
+        const int q = warp & 3;                          // TMEM lane quarter this warp may access
+        int as = 0; uint32_t aphase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int m_blk = tile / num_n, n_blk = tile % num_n;
+            mbar_wait(tfull_bar(as), aphase);
+            tc_fence_after();
+            const long long row = (long long)m_blk * kBM + q * 32 + lane;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t acc[32];
+                tmem_ld32(taddr + (uint32_t)(c * 32), acc);
+                tmem_ld_wait();
+                const int n0 = n_blk * BN + c * 32;
+                if (row < P.M && n0 < P.N) epilogue_chunk<EPI>(P, acc, row, n0);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(as));
+            if (++as == kAccStages) { as = 0; aphase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    });
+    return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] tensor with a {64 x box_rows} box and 128-byte swizzle
+static int make_tmap(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) { deco_set_error("cuTensorMapEncodeTiled entry point not available"); return DECO_ERR_DRIVER; }
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { deco_set_error("cuTensorMapEncodeTiled failed: %d", (int)r); return DECO_ERR_DRIVER; }
+    return DECO_OK;
+}
+
+template <int BN, int EPI>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& P, int max_ctas, cudaStream_t st) {
+    using Cfg = GemmCfg<BN>;
+    static bool attr_done = false;   // per (BN, EPI) instantiation
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, EPI>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+        if (e != cudaSuccess) { deco_set_error("gemm smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+        attr_done = true;
+    }
+    const int tiles = ((P.M + kBM - 1) / kBM) * ((P.N + BN - 1) / BN);
+    int grid = tiles < max_ctas ? tiles : max_ctas;
+    gemm_bf16_tcgen05_kernel<BN, EPI><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ta, tb, P);
+    DECO_CHECK_LAUNCH("gemm_bf16_tcgen05_kernel");
+    return DECO_OK;
+}
+
+template <int BN>
+static int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& P, int max_ctas, cudaStream_t st) {
+    switch (epi) {
+        case EPI_BIAS: return launch_gemm<BN, EPI_BIAS>(ta, tb, P, max_ctas, st);
+        case EPI_BIAS_SILU: return launch_gemm<BN, EPI_BIAS_SILU>(ta, tb, P, max_ctas, st);
+        case EPI_GATE_RESIDUAL: return launch_gemm<BN, EPI_GATE_RESIDUAL>(ta, tb, P, max_ctas, st);
+        case EPI_SWIGLU: return launch_gemm<BN, EPI_SWIGLU>(ta, tb, P, max_ctas, st);
+    }
+    deco_set_error("gemm: unknown epilogue %d", epi);
+    return DECO_ERR_ARG;
+}
+
+static int g_num_sms_cached = 0;
+static int num_sms() {
+    if (!g_num_sms_cached) {
+        int dev = 0, n = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        g_num_sms_cached = n > 0 ? n : kNumSMs;
+    }
+    return g_num_sms_cached;
+}
+
+}  // namespace deco
+
+extern "C" int deco_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, void* out, long long ldo,
+                              int M, int N, int K, int epilogue, const float* bias,
+                              const void* resid, long long ldr, const void* gate, long long gate_stride,
+                              int rows_per_gate, int tile_n, void* stream)
+{
+    using namespace deco;
+    DECO_CHECK_ARG(A && W && out, "gemm: null pointer");
+    DECO_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
+    DECO_CHECK_ARG(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldo % 8 == 0 && N % 8 == 0,
+                   "gemm: K, N and leading dimensions must be multiples of 8 (K=%d N=%d lda=%lld ldw=%lld ldo=%lld)",
+                   K, N, lda, ldw, ldo);
+    DECO_CHECK_ARG((((uintptr_t)A | (uintptr_t)W | (uintptr_t)out) & 15) == 0, "gemm: pointers must be 16-byte aligned");
+    if (epilogue == EPI_GATE_RESIDUAL)
+        DECO_CHECK_ARG(resid && gate && rows_per_gate > 0 && ldr % 8 == 0 && gate_stride % 8 == 0 &&
+                       (((uintptr_t)resid | (uintptr_t)gate) & 15) == 0, "gemm: gate/residual arguments invalid");
+    if (epilogue == EPI_SWIGLU) DECO_CHECK_ARG(N % 32 == 0, "gemm: swiglu epilogue needs N %% 32 == 0");
+    int bn = tile_n;
+    if (bn == 0) bn = (N % 256 == 0) ? 256 : ((N % 192 == 0) ? 192 : (N % 128 == 0 ? 128 : (N >= 1024 ? 256 : 128)));
+    DECO_CHECK_ARG(bn == 128 || bn == 192 || bn == 256, "gemm: tile_n must be 128, 192 or 256");
+    CUtensorMap ta, tb;
+    int rc = make_tmap(&ta, A, M, K, lda, kBM);
+    if (rc) return rc;
+    rc = make_tmap(&tb, W, N, K, ldw, bn);
+    if (rc) return rc;
+    GemmParams P;
+    P.out = out; P.ldo = ldo; P.bias = bias; P.resid = (const __nv_bfloat16*)resid; P.ldr = ldr;
+    P.gate = (const __nv_bfloat16*)gate; P.gate_stride = gate_stride; P.rows_per_gate = rows_per_gate > 0 ? rows_per_gate : 1;
+    P.M = M; P.N = N; P.K = K;
+    const int ctas = num_sms();
+    cudaStream_t st = (cudaStream_t)stream;
+    if (bn == 256) return dispatch_epi<256>(epilogue, ta, tb, P, ctas, st);
+    if (bn == 192) return dispatch_epi<192>(epilogue, ta, tb, P, ctas, st);
+    return dispatch_epi<128>(epilogue, ta, tb, P, ctas, st);
+}

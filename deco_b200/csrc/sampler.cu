@@ -1,0 +1,128 @@
+// CFG-batched flow sampler update: guidance combine + Euler / Heun / Adams-multistep state update, optional
+// prediction stash and optional fp2uint8 of the new state, one pass.
+//
+// Replaces (reference, /root/reference):
+//   src/diffusion/base/guidance.py:3-6          simple_guidance_fn  (rows [uncond || cond])
+//   src/diffusion/flow_matching/sampling.py:14-15, :89-104  ode_step_fn + Euler loop body
+//   src/diffusion/flow_matching/sampling.py:283-291        Heun corrector average
+//   src/diffusion/flow_matching/adam_sampling.py:109-117   multistep combination
+//   src/models/autoencoder/base.py:32-34                    fp2uint8
+//
+//   pred  = u + g * (c - u)
+//   v     = c0 * pred + c1 * p1 + c2 * p2 + c3 * p3          (p_j = earlier predictions, fp32)
+//   x_out = x + dt * v
+// Euler: c0 = 1.  Heun corrector: c0 = c1 = 1/2 with p1 = predictor velocity.  Adams order k: c_j from the host.
+// Bound: HBM.  Euler algorithmic bytes / element: 4 (x) + 2*sizeof(net out) + 4 (x_out) = 12 B with bf16 net output.
+#include "common.cuh"
+
+namespace deco {
+
+struct StepArgs {
+    const float* x;
+    const void* net_out;     // [2B, ...] rows [uncond || cond]
+    const float* p[3];       // optional earlier predictions
+    float* x_out;
+    float* pred_out;         // optional: store pred (fp32)
+    float* v_out;            // optional: store combined v (fp32)
+    uint8_t* u8_out;         // optional: fp2uint8(x_out)
+    float g, dt, c0, c[3];
+    long long n;             // elements per CFG half (B*C*H*W)
+};
+
+template <typename T> struct Vec4;
+template <> struct Vec4<float> {
+    static __device__ __forceinline__ float4 load(const void* p, long long i) {
+        return __ldg(reinterpret_cast<const float4*>(p) + i);
+    }
+};
+template <> struct Vec4<__nv_bfloat16> {
+    static __device__ __forceinline__ float4 load(const void* p, long long i) {
+        uint2 r = __ldg(reinterpret_cast<const uint2*>(p) + i);
+        float2 a = unpack_bf2(r.x), b = unpack_bf2(r.y);
+        return make_float4(a.x, a.y, b.x, b.y);
+    }
+};
+
+__device__ __forceinline__ uint8_t to_u8(float x) {
+    // clamp((x + 1) * 127.5 + 0.5, 0, 255).to(uint8): truncation toward zero
+    float v = fminf(fmaxf((x + 1.0f) * 127.5f + 0.5f, 0.0f), 255.0f);
+    return (uint8_t)v;
+}
+
+template <typename TNet>
+__global__ void __launch_bounds__(256) cfg_step_kernel(StepArgs a) {
+    const long long n4 = a.n >> 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(a.x) + i);
+        const float4 u = Vec4<TNet>::load(a.net_out, i);
+        const float4 c = Vec4<TNet>::load(a.net_out, i + n4);
+        float4 pr;
+        pr.x = u.x + a.g * (c.x - u.x);
+        pr.y = u.y + a.g * (c.y - u.y);
+        pr.z = u.z + a.g * (c.z - u.z);
+        pr.w = u.w + a.g * (c.w - u.w);
+        float4 v = make_float4(a.c0 * pr.x, a.c0 * pr.y, a.c0 * pr.z, a.c0 * pr.w);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            if (a.p[j]) {
+                const float4 q = __ldg(reinterpret_cast<const float4*>(a.p[j]) + i);
+                v.x = fmaf(a.c[j], q.x, v.x); v.y = fmaf(a.c[j], q.y, v.y);
+                v.z = fmaf(a.c[j], q.z, v.z); v.w = fmaf(a.c[j], q.w, v.w);
+            }
+        }
+        float4 xo = make_float4(fmaf(a.dt, v.x, x.x), fmaf(a.dt, v.y, x.y), fmaf(a.dt, v.z, x.z), fmaf(a.dt, v.w, x.w));
+        if (a.x_out) reinterpret_cast<float4*>(a.x_out)[i] = xo;
+        if (a.pred_out) reinterpret_cast<float4*>(a.pred_out)[i] = pr;
+        if (a.v_out) reinterpret_cast<float4*>(a.v_out)[i] = v;
+        if (a.u8_out) {
+            uchar4 q = make_uchar4(to_u8(xo.x), to_u8(xo.y), to_u8(xo.z), to_u8(xo.w));
+            reinterpret_cast<uchar4*>(a.u8_out)[i] = q;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) fp2uint8_kernel(const float* __restrict__ x, uint8_t* __restrict__ o, long long n4) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+        reinterpret_cast<uchar4*>(o)[i] = make_uchar4(to_u8(v.x), to_u8(v.y), to_u8(v.z), to_u8(v.w));
+    }
+}
+
+}  // namespace deco
+
+extern "C" int deco_cfg_step(const float* x, const void* net_out, int net_is_bf16,
+                             const float* p1, const float* p2, const float* p3,
+                             float g, float dt, float c0, float c1, float c2, float c3,
+                             float* x_out, float* pred_out, float* v_out, uint8_t* u8_out,
+                             long long n, void* stream)
+{
+    using namespace deco;
+    DECO_CHECK_ARG(x && net_out, "cfg_step: null input");
+    DECO_CHECK_ARG(n > 0 && (n % 4) == 0, "cfg_step: element count %lld must be a positive multiple of 4", n);
+    StepArgs a;
+    a.x = x; a.net_out = net_out; a.p[0] = p1; a.p[1] = p2; a.p[2] = p3;
+    a.x_out = x_out; a.pred_out = pred_out; a.v_out = v_out; a.u8_out = u8_out;
+    a.g = g; a.dt = dt; a.c0 = c0; a.c[0] = c1; a.c[1] = c2; a.c[2] = c3; a.n = n;
+    const long long n4 = n / 4;
+    long long blocks = (n4 + 255) / 256;
+    const long long cap = (long long)kNumSMs * 16;   // grid-stride: 16 CTAs of 256 threads per SM
+    if (blocks > cap) blocks = cap;
+    if (net_is_bf16) cfg_step_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+    else cfg_step_kernel<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+    DECO_CHECK_LAUNCH("cfg_step_kernel");
+    return DECO_OK;
+}
+
+extern "C" int deco_fp2uint8(const float* x, uint8_t* out, long long n, void* stream) {
+    using namespace deco;
+    DECO_CHECK_ARG(x && out && n > 0 && (n % 4) == 0, "fp2uint8: bad arguments");
+    const long long n4 = n / 4;
+    long long blocks = (n4 + 255) / 256;
+    const long long cap = (long long)kNumSMs * 16;
+    if (blocks > cap) blocks = cap;
+    fp2uint8_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, out, n4);
+    DECO_CHECK_LAUNCH("fp2uint8_kernel");
+    return DECO_OK;
+}

@@ -1,0 +1,376 @@
+"""B200-native class-conditional DeCo denoiser -- drop-in for the reference module.
+
+Mirrors `src/models/transformer/dit_c2i_DeCo.py:417-536` (class PixNerDiT): same constructor arguments, the same
+`state_dict` keys and shapes (checkpoint contract), the same `forward(x, t, y, s=None, mask=None)` and
+`forward_sx` signatures.  The computation itself never touches a PyTorch operator: every step is one of the
+hand-written sm_100a kernels behind include/deco_b200.h.
+
+Per forward (B' = CFG rows, L tokens, H hidden):
+   patchify -> s_embedder GEMM -> [t sinusoid -> 2 GEMMs] -> cond_combine -> ONE adaLN GEMM for all blocks
+   per block: rmsnorm_modulate -> QKV GEMM -> qknorm_rope (in place) -> attention (strided, no transposes)
+              -> proj GEMM (+gate, +residual) -> rmsnorm_modulate -> W1|W3 GEMM (SwiGLU epilogue) -> W2 GEMM (+gate, +res)
+   silu(t + s) -> cond_embed GEMM -> fused pixel decoder (NerfEmbedder + AdaLN-MLP + fold)
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+bf16 = torch.bfloat16
+
+
+# ------------------------------------------------------------------------------------------------ parameter holders
+class _Weight(nn.Module):
+    """RMSNorm parameter holder (dit_c2i_DeCo.py:85-92)."""
+
+    def __init__(self, dim: int):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(dim))
+
+
+class _Embed(nn.Module):
+    def __init__(self, in_chans: int, embed_dim: int):
+        super().__init__()
+        self.proj = nn.Linear(in_chans, embed_dim, bias=True)
+
+
+class _TimestepEmbedder(nn.Module):
+    def __init__(self, hidden_size: int, frequency_embedding_size: int = 256):
+        super().__init__()
+        self.mlp = nn.Sequential(nn.Linear(frequency_embedding_size, hidden_size, bias=True), nn.SiLU(),
+                                 nn.Linear(hidden_size, hidden_size, bias=True))
+        self.frequency_embedding_size = frequency_embedding_size
+
+
+class _LabelEmbedder(nn.Module):
+    def __init__(self, num_classes: int, hidden_size: int):
+        super().__init__()
+        self.embedding_table = nn.Embedding(num_classes, hidden_size)
+        self.num_classes = num_classes
+
+
+class _Attention(nn.Module):
+    def __init__(self, dim: int, num_heads: int):
+        super().__init__()
+        assert dim % num_heads == 0, "dim should be divisible by num_heads"
+        self.num_heads, self.head_dim = num_heads, dim // num_heads
+        self.qkv = nn.Linear(dim, dim * 3, bias=False)
+        self.q_norm = _Weight(self.head_dim)
+        self.k_norm = _Weight(self.head_dim)
+        self.proj = nn.Linear(dim, dim)
+
+
+class _FeedForward(nn.Module):
+    def __init__(self, dim: int, hidden_dim: int):
+        super().__init__()
+        hidden_dim = int(2 * hidden_dim / 3)
+        self.w1 = nn.Linear(dim, hidden_dim, bias=False)
+        self.w3 = nn.Linear(dim, hidden_dim, bias=False)
+        self.w2 = nn.Linear(hidden_dim, dim, bias=False)
+
+
+class _DiTBlock(nn.Module):
+    def __init__(self, hidden_size: int, groups: int, mlp_ratio: float = 4.0):
+        super().__init__()
+        self.norm1 = _Weight(hidden_size)
+        self.attn = _Attention(hidden_size, groups)
+        self.norm2 = _Weight(hidden_size)
+        self.mlp = _FeedForward(hidden_size, int(hidden_size * mlp_ratio))
+        self.adaLN_modulation = nn.Sequential(nn.Linear(hidden_size, 6 * hidden_size, bias=True))
+
+
+class _NerfEmbedder(nn.Module):
+    def __init__(self, in_channels: int, hidden_size_input: int, max_freqs: int):
+        super().__init__()
+        self.max_freqs = max_freqs
+        self.embedder = nn.Sequential(nn.Linear(in_channels + max_freqs ** 2, hidden_size_input, bias=True))
+
+
+class _ResBlock(nn.Module):
+    def __init__(self, channels: int):
+        super().__init__()
+        self.in_ln = nn.LayerNorm(channels, eps=1e-6)
+        self.mlp = nn.Sequential(nn.Linear(channels, channels, bias=True), nn.SiLU(),
+                                 nn.Linear(channels, channels, bias=True))
+        self.adaLN_modulation = nn.Sequential(nn.SiLU(), nn.Linear(channels, 3 * channels, bias=True))
+
+
+class _DecFinal(nn.Module):
+    def __init__(self, model_channels: int, out_channels: int):
+        super().__init__()
+        self.linear = nn.Linear(model_channels, out_channels, bias=True)
+
+
+class _PixelDecoder(nn.Module):
+    """Parameter layout of SimpleMLPAdaLN (dit_c2i_DeCo.py:334-393), including its init."""
+
+    def __init__(self, in_channels, model_channels, out_channels, z_channels, num_res_blocks, patch_size):
+        super().__init__()
+        self.cond_embed = nn.Linear(z_channels, patch_size ** 2 * model_channels)
+        self.input_proj = nn.Linear(in_channels, model_channels)
+        self.res_blocks = nn.ModuleList([_ResBlock(model_channels) for _ in range(num_res_blocks)])
+        self.final_layer = _DecFinal(model_channels, out_channels)
+        for m in self.modules():
+            if isinstance(m, nn.Linear):
+                nn.init.xavier_uniform_(m.weight)
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+        for blk in self.res_blocks:
+            nn.init.constant_(blk.adaLN_modulation[-1].weight, 0)
+            nn.init.constant_(blk.adaLN_modulation[-1].bias, 0)
+        nn.init.constant_(self.final_layer.linear.weight, 0)
+        nn.init.constant_(self.final_layer.linear.bias, 0)
+
+
+# ------------------------------------------------------------------------------------------------ host-side tables
+def rope_cos_sin(head_dim: int, height: int, width: int, theta: float = 10000.0, scale: float = 16.0) -> torch.Tensor:
+    """[L, head_dim/2, 2] (cos, sin) of the 2-D axial RoPE angles; pair 2k <-> x, 2k+1 <-> y
+    (dit_c2i_DeCo.py:116-131).  Evaluated in fp32 on the host exactly like the reference's table."""
+    x_pos = torch.linspace(0, scale, width)
+    y_pos = torch.linspace(0, scale, height)
+    y_pos, x_pos = torch.meshgrid(y_pos, x_pos, indexing="ij")
+    freqs = 1.0 / (theta ** (torch.arange(0, head_dim, 4)[: head_dim // 4].float() / head_dim))
+    ang = torch.stack([torch.outer(x_pos.reshape(-1), freqs), torch.outer(y_pos.reshape(-1), freqs)], dim=-1)
+    ang = ang.reshape(height * width, -1).float()
+    return torch.stack([torch.cos(ang), torch.sin(ang)], dim=-1).contiguous()
+
+
+def nerf_pos_table(patch_size: int, max_freqs: int) -> torch.Tensor:
+    """[p*p, max_freqs^2] constant of NerfEmbedder.fetch_pos (dit_c2i_DeCo.py:221-236)."""
+    pos = torch.linspace(0, 1, patch_size)
+    pos_y, pos_x = torch.meshgrid(pos, pos, indexing="ij")
+    pos_x, pos_y = pos_x.reshape(-1, 1, 1), pos_y.reshape(-1, 1, 1)
+    freqs = torch.linspace(0, max_freqs, max_freqs)
+    fx, fy = freqs[None, :, None], freqs[None, None, :]
+    return (torch.cos(pos_x * fx * torch.pi) * torch.cos(pos_y * fy * torch.pi) * (1 + fx * fy) ** -1
+            ).view(-1, max_freqs ** 2)
+
+
+def _frag(w: torch.Tensor, permuted: bool) -> torch.Tensor:
+    """Pack W [n_out, 32] (bf16) into mma.m16n8k16 B-fragment order: [n_tile, k_step, lane, 4] bf16.
+    lane = 4*g + t holds W[8j+g][k0], W[8j+g][k0+1], W[8j+g][k1], W[8j+g][k1+1] with (k0, k1) =
+    (16s+2t, 16s+8+2t), or -- for the adaLN layers whose A operand is the 16-byte condition chunk --
+    the permuted (8t+4s, 8t+4s+2).  See csrc/decoder.cu."""
+    n_out = w.shape[0]
+    j = torch.arange(n_out // 8).view(-1, 1, 1, 1)
+    s = torch.arange(2).view(1, -1, 1, 1)
+    lane = torch.arange(32).view(1, 1, -1, 1)
+    e = torch.arange(4).view(1, 1, 1, -1)
+    g, t = lane // 4, lane % 4
+    half, lo = e // 2, e % 2
+    if permuted:
+        k = 8 * t + 4 * s + 2 * half + lo
+    else:
+        k = 16 * s + 8 * half + 2 * t + lo
+    rows = (8 * j + g).expand(n_out // 8, 2, 32, 4)
+    return w[rows, k.expand_as(rows)].contiguous()
+
+
+# ------------------------------------------------------------------------------------------------ the module
+class PixNerDiT(nn.Module):
+    """Drop-in for src/models/transformer/dit_c2i_DeCo.py::PixNerDiT (constructor :417-433, forward :488-510)."""
+
+    def __init__(self, in_channels=4, num_groups=12, hidden_size=1152, hidden_size_x=64, nerf_mlpratio=4,
+                 num_blocks=18, num_cond_blocks=4, patch_size=2, num_classes=1000, learn_sigma=True,
+                 deep_supervision=0, weight_path=None, load_ema=False):
+        super().__init__()
+        self.deep_supervision = deep_supervision
+        self.learn_sigma = learn_sigma
+        self.in_channels = in_channels
+        self.out_channels = in_channels
+        self.hidden_size = hidden_size
+        self.hidden_size_x = hidden_size_x
+        self.num_groups = num_groups
+        self.num_blocks = num_blocks
+        self.num_cond_blocks = num_cond_blocks
+        self.patch_size = patch_size
+        self.x_embedder = _NerfEmbedder(in_channels, hidden_size_x, max_freqs=8)
+        self.s_embedder = _Embed(in_channels * patch_size ** 2, hidden_size)
+        self.t_embedder = _TimestepEmbedder(hidden_size)
+        self.y_embedder = _LabelEmbedder(num_classes + 1, hidden_size)
+        self.weight_path = weight_path
+        self.load_ema = load_ema
+        self.blocks = nn.ModuleList([_DiTBlock(hidden_size, num_groups) for _ in range(num_cond_blocks)])
+        self.dec_net = _PixelDecoder(hidden_size_x, hidden_size_x, in_channels, hidden_size,
+                                     num_blocks - num_cond_blocks, patch_size)
+        self.initialize_weights()
+        self.precompute_pos: Dict[Tuple[int, int], torch.Tensor] = {}
+        self._prep = None
+        self._prep_key = None
+
+    def initialize_weights(self):
+        """dit_c2i_DeCo.py:475-486."""
+        w = self.s_embedder.proj.weight.data
+        nn.init.xavier_uniform_(w.view([w.shape[0], -1]))
+        nn.init.constant_(self.s_embedder.proj.bias, 0)
+        nn.init.normal_(self.y_embedder.embedding_table.weight, std=0.02)
+        nn.init.normal_(self.t_embedder.mlp[0].weight, std=0.02)
+        nn.init.normal_(self.t_embedder.mlp[2].weight, std=0.02)
+
+    # -------------------------------------------------------------------------------------------- weight preparation
+    def _weights_key(self, device):
+        return (str(device),) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    @torch.no_grad()
+    def prepare(self, device) -> dict:
+        """bf16 copies / packed layouts of the fp32 master parameters; cached until a parameter changes."""
+        key = self._weights_key(device)
+        if self._prep is not None and self._prep_key == key:
+            return self._prep
+        H, Hx, p = self.hidden_size, self.hidden_size_x, self.patch_size
+        if Hx != 32 or p != 16 or self.in_channels != 3:
+            raise NotImplementedError("the fused pixel decoder is built for in_channels=3, patch_size=16, "
+                                      "hidden_size_x=32 (configs_c2i/DeCo_*.yaml)")
+        d = H // self.num_groups
+        if d not in (64, 72):
+            raise NotImplementedError(f"head_dim {d}: attention/qknorm kernels are built for 64 and 72")
+
+        def W(t):
+            return t.detach().to(device=device, dtype=bf16).contiguous()
+
+        def Fv(t):
+            return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+        P = {}
+        P["ws"], P["bs"] = W(self.s_embedder.proj.weight), Fv(self.s_embedder.proj.bias)
+        P["wt0"], P["bt0"] = W(self.t_embedder.mlp[0].weight), Fv(self.t_embedder.mlp[0].bias)
+        P["wt2"], P["bt2"] = W(self.t_embedder.mlp[2].weight), Fv(self.t_embedder.mlp[2].bias)
+        P["ytab"] = Fv(self.y_embedder.embedding_table.weight)
+        P["wada"] = W(torch.cat([b.adaLN_modulation[0].weight for b in self.blocks], 0))
+        P["bada"] = Fv(torch.cat([b.adaLN_modulation[0].bias for b in self.blocks], 0))
+        F = self.blocks[0].mlp.w1.weight.shape[0] if len(self.blocks) else 0
+        Fp = (F + 15) // 16 * 16     # pad the FFN width (L/16: 2730 -> 2736) with zero rows / columns
+        P["ffn_pad"] = Fp
+        blocks = []
+        for b in self.blocks:
+            w1 = torch.zeros(Fp, H, device=device, dtype=bf16)
+            w3 = torch.zeros(Fp, H, device=device, dtype=bf16)
+            w1[:F], w3[:F] = W(b.mlp.w1.weight), W(b.mlp.w3.weight)
+            # interleave 16 rows of w1 with 16 rows of w3 so that one 32-column accumulator chunk holds matching pairs
+            w13 = torch.stack([w1.view(Fp // 16, 16, H), w3.view(Fp // 16, 16, H)], dim=1).reshape(2 * Fp, H).contiguous()
+            w2 = torch.zeros(H, Fp, device=device, dtype=bf16)
+            w2[:, :F] = W(b.mlp.w2.weight)
+            blocks.append(dict(n1=Fv(b.norm1.weight), wqkv=W(b.attn.qkv.weight), qn=Fv(b.attn.q_norm.weight),
+                               kn=Fv(b.attn.k_norm.weight), wproj=W(b.attn.proj.weight), bproj=Fv(b.attn.proj.bias),
+                               n2=Fv(b.norm2.weight), w13=w13, w2=w2))
+        P["blocks"] = blocks
+        P["wcond"], P["bcond"] = W(self.dec_net.cond_embed.weight), Fv(self.dec_net.cond_embed.bias)
+        P["blob"], P["postab"] = self._pack_decoder(device)
+        self._prep, self._prep_key = P, key
+        return P
+
+    def _pack_decoder(self, device):
+        """Weights of NerfEmbedder / input_proj / ResBlocks / final layer in the layout csrc/decoder.cu expects."""
+        dn = self.dec_net
+        R = len(dn.res_blocks)
+        C = self.in_channels
+
+        def rb(t):  # bf16-rounded fp32 copy on the host
+            return t.detach().float().cpu().to(bf16)
+
+        wx = rb(self.x_embedder.embedder[0].weight)                      # [32, 3 + 64]
+        bx = self.x_embedder.embedder[0].bias.detach().float().cpu()
+        tab = nerf_pos_table(self.patch_size, self.x_embedder.max_freqs).to(bf16).float()   # Linear input cast
+        postab = tab @ wx[:, C:].float().t() + bx                       # [p*p, 32] fp32
+        frags = [_frag(rb(dn.input_proj.weight), False)]
+        vec = [wx[:, :C].float().reshape(-1), torch.zeros(96 - 32 * C), dn.input_proj.bias.detach().float().cpu()]
+        for blk in dn.res_blocks:
+            frags += [_frag(rb(blk.adaLN_modulation[1].weight), True), _frag(rb(blk.mlp[0].weight), False),
+                      _frag(rb(blk.mlp[2].weight), False)]
+            vec += [blk.adaLN_modulation[1].bias, blk.in_ln.weight, blk.in_ln.bias, blk.mlp[0].bias, blk.mlp[2].bias]
+        wf = torch.zeros(8, 32, dtype=bf16)
+        wf[:C] = rb(dn.final_layer.linear.weight)
+        frags.append(_frag(wf, False))
+        bf = torch.zeros(8)
+        bf[:C] = dn.final_layer.linear.bias.detach().float().cpu()
+        vec.append(bf)
+        frag_bytes = torch.cat([f.reshape(-1) for f in frags]).view(torch.uint8)
+        vec_bytes = torch.cat([v.detach().float().cpu().reshape(-1) for v in vec]).view(torch.uint8)
+        blob = torch.cat([frag_bytes, vec_bytes]).contiguous()
+        from . import _lib
+        assert blob.numel() == _lib.load().deco_decoder_blob_bytes(R), (blob.numel(), R)
+        return blob.to(device), postab.contiguous().to(device)
+
+    def fetch_pos(self, height, width, device):
+        """RoPE table cache per (h, w) (dit_c2i_DeCo.py:467-473); here as real (cos, sin)."""
+        key = (height, width)
+        if key not in self.precompute_pos:
+            self.precompute_pos[key] = rope_cos_sin(self.hidden_size // self.num_groups, height, width)
+        tab = self.precompute_pos[key]
+        if tab.device != torch.device(device):
+            tab = tab.to(device)
+            self.precompute_pos[key] = tab
+        return tab
+
+    # -------------------------------------------------------------------------------------------- forward
+    def _encode(self, P, xp, t, y, B, L, pos):
+        """Patch tokens -> DiT blocks -> decoder condition s (dit_c2i_DeCo.py:492-499)."""
+        H, heads = self.hidden_size, self.num_groups
+        d = H // heads
+        nb = len(P["blocks"])
+        tfreq = ops.timestep_freq(t, self.t_embedder.frequency_embedding_size)
+        h1 = ops.gemm(tfreq, P["wt0"], P["bt0"], ops.EPI_BIAS_SILU)
+        temb = ops.gemm(h1, P["wt2"], P["bt2"], ops.EPI_BIAS)                       # [B, H]
+        c = ops.cond_combine(temb, P["ytab"], y)
+        s = ops.gemm(xp, P["ws"], P["bs"], ops.EPI_BIAS)                            # [B*L, H]
+        if nb:
+            mod = ops.gemm(c, P["wada"], P["bada"], ops.EPI_BIAS)                   # [B, nb*6H]
+            hbuf = torch.empty_like(s)
+            qkv = torch.empty((B * L, 3 * H), dtype=bf16, device=s.device)
+            obuf = torch.empty_like(s)
+            ubuf = torch.empty((B * L, P["ffn_pad"]), dtype=bf16, device=s.device)
+        for i, bp in enumerate(P["blocks"]):
+            m = mod[:, i * 6 * H:(i + 1) * 6 * H]
+            sh1, sc1, g1, sh2, sc2, g2 = (m[:, j * H:(j + 1) * H] for j in range(6))
+            ops.rmsnorm_modulate(s, bp["n1"], sh1, sc1, L, out=hbuf)
+            ops.gemm(hbuf, bp["wqkv"], None, ops.EPI_BIAS, out=qkv)
+            ops.qknorm_rope_(qkv, bp["qn"], bp["kn"], pos, heads, d, L)
+            ops.attention(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], B, heads, d, out=obuf)
+            ops.gemm(obuf, bp["wproj"], bp["bproj"], ops.EPI_GATE_RESIDUAL, out=s, resid=s, gate=g1, rows_per_gate=L)
+            ops.rmsnorm_modulate(s, bp["n2"], sh2, sc2, L, out=hbuf)
+            ops.gemm(hbuf, bp["w13"], None, ops.EPI_SWIGLU, out=ubuf)
+            ops.gemm(ubuf, bp["w2"], None, ops.EPI_GATE_RESIDUAL, out=s, resid=s, gate=g2, rows_per_gate=L)
+        return ops.silu_add_rows(s, temb, L, out=s)
+
+    def _forward_impl(self, x, t, y, s=None, mask=None):
+        if mask is not None:
+            raise NotImplementedError("attention masks are not supported (the reference always passes mask=None)")
+        if not x.is_cuda:
+            raise RuntimeError("deco_b200.PixNerDiT runs on CUDA (sm_100a) only; there is no CPU fallback")
+        if torch.is_grad_enabled() and (x.requires_grad or (self.training and any(p.requires_grad for p in self.parameters()))):
+            raise NotImplementedError("backward kernels for the denoiser are not built yet (inference/eval only); "
+                                      "call under torch.no_grad() / .eval()")
+        B, Cc, Hh, Ww = x.shape
+        p, H = self.patch_size, self.hidden_size
+        assert Cc == self.in_channels and Hh % p == 0 and Ww % p == 0
+        L = (Hh // p) * (Ww // p)
+        with torch.no_grad():
+            P = self.prepare(x.device)
+            x32 = x.detach().to(torch.float32).contiguous()
+            if s is None:
+                pos = self.fetch_pos(Hh // p, Ww // p, x.device)
+                xp = ops.patchify(x32, p)
+                s2 = self._encode(P, xp, t.reshape(-1).to(torch.float32), y.reshape(-1), B, L, pos)
+            else:
+                s2 = s.detach().reshape(B * L, H).to(bf16).contiguous()
+            ycond = ops.gemm(s2, P["wcond"], P["bcond"], ops.EPI_BIAS)
+            out = ops.pixel_decoder(x32, ycond, P["blob"], P["postab"], p, self.hidden_size_x,
+                                    self.num_blocks - self.num_cond_blocks)
+        return out, s2.view(B, L, H)
+
+    def forward(self, x, t, y, s=None, mask=None):
+        """x [B,C,H,W], t [B] in [0,1], y [B] int64 (num_classes = null) -> velocity [B,C,H,W] (bf16, as the
+        reference under autocast)."""
+        return self._forward_impl(x, t, y, s, mask)[0]
+
+    def forward_sx(self, x, t, y, s=None, mask=None):
+        """dit_c2i_DeCo.py:512-536: also returns s as [B, H, sqrt(L), sqrt(L)]."""
+        out, s2 = self._forward_impl(x, t, y, s, mask)
+        B, L, H = s2.shape
+        r = int(math.sqrt(L))
+        return out, s2.reshape(B, r, r, H).permute(0, 3, 1, 2)

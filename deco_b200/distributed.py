@@ -1,0 +1,36 @@
+"""Data-parallel sampling: batch sharded over ranks, no collective inside the loop, ONE all-gather of the final
+uint8 images (reference: src/callbacks/save_images.py:56 `pl_module.all_gather(samples)`; shard rule
+src/lightning_data.py:142-144)."""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend: Optional[str] = None):
+    """One process per GPU (torchrun env).  Returns (rank, world_size, local_rank)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+        dist.init_process_group(backend=backend)
+    return rank, world, local
+
+
+def all_gather_images(local_u8: torch.Tensor, world_size: int, total: Optional[int] = None) -> torch.Tensor:
+    """Gather [B_local, C, H, W] uint8 shards and undo the rank-strided sharding: sample i of rank r is global
+    index r + i * world_size."""
+    if world_size == 1:
+        return local_u8
+    bufs = [torch.empty_like(local_u8) for _ in range(world_size)]
+    dist.all_gather(bufs, local_u8.contiguous())
+    stacked = torch.stack(bufs, dim=1)                       # [B_local, world, ...]
+    out = stacked.reshape((-1,) + tuple(local_u8.shape[1:]))  # global order r + i*world
+    return out if total is None else out[:total]

@@ -1,0 +1,203 @@
+"""Tensor-level wrappers over the C ABI (one function per entry point of include/deco_b200.h).
+
+PyTorch is used only for device memory and streams; every function launches the hand-written sm_100a kernel on
+`torch.cuda.current_stream()` and raises if the tensor is not on a CUDA device (there is no CPU path).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import call, ptr
+
+EPI_BIAS, EPI_BIAS_SILU, EPI_GATE_RESIDUAL, EPI_SWIGLU = 0, 1, 2, 3
+bf16 = torch.bfloat16
+
+
+def _cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("deco_b200 kernels need CUDA tensors (sm_100a); there is no CPU fallback")
+
+
+def _st(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, epilogue: int = EPI_BIAS,
+         out: Optional[torch.Tensor] = None, resid: Optional[torch.Tensor] = None,
+         gate: Optional[torch.Tensor] = None, rows_per_gate: int = 1, tile_n: int = 0) -> torch.Tensor:
+    """out = epilogue(a @ w.T): a [M,K] bf16 (row stride allowed), w [N,K] bf16, bias fp32 [N].
+    gate: bf16 2-D view [M/rows_per_gate, N] with arbitrary row stride; resid bf16 [M,N]."""
+    _cuda(a, w, bias, out, resid, gate)
+    assert a.dtype == bf16 and w.dtype == bf16 and a.dim() == 2 and w.dim() == 2
+    assert a.stride(1) == 1 and w.stride(1) == 1
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K, (a.shape, w.shape)
+    n_out = N // 2 if epilogue == EPI_SWIGLU else N
+    if out is None:
+        out = torch.empty((M, n_out), dtype=bf16, device=a.device)
+    assert out.dtype == bf16 and out.shape == (M, n_out) and out.stride(1) == 1
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == N and bias.is_contiguous()
+    ldr = gs = 0
+    if epilogue == EPI_GATE_RESIDUAL:
+        assert resid is not None and gate is not None
+        assert resid.dtype == bf16 and resid.shape == (M, N) and resid.stride(1) == 1
+        assert gate.dtype == bf16 and gate.dim() == 2 and gate.shape[1] == N and gate.stride(1) == 1
+        assert gate.shape[0] * rows_per_gate >= M
+        ldr, gs = resid.stride(0), gate.stride(0)
+    call("deco_gemm_bf16", ptr(a), a.stride(0), ptr(w), w.stride(0), ptr(out), out.stride(0), M, N, K, epilogue,
+         ptr(bias), ptr(resid), ldr, ptr(gate), gs, rows_per_gate, tile_n, _st(a))
+    return out
+
+
+def patchify(x: torch.Tensor, p: int) -> torch.Tensor:
+    _cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4
+    B, Cc, H, W = x.shape
+    out = torch.empty((B * (H // p) * (W // p), Cc * p * p), dtype=bf16, device=x.device)
+    call("deco_patchify", ptr(x), ptr(out), B, Cc, H, W, p, _st(x))
+    return out
+
+
+def timestep_freq(t: torch.Tensor, dim: int = 256, max_period: float = 10.0) -> torch.Tensor:
+    _cuda(t)
+    t = t.reshape(-1).to(torch.float32).contiguous()
+    out = torch.empty((t.numel(), dim), dtype=bf16, device=t.device)
+    call("deco_timestep_freq", ptr(t), ptr(out), t.numel(), dim, float(max_period), _st(t))
+    return out
+
+
+def cond_combine(temb: torch.Tensor, table: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+    _cuda(temb, table, labels)
+    assert temb.dtype == bf16 and temb.is_contiguous() and table.dtype == torch.float32 and table.is_contiguous()
+    labels = labels.reshape(-1).to(torch.int64).contiguous()
+    B, Hd = temb.shape
+    assert labels.numel() == B and table.shape[1] == Hd
+    out = torch.empty_like(temb)
+    call("deco_cond_combine", ptr(temb), ptr(table), ptr(labels), ptr(out), B, Hd, table.shape[0], _st(temb))
+    return out
+
+
+def rmsnorm_modulate(x: torch.Tensor, weight: torch.Tensor, shift: torch.Tensor, scale: torch.Tensor,
+                     rows_per_mod: int, eps: float = 1e-6, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x [M,H] bf16; shift/scale: bf16 views [M/rows_per_mod, H] sharing one row stride."""
+    _cuda(x, weight, shift, scale)
+    assert x.dtype == bf16 and x.is_contiguous() and weight.dtype == torch.float32
+    M, Hd = x.shape
+    assert shift.stride(0) == scale.stride(0) and shift.stride(1) == 1 and scale.stride(1) == 1
+    if out is None:
+        out = torch.empty_like(x)
+    call("deco_rmsnorm_modulate", ptr(x), ptr(weight), ptr(shift), ptr(scale), shift.stride(0), rows_per_mod,
+         ptr(out), M, Hd, float(eps), _st(x))
+    return out
+
+
+def qknorm_rope_(qkv: torch.Tensor, q_weight: torch.Tensor, k_weight: torch.Tensor, rope: torch.Tensor,
+                 heads: int, head_dim: int, L: int, eps: float = 1e-6) -> torch.Tensor:
+    """In place on qkv [M, 3*heads*head_dim]; rope fp32 [L, head_dim/2, 2] (cos, sin)."""
+    _cuda(qkv, q_weight, k_weight, rope)
+    assert qkv.dtype == bf16 and qkv.is_contiguous() and qkv.shape[1] == 3 * heads * head_dim
+    assert rope.dtype == torch.float32 and rope.is_contiguous() and rope.shape == (L, head_dim // 2, 2)
+    call("deco_qknorm_rope", ptr(qkv), ptr(q_weight), ptr(k_weight), ptr(rope), qkv.shape[0], heads, head_dim, L,
+         float(eps), _st(qkv))
+    return qkv
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, heads: int, head_dim: int,
+              k2: Optional[torch.Tensor] = None, v2: Optional[torch.Tensor] = None,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """q [B*Lq, heads*d] view, k/v [B*Lk, heads*d] views (row strides free), optional second KV segment.
+    Returns out [B*Lq, heads*d]."""
+    _cuda(q, k, v, k2, v2)
+    Hd = heads * head_dim
+    Lq, Lk = q.shape[0] // B, k.shape[0] // B
+    assert q.dtype == bf16 and q.shape[1] == Hd and k.shape[1] == Hd and v.shape == k.shape
+    assert k.stride(0) == v.stride(0)
+    if out is None:
+        out = torch.empty((q.shape[0], Hd), dtype=bf16, device=q.device)
+    Lk2, s2 = 0, 0
+    if k2 is not None:
+        Lk2, s2 = k2.shape[0] // B, k2.stride(0)
+        assert v2 is not None and v2.stride(0) == s2
+    call("deco_attention_fwd", ptr(q), q.stride(0), ptr(k), ptr(v), k.stride(0), Lk, ptr(k2), ptr(v2), s2, Lk2,
+         ptr(out), out.stride(0), B, heads, Lq, head_dim, float(head_dim) ** -0.5, _st(q))
+    return out
+
+
+def silu_add_rows(x: torch.Tensor, row: torch.Tensor, rows_per: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _cuda(x, row)
+    assert x.dtype == bf16 and row.dtype == bf16 and x.is_contiguous() and row.is_contiguous()
+    if out is None:
+        out = torch.empty_like(x)
+    call("deco_silu_add_rows", ptr(x), ptr(row), ptr(out), x.shape[0], x.shape[1], rows_per, _st(x))
+    return out
+
+
+def pixel_decoder(x: torch.Tensor, ycond: torch.Tensor, blob: torch.Tensor, postab: torch.Tensor, patch: int,
+                  hidden_x: int, num_res_blocks: int, out_dtype=bf16) -> torch.Tensor:
+    _cuda(x, ycond, blob, postab)
+    assert x.dtype == torch.float32 and x.is_contiguous() and ycond.dtype == bf16 and ycond.is_contiguous()
+    B, Cc, H, W = x.shape
+    assert Cc == 3, "pixel decoder is built for 3 image channels"
+    assert blob.numel() * blob.element_size() == _lib.load().deco_decoder_blob_bytes(num_res_blocks)
+    out = torch.empty((B, Cc, H, W), dtype=out_dtype, device=x.device)
+    call("deco_pixel_decoder", ptr(x), ptr(ycond), ptr(blob), ptr(postab), ptr(out), int(out_dtype == bf16),
+         B, H, W, patch, hidden_x, num_res_blocks, _st(x))
+    return out
+
+
+def cfg_step(x: torch.Tensor, net_out: torch.Tensor, g: float, dt: float, c0: float = 1.0,
+             prev=(), coeffs=(), x_out: Optional[torch.Tensor] = None, want_pred: bool = False,
+             want_v: bool = False, want_u8: bool = False):
+    """x_out = x + dt * (c0 * cfg(net_out, g) + sum_j coeffs[j] * prev[j]).  Returns (x_out, pred, v, u8)."""
+    _cuda(x, net_out)
+    assert x.dtype == torch.float32 and x.is_contiguous() and net_out.is_contiguous()
+    assert net_out.shape[0] == 2 * x.shape[0] and net_out.shape[1:] == x.shape[1:]
+    assert net_out.dtype in (bf16, torch.float32)
+    assert len(prev) == len(coeffs) <= 3
+    n = x.numel()
+    if x_out is None:
+        x_out = torch.empty_like(x)
+    pred = torch.empty_like(x) if want_pred else None
+    v = torch.empty_like(x) if want_v else None
+    u8 = torch.empty(x.shape, dtype=torch.uint8, device=x.device) if want_u8 else None
+    ps = [None, None, None]
+    cs = [0.0, 0.0, 0.0]
+    for j, (p, c) in enumerate(zip(prev, coeffs)):
+        assert p.dtype == torch.float32 and p.is_contiguous() and p.shape == x.shape
+        ps[j], cs[j] = p, float(c)
+    call("deco_cfg_step", ptr(x), ptr(net_out), int(net_out.dtype == bf16), ptr(ps[0]), ptr(ps[1]), ptr(ps[2]),
+         float(g), float(dt), float(c0), cs[0], cs[1], cs[2], ptr(x_out), ptr(pred), ptr(v), ptr(u8), n, _st(x))
+    return x_out, pred, v, u8
+
+
+def fp2uint8(x: torch.Tensor) -> torch.Tensor:
+    _cuda(x)
+    x = x.to(torch.float32).contiguous()
+    out = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    call("deco_fp2uint8", ptr(x), ptr(out), x.numel(), _st(x))
+    return out
+
+
+def dct_fm_loss(out: torch.Tensor, v_t: torch.Tensor, freq_w: torch.Tensor, freq_loss_weight: float,
+                want_loss: bool = True, want_grad: bool = False, upstream: Optional[torch.Tensor] = None):
+    """Returns (losses fp32[3] = fm, freq, total | None, grad | None)."""
+    _cuda(out, v_t, freq_w)
+    assert out.dim() == 4 and out.shape[1] == 3 and out.shape == v_t.shape
+    assert out.dtype in (bf16, torch.float32) and out.is_contiguous()
+    assert v_t.dtype == torch.float32 and v_t.is_contiguous()
+    assert freq_w.dtype == torch.float32 and freq_w.numel() == 192 and freq_w.is_contiguous()
+    B, _, H, W = out.shape
+    losses = torch.empty(3, dtype=torch.float32, device=out.device) if want_loss else None
+    grad = torch.empty_like(out) if want_grad else None
+    accum = torch.empty(2, dtype=torch.float64, device=out.device)
+    if upstream is not None:
+        upstream = upstream.reshape(()).to(torch.float32)
+    call("deco_dct_fm_loss", ptr(out), int(out.dtype == bf16), ptr(v_t), ptr(freq_w), B, H, W,
+         float(freq_loss_weight), ptr(losses), ptr(grad), ptr(upstream), ptr(accum), _st(out))
+    return losses, grad

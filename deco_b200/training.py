@@ -1,0 +1,151 @@
+"""Flow-matching trainer with the frequency-aware 8x8 block-DCT loss, forward and backward as one fused kernel.
+
+Mirrors (reference paths):
+  src/diffusion/base/training.py:7-28                         BaseTrainer (label dropout, call signature)
+  src/diffusion/flow_matching/training_repa_DeCo.py:44-93     REPATrainer constructor
+  src/diffusion/flow_matching/training_repa_DeCo.py:95-195    DCT matrix / YCbCr / JPEG frequency weights
+  src/diffusion/flow_matching/training_repa_DeCo.py:216-288   _impl_trainstep; the DCT term is the formula at
+      :276-285 (commented out in the fork, live in the original trainer -- SURVEY.md fact 3):
+      loss = fm_loss.mean() + freq_loss_weight * (freq_w * (dct(ycbcr(out)) - dct(ycbcr(v_t)))**2).mean()
+The REPA feature-alignment branch (DINOv2 encoder) is out of scope.
+"""
+from __future__ import annotations
+
+from typing import Callable
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .scheduling import BaseScheduler
+
+JPEG_LUMA = [
+    [16, 11, 10, 16, 24, 40, 51, 61], [12, 12, 14, 19, 26, 58, 60, 55], [14, 13, 16, 24, 40, 57, 69, 56],
+    [14, 17, 22, 29, 51, 87, 80, 62], [18, 22, 37, 56, 68, 109, 103, 77], [24, 35, 55, 64, 81, 104, 113, 92],
+    [49, 64, 78, 87, 103, 121, 120, 101], [72, 92, 95, 98, 112, 100, 103, 99]]
+JPEG_CHROMA = [
+    [17, 18, 24, 47, 99, 99, 99, 99], [18, 21, 26, 66, 99, 99, 99, 99], [24, 26, 56, 99, 99, 99, 99, 99],
+    [47, 66, 99, 99, 99, 99, 99, 99], [99] * 8, [99] * 8, [99] * 8, [99] * 8]
+
+
+def constant(alpha, sigma):
+    return 1
+
+
+def time_shift_fn(t, timeshift=1.0):
+    return t / (t + (1 - t) * timeshift)
+
+
+def build_freq_weight(quality=85, mode="inv_gamma", gamma=1.0) -> torch.Tensor:
+    """JPEG quantisation tables scaled to `quality`, turned into per-frequency weights with channel mean 1;
+    shape (1,3,1,1,8,8) like the reference buffer (training_repa_DeCo.py:138-195)."""
+    def scale_q(base):
+        q = max(1, min(100, int(quality)))
+        scale = 5000 / q if q < 50 else 200 - 2 * q
+        return torch.floor((torch.tensor(base, dtype=torch.float32) * scale + 50) / 100).clamp(1, 255)
+
+    def q_to_weight(Q):
+        if mode == "inv":
+            w = 1.0 / Q
+        elif mode == "inv_gamma":
+            w = (Q.mean() / Q) ** gamma
+        else:
+            raise ValueError("mode must be 'inv' or 'inv_gamma'")
+        return w / w.mean()
+    w_y, w_c = q_to_weight(scale_q(JPEG_LUMA)), q_to_weight(scale_q(JPEG_CHROMA))
+    return torch.stack([w_y, w_c, w_c], dim=0).unsqueeze(0).unsqueeze(2).unsqueeze(3)
+
+
+class _DctFmLoss(torch.autograd.Function):
+    """(fm, freq, total) = f(out, v_t).  Forward computes the three scalars AND the unit gradient of `total` in the
+    same pass when `out` needs a gradient (nothing is stashed but that gradient); backward only scales it."""
+
+    @staticmethod
+    def forward(ctx, out, v_t, freq_w, freq_loss_weight):
+        need_grad = out.requires_grad
+        o = out.detach().contiguous()
+        if o.dtype not in (torch.bfloat16, torch.float32):
+            o = o.float()
+        ragged = (o.shape[2] % 8 != 0) or (o.shape[3] % 8 != 0)
+        if ragged and o.dtype != torch.float32:
+            o = o.float()
+        v = v_t.detach().to(torch.float32).contiguous()
+        losses, grad = ops.dct_fm_loss(o, v, freq_w, freq_loss_weight, want_loss=True, want_grad=need_grad)
+        ctx.save_for_backward(grad)
+        ctx.out_dtype = out.dtype
+        ctx.mark_non_differentiable(losses)
+        total = losses[2].clone()
+        return total, losses
+
+    @staticmethod
+    def backward(ctx, g_total, _g_losses):
+        (grad,) = ctx.saved_tensors
+        if grad is None:
+            return None, None, None, None
+        return (grad * g_total.to(grad.dtype)).to(ctx.out_dtype), None, None, None
+
+
+class BaseTrainer(nn.Module):
+    def __init__(self, null_condition_p=0.1):
+        super().__init__()
+        self.null_condition_p = null_condition_p
+
+    def preproprocess(self, x, condition, uncondition, metadata):
+        bsz = x.shape[0]
+        if self.null_condition_p > 0:
+            mask = torch.rand((bsz), device=condition.device) < self.null_condition_p
+            mask = mask.view(-1, *([1] * (len(condition.shape) - 1))).to(condition.dtype)
+            condition = condition * (1 - mask) + uncondition * mask
+        return x, condition, metadata
+
+    def _impl_trainstep(self, net, ema_net, solver, x, y, metadata=None):
+        raise NotImplementedError
+
+    def __call__(self, net, ema_net, solver, x, condition, uncondition, metadata=None):
+        x, condition, metadata = self.preproprocess(x, condition, uncondition, metadata)
+        return self._impl_trainstep(net, ema_net, solver, x, condition, metadata)
+
+
+class REPATrainer(BaseTrainer):
+    def __init__(self, scheduler: BaseScheduler, loss_weight_fn: Callable = constant, feat_loss_weight: float = 0.5,
+                 lognorm_t=False, timeshift=1.0, encoder: nn.Module = None, align_layer=8, proj_denoiser_dim=256,
+                 proj_hidden_dim=256, proj_encoder_dim=256, freq_loss_weight=1, freq_quality: int = 85,
+                 freq_mode: str = "inv_gamma", freq_gamma: float = 1.0, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.lognorm_t = lognorm_t
+        self.scheduler = scheduler() if isinstance(scheduler, type) else scheduler
+        self.timeshift = timeshift
+        self.loss_weight_fn = loss_weight_fn
+        self.feat_loss_weight = feat_loss_weight
+        self.align_layer = align_layer
+        self.freq_loss_weight = freq_loss_weight
+        self.encoder = None  # REPA alignment branch is out of scope; the argument is accepted and ignored
+        self.block_size = 8
+        self.register_buffer("freq_w", build_freq_weight(freq_quality, freq_mode, freq_gamma))
+        if loss_weight_fn is not constant and getattr(loss_weight_fn, "__name__", "") != "constant":
+            raise NotImplementedError("only the constant loss weight is fused into the loss kernel")
+
+    def loss(self, out, v_t):
+        """dict(fm_loss, fm_loss_freq, loss) for network output `out` and target `v_t` (both [B,3,H,W])."""
+        fw = self.freq_w.reshape(3, 8, 8).to(device=out.device, dtype=torch.float32).contiguous()
+        total, losses = _DctFmLoss.apply(out, v_t, fw, float(self.freq_loss_weight))
+        return dict(fm_loss=losses[0], fm_loss_freq=losses[1], loss=total)
+
+    def _impl_trainstep(self, net, ema_net, solver, x, y, metadata=None):
+        batch_size = x.shape[0]
+        # mixed timestep distribution: 90 % sigmoid(randn), 10 % uniform (training_repa_DeCo.py:222-229)
+        nt = torch.randn((batch_size,), device=x.device, dtype=torch.float32)
+        t_lognorm = torch.sigmoid(nt)
+        t_uniform = torch.rand((batch_size,), device=x.device, dtype=torch.float32)
+        base_t = torch.where(torch.rand((batch_size,), device=x.device) <= 0.9, t_lognorm, t_uniform)
+        t = time_shift_fn(base_t, self.timeshift)
+        noise = torch.randn_like(x)
+        alpha, dalpha = self.scheduler.alpha(t), self.scheduler.dalpha(t)
+        sigma, dsigma = self.scheduler.sigma(t), self.scheduler.dsigma(t)
+        x_t = alpha * x + noise * sigma
+        v_t = dalpha * x + dsigma * noise
+        out = net(x_t, t, y)
+        return self.loss(out, v_t)
+
+    def state_dict(self, *args, destination=None, prefix="", keep_vars=False):
+        pass  # as the reference: the trainer contributes nothing to checkpoints (training_repa_DeCo.py:290-291)

@@ -1,0 +1,115 @@
+/* deco_b200 -- C ABI of the B200 (sm_100a) kernels behind the DeCo denoise / sample / DCT-loss hot path.
+ *
+ * The reference (hhhhzp/DeCo) is pure Python/PyTorch: it has no FFI or operator registry, its "plugin boundary" is
+ * class substitution in the YAML configs.  This header is therefore the boundary the *new* Python
+ * modules (deco_b200/*.py, which mirror the reference classes) bind with ctypes; each entry point cites the
+ * reference call site(s) it replaces (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - plain pointers + sizes; every pointer is DEVICE memory unless stated; no allocation inside the library
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream); all calls are asynchronous
+ *   - return 0 on success, a cudaError_t (>0) or a negative DECO_ERR_* code; deco_last_error() gives the message
+ *   - bf16 tensors are passed as void*; "ld*" / "*_stride" are in ELEMENTS
+ *   - thread-compatible: no global mutable state besides lazily initialised, idempotent function attributes
+ */
+#ifndef DECO_B200_H
+#define DECO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DECO_ERR_ARG (-1)
+#define DECO_ERR_UNSUPPORTED (-2)
+#define DECO_ERR_DRIVER (-3)
+
+const char* deco_last_error(void);
+int deco_abi_version(void);
+
+/* GEMM epilogues */
+#define DECO_EPI_BIAS 0           /* out = A.W^T + bias                                  (nn.Linear)              */
+#define DECO_EPI_BIAS_SILU 1      /* out = silu(A.W^T + bias)                            (t_embedder.mlp[0:2])    */
+#define DECO_EPI_GATE_RESIDUAL 2  /* out = resid + gate[row / rows_per_gate] * (A.W^T + bias)                     */
+#define DECO_EPI_SWIGLU 3         /* W rows interleaved [16 x w1 | 16 x w3]: out[:, j] = silu(a_j) * b_j, N/2 cols */
+
+/* tcgen05 / TMEM / TMA bf16 GEMM: out[M, N(or N/2)] = epilogue(A[M,K] . W[N,K]^T), fp32 accumulate.
+ * Replaces nn.Linear at src/models/transformer/dit_c2i_DeCo.py:496 (s_embedder), :55-57 (t_embedder.mlp),
+ * :207 (adaLN_modulation, all blocks in one call), :176 (attn.qkv), :188+:208 (attn.proj + gated residual),
+ * :113 (mlp.w1/w3/w2, SwiGLU), :209 (gated residual), :404 (dec_net.cond_embed).
+ * K, N, lda, ldw, ldo multiples of 8; pointers 16-byte aligned; tile_n in {0 (auto), 128, 192, 256}. */
+int deco_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, void* out, long long ldo,
+                   int M, int N, int K, int epilogue, const float* bias,
+                   const void* resid, long long ldr, const void* gate, long long gate_stride, int rows_per_gate,
+                   int tile_n, void* stream);
+
+/* F.unfold + transpose (dit_c2i_DeCo.py:491): fp32 [B,C,H,W] -> bf16 [B*L, C*p*p], feature order c*p*p + ky*p + kx */
+int deco_patchify(const float* x, void* out_bf16, int B, int C, int H, int W, int p, void* stream);
+
+/* TimestepEmbedder.timestep_embedding (dit_c2i_DeCo.py:43-53): [B] -> bf16 [B, dim] = [cos || sin] */
+int deco_timestep_freq(const float* t, void* out_bf16, int B, int dim, float max_period, void* stream);
+
+/* c = silu(t_emb + embedding_table[y]) (dit_c2i_DeCo.py:493-494); labels int64, table fp32 [num_rows, hidden] */
+int deco_cond_combine(const void* temb_bf16, const float* table, const long long* labels, void* c_bf16,
+                      int B, int hidden, int num_rows, void* stream);
+
+/* RMSNorm (dit_c2i_DeCo.py:94-99) + modulate (:11-12): out = w * rms(x) * (1 + scale) + shift.
+ * shift/scale point into the batched adaLN output; row m uses modulation row m / rows_per_mod. */
+int deco_rmsnorm_modulate(const void* x_bf16, const float* weight, const void* shift_bf16, const void* scale_bf16,
+                          long long mod_row_stride, int rows_per_mod, void* out_bf16, long long M, int hidden,
+                          float eps, void* stream);
+
+/* q_norm / k_norm + apply_rotary_emb (dit_c2i_DeCo.py:178-180, :134-145), in place on the QKV GEMM output
+ * [M, 3*heads*head_dim]; rope_cos_sin: fp32 [L, head_dim/2, 2]; token position = row % L. head_dim in {64, 72}. */
+int deco_qknorm_rope(void* qkv_bf16, const float* q_weight, const float* k_weight, const float* rope_cos_sin,
+                     long long M, int heads, int head_dim, int L, float eps, void* stream);
+
+/* scaled_dot_product_attention, non-causal, no mask (dit_c2i_DeCo.py:185; layers/attention_op.py:4).
+ * q/k/v/out are strided views ([B*L, stride] rows, head h at column h*head_dim), so Q/K/V are read in place from the
+ * QKV GEMM output.  A second key/value segment (k1, v1, Lk1) implements the t2i [image || text] keys
+ * (dit_t2i_pixnerd.py:52-59); pass Lk1 = 0 for plain self-attention. */
+int deco_attention_fwd(const void* q, long long q_stride,
+                       const void* k0, const void* v0, long long kv0_stride, int Lk0,
+                       const void* k1, const void* v1, long long kv1_stride, int Lk1,
+                       void* out, long long out_stride,
+                       int B, int heads, int Lq, int head_dim, float scale, void* stream);
+
+/* s = silu(t + s) (dit_c2i_DeCo.py:499): out[m,:] = silu(x[m,:] + row[m / rows_per,:]); out may alias x */
+int deco_silu_add_rows(const void* x_bf16, const void* row_bf16, void* out_bf16, long long M, int hidden,
+                       int rows_per, void* stream);
+
+/* NerfEmbedder + SimpleMLPAdaLN + fold (dit_c2i_DeCo.py:212-248, :288-415, :501-509).
+ * x fp32 [B,3,H,W]; ycond = cond_embed output bf16 [B*L, p*p*32]; blob = packed weights
+ * (deco_decoder_blob_bytes bytes, layout in csrc/decoder.cu, packed by deco_b200/denoiser.py); postab fp32 [p*p, 32].
+ * out [B,3,H,W] bf16 or fp32.  Built for patch 16, hidden_size_x 32. */
+int deco_decoder_blob_bytes(int num_res_blocks);
+int deco_pixel_decoder(const float* x, const void* ycond_bf16, const void* blob, const float* postab,
+                       void* out, int out_is_bf16, int B, int H, int W, int patch, int hidden_x,
+                       int num_res_blocks, void* stream);
+
+/* CFG combine + sampler state update (base/guidance.py:3-6; flow_matching/sampling.py:14-15,:89-104,:283-291;
+ * flow_matching/adam_sampling.py:109-117; autoencoder/base.py:32-34):
+ *   pred = u + g (c - u);  v = c0 pred + c1 p1 + c2 p2 + c3 p3;  x_out = x + dt v
+ * net_out [2n] rows [uncond || cond] (bf16 or fp32); optional outputs pred_out, v_out (fp32), u8_out = fp2uint8(x_out).
+ * n = elements per CFG half, multiple of 4. */
+int deco_cfg_step(const float* x, const void* net_out, int net_is_bf16,
+                  const float* p1, const float* p2, const float* p3,
+                  float g, float dt, float c0, float c1, float c2, float c3,
+                  float* x_out, float* pred_out, float* v_out, uint8_t* u8_out, long long n, void* stream);
+int deco_fp2uint8(const float* x, uint8_t* out, long long n, void* stream);
+
+/* Frequency-aware FM loss, forward and/or backward in one pass
+ * (flow_matching/training_repa_DeCo.py:106-136 _rgb2ycbcr/_dct, :138-195 weights, :273-285 loss):
+ *   losses[0] = mean((out - v_t)^2), losses[1] = mean(freq_w * dct(ycbcr(out - v_t))^2), losses[2] = [0] + flw * [1]
+ *   grad = upstream * d losses[2] / d out   (same dtype as out; fp32 required for ragged H/W)
+ * out [B,3,H,W] fp32 or bf16; v_t fp32; freq_w fp32 [3,8,8]; accum = 2 doubles of scratch;
+ * losses and/or grad may be NULL; upstream = device scalar or NULL (1.0). */
+int deco_dct_fm_loss(const void* out, int out_is_bf16, const float* v_t, const float* freq_w,
+                     int B, int H, int W, float freq_loss_weight,
+                     float* losses, void* grad, const float* upstream, double* accum, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DECO_B200_H */

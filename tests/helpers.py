@@ -1,0 +1,52 @@
+import os
+
+import numpy as np
+import torch
+
+from oracle import deco_oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def rel_l2(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def psnr(a, b, peak):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    mse = float(((a - b) ** 2).mean())
+    return float("inf") if mse == 0 else 10.0 * np.log10(peak * peak / mse)
+
+
+def load_golden(name):
+    return np.load(os.path.join(GOLDEN, name))
+
+
+def cfg_from_array(a) -> O.DenoiserCfg:
+    a = [int(v) for v in a]
+    return O.DenoiserCfg(in_channels=a[0], num_groups=a[1], hidden_size=a[2], hidden_size_x=a[3], num_blocks=a[4],
+                         num_cond_blocks=a[5], patch_size=a[6], num_classes=a[7])
+
+
+def build_module(cfg: O.DenoiserCfg, device, seed=1234):
+    """deco_b200.PixNerDiT holding oracle.seeded_params(cfg) (the same weights the golden fixtures were made with)."""
+    from deco_b200 import PixNerDiT
+    with torch.device("meta"):
+        m = PixNerDiT(in_channels=cfg.in_channels, num_groups=cfg.num_groups, hidden_size=cfg.hidden_size,
+                      hidden_size_x=cfg.hidden_size_x, num_blocks=cfg.num_blocks, num_cond_blocks=cfg.num_cond_blocks,
+                      patch_size=cfg.patch_size, num_classes=cfg.num_classes)
+    P = O.seeded_params(cfg, seed)
+    m = m.to_empty(device=device)
+    m.load_state_dict({k: v.to(device) for k, v in P.items()})
+    return m.eval(), P
+
+
+def seeded_noise(n, shape, seed0=0):
+    return torch.stack([torch.randn(shape, generator=torch.Generator().manual_seed(seed0 + i), dtype=torch.float32)
+                        for i in range(n)])
+
+
+def toy_net(x, t, y):
+    """Analytic stand-in network used for the sampler golden fixtures (tests/golden/make_golden.py)."""
+    return torch.tanh(x * (0.5 + t.view(-1, 1, 1, 1))) - 0.1 * y.view(-1, 1, 1, 1).float()

@@ -1,0 +1,174 @@
+"""Per-kernel parity: every C-ABI entry point against a plain PyTorch fp32 evaluation of the same operands."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import rel_l2
+from oracle import deco_oracle as O
+
+pytestmark = pytest.mark.gpu
+bf16 = torch.bfloat16
+
+
+def _rand(shape, dev, seed, scale=1.0, dtype=bf16):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(device=dev, dtype=dtype)
+
+
+@pytest.mark.parametrize("M,N,K,tile_n", [
+    (256, 256, 128, 128), (256, 256, 128, 256), (300, 1152, 1152, 0), (128, 3456, 1152, 192),
+    (520, 576, 576, 128), (8, 1024, 256, 0), (1024, 8192, 1152, 256), (640, 2736, 1024, 0), (384, 1152, 2736, 0),
+])
+def test_gemm_bias(cuda_dev, M, N, K, tile_n):
+    from deco_b200 import ops
+    a, w = _rand((M, K), cuda_dev, 1), _rand((N, K), cuda_dev, 2, K ** -0.5)
+    bias = _rand((N,), cuda_dev, 3, 0.1, torch.float32)
+    ref = a.float() @ w.float().t() + bias
+    out = ops.gemm(a, w, bias, ops.EPI_BIAS, tile_n=tile_n)
+    torch.cuda.synchronize()
+    assert rel_l2(out.float(), ref) < 4e-3
+    out = ops.gemm(a, w, None, ops.EPI_BIAS, tile_n=tile_n)
+    assert rel_l2(out.float(), a.float() @ w.float().t()) < 4e-3
+    out = ops.gemm(a, w, bias, ops.EPI_BIAS_SILU, tile_n=tile_n)
+    assert rel_l2(out.float(), F.silu(ref)) < 4e-3
+
+
+def test_gemm_strided_a(cuda_dev):
+    """A operand as a column slice of a wider matrix (how attention output / qkv views are consumed)."""
+    from deco_b200 import ops
+    big = _rand((384, 3 * 256), cuda_dev, 5)
+    a = big[:, 256:512]
+    w = _rand((128, 256), cuda_dev, 6, 1 / 16)
+    out = ops.gemm(a, w)
+    assert rel_l2(out.float(), a.float() @ w.float().t()) < 4e-3
+
+
+@pytest.mark.parametrize("M,N,K,L,tile_n", [(512, 1152, 1152, 256, 0), (200, 576, 3072, 100, 128), (512, 1024, 2736, 64, 256)])
+def test_gemm_gate_residual(cuda_dev, M, N, K, L, tile_n):
+    from deco_b200 import ops
+    a, w = _rand((M, K), cuda_dev, 1), _rand((N, K), cuda_dev, 2, K ** -0.5)
+    bias = _rand((N,), cuda_dev, 3, 0.1, torch.float32)
+    resid = _rand((M, N), cuda_dev, 4)
+    nb = (M + L - 1) // L
+    mod = _rand((nb, 6 * N), cuda_dev, 5)
+    gate = mod[:, 2 * N:3 * N]
+    ref = resid.float() + gate.float().repeat_interleave(L, 0)[:M] * (a.float() @ w.float().t() + bias)
+    out = resid.clone()
+    ops.gemm(a, w, bias, ops.EPI_GATE_RESIDUAL, out=out, resid=out, gate=gate, rows_per_gate=L, tile_n=tile_n)
+    assert rel_l2(out.float(), ref) < 4e-3
+
+
+@pytest.mark.parametrize("M,F_,K,tile_n", [(256, 3072, 1152, 0), (130, 2736, 1024, 0), (256, 512, 256, 128)])
+def test_gemm_swiglu(cuda_dev, M, F_, K, tile_n):
+    from deco_b200 import ops
+    a = _rand((M, K), cuda_dev, 1)
+    w1, w3 = _rand((F_, K), cuda_dev, 2, K ** -0.5), _rand((F_, K), cuda_dev, 3, K ** -0.5)
+    w13 = torch.stack([w1.view(F_ // 16, 16, K), w3.view(F_ // 16, 16, K)], 1).reshape(2 * F_, K).contiguous()
+    ref = F.silu(a.float() @ w1.float().t()) * (a.float() @ w3.float().t())
+    out = ops.gemm(a, w13, None, ops.EPI_SWIGLU, tile_n=tile_n)
+    assert out.shape == (M, F_)
+    assert rel_l2(out.float(), ref) < 5e-3
+
+
+def test_patchify_exact(cuda_dev):
+    from deco_b200 import ops
+    x = _rand((3, 3, 64, 96), cuda_dev, 7, dtype=torch.float32)
+    ref = F.unfold(x, kernel_size=16, stride=16).transpose(1, 2).reshape(-1, 768).to(bf16)
+    assert torch.equal(ops.patchify(x, 16), ref)
+
+
+def test_timestep_and_cond(cuda_dev):
+    from deco_b200 import ops
+    t = torch.tensor([0.0, 0.5, 0.0999, 1.0], device=cuda_dev)
+    ref = O.timestep_embedding(t)
+    got = ops.timestep_freq(t).float()
+    assert (got - ref).abs().max() < 5e-3          # bf16 storage
+    assert abs(float(ref[1, 0]) - 0.8775826) < 1e-6 and abs(float(ref[1, 128 + 127]) - 0.0508856) < 1e-6
+    temb = _rand((4, 128), cuda_dev, 1)
+    table = _rand((11, 128), cuda_dev, 2, dtype=torch.float32)
+    y = torch.tensor([0, 10, 3, 7], device=cuda_dev)
+    ref = F.silu(temb.float() + table[y])
+    assert rel_l2(ops.cond_combine(temb, table, y).float(), ref) < 4e-3
+
+
+@pytest.mark.parametrize("H", [1152, 1024, 576, 1536])
+def test_rmsnorm_modulate(cuda_dev, H):
+    from deco_b200 import ops
+    M, L = 96, 16
+    x = _rand((M, H), cuda_dev, 1, 2.0)
+    w = 1 + 0.1 * _rand((H,), cuda_dev, 2, dtype=torch.float32)
+    mod = _rand((M // L, 6 * H), cuda_dev, 3, 0.5)
+    sh, sc = mod[:, :H], mod[:, H:2 * H]
+    ref = O.modulate(O.rmsnorm(x, w), sh.float().repeat_interleave(L, 0), sc.float().repeat_interleave(L, 0))
+    got = ops.rmsnorm_modulate(x, w, sh, sc, L)
+    assert rel_l2(got.float(), ref) < 4e-3
+
+
+@pytest.mark.parametrize("heads,d,hw", [(16, 72, (4, 4)), (8, 64, (3, 5))])
+def test_qknorm_rope(cuda_dev, heads, d, hw):
+    from deco_b200 import ops
+    from deco_b200.denoiser import rope_cos_sin
+    L = hw[0] * hw[1]
+    B = 3
+    qkv = _rand((B * L, 3 * heads * d), cuda_dev, 1)
+    qw = 1 + 0.1 * _rand((d,), cuda_dev, 2, dtype=torch.float32)
+    kw = 1 + 0.1 * _rand((d,), cuda_dev, 3, dtype=torch.float32)
+    ang = O.rope_table_2d(d, hw[0], hw[1]).to(cuda_dev)
+    r = qkv.view(B, L, 3, heads, d)
+    q_ref = O.apply_rope(O.rmsnorm(r[:, :, 0], qw), ang)
+    k_ref = O.apply_rope(O.rmsnorm(r[:, :, 1], kw), ang)
+    v_ref = r[:, :, 2].clone()
+    got = ops.qknorm_rope_(qkv.clone(), qw, kw, rope_cos_sin(d, hw[0], hw[1]).to(cuda_dev), heads, d, L)
+    g = got.view(B, L, 3, heads, d)
+    assert rel_l2(g[:, :, 0].float(), q_ref) < 4e-3
+    assert rel_l2(g[:, :, 1].float(), k_ref) < 4e-3
+    assert torch.equal(g[:, :, 2], v_ref)
+
+
+@pytest.mark.parametrize("heads,d,Lq,Lk2", [(16, 72, 256, 0), (4, 64, 100, 0), (2, 72, 1024, 0), (3, 64, 200, 77), (2, 72, 64, 128)])
+def test_attention(cuda_dev, heads, d, Lq, Lk2):
+    from deco_b200 import ops
+    B, H = 2, heads * d
+    qkv = _rand((B * Lq, 3 * H), cuda_dev, 1)
+    q, k, v = qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:]
+    k2 = v2 = None
+    kk = k.reshape(B, Lq, heads, d).transpose(1, 2).float()
+    vv = v.reshape(B, Lq, heads, d).transpose(1, 2).float()
+    if Lk2:
+        kv2 = _rand((B * Lk2, 2 * H), cuda_dev, 2)
+        k2, v2 = kv2[:, :H], kv2[:, H:]
+        kk = torch.cat([kk, k2.reshape(B, Lk2, heads, d).transpose(1, 2).float()], 2)
+        vv = torch.cat([vv, v2.reshape(B, Lk2, heads, d).transpose(1, 2).float()], 2)
+    qq = q.reshape(B, Lq, heads, d).transpose(1, 2).float()
+    ref = F.scaled_dot_product_attention(qq, kk, vv).transpose(1, 2).reshape(B * Lq, H)
+    got = ops.attention(q, k, v, B, heads, d, k2=k2, v2=v2)
+    assert rel_l2(got.float(), ref) < 6e-3
+
+
+def test_silu_add_rows(cuda_dev):
+    from deco_b200 import ops
+    x, row = _rand((64, 256), cuda_dev, 1), _rand((4, 256), cuda_dev, 2)
+    ref = F.silu((x + row.repeat_interleave(16, 0)).float())
+    assert rel_l2(ops.silu_add_rows(x, row, 16).float(), ref) < 4e-3
+    assert rel_l2(ops.silu_add_rows(x, row, 16, out=x).float(), ref) < 4e-3   # in place
+
+
+@pytest.mark.parametrize("net_dtype", [bf16, torch.float32])
+def test_cfg_step(cuda_dev, net_dtype):
+    from deco_b200 import ops
+    x = _rand((3, 3, 16, 16), cuda_dev, 1, dtype=torch.float32)
+    out = _rand((6, 3, 16, 16), cuda_dev, 2, dtype=net_dtype)
+    p1 = _rand((3, 3, 16, 16), cuda_dev, 3, dtype=torch.float32)
+    p2 = _rand((3, 3, 16, 16), cuda_dev, 4, dtype=torch.float32)
+    u, c = out.float().chunk(2)
+    pred = u + 3.2 * (c - u)
+    x1, pr, v, u8 = ops.cfg_step(x, out, 3.2, 0.01, want_pred=True, want_v=True, want_u8=True)
+    assert torch.allclose(pr, pred, atol=1e-6) and torch.allclose(x1, x + 0.01 * pred, atol=1e-6)
+    assert torch.equal(u8, O.fp2uint8(x1))
+    x2, _, v2, _ = ops.cfg_step(x, out, 1.0, 0.5, c0=0.25, prev=(p1, p2), coeffs=(-0.5, 1.25), want_v=True)
+    vr = 0.25 * c + -0.5 * p1 + 1.25 * p2
+    assert torch.allclose(v2, vr, atol=1e-5) and torch.allclose(x2, x + 0.5 * vr, atol=1e-5)
+    z = torch.tensor([-1.5, -1.0, -0.999, 0.0, 0.5, 0.996, 1.0, 3.0], device=cuda_dev)
+    assert torch.equal(ops.fp2uint8(z), O.fp2uint8(z))
