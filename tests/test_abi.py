@@ -1,0 +1,60 @@
+"""CPU: the C-ABI library loads and exports exactly what include/deco_b200.h declares; argument validation works
+without a GPU (checks run before any launch)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    src = open(os.path.join(ROOT, "include", "deco_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(deco_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(lib):
+    from deco_b200 import _lib
+    names = declared_functions()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/deco_b200.h but not exported"
+    assert sorted(_lib.SIGNATURES) == names, "ctypes table and header disagree"
+
+
+def test_header_arity_matches_ctypes_table():
+    from deco_b200 import _lib
+    src = open(os.path.join(ROOT, "include", "deco_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    for name, (_, args) in _lib.SIGNATURES.items():
+        m = re.search(r"\b" + name + r"\s*\((.*?)\)\s*;", src, flags=re.S)
+        assert m, name
+        params = [p for p in m.group(1).split(",") if p.strip() and p.strip() != "void"]
+        assert len(params) == len(args), (name, len(params), len(args))
+
+
+def test_host_only_entry_points(lib):
+    assert lib.deco_abi_version() == 1
+    assert lib.deco_decoder_blob_bytes(3) == 36512
+    assert lib.deco_decoder_blob_bytes(4) > lib.deco_decoder_blob_bytes(3)
+
+
+def test_argument_errors_do_not_need_a_gpu(lib):
+    rc = lib.deco_cfg_step(None, None, 1, None, None, None, 1.0, 0.1, 1.0, 0, 0, 0, None, None, None, None, 8, None)
+    assert rc == -1 and b"null" in lib.deco_last_error()
+    rc = lib.deco_gemm_bf16(ctypes.c_void_p(16), 8, ctypes.c_void_p(16), 8, ctypes.c_void_p(16), 8, 4, 8, 7, 0,
+                            None, None, 0, None, 0, 1, 0, None)
+    assert rc == -1 and b"multiples of 8" in lib.deco_last_error()
+    rc = lib.deco_qknorm_rope(ctypes.c_void_p(16), ctypes.c_void_p(16), ctypes.c_void_p(16), ctypes.c_void_p(16),
+                              4, 2, 48, 4, 1e-6, None)
+    assert rc == -2 and b"head_dim" in lib.deco_last_error()
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from deco_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libdeco_b200.so")
+    with pytest.raises(_lib.DecoLibraryError, match="no CPU or PyTorch fallback"):
+        _lib.load()

@@ -1,0 +1,214 @@
+"""CPU: host-side logic of the drop-in modules -- parameter/checkpoint contract, YAML wiring, sampler schedules and
+control flow, weight packing, data-parallel sharding (gloo, world_size 2).  No CUDA kernel runs here."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from helpers import load_golden, rel_l2, toy_net
+from oracle import deco_oracle as O
+
+XL_YAML = """
+model:
+  vae:
+    class_path: src.models.autoencoder.pixel.PixelAE
+    init_args: {scale: 1.0}
+  denoiser:
+    class_path: src.models.transformer.dit_c2i_DeCo.PixNerDiT
+    init_args:
+      in_channels: 3
+      patch_size: 16
+      num_groups: 4
+      hidden_size: &hidden_dim 256
+      hidden_size_x: 32
+      num_blocks: 5
+      num_cond_blocks: 2
+      nerf_mlpratio: 2
+      num_classes: &num_classes 10
+  conditioner:
+    class_path: src.models.conditioner.class_label.LabelConditioner
+    init_args: {num_classes: *num_classes}
+  diffusion_trainer:
+    class_path: src.diffusion.flow_matching.training_repa_DeCo.REPATrainer
+    init_args:
+      lognorm_t: true
+      encoder:
+        class_path: src.models.encoder.DINOv2
+        init_args: {weight_path: /nonexistent}
+      align_layer: 8
+      proj_denoiser_dim: *hidden_dim
+      proj_hidden_dim: *hidden_dim
+      proj_encoder_dim: 768
+      null_condition_p: 0.2
+      scheduler: &scheduler src.diffusion.flow_matching.scheduling.LinearScheduler
+  diffusion_sampler:
+    class_path: src.diffusion.flow_matching.sampling.EulerSampler
+    init_args:
+      num_steps: 100
+      guidance: 3.2
+      guidance_interval_min: 0.1
+      guidance_interval_max: 1.0
+      scheduler: *scheduler
+      w_scheduler: src.diffusion.flow_matching.scheduling.LinearScheduler
+      guidance_fn: src.diffusion.base.guidance.simple_guidance_fn
+      step_fn: src.diffusion.flow_matching.sampling.ode_step_fn
+"""
+
+
+@pytest.mark.parametrize("cfg", [O.CFG_XL, O.CFG_L])
+def test_state_dict_is_the_reference_checkpoint_contract(cfg):
+    from deco_b200 import PixNerDiT
+    with torch.device("meta"):
+        m = PixNerDiT(in_channels=3, num_groups=cfg.num_groups, hidden_size=cfg.hidden_size, hidden_size_x=32,
+                      num_blocks=cfg.num_blocks, num_cond_blocks=cfg.num_cond_blocks, patch_size=16, num_classes=1000)
+    sd = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert sd == O.param_shapes(cfg)
+    assert m.weight_path is None and m.load_ema is False
+
+
+def test_default_init_follows_reference():
+    from deco_b200 import PixNerDiT
+    torch.manual_seed(0)
+    m = PixNerDiT(in_channels=3, num_groups=4, hidden_size=256, hidden_size_x=32, num_blocks=4, num_cond_blocks=1,
+                  patch_size=16, num_classes=10)
+    assert float(m.dec_net.final_layer.linear.weight.abs().max()) == 0.0
+    assert all(float(b.adaLN_modulation[1].weight.abs().max()) == 0.0 for b in m.dec_net.res_blocks)
+    assert float(m.s_embedder.proj.bias.abs().max()) == 0.0
+    assert abs(float(m.y_embedder.embedding_table.weight.std()) - 0.02) < 2e-3
+
+
+def test_yaml_wiring(tmp_path):
+    from deco_b200 import EulerSampler, LinearScheduler, PixNerDiT, REPATrainer, config, ode_step_fn, simple_guidance_fn
+    p = tmp_path / "cfg.yaml"
+    p.write_text(XL_YAML)
+    parts = config.load_model_section(str(p))
+    assert isinstance(parts["denoiser"], PixNerDiT) and isinstance(parts["diffusion_sampler"], EulerSampler)
+    s, tr = parts["diffusion_sampler"], parts["diffusion_trainer"]
+    assert isinstance(tr, REPATrainer) and tr.null_condition_p == 0.2 and isinstance(tr.scheduler, LinearScheduler)
+    assert s.guidance_fn is simple_guidance_fn and s.step_fn is ode_step_fn and isinstance(s.scheduler, LinearScheduler)
+    assert s.num_steps == 100 and s.guidance == 3.2
+    assert float(s.timesteps[10]) == 0.09999999403953552
+    cond, unc = parts["conditioner"]([1, 2, 3], device="cpu")
+    assert cond.dtype == torch.int64 and unc.tolist() == [10, 10, 10]
+
+
+def test_no_cpu_fallback():
+    from deco_b200 import EulerSampler, LinearScheduler, PixNerDiT, REPATrainer, ops
+    m = PixNerDiT(in_channels=3, num_groups=4, hidden_size=256, hidden_size_x=32, num_blocks=4, num_cond_blocks=1,
+                  patch_size=16, num_classes=10).eval()
+    x = torch.zeros(1, 3, 32, 32)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(x, torch.zeros(1), torch.zeros(1, dtype=torch.long))
+    s = EulerSampler(scheduler=LinearScheduler(), num_steps=2)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        s(toy_net, x, torch.zeros(1, dtype=torch.long), torch.zeros(1, dtype=torch.long))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        REPATrainer(scheduler=LinearScheduler()).loss(x, x)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.fp2uint8(x)
+
+
+def _torch_cfg_step(x, net_out, g, dt, c0=1.0, prev=(), coeffs=(), x_out=None, want_pred=False, want_v=False,
+                    want_u8=False):
+    """Test-only torch statement of csrc/sampler.cu so the samplers' host control flow can be checked without a GPU."""
+    u, c = net_out.float().chunk(2)
+    pred = u + g * (c - u)
+    v = c0 * pred
+    for p, cf in zip(prev, coeffs):
+        v = v + cf * p
+    xo = x + dt * v
+    return xo, (pred if want_pred else None), (v if want_v else None), (O.fp2uint8(xo) if want_u8 else None)
+
+
+def test_sampler_control_flow_matches_reference(monkeypatch):
+    from deco_b200 import AdamLMSampler, EulerSampler, HeunSampler, LinearScheduler, ode_step_fn, ops, sampling, simple_guidance_fn
+    monkeypatch.setattr(ops, "cfg_step", _torch_cfg_step)
+    monkeypatch.setattr(sampling, "_prep_inputs", lambda n, c, u: (n.float().contiguous(), torch.cat([u, c], 0)))
+    g = load_golden("samplers_toy.npz")
+    noise = torch.from_numpy(g["noise"])
+    cond, unc = torch.tensor([1, 2, 3]), torch.tensor([10, 10, 10])
+    sch = LinearScheduler()
+    for n, gd, lo, hi, shift in [(10, 3.2, 0.1, 1.0, 1.0), (7, 2.0, 0.0, 0.6, 3.0)]:
+        kw = dict(scheduler=sch, w_scheduler=sch, guidance_fn=simple_guidance_fn, num_steps=n, guidance=gd,
+                  guidance_interval_min=lo, guidance_interval_max=hi, timeshift=shift, step_fn=ode_step_fn)
+        assert rel_l2(EulerSampler(**kw)(toy_net, noise, cond, unc), torch.from_numpy(g[f"euler_{n}"])) < 1e-6
+        assert rel_l2(HeunSampler(**kw)(toy_net, noise, cond, unc), torch.from_numpy(g[f"heun_{n}"])) < 1e-6
+        assert rel_l2(HeunSampler(exact_henu=True, **kw)(toy_net, noise, cond, unc),
+                      torch.from_numpy(g[f"heun_exact_{n}"])) < 1e-6
+    for n, order, shift, gd in [(25, 2, 3.0, 4.0), (8, 3, 1.0, 2.0), (6, 4, 2.0, 1.5)]:
+        a = AdamLMSampler(order=order, timeshift=shift, scheduler=sch, guidance_fn=simple_guidance_fn, num_steps=n,
+                          guidance=gd, guidance_interval_min=0.0, guidance_interval_max=1.0)
+        assert np.array_equal(a.timesteps.numpy(), g[f"adam_{n}_{order}_ts"])
+        ref = g[f"adam_{n}_{order}_coeffs"]
+        for i in range(n):
+            assert np.allclose(a.solver_coeffs[i], ref[i][: len(a.solver_coeffs[i])], rtol=2e-4, atol=5e-5)
+        assert rel_l2(a(toy_net, noise, cond, unc), torch.from_numpy(g[f"adam_{n}_{order}"])) < 1e-4
+    with pytest.raises(NotImplementedError):
+        EulerSampler(scheduler=sch, step_fn=lambda *a, **k: None, num_steps=2)
+
+
+def test_decoder_fragment_packing_roundtrip():
+    """_frag must place W[n][k] where mma.m16n8k16 expects B[k][n] (see csrc/decoder.cu)."""
+    from deco_b200.denoiser import _frag
+    w = torch.arange(96 * 32, dtype=torch.float32).reshape(96, 32).to(torch.bfloat16)
+    for permuted in (False, True):
+        f = _frag(w, permuted).float()                  # [12, 2, 32, 4]
+        for j in (0, 5, 11):
+            for s in (0, 1):
+                for lane in (0, 7, 18, 31):
+                    g, t = lane // 4, lane % 4
+                    for e in range(4):
+                        half, lo = e // 2, e % 2
+                        k = (8 * t + 4 * s + 2 * half + lo) if permuted else (16 * s + 8 * half + 2 * t + lo)
+                        assert float(f[j, s, lane, e]) == float(w[8 * j + g, k])
+    # every (n, k) appears exactly once
+    assert sorted(_frag(w, True).float().reshape(-1).tolist()) == sorted(w.float().reshape(-1).tolist())
+
+
+def test_rank_sharding_matches_distributed_sampler():
+    from torch.utils.data import DistributedSampler
+    from deco_b200.data import ClassLabelRandomNDataset, rank_indices, seeded_noise
+    ds = ClassLabelRandomNDataset(latent_shape=(3, 8, 8), num_classes=10, max_num_instances=25)
+    for world in (1, 2, 4, 8):
+        for r in range(world):
+            ref = list(DistributedSampler(range(len(ds)), num_replicas=world, rank=r, shuffle=False))
+            assert rank_indices(len(ds), r, world) == ref
+    lat, cond, meta = ds[7]
+    assert cond == 7 // ds.num_seeds
+    ref = torch.randn((3, 8, 8), generator=torch.Generator().manual_seed(meta["seed"]))
+    assert torch.equal(lat, ref)
+    assert torch.equal(seeded_noise([meta["seed"]], (3, 8, 8), pin=False)[0], ref)
+
+
+def _gather_worker(rank, world, port, n_total, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from deco_b200 import distributed as D
+    from deco_b200.data import rank_indices
+    r, w, _ = D.init_from_env("gloo")
+    idx = rank_indices(n_total, r, w)
+    local = torch.tensor(idx, dtype=torch.uint8).view(-1, 1, 1, 1).expand(-1, 3, 2, 2).contiguous()
+    out = D.all_gather_images(local, w, total=n_total)
+    if r == 0:
+        ret.put(out[:, 0, 0, 0].tolist())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_all_gather_restores_global_order_gloo_world2():
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, 10, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = ret.get(timeout=120)
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert got == list(range(10))
