@@ -21,10 +21,10 @@ SIGNATURES = {
     "deco_patchify": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "deco_timestep_freq": (_i, [_vp, _vp, _i, _i, _f, _vp]),
     "deco_cond_combine": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
-    "deco_rmsnorm_modulate": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _vp, _ll, _i, _f, _vp]),
+    "deco_rmsnorm_modulate": (_i, [_vp, _i, _vp, _vp, _vp, _ll, _i, _vp, _ll, _i, _f, _vp]),
     "deco_qknorm_rope": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i, _i, _f, _vp]),
     "deco_attention_fwd": (_i, [_vp, _ll, _vp, _vp, _ll, _i, _vp, _vp, _ll, _i, _vp, _ll, _i, _i, _i, _i, _f, _vp]),
-    "deco_silu_add_rows": (_i, [_vp, _vp, _vp, _ll, _i, _i, _vp]),
+    "deco_silu_add_rows": (_i, [_vp, _i, _vp, _vp, _ll, _i, _i, _vp]),
     "deco_decoder_blob_bytes": (_i, [_i]),
     "deco_pixel_decoder": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "deco_cfg_step": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _f, _f, _f, _f, _f, _f, _vp, _vp, _vp, _vp, _ll, _vp]),

@@ -67,27 +67,39 @@ __global__ void cond_combine_kernel(const __nv_bfloat16* __restrict__ temb, cons
 
 // ---------------------------------------------------------------- h = rms(x) * w * (1 + scale) + shift
 // One warp per row; the row lives in registers between the two passes.  Hd % 8 == 0, Hd <= 2048.
-template <int kMaxChunks>
+// TIn = float: fp32 residual stream (no intermediate rounding); TIn = bf16: the reference's rounding points
+// (normalised value cast back to bf16, dit_c2i_DeCo.py:99; (1 + scale) evaluated as a bf16 op).
+template <typename TIn> __device__ __forceinline__ void load8(const TIn* p, float (&v)[8]);
+template <> __device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 q = ld_stream16(p);
+    const float2 a = unpack_bf2(q.x), b = unpack_bf2(q.y), c = unpack_bf2(q.z), d = unpack_bf2(q.w);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+template <> __device__ __forceinline__ void load8<float>(const float* p, float (&v)[8]) {
+    const uint4 a = ld_stream16(p), b = ld_stream16(p + 4);
+    v[0] = __uint_as_float(a.x); v[1] = __uint_as_float(a.y); v[2] = __uint_as_float(a.z); v[3] = __uint_as_float(a.w);
+    v[4] = __uint_as_float(b.x); v[5] = __uint_as_float(b.y); v[6] = __uint_as_float(b.z); v[7] = __uint_as_float(b.w);
+}
+
+template <typename TIn, int kMaxChunks>
 __global__ void __launch_bounds__(256) rmsnorm_modulate_kernel(
-    const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
+    const TIn* __restrict__ x, const float* __restrict__ w,
     const __nv_bfloat16* __restrict__ shift, const __nv_bfloat16* __restrict__ scale, long long mod_row_stride,
     int rows_per_mod, __nv_bfloat16* __restrict__ out, long long M, int Hd, float eps)
 {
+    constexpr bool kRefRounding = sizeof(TIn) == 2;
     const int lane = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= M) return;
     const int nch = Hd >> 3;
-    const uint4* xr = reinterpret_cast<const uint4*>(x + row * Hd);
+    const TIn* xr = x + row * Hd;
     float v[kMaxChunks][8];
     float ss = 0.f;
 #pragma unroll
     for (int j = 0; j < kMaxChunks; ++j) {
         const int ch = lane + j * 32;
         if (ch < nch) {
-            const uint4 q = ld_stream16(xr + ch);
-            const float2 a = unpack_bf2(q.x), b = unpack_bf2(q.y), c = unpack_bf2(q.z), d = unpack_bf2(q.w);
-            v[j][0] = a.x; v[j][1] = a.y; v[j][2] = b.x; v[j][3] = b.y;
-            v[j][4] = c.x; v[j][5] = c.y; v[j][6] = d.x; v[j][7] = d.y;
+            load8<TIn>(xr + ch * 8, v[j]);
 #pragma unroll
             for (int e = 0; e < 8; ++e) ss = fmaf(v[j][e], v[j][e], ss);
         }
@@ -111,10 +123,10 @@ __global__ void __launch_bounds__(256) rmsnorm_modulate_kernel(
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const float2 s2 = unpack_bf2(shw[e]), c2 = unpack_bf2(scw[e]);
-                // reference rounding points: normalised value cast back to bf16 (:99), (1 + scale) is a bf16 op
-                const float n0 = wv[2 * e] * round_bf(v[j][2 * e] * rs);
-                const float n1 = wv[2 * e + 1] * round_bf(v[j][2 * e + 1] * rs);
-                o[e] = pack_bf2(fmaf(n0, round_bf(1.0f + c2.x), s2.x), fmaf(n1, round_bf(1.0f + c2.y), s2.y));
+                float n0 = v[j][2 * e] * rs, n1 = v[j][2 * e + 1] * rs;
+                float m0 = 1.0f + c2.x, m1 = 1.0f + c2.y;
+                if (kRefRounding) { n0 = round_bf(n0); n1 = round_bf(n1); m0 = round_bf(m0); m1 = round_bf(m1); }
+                o[e] = pack_bf2(fmaf(wv[2 * e] * n0, m0, s2.x), fmaf(wv[2 * e + 1] * n1, m1, s2.y));
             }
             orow[ch] = make_uint4(o[0], o[1], o[2], o[3]);
         }
@@ -166,7 +178,8 @@ __global__ void __launch_bounds__(128) qknorm_rope_kernel(__nv_bfloat16* __restr
 }
 
 // ---------------------------------------------------------------- out[m, :] = silu(x[m, :] + row[m / rows_per][:])
-__global__ void __launch_bounds__(256) silu_add_rows_kernel(const __nv_bfloat16* __restrict__ x,
+template <typename TIn>
+__global__ void __launch_bounds__(256) silu_add_rows_kernel(const TIn* __restrict__ x,
                                                             const __nv_bfloat16* __restrict__ rowv,
                                                             __nv_bfloat16* __restrict__ out, long long M, int Hd,
                                                             int rows_per)
@@ -177,14 +190,22 @@ __global__ void __launch_bounds__(256) silu_add_rows_kernel(const __nv_bfloat16*
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
         const long long m = i / nch;
         const int ch = (int)(i % nch);
-        const uint4 a = reinterpret_cast<const uint4*>(x)[i];   // plain load: out may alias x
+        float a[8];
+        if (sizeof(TIn) == 2) {
+            const uint4 q = reinterpret_cast<const uint4*>(x)[i];   // plain load: out may alias x
+            const float2 p0 = unpack_bf2(q.x), p1 = unpack_bf2(q.y), p2 = unpack_bf2(q.z), p3 = unpack_bf2(q.w);
+            a[0] = p0.x; a[1] = p0.y; a[2] = p1.x; a[3] = p1.y; a[4] = p2.x; a[5] = p2.y; a[6] = p3.x; a[7] = p3.y;
+        } else {
+            const float4 q0 = reinterpret_cast<const float4*>(x)[2 * i], q1 = reinterpret_cast<const float4*>(x)[2 * i + 1];
+            a[0] = q0.x; a[1] = q0.y; a[2] = q0.z; a[3] = q0.w; a[4] = q1.x; a[5] = q1.y; a[6] = q1.z; a[7] = q1.w;
+        }
         const uint4 b = __ldg(reinterpret_cast<const uint4*>(rowv + (m / rows_per) * Hd) + ch);
-        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+        const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
         uint32_t o[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            const float2 p = unpack_bf2(aw[e]), q = unpack_bf2(bw[e]);
-            o[e] = pack_bf2(silu_f(round_bf(p.x + q.x)), silu_f(round_bf(p.y + q.y)));
+            const float2 q = unpack_bf2(bw[e]);
+            o[e] = pack_bf2(silu_f(a[2 * e] + q.x), silu_f(a[2 * e + 1] + q.y));
         }
         reinterpret_cast<uint4*>(out)[i] = make_uint4(o[0], o[1], o[2], o[3]);
     }
@@ -232,23 +253,24 @@ extern "C" int deco_cond_combine(const void* temb_bf16, const float* table, cons
     return DECO_OK;
 }
 
-extern "C" int deco_rmsnorm_modulate(const void* x_bf16, const float* weight, const void* shift_bf16,
+extern "C" int deco_rmsnorm_modulate(const void* x, int x_is_f32, const float* weight, const void* shift_bf16,
                                      const void* scale_bf16, long long mod_row_stride, int rows_per_mod,
                                      void* out_bf16, long long M, int hidden, float eps, void* stream) {
     using namespace deco;
-    DECO_CHECK_ARG(x_bf16 && weight && shift_bf16 && scale_bf16 && out_bf16, "rmsnorm_modulate: null pointer");
+    DECO_CHECK_ARG(x && weight && shift_bf16 && scale_bf16 && out_bf16, "rmsnorm_modulate: null pointer");
     DECO_CHECK_ARG(M > 0 && hidden % 8 == 0 && hidden <= 2048 && rows_per_mod > 0 && mod_row_stride % 8 == 0,
                    "rmsnorm_modulate: unsupported M=%lld hidden=%d", M, hidden);
     const int warps = 8;
     const unsigned grid = (unsigned)((M + warps - 1) / warps);
-    if (hidden <= 1280)
-        rmsnorm_modulate_kernel<5><<<grid, warps * 32, 0, (cudaStream_t)stream>>>(
-            (const __nv_bfloat16*)x_bf16, weight, (const __nv_bfloat16*)shift_bf16, (const __nv_bfloat16*)scale_bf16,
-            mod_row_stride, rows_per_mod, (__nv_bfloat16*)out_bf16, M, hidden, eps);
-    else
-        rmsnorm_modulate_kernel<8><<<grid, warps * 32, 0, (cudaStream_t)stream>>>(
-            (const __nv_bfloat16*)x_bf16, weight, (const __nv_bfloat16*)shift_bf16, (const __nv_bfloat16*)scale_bf16,
-            mod_row_stride, rows_per_mod, (__nv_bfloat16*)out_bf16, M, hidden, eps);
+    cudaStream_t st = (cudaStream_t)stream;
+    const __nv_bfloat16* sh = (const __nv_bfloat16*)shift_bf16;
+    const __nv_bfloat16* sc = (const __nv_bfloat16*)scale_bf16;
+    __nv_bfloat16* o = (__nv_bfloat16*)out_bf16;
+#define RMS_LAUNCH(T, C) rmsnorm_modulate_kernel<T, C><<<grid, warps * 32, 0, st>>>( \
+        (const T*)x, weight, sh, sc, mod_row_stride, rows_per_mod, o, M, hidden, eps)
+    if (x_is_f32) { if (hidden <= 1280) RMS_LAUNCH(float, 5); else RMS_LAUNCH(float, 8); }
+    else { if (hidden <= 1280) RMS_LAUNCH(__nv_bfloat16, 5); else RMS_LAUNCH(__nv_bfloat16, 8); }
+#undef RMS_LAUNCH
     DECO_CHECK_LAUNCH("rmsnorm_modulate_kernel");
     return DECO_OK;
 }
@@ -274,13 +296,17 @@ extern "C" int deco_qknorm_rope(void* qkv_bf16, const float* q_weight, const flo
     return DECO_OK;
 }
 
-extern "C" int deco_silu_add_rows(const void* x_bf16, const void* row_bf16, void* out_bf16, long long M, int hidden,
-                                  int rows_per, void* stream) {
+extern "C" int deco_silu_add_rows(const void* x, int x_is_f32, const void* row_bf16, void* out_bf16, long long M,
+                                  int hidden, int rows_per, void* stream) {
     using namespace deco;
-    DECO_CHECK_ARG(x_bf16 && row_bf16 && out_bf16 && M > 0 && hidden % 8 == 0 && rows_per > 0, "silu_add_rows: bad arguments");
+    DECO_CHECK_ARG(x && row_bf16 && out_bf16 && M > 0 && hidden % 8 == 0 && rows_per > 0, "silu_add_rows: bad arguments");
     const long long total = M * (hidden / 8);
-    silu_add_rows_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)x_bf16, (const __nv_bfloat16*)row_bf16, (__nv_bfloat16*)out_bf16, M, hidden, rows_per);
+    if (x_is_f32)
+        silu_add_rows_kernel<float><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+            (const float*)x, (const __nv_bfloat16*)row_bf16, (__nv_bfloat16*)out_bf16, M, hidden, rows_per);
+    else
+        silu_add_rows_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+            (const __nv_bfloat16*)x, (const __nv_bfloat16*)row_bf16, (__nv_bfloat16*)out_bf16, M, hidden, rows_per);
     DECO_CHECK_LAUNCH("silu_add_rows_kernel");
     return DECO_OK;
 }

@@ -28,15 +28,16 @@ constexpr int kAccStages = 2;
 enum GemmEpilogue : int {
     EPI_BIAS = 0,           // out = acc + bias
     EPI_BIAS_SILU = 1,      // out = silu(acc + bias)
-    EPI_GATE_RESIDUAL = 2,  // out = resid + gate[row / rows_per_gate] * (acc + bias)
+    EPI_GATE_RESIDUAL = 2,  // out = resid + gate[row / rows_per_gate] * (acc + bias); resid / out are FP32
     EPI_SWIGLU = 3,         // columns interleaved in 16s: out[:, n/2 + i] = silu(acc[n + i]) * acc[n + 16 + i]
+    EPI_BIAS_F32 = 4,       // out = acc + bias, FP32 output (starts the fp32 residual stream)
 };
 
 struct GemmParams {
-    void* out;                       // bf16 [M, ldo]
+    void* out;                       // [M, ldo] bf16 (fp32 for EPI_GATE_RESIDUAL / EPI_BIAS_F32)
     long long ldo;
     const float* bias;               // [N] fp32 or null
-    const __nv_bfloat16* resid;      // [M, ldr] (EPI_GATE_RESIDUAL)
+    const float* resid;              // [M, ldr] fp32 (EPI_GATE_RESIDUAL)
     long long ldr;
     const __nv_bfloat16* gate;       // [M / rows_per_gate, gate_stride]
     long long gate_stride;
@@ -177,27 +178,34 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& P, const uint32
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = silu_f(v[i]);
     }
-    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(P.out) + row * P.ldo + n0;
     if (EPI == EPI_GATE_RESIDUAL) {
-        const __nv_bfloat16* r = P.resid + row * P.ldr + n0;
+        // fp32 residual stream: x <- x + gate * (acc + bias); may run in place (out == resid)
+        float* o = reinterpret_cast<float*>(P.out) + row * P.ldo + n0;
+        const float* r = P.resid + row * P.ldr + n0;
         const __nv_bfloat16* gt = P.gate + (row / P.rows_per_gate) * P.gate_stride + n0;
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
             if (n0 + i < P.N) {
-                const uint4 rv = *reinterpret_cast<const uint4*>(r + i);
+                const float4 r0 = *reinterpret_cast<const float4*>(r + i);
+                const float4 r1 = *reinterpret_cast<const float4*>(r + i + 4);
                 const uint4 gv = __ldg(reinterpret_cast<const uint4*>(gt + i));
-                const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w}, gw[4] = {gv.x, gv.y, gv.z, gv.w};
-                uint32_t w[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float2 rr = unpack_bf2(rw[e]), gg = unpack_bf2(gw[e]);
-                    w[e] = pack_bf2(fmaf(gg.x, v[i + 2 * e], rr.x), fmaf(gg.y, v[i + 2 * e + 1], rr.y));
-                }
-                *reinterpret_cast<uint4*>(o + i) = make_uint4(w[0], w[1], w[2], w[3]);
+                const float2 g0 = unpack_bf2(gv.x), g1 = unpack_bf2(gv.y), g2 = unpack_bf2(gv.z), g3 = unpack_bf2(gv.w);
+                *reinterpret_cast<float4*>(o + i) = make_float4(fmaf(g0.x, v[i], r0.x), fmaf(g0.y, v[i + 1], r0.y),
+                                                                fmaf(g1.x, v[i + 2], r0.z), fmaf(g1.y, v[i + 3], r0.w));
+                *reinterpret_cast<float4*>(o + i + 4) = make_float4(fmaf(g2.x, v[i + 4], r1.x), fmaf(g2.y, v[i + 5], r1.y),
+                                                                    fmaf(g3.x, v[i + 6], r1.z), fmaf(g3.y, v[i + 7], r1.w));
             }
         }
         return;
     }
+    if (EPI == EPI_BIAS_F32) {
+        float* o = reinterpret_cast<float*>(P.out) + row * P.ldo + n0;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+            if (n0 + i < P.N) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        return;
+    }
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(P.out) + row * P.ldo + n0;
 #pragma unroll
     for (int i = 0; i < 32; i += 8) {
         if (n0 + i < P.N) {
@@ -376,6 +384,7 @@ static int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, c
         case EPI_BIAS_SILU: return launch_gemm<BN, EPI_BIAS_SILU>(ta, tb, P, max_ctas, st);
         case EPI_GATE_RESIDUAL: return launch_gemm<BN, EPI_GATE_RESIDUAL>(ta, tb, P, max_ctas, st);
         case EPI_SWIGLU: return launch_gemm<BN, EPI_SWIGLU>(ta, tb, P, max_ctas, st);
+        case EPI_BIAS_F32: return launch_gemm<BN, EPI_BIAS_F32>(ta, tb, P, max_ctas, st);
     }
     deco_set_error("gemm: unknown epilogue %d", epi);
     return DECO_ERR_ARG;
@@ -419,7 +428,7 @@ extern "C" int deco_gemm_bf16(const void* A, long long lda, const void* W, long 
     rc = make_tmap(&tb, W, N, K, ldw, bn);
     if (rc) return rc;
     GemmParams P;
-    P.out = out; P.ldo = ldo; P.bias = bias; P.resid = (const __nv_bfloat16*)resid; P.ldr = ldr;
+    P.out = out; P.ldo = ldo; P.bias = bias; P.resid = (const float*)resid; P.ldr = ldr;
     P.gate = (const __nv_bfloat16*)gate; P.gate_stride = gate_stride; P.rows_per_gate = rows_per_gate > 0 ? rows_per_gate : 1;
     P.M = M; P.N = N; P.K = K;
     const int ctas = num_sms();

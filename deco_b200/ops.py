@@ -12,8 +12,9 @@ import torch
 from . import _lib
 from ._lib import call, ptr
 
-EPI_BIAS, EPI_BIAS_SILU, EPI_GATE_RESIDUAL, EPI_SWIGLU = 0, 1, 2, 3
+EPI_BIAS, EPI_BIAS_SILU, EPI_GATE_RESIDUAL, EPI_SWIGLU, EPI_BIAS_F32 = 0, 1, 2, 3, 4
 bf16 = torch.bfloat16
+gemm_probe = None   # set to a deco_b200.utils.GemmProbe to time every GEMM launch with CUDA events
 
 
 def _cuda(*ts):
@@ -30,7 +31,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
          out: Optional[torch.Tensor] = None, resid: Optional[torch.Tensor] = None,
          gate: Optional[torch.Tensor] = None, rows_per_gate: int = 1, tile_n: int = 0) -> torch.Tensor:
     """out = epilogue(a @ w.T): a [M,K] bf16 (row stride allowed), w [N,K] bf16, bias fp32 [N].
-    gate: bf16 2-D view [M/rows_per_gate, N] with arbitrary row stride; resid bf16 [M,N]."""
+    gate: bf16 2-D view [M/rows_per_gate, N] with arbitrary row stride; resid fp32 [M,N].
+    Output is bf16 except for EPI_GATE_RESIDUAL / EPI_BIAS_F32 (the fp32 residual stream)."""
     _cuda(a, w, bias, out, resid, gate)
     assert a.dtype == bf16 and w.dtype == bf16 and a.dim() == 2 and w.dim() == 2
     assert a.stride(1) == 1 and w.stride(1) == 1
@@ -38,20 +40,25 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     N = w.shape[0]
     assert w.shape[1] == K, (a.shape, w.shape)
     n_out = N // 2 if epilogue == EPI_SWIGLU else N
+    odt = torch.float32 if epilogue in (EPI_GATE_RESIDUAL, EPI_BIAS_F32) else bf16
     if out is None:
-        out = torch.empty((M, n_out), dtype=bf16, device=a.device)
-    assert out.dtype == bf16 and out.shape == (M, n_out) and out.stride(1) == 1
+        out = torch.empty((M, n_out), dtype=odt, device=a.device)
+    assert out.dtype == odt and out.shape == (M, n_out) and out.stride(1) == 1
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() == N and bias.is_contiguous()
     ldr = gs = 0
     if epilogue == EPI_GATE_RESIDUAL:
         assert resid is not None and gate is not None
-        assert resid.dtype == bf16 and resid.shape == (M, N) and resid.stride(1) == 1
+        assert resid.dtype == torch.float32 and resid.shape == (M, N) and resid.stride(1) == 1
         assert gate.dtype == bf16 and gate.dim() == 2 and gate.shape[1] == N and gate.stride(1) == 1
         assert gate.shape[0] * rows_per_gate >= M
         ldr, gs = resid.stride(0), gate.stride(0)
+    probe = gemm_probe
+    ev = probe.before() if probe is not None else None
     call("deco_gemm_bf16", ptr(a), a.stride(0), ptr(w), w.stride(0), ptr(out), out.stride(0), M, N, K, epilogue,
          ptr(bias), ptr(resid), ldr, ptr(gate), gs, rows_per_gate, tile_n, _st(a))
+    if probe is not None:
+        probe.after(ev, 2.0 * M * N * K)
     return out
 
 
@@ -85,14 +92,14 @@ def cond_combine(temb: torch.Tensor, table: torch.Tensor, labels: torch.Tensor) 
 
 def rmsnorm_modulate(x: torch.Tensor, weight: torch.Tensor, shift: torch.Tensor, scale: torch.Tensor,
                      rows_per_mod: int, eps: float = 1e-6, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """x [M,H] bf16; shift/scale: bf16 views [M/rows_per_mod, H] sharing one row stride."""
+    """x [M,H] fp32 or bf16; shift/scale: bf16 views [M/rows_per_mod, H] sharing one row stride; out bf16."""
     _cuda(x, weight, shift, scale)
-    assert x.dtype == bf16 and x.is_contiguous() and weight.dtype == torch.float32
+    assert x.dtype in (bf16, torch.float32) and x.is_contiguous() and weight.dtype == torch.float32
     M, Hd = x.shape
     assert shift.stride(0) == scale.stride(0) and shift.stride(1) == 1 and scale.stride(1) == 1
     if out is None:
-        out = torch.empty_like(x)
-    call("deco_rmsnorm_modulate", ptr(x), ptr(weight), ptr(shift), ptr(scale), shift.stride(0), rows_per_mod,
+        out = torch.empty(x.shape, dtype=bf16, device=x.device)
+    call("deco_rmsnorm_modulate", ptr(x), int(x.dtype == torch.float32), ptr(weight), ptr(shift), ptr(scale), shift.stride(0), rows_per_mod,
          ptr(out), M, Hd, float(eps), _st(x))
     return out
 
@@ -131,10 +138,11 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, heads: 
 
 def silu_add_rows(x: torch.Tensor, row: torch.Tensor, rows_per: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _cuda(x, row)
-    assert x.dtype == bf16 and row.dtype == bf16 and x.is_contiguous() and row.is_contiguous()
+    assert x.dtype in (bf16, torch.float32) and row.dtype == bf16 and x.is_contiguous() and row.is_contiguous()
     if out is None:
-        out = torch.empty_like(x)
-    call("deco_silu_add_rows", ptr(x), ptr(row), ptr(out), x.shape[0], x.shape[1], rows_per, _st(x))
+        out = torch.empty(x.shape, dtype=bf16, device=x.device)
+    assert out.dtype == bf16
+    call("deco_silu_add_rows", ptr(x), int(x.dtype == torch.float32), ptr(row), ptr(out), x.shape[0], x.shape[1], rows_per, _st(x))
     return out
 
 

@@ -31,8 +31,9 @@ int deco_abi_version(void);
 /* GEMM epilogues */
 #define DECO_EPI_BIAS 0           /* out = A.W^T + bias                                  (nn.Linear)              */
 #define DECO_EPI_BIAS_SILU 1      /* out = silu(A.W^T + bias)                            (t_embedder.mlp[0:2])    */
-#define DECO_EPI_GATE_RESIDUAL 2  /* out = resid + gate[row / rows_per_gate] * (A.W^T + bias)                     */
+#define DECO_EPI_GATE_RESIDUAL 2  /* out = resid + gate[row / rows_per_gate] * (A.W^T + bias); resid, out FP32      */
 #define DECO_EPI_SWIGLU 3         /* W rows interleaved [16 x w1 | 16 x w3]: out[:, j] = silu(a_j) * b_j, N/2 cols */
+#define DECO_EPI_BIAS_F32 4       /* out = A.W^T + bias, FP32 output (head of the fp32 residual stream)           */
 
 /* tcgen05 / TMEM / TMA bf16 GEMM: out[M, N(or N/2)] = epilogue(A[M,K] . W[N,K]^T), fp32 accumulate.
  * Replaces nn.Linear at src/models/transformer/dit_c2i_DeCo.py:496 (s_embedder), :55-57 (t_embedder.mlp),
@@ -55,10 +56,11 @@ int deco_cond_combine(const void* temb_bf16, const float* table, const long long
                       int B, int hidden, int num_rows, void* stream);
 
 /* RMSNorm (dit_c2i_DeCo.py:94-99) + modulate (:11-12): out = w * rms(x) * (1 + scale) + shift.
- * shift/scale point into the batched adaLN output; row m uses modulation row m / rows_per_mod. */
-int deco_rmsnorm_modulate(const void* x_bf16, const float* weight, const void* shift_bf16, const void* scale_bf16,
-                          long long mod_row_stride, int rows_per_mod, void* out_bf16, long long M, int hidden,
-                          float eps, void* stream);
+ * shift/scale point into the batched adaLN output; row m uses modulation row m / rows_per_mod.
+ * x is the residual stream: fp32 (x_is_f32, the product path) or bf16 (the reference's rounding points). */
+int deco_rmsnorm_modulate(const void* x, int x_is_f32, const float* weight, const void* shift_bf16,
+                          const void* scale_bf16, long long mod_row_stride, int rows_per_mod, void* out_bf16,
+                          long long M, int hidden, float eps, void* stream);
 
 /* q_norm / k_norm + apply_rotary_emb (dit_c2i_DeCo.py:178-180, :134-145), in place on the QKV GEMM output
  * [M, 3*heads*head_dim]; rope_cos_sin: fp32 [L, head_dim/2, 2]; token position = row % L. head_dim in {64, 72}. */
@@ -76,7 +78,7 @@ int deco_attention_fwd(const void* q, long long q_stride,
                        int B, int heads, int Lq, int head_dim, float scale, void* stream);
 
 /* s = silu(t + s) (dit_c2i_DeCo.py:499): out[m,:] = silu(x[m,:] + row[m / rows_per,:]); out may alias x */
-int deco_silu_add_rows(const void* x_bf16, const void* row_bf16, void* out_bf16, long long M, int hidden,
+int deco_silu_add_rows(const void* x, int x_is_f32, const void* row_bf16, void* out_bf16, long long M, int hidden,
                        int rows_per, void* stream);
 
 /* NerfEmbedder + SimpleMLPAdaLN + fold (dit_c2i_DeCo.py:212-248, :288-415, :501-509).

@@ -50,14 +50,16 @@ def test_gemm_gate_residual(cuda_dev, M, N, K, L, tile_n):
     from deco_b200 import ops
     a, w = _rand((M, K), cuda_dev, 1), _rand((N, K), cuda_dev, 2, K ** -0.5)
     bias = _rand((N,), cuda_dev, 3, 0.1, torch.float32)
-    resid = _rand((M, N), cuda_dev, 4)
+    resid = _rand((M, N), cuda_dev, 4, dtype=torch.float32)
     nb = (M + L - 1) // L
     mod = _rand((nb, 6 * N), cuda_dev, 5)
     gate = mod[:, 2 * N:3 * N]
     ref = resid.float() + gate.float().repeat_interleave(L, 0)[:M] * (a.float() @ w.float().t() + bias)
     out = resid.clone()
     ops.gemm(a, w, bias, ops.EPI_GATE_RESIDUAL, out=out, resid=out, gate=gate, rows_per_gate=L, tile_n=tile_n)
-    assert rel_l2(out.float(), ref) < 4e-3
+    assert out.dtype == torch.float32 and rel_l2(out, ref) < 1e-5        # fp32 accumulate, fp32 residual stream
+    o32 = ops.gemm(a, w, bias, ops.EPI_BIAS_F32, tile_n=tile_n)
+    assert o32.dtype == torch.float32 and rel_l2(o32, a.float() @ w.float().t() + bias) < 1e-5
 
 
 @pytest.mark.parametrize("M,F_,K,tile_n", [(256, 3072, 1152, 0), (130, 2736, 1024, 0), (256, 512, 256, 128)])
@@ -93,11 +95,12 @@ def test_timestep_and_cond(cuda_dev):
     assert rel_l2(ops.cond_combine(temb, table, y).float(), ref) < 4e-3
 
 
+@pytest.mark.parametrize("xdt", [torch.float32, bf16])
 @pytest.mark.parametrize("H", [1152, 1024, 576, 1536])
-def test_rmsnorm_modulate(cuda_dev, H):
+def test_rmsnorm_modulate(cuda_dev, H, xdt):
     from deco_b200 import ops
     M, L = 96, 16
-    x = _rand((M, H), cuda_dev, 1, 2.0)
+    x = _rand((M, H), cuda_dev, 1, 2.0, dtype=xdt)
     w = 1 + 0.1 * _rand((H,), cuda_dev, 2, dtype=torch.float32)
     mod = _rand((M // L, 6 * H), cuda_dev, 3, 0.5)
     sh, sc = mod[:, :H], mod[:, H:2 * H]
@@ -152,6 +155,7 @@ def test_silu_add_rows(cuda_dev):
     x, row = _rand((64, 256), cuda_dev, 1), _rand((4, 256), cuda_dev, 2)
     ref = F.silu((x + row.repeat_interleave(16, 0)).float())
     assert rel_l2(ops.silu_add_rows(x, row, 16).float(), ref) < 4e-3
+    assert rel_l2(ops.silu_add_rows(x.float(), row, 16).float(), ref) < 4e-3   # fp32 residual stream input
     assert rel_l2(ops.silu_add_rows(x, row, 16, out=x).float(), ref) < 4e-3   # in place
 
 

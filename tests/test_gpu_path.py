@@ -29,6 +29,29 @@ def test_denoiser_forward_vs_reference_golden(cuda_dev, name):
     assert rel_l2(O.denoiser_forward(Pd, cfg, x, t, y), ref) < 1e-4
 
 
+def test_xl16_forward_vs_oracle(cuda_dev):
+    """The benchmark architecture itself (DeCo-XL/16, 28 blocks, head_dim 72) at a size the fp32 oracle finishes in
+    seconds on the GPU: 2 CFG rows of 256 x 256.  Tolerance (north_star): rel-L2 <= 1e-2."""
+    cfg = O.CFG_XL
+    m, P = build_module(cfg, cuda_dev)
+    Pd = {k: v.to(cuda_dev) for k, v in P.items()}
+    x = seeded_noise(1, (3, 256, 256), 3).to(cuda_dev).repeat(2, 1, 1, 1)
+    t = torch.tensor([0.37, 0.37], device=cuda_dev)
+    y = torch.tensor([1000, 207], device=cuda_dev)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        ref = O.denoiser_forward(Pd, cfg, x, t, y)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            ref_bf = O.denoiser_forward(Pd, cfg, x, t, y).float()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    out = m(x, t, y)
+    e, floor = rel_l2(out.float(), ref), rel_l2(ref_bf, ref)
+    print(f"XL/16: rel-L2 vs fp32 oracle = {e:.3e}; torch bf16-autocast (the reference's numerics) vs fp32 = {floor:.3e}")
+    assert e <= 1e-2
+
+
 def test_pixel_decoder_alone(cuda_dev):
     """forward(x, t, y, s=...) skips the DiT (dit_c2i_DeCo.py:495): isolates cond_embed GEMM + fused decoder."""
     cfg = O.DenoiserCfg(num_groups=4, hidden_size=256, num_blocks=5, num_cond_blocks=2, num_classes=10)
