@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-steps", type=int, default=2)
+    ap.add_argument("--profile", action="store_true",
+                    help="bracket the timed steps with cudaProfilerStart/Stop (use with ncu --profile-from-start off)")
     return ap.parse_args()
 
 
@@ -205,11 +207,15 @@ def run_deco(args):
     launches0 = _lib.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
+        if args.profile:
+            torch.cuda.profiler.start()
         e0.record()
         for i in range(args.steps):
             x = one_step(x, args.warmup + i)
         e1.record()
         barrier()
+        if args.profile:
+            torch.cuda.profiler.stop()
     ops.gemm_probe = None
     launches = _lib.launch_count - launches0
     ms_total = e0.elapsed_time(e1)

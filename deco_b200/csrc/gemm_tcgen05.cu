@@ -144,75 +144,79 @@ template <int BN> struct GemmCfg {
     static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
     static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 192 ? 5 : 6);
     static constexpr int kTmemCols = (kAccStages * BN > 256) ? 512 : 256;
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int kEpiStageBytes = 4 * 32 * 36 * 4;   // 4 epilogue warps x [32][36] fp32
+    static constexpr int kSmemBytes = kStages * kStageBytes + kEpiStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-// ------------------------------------------------------------------ epilogue math on one 32-column chunk
+// ------------------------------------------------------------------ epilogue on one 32-column chunk
+// A warp owns 32 tile rows (TMEM lanes).  tcgen05.ld hands each thread one ROW of the chunk, which would make every
+// global access row-strided (32 cache lines per instruction).  So the raw fp32 accumulators go through a per-warp
+// shared-memory staging tile [32 rows][36 floats] (conflict-free for 128-bit accesses in both directions) and the
+// global side runs with lane = (row % 4 rows, 4 consecutive columns): 8 lanes cover 128 contiguous bytes of a row.
+constexpr int kStageLd = 36;
+constexpr int kStageFloatsPerWarp = 32 * kStageLd;
+
 template <int EPI>
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& P, const uint32_t (&acc)[32], long long row, int n0) {
-    float v[32];
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& P, const uint32_t (&acc)[32], float* stg,
+                                               long long row0, int n0, int lane) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
-    if (P.bias) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-            if (n0 + i < P.N) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(P.bias + n0 + i));
-                v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
-            }
-        }
-    }
+    for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(stg + lane * kStageLd + 4 * j) =
+            make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]),
+                        __uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3]));
+    __syncwarp();
+    const int cg = lane & 7, rsub = lane >> 3;
     if (EPI == EPI_SWIGLU) {
-        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(P.out) + row * P.ldo + (n0 >> 1);
-        if (n0 < P.N) {
-            uint32_t w[8];
+        // chunk = [16 x w1-columns | 16 x w3-columns]; lanes 0..3 of each row group produce 4 outputs each
+        const int no = (n0 >> 1) + 4 * cg;
+        if (cg < 4 && n0 + 4 * cg < P.N) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-                w[i] = pack_bf2(silu_f(v[2 * i]) * v[16 + 2 * i], silu_f(v[2 * i + 1]) * v[16 + 2 * i + 1]);
-            *reinterpret_cast<uint4*>(o) = make_uint4(w[0], w[1], w[2], w[3]);
-            *reinterpret_cast<uint4*>(o + 8) = make_uint4(w[4], w[5], w[6], w[7]);
-        }
-        return;
-    }
-    if (EPI == EPI_BIAS_SILU) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = silu_f(v[i]);
-    }
-    if (EPI == EPI_GATE_RESIDUAL) {
-        // fp32 residual stream: x <- x + gate * (acc + bias); may run in place (out == resid)
-        float* o = reinterpret_cast<float*>(P.out) + row * P.ldo + n0;
-        const float* r = P.resid + row * P.ldr + n0;
-        const __nv_bfloat16* gt = P.gate + (row / P.rows_per_gate) * P.gate_stride + n0;
-#pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-            if (n0 + i < P.N) {
-                const float4 r0 = *reinterpret_cast<const float4*>(r + i);
-                const float4 r1 = *reinterpret_cast<const float4*>(r + i + 4);
-                const uint4 gv = __ldg(reinterpret_cast<const uint4*>(gt + i));
-                const float2 g0 = unpack_bf2(gv.x), g1 = unpack_bf2(gv.y), g2 = unpack_bf2(gv.z), g3 = unpack_bf2(gv.w);
-                *reinterpret_cast<float4*>(o + i) = make_float4(fmaf(g0.x, v[i], r0.x), fmaf(g0.y, v[i + 1], r0.y),
-                                                                fmaf(g1.x, v[i + 2], r0.z), fmaf(g1.y, v[i + 3], r0.w));
-                *reinterpret_cast<float4*>(o + i + 4) = make_float4(fmaf(g2.x, v[i + 4], r1.x), fmaf(g2.y, v[i + 5], r1.y),
-                                                                    fmaf(g3.x, v[i + 6], r1.z), fmaf(g3.y, v[i + 7], r1.w));
+            for (int it = 0; it < 8; ++it) {
+                const int r = it * 4 + rsub;
+                const long long row = row0 + r;
+                const float4 a = *reinterpret_cast<const float4*>(stg + r * kStageLd + 4 * cg);
+                const float4 b = *reinterpret_cast<const float4*>(stg + r * kStageLd + 16 + 4 * cg);
+                if (row < P.M) {
+                    uint2 w;
+                    w.x = pack_bf2(silu_f(a.x) * b.x, silu_f(a.y) * b.y);
+                    w.y = pack_bf2(silu_f(a.z) * b.z, silu_f(a.w) * b.w);
+                    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(P.out) + row * P.ldo + no) = w;
+                }
             }
         }
+        __syncwarp();
         return;
     }
-    if (EPI == EPI_BIAS_F32) {
-        float* o = reinterpret_cast<float*>(P.out) + row * P.ldo + n0;
+    const int n = n0 + 4 * cg;
+    if (n < P.N) {
+        float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (P.bias) bz = __ldg(reinterpret_cast<const float4*>(P.bias + n));
 #pragma unroll
-        for (int i = 0; i < 32; i += 4)
-            if (n0 + i < P.N) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-        return;
-    }
-    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(P.out) + row * P.ldo + n0;
-#pragma unroll
-    for (int i = 0; i < 32; i += 8) {
-        if (n0 + i < P.N) {
-            *reinterpret_cast<uint4*>(o + i) = make_uint4(pack_bf2(v[i], v[i + 1]), pack_bf2(v[i + 2], v[i + 3]),
-                                                          pack_bf2(v[i + 4], v[i + 5]), pack_bf2(v[i + 6], v[i + 7]));
+        for (int it = 0; it < 8; ++it) {
+            const int r = it * 4 + rsub;
+            const long long row = row0 + r;
+            float4 v = *reinterpret_cast<const float4*>(stg + r * kStageLd + 4 * cg);
+            v.x += bz.x; v.y += bz.y; v.z += bz.z; v.w += bz.w;
+            if (row < P.M) {
+                if (EPI == EPI_GATE_RESIDUAL) {
+                    // fp32 residual stream: x <- x + gate * (acc + bias); may run in place (out == resid)
+                    const float4 rv = *reinterpret_cast<const float4*>(P.resid + row * P.ldr + n);
+                    const uint2 gv = __ldg(reinterpret_cast<const uint2*>(P.gate + (row / P.rows_per_gate) * P.gate_stride + n));
+                    const float2 g0 = unpack_bf2(gv.x), g1 = unpack_bf2(gv.y);
+                    *reinterpret_cast<float4*>(reinterpret_cast<float*>(P.out) + row * P.ldo + n) =
+                        make_float4(fmaf(g0.x, v.x, rv.x), fmaf(g0.y, v.y, rv.y), fmaf(g1.x, v.z, rv.z), fmaf(g1.y, v.w, rv.w));
+                } else if (EPI == EPI_BIAS_F32) {
+                    *reinterpret_cast<float4*>(reinterpret_cast<float*>(P.out) + row * P.ldo + n) = v;
+                } else {
+                    if (EPI == EPI_BIAS_SILU) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
+                    uint2 w;
+                    w.x = pack_bf2(v.x, v.y); w.y = pack_bf2(v.z, v.w);
+                    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(P.out) + row * P.ldo + n) = w;
+                }
+            }
         }
     }
+    __syncwarp();
 }
 
 // ------------------------------------------------------------------ kernel
@@ -225,7 +229,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte alignment is required by the 128-byte swizzle atom (8 rows x 128 B)
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+    const uint32_t epi_stage_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
+    const uint32_t bar_base = epi_stage_base + Cfg::kEpiStageBytes;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::kStages + s); };
     auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * Cfg::kStages + s); };
@@ -305,15 +310,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             const int m_blk = tile / num_n, n_blk = tile % num_n;
             mbar_wait(tfull_bar(as), aphase);
             tc_fence_after();
-            const long long row = (long long)m_blk * kBM + q * 32 + lane;
+            const long long row0 = (long long)m_blk * kBM + q * 32;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+            float* stg = reinterpret_cast<float*>(smem_raw + (epi_stage_base - smem_u32(smem_raw))) + q * kStageFloatsPerWarp;
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
                 uint32_t acc[32];
                 tmem_ld32(taddr + (uint32_t)(c * 32), acc);
                 tmem_ld_wait();
                 const int n0 = n_blk * BN + c * 32;
-                if (row < P.M && n0 < P.N) epilogue_chunk<EPI>(P, acc, row, n0);
+                if (row0 < P.M && n0 < P.N) epilogue_chunk<EPI>(P, acc, stg, row0, n0, lane);   // warp-uniform guard
             }
             tc_fence_before();
             __syncwarp();
