@@ -1,6 +1,11 @@
 // Persistent, warp-specialised bf16 GEMM for sm_100a:  D[M,N] = epilogue(A[M,K] . W[N,K]^T)
 //   * operands staged by TMA (cp.async.bulk.tensor, 128-byte swizzle) into a multi-stage shared-memory ring,
-//   * tcgen05.mma (cta_group::1, M=128, N=BN, K=16, kind::f16, bf16 in / fp32 accumulate) issued by one thread,
+//   * tcgen05.mma (kind::f16, bf16 in / fp32 accumulate, K=16) issued by one thread:
+//       cta_group::2 (default): a CTA PAIR (2-CTA cluster = one TPC) computes a 256 x BN tile; each CTA stages its own
+//                      128 rows of A and HALF of the W tile, the leader's MMA reads both CTAs' shared memory.  Versus
+//                      cta_group::1 this cuts L2->SMEM traffic per MAC by 1/3 and the per-SM operand read rate from
+//                      ~100 to 64 B/clk (the 128 B/clk SMEM port is what throttled the 1-CTA version),
+//       cta_group::1: 128 x BN tile per CTA (kept for M <= 128 and as the A/B reference),
 //   * accumulators in TMEM, double buffered (2 x BN columns) so the epilogue of tile i overlaps the MMAs of tile i+1,
 //   * epilogue warps read TMEM with tcgen05.ld and fuse bias / SiLU / AdaLN gate + residual / SwiGLU.
 //
@@ -120,6 +125,52 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+
+// ---- cluster / 2-CTA variants
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local_addr` in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t local_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
+}
+// TMA load whose completion bytes are credited to a barrier that may live in the PEER CTA of the pair
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        :: "r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_dst), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// completion of all prior MMAs -> arrive on the barrier at the same offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(bar), "h"((uint16_t)3) : "memory");
+}
+
 // K-major, 128-byte-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 //   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (unused for swizzled K-major, 1) |
 //   [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024 B -> 64) | [46,48) version = 1 | [61,64) layout = 2 (SW128)
@@ -138,27 +189,30 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-template <int BN> struct GemmCfg {
-    static constexpr int kStageBytesA = kBM * kBK * 2;
-    static constexpr int kStageBytesB = BN * kBK * 2;
+template <int BN, int CG> struct GemmCfg {
+    static constexpr int kStageBytesA = kBM * kBK * 2;               // this CTA's 128 rows of A
+    static constexpr int kStageBytesB = (BN / CG) * kBK * 2;         // this CTA's share of the W tile
     static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
-    static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 192 ? 5 : 6);
+    static constexpr int kEpiStageBytes = 4 * 32 * 36 * 4;           // 4 epilogue warps x [32][36] fp32
+    static constexpr int kBudget = 227 * 1024 - kEpiStageBytes - 1024 - 256;
+    static constexpr int kStagesRaw = kBudget / kStageBytes;
+    static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
     static constexpr int kTmemCols = (kAccStages * BN > 256) ? 512 : 256;
-    static constexpr int kEpiStageBytes = 4 * 32 * 36 * 4;   // 4 epilogue warps x [32][36] fp32
     static constexpr int kSmemBytes = kStages * kStageBytes + kEpiStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 // ------------------------------------------------------------------ epilogue on one 32-column chunk
-// A warp owns 32 tile rows (TMEM lanes).  tcgen05.ld hands each thread one ROW of the chunk, which would make every
-// global access row-strided (32 cache lines per instruction).  So the raw fp32 accumulators go through a per-warp
-// shared-memory staging tile [32 rows][36 floats] (conflict-free for 128-bit accesses in both directions) and the
-// global side runs with lane = (row % 4 rows, 4 consecutive columns): 8 lanes cover 128 contiguous bytes of a row.
+// A warp owns 32 tile rows (TMEM lanes); tcgen05.ld 32x32b hands each thread one ROW of the chunk.
+//   direct : each thread reads/writes its own row (row-strided 16-byte accesses, 32 cache lines per instruction).
+//   staged : raw fp32 accumulators go through a per-warp shared-memory tile [32 rows][36 floats] (conflict-free for
+//            128-bit accesses both ways) and the global side runs with lane = (row % 4, 4 consecutive columns): 8 lanes
+//            cover 128 contiguous bytes of a row.  Costs SMEM bandwidth, which only the 2-CTA MMA has to spare.
 constexpr int kStageLd = 36;
 constexpr int kStageFloatsPerWarp = 32 * kStageLd;
 
 template <int EPI>
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& P, const uint32_t (&acc)[32], float* stg,
-                                               long long row0, int n0, int lane) {
+__device__ __forceinline__ void epilogue_chunk_staged(const GemmParams& P, const uint32_t (&acc)[32], float* stg,
+                                                      long long row0, int n0, int lane) {
 #pragma unroll
     for (int j = 0; j < 8; ++j)
         *reinterpret_cast<float4*>(stg + lane * kStageLd + 4 * j) =
@@ -219,15 +273,81 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& P, const uint32
     __syncwarp();
 }
 
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk_direct(const GemmParams& P, const uint32_t (&acc)[32], long long row, int n0) {
+    if (row >= P.M) return;
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
+    if (P.bias) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+            if (n0 + i < P.N) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(P.bias + n0 + i));
+                v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+            }
+        }
+    }
+    if (EPI == EPI_SWIGLU) {
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(P.out) + row * P.ldo + (n0 >> 1);
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            w[i] = pack_bf2(silu_f(v[2 * i]) * v[16 + 2 * i], silu_f(v[2 * i + 1]) * v[16 + 2 * i + 1]);
+        *reinterpret_cast<uint4*>(o) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(o + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+        return;
+    }
+    if (EPI == EPI_GATE_RESIDUAL) {
+        float* o = reinterpret_cast<float*>(P.out) + row * P.ldo + n0;
+        const float* r = P.resid + row * P.ldr + n0;
+        const __nv_bfloat16* gt = P.gate + (row / P.rows_per_gate) * P.gate_stride + n0;
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+            if (n0 + i < P.N) {
+                const float4 r0 = *reinterpret_cast<const float4*>(r + i);
+                const float4 r1 = *reinterpret_cast<const float4*>(r + i + 4);
+                const uint4 gv = __ldg(reinterpret_cast<const uint4*>(gt + i));
+                const float2 g0 = unpack_bf2(gv.x), g1 = unpack_bf2(gv.y), g2 = unpack_bf2(gv.z), g3 = unpack_bf2(gv.w);
+                *reinterpret_cast<float4*>(o + i) = make_float4(fmaf(g0.x, v[i], r0.x), fmaf(g0.y, v[i + 1], r0.y),
+                                                                fmaf(g1.x, v[i + 2], r0.z), fmaf(g1.y, v[i + 3], r0.w));
+                *reinterpret_cast<float4*>(o + i + 4) = make_float4(fmaf(g2.x, v[i + 4], r1.x), fmaf(g2.y, v[i + 5], r1.y),
+                                                                    fmaf(g3.x, v[i + 6], r1.z), fmaf(g3.y, v[i + 7], r1.w));
+            }
+        }
+        return;
+    }
+    if (EPI == EPI_BIAS_F32) {
+        float* o = reinterpret_cast<float*>(P.out) + row * P.ldo + n0;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+            if (n0 + i < P.N) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        return;
+    }
+    if (EPI == EPI_BIAS_SILU) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = silu_f(v[i]);
+    }
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(P.out) + row * P.ldo + n0;
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+        if (n0 + i < P.N) {
+            *reinterpret_cast<uint4*>(o + i) = make_uint4(pack_bf2(v[i], v[i + 1]), pack_bf2(v[i + 2], v[i + 3]),
+                                                          pack_bf2(v[i + 4], v[i + 5]), pack_bf2(v[i + 6], v[i + 7]));
+        }
+    }
+}
+
 // ------------------------------------------------------------------ kernel
-template <int BN, int EPI>
+// CG = 1: one CTA per 128 x BN tile.   CG = 2: a 2-CTA cluster per 256 x BN tile (rank 0 = leader issues the MMAs).
+template <int BN, int EPI, int CG, bool STAGED>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const GemmParams P)
 {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, CG>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // 1024-byte alignment is required by the 128-byte swizzle atom (8 rows x 128 B)
+    // 1024-byte alignment is required by the 128-byte swizzle atom (8 rows x 128 B); identical offsets in both CTAs
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t epi_stage_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
     const uint32_t bar_base = epi_stage_base + Cfg::kEpiStageBytes;
@@ -239,9 +359,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int num_m = (P.M + kBM - 1) / kBM, num_n = (P.N + BN - 1) / BN;
+    const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+    const bool is_leader = cta_rank == 0;
+    const int num_m = (P.M + kBM * CG - 1) / (kBM * CG), num_n = (P.N + BN - 1) / BN;
     const int num_tiles = num_m * num_n;
     const int num_k = (P.K + kBK - 1) / kBK;
+    const int tile0 = blockIdx.x / CG, tile_stride = gridDim.x / CG;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
@@ -249,40 +372,53 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < kAccStages; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+        for (int s = 0; s < kAccStages; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4 * CG); }
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    if (warp == 2) {
+        if (CG == 2) tmem_alloc_2sm(tmem_slot, Cfg::kTmemCols);
+        else tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    }
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
+        // ===================== TMA producer (every CTA loads its own A rows and its share of W) =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = tile0; tile < num_tiles; tile += tile_stride) {
                 const int m_blk = tile / num_n, n_blk = tile % num_n;
+                const int arow = (m_blk * CG + (int)cta_rank) * kBM;
+                const int brow = n_blk * BN + (int)cta_rank * (BN / CG);
                 for (int kb = 0; kb < num_k; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
                     const uint32_t sb = sa + Cfg::kStageBytesA;
-                    mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
-                    tma_load_2d(sa, &tmap_a, full_bar(stage), kb * kBK, m_blk * kBM);
-                    tma_load_2d(sb, &tmap_b, full_bar(stage), kb * kBK, n_blk * BN);
+                    if (CG == 1) {
+                        mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
+                        tma_load_2d(sa, &tmap_a, full_bar(stage), kb * kBK, arow);
+                        tma_load_2d(sb, &tmap_b, full_bar(stage), kb * kBK, brow);
+                    } else {
+                        // both CTAs' bytes are credited to the LEADER's full barrier, which expects the pair's total
+                        if (is_leader) mbar_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
+                        const uint32_t fb = mapa_shared(full_bar(stage), 0);
+                        tma_load_2d_2sm(sa, &tmap_a, fb, kb * kBK, arow);
+                        tma_load_2d_2sm(sb, &tmap_b, fb, kb * kBK, brow);
+                    }
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(kBM, BN);
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (lane == 0 && is_leader) {
+            constexpr uint32_t idesc = make_idesc(kBM * CG, BN);
             int stage = 0; uint32_t phase = 0;
             int as = 0; uint32_t aphase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                mbar_wait(tempty_bar(as), aphase ^ 1);   // epilogue has drained this accumulator stage
+            for (int tile = tile0; tile < num_tiles; tile += tile_stride) {
+                mbar_wait(tempty_bar(as), aphase ^ 1);   // epilogues (of both CTAs) have drained this accumulator stage
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
                 for (int kb = 0; kb < num_k; ++kb) {
@@ -293,44 +429,55 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #pragma unroll
                     for (int k = 0; k < kBK / kUmmaK; ++k) {
                         // advance 16 elements = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
-                        umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+                        if (CG == 2) umma_bf16_2sm(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+                        else umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
                     }
-                    umma_commit(empty_bar(stage));       // frees the smem stage once these MMAs retire
+                    // frees the smem stage (in both CTAs) once these MMAs retire
+                    if (CG == 2) umma_commit_2sm(empty_bar(stage)); else umma_commit(empty_bar(stage));
                     if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(tfull_bar(as));              // accumulator complete -> epilogue
+                if (CG == 2) umma_commit_2sm(tfull_bar(as)); else umma_commit(tfull_bar(as));   // accumulator -> epilogue
                 if (++as == kAccStages) { as = 0; aphase ^= 1; }
             }
         }
     } else if (warp >= kEpiWarp0) {
-        // ===================== epilogue =====================
+        // ===================== epilogue (each CTA drains its own 128 accumulator rows) =====================
         const int q = warp & 3;                          // TMEM lane quarter this warp may access
         int as = 0; uint32_t aphase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        float* stg = reinterpret_cast<float*>(smem_raw + (epi_stage_base - smem_u32(smem_raw))) + q * kStageFloatsPerWarp;
+        for (int tile = tile0; tile < num_tiles; tile += tile_stride) {
             const int m_blk = tile / num_n, n_blk = tile % num_n;
             mbar_wait(tfull_bar(as), aphase);
             tc_fence_after();
-            const long long row0 = (long long)m_blk * kBM + q * 32;
+            const long long row0 = (long long)(m_blk * CG + (int)cta_rank) * kBM + q * 32;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
-            float* stg = reinterpret_cast<float*>(smem_raw + (epi_stage_base - smem_u32(smem_raw))) + q * kStageFloatsPerWarp;
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
                 uint32_t acc[32];
                 tmem_ld32(taddr + (uint32_t)(c * 32), acc);
                 tmem_ld_wait();
                 const int n0 = n_blk * BN + c * 32;
-                if (row0 < P.M && n0 < P.N) epilogue_chunk<EPI>(P, acc, stg, row0, n0, lane);   // warp-uniform guard
+                if (row0 < P.M && n0 < P.N) {             // warp-uniform guard
+                    if (STAGED) epilogue_chunk_staged<EPI>(P, acc, stg, row0, n0, lane);
+                    else epilogue_chunk_direct<EPI>(P, acc, row0 + lane, n0);
+                }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(as));
+            if (lane == 0) {
+                if (CG == 2) mbar_arrive_cluster(mapa_shared(tempty_bar(as), 0));
+                else mbar_arrive(tempty_bar(as));
+            }
             if (++as == kAccStages) { as = 0; aphase ^= 1; }
         }
     }
 
     tc_fence_before();
-    __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
+    if (warp == 2) {
+        if (CG == 2) tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
+        else tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    }
 }
 
 // ------------------------------------------------------------------ host side
@@ -366,35 +513,59 @@ static int make_tmap(CUtensorMap* map, const void* ptr, long long rows, long lon
     return DECO_OK;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CG, bool STAGED>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& P, int max_ctas, cudaStream_t st) {
-    using Cfg = GemmCfg<BN>;
-    static bool attr_done = false;   // per (BN, EPI) instantiation
+    using Cfg = GemmCfg<BN, CG>;
+    auto kern = gemm_bf16_tcgen05_kernel<BN, EPI, CG, STAGED>;
+    static bool attr_done = false;   // per instantiation
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, EPI>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
         if (e != cudaSuccess) { deco_set_error("gemm smem attr: %s", cudaGetErrorString(e)); return (int)e; }
         attr_done = true;
     }
-    const int tiles = ((P.M + kBM - 1) / kBM) * ((P.N + BN - 1) / BN);
-    int grid = tiles < max_ctas ? tiles : max_ctas;
-    gemm_bf16_tcgen05_kernel<BN, EPI><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(ta, tb, P);
-    DECO_CHECK_LAUNCH("gemm_bf16_tcgen05_kernel");
+    const int tiles = ((P.M + kBM * CG - 1) / (kBM * CG)) * ((P.N + BN - 1) / BN);
+    int groups = max_ctas / CG;
+    if (tiles < groups) groups = tiles;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(groups * CG);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, P);
+    if (e != cudaSuccess) { deco_set_error("gemm launch failed: %s", cudaGetErrorString(e)); return (int)e; }
     return DECO_OK;
 }
 
-template <int BN>
+template <int BN, int CG, bool STAGED>
 static int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& P, int max_ctas, cudaStream_t st) {
     switch (epi) {
-        case EPI_BIAS: return launch_gemm<BN, EPI_BIAS>(ta, tb, P, max_ctas, st);
-        case EPI_BIAS_SILU: return launch_gemm<BN, EPI_BIAS_SILU>(ta, tb, P, max_ctas, st);
-        case EPI_GATE_RESIDUAL: return launch_gemm<BN, EPI_GATE_RESIDUAL>(ta, tb, P, max_ctas, st);
-        case EPI_SWIGLU: return launch_gemm<BN, EPI_SWIGLU>(ta, tb, P, max_ctas, st);
-        case EPI_BIAS_F32: return launch_gemm<BN, EPI_BIAS_F32>(ta, tb, P, max_ctas, st);
+        case EPI_BIAS: return launch_gemm<BN, EPI_BIAS, CG, STAGED>(ta, tb, P, max_ctas, st);
+        case EPI_BIAS_SILU: return launch_gemm<BN, EPI_BIAS_SILU, CG, STAGED>(ta, tb, P, max_ctas, st);
+        case EPI_GATE_RESIDUAL: return launch_gemm<BN, EPI_GATE_RESIDUAL, CG, STAGED>(ta, tb, P, max_ctas, st);
+        case EPI_SWIGLU: return launch_gemm<BN, EPI_SWIGLU, CG, STAGED>(ta, tb, P, max_ctas, st);
+        case EPI_BIAS_F32: return launch_gemm<BN, EPI_BIAS_F32, CG, STAGED>(ta, tb, P, max_ctas, st);
     }
     deco_set_error("gemm: unknown epilogue %d", epi);
     return DECO_ERR_ARG;
 }
+
+template <int BN>
+static int dispatch_variant(int cg, int staged, int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& P,
+                            int max_ctas, cudaStream_t st) {
+    if (cg == 2) return staged ? dispatch_epi<BN, 2, true>(epi, ta, tb, P, max_ctas, st)
+                               : dispatch_epi<BN, 2, false>(epi, ta, tb, P, max_ctas, st);
+    return staged ? dispatch_epi<BN, 1, true>(epi, ta, tb, P, max_ctas, st)
+                  : dispatch_epi<BN, 1, false>(epi, ta, tb, P, max_ctas, st);
+}
+
+// tuning knobs (process-wide; -1 = automatic)
+static int g_force_cta_group = -1;
+static int g_force_staged = -1;
 
 static int g_num_sms_cached = 0;
 static int num_sms() {
@@ -428,10 +599,13 @@ extern "C" int deco_gemm_bf16(const void* A, long long lda, const void* W, long 
     int bn = tile_n;
     if (bn == 0) bn = (N % 256 == 0) ? 256 : ((N % 192 == 0) ? 192 : (N % 128 == 0 ? 128 : (N >= 1024 ? 256 : 128)));
     DECO_CHECK_ARG(bn == 128 || bn == 192 || bn == 256, "gemm: tile_n must be 128, 192 or 256");
+    // 2-CTA pairs for anything with at least one full 256-row pair tile; staged (coalesced) epilogue only there
+    int cg = (g_force_cta_group > 0) ? g_force_cta_group : (M > kBM ? 2 : 1);
+    int staged = (g_force_staged >= 0) ? g_force_staged : (cg == 2 ? 1 : 0);
     CUtensorMap ta, tb;
     int rc = make_tmap(&ta, A, M, K, lda, kBM);
     if (rc) return rc;
-    rc = make_tmap(&tb, W, N, K, ldw, bn);
+    rc = make_tmap(&tb, W, N, K, ldw, bn / cg);
     if (rc) return rc;
     GemmParams P;
     P.out = out; P.ldo = ldo; P.bias = bias; P.resid = (const float*)resid; P.ldr = ldr;
@@ -439,7 +613,16 @@ extern "C" int deco_gemm_bf16(const void* A, long long lda, const void* W, long 
     P.M = M; P.N = N; P.K = K;
     const int ctas = num_sms();
     cudaStream_t st = (cudaStream_t)stream;
-    if (bn == 256) return dispatch_epi<256>(epilogue, ta, tb, P, ctas, st);
-    if (bn == 192) return dispatch_epi<192>(epilogue, ta, tb, P, ctas, st);
-    return dispatch_epi<128>(epilogue, ta, tb, P, ctas, st);
+    if (bn == 256) return dispatch_variant<256>(cg, staged, epilogue, ta, tb, P, ctas, st);
+    if (bn == 192) return dispatch_variant<192>(cg, staged, epilogue, ta, tb, P, ctas, st);
+    return dispatch_variant<128>(cg, staged, epilogue, ta, tb, P, ctas, st);
+}
+
+extern "C" int deco_gemm_set_tuning(int cta_group, int staged_epilogue) {
+    using namespace deco;
+    DECO_CHECK_ARG(cta_group == -1 || cta_group == 1 || cta_group == 2, "gemm tuning: cta_group must be -1, 1 or 2");
+    DECO_CHECK_ARG(staged_epilogue >= -1 && staged_epilogue <= 1, "gemm tuning: staged_epilogue must be -1, 0 or 1");
+    g_force_cta_group = cta_group;
+    g_force_staged = staged_epilogue;
+    return DECO_OK;
 }

@@ -35,6 +35,30 @@ def test_gemm_bias(cuda_dev, M, N, K, tile_n):
     assert rel_l2(out.float(), F.silu(ref)) < 4e-3
 
 
+@pytest.mark.parametrize("cg,staged", [(1, 0), (1, 1), (2, 0), (2, 1)])
+def test_gemm_variants_agree(cuda_dev, lib, cg, staged):
+    """Every (cta_group, epilogue style) build of the kernel on a ragged shape (M, N not multiples of the tile)."""
+    from deco_b200 import ops
+    M, N, K, L = 1000, 1160, 1152, 250
+    a, w = _rand((M, K), cuda_dev, 1), _rand((N, K), cuda_dev, 2, K ** -0.5)
+    bias = _rand((N,), cuda_dev, 3, 0.1, torch.float32)
+    resid = _rand((M, N), cuda_dev, 4, dtype=torch.float32)
+    gate = _rand((M // L, N), cuda_dev, 5)
+    ref = a.float() @ w.float().t() + bias
+    lib.deco_gemm_set_tuning(cg, staged)
+    try:
+        for tn in (128, 192, 256):
+            assert rel_l2(ops.gemm(a, w, bias, ops.EPI_BIAS, tile_n=tn).float(), ref) < 4e-3
+            o = ops.gemm(a, w, bias, ops.EPI_GATE_RESIDUAL, resid=resid, gate=gate, rows_per_gate=L, tile_n=tn)
+            assert rel_l2(o, resid + gate.float().repeat_interleave(L, 0) * ref) < 1e-5
+        w13 = _rand((1184, K), cuda_dev, 6, K ** -0.5)       # 37 groups of [16 | 16]
+        g = w13.view(37, 2, 16, K)
+        sw = F.silu(a.float() @ g[:, 0].reshape(-1, K).float().t()) * (a.float() @ g[:, 1].reshape(-1, K).float().t())
+        assert rel_l2(ops.gemm(a, w13, None, ops.EPI_SWIGLU).float(), sw) < 5e-3
+    finally:
+        lib.deco_gemm_set_tuning(-1, -1)
+
+
 def test_gemm_strided_a(cuda_dev):
     """A operand as a column slice of a wider matrix (how attention output / qkv views are consumed)."""
     from deco_b200 import ops
