@@ -210,9 +210,32 @@ template <int BN, int CG> struct GemmCfg {
 constexpr int kStageLd = 36;
 constexpr int kStageFloatsPerWarp = 32 * kStageLd;
 
+// Residual / gate operands of one staged chunk, fetched EARLY (before the accumulator is ready) so that their
+// global-memory latency overlaps the MMA main loop instead of sitting in the epilogue's critical path.
+struct ResidChunk {
+    float4 rv[8];     // residual, rows it*4 + (lane >> 3), columns 4*(lane & 7) .. +3
+    uint2 gv[8];      // gate (bf16 x4) per row; gv[0] only when the 32 rows share one modulation row
+};
+
+__device__ __forceinline__ void load_resid_chunk(const GemmParams& P, ResidChunk& rc, long long row0, int n0, int lane,
+                                                 bool uniform_gate) {
+    const int n = n0 + 4 * (lane & 7), rsub = lane >> 3;
+    const bool col_ok = n < P.N;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const long long row = row0 + it * 4 + rsub;
+        const bool ok = col_ok && row < P.M;
+        rc.rv[it] = ok ? *reinterpret_cast<const float4*>(P.resid + row * P.ldr + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!uniform_gate || it == 0)
+            rc.gv[it] = ok ? __ldg(reinterpret_cast<const uint2*>(P.gate + (row / P.rows_per_gate) * P.gate_stride + n))
+                           : make_uint2(0u, 0u);
+    }
+}
+
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk_staged(const GemmParams& P, const uint32_t (&acc)[32], float* stg,
-                                                      long long row0, int n0, int lane) {
+                                                      long long row0, int n0, int lane, const ResidChunk& rc,
+                                                      bool uniform_gate) {
 #pragma unroll
     for (int j = 0; j < 8; ++j)
         *reinterpret_cast<float4*>(stg + lane * kStageLd + 4 * j) =
@@ -220,28 +243,31 @@ __device__ __forceinline__ void epilogue_chunk_staged(const GemmParams& P, const
                         __uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3]));
     __syncwarp();
     const int cg = lane & 7, rsub = lane >> 3;
+    const int n = n0 + 4 * cg;
     if (EPI == EPI_SWIGLU) {
-        // chunk = [16 x w1-columns | 16 x w3-columns]; lanes 0..3 of each row group produce 4 outputs each
-        const int no = (n0 >> 1) + 4 * cg;
-        if (cg < 4 && n0 + 4 * cg < P.N) {
+        // chunk = [16 x w1-columns | 16 x w3-columns]: lanes cg<4 hold a[4cg..], lanes cg>=4 hold b[4(cg-4)..].
+        // Partner lanes (cg ^ 4) swap their float4 and each produces two of the four outputs: all lanes busy.
+        const int no = (n0 >> 1) + 4 * (cg & 3) + ((cg >> 2) << 1);
+        const bool col_ok = n0 + 4 * (cg & 3) < P.N;
 #pragma unroll
-            for (int it = 0; it < 8; ++it) {
-                const int r = it * 4 + rsub;
-                const long long row = row0 + r;
-                const float4 a = *reinterpret_cast<const float4*>(stg + r * kStageLd + 4 * cg);
-                const float4 b = *reinterpret_cast<const float4*>(stg + r * kStageLd + 16 + 4 * cg);
-                if (row < P.M) {
-                    uint2 w;
-                    w.x = pack_bf2(silu_f(a.x) * b.x, silu_f(a.y) * b.y);
-                    w.y = pack_bf2(silu_f(a.z) * b.z, silu_f(a.w) * b.w);
-                    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(P.out) + row * P.ldo + no) = w;
-                }
-            }
+        for (int it = 0; it < 8; ++it) {
+            const int r = it * 4 + rsub;
+            const long long row = row0 + r;
+            const float4 mine = *reinterpret_cast<const float4*>(stg + r * kStageLd + 4 * cg);
+            float4 other;
+            other.x = __shfl_xor_sync(0xffffffffu, mine.x, 4); other.y = __shfl_xor_sync(0xffffffffu, mine.y, 4);
+            other.z = __shfl_xor_sync(0xffffffffu, mine.z, 4); other.w = __shfl_xor_sync(0xffffffffu, mine.w, 4);
+            // low lane: outputs 0,1 = silu(a.x)*b.x, silu(a.y)*b.y ; high lane: outputs 2,3
+            const bool hi = cg >= 4;
+            const float a0 = hi ? other.z : mine.x, a1 = hi ? other.w : mine.y;
+            const float b0 = hi ? mine.z : other.x, b1 = hi ? mine.w : other.y;
+            if (col_ok && row < P.M)
+                *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(P.out) + row * P.ldo + no) =
+                    pack_bf2(silu_f(a0) * b0, silu_f(a1) * b1);
         }
         __syncwarp();
         return;
     }
-    const int n = n0 + 4 * cg;
     if (n < P.N) {
         float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
         if (P.bias) bz = __ldg(reinterpret_cast<const float4*>(P.bias + n));
@@ -254,8 +280,8 @@ __device__ __forceinline__ void epilogue_chunk_staged(const GemmParams& P, const
             if (row < P.M) {
                 if (EPI == EPI_GATE_RESIDUAL) {
                     // fp32 residual stream: x <- x + gate * (acc + bias); may run in place (out == resid)
-                    const float4 rv = *reinterpret_cast<const float4*>(P.resid + row * P.ldr + n);
-                    const uint2 gv = __ldg(reinterpret_cast<const uint2*>(P.gate + (row / P.rows_per_gate) * P.gate_stride + n));
+                    const float4 rv = rc.rv[it];
+                    const uint2 gv = uniform_gate ? rc.gv[0] : rc.gv[it];
                     const float2 g0 = unpack_bf2(gv.x), g1 = unpack_bf2(gv.y);
                     *reinterpret_cast<float4*>(reinterpret_cast<float*>(P.out) + row * P.ldo + n) =
                         make_float4(fmaf(g0.x, v.x, rv.x), fmaf(g0.y, v.y, rv.y), fmaf(g1.x, v.z, rv.z), fmaf(g1.y, v.w, rv.w));
@@ -447,19 +473,44 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         float* stg = reinterpret_cast<float*>(smem_raw + (epi_stage_base - smem_u32(smem_raw))) + q * kStageFloatsPerWarp;
         for (int tile = tile0; tile < num_tiles; tile += tile_stride) {
             const int m_blk = tile / num_n, n_blk = tile % num_n;
-            mbar_wait(tfull_bar(as), aphase);
-            tc_fence_after();
             const long long row0 = (long long)(m_blk * CG + (int)cta_rank) * kBM + q * 32;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+            const int nbase = n_blk * BN;
+            if (STAGED && EPI == EPI_GATE_RESIDUAL) {
+                // residual chunks are fetched one chunk ahead; chunk 0 before the accumulator barrier, so that
+                // HBM latency hides behind the MMA main loop
+                const bool ug = (P.rows_per_gate % 32) == 0;
+                ResidChunk rcA, rcB;
+                load_resid_chunk(P, rcA, row0, nbase, lane, ug);
+                mbar_wait(tfull_bar(as), aphase);
+                tc_fence_after();
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t acc[32];
-                tmem_ld32(taddr + (uint32_t)(c * 32), acc);
-                tmem_ld_wait();
-                const int n0 = n_blk * BN + c * 32;
-                if (row0 < P.M && n0 < P.N) {             // warp-uniform guard
-                    if (STAGED) epilogue_chunk_staged<EPI>(P, acc, stg, row0, n0, lane);
-                    else epilogue_chunk_direct<EPI>(P, acc, row0 + lane, n0);
+                for (int c = 0; c < BN / 32; c += 2) {
+                    uint32_t acc[32];
+                    load_resid_chunk(P, rcB, row0, nbase + (c + 1) * 32, lane, ug);
+                    tmem_ld32(taddr + (uint32_t)(c * 32), acc);
+                    tmem_ld_wait();
+                    if (row0 < P.M && nbase + c * 32 < P.N)
+                        epilogue_chunk_staged<EPI>(P, acc, stg, row0, nbase + c * 32, lane, rcA, ug);
+                    if (c + 2 < BN / 32) load_resid_chunk(P, rcA, row0, nbase + (c + 2) * 32, lane, ug);
+                    tmem_ld32(taddr + (uint32_t)((c + 1) * 32), acc);
+                    tmem_ld_wait();
+                    if (row0 < P.M && nbase + (c + 1) * 32 < P.N)
+                        epilogue_chunk_staged<EPI>(P, acc, stg, row0, nbase + (c + 1) * 32, lane, rcB, ug);
+                }
+            } else {
+                mbar_wait(tfull_bar(as), aphase);
+                tc_fence_after();
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t acc[32];
+                    tmem_ld32(taddr + (uint32_t)(c * 32), acc);
+                    tmem_ld_wait();
+                    const int n0 = nbase + c * 32;
+                    if (row0 < P.M && n0 < P.N) {             // warp-uniform guard
+                        if (STAGED) { ResidChunk none; epilogue_chunk_staged<EPI>(P, acc, stg, row0, n0, lane, none, false); }
+                        else epilogue_chunk_direct<EPI>(P, acc, row0 + lane, n0);
+                    }
                 }
             }
             tc_fence_before();
