@@ -647,12 +647,16 @@ extern "C" int deco_gemm_bf16(const void* A, long long lda, const void* W, long 
         DECO_CHECK_ARG(resid && gate && rows_per_gate > 0 && ldr % 8 == 0 && gate_stride % 8 == 0 &&
                        (((uintptr_t)resid | (uintptr_t)gate) & 15) == 0, "gemm: gate/residual arguments invalid");
     if (epilogue == EPI_SWIGLU) DECO_CHECK_ARG(N % 32 == 0, "gemm: swiglu epilogue needs N %% 32 == 0");
+    // tile width: measured on the XL shapes (scripts/gemm_bench.py, profiles/gemm_bench_r1.txt): 256 where it divides N
+    // (cond_embed 1315 TFLOP/s, SwiGLU 1554 with the direct epilogue), 192 for the 1152-multiples
     int bn = tile_n;
     if (bn == 0) bn = (N % 256 == 0) ? 256 : ((N % 192 == 0) ? 192 : (N % 128 == 0 ? 128 : (N >= 1024 ? 256 : 128)));
     DECO_CHECK_ARG(bn == 128 || bn == 192 || bn == 256, "gemm: tile_n must be 128, 192 or 256");
     // 2-CTA pairs for anything with at least one full 256-row pair tile; staged (coalesced) epilogue only there
     int cg = (g_force_cta_group > 0) ? g_force_cta_group : (M > kBM ? 2 : 1);
-    int staged = (g_force_staged >= 0) ? g_force_staged : (cg == 2 ? 1 : 0);
+    // staged (coalesced) epilogue everywhere except SwiGLU, whose output is half as wide as its accumulator tile and
+    // is compute-heavy: the row-per-thread form keeps all 128 epilogue threads busy (1554 vs 1069 TFLOP/s at BN = 256)
+    int staged = (g_force_staged >= 0) ? g_force_staged : (epilogue == EPI_SWIGLU ? 0 : 1);
     CUtensorMap ta, tb;
     int rc = make_tmap(&ta, A, M, K, lda, kBM);
     if (rc) return rc;
