@@ -174,6 +174,60 @@ def test_attention(cuda_dev, heads, d, Lq, Lk2):
     assert rel_l2(got.float(), ref) < 6e-3
 
 
+@pytest.mark.parametrize("heads,d,hw,Lk2", [(16, 72, (16, 16), 0), (4, 64, (10, 10), 0), (2, 72, (32, 32), 0),
+                                            (3, 64, (12, 17), 77), (2, 64, (32, 32), 128)])
+def test_attention_fused_qknorm_rope(cuda_dev, heads, d, hw, Lk2):
+    """q_norm / k_norm / RoPE inside the attention kernel (dit_c2i_DeCo.py:176-187; t2i: text keys get k_norm but
+    no RoPE, dit_t2i_pixnerd.py:46-59) against the oracle's rmsnorm / apply_rope / fp32 SDPA."""
+    from deco_b200 import ops
+    from deco_b200.denoiser import rope_cos_sin
+    L = hw[0] * hw[1]
+    B, H = 2, heads * d
+    qkv = _rand((B * L, 3 * H), cuda_dev, 1)
+    qw = 1 + 0.1 * _rand((d,), cuda_dev, 2, dtype=torch.float32)
+    kw = 1 + 0.1 * _rand((d,), cuda_dev, 3, dtype=torch.float32)
+    ang = O.rope_table_2d(d, hw[0], hw[1]).to(cuda_dev)
+    r = qkv.view(B, L, 3, heads, d)
+    qq = O.apply_rope(O.rmsnorm(r[:, :, 0], qw), ang).to(bf16).float().transpose(1, 2)
+    kk = O.apply_rope(O.rmsnorm(r[:, :, 1], kw), ang).to(bf16).float().transpose(1, 2)
+    vv = r[:, :, 2].float().transpose(1, 2)
+    k2 = v2 = None
+    if Lk2:
+        kv2 = _rand((B * Lk2, 2 * H), cuda_dev, 4)
+        k2, v2 = kv2[:, :H], kv2[:, H:]
+        kk = torch.cat([kk, O.rmsnorm(k2.reshape(B, Lk2, heads, d), kw).to(bf16).float().transpose(1, 2)], 2)
+        vv = torch.cat([vv, v2.reshape(B, Lk2, heads, d).transpose(1, 2).float()], 2)
+    ref = F.scaled_dot_product_attention(qq, kk, vv).transpose(1, 2).reshape(B * L, H)
+    rope = rope_cos_sin(d, hw[0], hw[1]).to(cuda_dev)
+    got = ops.attention(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], B, heads, d, k2=k2, v2=v2,
+                        q_norm=qw, k_norm=kw, rope=rope)
+    assert rel_l2(got.float(), ref) < 6e-3
+    # the stand-alone norm/RoPE kernel followed by the plain attention must give the same bits
+    if not Lk2:
+        pre = ops.qknorm_rope_(qkv.clone(), qw, kw, rope, heads, d, L)
+        two = ops.attention(pre[:, :H], pre[:, H:2 * H], pre[:, 2 * H:], B, heads, d)
+        assert torch.equal(two, got)
+
+
+def test_attention_running_max_rescale(cuda_dev):
+    """Keys whose scores grow block by block force the lazy exponent-reference update (and the O rescale through
+    tensor memory) in every 128-key block; one huge outlier key in the last block dominates the softmax."""
+    from deco_b200 import ops
+    B, heads, d, L = 1, 2, 64, 640
+    H = heads * d
+    g = torch.Generator().manual_seed(7)
+    q = torch.randn((B * L, H), generator=g)
+    k = torch.randn((B * L, H), generator=g) * (1 + torch.arange(L).view(-1, 1) // 128 * 3.0)   # block j: scale 1 + 3j
+    v = torch.randn((B * L, H), generator=g)
+    k[L - 5] *= 4.0
+    q, k, v = (t.to(device=cuda_dev, dtype=bf16) for t in (q, k, v))
+    sp = lambda t: t.reshape(B, L, heads, d).transpose(1, 2).float()
+    ref = F.scaled_dot_product_attention(sp(q), sp(k), sp(v)).transpose(1, 2).reshape(B * L, H)
+    got = ops.attention(q, k, v, B, heads, d)
+    assert torch.isfinite(got.float()).all()
+    assert rel_l2(got.float(), ref) < 6e-3
+
+
 def test_silu_add_rows(cuda_dev):
     from deco_b200 import ops
     x, row = _rand((64, 256), cuda_dev, 1), _rand((4, 256), cuda_dev, 2)
