@@ -7,7 +7,7 @@ hand-written sm_100a kernels behind include/deco_b200.h.
 
 Per forward (B' = CFG rows, L tokens, H hidden):
    patchify -> s_embedder GEMM -> [t sinusoid -> 2 GEMMs] -> cond_combine -> ONE adaLN GEMM for all blocks
-   per block: rmsnorm_modulate -> QKV GEMM -> attention (tcgen05; q/k RMSNorm + RoPE fused into its operand load)
+   per block: rmsnorm_modulate -> QKV GEMM -> qknorm_rope (in place) -> attention (strided, no transposes)
               -> proj GEMM (+gate, +residual) -> rmsnorm_modulate -> W1|W3 GEMM (SwiGLU epilogue) -> W2 GEMM (+gate, +res)
    silu(t + s) -> cond_embed GEMM -> fused pixel decoder (NerfEmbedder + AdaLN-MLP + fold)
 """
@@ -331,8 +331,8 @@ class PixNerDiT(nn.Module):
             sh1, sc1, g1, sh2, sc2, g2 = (m[:, j * H:(j + 1) * H] for j in range(6))
             ops.rmsnorm_modulate(s, bp["n1"], sh1, sc1, L, out=hbuf)
             ops.gemm(hbuf, bp["wqkv"], None, ops.EPI_BIAS, out=qkv)
-            ops.attention(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], B, heads, d, out=obuf,
-                          q_norm=bp["qn"], k_norm=bp["kn"], rope=pos)
+            ops.qknorm_rope_(qkv, bp["qn"], bp["kn"], pos, heads, d, L)
+            ops.attention(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], B, heads, d, out=obuf)
             ops.gemm(obuf, bp["wproj"], bp["bproj"], ops.EPI_GATE_RESIDUAL, out=s, resid=s, gate=g1, rows_per_gate=L)
             ops.rmsnorm_modulate(s, bp["n2"], sh2, sc2, L, out=hbuf)
             ops.gemm(hbuf, bp["w13"], None, ops.EPI_SWIGLU, out=ubuf)

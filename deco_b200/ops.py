@@ -117,13 +117,10 @@ def qknorm_rope_(qkv: torch.Tensor, q_weight: torch.Tensor, k_weight: torch.Tens
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, heads: int, head_dim: int,
               k2: Optional[torch.Tensor] = None, v2: Optional[torch.Tensor] = None,
-              out: Optional[torch.Tensor] = None, q_norm: Optional[torch.Tensor] = None,
-              k_norm: Optional[torch.Tensor] = None, rope: Optional[torch.Tensor] = None,
-              eps: float = 1e-6) -> torch.Tensor:
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """q [B*Lq, heads*d] view, k/v [B*Lk, heads*d] views (row strides free), optional second KV segment.
-    q_norm / k_norm: fp32 [d] RMSNorm weights applied to q and to every key inside the kernel (both or neither);
-    rope: fp32 [Lq, d/2, 2] (cos, sin) applied to q and to the first key segment.  Returns out [B*Lq, heads*d]."""
-    _cuda(q, k, v, k2, v2, q_norm, k_norm, rope)
+    Returns out [B*Lq, heads*d]."""
+    _cuda(q, k, v, k2, v2)
     Hd = heads * head_dim
     Lq, Lk = q.shape[0] // B, k.shape[0] // B
     assert q.dtype == bf16 and q.shape[1] == Hd and k.shape[1] == Hd and v.shape == k.shape
@@ -134,15 +131,8 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, heads: 
     if k2 is not None:
         Lk2, s2 = k2.shape[0] // B, k2.stride(0)
         assert v2 is not None and v2.stride(0) == s2
-    if q_norm is not None:
-        assert k_norm is not None and q_norm.dtype == torch.float32 and k_norm.dtype == torch.float32
-        assert q_norm.numel() == head_dim and k_norm.numel() == head_dim
-        assert q_norm.is_contiguous() and k_norm.is_contiguous()
-    if rope is not None:
-        assert rope.dtype == torch.float32 and rope.is_contiguous() and rope.shape == (Lq, head_dim // 2, 2)
     call("deco_attention_fwd", ptr(q), q.stride(0), ptr(k), ptr(v), k.stride(0), Lk, ptr(k2), ptr(v2), s2, Lk2,
-         ptr(out), out.stride(0), ptr(q_norm), ptr(k_norm), ptr(rope), float(eps),
-         B, heads, Lq, head_dim, float(head_dim) ** -0.5, _st(q))
+         ptr(out), out.stride(0), B, heads, Lq, head_dim, float(head_dim) ** -0.5, _st(q))
     return out
 
 

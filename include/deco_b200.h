@@ -71,18 +71,15 @@ int deco_rmsnorm_modulate(const void* x, int x_is_f32, const float* weight, cons
 int deco_qknorm_rope(void* qkv_bf16, const float* q_weight, const float* k_weight, const float* rope_cos_sin,
                      long long M, int heads, int head_dim, int L, float eps, void* stream);
 
-/* scaled_dot_product_attention, non-causal, no mask (dit_c2i_DeCo.py:176-187; layers/attention_op.py:4), with the
- * preceding q_norm / k_norm (RMSNorm over head_dim, dit_c2i_DeCo.py:178-179) and 2-D RoPE (:134-145, :180) fused into
- * the operand load.  q/k/v/out are strided views ([B*L, stride] rows, head h at column h*head_dim), so Q/K/V are read
- * in place from the QKV GEMM output.  q_norm_w / k_norm_w: fp32 [head_dim] or both NULL (inputs already normalised);
- * rope_cos_sin: fp32 [Lq, head_dim/2, 2] applied to q and to key segment 0 (needs Lk0 == Lq) or NULL.  A second
- * key/value segment (k1, v1, Lk1) implements the t2i [image || text] keys (dit_t2i_pixnerd.py:46-59: k_norm on both,
- * RoPE on the image part only); pass Lk1 = 0 for plain self-attention.  tcgen05/TMEM kernel (csrc/attention_tc.cu). */
+/* scaled_dot_product_attention, non-causal, no mask (dit_c2i_DeCo.py:185; layers/attention_op.py:4).
+ * q/k/v/out are strided views ([B*L, stride] rows, head h at column h*head_dim), so Q/K/V are read in place from the
+ * QKV GEMM output.  A second key/value segment (k1, v1, Lk1) implements the t2i [image || text] keys
+ * (dit_t2i_pixnerd.py:52-59); pass Lk1 = 0 for plain self-attention.  tcgen05/TMEM kernel fed by TMA
+ * (csrc/attention_tc.cu); q_norm / k_norm / RoPE are applied beforehand (deco_qknorm_rope). */
 int deco_attention_fwd(const void* q, long long q_stride,
                        const void* k0, const void* v0, long long kv0_stride, int Lk0,
                        const void* k1, const void* v1, long long kv1_stride, int Lk1,
                        void* out, long long out_stride,
-                       const float* q_norm_w, const float* k_norm_w, const float* rope_cos_sin, float eps,
                        int B, int heads, int Lq, int head_dim, float scale, void* stream);
 
 /* s = silu(t + s) (dit_c2i_DeCo.py:499): out[m,:] = silu(x[m,:] + row[m / rows_per,:]); out may alias x */

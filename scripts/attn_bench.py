@@ -18,11 +18,10 @@ for name, B, heads, d, hw, Lt in [("XL/16 256px B'=512", 512, 16, 72, (16, 16), 
     kw = torch.ones(d, device=dev)
     rope = rope_cos_sin(d, *hw).to(dev)
     out = torch.empty((B * L, H), device=dev, dtype=torch.bfloat16)
-    for fused in (True, False):
+    for fused in (False,):
         def run():
             ops.attention(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], B, heads, d, out=out,
-                          k2=None if kv2 is None else kv2[:, :H], v2=None if kv2 is None else kv2[:, H:],
-                          q_norm=qw if fused else None, k_norm=kw if fused else None, rope=rope if fused else None)
+                          k2=None if kv2 is None else kv2[:, :H], v2=None if kv2 is None else kv2[:, H:])
         for _ in range(3):
             run()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

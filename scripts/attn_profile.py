@@ -16,6 +16,5 @@ qw = torch.ones(d, device=dev)
 rope = rope_cos_sin(d, *hw).to(dev)
 out = torch.empty((B * L, H), device=dev, dtype=torch.bfloat16)
 for _ in range(2):
-    ops.attention(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], B, heads, d, out=out, q_norm=qw, k_norm=qw, rope=rope)
     ops.attention(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], B, heads, d, out=out)
 torch.cuda.synchronize()

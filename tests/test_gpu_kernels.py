@@ -176,9 +176,9 @@ def test_attention(cuda_dev, heads, d, Lq, Lk2):
 
 @pytest.mark.parametrize("heads,d,hw,Lk2", [(16, 72, (16, 16), 0), (4, 64, (10, 10), 0), (2, 72, (32, 32), 0),
                                             (3, 64, (12, 17), 77), (2, 64, (32, 32), 128)])
-def test_attention_fused_qknorm_rope(cuda_dev, heads, d, hw, Lk2):
-    """q_norm / k_norm / RoPE inside the attention kernel (dit_c2i_DeCo.py:176-187; t2i: text keys get k_norm but
-    no RoPE, dit_t2i_pixnerd.py:46-59) against the oracle's rmsnorm / apply_rope / fp32 SDPA."""
+def test_attention_after_qknorm_rope(cuda_dev, heads, d, hw, Lk2):
+    """q_norm / k_norm / RoPE followed by attention (dit_c2i_DeCo.py:176-187; t2i: text keys get k_norm but no RoPE,
+    dit_t2i_pixnerd.py:46-59) against the oracle's rmsnorm / apply_rope / fp32 SDPA."""
     from deco_b200 import ops
     from deco_b200.denoiser import rope_cos_sin
     L = hw[0] * hw[1]
@@ -199,14 +199,15 @@ def test_attention_fused_qknorm_rope(cuda_dev, heads, d, hw, Lk2):
         vv = torch.cat([vv, v2.reshape(B, Lk2, heads, d).transpose(1, 2).float()], 2)
     ref = F.scaled_dot_product_attention(qq, kk, vv).transpose(1, 2).reshape(B * L, H)
     rope = rope_cos_sin(d, hw[0], hw[1]).to(cuda_dev)
-    got = ops.attention(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], B, heads, d, k2=k2, v2=v2,
-                        q_norm=qw, k_norm=kw, rope=rope)
+    pre = ops.qknorm_rope_(qkv.clone(), qw, kw, rope, heads, d, L)
+    if Lk2:
+        # text keys: k_norm without RoPE = the same kernel with an identity rotation table
+        ident = torch.stack([torch.ones(Lk2, d // 2), torch.zeros(Lk2, d // 2)], -1).contiguous().to(cuda_dev)
+        kvq = torch.cat([kv2[:, :H], kv2], 1).contiguous()          # [q-slot (unused) | k | v]
+        pre2 = ops.qknorm_rope_(kvq, kw, kw, ident, heads, d, Lk2)
+        k2, v2 = pre2[:, H:2 * H], pre2[:, 2 * H:]
+    got = ops.attention(pre[:, :H], pre[:, H:2 * H], pre[:, 2 * H:], B, heads, d, k2=k2, v2=v2)
     assert rel_l2(got.float(), ref) < 6e-3
-    # the stand-alone norm/RoPE kernel followed by the plain attention must give the same bits
-    if not Lk2:
-        pre = ops.qknorm_rope_(qkv.clone(), qw, kw, rope, heads, d, L)
-        two = ops.attention(pre[:, :H], pre[:, H:2 * H], pre[:, 2 * H:], B, heads, d)
-        assert torch.equal(two, got)
 
 
 def test_attention_running_max_rescale(cuda_dev):
