@@ -24,6 +24,9 @@ SIGNATURES = {
     "deco_cond_combine": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "deco_rmsnorm_modulate": (_i, [_vp, _i, _vp, _vp, _vp, _ll, _i, _vp, _ll, _i, _f, _vp]),
     "deco_qknorm_rope": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i, _i, _f, _vp]),
+    "deco_headnorm_rope": (_i, [_vp, _ll, _i, _i, _i, _vp, _vp, _vp, _ll, _i, _i, _i, _f, _vp]),
+    "deco_rmsnorm_addpos": (_i, [_vp, _vp, _vp, _i, _vp, _ll, _i, _f, _vp]),
+    "deco_cast_f32_bf16": (_i, [_vp, _vp, _ll, _vp]),
     "deco_attention_fwd": (_i, [_vp, _ll, _vp, _vp, _ll, _i, _vp, _vp, _ll, _i, _vp, _ll, _i, _i, _i, _i, _f, _vp]),
     "deco_silu_add_rows": (_i, [_vp, _i, _vp, _vp, _ll, _i, _i, _vp]),
     "deco_decoder_blob_bytes": (_i, [_i]),

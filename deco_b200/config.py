@@ -13,6 +13,7 @@ import yaml
 
 CLASS_MAP = {
     "src.models.transformer.dit_c2i_DeCo.PixNerDiT": "deco_b200.denoiser.PixNerDiT",
+    "src.models.transformer.dit_t2i_DeCo.PixNerDiT": "deco_b200.denoiser_t2i.PixNerDiT",
     "src.diffusion.flow_matching.sampling.EulerSampler": "deco_b200.sampling.EulerSampler",
     "src.diffusion.flow_matching.sampling.HeunSampler": "deco_b200.sampling.HeunSampler",
     "src.diffusion.flow_matching.adam_sampling.AdamLMSampler": "deco_b200.sampling.AdamLMSampler",

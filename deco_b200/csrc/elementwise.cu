@@ -134,22 +134,24 @@ __global__ void __launch_bounds__(256) rmsnorm_modulate_kernel(
 }
 
 // ---------------------------------------------------------------- per-head RMSNorm + 2-D RoPE, in place
-// qkv: [M, 3*heads*D] (q | k | v).  One thread per (token, q|k, head) vector of D elements.
-// rope: [L, D/2] float2 (cos, sin); token position = row % L.
+// buf: [M, row_stride]; segment 0 starts at column col0 (weights qw), optional segment 1 at col1 (weights kw); each
+// segment is heads x D.  One thread per (token, segment, head) vector of D elements.
+// rope: [L, D/2] float2 (cos, sin) or NULL (norm only -- the t2i text keys); token position = row % L.
 template <int D>
-__global__ void __launch_bounds__(128) qknorm_rope_kernel(__nv_bfloat16* __restrict__ qkv, const float* __restrict__ qw,
+__global__ void __launch_bounds__(128) qknorm_rope_kernel(__nv_bfloat16* __restrict__ qkv, long long row_stride,
+                                                          int nseg, int col0, int col1, const float* __restrict__ qw,
                                                           const float* __restrict__ kw, const float2* __restrict__ rope,
                                                           long long M, int heads, int L, float eps)
 {
     const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int per_tok = 2 * heads;
+    const int per_tok = nseg * heads;
     if (item >= M * per_tok) return;
     const long long tok = item / per_tok;
     const int r = (int)(item % per_tok);
     const int is_k = r / heads, head = r % heads;
-    __nv_bfloat16* p = qkv + tok * (3LL * heads * D) + (long long)is_k * heads * D + (long long)head * D;
+    __nv_bfloat16* p = qkv + tok * row_stride + (is_k ? col1 : col0) + (long long)head * D;
     const float* wv = is_k ? kw : qw;
-    const float2* rp = rope + (long long)(tok % L) * (D / 2);
+    const float2* rp = rope ? rope + (long long)(tok % L) * (D / 2) : nullptr;
     float v[D];
     float ss = 0.f;
 #pragma unroll
@@ -170,7 +172,7 @@ __global__ void __launch_bounds__(128) qknorm_rope_kernel(__nv_bfloat16* __restr
             const int j = c * 4 + e;   // pair index
             const float a = __ldg(wv + 2 * j) * round_bf(v[2 * j] * rs);
             const float b = __ldg(wv + 2 * j + 1) * round_bf(v[2 * j + 1] * rs);
-            const float2 cs = __ldg(rp + j);
+            const float2 cs = rp ? __ldg(rp + j) : make_float2(1.f, 0.f);
             o[e] = pack_bf2(a * cs.x - b * cs.y, a * cs.y + b * cs.x);
         }
         *reinterpret_cast<uint4*>(p + c * 8) = make_uint4(o[0], o[1], o[2], o[3]);
@@ -208,6 +210,55 @@ __global__ void __launch_bounds__(256) silu_add_rows_kernel(const TIn* __restric
             o[e] = pack_bf2(silu_f(a[2 * e] + q.x), silu_f(a[2 * e + 1] + q.y));
         }
         reinterpret_cast<uint4*>(out)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// ---------------------------------------------------------------- text embed: y = w * rms(x) + pos[m % T]
+// Embed(norm_layer=RMSNorm) + learned position (dit_t2i_pixnerd.py:280; layers/patch_embed.py:19-22).  fp32 in/out.
+template <int kMaxChunks>
+__global__ void __launch_bounds__(256) rmsnorm_addpos_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                             const float* __restrict__ pos, int T,
+                                                             float* __restrict__ out, long long M, int Hd, float eps)
+{
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const int nch = Hd >> 2;
+    const float4* xr = reinterpret_cast<const float4*>(x + row * Hd);
+    float4 v[kMaxChunks];
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < kMaxChunks; ++j) {
+        const int ch = lane + j * 32;
+        if (ch < nch) {
+            v[j] = xr[ch];
+            ss = fmaf(v[j].x, v[j].x, fmaf(v[j].y, v[j].y, fmaf(v[j].z, v[j].z, fmaf(v[j].w, v[j].w, ss))));
+        }
+    }
+    ss = warp_sum(ss);
+    const float rs = rsqrtf(ss / (float)Hd + eps);
+    const float4* pr = reinterpret_cast<const float4*>(pos + (row % T) * Hd);
+    float4* orow = reinterpret_cast<float4*>(out + row * Hd);
+#pragma unroll
+    for (int j = 0; j < kMaxChunks; ++j) {
+        const int ch = lane + j * 32;
+        if (ch < nch) {
+            const float4 ww = __ldg(reinterpret_cast<const float4*>(w) + ch), pp = __ldg(pr + ch);
+            orow[ch] = make_float4(fmaf(ww.x, v[j].x * rs, pp.x), fmaf(ww.y, v[j].y * rs, pp.y),
+                                   fmaf(ww.z, v[j].z * rs, pp.z), fmaf(ww.w, v[j].w * rs, pp.w));
+        }
+    }
+}
+
+// ---------------------------------------------------------------- fp32 -> bf16 copy (text stream -> kv_y GEMM operand)
+__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                            long long total8)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += stride) {
+        const float4 a = reinterpret_cast<const float4*>(x)[2 * i], b = reinterpret_cast<const float4*>(x)[2 * i + 1];
+        reinterpret_cast<uint4*>(out)[i] = make_uint4(pack_bf2(a.x, a.y), pack_bf2(a.z, a.w), pack_bf2(b.x, b.y),
+                                                      pack_bf2(b.z, b.w));
     }
 }
 
@@ -275,24 +326,53 @@ extern "C" int deco_rmsnorm_modulate(const void* x, int x_is_f32, const float* w
     return DECO_OK;
 }
 
-extern "C" int deco_qknorm_rope(void* qkv_bf16, const float* q_weight, const float* k_weight, const float* rope_cos_sin,
-                                long long M, int heads, int head_dim, int L, float eps, void* stream) {
+extern "C" int deco_headnorm_rope(void* buf_bf16, long long row_stride, int nseg, int col0, int col1,
+                                  const float* w0, const float* w1, const float* rope_cos_sin,
+                                  long long M, int heads, int head_dim, int L, float eps, void* stream) {
     using namespace deco;
-    DECO_CHECK_ARG(qkv_bf16 && q_weight && k_weight && rope_cos_sin, "qknorm_rope: null pointer");
-    DECO_CHECK_ARG(M > 0 && heads > 0 && L > 0, "qknorm_rope: bad shape");
-    const long long items = M * 2 * heads;
+    DECO_CHECK_ARG(buf_bf16 && w0 && (nseg == 1 || (nseg == 2 && w1)), "headnorm_rope: null pointer / bad nseg");
+    DECO_CHECK_ARG(M > 0 && heads > 0 && L > 0 && row_stride % 8 == 0 && col0 % 8 == 0 && col1 % 8 == 0 && col0 >= 0 && col1 >= 0,
+                   "headnorm_rope: bad shape");
+    const long long items = M * nseg * heads;
     const unsigned grid = (unsigned)((items + 127) / 128);
     if (head_dim == 72)
-        qknorm_rope_kernel<72><<<grid, 128, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)qkv_bf16, q_weight, k_weight,
-                                                                      (const float2*)rope_cos_sin, M, heads, L, eps);
+        qknorm_rope_kernel<72><<<grid, 128, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)buf_bf16, row_stride, nseg, col0, col1,
+                                                                      w0, w1, (const float2*)rope_cos_sin, M, heads, L, eps);
     else if (head_dim == 64)
-        qknorm_rope_kernel<64><<<grid, 128, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)qkv_bf16, q_weight, k_weight,
-                                                                      (const float2*)rope_cos_sin, M, heads, L, eps);
+        qknorm_rope_kernel<64><<<grid, 128, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)buf_bf16, row_stride, nseg, col0, col1,
+                                                                      w0, w1, (const float2*)rope_cos_sin, M, heads, L, eps);
     else {
-        deco_set_error("qknorm_rope: head_dim %d not built (64, 72)", head_dim);
+        deco_set_error("headnorm_rope: head_dim %d not built (64, 72)", head_dim);
         return DECO_ERR_UNSUPPORTED;
     }
     DECO_CHECK_LAUNCH("qknorm_rope_kernel");
+    return DECO_OK;
+}
+
+extern "C" int deco_qknorm_rope(void* qkv_bf16, const float* q_weight, const float* k_weight, const float* rope_cos_sin,
+                                long long M, int heads, int head_dim, int L, float eps, void* stream) {
+    if (!rope_cos_sin) { deco_set_error("qknorm_rope: null pointer"); return DECO_ERR_ARG; }
+    return deco_headnorm_rope(qkv_bf16, 3LL * heads * head_dim, 2, 0, heads * head_dim, q_weight, k_weight, rope_cos_sin,
+                              M, heads, head_dim, L, eps, stream);
+}
+
+extern "C" int deco_rmsnorm_addpos(const float* x, const float* weight, const float* pos, int T, float* out,
+                                   long long M, int hidden, float eps, void* stream) {
+    using namespace deco;
+    DECO_CHECK_ARG(x && weight && pos && out && M > 0 && T > 0 && hidden % 4 == 0 && hidden <= 2048,
+                   "rmsnorm_addpos: bad arguments (hidden %% 4 == 0, <= 2048)");
+    const int warps = 8;
+    const unsigned grid = (unsigned)((M + warps - 1) / warps);
+    rmsnorm_addpos_kernel<16><<<grid, warps * 32, 0, (cudaStream_t)stream>>>(x, weight, pos, T, out, M, hidden, eps);
+    DECO_CHECK_LAUNCH("rmsnorm_addpos_kernel");
+    return DECO_OK;
+}
+
+extern "C" int deco_cast_f32_bf16(const float* x, void* out_bf16, long long n, void* stream) {
+    using namespace deco;
+    DECO_CHECK_ARG(x && out_bf16 && n > 0 && n % 8 == 0, "cast_f32_bf16: n must be a positive multiple of 8");
+    cast_f32_bf16_kernel<<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)out_bf16, n / 8);
+    DECO_CHECK_LAUNCH("cast_f32_bf16_kernel");
     return DECO_OK;
 }
 

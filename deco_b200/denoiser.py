@@ -171,6 +171,49 @@ def _frag(w: torch.Tensor, permuted: bool) -> torch.Tensor:
     return w[rows, k.expand_as(rows)].contiguous()
 
 
+def pack_decoder(embed_linear: nn.Linear, dn: "_PixelDecoder", C: int, pos_table: torch.Tensor, device):
+    """Weights of NerfEmbedder / input_proj / ResBlocks / final layer in the layout csrc/decoder.cu expects.
+    pos_table [p*p, max_freqs^2] is the model's constant positional input of the NerfEmbedder; it is folded with the
+    embedder weight into postab [p*p, 32] (fp32)."""
+    R = len(dn.res_blocks)
+
+    def rb(t):  # bf16-rounded fp32 copy on the host
+        return t.detach().float().cpu().to(bf16)
+
+    wx = rb(embed_linear.weight)                                     # [32, C + 64]
+    bx = embed_linear.bias.detach().float().cpu()
+    tab = pos_table.to(bf16).float()                                 # Linear input cast
+    postab = tab @ wx[:, C:].float().t() + bx                        # [p*p, 32] fp32
+    frags = [_frag(rb(dn.input_proj.weight), False)]
+    vec = [wx[:, :C].float().reshape(-1), torch.zeros(96 - 32 * C), dn.input_proj.bias.detach().float().cpu()]
+    for blk in dn.res_blocks:
+        frags += [_frag(rb(blk.adaLN_modulation[1].weight), True), _frag(rb(blk.mlp[0].weight), False),
+                  _frag(rb(blk.mlp[2].weight), False)]
+        vec += [blk.adaLN_modulation[1].bias, blk.in_ln.weight, blk.in_ln.bias, blk.mlp[0].bias, blk.mlp[2].bias]
+    wf = torch.zeros(8, 32, dtype=bf16)
+    wf[:C] = rb(dn.final_layer.linear.weight)
+    frags.append(_frag(wf, False))
+    bf = torch.zeros(8)
+    bf[:C] = dn.final_layer.linear.bias.detach().float().cpu()
+    vec.append(bf)
+    frag_bytes = torch.cat([f.reshape(-1) for f in frags]).view(torch.uint8)
+    vec_bytes = torch.cat([v.detach().float().cpu().reshape(-1) for v in vec]).view(torch.uint8)
+    blob = torch.cat([frag_bytes, vec_bytes]).contiguous()
+    from . import _lib
+    assert blob.numel() == _lib.load().deco_decoder_blob_bytes(R), (blob.numel(), R)
+    return blob.to(device), postab.contiguous().to(device)
+
+
+def interleave_w13(w1: torch.Tensor, w3: torch.Tensor, Fp: int) -> torch.Tensor:
+    """Rows of w1 and w3 (bf16 [F, H]) zero-padded to Fp and interleaved in groups of 16, the layout the SwiGLU GEMM
+    epilogue expects (one 32-column accumulator chunk holds 16 matching (a, b) pairs)."""
+    F_, H = w1.shape
+    a = torch.zeros(Fp, H, device=w1.device, dtype=w1.dtype)
+    b = torch.zeros(Fp, H, device=w1.device, dtype=w1.dtype)
+    a[:F_], b[:F_] = w1, w3
+    return torch.stack([a.view(Fp // 16, 16, H), b.view(Fp // 16, 16, H)], dim=1).reshape(2 * Fp, H).contiguous()
+
+
 # ------------------------------------------------------------------------------------------------ the module
 class PixNerDiT(nn.Module):
     """Drop-in for src/models/transformer/dit_c2i_DeCo.py::PixNerDiT (constructor :417-433, forward :488-510)."""
@@ -265,36 +308,8 @@ class PixNerDiT(nn.Module):
         return P
 
     def _pack_decoder(self, device):
-        """Weights of NerfEmbedder / input_proj / ResBlocks / final layer in the layout csrc/decoder.cu expects."""
-        dn = self.dec_net
-        R = len(dn.res_blocks)
-        C = self.in_channels
-
-        def rb(t):  # bf16-rounded fp32 copy on the host
-            return t.detach().float().cpu().to(bf16)
-
-        wx = rb(self.x_embedder.embedder[0].weight)                      # [32, 3 + 64]
-        bx = self.x_embedder.embedder[0].bias.detach().float().cpu()
-        tab = nerf_pos_table(self.patch_size, self.x_embedder.max_freqs).to(bf16).float()   # Linear input cast
-        postab = tab @ wx[:, C:].float().t() + bx                       # [p*p, 32] fp32
-        frags = [_frag(rb(dn.input_proj.weight), False)]
-        vec = [wx[:, :C].float().reshape(-1), torch.zeros(96 - 32 * C), dn.input_proj.bias.detach().float().cpu()]
-        for blk in dn.res_blocks:
-            frags += [_frag(rb(blk.adaLN_modulation[1].weight), True), _frag(rb(blk.mlp[0].weight), False),
-                      _frag(rb(blk.mlp[2].weight), False)]
-            vec += [blk.adaLN_modulation[1].bias, blk.in_ln.weight, blk.in_ln.bias, blk.mlp[0].bias, blk.mlp[2].bias]
-        wf = torch.zeros(8, 32, dtype=bf16)
-        wf[:C] = rb(dn.final_layer.linear.weight)
-        frags.append(_frag(wf, False))
-        bf = torch.zeros(8)
-        bf[:C] = dn.final_layer.linear.bias.detach().float().cpu()
-        vec.append(bf)
-        frag_bytes = torch.cat([f.reshape(-1) for f in frags]).view(torch.uint8)
-        vec_bytes = torch.cat([v.detach().float().cpu().reshape(-1) for v in vec]).view(torch.uint8)
-        blob = torch.cat([frag_bytes, vec_bytes]).contiguous()
-        from . import _lib
-        assert blob.numel() == _lib.load().deco_decoder_blob_bytes(R), (blob.numel(), R)
-        return blob.to(device), postab.contiguous().to(device)
+        tab = nerf_pos_table(self.patch_size, self.x_embedder.max_freqs)
+        return pack_decoder(self.x_embedder.embedder[0], self.dec_net, self.in_channels, tab, device)
 
     def fetch_pos(self, height, width, device):
         """RoPE table cache per (h, w) (dit_c2i_DeCo.py:467-473); here as real (cos, sin)."""

@@ -115,6 +115,40 @@ def qknorm_rope_(qkv: torch.Tensor, q_weight: torch.Tensor, k_weight: torch.Tens
     return qkv
 
 
+def headnorm_rope_(buf: torch.Tensor, col0: int, w0: torch.Tensor, heads: int, head_dim: int, L: int,
+                   col1: Optional[int] = None, w1: Optional[torch.Tensor] = None,
+                   rope: Optional[torch.Tensor] = None, eps: float = 1e-6) -> torch.Tensor:
+    """In place per-head RMSNorm (+ optional RoPE) on one or two column segments of buf [M, row_stride]
+    (the t2i layouts: qkv_x, kv_y, text-refine qkv).  rope fp32 [L, head_dim/2, 2] or None."""
+    _cuda(buf, w0, w1, rope)
+    assert buf.dtype == bf16 and buf.dim() == 2 and buf.stride(1) == 1
+    if rope is not None:
+        assert rope.dtype == torch.float32 and rope.is_contiguous() and rope.shape == (L, head_dim // 2, 2)
+    nseg = 1 if col1 is None else 2
+    call("deco_headnorm_rope", ptr(buf), buf.stride(0), nseg, col0, 0 if col1 is None else col1, ptr(w0), ptr(w1),
+         ptr(rope), buf.shape[0], heads, head_dim, L, float(eps), _st(buf))
+    return buf
+
+
+def rmsnorm_addpos(x: torch.Tensor, weight: torch.Tensor, pos: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
+    """out[m] = weight * rms(x[m]) + pos[m % T]; x fp32 [M,H], pos fp32 [T,H]; fp32 output."""
+    _cuda(x, weight, pos)
+    assert x.dtype == torch.float32 and x.is_contiguous() and pos.dtype == torch.float32 and pos.is_contiguous()
+    assert weight.dtype == torch.float32 and pos.shape[1] == x.shape[1] and x.shape[0] % pos.shape[0] == 0
+    out = torch.empty_like(x)
+    call("deco_rmsnorm_addpos", ptr(x), ptr(weight), ptr(pos), pos.shape[0], ptr(out), x.shape[0], x.shape[1],
+         float(eps), _st(x))
+    return out
+
+
+def cast_bf16(x: torch.Tensor) -> torch.Tensor:
+    _cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.numel() % 8 == 0
+    out = torch.empty(x.shape, dtype=bf16, device=x.device)
+    call("deco_cast_f32_bf16", ptr(x), ptr(out), x.numel(), _st(x))
+    return out
+
+
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, heads: int, head_dim: int,
               k2: Optional[torch.Tensor] = None, v2: Optional[torch.Tensor] = None,
               out: Optional[torch.Tensor] = None) -> torch.Tensor:

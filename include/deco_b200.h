@@ -71,6 +71,21 @@ int deco_rmsnorm_modulate(const void* x, int x_is_f32, const float* weight, cons
 int deco_qknorm_rope(void* qkv_bf16, const float* q_weight, const float* k_weight, const float* rope_cos_sin,
                      long long M, int heads, int head_dim, int L, float eps, void* stream);
 
+/* General form of the above for the t2i layouts (dit_t2i_pixnerd.py:43-50, :170-173): buf [M, row_stride]; segment 0 =
+ * heads*head_dim columns from col0 normalised with w0, optional segment 1 from col1 with w1 (nseg = 1 or 2);
+ * rope_cos_sin may be NULL (norm only: the text keys of kv_y and the text-refine q/k carry no RoPE). */
+int deco_headnorm_rope(void* buf_bf16, long long row_stride, int nseg, int col0, int col1,
+                       const float* w0, const float* w1, const float* rope_cos_sin,
+                       long long M, int heads, int head_dim, int L, float eps, void* stream);
+
+/* Text embedder tail (dit_t2i_pixnerd.py:280 with layers/patch_embed.py:19-22, layers/rmsnorm.py:15-20):
+ * out[m,:] = weight * rms(x[m,:]) + pos[m % T,:]; x = y_embedder.proj output, pos = y_pos_embedding; all fp32. */
+int deco_rmsnorm_addpos(const float* x, const float* weight, const float* pos, int T, float* out,
+                        long long M, int hidden, float eps, void* stream);
+
+/* fp32 -> bf16 copy (the refined text stream as the kv_y GEMM operand, dit_t2i_pixnerd.py:47); n % 8 == 0 */
+int deco_cast_f32_bf16(const float* x, void* out_bf16, long long n, void* stream);
+
 /* scaled_dot_product_attention, non-causal, no mask (dit_c2i_DeCo.py:185; layers/attention_op.py:4).
  * q/k/v/out are strided views ([B*L, stride] rows, head h at column h*head_dim), so Q/K/V are read in place from the
  * QKV GEMM output.  A second key/value segment (k1, v1, Lk1) implements the t2i [image || text] keys

@@ -499,3 +499,221 @@ def make_xt_vt(x: torch.Tensor, noise: torch.Tensor, t: torch.Tensor):
     (training_repa_DeCo.py:231-237, scheduling.py:6-14)."""
     a = t.view(-1, 1, 1, 1)
     return a * x + (1 - a) * noise, x - noise
+
+
+# --------------------------------------------------------------------------- text-to-image denoiser (config 5)
+# The original `src/models/transformer/dit_t2i_DeCo.py` survives only as CPython-3.10 bytecode in the checkout
+# (SURVEY.md 8c); its encoder is the logic of `src/models/transformer/dit_t2i_pixnerd.py` (Attention :16-63,
+# FlattenDiTBlock :65-81, NerfEmbedder :83-108, TextRefineAttention/Block :144-198, forward :276-297) and its
+# decoder is SimpleMLPAdaLN of `dit_c2i_DeCo.py:288-415`.  tests/golden/make_golden.py composes exactly those
+# importable reference classes into a module and pins `t2i_forward` against it.
+@dataclass(frozen=True)
+class T2ICfg:
+    """Constructor arguments of the text-to-image denoiser (configs_t2i/sft_res512.yaml:45-56)."""
+    in_channels: int = 3
+    num_groups: int = 24
+    hidden_size: int = 1536
+    decoder_hidden_size: int = 32
+    num_encoder_blocks: int = 16
+    num_decoder_blocks: int = 3
+    num_text_blocks: int = 4
+    patch_size: int = 16
+    txt_embed_dim: int = 2048
+    txt_max_length: int = 128
+    max_freqs: int = 8
+
+    @property
+    def head_dim(self) -> int:
+        return self.hidden_size // self.num_groups
+
+    @property
+    def ffn_hidden(self) -> int:
+        # FlattenDiTBlock: mlp_hidden_dim = int(hidden * 4); SwiGLU keeps it un-scaled (layers/swiglu.py:11-12)
+        return int(self.hidden_size * 4)
+
+
+CFG_XXL_T2I = T2ICfg()
+
+
+def t2i_param_shapes(cfg: T2ICfg) -> Dict[str, Tuple[int, ...]]:
+    """state_dict names/shapes of the original t2i module (members per the 3.10 bytecode: s_embedder, x_embedder,
+    t_embedder, y_embedder, y_pos_embedding, blocks, dec_net, text_refine_blocks)."""
+    H, Hx, p, C = cfg.hidden_size, cfg.decoder_hidden_size, cfg.patch_size, cfg.in_channels
+    d, ffn = cfg.head_dim, cfg.ffn_hidden
+    s: Dict[str, Tuple[int, ...]] = {
+        "x_embedder.embedder.0.weight": (Hx, C + cfg.max_freqs ** 2),
+        "x_embedder.embedder.0.bias": (Hx,),
+        "s_embedder.proj.weight": (H, C * p * p),
+        "s_embedder.proj.bias": (H,),
+        "t_embedder.mlp.0.weight": (H, 256),
+        "t_embedder.mlp.0.bias": (H,),
+        "t_embedder.mlp.2.weight": (H, H),
+        "t_embedder.mlp.2.bias": (H,),
+        "y_embedder.proj.weight": (H, cfg.txt_embed_dim),
+        "y_embedder.proj.bias": (H,),
+        "y_embedder.norm.weight": (H,),
+        "y_pos_embedding": (1, cfg.txt_max_length, H),
+    }
+
+    def block(b, joint):
+        s[b + "norm1.weight"] = (H,)
+        if joint:
+            s[b + "attn.qkv_x.weight"] = (3 * H, H)
+            s[b + "attn.kv_y.weight"] = (2 * H, H)
+        else:
+            s[b + "attn.qkv.weight"] = (3 * H, H)
+        s[b + "attn.q_norm.weight"] = (d,)
+        s[b + "attn.k_norm.weight"] = (d,)
+        s[b + "attn.proj.weight"] = (H, H)
+        s[b + "attn.proj.bias"] = (H,)
+        s[b + "norm2.weight"] = (H,)
+        s[b + "mlp.w12.weight"] = (2 * ffn, H)
+        s[b + "mlp.w3.weight"] = (H, ffn)
+        s[b + "adaLN_modulation.0.weight"] = (6 * H, H)
+        s[b + "adaLN_modulation.0.bias"] = (6 * H,)
+
+    for i in range(cfg.num_encoder_blocks):
+        block(f"blocks.{i}.", True)
+    for i in range(cfg.num_text_blocks):
+        block(f"text_refine_blocks.{i}.", False)
+    s["dec_net.cond_embed.weight"] = (p * p * Hx, H)
+    s["dec_net.cond_embed.bias"] = (p * p * Hx,)
+    s["dec_net.input_proj.weight"] = (Hx, Hx)
+    s["dec_net.input_proj.bias"] = (Hx,)
+    for j in range(cfg.num_decoder_blocks):
+        b = f"dec_net.res_blocks.{j}."
+        s[b + "in_ln.weight"] = (Hx,)
+        s[b + "in_ln.bias"] = (Hx,)
+        s[b + "mlp.0.weight"] = (Hx, Hx)
+        s[b + "mlp.0.bias"] = (Hx,)
+        s[b + "mlp.2.weight"] = (Hx, Hx)
+        s[b + "mlp.2.bias"] = (Hx,)
+        s[b + "adaLN_modulation.1.weight"] = (3 * Hx, Hx)
+        s[b + "adaLN_modulation.1.bias"] = (3 * Hx,)
+    s["dec_net.final_layer.linear.weight"] = (C, Hx)
+    s["dec_net.final_layer.linear.bias"] = (C,)
+    return s
+
+
+def t2i_seeded_params(cfg: T2ICfg, seed: int = 4321, device="cpu") -> Params:
+    """Deterministic fully non-zero weights keyed by name (same recipe as `seeded_params`)."""
+    out: Params = {}
+    for idx, (name, shape) in enumerate(sorted(t2i_param_shapes(cfg).items())):
+        g = torch.Generator().manual_seed(seed * 100003 + idx)
+        if name == "y_pos_embedding":
+            w = 0.5 * torch.randn(shape, generator=g)
+        elif len(shape) == 2:
+            std = 1.0 / math.sqrt(shape[1])
+            if "adaLN_modulation" in name:
+                std *= 0.5
+            w = torch.randn(shape, generator=g) * std
+        elif name.endswith("norm.weight") or name.endswith("norm1.weight") or name.endswith("norm2.weight") \
+                or name.endswith("in_ln.weight"):
+            w = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        else:
+            w = 0.05 * torch.randn(shape, generator=g)
+        out[name] = w.to(device)
+    return out
+
+
+def rope_table_ex2d(head_dim: int, height: int, width: int, theta: float = 10000.0, scale: float = 1.0) -> torch.Tensor:
+    """Angles of precompute_freqs_cis_ex2d (layers/rope.py:22-37): positions linspace(0, height*scale, width) for x and
+    linspace(0, width*scale, height) for y (sic); pair 2k -> x, 2k+1 -> y.  Returned as real angles [L, head_dim/2]."""
+    x_pos = torch.linspace(0, height * scale, width)
+    y_pos = torch.linspace(0, width * scale, height)
+    y_pos, x_pos = torch.meshgrid(y_pos, x_pos, indexing="ij")
+    freqs = 1.0 / (theta ** (torch.arange(0, head_dim, 4)[: head_dim // 4].float() / head_dim))
+    xa = torch.outer(x_pos.reshape(-1), freqs).float()
+    ya = torch.outer(y_pos.reshape(-1), freqs).float()
+    return torch.stack([xa, ya], dim=-1).reshape(height * width, -1)
+
+
+def t2i_nerf_pos_table(patch_size: int, max_freqs: int = 8) -> torch.Tensor:
+    """NerfEmbedder.fetch_pos of the t2i model (dit_t2i_pixnerd.py:92-96): the complex ex2d table of dim
+    2*max_freqs^2 cast to a real dtype, i.e. its real part cos(angle): [p*p, max_freqs^2]."""
+    return torch.cos(rope_table_ex2d(max_freqs ** 2 * 2, patch_size, patch_size))
+
+
+def _swiglu12(P: Params, pre: str, x: torch.Tensor) -> torch.Tensor:
+    """layers/swiglu.py:15-17."""
+    x1, x2 = F.linear(x, P[pre + "w12.weight"]).chunk(2, dim=-1)
+    return F.linear(F.silu(x1) * x2, P[pre + "w3.weight"])
+
+
+def _heads(x: torch.Tensor, n: int, heads: int) -> Tuple[torch.Tensor, ...]:
+    B, N, C = x.shape
+    return tuple(x.reshape(B, N, n, heads, C // n // heads).permute(2, 0, 3, 1, 4))   # n x [B, heads, N, d]
+
+
+def _rope_bhnd(x: torch.Tensor, angles: torch.Tensor) -> torch.Tensor:
+    """apply_rotary_emb in the [B, heads, N, d] layout (layers/rope.py:40-51)."""
+    xf = x.float().reshape(*x.shape[:-1], -1, 2)
+    cos, sin = torch.cos(angles)[None, None], torch.sin(angles)[None, None]
+    a, b = xf[..., 0], xf[..., 1]
+    return torch.stack([a * cos - b * sin, a * sin + b * cos], dim=-1).flatten(3).type_as(x)
+
+
+def t2i_joint_attention(P: Params, pre: str, x, y, angles, heads: int) -> torch.Tensor:
+    """Attention.forward (dit_t2i_pixnerd.py:41-63): image queries over [image || text] keys; k_norm is shared by
+    the image and the text keys, RoPE touches the image q/k only."""
+    B, N, C = x.shape
+    q, kx, vx = _heads(F.linear(x, P[pre + "qkv_x.weight"]), 3, heads)
+    q = rmsnorm(q, P[pre + "q_norm.weight"])
+    kx = rmsnorm(kx, P[pre + "k_norm.weight"])
+    q, kx = _rope_bhnd(q, angles), _rope_bhnd(kx, angles)
+    ky, vy = _heads(F.linear(y, P[pre + "kv_y.weight"]), 2, heads)
+    ky = rmsnorm(ky, P[pre + "k_norm.weight"])
+    k, v = torch.cat([kx, ky], dim=2), torch.cat([vx, vy], dim=2)
+    o = F.scaled_dot_product_attention(q, k, v)
+    return F.linear(o.transpose(1, 2).reshape(B, N, C), P[pre + "proj.weight"], P[pre + "proj.bias"])
+
+
+def t2i_text_attention(P: Params, pre: str, x, heads: int) -> torch.Tensor:
+    """TextRefineAttention.forward (dit_t2i_pixnerd.py:166-179): q/k-normed self-attention, no RoPE."""
+    B, N, C = x.shape
+    q, k, v = _heads(F.linear(x, P[pre + "qkv.weight"]), 3, heads)
+    q, k = rmsnorm(q, P[pre + "q_norm.weight"]), rmsnorm(k, P[pre + "k_norm.weight"])
+    o = F.scaled_dot_product_attention(q, k, v)
+    return F.linear(o.transpose(1, 2).reshape(B, N, C), P[pre + "proj.weight"], P[pre + "proj.bias"])
+
+
+def t2i_forward(P: Params, cfg: T2ICfg, x: torch.Tensor, t: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """Original t2i PixNerDiT.forward: dit_t2i_pixnerd.py:276-297 up to x_embedder, then dec_net + fold as
+    dit_c2i_DeCo.py:501-509.  x:[B,C,H,W], t:[B], y:[B, T, txt_embed_dim]."""
+    B, _, Hh, Ww = x.shape
+    p, H, heads = cfg.patch_size, cfg.hidden_size, cfg.num_groups
+    xp = F.unfold(x, kernel_size=p, stride=p).transpose(1, 2)
+    angles = rope_table_ex2d(cfg.head_dim, Hh // p, Ww // p).to(x.device)
+    tf = timestep_embedding(t.view(-1)).to(t.dtype)
+    te = F.linear(F.silu(F.linear(tf, P["t_embedder.mlp.0.weight"], P["t_embedder.mlp.0.bias"])),
+                  P["t_embedder.mlp.2.weight"], P["t_embedder.mlp.2.bias"]).view(B, -1, H)
+    ye = rmsnorm(F.linear(y, P["y_embedder.proj.weight"], P["y_embedder.proj.bias"]), P["y_embedder.norm.weight"])
+    ye = ye.view(B, -1, H) + P["y_pos_embedding"].to(y.dtype)
+    c = F.silu(te)
+
+    def mods(b):
+        return F.linear(c, P[b + "adaLN_modulation.0.weight"], P[b + "adaLN_modulation.0.bias"]).chunk(6, dim=-1)
+
+    for i in range(cfg.num_text_blocks):
+        b = f"text_refine_blocks.{i}."
+        sh1, sc1, g1, sh2, sc2, g2 = mods(b)
+        ye = ye + g1 * t2i_text_attention(P, b + "attn.", modulate(rmsnorm(ye, P[b + "norm1.weight"]), sh1, sc1), heads)
+        ye = ye + g2 * _swiglu12(P, b + "mlp.", modulate(rmsnorm(ye, P[b + "norm2.weight"]), sh2, sc2))
+    s = F.linear(xp, P["s_embedder.proj.weight"], P["s_embedder.proj.bias"])
+    for i in range(cfg.num_encoder_blocks):
+        b = f"blocks.{i}."
+        sh1, sc1, g1, sh2, sc2, g2 = mods(b)
+        s = s + g1 * t2i_joint_attention(P, b + "attn.", modulate(rmsnorm(s, P[b + "norm1.weight"]), sh1, sc1),
+                                         ye, angles, heads)
+        s = s + g2 * _swiglu12(P, b + "mlp.", modulate(rmsnorm(s, P[b + "norm2.weight"]), sh2, sc2))
+    s = F.silu(te + s)
+    L = s.shape[1]
+    px = xp.reshape(B * L, cfg.in_channels, p * p).transpose(1, 2)
+    tab = t2i_nerf_pos_table(p, cfg.max_freqs).to(device=px.device, dtype=px.dtype)
+    px = F.linear(torch.cat([px, tab[None].expand(B * L, -1, -1)], dim=-1),
+                  P["x_embedder.embedder.0.weight"], P["x_embedder.embedder.0.bias"])
+    dcfg = DenoiserCfg(in_channels=cfg.in_channels, hidden_size=H, hidden_size_x=cfg.decoder_hidden_size,
+                       num_blocks=cfg.num_decoder_blocks, num_cond_blocks=0, patch_size=p)
+    out = pixel_decoder(P, dcfg, px, s.reshape(B * L, H))
+    out = out.transpose(1, 2).reshape(B, L, -1)
+    return F.fold(out.transpose(1, 2).contiguous(), (Hh, Ww), kernel_size=p, stride=p)

@@ -206,8 +206,85 @@ def golden_cfg1():
                         cond=cond.numpy(), ref_seconds=np.float64(el), ref_threads=np.int64(torch.get_num_threads()))
 
 
+def build_ref_t2i(cfg):
+    """The original text-to-image denoiser, re-assembled from the importable reference classes: encoder / text path
+    from dit_t2i_pixnerd.py (Attention, FlattenDiTBlock, NerfEmbedder, TextRefineBlock, forward :276-297), decoder
+    SimpleMLPAdaLN from dit_c2i_DeCo.py; member names as in the 3.10 bytecode of the original dit_t2i_DeCo.py."""
+    import torch.nn as nn
+    from src.models.transformer import dit_t2i_pixnerd as T
+    from src.models.transformer.dit_c2i_DeCo import SimpleMLPAdaLN
+
+    class RefT2I(nn.Module):
+        def __init__(self):
+            super().__init__()
+            H = cfg.hidden_size
+            self.cfg = cfg
+            self.s_embedder = T.Embed(cfg.in_channels * cfg.patch_size ** 2, H, bias=True)
+            self.x_embedder = T.NerfEmbedder(cfg.in_channels, cfg.decoder_hidden_size, max_freqs=8)
+            self.t_embedder = T.TimestepEmbedder(H)
+            self.y_embedder = T.Embed(cfg.txt_embed_dim, H, bias=True, norm_layer=T.Norm)
+            self.y_pos_embedding = nn.Parameter(torch.randn(1, cfg.txt_max_length, H))
+            self.blocks = nn.ModuleList([T.FlattenDiTBlock(H, cfg.num_groups) for _ in range(cfg.num_encoder_blocks)])
+            self.dec_net = SimpleMLPAdaLN(in_channels=cfg.decoder_hidden_size, model_channels=cfg.decoder_hidden_size,
+                                          out_channels=cfg.in_channels, z_channels=H,
+                                          num_res_blocks=cfg.num_decoder_blocks, patch_size=cfg.patch_size)
+            self.text_refine_blocks = nn.ModuleList([T.TextRefineBlock(H, cfg.num_groups)
+                                                     for _ in range(cfg.num_text_blocks)])
+
+        def forward(self, x, t, y):
+            c = self.cfg
+            B, _, Hh, Ww = x.shape
+            p = c.patch_size
+            x = torch.nn.functional.unfold(x, kernel_size=p, stride=p).transpose(1, 2)
+            xpos = T.precompute_freqs_cis_2d(c.hidden_size // c.num_groups, Hh // p, Ww // p)
+            t = self.t_embedder(t.view(-1)).view(B, -1, c.hidden_size)
+            y = self.y_embedder(y).view(B, -1, c.hidden_size) + self.y_pos_embedding.to(y.dtype)
+            condition = torch.nn.functional.silu(t)
+            for blk in self.text_refine_blocks:
+                y = blk(y, condition)
+            s = self.s_embedder(x)
+            for blk in self.blocks:
+                s = blk(s, y, condition, xpos)
+            s = torch.nn.functional.silu(t + s)
+            bsz, length, _ = s.shape
+            x = x.reshape(bsz * length, c.in_channels, p ** 2).transpose(1, 2)
+            s = s.view(bsz * length, c.hidden_size)
+            x = self.x_embedder(x)
+            x = self.dec_net(x, s)
+            x = x.transpose(1, 2).reshape(bsz, length, -1)
+            return torch.nn.functional.fold(x.transpose(1, 2).contiguous(), (Hh, Ww), kernel_size=p, stride=p)
+
+    m = RefT2I()
+    P = O.t2i_seeded_params(cfg)
+    sd = m.state_dict()
+    assert set(sd.keys()) == set(P.keys()), set(sd.keys()) ^ set(P.keys())
+    for k in sd:
+        assert tuple(sd[k].shape) == tuple(P[k].shape), k
+    m.load_state_dict(P)
+    return m.eval(), P
+
+
+def golden_t2i(name, cfg, B, res, seed):
+    import warnings
+    m, P = build_ref_t2i(cfg)
+    x = seeded_noise(B, (cfg.in_channels, res, res), seed)
+    t = torch.linspace(0.1, 0.9, B)
+    y = torch.randn((B, cfg.txt_max_length, cfg.txt_embed_dim), generator=torch.Generator().manual_seed(seed + 1))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")     # NerfEmbedder casts its complex table to real (discards the imaginary part)
+        ref = m(x, t, y)
+    ora = O.t2i_forward(P, cfg, x, t, y)
+    e = rel_l2(ora, ref)
+    print(f"[{name}] t2i oracle vs composed reference forward rel-L2 = {e:.3e}")
+    assert e < 2e-6, e
+    np.savez_compressed(os.path.join(OUT, f"{name}.npz"), x=x.numpy(), t=t.numpy(), y=y.numpy(), out=ref.numpy(),
+                        cfg=np.array([cfg.in_channels, cfg.num_groups, cfg.hidden_size, cfg.decoder_hidden_size,
+                                      cfg.num_encoder_blocks, cfg.num_decoder_blocks, cfg.num_text_blocks,
+                                      cfg.patch_size, cfg.txt_embed_dim, cfg.txt_max_length]))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["dct", "samplers", "tiny", "cfg1"]
+    which = sys.argv[1:] or ["dct", "samplers", "tiny", "t2i", "cfg1"]
     if "dct" in which:
         golden_dct()
     if "samplers" in which:
@@ -218,5 +295,9 @@ if __name__ == "__main__":
                                                 num_classes=10), B=4, res=64, seed=11)
         golden_forward("fwd_d64", O.DenoiserCfg(num_groups=4, hidden_size=256, num_blocks=4, num_cond_blocks=2,
                                                 num_classes=10), B=2, res=96, seed=21)
+    if "t2i" in which:
+        # XXL-t2i-like: head_dim 64, joint [image || text] keys with a ragged text length, 2 text + 2 image blocks
+        golden_t2i("t2i_d64", O.T2ICfg(num_groups=4, hidden_size=256, num_encoder_blocks=2, num_decoder_blocks=3,
+                                       num_text_blocks=2, txt_embed_dim=96, txt_max_length=24), B=2, res=64, seed=31)
     if "cfg1" in which:
         golden_cfg1()

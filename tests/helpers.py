@@ -50,3 +50,24 @@ def seeded_noise(n, shape, seed0=0):
 def toy_net(x, t, y):
     """Analytic stand-in network used for the sampler golden fixtures (tests/golden/make_golden.py)."""
     return torch.tanh(x * (0.5 + t.view(-1, 1, 1, 1))) - 0.1 * y.view(-1, 1, 1, 1).float()
+
+
+def t2i_cfg_from_array(a) -> O.T2ICfg:
+    a = [int(v) for v in a]
+    return O.T2ICfg(in_channels=a[0], num_groups=a[1], hidden_size=a[2], decoder_hidden_size=a[3],
+                    num_encoder_blocks=a[4], num_decoder_blocks=a[5], num_text_blocks=a[6], patch_size=a[7],
+                    txt_embed_dim=a[8], txt_max_length=a[9])
+
+
+def build_t2i_module(cfg: O.T2ICfg, device, seed=4321):
+    """deco_b200 t2i PixNerDiT holding oracle.t2i_seeded_params(cfg)."""
+    from deco_b200.denoiser_t2i import PixNerDiT
+    with torch.device("meta"):
+        m = PixNerDiT(in_channels=cfg.in_channels, num_groups=cfg.num_groups, hidden_size=cfg.hidden_size,
+                      decoder_hidden_size=cfg.decoder_hidden_size, num_encoder_blocks=cfg.num_encoder_blocks,
+                      num_decoder_blocks=cfg.num_decoder_blocks, num_text_blocks=cfg.num_text_blocks,
+                      patch_size=cfg.patch_size, txt_embed_dim=cfg.txt_embed_dim, txt_max_length=cfg.txt_max_length)
+    P = O.t2i_seeded_params(cfg, seed)
+    m = m.to_empty(device=device)
+    m.load_state_dict({k: v.to(device) for k, v in P.items()})
+    return m.eval(), P

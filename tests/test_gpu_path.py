@@ -52,6 +52,46 @@ def test_xl16_forward_vs_oracle(cuda_dev):
     assert e <= 1e-2
 
 
+def test_t2i_forward_vs_reference_golden(cuda_dev):
+    """Text-to-image denoiser (joint [image || text] attention, text-refine blocks) against the fixture produced by the
+    composed reference classes.  Tolerance (north_star): rel-L2 <= 1e-2 per bf16 forward vs the fp32 reference."""
+    from helpers import build_t2i_module, t2i_cfg_from_array
+    g = load_golden("t2i_d64.npz")
+    cfg = t2i_cfg_from_array(g["cfg"])
+    m, P = build_t2i_module(cfg, cuda_dev)
+    x, t, y = (torch.from_numpy(g[k]).to(cuda_dev) for k in ("x", "t", "y"))
+    out = m(x, t, y)
+    assert out.dtype == bf16 and out.shape == x.shape
+    ref = torch.from_numpy(g["out"])
+    e = rel_l2(out.float(), ref)
+    print(f"t2i_d64: rel-L2 vs reference fp32 = {e:.3e}")
+    assert e <= 1e-2
+    Pd = {k: v.to(cuda_dev) for k, v in P.items()}
+    assert rel_l2(O.t2i_forward(Pd, cfg, x, t, y), ref) < 1e-4
+
+
+def test_t2i_xxl_forward_vs_oracle(cuda_dev):
+    """BASELINE.json configs[4] architecture (DeCo-XXL t2i: H 1536, 24 x 64 heads, 16 + 4 blocks, text 128 x 2048) at
+    512 px (1024 image tokens + 128 text keys), 2 CFG rows, against the fp32 oracle on the GPU."""
+    from helpers import build_t2i_module
+    cfg = O.CFG_XXL_T2I
+    m, P = build_t2i_module(cfg, cuda_dev)
+    Pd = {k: v.to(cuda_dev) for k, v in P.items()}
+    x = seeded_noise(1, (3, 512, 512), 5).to(cuda_dev).repeat(2, 1, 1, 1)
+    t = torch.tensor([0.42, 0.42], device=cuda_dev)
+    y = torch.randn((2, 128, 2048), generator=torch.Generator().manual_seed(9)).to(cuda_dev)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        ref = O.t2i_forward(Pd, cfg, x, t, y)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    out = m(x, t, y.to(bf16))
+    e = rel_l2(out.float(), ref)
+    print(f"XXL t2i 512px: rel-L2 vs fp32 oracle = {e:.3e}")
+    assert e <= 1e-2
+
+
 def test_pixel_decoder_alone(cuda_dev):
     """forward(x, t, y, s=...) skips the DiT (dit_c2i_DeCo.py:495): isolates cond_embed GEMM + fused decoder."""
     cfg = O.DenoiserCfg(num_groups=4, hidden_size=256, num_blocks=5, num_cond_blocks=2, num_classes=10)

@@ -70,6 +70,23 @@ def test_state_dict_is_the_reference_checkpoint_contract(cfg):
     assert m.weight_path is None and m.load_ema is False
 
 
+def test_t2i_state_dict_is_the_reference_checkpoint_contract():
+    from deco_b200 import config
+    from deco_b200.denoiser_t2i import PixNerDiT as T2I
+    cfg = O.CFG_XXL_T2I
+    assert config.resolve("src.models.transformer.dit_t2i_DeCo.PixNerDiT") is T2I
+    with torch.device("meta"):
+        m = T2I(in_channels=3, patch_size=16, num_groups=24, hidden_size=1536, txt_embed_dim=2048, txt_max_length=128,
+                num_text_blocks=4, decoder_hidden_size=32, num_encoder_blocks=16, num_decoder_blocks=3)
+    sd = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert sd == O.t2i_param_shapes(cfg)
+    assert m.weight_path is None and m.load_ema is False and m.num_blocks == 19
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        T2I(in_channels=3, patch_size=16, num_groups=4, hidden_size=256, txt_embed_dim=32, txt_max_length=8,
+            num_text_blocks=1, decoder_hidden_size=32, num_encoder_blocks=1, num_decoder_blocks=1).eval()(
+            torch.zeros(1, 3, 32, 32), torch.zeros(1), torch.zeros(1, 8, 32))
+
+
 def test_default_init_follows_reference():
     from deco_b200 import PixNerDiT
     torch.manual_seed(0)

@@ -57,6 +57,23 @@ def test_forward_matches_reference_fixtures():
         assert float(torch.from_numpy(g["out"]).abs().mean()) > 1e-2   # non-vacuous: default init would give zeros
 
 
+def test_t2i_forward_matches_reference_fixture():
+    """The t2i oracle against the output of the reference classes composed in tests/golden/make_golden.py::build_ref_t2i."""
+    from helpers import t2i_cfg_from_array
+    g = load_golden("t2i_d64.npz")
+    cfg = t2i_cfg_from_array(g["cfg"])
+    P = O.t2i_seeded_params(cfg)
+    out = O.t2i_forward(P, cfg, torch.from_numpy(g["x"]), torch.from_numpy(g["t"]), torch.from_numpy(g["y"]))
+    assert rel_l2(out, torch.from_numpy(g["out"])) < 2e-6
+    assert float(torch.from_numpy(g["out"]).abs().mean()) > 1e-2
+    # known answers: XXL t2i sizes (README "1.1B"; configs_t2i/sft_res512.yaml:45-56)
+    n = sum(int(np.prod(s)) for s in O.t2i_param_shapes(O.CFG_XXL_T2I).values())
+    assert 1.10e9 < n < 1.16e9, n
+    assert O.CFG_XXL_T2I.head_dim == 64 and O.CFG_XXL_T2I.ffn_hidden == 6144
+    # the NerfEmbedder table is the real part of the complex ex2d table: first pixel has angle 0 -> all ones
+    assert torch.equal(O.t2i_nerf_pos_table(16)[0], torch.ones(64))
+
+
 def test_samplers_match_reference_fixtures():
     g = load_golden("samplers_toy.npz")
     noise = torch.from_numpy(g["noise"])
