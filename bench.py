@@ -25,14 +25,38 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-NUM_SAMPLING_STEPS = 100
-GLOBAL_BATCH = 256
-RES = 256
-GUIDANCE, G_MIN, G_MAX = 3.2, 0.1, 1.0
 XL = dict(in_channels=3, num_groups=16, hidden_size=1152, hidden_size_x=32, num_blocks=31, num_cond_blocks=28,
           patch_size=16, num_classes=1000, nerf_mlpratio=2)
-METRIC = "DeCo-XL/16 256px class-conditional sampling throughput (Euler 100 steps x CFG, fixed NFE)"
+LARGE = dict(XL, hidden_size=1024, num_blocks=25, num_cond_blocks=22)
+XXL_T2I = dict(in_channels=3, patch_size=16, num_groups=24, hidden_size=1536, txt_embed_dim=2048, txt_max_length=128,
+               num_text_blocks=4, decoder_hidden_size=32, num_encoder_blocks=16, num_decoder_blocks=3)
 UNIT = "images/s"
+# BASELINE.json configs; "xl256" (configs[1]) is the one the headline metric is quoted on and the default.
+# gflop = algorithmic GFLOP per image-forward (2*MAC, no padding counted).
+WORKLOADS = {
+    "xl256": dict(kind="c2i", model=XL, res=256, batch=256, sampler="euler", steps=100, guidance=3.2, gmin=0.1, gmax=1.0,
+                  timeshift=1.0, gflop=244.9,
+                  metric="DeCo-XL/16 256px class-conditional sampling throughput (Euler 100 steps x CFG, fixed NFE)",
+                  name="DeCo-XL/16 256px c2i (configs_c2i/DeCo_XL.yaml), Euler 100 steps x CFG 3.2 on (0.1,1]"),
+    "xl512": dict(kind="c2i", model=XL, res=512, batch=64, sampler="euler", steps=100, guidance=5.0, gmin=0.1, gmax=1.0,
+                  timeshift=1.0, gflop=1079.9,
+                  metric="DeCo-XL/16 512px class-conditional sampling throughput (Euler 100 steps x CFG, fixed NFE)",
+                  name="DeCo-XL/16 512px c2i (configs_c2i/DeCo_XL_512.yaml), Euler 100 steps x CFG 5.0 on (0.1,1]"),
+    "l256": dict(kind="c2i", model=LARGE, res=256, batch=256, sampler="euler", steps=100, guidance=3.2, gmin=0.1, gmax=1.0,
+                 timeshift=1.0, gflop=155.0,
+                 metric="DeCo-L/16 256px class-conditional sampling throughput (Euler 100 steps x CFG, fixed NFE)",
+                 name="DeCo-L/16 256px c2i (configs_c2i/DeCo_large.yaml architecture), Euler 100 steps x CFG 3.2 on (0.1,1]"),
+    "t2i512": dict(kind="t2i", model=XXL_T2I, res=512, batch=32, sampler="adam2", steps=25, guidance=4.0, gmin=0.0, gmax=1.0,
+                   timeshift=3.0, gflop=1450.6,
+                   metric="DeCo-XXL/16 512px text-to-image sampling throughput (AdamLM order 2, 25 steps x CFG, fixed NFE)",
+                   name="DeCo-XXL/16 512px t2i (configs_t2i/sft_res512.yaml), AdamLM order 2, 25 steps x CFG 4.0, "
+                        "timeshift 3, synthetic text-encoder states [128 x 2048]"),
+}
+# the reference arm / cpu_baseline always time the headline workload's CPU restatement
+NUM_SAMPLING_STEPS = WORKLOADS["xl256"]["steps"]
+RES = WORKLOADS["xl256"]["res"]
+GUIDANCE, G_MIN, G_MAX = 3.2, 0.1, 1.0
+METRIC = WORKLOADS["xl256"]["metric"]
 
 
 def parse():
@@ -41,13 +65,20 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="deco_b200", choices=["deco_b200", "reference"])
-    ap.add_argument("--global-batch", type=int, default=GLOBAL_BATCH)
+    ap.add_argument("--workload", default="xl256", choices=sorted(WORKLOADS))
+    ap.add_argument("--global-batch", type=int, default=0, help="0 = the workload's batch (BASELINE.json)")
+    ap.add_argument("--no-hbm-kernels", action="store_true", help="skip the per-kernel HBM roofline section")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-steps", type=int, default=2)
     ap.add_argument("--profile", action="store_true",
                     help="bracket the timed steps with cudaProfilerStart/Stop (use with ncu --profile-from-start off)")
     return ap.parse_args()
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the GEMM kernel, averaged over the launches of one step
+# (ncu --set full capture, profiles/): filled in from the capture of the same command, None until captured.
+GEMM_TRAFFIC = {}
 
 
 def measured_peaks():
@@ -155,14 +186,97 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------------------------- deco_b200 arm
+def _time_kernel(fn, iters, torch):
+    """Average milliseconds per call of fn(i) over `iters` calls, CUDA events on the current stream, after 2 warm-ups."""
+    for i in range(2):
+        fn(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def hbm_kernel_rooflines(torch, ops, net, dev, B2, res, hbm_gbs):
+    """Achieved HBM GB/s of the memory-bound kernels at the bench shape (B2 CFG rows), each timed alone with CUDA events
+    over buffers far larger than L2 (or rotated through > L2 of distinct buffers).  Algorithmic bytes per DESIGN.md."""
+    from deco_b200.training import build_freq_weight
+    bf = torch.bfloat16
+    out = []
+    H = net.hidden_size
+    L = (res // net.patch_size) ** 2
+    M = B2 * L
+    B = B2 // 2
+    npx = 3 * res * res
+
+    def add(name, ms, nbytes, note, flops=None):
+        d = dict(kernel=name, bound="hbm", ms=ms, algorithmic_bytes=nbytes, achieved=nbytes / (ms * 1e-3) / 1e9,
+                 peak=hbm_gbs, unit="GB/s", frac=nbytes / (ms * 1e-3) / 1e9 / hbm_gbs, note=note)
+        if flops:
+            d["tflops"] = flops / (ms * 1e-3) / 1e12
+        out.append(d)
+
+    # sampler update: x fp32 r/w + two bf16 network rows = 12 B per element
+    x = torch.randn(B, 3, res, res, device=dev)
+    v = torch.randn(2 * B, 3, res, res, device=dev).to(bf)
+    xo = torch.empty_like(x)
+    ms = _time_kernel(lambda i: ops.cfg_step(x, v, 3.2, 0.01, x_out=xo), 20, torch)
+    add("cfg_step_kernel", ms, 12.0 * B * npx, "x fp32 read+write, uncond/cond bf16 read")
+    # rmsnorm + modulate on the fp32 stream: 4 B read + 2 B write per element
+    s = torch.randn(M, H, device=dev)
+    mod = torch.randn(B2, 2 * H, device=dev).to(bf)
+    w = torch.ones(H, device=dev)
+    hb = torch.empty(M, H, device=dev, dtype=bf)
+    ms = _time_kernel(lambda i: ops.rmsnorm_modulate(s, w, mod[:, :H], mod[:, H:], L, out=hb), 20, torch)
+    add("rmsnorm_modulate_kernel", ms, 6.0 * M * H, "fp32 stream read, bf16 write")
+    del s, hb
+    # q/k head norm + RoPE in place: q,k bf16 read + write = 8 B per (q,k) element pair -> 2*2*2H B per row
+    d = H // net.num_groups
+    qkv = torch.randn(M, 3 * H, device=dev).to(bf)
+    pos = net.fetch_pos(res // net.patch_size, res // net.patch_size, dev)
+    ms = _time_kernel(lambda i: ops.qknorm_rope_(qkv, w[:d], w[:d], pos, net.num_groups, d, L), 20, torch)
+    add("qknorm_rope_kernel", ms, 8.0 * M * H, "q and k bf16, read + write in place")
+    del qkv
+    # fused pixel decoder: x fp32 12 B + condition 64 B + out bf16 6 B per pixel; 37 kFLOP per pixel
+    P = net.prepare(dev)
+    ycond = torch.randn(M, net.patch_size ** 2 * 32, device=dev).to(bf)
+    xx = torch.randn(B2, 3, res, res, device=dev)
+    nres = net.num_blocks - net.num_cond_blocks if hasattr(net, "num_cond_blocks") else net.num_decoder_blocks
+    ms = _time_kernel(lambda i: ops.pixel_decoder(xx, ycond, P["blob"], P["postab"], net.patch_size, 32, nres), 5, torch)
+    add("pixel_decoder_kernel", ms, 82.0 * B2 * res * res,
+        "82 B/pixel (64 condition + 12 x + 6 out); compute/issue-bound once fused (DESIGN.md): tflops on 37.2 kFLOP/pixel",
+        flops=37.2e3 * B2 * res * res)
+    del ycond, xx
+    # DCT + FM loss, forward + backward in one pass: out, v_t read + grad write fp32 = 12 B per element
+    # (BASELINE.json configs[3]: 32 images per GPU = 25 MB per tensor, L2-resident -> rotate 8 distinct sets)
+    nset, Bt = 8, 32
+    outs = [torch.randn(Bt, 3, res, res, device=dev) for _ in range(nset)]
+    vts = [torch.randn(Bt, 3, res, res, device=dev) for _ in range(nset)]
+    fw = build_freq_weight(85).reshape(3, 8, 8).contiguous().to(dev)
+    ms = _time_kernel(lambda i: ops.dct_fm_loss(outs[i % nset], vts[i % nset], fw, 1.0, want_loss=True, want_grad=True),
+                      24, torch)
+    add("dct_fm_loss_kernel (fwd+bwd)", ms, 12.0 * Bt * npx, "32 images, out + v_t fp32 read, grad fp32 write, 8 rotating sets")
+    ms = _time_kernel(lambda i: ops.dct_fm_loss(outs[i % nset], vts[i % nset], fw, 1.0, want_loss=True, want_grad=False),
+                      24, torch)
+    add("dct_fm_loss_kernel (fwd)", ms, 8.0 * Bt * npx, "32 images, out + v_t fp32 read, 8 rotating sets")
+    return out
+
+
 def run_deco(args):
     import torch
     import torch.distributed as dist
-    from deco_b200 import EulerSampler, LinearScheduler, PixNerDiT, _lib, ode_step_fn, ops, simple_guidance_fn
+    from deco_b200 import AdamLMSampler, EulerSampler, LinearScheduler, PixNerDiT, _lib, ode_step_fn, ops, simple_guidance_fn
     from deco_b200 import distributed as D
     from deco_b200.data import rank_indices, seeded_noise
+    from deco_b200.denoiser_t2i import PixNerDiT as PixNerDiTT2I
     from deco_b200.utils import GemmProbe, randomize_
 
+    wl = WORKLOADS[args.workload]
+    nsteps, res = wl["steps"], wl["res"]
+    gbatch = args.global_batch or wl["batch"]
     rank, world, local = D.init_from_env("nccl" if int(os.environ.get("WORLD_SIZE", "1")) > 1 else None)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: deco_b200 has no CPU path (use --impl reference for the CPU arm)")
@@ -171,28 +285,52 @@ def run_deco(args):
     _lib.load()
     assert world == args.gpus or world == 1, (world, args.gpus)
 
-    idx = rank_indices(args.global_batch, rank, world)          # DistributedSampler(shuffle=False) shard
+    idx = rank_indices(gbatch, rank, world)          # DistributedSampler(shuffle=False) shard
     B = len(idx)
     with torch.device("meta"):
-        net = PixNerDiT(**XL)
+        net = (PixNerDiTT2I if wl["kind"] == "t2i" else PixNerDiT)(**wl["model"])
     net = randomize_(net.to_empty(device=dev), seed=0).eval()
     net.prepare(dev)
     sch = LinearScheduler()
-    sampler = EulerSampler(scheduler=sch, w_scheduler=sch, guidance_fn=simple_guidance_fn, num_steps=NUM_SAMPLING_STEPS,
-                           guidance=GUIDANCE, guidance_interval_min=G_MIN, guidance_interval_max=G_MAX, step_fn=ode_step_fn)
-    noise_host = seeded_noise(idx, (3, RES, RES))                # pinned host batch
-    cond_host = torch.tensor(labels_for(idx), dtype=torch.int64).pin_memory()
+    if wl["sampler"] == "euler":
+        sampler = EulerSampler(scheduler=sch, w_scheduler=sch, guidance_fn=simple_guidance_fn, num_steps=nsteps,
+                               guidance=wl["guidance"], guidance_interval_min=wl["gmin"], guidance_interval_max=wl["gmax"],
+                               timeshift=wl["timeshift"], step_fn=ode_step_fn)
+    else:
+        sampler = AdamLMSampler(order=2, timeshift=wl["timeshift"], scheduler=sch, guidance_fn=simple_guidance_fn,
+                                num_steps=nsteps, guidance=wl["guidance"], guidance_interval_min=wl["gmin"],
+                                guidance_interval_max=wl["gmax"])
+    noise_host = seeded_noise(idx, (3, res, res))                # pinned host batch
+    if wl["kind"] == "t2i":
+        # synthetic text-encoder states: one seeded [T, D] block per prompt, one shared block for the null prompt
+        T_, D_ = wl["model"]["txt_max_length"], wl["model"]["txt_embed_dim"]
+        cond_host = torch.stack([torch.randn((T_, D_), generator=torch.Generator().manual_seed(10_000 + i))
+                                 for i in idx]).to(torch.bfloat16).pin_memory()
+        unc_row = torch.randn((T_, D_), generator=torch.Generator().manual_seed(9_999)).to(torch.bfloat16)
+        make_unc = lambda: unc_row.to(dev).unsqueeze(0).repeat(B, 1, 1)   # noqa: E731
+    else:
+        cond_host = torch.tensor(labels_for(idx), dtype=torch.int64).pin_memory()
+        make_unc = lambda: torch.full((B,), 1000, dtype=torch.int64, device=dev)   # noqa: E731
     x = noise_host.to(dev, non_blocking=True)
     cond = cond_host.to(dev, non_blocking=True)
-    unc = torch.full((B,), 1000, dtype=torch.int64, device=dev)
-    cfg_cond = torch.cat([unc, cond])
+    cfg_cond = torch.cat([make_unc(), cond])
     ts = sampler.timesteps
+    state = dict(pred=None)
 
     def one_step(x, i):
-        t_cur, t_next = ts[i % NUM_SAMPLING_STEPS], ts[i % NUM_SAMPLING_STEPS + 1]
+        k = i % nsteps
+        t_cur, t_next = ts[k], ts[k + 1]
         out = net(torch.cat([x, x]), torch.full((2 * B,), float(t_cur), device=dev), cfg_cond)
-        g = GUIDANCE if (bool(t_cur > G_MIN) and bool(t_cur <= G_MAX)) else 1.0
-        return ops.cfg_step(x, out, g, float(t_next - t_cur))[0]
+        if wl["sampler"] == "euler":
+            g = wl["guidance"] if (bool(t_cur > wl["gmin"]) and bool(t_cur <= wl["gmax"])) else 1.0
+            return ops.cfg_step(x, out, g, float(t_next - t_cur))[0]
+        g = wl["guidance"] if (bool(t_cur > wl["gmin"]) and bool(t_cur < wl["gmax"])) else 1.0
+        cs = sampler.solver_coeffs[k] if state["pred"] is not None else (1.0,)
+        prev = (state["pred"],) if len(cs) > 1 else ()
+        xn, pred, _, _ = ops.cfg_step(x, out, g, float(t_next - t_cur), c0=cs[-1], prev=prev, coeffs=tuple(cs[:-1]),
+                                      want_pred=True)
+        state["pred"] = pred
+        return xn
 
     def barrier():
         if world > 1:
@@ -224,21 +362,21 @@ def run_deco(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms_total = float(tt)
     ms_per_step = ms_total / args.steps
-    value = args.global_batch / (ms_per_step * 1e-3 * NUM_SAMPLING_STEPS)
+    value = gbatch / (ms_per_step * 1e-3 * nsteps)
     gs = probe.summary()
     peaks = measured_peaks()
 
     # ---- e2e: public sampler API, host buffers in, uint8 images out (+ all-gather)
     e2e = None
     if not args.no_e2e:
-        out_host = torch.empty((args.global_batch if world > 1 else B, 3, RES, RES), dtype=torch.uint8).pin_memory()
+        out_host = torch.empty((gbatch if world > 1 else B, 3, res, res), dtype=torch.uint8).pin_memory()
         barrier()
         t0 = torch.cuda.Event(enable_timing=True)
         t1 = torch.cuda.Event(enable_timing=True)
         t0.record()
         xd = noise_host.to(dev, non_blocking=True)
         cd = cond_host.to(dev, non_blocking=True)
-        ud = torch.full((B,), 1000, dtype=torch.int64, device=dev)
+        ud = make_unc()
         _, u8 = sampler.sample_uint8(net, xd, cd, ud)
         if world > 1:
             u8 = D.all_gather_images(u8, world)
@@ -251,47 +389,59 @@ def run_deco(args):
             tt = torch.tensor([ms], device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             ms = float(tt)
-        h2d = noise_host.numel() * 4 + cond_host.numel() * 8
+        h2d = noise_host.numel() * 4 + cond_host.numel() * cond_host.element_size()
         d2h = out_host.numel()
-        e2e = dict(value=args.global_batch / (ms * 1e-3), unit=UNIT,
-                   h2d_bytes_per_step=h2d / NUM_SAMPLING_STEPS, d2h_bytes_per_step=d2h / NUM_SAMPLING_STEPS,
+        e2e = dict(value=gbatch / (ms * 1e-3), unit=UNIT,
+                   h2d_bytes_per_step=h2d / nsteps, d2h_bytes_per_step=d2h / nsteps,
                    seconds_per_trajectory=ms * 1e-3,
-                   note="one EulerSampler.sample_uint8 call = 100 steps; bytes are per rank per trajectory / 100")
+                   note=f"one sampler.sample_uint8 call = {nsteps} steps; bytes are per rank per trajectory / {nsteps}")
 
-    if rank != 0:
+    def finish():
         if world > 1:
             dist.barrier()
+            dist.destroy_process_group()
+
+    if rank != 0:
+        finish()
         return
+
+    hbm = None
+    if not args.no_hbm_kernels and world == 1 and not args.profile:
+        del x
+        torch.cuda.empty_cache()
+        hbm = hbm_kernel_rooflines(torch, ops, net, dev, 2 * B, res, peaks["hbm_gbs"])
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        sd = {k: v.detach().float().cpu() for k, v in net.state_dict().items()}
+        sd = None
+        if args.workload == "xl256":
+            sd = {k: v.detach().float().cpu() for k, v in net.state_dict().items()}
         sec, cores = cpu_reference_step_seconds(sd, args.cpu_sample_steps, 1, 1)
         cpu = dict(value=1.0 / (sec * NUM_SAMPLING_STEPS), unit=UNIT, cores=cores, kind="port",
-                   sample=f"1 image, {args.cpu_sample_steps} CFG-batched Euler steps (fp32 oracle port) timed after 1 warm-up, "
-                          f"extrapolated linearly to 100 steps; {sec:.2f} s per step")
+                   sample=f"XL/16 256px: 1 image, {args.cpu_sample_steps} CFG-batched Euler steps (fp32 oracle port) timed "
+                          f"after 1 warm-up, extrapolated linearly to 100 steps; {sec:.2f} s per step")
 
-    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+    line = dict(metric=wl["metric"], value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms_per_step, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="bf16",
                 data="synthetic",
-                config=dict(workload="DeCo-XL/16 256px c2i (configs_c2i/DeCo_XL.yaml), Euler 100 steps x CFG 3.2 on (0.1,1]",
-                            global_batch=args.global_batch, per_gpu_batch=B, cfg_rows_per_gpu=2 * B,
-                            num_sampling_steps=NUM_SAMPLING_STEPS, step="one CFG-batched denoiser step + fused update",
-                            l2="inputs larger than L2 (1.36 GB bf16 weights + >1 GB activations per step)",
+                config=dict(workload=wl["name"], global_batch=gbatch, per_gpu_batch=B, cfg_rows_per_gpu=2 * B,
+                            num_sampling_steps=nsteps, step="one CFG-batched denoiser step + fused update",
+                            l2="inputs larger than L2 (>1.3 GB bf16 weights + >1 GB activations per step)",
                             parallelism=f"dp{world}"),
                 ms_per_denoiser_step=ms_per_step,
                 clocks=clk.report(), e2e=e2e, gpu_launches=launches,
                 roofline=dict(kernel="gemm_bf16_tcgen05_kernel (all DiT / embed / cond_embed GEMMs)", bound="tensor",
                               achieved=gs["tflops"], peak=peaks["tf_sustained"], unit="TFLOP/s",
                               frac=(gs["tflops"] / peaks["tf_sustained"]) if peaks["tf_sustained"] else None,
-                              traffic=None, peak_source=peaks["source"] + ", sustained bf16",
+                              traffic=GEMM_TRAFFIC.get(args.workload), peak_source=peaks["source"] + ", sustained bf16",
                               launches=gs["launches"], avg_launch_ms=gs["avg_ms"],
+                              avg_launch_algorithmic_gflop=gs["total_flops"] / max(1, gs["launches"]) / 1e9,
                               gemm_share_of_step=gs["total_ms"] / ms_total if ms_total else None,
-                              per_gpu_step_tflops_algorithmic=(244.9e9 * 2 * B) / (ms_per_step * 1e-3) / 1e12),
-                cpu_baseline=cpu)
+                              per_gpu_step_tflops_algorithmic=(wl["gflop"] * 1e9 * 2 * B) / (ms_per_step * 1e-3) / 1e12,
+                              step_frac_of_peak=(wl["gflop"] * 1e9 * 2 * B) / (ms_per_step * 1e-3) / 1e12 / peaks["tf_sustained"]),
+                hbm_kernels=hbm, cpu_baseline=cpu)
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
+    finish()
 
 
 if __name__ == "__main__":

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_C")
 LIB = os.path.join(OUT_DIR, "libdeco_b200.so")
-SOURCES = ["api.cu", "dct_loss.cu", "sampler.cu", "elementwise.cu", "decoder.cu", "attention_tc.cu", "gemm_tcgen05.cu"]
+SOURCES = ["api.cu", "dct_loss.cu", "sampler.cu", "elementwise.cu", "decoder.cu", "attention_tc.cu", "gemm_tcgen05.cu", "gemm_fused.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC"]

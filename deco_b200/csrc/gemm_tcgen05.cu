@@ -374,7 +374,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-                if (CG == 2) mbar_arrive_cluster(mapa_shared(tempty_bar(as), 0));
+                if (CG == 2) mbar_arrive_cluster_relaxed(mapa_shared(tempty_bar(as), 0));   // TMEM hand-over only
                 else mbar_arrive(tempty_bar(as));
             }
             if (++as == kAccStages) { as = 0; aphase ^= 1; }

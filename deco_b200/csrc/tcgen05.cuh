@@ -103,6 +103,11 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t local_addr, uint32_t ra
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
 }
+// Same, without release semantics: for arrivals that hand over TENSOR memory only (ordered by tcgen05.fence), so that
+// the warp's outstanding global stores need not drain first (a release arrive compiles to MEMBAR + ERRBAR).
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
+}
 // TMA load whose completion bytes are credited to a barrier that may live in the PEER CTA of the pair
 __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
     asm volatile(

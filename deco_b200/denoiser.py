@@ -14,6 +14,7 @@ Per forward (B' = CFG rows, L tokens, H hidden):
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -214,6 +215,57 @@ def interleave_w13(w1: torch.Tensor, w3: torch.Tensor, Fp: int) -> torch.Tensor:
     return torch.stack([a.view(Fp // 16, 16, H), b.view(Fp // 16, 16, H)], dim=1).reshape(2 * Fp, H).contiguous()
 
 
+class StreamState:
+    """Working set of the fused block path: fp32 stream s, its pre-modulated bf16 copy xg for the NEXT norm, and the
+    ping-pong partial sums of squares the FE_STREAM epilogues leave for the consumer GEMMs (csrc/gemm_fused.cu)."""
+
+    def __init__(self, M: int, H: int, ffn: int, device):
+        self.s = torch.empty((M, H), dtype=torch.float32, device=device)
+        self.xg = torch.empty((M, H), dtype=bf16, device=device)
+        self.ssq = torch.empty((2, ops.gemm_stream_parts(H), M), dtype=torch.float32, device=device)
+        self.qkv = torch.empty((M, 3 * H), dtype=bf16, device=device)
+        self.o = torch.empty((M, H), dtype=bf16, device=device)
+        self.u = torch.empty((M, ffn), dtype=bf16, device=device)
+
+
+def fused_blocks(blocks, mod: torch.Tensor, mod0: int, st: StreamState, a0: torch.Tensor, w0: torch.Tensor,
+                 b0: torch.Tensor, B: int, L: int, H: int, heads: int, pos, wp: int, ytxt=None, T: int = 0):
+    """s = a0 @ w0.T + b0, then every AdaLN block of `blocks` on the fp32 stream, with no stand-alone norm / modulate /
+    q-k-norm / RoPE pass: see csrc/gemm_fused.cu.  mod [B, *] is the batched adaLN output; block i uses the six H-wide
+    column groups starting at (mod0 + i) * 6H (shift, scale, gate) x (attention, MLP) (dit_c2i_DeCo.py:207).
+    ytxt (t2i): refined text stream bf16 [B*T, H] feeding kv_y (dit_t2i_pixnerd.py:47-49)."""
+    d = H // heads
+    nb = len(blocks)
+
+    def sl(i, j):
+        k = (mod0 + i) * 6 + j
+        return mod[:, k * H:(k + 1) * H]
+
+    # shift products sh @ W^T of every block: tiny GEMMs ([B, H] x [H, N]) that depend on the modulation only
+    shw_qkv = [ops.gemm(sl(i, 0), bp["wqkv"], None, ops.EPI_BIAS_F32) for i, bp in enumerate(blocks)]
+    shw_13 = [ops.gemm(sl(i, 3), bp["w13"], None, ops.EPI_BIAS_F32) for i, bp in enumerate(blocks)]
+    s, xg, ssq = st.s, st.xg, st.ssq
+    ops.gemm_stream(a0, w0, b0, s, rows_per_image=L, next_w=blocks[0]["n1"], next_scale=sl(0, 1), xg=xg, ssq=ssq[0])
+    for i, bp in enumerate(blocks):
+        ops.gemm_norm_qkv(xg, bp["wqkv"], st.qkv, L, heads, d, seg_w=(bp["qn"], bp["kn"], None), rope_mask=3, rope=pos,
+                          rope_tokens_per_row=wp, ssq=ssq[0], norm_hidden=H, shw=shw_qkv[i])
+        k2 = v2 = None
+        if ytxt is not None:
+            kvy = torch.empty((ytxt.shape[0], 2 * H), dtype=bf16, device=s.device)
+            ops.gemm_norm_qkv(ytxt, bp["wkvy"], kvy, T, heads, d, seg_w=(bp["kn"], None), rope_mask=0)
+            k2, v2 = kvy[:, :H], kvy[:, H:]
+        ops.attention(st.qkv[:, :H], st.qkv[:, H:2 * H], st.qkv[:, 2 * H:], B, heads, d, k2=k2, v2=v2, out=st.o)
+        ops.gemm_stream(st.o, bp["wproj"], bp["bproj"], s, resid=s, gate=sl(i, 2), rows_per_image=L,
+                        next_w=bp["n2"], next_scale=sl(i, 4), xg=xg, ssq=ssq[1])
+        ops.gemm_norm_swiglu(xg, bp["w13"], st.u, L, ssq=ssq[1], norm_hidden=H, shw=shw_13[i])
+        if i + 1 < nb:
+            ops.gemm_stream(st.u, bp["w2"], None, s, resid=s, gate=sl(i, 5), rows_per_image=L,
+                            next_w=blocks[i + 1]["n1"], next_scale=sl(i + 1, 1), xg=xg, ssq=ssq[0])
+        else:
+            ops.gemm_stream(st.u, bp["w2"], None, s, resid=s, gate=sl(i, 5), rows_per_image=L)
+    return s
+
+
 # ------------------------------------------------------------------------------------------------ the module
 class PixNerDiT(nn.Module):
     """Drop-in for src/models/transformer/dit_c2i_DeCo.py::PixNerDiT (constructor :417-433, forward :488-510)."""
@@ -245,6 +297,8 @@ class PixNerDiT(nn.Module):
         self.precompute_pos: Dict[Tuple[int, int], torch.Tensor] = {}
         self._prep = None
         self._prep_key = None
+        # fused block path (csrc/gemm_fused.cu); False = one kernel per reference op (kept for A/B measurements)
+        self.fused = os.environ.get("DECO_B200_FUSED", "1") != "0"
 
     def initialize_weights(self):
         """dit_c2i_DeCo.py:475-486."""
@@ -323,7 +377,7 @@ class PixNerDiT(nn.Module):
         return tab
 
     # -------------------------------------------------------------------------------------------- forward
-    def _encode(self, P, xp, t, y, B, L, pos):
+    def _encode(self, P, xp, t, y, B, L, pos, wp):
         """Patch tokens -> DiT blocks -> decoder condition s (dit_c2i_DeCo.py:492-499)."""
         H, heads = self.hidden_size, self.num_groups
         d = H // heads
@@ -334,6 +388,11 @@ class PixNerDiT(nn.Module):
         c = ops.cond_combine(temb, P["ytab"], y)
         # residual stream in fp32 (the reference keeps it in bf16; fp32 costs ~4 % more HBM traffic per block and
         # halves the distance to the fp32 reference -- DESIGN.md "precision")
+        if nb and self.fused and heads % 2 == 0 and H % 32 == 0:
+            mod = ops.gemm(c, P["wada"], P["bada"], ops.EPI_BIAS)                   # [B, nb*6H]
+            st = StreamState(B * L, H, P["ffn_pad"], xp.device)
+            s = fused_blocks(P["blocks"], mod, 0, st, xp, P["ws"], P["bs"], B, L, H, heads, pos, wp)
+            return ops.silu_add_rows(s, temb, L, out=st.o)
         s = ops.gemm(xp, P["ws"], P["bs"], ops.EPI_BIAS_F32)                        # [B*L, H] fp32
         if nb:
             mod = ops.gemm(c, P["wada"], P["bada"], ops.EPI_BIAS)                   # [B, nb*6H]
@@ -372,7 +431,7 @@ class PixNerDiT(nn.Module):
             if s is None:
                 pos = self.fetch_pos(Hh // p, Ww // p, x.device)
                 xp = ops.patchify(x32, p)
-                s2 = self._encode(P, xp, t.reshape(-1).to(torch.float32), y.reshape(-1), B, L, pos)
+                s2 = self._encode(P, xp, t.reshape(-1).to(torch.float32), y.reshape(-1), B, L, pos, Ww // p)
             else:
                 s2 = s.detach().reshape(B * L, H).to(bf16).contiguous()
             ycond = ops.gemm(s2, P["wcond"], P["bcond"], ops.EPI_BIAS)

@@ -17,13 +17,15 @@ Per forward:  t sinusoid -> 2 GEMMs -> silu -> ONE adaLN GEMM for all text + ima
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Tuple
 
 import torch
 import torch.nn as nn
 
 from . import ops
-from .denoiser import (_Embed, _NerfEmbedder, _PixelDecoder, _TimestepEmbedder, _Weight, interleave_w13, pack_decoder)
+from .denoiser import (StreamState, _Embed, _NerfEmbedder, _PixelDecoder, _TimestepEmbedder, _Weight, fused_blocks,
+                       interleave_w13, pack_decoder)
 
 bf16 = torch.bfloat16
 
@@ -124,6 +126,7 @@ class PixNerDiT(nn.Module):
         self.load_ema = load_ema
         self._prep = None
         self._prep_key = None
+        self.fused = os.environ.get("DECO_B200_FUSED", "1") != "0"   # image blocks on csrc/gemm_fused.cu
 
     def initialize_weights(self):
         """dit_t2i_pixnerd.py:258-270 (the decoder's zero-init lives in _PixelDecoder)."""
@@ -264,7 +267,13 @@ class PixNerDiT(nn.Module):
             ytxt = ops.cast_bf16(ys)
             # ---- image path
             xp = ops.patchify(x32, p)
-            s = ops.gemm(xp, P["ws"], P["bs"], ops.EPI_BIAS_F32)
+            if ni and self.fused and self.num_groups % 2 == 0 and H % 32 == 0:
+                st = StreamState(B * L, H, P["ffn"], dev)
+                s = fused_blocks(P["blocks"], mod, nt, st, xp, P["ws"], P["bs"], B, L, H, self.num_groups, pos,
+                                 Ww // p, ytxt=ytxt, T=T)
+                ni = 0
+            else:
+                s = ops.gemm(xp, P["ws"], P["bs"], ops.EPI_BIAS_F32)
             if ni:
                 bufs = self._bufs(B * L, P, dev)
                 for i, bp in enumerate(P["blocks"]):

@@ -62,6 +62,97 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     return out
 
 
+def gemm_stream_parts(N: int) -> int:
+    return _lib.load().deco_gemm_stream_parts(int(N))
+
+
+def gemm_stream(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor,
+                resid: Optional[torch.Tensor] = None, gate: Optional[torch.Tensor] = None, rows_per_image: int = 1,
+                next_w: Optional[torch.Tensor] = None, next_scale: Optional[torch.Tensor] = None,
+                xg: Optional[torch.Tensor] = None, ssq: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Residual-stream GEMM (csrc/gemm_fused.cu FE_STREAM): out = [resid + gate *] (a @ w.T + bias) in fp32 (out may be
+    resid), plus ssq[p, row] partial sums of squares of out and xg = bf16(out * next_w * (1 + next_scale))."""
+    _cuda(a, w, bias, out, resid, gate, next_w, next_scale, xg, ssq)
+    assert a.dtype == bf16 and w.dtype == bf16 and a.stride(1) == 1 and w.stride(1) == 1
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K and out.dtype == torch.float32 and out.shape == (M, N) and out.stride(1) == 1
+    if resid is not None:
+        assert resid.dtype == torch.float32 and resid.shape == (M, N) and resid.stride(1) == 1
+    if gate is not None:
+        assert gate.dtype == bf16 and gate.shape[1] == N and gate.stride(1) == 1 and gate.shape[0] * rows_per_image >= M
+    if next_w is not None:
+        assert next_w.dtype == torch.float32 and next_w.numel() == N and next_w.is_contiguous()
+        assert next_scale.dtype == bf16 and next_scale.shape[1] == N and next_scale.stride(1) == 1
+        assert next_scale.shape[0] * rows_per_image >= M
+        assert xg is not None and xg.dtype == bf16 and xg.shape == (M, N) and xg.stride(1) == 1
+    if ssq is not None:
+        assert ssq.dtype == torch.float32 and ssq.is_contiguous() and ssq.shape == (gemm_stream_parts(N), M)
+    probe = gemm_probe
+    ev = probe.before() if probe is not None else None
+    call("deco_gemm_stream", ptr(a), a.stride(0), ptr(w), w.stride(0), M, N, K, ptr(bias), ptr(resid),
+         resid.stride(0) if resid is not None else 0, ptr(out), out.stride(0), ptr(gate),
+         gate.stride(0) if gate is not None else 0, rows_per_image, ptr(next_w), ptr(next_scale),
+         next_scale.stride(0) if next_scale is not None else 0, ptr(xg), xg.stride(0) if xg is not None else 0,
+         ptr(ssq), _st(a))
+    if probe is not None:
+        probe.after(ev, 2.0 * M * N * K)
+    return out
+
+
+def gemm_norm_qkv(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, rows_per_image: int, heads: int, head_dim: int,
+                  seg_w=(None, None, None), rope_mask: int = 0, rope: Optional[torch.Tensor] = None,
+                  rope_tokens_per_row: int = 0, ssq: Optional[torch.Tensor] = None, norm_hidden: int = 0, shw: Optional[torch.Tensor] = None,
+                  norm_eps: float = 1e-6, head_eps: float = 1e-6) -> torch.Tensor:
+    """out = headnorm/rope(rstd * (a @ w.T) + shw[row // rows_per_image]) (csrc/gemm_fused.cu FE_NORM_QKV)."""
+    _cuda(a, w, out, rope, ssq, shw, *seg_w)
+    assert a.dtype == bf16 and w.dtype == bf16 and a.stride(1) == 1 and w.stride(1) == 1
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K and out.dtype == bf16 and out.shape == (M, N) and out.stride(1) == 1
+    if ssq is not None:
+        assert ssq.dtype == torch.float32 and ssq.is_contiguous() and ssq.dim() == 2 and ssq.shape[1] == M
+    if shw is not None:
+        assert shw.dtype == torch.float32 and shw.shape[1] == N and shw.stride(1) == 1 and shw.shape[0] * rows_per_image >= M
+    if rope is not None:
+        assert rope.dtype == torch.float32 and rope.is_contiguous() and rope.shape == (rows_per_image, head_dim // 2, 2)
+    sw = list(seg_w) + [None] * (3 - len(seg_w))
+    for t in sw:
+        assert t is None or (t.dtype == torch.float32 and t.numel() == head_dim and t.is_contiguous())
+    probe = gemm_probe
+    ev = probe.before() if probe is not None else None
+    call("deco_gemm_norm_qkv", ptr(a), a.stride(0), ptr(w), w.stride(0), ptr(out), out.stride(0), M, N, K, rows_per_image,
+         ptr(ssq), ssq.shape[0] if ssq is not None else 0, norm_hidden, float(norm_eps), ptr(shw),
+         shw.stride(0) if shw is not None else 0, heads, head_dim, ptr(sw[0]), ptr(sw[1]), ptr(sw[2]), rope_mask,
+         ptr(rope), int(rope_tokens_per_row), float(head_eps), _st(a))
+    if probe is not None:
+        probe.after(ev, 2.0 * M * N * K)
+    return out
+
+
+def gemm_norm_swiglu(a: torch.Tensor, w13: torch.Tensor, out: torch.Tensor, rows_per_image: int,
+                     ssq: Optional[torch.Tensor] = None, norm_hidden: int = 0, shw: Optional[torch.Tensor] = None,
+                     norm_eps: float = 1e-6) -> torch.Tensor:
+    """out = silu(y_a) * y_b with y = rstd * (a @ w13.T) + shw[row // rows_per_image] on the interleaved columns."""
+    _cuda(a, w13, out, ssq, shw)
+    assert a.dtype == bf16 and w13.dtype == bf16 and a.stride(1) == 1 and w13.stride(1) == 1
+    M, K = a.shape
+    N = w13.shape[0]
+    assert w13.shape[1] == K and out.dtype == bf16 and out.shape == (M, N // 2) and out.stride(1) == 1
+    if ssq is not None:
+        assert ssq.dtype == torch.float32 and ssq.is_contiguous() and ssq.dim() == 2 and ssq.shape[1] == M
+    if shw is not None:
+        assert shw.dtype == torch.float32 and shw.shape[1] == N and shw.stride(1) == 1 and shw.shape[0] * rows_per_image >= M
+    probe = gemm_probe
+    ev = probe.before() if probe is not None else None
+    call("deco_gemm_norm_swiglu", ptr(a), a.stride(0), ptr(w13), w13.stride(0), ptr(out), out.stride(0), M, N, K,
+         rows_per_image, ptr(ssq), ssq.shape[0] if ssq is not None else 0, norm_hidden, float(norm_eps), ptr(shw),
+         shw.stride(0) if shw is not None else 0, _st(a))
+    if probe is not None:
+        probe.after(ev, 2.0 * M * N * K)
+    return out
+
+
 def patchify(x: torch.Tensor, p: int) -> torch.Tensor:
     _cuda(x)
     assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4

@@ -45,6 +45,46 @@ int deco_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, v
                    const void* resid, long long ldr, const void* gate, long long gate_stride, int rows_per_gate,
                    int tile_n, void* stream);
 
+/* ---- GEMMs whose epilogues absorb the memory-bound neighbours of a DiT block (csrc/gemm_fused.cu) ----
+ * RMSNorm commutes with the following Linear because its row factor is a scalar:
+ *   Linear(modulate(RMSNorm(x))) = rstd[row] * ((x * w_norm * (1 + scale)) . W^T) + (shift . W^T)[image]
+ * so the producer of x emits xg = bf16(x * w_norm * (1 + scale)) and per-row partial sums of squares, the consumer GEMM
+ * applies rstd and adds the (tiny, separately computed) shift product.  Replaces, per FlattenDiTBlock.forward
+ * (dit_c2i_DeCo.py:206-210), the stand-alone RMSNorm/modulate passes (:94-99, :11-12) and q/k-norm + RoPE (:178-180). */
+
+/* Residual-stream update (dit_c2i_DeCo.py:208/:209, also :496 with resid = gate = NULL):
+ *   out = [resid + gate[row / rows_per_image] *] (A.W^T + bias)          fp32 [M, N], may alias resid
+ *   ssq_out[p][row] = sum over the p-th column tile of out[row]^2        fp32 [deco_gemm_stream_parts(N)][M] or NULL
+ *   xg_out = bf16(out * next_norm_w * (1 + next_scale[row / rows_per_image]))   or nothing when next_norm_w = NULL
+ * N % 32 == 0; gate / next_scale are bf16 [M / rows_per_image, stride]. */
+int deco_gemm_stream_parts(int N);
+int deco_gemm_stream(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K,
+                     const float* bias, const float* resid, long long ldr, float* out, long long ldo,
+                     const void* gate, long long gate_stride, int rows_per_image,
+                     const float* next_norm_w, const void* next_scale, long long next_scale_stride,
+                     void* xg_out, long long ldx, float* ssq_out, void* stream);
+
+/* QKV projection of a normalised + modulated stream with q_norm / k_norm / RoPE fused (dit_c2i_DeCo.py:176-180;
+ * dit_t2i_pixnerd.py:43-50, :170-173):  y = rstd[row] * (A.W^T) + shw[row / rows_per_image], rstd from ssq_in (NULL: 1,
+ * shw NULL: 0).  N = 1..3 segments of heads*head_dim columns; segment i gets a per-head RMSNorm with weight w_seg<i>
+ * (NULL: passed through) and RoPE when bit i of rope_mask is set (table fp32 [rows_per_image, head_dim/2, 2]).
+ * rope_tokens_per_row > 0 declares the table AXIAL as built by precompute_freqs_cis_2d / _ex2d (dit_c2i_DeCo.py:116-131,
+ * layers/rope.py:22-37): even pairs depend on tok % tokens_per_row only, odd pairs on tok / tokens_per_row only, so the
+ * kernel keeps just those rows in shared memory; 0 = arbitrary table, read from global memory. bf16 out. */
+int deco_gemm_norm_qkv(const void* A, long long lda, const void* W, long long ldw, void* out, long long ldo,
+                       int M, int N, int K, int rows_per_image,
+                       const float* ssq_in, int ssq_parts, int norm_hidden, float norm_eps,
+                       const float* shw, long long shw_stride,
+                       int heads, int head_dim, const float* w_seg0, const float* w_seg1, const float* w_seg2,
+                       int rope_mask, const float* rope_cos_sin, int rope_tokens_per_row, float head_eps, void* stream);
+
+/* SwiGLU up-projection of a normalised + modulated stream (dit_c2i_DeCo.py:113 on :209's modulate input): W rows
+ * interleaved [16 x w1 | 16 x w3] as for DECO_EPI_SWIGLU; out bf16 [M, N/2]. */
+int deco_gemm_norm_swiglu(const void* A, long long lda, const void* W, long long ldw, void* out, long long ldo,
+                          int M, int N, int K, int rows_per_image,
+                          const float* ssq_in, int ssq_parts, int norm_hidden, float norm_eps,
+                          const float* shw, long long shw_stride, void* stream);
+
 /* Tuning knob (process-wide, for A/B measurements): cta_group -1 = auto (2-CTA pairs when M > 128), 1, 2;
  * staged_epilogue -1 = auto (staged with 2-CTA), 0 = direct row-per-thread stores, 1 = shared-memory staged. */
 int deco_gemm_set_tuning(int cta_group, int staged_epilogue);

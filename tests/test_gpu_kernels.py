@@ -255,3 +255,126 @@ def test_cfg_step(cuda_dev, net_dtype):
     assert torch.allclose(v2, vr, atol=1e-5) and torch.allclose(x2, x + 0.5 * vr, atol=1e-5)
     z = torch.tensor([-1.5, -1.0, -0.999, 0.0, 0.5, 0.996, 1.0, 3.0], device=cuda_dev)
     assert torch.equal(ops.fp2uint8(z), O.fp2uint8(z))
+
+
+# ------------------------------------------------------------------------------------------------ fused-epilogue GEMMs
+def _fp32(fn):
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        return fn()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+@pytest.mark.parametrize("M,N,K,L,mode", [
+    (512, 1152, 1152, 256, "full"), (1000, 1152, 3072, 250, "full"), (96, 576, 576, 16, "full"),
+    (300, 256, 256, 100, "full"), (512, 1536, 6144, 128, "full"), (640, 1024, 2736, 64, "full"),
+    (512, 1152, 768, 256, "embed"), (512, 1152, 1152, 256, "last"),
+])
+def test_gemm_stream(cuda_dev, M, N, K, L, mode):
+    """FE_STREAM: out = [resid + gate *](A.W^T + bias) in place, row sums of squares, pre-modulated bf16 copy."""
+    from deco_b200 import ops
+    nimg = (M + L - 1) // L
+    a, w = _rand((M, K), cuda_dev, 1), _rand((N, K), cuda_dev, 2, K ** -0.5)
+    bias = _rand((N,), cuda_dev, 3, 0.1, torch.float32)
+    resid = _rand((M, N), cuda_dev, 4, 1.5, dtype=torch.float32)
+    gate = _rand((nimg, 3 * N), cuda_dev, 5)[:, N:2 * N]
+    nscale = _rand((nimg, 3 * N), cuda_dev, 6, 0.5)[:, :N]
+    nw = 1 + 0.1 * _rand((N,), cuda_dev, 7, dtype=torch.float32)
+    rep = lambda t: t.float().repeat_interleave(L, 0)[:M]   # noqa: E731
+    lin = _fp32(lambda: a.float() @ w.float().t() + bias)
+    parts = ops.gemm_stream_parts(N)
+    ssq = torch.full((parts, M), -1.0, device=cuda_dev)
+    if mode == "embed":
+        out = torch.empty((M, N), device=cuda_dev)
+        xg = torch.empty((M, N), device=cuda_dev, dtype=bf16)
+        ops.gemm_stream(a, w, bias, out, rows_per_image=L, next_w=nw, next_scale=nscale, xg=xg, ssq=ssq)
+        ref = lin
+    elif mode == "last":
+        out = resid.clone()
+        xg = None
+        ops.gemm_stream(a, w, bias, out, resid=out, gate=gate, rows_per_image=L, ssq=None)
+        ref = resid + rep(gate) * lin
+    else:
+        out = resid.clone()
+        xg = torch.empty((M, N), device=cuda_dev, dtype=bf16)
+        ops.gemm_stream(a, w, bias, out, resid=out, gate=gate, rows_per_image=L, next_w=nw, next_scale=nscale, xg=xg, ssq=ssq)
+        ref = resid + rep(gate) * lin
+    torch.cuda.synchronize()
+    assert rel_l2(out, ref) < 3e-3
+    if mode != "last":
+        assert rel_l2(ssq.sum(0), (out.double() ** 2).sum(1).float()) < 1e-5
+        assert rel_l2(xg.float(), out * nw * (1 + rep(nscale))) < 4e-3
+
+
+@pytest.mark.parametrize("axial", [True, False])
+@pytest.mark.parametrize("heads,d,hw,B,K,nseg,normed", [
+    (16, 72, (16, 16), 2, 1152, 3, True), (8, 72, (4, 4), 3, 576, 3, True), (4, 64, (10, 10), 2, 256, 3, True),
+    (24, 64, (8, 8), 2, 1536, 3, True), (4, 64, (3, 8), 2, 256, 2, False), (16, 64, (4, 4), 5, 1024, 3, True),
+    (4, 72, (32, 32), 1, 576, 3, True), (2, 64, (8, 16), 2, 256, 3, True),
+])
+def test_gemm_norm_qkv(cuda_dev, heads, d, hw, B, K, nseg, normed, axial):
+    """FE_NORM_QKV against Linear(modulate(RMSNorm(x))) -> q_norm/k_norm -> RoPE evaluated in fp32 torch.
+    nseg=2, normed=False is the t2i kv_y projection: k-norm only on segment 0, no RoPE, no input normalisation."""
+    from deco_b200 import ops
+    from deco_b200.denoiser import rope_cos_sin
+    L = hw[0] * hw[1]
+    M, H = B * L, heads * d
+    N = nseg * H
+    w = _rand((N, K), cuda_dev, 2, K ** -0.5)
+    qw = 1 + 0.1 * _rand((d,), cuda_dev, 3, dtype=torch.float32)
+    kw = 1 + 0.1 * _rand((d,), cuda_dev, 4, dtype=torch.float32)
+    out = torch.empty((M, N), device=cuda_dev, dtype=bf16)
+    if normed:
+        x = _rand((M, K), cuda_dev, 1, 3.0, dtype=torch.float32)
+        nw = 1 + 0.1 * _rand((K,), cuda_dev, 5, dtype=torch.float32)
+        mod = _rand((B, 2 * K), cuda_dev, 6, 0.5)
+        sh, sc = mod[:, :K], mod[:, K:]
+        xg = (x * nw * (1 + sc.float().repeat_interleave(L, 0))).to(bf16)
+        # partial sums of squares in 3 parts, as the producing GEMM would leave them
+        ssq = torch.stack([(x[:, i::3] ** 2).sum(1) for i in range(3)]).contiguous()
+        shw = _fp32(lambda: sh.float() @ w.float().t()).contiguous()
+        rope = rope_cos_sin(d, hw[0], hw[1]).to(cuda_dev)
+        ops.gemm_norm_qkv(xg, w, out, L, heads, d, seg_w=(qw, kw, None), rope_mask=3, rope=rope,
+                          rope_tokens_per_row=(hw[1] if axial else 0), ssq=ssq, norm_hidden=K, shw=shw)
+        h = O.modulate(O.rmsnorm(x, nw), sh.float().repeat_interleave(L, 0), sc.float().repeat_interleave(L, 0))
+        y = _fp32(lambda: h @ w.float().t()).view(B, L, 3, heads, d)
+        ang = O.rope_table_2d(d, hw[0], hw[1]).to(cuda_dev)
+        ref = torch.stack([O.apply_rope(O.rmsnorm(y[:, :, 0], qw), ang), O.apply_rope(O.rmsnorm(y[:, :, 1], kw), ang),
+                           y[:, :, 2]], dim=2)
+    else:
+        a = _rand((M, K), cuda_dev, 1)
+        ops.gemm_norm_qkv(a, w, out, L, heads, d, seg_w=(kw, None), rope_mask=0)
+        y = _fp32(lambda: a.float() @ w.float().t()).view(B, L, 2, heads, d)
+        ref = torch.stack([O.rmsnorm(y[:, :, 0], kw), y[:, :, 1]], dim=2)
+    torch.cuda.synchronize()
+    g = out.view(ref.shape).float()
+    for s in range(nseg):
+        assert rel_l2(g[:, :, s], ref[:, :, s]) < 6e-3, s
+
+
+@pytest.mark.parametrize("M,F_,K,L", [(512, 3072, 1152, 256), (300, 592, 576, 100), (640, 2736, 1024, 64), (256, 6144, 1536, 128)])
+def test_gemm_norm_swiglu(cuda_dev, M, F_, K, L):
+    from deco_b200 import ops
+    from deco_b200.denoiser import interleave_w13
+    B = (M + L - 1) // L
+    x = _rand((M, K), cuda_dev, 1, 3.0, dtype=torch.float32)
+    nw = 1 + 0.1 * _rand((K,), cuda_dev, 5, dtype=torch.float32)
+    mod = _rand((B, 2 * K), cuda_dev, 6, 0.5)
+    sh, sc = mod[:, :K], mod[:, K:]
+    rep = lambda t: t.float().repeat_interleave(L, 0)[:M]   # noqa: E731
+    xg = (x * nw * (1 + rep(sc))).to(bf16)
+    ssq = torch.stack([(x[:, i::2] ** 2).sum(1) for i in range(2)]).contiguous()
+    w1, w3 = _rand((F_, K), cuda_dev, 2, K ** -0.5), _rand((F_, K), cuda_dev, 3, K ** -0.5)
+    Fp = (F_ + 15) // 16 * 16
+    w13 = interleave_w13(w1, w3, Fp)
+    shw = _fp32(lambda: sh.float() @ w13.float().t()).contiguous()
+    out = torch.empty((M, Fp), device=cuda_dev, dtype=bf16)
+    ops.gemm_norm_swiglu(xg, w13, out, L, ssq=ssq, norm_hidden=K, shw=shw)
+    h = O.modulate(O.rmsnorm(x, nw), rep(sh), rep(sc))
+    ref = _fp32(lambda: F.silu(h @ w1.float().t()) * (h @ w3.float().t()))
+    torch.cuda.synchronize()
+    assert rel_l2(out[:, :F_].float(), ref) < 6e-3
+    if Fp > F_:
+        assert float(out[:, F_:].float().abs().max()) == 0.0

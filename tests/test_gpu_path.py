@@ -92,6 +92,24 @@ def test_t2i_xxl_forward_vs_oracle(cuda_dev):
     assert e <= 1e-2
 
 
+def test_fused_and_unfused_block_paths_agree(cuda_dev):
+    """The fused-epilogue block path (csrc/gemm_fused.cu) and the one-kernel-per-op path are two evaluations of the
+    same function: both within tolerance of the reference fixture, and close to each other."""
+    g = load_golden("fwd_d72.npz")
+    cfg = cfg_from_array(g["cfg"])
+    m, _ = build_module(cfg, cuda_dev)
+    x, t, y = (torch.from_numpy(g[k]).to(cuda_dev) for k in ("x", "t", "y"))
+    ref = torch.from_numpy(g["out"])
+    outs = {}
+    for fused in (True, False):
+        m.fused = fused
+        outs[fused] = m(x, t, y).float()
+        e = rel_l2(outs[fused], ref)
+        print(f"fused={fused}: rel-L2 vs reference fp32 = {e:.3e}")
+        assert e <= 1e-2
+    assert rel_l2(outs[True], outs[False]) <= 1e-2
+
+
 def test_pixel_decoder_alone(cuda_dev):
     """forward(x, t, y, s=...) skips the DiT (dit_c2i_DeCo.py:495): isolates cond_embed GEMM + fused decoder."""
     cfg = O.DenoiserCfg(num_groups=4, hidden_size=256, num_blocks=5, num_cond_blocks=2, num_classes=10)
