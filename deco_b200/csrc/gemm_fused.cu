@@ -32,7 +32,10 @@ constexpr int kThreads = 256;
 constexpr int kAccStages = 2;
 constexpr int kMaxSsqParts = 16;   // column tiles of the producing FE_STREAM GEMM (hidden <= 16 x 128)
 
-enum FusedEpi : int { FE_STREAM = 0, FE_NORM_QKV = 1, FE_NORM_SWIGLU = 2 };
+// FE_STREAM_RING = FE_STREAM with a 3-deep ring of residual chunk buffers per warp instead of a whole staged tile: 48 KB
+// less staging = two more operand stages, for the deep-K (w2) GEMM whose main loop is latency-bound on operand loads
+// while its epilogue has time to spare; the K = hidden GEMMs keep the whole-tile prefetch (epilogue is HBM-bound there).
+enum FusedEpi : int { FE_STREAM = 0, FE_NORM_QKV = 1, FE_NORM_SWIGLU = 2, FE_STREAM_RING = 3 };
 
 struct Maps { CUtensorMap a, b, r, o, x; };   // A, W, residual in (fp32), stream out (fp32) / qkv out (bf16), xg out (bf16)
 
@@ -75,19 +78,24 @@ template <int BN, int EPI> struct Cfg {
     //   FE_STREAM      fp32 [BN/32 chunks][32 rows][128 B] (SW128, residual in / stream out) + 3 x [BN] fp32 coefficients
     //   FE_NORM_QKV    2 x bf16 [32 rows][d] (output) + [BN] fp32 shift product
     //   FE_NORM_SWIGLU [BN] fp32 shift product
-    static constexpr int kVecBytes = EPI == FE_STREAM ? 3 * BN * 4 : BN * 4;
-    static constexpr int kOutStage = EPI == FE_STREAM ? (BN / 32) * 4096 : EPI == FE_NORM_QKV ? 2 * 32 * kHeadDim * 2 : 0;
-    static constexpr int kWarpStage = ((kOutStage + kVecBytes + 1023) / 1024) * 1024;
+    static constexpr bool kStream = EPI == FE_STREAM || EPI == FE_STREAM_RING;
+    static constexpr int kRing = 3;
+    static constexpr int kVecBytes = kStream ? 3 * BN * 4 : BN * 4;
+    static constexpr int kOutStage = EPI == FE_STREAM ? (BN / 32) * 4096 : EPI == FE_STREAM_RING ? kRing * 4096
+                                   : EPI == FE_NORM_QKV ? 2 * 32 * kHeadDim * 2 : 0;
+    // layout: 4 x kOutStage (1024-aligned buffers), then 4 x kVecBytes
+    static constexpr int kWarpAll = ((4 * (kOutStage + kVecBytes) + 1023) / 1024) * 1024;
+    static_assert(kOutStage % 1024 == 0, "TMA staging buffers must stay 1024-byte aligned");
     // CTA-wide tables of FE_NORM_QKV: axial RoPE (cos, sin) rows, 144-byte pitch, and the 3 head-norm weight vectors
     static constexpr int kRopePitch = 144;
     static constexpr int kRopeMaxPos = 96;
     static constexpr int kTableBytes = EPI == FE_NORM_QKV ? kRopeMaxPos * kRopePitch + 3 * kHeadDim * 4 : 0;
-    static constexpr int kEpiBytes = 4 * kWarpStage + ((kTableBytes + 1023) / 1024) * 1024;
-    static constexpr int kBudget = 227 * 1024 - kEpiBytes - 1024 - 256;
+    static constexpr int kEpiBytes = kWarpAll + ((kTableBytes + 1023) / 1024) * 1024;
+    static constexpr int kBudget = 227 * 1024 - kEpiBytes - 1024 - 512;
     static constexpr int kStagesRaw = kBudget / kStageBytes;
     static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
     static constexpr int kTmemCols = (kAccStages * BN > 256) ? 512 : 256;
-    static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 + 256;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align slack*/ + 512 /*barriers*/;
     static_assert(kStages >= 3, "not enough shared memory for the operand ring");
     static_assert(kStageBytes % 1024 == 0, "stage must keep the 1024-byte swizzle alignment");
 };
@@ -127,7 +135,8 @@ gemm_fused_kernel(const __grid_constant__ Maps maps, const Params P)
     auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * C::kStages + s); };
     auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * C::kStages + kAccStages + s); };
     auto resid_bar = [&](int w) { return bar_base + 8u * (2 * C::kStages + 2 * kAccStages + w); };
-    const uint32_t tmem_slot = bar_base + 8u * (2 * C::kStages + 2 * kAccStages + 4);
+    auto ring_bar = [&](int w, int b) { return bar_base + 8u * (2 * C::kStages + 2 * kAccStages + 4 + w * 3 + b); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * C::kStages + 2 * kAccStages + 16);
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -142,12 +151,12 @@ gemm_fused_kernel(const __grid_constant__ Maps maps, const Params P)
         tma_prefetch_desc(&maps.a);
         tma_prefetch_desc(&maps.b);
         if (EPI != FE_NORM_SWIGLU) tma_prefetch_desc(&maps.o);
-        if (EPI == FE_STREAM) tma_prefetch_desc(&maps.r);
+        if (C::kStream) tma_prefetch_desc(&maps.r);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < C::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         for (int s = 0; s < kAccStages; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8); }
-        for (int w = 0; w < 4; ++w) mbar_init(resid_bar(w), 1);
+        for (int w = 0; w < 4; ++w) { mbar_init(resid_bar(w), 1); for (int b = 0; b < 3; ++b) mbar_init(ring_bar(w, b), 1); }
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc_2sm(tmem_slot, C::kTmemCols);
@@ -210,8 +219,8 @@ gemm_fused_kernel(const __grid_constant__ Maps maps, const Params P)
         // warp spanning several images, arbitrary RoPE tables) with per-thread global loads.
         const int q = warp & 3;
         int as = 0; uint32_t aphase = 0;
-        const uint32_t wstg = epi_base + q * C::kWarpStage;
-        const uint32_t vec = wstg + C::kOutStage;
+        const uint32_t wstg = epi_base + q * C::kOutStage;
+        const uint32_t vec = epi_base + 4 * C::kOutStage + q * C::kVecBytes;
         const bool uni = (P.L % 32) == 0;   // the 32 rows of a warp belong to one image
         auto release_acc = [&]() {
             // TMEM reads are complete (tcgen05.wait::ld) and fenced; the arrive carries no generic-memory data, so it
@@ -222,15 +231,28 @@ gemm_fused_kernel(const __grid_constant__ Maps maps, const Params P)
         };
         auto tile_row0 = [&](int tile) { return ((tile / num_n) * 2 + (int)cta_rank) * kBM + q * 32; };
 
-        if (EPI == FE_STREAM) {
+        if (C::kStream) {
+            constexpr bool RING = EPI == FE_STREAM_RING;
             constexpr int NC = BN / 32;
             constexpr int NV = BN / 64;        // column pairs per lane
             const bool fast = uni && P.has_resid;
             uint32_t rphase = 0;
+            // whole-tile staging: all NC residual chunks of the next tile are requested when this tile's stores are out
             auto issue_resid = [&](int tile) {
                 const int r0 = tile_row0(tile), n_blk = tile % num_n;
                 mbar_expect_tx(resid_bar(q), NC * 4096);
                 for (int c = 0; c < NC; ++c) tma_load_2d(wstg + c * 4096, &maps.r, resid_bar(q), n_blk * BN + c * 32, r0);
+            };
+            // ring staging: chunk sequence number g lives in buffer g % 3; the load of chunk g + 2 is issued when the
+            // store of chunk g - 1 has released that buffer
+            int ltile = tile0, lc = 0, lseq = 0, gseq = 0;
+            auto issue_next_chunk = [&]() {
+                if (ltile >= num_tiles) return;
+                const int b = lseq % 3;
+                mbar_expect_tx(ring_bar(q, b), 4096);
+                tma_load_2d(wstg + b * 4096, &maps.r, ring_bar(q, b), (ltile % num_n) * BN + lc * 32, tile_row0(ltile));
+                ++lseq;
+                if (++lc == NC) { lc = 0; ltile += tile_stride; }
             };
             // raw per-column operands of the coefficient vectors, fetched one tile ahead
             uint32_t rg[NV], rs_[NV];
@@ -250,7 +272,10 @@ gemm_fused_kernel(const __grid_constant__ Maps maps, const Params P)
                 }
             };
             if (tile0 < num_tiles) {
-                if (P.has_resid && lane == 0) issue_resid(tile0);
+                if (P.has_resid && lane == 0) {
+                    if (RING) { issue_next_chunk(); issue_next_chunk(); issue_next_chunk(); }
+                    else issue_resid(tile0);
+                }
                 if (uni) fetch(tile0);
             }
             for (int tile = tile0; tile < num_tiles; tile += tile_stride) {
@@ -276,7 +301,7 @@ gemm_fused_kernel(const __grid_constant__ Maps maps, const Params P)
                     __syncwarp();
                     if (tile + tile_stride < num_tiles) fetch(tile + tile_stride);
                 }
-                if (P.has_resid) { mbar_wait(resid_bar(q), rphase); rphase ^= 1; }
+                if (!RING && P.has_resid) { mbar_wait(resid_bar(q), rphase); rphase ^= 1; }
                 mbar_wait(tfull_bar(as), aphase);
                 tc_fence_after();
                 float ssq = 0.f;
@@ -288,9 +313,10 @@ gemm_fused_kernel(const __grid_constant__ Maps maps, const Params P)
                         tmem_ld32(taddr + (uint32_t)(c * 32), acc);
                         tmem_ld_wait();
                         if (c == NC - 1) release_acc();          // accumulator stage is free for the next-but-one tile
-                        const int n0 = nbase + c * 32;
-                        if (n0 >= P.N) continue;                 // warp-uniform (N % 32 == 0)
-                        const uint32_t crow = wstg + c * 4096 + lane * 128;
+                        const int n0 = nbase + c * 32;           // < N: the host requires N % BN == 0
+                        const int buf = RING ? gseq % 3 : c;
+                        if (RING && P.has_resid) mbar_wait(ring_bar(q, buf), (uint32_t)((gseq / 3) & 1));
+                        const uint32_t crow = wstg + buf * 4096 + lane * 128;
 #pragma unroll
                         for (int j = 0; j < 8; j += 2) {
                             uint32_t xb[4];
@@ -342,20 +368,27 @@ gemm_fused_kernel(const __grid_constant__ Maps maps, const Params P)
                         fence_proxy_async();
                         __syncwarp();
                         if (lane == 0) {
-                            tma_store_2d(&maps.o, wstg + c * 4096, n0, row0);
+                            tma_store_2d(&maps.o, wstg + buf * 4096, n0, row0);
                             bulk_commit();
+                            if (RING) {
+                                bulk_wait_read<1>();             // the store of chunk g - 1 has released its buffer
+                                if (P.has_resid && gseq >= 1) issue_next_chunk();
+                            }
                         }
+                        if (RING) { ++gseq; __syncwarp(); }
                     }
                 };
                 if (fast) body(std::true_type{}); else body(std::false_type{});
                 if (P.ssq_out && row < P.M) P.ssq_out[(long long)n_blk * P.M + row] = ssq;
-                // the staging tile is reused by the next tile's residual prefetch once the stores have read it
-                if (lane == 0) {
-                    bulk_wait_read<0>();
-                    const int next = tile + tile_stride;
-                    if (P.has_resid && next < num_tiles) issue_resid(next);
+                if (!RING) {
+                    // the staging tile is reused by the next tile's residual prefetch once the stores have read it
+                    if (lane == 0) {
+                        bulk_wait_read<0>();
+                        const int next = tile + tile_stride;
+                        if (P.has_resid && next < num_tiles) issue_resid(next);
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
                 if (++as == kAccStages) { as = 0; aphase ^= 1; }
             }
             if (lane == 0) bulk_wait_all();
@@ -364,7 +397,7 @@ gemm_fused_kernel(const __grid_constant__ Maps maps, const Params P)
             constexpr int kRowBytes = D * 2;
             constexpr int NV4 = (BN / 4 + 31) / 32;   // float4 of the shift product per lane
             // ---- CTA-wide tables: axial RoPE rows (x positions, y positions, one identity row), head-norm weights
-            const uint32_t tbl = epi_base + 4 * C::kWarpStage;
+            const uint32_t tbl = epi_base + C::kWarpAll;
             const uint32_t tblw = tbl + C::kRopeMaxPos * C::kRopePitch;
             const int Wp = P.rope_wp;
             const int Hp = Wp > 0 ? P.L / Wp : 0;
@@ -701,6 +734,7 @@ extern "C" int deco_gemm_stream(const void* A, long long lda, const void* W, lon
                                     ((uintptr_t)xg_out & 15) == 0 && ((uintptr_t)next_scale & 7) == 0),
                    "gemm_stream: next-norm arguments invalid");
     const int bn = stream_tile_n(N);
+    DECO_CHECK_ARG(N % bn == 0, "gemm_stream: N must be a multiple of 128 (or of 192)");
     Maps maps;
     if ((rc = make_map(&maps.a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, A, M, K, lda, kBK, kBM, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
     if ((rc = make_map(&maps.b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, W, N, K, ldw, kBK, bn / 2, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
@@ -714,8 +748,11 @@ extern "C" int deco_gemm_stream(const void* A, long long lda, const void* W, lon
     P.bias = bias; P.gate = (const __nv_bfloat16*)gate; P.gate_stride = gate_stride; P.has_resid = resid ? 1 : 0;
     P.next_w = next_norm_w; P.next_scale = (const __nv_bfloat16*)next_scale; P.next_scale_stride = next_scale_stride;
     P.ssq_out = ssq_out; P.xg = (__nv_bfloat16*)xg_out; P.ldx = ldx;
-    if (bn == 192) return launch<192, FE_STREAM>(maps, P, (cudaStream_t)stream);
-    return launch<128, FE_STREAM>(maps, P, (cudaStream_t)stream);
+    static int ring_k = -1;   // K above which the ring-staged variant is used (DECO_STREAM_RING_K overrides, 0 = never)
+    if (ring_k < 0) { const char* e = getenv("DECO_STREAM_RING_K"); ring_k = e ? atoi(e) : 2048; }
+    const bool ring = ring_k > 0 && K > ring_k;
+    if (bn == 192) return ring ? launch<192, FE_STREAM_RING>(maps, P, (cudaStream_t)stream) : launch<192, FE_STREAM>(maps, P, (cudaStream_t)stream);
+    return ring ? launch<128, FE_STREAM_RING>(maps, P, (cudaStream_t)stream) : launch<128, FE_STREAM>(maps, P, (cudaStream_t)stream);
 }
 
 extern "C" int deco_gemm_norm_qkv(const void* A, long long lda, const void* W, long long ldw, void* out, long long ldo,
