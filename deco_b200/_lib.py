@@ -18,7 +18,7 @@ SIGNATURES = {
     "deco_last_error": (C.c_char_p, []),
     "deco_abi_version": (_i, []),
     "deco_gemm_bf16": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _vp, _vp, _ll, _vp, _ll, _i, _i, _vp]),
-    "deco_gemm_stream_parts": (_i, [_i]),
+    "deco_gemm_stream_parts": (_i, [_i, _i]),
     "deco_gemm_stream": (_i, [_vp, _ll, _vp, _ll, _i, _i, _i, _vp, _vp, _ll, _vp, _ll, _vp, _ll, _i, _vp, _vp, _ll, _vp, _ll,
                               _vp, _vp]),
     "deco_gemm_norm_qkv": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _vp, _i, _i, _f, _vp, _ll, _i, _i, _vp, _vp, _vp,

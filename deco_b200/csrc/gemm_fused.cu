@@ -73,14 +73,19 @@ struct Params {
 
 template <int BN, int EPI> struct Cfg {
     static constexpr int kStageBytes = kBM * kBK * 2 + (BN / 2) * kBK * 2;
-    static constexpr int kHeadDim = BN / 2;
+    // FE_NORM_QKV tiles hold whole heads: BN = 224 -> 3 heads of 72 (216 useful columns, 8 recomputed by the next tile),
+    // BN = 256 -> 4 heads of 64.  Wide tiles matter: the operand fill rate (L2 -> SMEM) caps the MMA rate of narrow ones
+    // (measured 850 / 1220 / 1590 TFLOP/s at BN = 128 / 192 / 256, profiles/gemm_bench_r1.txt).
+    static constexpr int kHeadDim = EPI == FE_NORM_QKV ? (BN == 224 ? 72 : 64) : 0;
+    static constexpr int kHeadsPerTile = EPI == FE_NORM_QKV ? (BN == 224 ? 3 : 4) : 0;
+    static constexpr int kTileN = EPI == FE_NORM_QKV ? kHeadDim * kHeadsPerTile : BN;   // column stride between tiles
     // per-warp staging
     //   FE_STREAM      fp32 [BN/32 chunks][32 rows][128 B] (SW128, residual in / stream out) + 3 x [BN] fp32 coefficients
     //   FE_NORM_QKV    2 x bf16 [32 rows][d] (output) + [BN] fp32 shift product
     //   FE_NORM_SWIGLU [BN] fp32 shift product
     static constexpr bool kStream = EPI == FE_STREAM || EPI == FE_STREAM_RING;
     static constexpr int kRing = 3;
-    static constexpr int kVecBytes = kStream ? 3 * BN * 4 : BN * 4;
+    static constexpr int kVecBytes = kStream ? 3 * BN * 4 : kTileN * 4;
     static constexpr int kOutStage = EPI == FE_STREAM ? (BN / 32) * 4096 : EPI == FE_STREAM_RING ? kRing * 4096
                                    : EPI == FE_NORM_QKV ? 2 * 32 * kHeadDim * 2 : 0;
     // layout: 4 x kOutStage (1024-aligned buffers), then 4 x kVecBytes
@@ -142,7 +147,7 @@ gemm_fused_kernel(const __grid_constant__ Maps maps, const Params P)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t cta_rank = cluster_ctarank();
     const bool is_leader = cta_rank == 0;
-    const int num_m = (P.M + 2 * kBM - 1) / (2 * kBM), num_n = (P.N + BN - 1) / BN;
+    const int num_m = (P.M + 2 * kBM - 1) / (2 * kBM), num_n = (P.N + C::kTileN - 1) / C::kTileN;
     const int num_tiles = num_m * num_n;
     const int num_k = (P.K + kBK - 1) / kBK;
     const int tile0 = blockIdx.x / 2, tile_stride = gridDim.x / 2;
@@ -172,7 +177,7 @@ gemm_fused_kernel(const __grid_constant__ Maps maps, const Params P)
             for (int tile = tile0; tile < num_tiles; tile += tile_stride) {
                 const int m_blk = tile / num_n, n_blk = tile % num_n;
                 const int arow = (m_blk * 2 + (int)cta_rank) * kBM;
-                const int brow = n_blk * BN + (int)cta_rank * (BN / 2);
+                const int brow = n_blk * C::kTileN + (int)cta_rank * (BN / 2);
                 for (int kb = 0; kb < num_k; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     const uint32_t sa = smem_base + stage * C::kStageBytes;
@@ -231,7 +236,7 @@ gemm_fused_kernel(const __grid_constant__ Maps maps, const Params P)
         };
         auto tile_row0 = [&](int tile) { return ((tile / num_n) * 2 + (int)cta_rank) * kBM + q * 32; };
 
-        if (C::kStream) {
+        if constexpr (C::kStream) {
             constexpr bool RING = EPI == FE_STREAM_RING;
             constexpr int NC = BN / 32;
             constexpr int NV = BN / 64;        // column pairs per lane
@@ -313,10 +318,12 @@ gemm_fused_kernel(const __grid_constant__ Maps maps, const Params P)
                         tmem_ld32(taddr + (uint32_t)(c * 32), acc);
                         tmem_ld_wait();
                         if (c == NC - 1) release_acc();          // accumulator stage is free for the next-but-one tile
-                        const int n0 = nbase + c * 32;           // < N: the host requires N % BN == 0
+                        const int n0 = nbase + c * 32;           // may lie beyond N in a ragged last tile: zero operands, clipped stores
                         const int buf = RING ? gseq % 3 : c;
                         if (RING && P.has_resid) mbar_wait(ring_bar(q, buf), (uint32_t)((gseq / 3) & 1));
                         const uint32_t crow = wstg + buf * 4096 + lane * 128;
+                        const bool live = n0 < P.N;              // warp-uniform (N % 32 == 0)
+                        if (live) {
 #pragma unroll
                         for (int j = 0; j < 8; j += 2) {
                             uint32_t xb[4];
@@ -365,11 +372,12 @@ gemm_fused_kernel(const __grid_constant__ Maps maps, const Params P)
                             if (srow && row < P.M)
                                 *reinterpret_cast<uint4*>(P.xg + row * P.ldx + n0 + 4 * j) = make_uint4(xb[0], xb[1], xb[2], xb[3]);
                         }
+                        }
                         fence_proxy_async();
                         __syncwarp();
                         if (lane == 0) {
-                            tma_store_2d(&maps.o, wstg + buf * 4096, n0, row0);
-                            bulk_commit();
+                            if (live) tma_store_2d(&maps.o, wstg + buf * 4096, n0, row0);
+                            bulk_commit();                       // (an empty group for a dead chunk keeps the ring's group count)
                             if (RING) {
                                 bulk_wait_read<1>();             // the store of chunk g - 1 has released its buffer
                                 if (P.has_resid && gseq >= 1) issue_next_chunk();
@@ -392,10 +400,12 @@ gemm_fused_kernel(const __grid_constant__ Maps maps, const Params P)
                 if (++as == kAccStages) { as = 0; aphase ^= 1; }
             }
             if (lane == 0) bulk_wait_all();
-        } else if (EPI == FE_NORM_QKV) {
-            constexpr int D = BN / 2;
+        } else if constexpr (EPI == FE_NORM_QKV) {
+            constexpr int D = C::kHeadDim;
+            constexpr int HPT = C::kHeadsPerTile;
+            constexpr int TN = C::kTileN;
             constexpr int kRowBytes = D * 2;
-            constexpr int NV4 = (BN / 4 + 31) / 32;   // float4 of the shift product per lane
+            constexpr int NV4 = (TN / 4 + 31) / 32;   // float4 of the shift product per lane
             // ---- CTA-wide tables: axial RoPE rows (x positions, y positions, one identity row), head-norm weights
             const uint32_t tbl = epi_base + C::kWarpAll;
             const uint32_t tblw = tbl + C::kRopeMaxPos * C::kRopePitch;
@@ -422,19 +432,20 @@ gemm_fused_kernel(const __grid_constant__ Maps maps, const Params P)
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
             }
+            int hcount = 0;
             float sq[kMaxSsqParts];
             float4 pre[NV4];
             auto fetch = [&](int tile) {
                 const long long row = tile_row0(tile) + lane;
                 const long long rowc = row < P.M ? row : (long long)P.M - 1;
-                const int nb = (tile % num_n) * BN;
+                const int nb = (tile % num_n) * TN;
 #pragma unroll
                 for (int p = 0; p < kMaxSsqParts; ++p)
                     sq[p] = (P.ssq_in && p < P.ssq_parts) ? __ldg(P.ssq_in + (long long)p * P.M + rowc) : 0.f;
 #pragma unroll
                 for (int k = 0; k < NV4; ++k) {
                     const int ci = 4 * (lane + 32 * k);
-                    pre[k] = (P.shw && uni && ci < BN && nb + ci < P.N)
+                    pre[k] = (P.shw && uni && ci < TN && nb + ci < P.N)
                                  ? __ldg(reinterpret_cast<const float4*>(P.shw + (rowc / P.L) * P.shw_stride + nb + ci))
                                  : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
@@ -448,14 +459,7 @@ gemm_fused_kernel(const __grid_constant__ Maps maps, const Params P)
                 const long long img = rowc / P.L;
                 const int tok = (int)(rowc % P.L);
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
-                const int nbase = n_blk * BN;
-                const int seg = nbase / P.seg_cols;           // warp-uniform: seg_cols % BN == 0
-                const bool do_norm = P.seg_w[seg] != nullptr;
-                const bool do_rope = P.seg_rope[seg] != 0;
-                const float2* rp = do_rope ? P.rope + (long long)tok * (D / 2) : nullptr;
-                const uint32_t txrow = tbl + ((axial && do_rope) ? tok % Wp : npos) * C::kRopePitch;
-                const uint32_t tyrow = tbl + ((axial && do_rope) ? Wp + tok / Wp : npos) * C::kRopePitch;
-                const uint32_t wrow = tblw + seg * D * 4;
+                const int nbase = n_blk * TN;
                 const float* shrow = P.shw ? P.shw + img * P.shw_stride : nullptr;
                 float ssum = 0.f;
 #pragma unroll
@@ -464,7 +468,7 @@ gemm_fused_kernel(const __grid_constant__ Maps maps, const Params P)
 #pragma unroll
                 for (int k = 0; k < NV4; ++k) {
                     const int ci = 4 * (lane + 32 * k);
-                    if (ci < BN) sts128(vec + ci * 4, pre[k]);
+                    if (ci < TN) sts128(vec + ci * 4, pre[k]);
                 }
                 __syncwarp();
                 if (tile + tile_stride < num_tiles) fetch(tile + tile_stride);
@@ -473,8 +477,18 @@ gemm_fused_kernel(const __grid_constant__ Maps maps, const Params P)
                 auto body = [&](auto fast_tag) {
                     constexpr bool F = decltype(fast_tag)::value;
 #pragma unroll 1
-                    for (int hh = 0; hh < 2; ++hh) {
+                    for (int hh = 0; hh < HPT; ++hh) {
                         const int col0 = nbase + hh * D;
+                        // a tile may straddle the q | k | v boundary: the segment is a property of the head
+                        const int seg = min(col0 / P.seg_cols, 2);
+                        const bool do_norm = P.seg_w[seg] != nullptr;
+                        const bool do_rope = P.seg_rope[seg] != 0;
+                        const float2* rp = do_rope ? P.rope + (long long)tok * (D / 2) : nullptr;
+                        const uint32_t txrow = tbl + ((axial && do_rope) ? tok % Wp : npos) * C::kRopePitch;
+                        const uint32_t tyrow = tbl + ((axial && do_rope) ? Wp + tok / Wp : npos) * C::kRopePitch;
+                        const uint32_t wrow = tblw + seg * D * 4;
+                        const int hb = hcount & 1;               // output staging buffer (double buffered across heads)
+                        ++hcount;
                         uint32_t acc[D];
                         {
                             uint32_t t32[32];
@@ -494,7 +508,7 @@ gemm_fused_kernel(const __grid_constant__ Maps maps, const Params P)
                                 for (int i = 0; i < 8; ++i) acc[(D == 72 ? 64 : 0) + i] = t8[i];
                             }
                         }
-                        if (hh == 1) release_acc();
+                        if (hh == HPT - 1) release_acc();
                         if (col0 >= P.N) continue;
                         float v[D];
                         float ss = 0.f;
@@ -509,10 +523,10 @@ gemm_fused_kernel(const __grid_constant__ Maps maps, const Params P)
                             v[i + 3] = fmaf(rstd, __uint_as_float(acc[i + 3]), s4.w);
                             ss = fmaf(v[i], v[i], fmaf(v[i + 1], v[i + 1], fmaf(v[i + 2], v[i + 2], fmaf(v[i + 3], v[i + 3], ss))));
                         }
-                        // staging buffer hh was last used by the previous tile: its store must have finished reading
+                        // staging buffer hb was last used two heads ago: that store must have finished reading
                         if (lane == 0) bulk_wait_read<1>();
                         __syncwarp();
-                        const uint32_t srow = wstg + hh * (32 * kRowBytes) + lane * kRowBytes;
+                        const uint32_t srow = wstg + hb * (32 * kRowBytes) + lane * kRowBytes;
                         const float rs = do_norm ? rsqrtf(ss / (float)D + P.eps_head) : 1.0f;
 #pragma unroll
                         for (int c8 = 0; c8 < D / 8; ++c8) {
@@ -548,7 +562,7 @@ gemm_fused_kernel(const __grid_constant__ Maps maps, const Params P)
                         fence_proxy_async();
                         __syncwarp();
                         if (lane == 0) {
-                            tma_store_2d(&maps.o, wstg + hh * (32 * kRowBytes), col0, row0);
+                            tma_store_2d(&maps.o, wstg + hb * (32 * kRowBytes), col0, row0);
                             bulk_commit();
                         }
                     }
@@ -695,17 +709,23 @@ static int launch(const Maps& maps, const Params& P, cudaStream_t st) {
     return DECO_OK;
 }
 
-static int stream_tile_n(int N) {
-    static int force = -1;
-    if (force < 0) { const char* e = getenv("DECO_STREAM_BN"); force = e ? atoi(e) : 0; }
-    if (force == 128 || (force == 192 && N % 192 == 0)) return force;
+// K above which the ring-staged FE_STREAM variant is used (DECO_STREAM_RING_K overrides, 0 = never)
+static bool stream_uses_ring(int K) {
+    static int ring_k = -1;
+    if (ring_k < 0) { const char* e = getenv("DECO_STREAM_RING_K"); ring_k = e ? atoi(e) : 2048; }
+    return ring_k > 0 && K > ring_k;
+}
+// Column tile: the ring variant affords 256-wide tiles (a ragged last tile is cheaper than narrow MMAs); whole-tile
+// staging fits 192.
+static int stream_tile_n(int N, int K) {
+    if (stream_uses_ring(K) && N >= 256) return 256;
     return (N % 192 == 0) ? 192 : 128;
 }
 
-static int check_ab(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K) {
+static int check_ab(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K, int n_mult = 32) {
     DECO_CHECK_ARG(A && W, "fused gemm: null operand");
-    DECO_CHECK_ARG(M > 0 && N > 0 && K > 0 && K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && N % 32 == 0,
-                   "fused gemm: bad shape M=%d N=%d K=%d (K, lda, ldw %% 8 == 0; N %% 32 == 0)", M, N, K);
+    DECO_CHECK_ARG(M > 0 && N > 0 && K > 0 && K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && N % n_mult == 0,
+                   "fused gemm: bad shape M=%d N=%d K=%d (K, lda, ldw %% 8 == 0; N %% %d == 0)", M, N, K, n_mult);
     DECO_CHECK_ARG((((uintptr_t)A | (uintptr_t)W) & 15) == 0, "fused gemm: operands must be 16-byte aligned");
     return DECO_OK;
 }
@@ -716,7 +736,7 @@ static int check_ab(const void* A, long long lda, const void* W, long long ldw, 
 using namespace deco;
 using namespace deco::fused;
 
-extern "C" int deco_gemm_stream_parts(int N) { return N > 0 ? (N + stream_tile_n(N) - 1) / stream_tile_n(N) : 0; }
+extern "C" int deco_gemm_stream_parts(int N, int K) { return N > 0 ? (N + stream_tile_n(N, K) - 1) / stream_tile_n(N, K) : 0; }
 
 extern "C" int deco_gemm_stream(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K,
                                 const float* bias, const float* resid, long long ldr, float* out, long long ldo,
@@ -733,8 +753,7 @@ extern "C" int deco_gemm_stream(const void* A, long long lda, const void* W, lon
     DECO_CHECK_ARG(!next_norm_w || (next_scale && xg_out && next_scale_stride % 4 == 0 && ldx % 8 == 0 &&
                                     ((uintptr_t)xg_out & 15) == 0 && ((uintptr_t)next_scale & 7) == 0),
                    "gemm_stream: next-norm arguments invalid");
-    const int bn = stream_tile_n(N);
-    DECO_CHECK_ARG(N % bn == 0, "gemm_stream: N must be a multiple of 128 (or of 192)");
+    const int bn = stream_tile_n(N, K);
     Maps maps;
     if ((rc = make_map(&maps.a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, A, M, K, lda, kBK, kBM, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
     if ((rc = make_map(&maps.b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, W, N, K, ldw, kBK, bn / 2, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
@@ -748,11 +767,13 @@ extern "C" int deco_gemm_stream(const void* A, long long lda, const void* W, lon
     P.bias = bias; P.gate = (const __nv_bfloat16*)gate; P.gate_stride = gate_stride; P.has_resid = resid ? 1 : 0;
     P.next_w = next_norm_w; P.next_scale = (const __nv_bfloat16*)next_scale; P.next_scale_stride = next_scale_stride;
     P.ssq_out = ssq_out; P.xg = (__nv_bfloat16*)xg_out; P.ldx = ldx;
-    static int ring_k = -1;   // K above which the ring-staged variant is used (DECO_STREAM_RING_K overrides, 0 = never)
-    if (ring_k < 0) { const char* e = getenv("DECO_STREAM_RING_K"); ring_k = e ? atoi(e) : 2048; }
-    const bool ring = ring_k > 0 && K > ring_k;
-    if (bn == 192) return ring ? launch<192, FE_STREAM_RING>(maps, P, (cudaStream_t)stream) : launch<192, FE_STREAM>(maps, P, (cudaStream_t)stream);
-    return ring ? launch<128, FE_STREAM_RING>(maps, P, (cudaStream_t)stream) : launch<128, FE_STREAM>(maps, P, (cudaStream_t)stream);
+    if (stream_uses_ring(K)) {
+        if (bn == 256) return launch<256, FE_STREAM_RING>(maps, P, (cudaStream_t)stream);
+        if (bn == 192) return launch<192, FE_STREAM_RING>(maps, P, (cudaStream_t)stream);
+        return launch<128, FE_STREAM_RING>(maps, P, (cudaStream_t)stream);
+    }
+    if (bn == 192) return launch<192, FE_STREAM>(maps, P, (cudaStream_t)stream);
+    return launch<128, FE_STREAM>(maps, P, (cudaStream_t)stream);
 }
 
 extern "C" int deco_gemm_norm_qkv(const void* A, long long lda, const void* W, long long ldw, void* out, long long ldo,
@@ -762,17 +783,17 @@ extern "C" int deco_gemm_norm_qkv(const void* A, long long lda, const void* W, l
                                   int heads, int head_dim, const float* w_seg0, const float* w_seg1, const float* w_seg2,
                                   int rope_mask, const float* rope_cos_sin, int rope_tokens_per_row, float head_eps, void* stream)
 {
-    int rc = check_ab(A, lda, W, ldw, M, N, K);
+    int rc = check_ab(A, lda, W, ldw, M, N, K, 8);
     if (rc) return rc;
     DECO_CHECK_ARG(out && ldo % 8 == 0 && ((uintptr_t)out & 15) == 0, "gemm_norm_qkv: bad output");
     DECO_CHECK_ARG(head_dim == 64 || head_dim == 72, "gemm_norm_qkv: head_dim %d not built (64, 72)", head_dim);
     const int seg = heads * head_dim;
-    DECO_CHECK_ARG(heads > 0 && heads % 2 == 0 && N % seg == 0 && N / seg >= 1 && N / seg <= 3,
-                   "gemm_norm_qkv: N must be 1..3 segments of heads*head_dim with an even number of heads");
+    DECO_CHECK_ARG(heads > 0 && N % seg == 0 && N / seg >= 1 && N / seg <= 3,
+                   "gemm_norm_qkv: N must be 1..3 segments of heads*head_dim");
     DECO_CHECK_ARG(rows_per_image > 0 && (!ssq_in || (ssq_parts > 0 && ssq_parts <= kMaxSsqParts && norm_hidden > 0)), "gemm_norm_qkv: bad norm arguments");
     DECO_CHECK_ARG(!rope_mask || rope_cos_sin, "gemm_norm_qkv: rope table missing");
     DECO_CHECK_ARG(!shw || (shw_stride % 4 == 0 && ((uintptr_t)shw & 15) == 0), "gemm_norm_qkv: bad shift-product matrix");
-    const int bn = 2 * head_dim;
+    const int bn = head_dim == 72 ? 224 : 256;
     Maps maps;
     if ((rc = make_map(&maps.a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, A, M, K, lda, kBK, kBM, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
     if ((rc = make_map(&maps.b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, W, N, K, ldw, kBK, bn / 2, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
@@ -787,8 +808,8 @@ extern "C" int deco_gemm_norm_qkv(const void* A, long long lda, const void* W, l
     P.seg_w[0] = w_seg0; P.seg_w[1] = w_seg1; P.seg_w[2] = w_seg2;
     for (int i = 0; i < 3; ++i) P.seg_rope[i] = (rope_mask >> i) & 1;
     P.rope = (const float2*)rope_cos_sin; P.rope_wp = rope_tokens_per_row; P.eps_head = head_eps;
-    if (head_dim == 72) return launch<144, FE_NORM_QKV>(maps, P, (cudaStream_t)stream);
-    return launch<128, FE_NORM_QKV>(maps, P, (cudaStream_t)stream);
+    if (head_dim == 72) return launch<224, FE_NORM_QKV>(maps, P, (cudaStream_t)stream);
+    return launch<256, FE_NORM_QKV>(maps, P, (cudaStream_t)stream);
 }
 
 extern "C" int deco_gemm_norm_swiglu(const void* A, long long lda, const void* W, long long ldw, void* out, long long ldo,

@@ -222,10 +222,14 @@ class StreamState:
     def __init__(self, M: int, H: int, ffn: int, device):
         self.s = torch.empty((M, H), dtype=torch.float32, device=device)
         self.xg = torch.empty((M, H), dtype=bf16, device=device)
-        self.ssq = torch.empty((2, ops.gemm_stream_parts(H), M), dtype=torch.float32, device=device)
+        self._ssq = torch.empty((2, (H + 127) // 128, M), dtype=torch.float32, device=device)
         self.qkv = torch.empty((M, 3 * H), dtype=bf16, device=device)
         self.o = torch.empty((M, H), dtype=bf16, device=device)
         self.u = torch.empty((M, ffn), dtype=bf16, device=device)
+
+    def ssq(self, which: int, N: int, K: int) -> torch.Tensor:
+        """Partial-sum buffer `which` (ping-pong), sized for its producer: the [*, K] x [K, N] FE_STREAM GEMM."""
+        return self._ssq[which, :ops.gemm_stream_parts(N, K)]
 
 
 def fused_blocks(blocks, mod: torch.Tensor, mod0: int, st: StreamState, a0: torch.Tensor, w0: torch.Tensor,
@@ -244,11 +248,16 @@ def fused_blocks(blocks, mod: torch.Tensor, mod0: int, st: StreamState, a0: torc
     # shift products sh @ W^T of every block: tiny GEMMs ([B, H] x [H, N]) that depend on the modulation only
     shw_qkv = [ops.gemm(sl(i, 0), bp["wqkv"], None, ops.EPI_BIAS_F32) for i, bp in enumerate(blocks)]
     shw_13 = [ops.gemm(sl(i, 3), bp["w13"], None, ops.EPI_BIAS_F32) for i, bp in enumerate(blocks)]
-    s, xg, ssq = st.s, st.xg, st.ssq
-    ops.gemm_stream(a0, w0, b0, s, rows_per_image=L, next_w=blocks[0]["n1"], next_scale=sl(0, 1), xg=xg, ssq=ssq[0])
+    s, xg = st.s, st.xg
+    ffn = st.u.shape[1]
+    q0 = st.ssq(0, H, a0.shape[1])      # statistics of the stream entering block 0 (producer: the embedding GEMM)
+    q_attn = st.ssq(1, H, H)            # ... after the attention branch (producer: proj, K = H)
+    q_mlp = st.ssq(0, H, ffn)           # ... after the MLP branch (producer: w2, K = ffn)
+    ops.gemm_stream(a0, w0, b0, s, rows_per_image=L, next_w=blocks[0]["n1"], next_scale=sl(0, 1), xg=xg, ssq=q0)
+    q_in = q0
     for i, bp in enumerate(blocks):
         ops.gemm_norm_qkv(xg, bp["wqkv"], st.qkv, L, heads, d, seg_w=(bp["qn"], bp["kn"], None), rope_mask=3, rope=pos,
-                          rope_tokens_per_row=wp, ssq=ssq[0], norm_hidden=H, shw=shw_qkv[i])
+                          rope_tokens_per_row=wp, ssq=q_in, norm_hidden=H, shw=shw_qkv[i])
         k2 = v2 = None
         if ytxt is not None:
             kvy = torch.empty((ytxt.shape[0], 2 * H), dtype=bf16, device=s.device)
@@ -256,11 +265,12 @@ def fused_blocks(blocks, mod: torch.Tensor, mod0: int, st: StreamState, a0: torc
             k2, v2 = kvy[:, :H], kvy[:, H:]
         ops.attention(st.qkv[:, :H], st.qkv[:, H:2 * H], st.qkv[:, 2 * H:], B, heads, d, k2=k2, v2=v2, out=st.o)
         ops.gemm_stream(st.o, bp["wproj"], bp["bproj"], s, resid=s, gate=sl(i, 2), rows_per_image=L,
-                        next_w=bp["n2"], next_scale=sl(i, 4), xg=xg, ssq=ssq[1])
-        ops.gemm_norm_swiglu(xg, bp["w13"], st.u, L, ssq=ssq[1], norm_hidden=H, shw=shw_13[i])
+                        next_w=bp["n2"], next_scale=sl(i, 4), xg=xg, ssq=q_attn)
+        ops.gemm_norm_swiglu(xg, bp["w13"], st.u, L, ssq=q_attn, norm_hidden=H, shw=shw_13[i])
         if i + 1 < nb:
             ops.gemm_stream(st.u, bp["w2"], None, s, resid=s, gate=sl(i, 5), rows_per_image=L,
-                            next_w=blocks[i + 1]["n1"], next_scale=sl(i + 1, 1), xg=xg, ssq=ssq[0])
+                            next_w=blocks[i + 1]["n1"], next_scale=sl(i + 1, 1), xg=xg, ssq=q_mlp)
+            q_in = q_mlp
         else:
             ops.gemm_stream(st.u, bp["w2"], None, s, resid=s, gate=sl(i, 5), rows_per_image=L)
     return s
@@ -388,7 +398,7 @@ class PixNerDiT(nn.Module):
         c = ops.cond_combine(temb, P["ytab"], y)
         # residual stream in fp32 (the reference keeps it in bf16; fp32 costs ~4 % more HBM traffic per block and
         # halves the distance to the fp32 reference -- DESIGN.md "precision")
-        if nb and self.fused and heads % 2 == 0 and H % 32 == 0:
+        if nb and self.fused and H % 32 == 0:
             mod = ops.gemm(c, P["wada"], P["bada"], ops.EPI_BIAS)                   # [B, nb*6H]
             st = StreamState(B * L, H, P["ffn_pad"], xp.device)
             s = fused_blocks(P["blocks"], mod, 0, st, xp, P["ws"], P["bs"], B, L, H, heads, pos, wp)

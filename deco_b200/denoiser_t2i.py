@@ -267,7 +267,7 @@ class PixNerDiT(nn.Module):
             ytxt = ops.cast_bf16(ys)
             # ---- image path
             xp = ops.patchify(x32, p)
-            if ni and self.fused and self.num_groups % 2 == 0 and H % 32 == 0:
+            if ni and self.fused and H % 32 == 0:
                 st = StreamState(B * L, H, P["ffn"], dev)
                 s = fused_blocks(P["blocks"], mod, nt, st, xp, P["ws"], P["bs"], B, L, H, self.num_groups, pos,
                                  Ww // p, ytxt=ytxt, T=T)

@@ -62,8 +62,9 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     return out
 
 
-def gemm_stream_parts(N: int) -> int:
-    return _lib.load().deco_gemm_stream_parts(int(N))
+def gemm_stream_parts(N: int, K: int) -> int:
+    """Number of per-row partial sums the FE_STREAM epilogue of an [*, K] x [K, N] GEMM writes (its column tiles)."""
+    return _lib.load().deco_gemm_stream_parts(int(N), int(K))
 
 
 def gemm_stream(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: torch.Tensor,
@@ -87,7 +88,7 @@ def gemm_stream(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], 
         assert next_scale.shape[0] * rows_per_image >= M
         assert xg is not None and xg.dtype == bf16 and xg.shape == (M, N) and xg.stride(1) == 1
     if ssq is not None:
-        assert ssq.dtype == torch.float32 and ssq.is_contiguous() and ssq.shape == (gemm_stream_parts(N), M)
+        assert ssq.dtype == torch.float32 and ssq.is_contiguous() and ssq.shape == (gemm_stream_parts(N, K), M)
     probe = gemm_probe
     ev = probe.before() if probe is not None else None
     call("deco_gemm_stream", ptr(a), a.stride(0), ptr(w), w.stride(0), M, N, K, ptr(bias), ptr(resid),

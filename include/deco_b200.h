@@ -54,10 +54,10 @@ int deco_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, v
 
 /* Residual-stream update (dit_c2i_DeCo.py:208/:209, also :496 with resid = gate = NULL):
  *   out = [resid + gate[row / rows_per_image] *] (A.W^T + bias)          fp32 [M, N], may alias resid
- *   ssq_out[p][row] = sum over the p-th column tile of out[row]^2        fp32 [deco_gemm_stream_parts(N)][M] or NULL
+ *   ssq_out[p][row] = sum over the p-th column tile of out[row]^2        fp32 [deco_gemm_stream_parts(N, K)][M] or NULL
  *   xg_out = bf16(out * next_norm_w * (1 + next_scale[row / rows_per_image]))   or nothing when next_norm_w = NULL
  * N % 32 == 0; gate / next_scale are bf16 [M / rows_per_image, stride]. */
-int deco_gemm_stream_parts(int N);
+int deco_gemm_stream_parts(int N, int K);
 int deco_gemm_stream(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K,
                      const float* bias, const float* resid, long long ldr, float* out, long long ldo,
                      const void* gate, long long gate_stride, int rows_per_image,

@@ -284,7 +284,7 @@ def test_gemm_stream(cuda_dev, M, N, K, L, mode):
     nw = 1 + 0.1 * _rand((N,), cuda_dev, 7, dtype=torch.float32)
     rep = lambda t: t.float().repeat_interleave(L, 0)[:M]   # noqa: E731
     lin = _fp32(lambda: a.float() @ w.float().t() + bias)
-    parts = ops.gemm_stream_parts(N)
+    parts = ops.gemm_stream_parts(N, K)
     ssq = torch.full((parts, M), -1.0, device=cuda_dev)
     if mode == "embed":
         out = torch.empty((M, N), device=cuda_dev)
@@ -312,7 +312,8 @@ def test_gemm_stream(cuda_dev, M, N, K, L, mode):
 @pytest.mark.parametrize("heads,d,hw,B,K,nseg,normed", [
     (16, 72, (16, 16), 2, 1152, 3, True), (8, 72, (4, 4), 3, 576, 3, True), (4, 64, (10, 10), 2, 256, 3, True),
     (24, 64, (8, 8), 2, 1536, 3, True), (4, 64, (3, 8), 2, 256, 2, False), (16, 64, (4, 4), 5, 1024, 3, True),
-    (4, 72, (32, 32), 1, 576, 3, True), (2, 64, (8, 16), 2, 256, 3, True),
+    (4, 72, (32, 32), 1, 576, 3, True), (2, 64, (8, 16), 2, 256, 3, True), (3, 64, (4, 8), 2, 192, 3, True),
+    (5, 72, (4, 4), 2, 360, 3, True),
 ])
 def test_gemm_norm_qkv(cuda_dev, heads, d, hw, B, K, nseg, normed, axial):
     """FE_NORM_QKV against Linear(modulate(RMSNorm(x))) -> q_norm/k_norm -> RoPE evaluated in fp32 torch.
