@@ -22,6 +22,7 @@ CLASS_MAP = {
     "src.diffusion.base.guidance.simple_guidance_fn": "deco_b200.sampling.simple_guidance_fn",
     "src.diffusion.flow_matching.sampling.ode_step_fn": "deco_b200.sampling.ode_step_fn",
     "src.diffusion.flow_matching.adam_sampling.ode_step_fn": "deco_b200.sampling.ode_step_fn",
+    "src.utils.model_loader.ModelLoader": "deco_b200.io.ModelLoader",
     "src.models.autoencoder.pixel.PixelAE": "deco_b200.data.PixelAE",
     "src.models.conditioner.class_label.LabelConditioner": "deco_b200.data.LabelConditioner",
     "src.data.dataset.randn.ClassLabelRandomNDataset": "deco_b200.data.ClassLabelRandomNDataset",
