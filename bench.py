@@ -78,7 +78,7 @@ def parse():
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the GEMM kernel, averaged over the launches of one step
 # (ncu --set full capture, profiles/): filled in from the capture of the same command, None until captured.
-GEMM_TRAFFIC = {}
+GEMM_TRAFFIC = {"xl256": 1.0619e9}   # profiles/traffic_r1.txt: 173 GEMM launches of one step, 183.7 GB in total
 
 
 def measured_peaks():
@@ -187,14 +187,20 @@ def run_reference(args):
 
 # ----------------------------------------------------------------------------------------------- deco_b200 arm
 def _time_kernel(fn, iters, torch):
-    """Average milliseconds per call of fn(i) over `iters` calls, CUDA events on the current stream, after 2 warm-ups."""
+    """Average milliseconds per call of fn(i): `iters` calls captured into one CUDA graph (so that host-side launch cost
+    does not pace kernels that run for tens of microseconds), replayed once after a warm replay, CUDA events around it."""
     for i in range(2):
         fn(i)
     torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(iters):
+            fn(i)
+    g.replay()
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(iters):
-        fn(i)
+    g.replay()
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / iters
@@ -250,18 +256,21 @@ def hbm_kernel_rooflines(torch, ops, net, dev, B2, res, hbm_gbs):
         "82 B/pixel (64 condition + 12 x + 6 out); compute/issue-bound once fused (DESIGN.md): tflops on 37.2 kFLOP/pixel",
         flops=37.2e3 * B2 * res * res)
     del ycond, xx
-    # DCT + FM loss, forward + backward in one pass: out, v_t read + grad write fp32 = 12 B per element
-    # (BASELINE.json configs[3]: 32 images per GPU = 25 MB per tensor, L2-resident -> rotate 8 distinct sets)
-    nset, Bt = 8, 32
-    outs = [torch.randn(Bt, 3, res, res, device=dev) for _ in range(nset)]
-    vts = [torch.randn(Bt, 3, res, res, device=dev) for _ in range(nset)]
+    # DCT + FM loss, forward + backward in one launch: out, v_t read + grad write fp32 = 12 B per element.
+    # BASELINE.json configs[3] is 32 images per GPU = 25 MB per tensor (L2-resident, ~10 us at the roofline: launch and
+    # tail latency weigh in), so 8 distinct input sets rotate; a 256-image batch shows the streaming rate.
     fw = build_freq_weight(85).reshape(3, 8, 8).contiguous().to(dev)
-    ms = _time_kernel(lambda i: ops.dct_fm_loss(outs[i % nset], vts[i % nset], fw, 1.0, want_loss=True, want_grad=True),
-                      24, torch)
-    add("dct_fm_loss_kernel (fwd+bwd)", ms, 12.0 * Bt * npx, "32 images, out + v_t fp32 read, grad fp32 write, 8 rotating sets")
-    ms = _time_kernel(lambda i: ops.dct_fm_loss(outs[i % nset], vts[i % nset], fw, 1.0, want_loss=True, want_grad=False),
-                      24, torch)
-    add("dct_fm_loss_kernel (fwd)", ms, 8.0 * Bt * npx, "32 images, out + v_t fp32 read, 8 rotating sets")
+    for Bt, nset, iters in ((32, 8, 24), (256, 2, 6)):
+        outs = [torch.randn(Bt, 3, res, res, device=dev) for _ in range(nset)]
+        vts = [torch.randn(Bt, 3, res, res, device=dev) for _ in range(nset)]
+        ms = _time_kernel(lambda i: ops.dct_fm_loss(outs[i % nset], vts[i % nset], fw, 1.0, want_loss=True, want_grad=True),
+                          iters, torch)
+        add(f"dct_fm_loss_vec_kernel (fwd+bwd, {Bt} images)", ms, 12.0 * Bt * npx,
+            f"out + v_t fp32 read, grad fp32 write, {nset} rotating input sets")
+        ms = _time_kernel(lambda i: ops.dct_fm_loss(outs[i % nset], vts[i % nset], fw, 1.0, want_loss=True, want_grad=False),
+                          iters, torch)
+        add(f"dct_fm_loss_vec_kernel (fwd, {Bt} images)", ms, 8.0 * Bt * npx, f"out + v_t fp32 read, {nset} rotating input sets")
+        del outs, vts
     return out
 
 

@@ -207,12 +207,178 @@ __global__ void __launch_bounds__(kTileW) dct_fm_loss_kernel(
     }
 }
 
-__global__ void dct_fm_finalize_kernel(const double* __restrict__ accum, float* __restrict__ losses,
+// ---------------------------------------------------------------- vectorised kernel for H, W multiples of 8
+// Same 8 x 128 strip per CTA, but the HORIZONTAL transform runs first so that global traffic is 128-bit:
+//   pass 1: thread (r = tid / 16, bx = tid % 16) owns the 8 consecutive pixels of image row r0 + r in 8x8 block bx:
+//           two float4 (one uint4 for bf16) per plane = 12 LDG.128 per thread, all in flight before the first use;
+//           colour transform + horizontal 8-point DCT in registers -> Z[ch][r][8 bx + l].
+//   pass 2: thread c owns column c: vertical DCT, weighted square (loss), gradient coefficients, transposed vertical
+//           DCT back into Z.
+//   pass 3: thread (r, bx) again: transposed horizontal DCT, transposed colour matrix, + FM gradient from the d it
+//           still holds in registers (nothing is re-read), 6 STG.128 per thread.
+// The last CTA to finish turns the two double accumulators into the three losses and re-zeroes the scratch, so the
+// whole loss (forward + backward) is ONE launch.
+constexpr int kZs = 132;   // row stride of Z in floats: 16-byte aligned rows, conflict-free column reads
+
+template <typename T> __device__ __forceinline__ void load_row8(const T* p, float (&v)[8]);
+template <> __device__ __forceinline__ void load_row8<float>(const float* p, float (&v)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <> __device__ __forceinline__ void load_row8<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
+    const float2 a = unpack_bf2(q.x), b = unpack_bf2(q.y), c = unpack_bf2(q.z), d = unpack_bf2(q.w);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+template <typename T> __device__ __forceinline__ void store_row8(T* p, const float (&v)[8]);
+template <> __device__ __forceinline__ void store_row8<float>(float* p, const float (&v)[8]) {
+    reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <> __device__ __forceinline__ void store_row8<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[8]) {
+    *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf2(v[0], v[1]), pack_bf2(v[2], v[3]), pack_bf2(v[4], v[5]), pack_bf2(v[6], v[7]));
+}
+
+template <typename TOut, bool kLoss, bool kGrad>
+__global__ void __launch_bounds__(kTileW, 8) dct_fm_loss_vec_kernel(
+    const TOut* __restrict__ out, const float* __restrict__ vt, const float* __restrict__ freq_w,
+    TOut* __restrict__ grad, double* __restrict__ accum, float* __restrict__ losses, const float* __restrict__ upstream,
+    int H, int W, float fm_scale, float freq_scale, float freq_loss_weight, double inv_fm, double inv_fq)
+{
+    __shared__ __align__(16) float Z[3][8][kZs];
+    __shared__ float red[2][kTileW / 32];
+
+    const int tid = threadIdx.x;
+    const int b = blockIdx.z;
+    const int r0 = blockIdx.y * 8;
+    const int r = tid >> 4, bx = tid & 15;
+    const int c0 = blockIdx.x * kTileW + bx * 8;
+    const bool ok = c0 < W;                       // W % 8 == 0: a block is inside or outside as a whole
+    const size_t plane = (size_t)H * W;
+    const size_t o = (size_t)b * 3 * plane + (size_t)(r0 + r) * W + c0;
+
+    float d[3][8];                                // out - v_t per RGB plane, kept for the FM gradient
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[ch][j] = 0.f;
+    if (ok) {
+        float a[3][8], v[3][8];
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) { load_row8<TOut>(out + o + ch * plane, a[ch]); load_row8<float>(vt + o + ch * plane, v[ch]); }
+        asm volatile("" ::: "memory");            // compiler barrier: all 12 loads are issued before the first use
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) d[ch][j] = a[ch][j] - v[ch][j];
+    }
+    float fm_part = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) fm_part = fmaf(d[ch][j], d[ch][j], fm_part);
+    {
+        float ycc[3][8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            ycc[0][j] = 0.299f * d[0][j] + 0.587f * d[1][j] + 0.114f * d[2][j];
+            ycc[1][j] = -0.168736f * d[0][j] - 0.331264f * d[1][j] + 0.5f * d[2][j];
+            ycc[2][j] = 0.5f * d[0][j] - 0.418688f * d[1][j] - 0.081312f * d[2][j];
+        }
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            float y[8];
+            dct8_fwd(ycc[ch], y);                 // horizontal: y[l], l = horizontal frequency
+            float4* zp = reinterpret_cast<float4*>(&Z[ch][r][bx * 8]);
+            zp[0] = make_float4(y[0], y[1], y[2], y[3]);
+            zp[1] = make_float4(y[4], y[5], y[6], y[7]);
+        }
+    }
+    __syncthreads();
+    // ---- pass 2: vertical transform on column tid (horizontal frequency l = tid % 8)
+    float fq_part = 0.f;
+    {
+        const int l = tid & 7;
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            float x[8], y[8];
+#pragma unroll
+            for (int rr = 0; rr < 8; ++rr) x[rr] = Z[ch][rr][tid];
+            dct8_fwd(x, y);                       // y[k], k = vertical frequency
+            float g[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float w = __ldg(freq_w + ch * 64 + k * 8 + l);
+                fq_part = fmaf(w * y[k], y[k], fq_part);
+                g[k] = w * y[k];
+            }
+            if (kGrad) {
+                float xb[8];
+                dct8_bwd(g, xb);
+#pragma unroll
+                for (int rr = 0; rr < 8; ++rr) Z[ch][rr][tid] = xb[rr];   // own column: no hazard with other threads
+            }
+        }
+    }
+    if (kLoss) {
+        fm_part = warp_sum(fm_part);
+        fq_part = warp_sum(fq_part);
+        if ((tid & 31) == 0) { red[0][tid >> 5] = fm_part; red[1][tid >> 5] = fq_part; }
+    }
+    __syncthreads();
+    if (kGrad && ok) {
+        const float up = upstream ? __ldg(upstream) : 1.0f;
+        const float kf = up * freq_loss_weight * 2.0f * freq_scale;
+        const float km = up * 2.0f * fm_scale;
+        float gy[3][8];
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            const float4* zp = reinterpret_cast<const float4*>(&Z[ch][r][bx * 8]);
+            const float4 z0 = zp[0], z1 = zp[1];
+            const float y[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+            dct8_bwd(y, gy[ch]);
+        }
+        float gr[8], gg[8], gb[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float a0 = gy[0][j] * kf, a1 = gy[1][j] * kf, a2 = gy[2][j] * kf;
+            gr[j] = fmaf(km, d[0][j], 0.299f * a0 - 0.168736f * a1 + 0.5f * a2);
+            gg[j] = fmaf(km, d[1][j], 0.587f * a0 - 0.331264f * a1 - 0.418688f * a2);
+            gb[j] = fmaf(km, d[2][j], 0.114f * a0 + 0.5f * a1 - 0.081312f * a2);
+        }
+        store_row8<TOut>(grad + o, gr);
+        store_row8<TOut>(grad + o + plane, gg);
+        store_row8<TOut>(grad + o + 2 * plane, gb);
+    }
+    if (kLoss && tid == 0) {
+        float a = 0.f, q = 0.f;
+#pragma unroll
+        for (int i = 0; i < kTileW / 32; ++i) { a += red[0][i]; q += red[1][i]; }
+        atomicAdd(accum + 0, (double)a);
+        atomicAdd(accum + 1, (double)q);
+        __threadfence();
+        unsigned int* ticket = reinterpret_cast<unsigned int*>(accum + 2);
+        const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
+        if (atomicAdd(ticket, 1u) == total - 1) {
+            // last CTA: every partial sum is visible (fence + atomic ticket); publish and leave the scratch zeroed
+            __threadfence();
+            const double fm = atomicAdd(accum + 0, 0.0) * inv_fm, fq = atomicAdd(accum + 1, 0.0) * inv_fq;
+            losses[0] = (float)fm;
+            losses[1] = (float)fq;
+            losses[2] = (float)(fm + (double)freq_loss_weight * fq);
+            accum[0] = 0.0; accum[1] = 0.0;
+            *ticket = 0u;
+        }
+    }
+}
+
+__global__ void dct_fm_finalize_kernel(double* __restrict__ accum, float* __restrict__ losses,
                                        double inv_fm, double inv_fq, float freq_loss_weight) {
     const double fm = accum[0] * inv_fm, fq = accum[1] * inv_fq;
     losses[0] = (float)fm;
     losses[1] = (float)fq;
     losses[2] = (float)(fm + (double)freq_loss_weight * fq);
+    accum[0] = 0.0; accum[1] = 0.0; accum[2] = 0.0;   // same scratch contract as the one-launch path: zero on exit
 }
 
 static bool g_dct_init = false;
@@ -246,7 +412,7 @@ static int launch_dct(const TOut* out, const float* vt, const float* freq_w, TOu
     const bool ragged = (H2 != H) || (W2 != W);
     const double n_fm = (double)B * 3 * H * W, n_fq = (double)B * 3 * H2 * W2;
     dim3 grid((W2 + kTileW - 1) / kTileW, H2 / 8, B), block(kTileW);
-    if (want_loss) cudaMemsetAsync(accum, 0, 2 * sizeof(double), st);
+    if (want_loss && ragged) cudaMemsetAsync(accum, 0, 3 * sizeof(double), st);
     const float fms = (float)(1.0 / n_fm), fqs = (float)(1.0 / n_fq);
 #define DCT_LAUNCH(R, L, G) dct_fm_loss_kernel<TOut, R, L, G><<<grid, block, 0, st>>>( \
         out, vt, freq_w, grad, accum, upstream, H, W, H2, W2, fms, fqs, flw)
@@ -256,9 +422,15 @@ static int launch_dct(const TOut* out, const float* vt, const float* freq_w, TOu
         else if (want_grad) DCT_LAUNCH(true, false, true);
         else DCT_LAUNCH(true, true, false);
     } else {
-        if (want_loss && want_grad) DCT_LAUNCH(false, true, true);
-        else if (want_grad) DCT_LAUNCH(false, false, true);
-        else DCT_LAUNCH(false, true, false);
+        // scratch contract of the one-launch path: accum[0..2] are zero on entry and zero again on exit
+#define DCT_VEC(L, G) dct_fm_loss_vec_kernel<TOut, L, G><<<grid, block, 0, st>>>( \
+        out, vt, freq_w, grad, accum, losses, upstream, H, W, fms, fqs, flw, 1.0 / n_fm, 1.0 / n_fq)
+        if (want_loss && want_grad) DCT_VEC(true, true);
+        else if (want_grad) DCT_VEC(false, true);
+        else DCT_VEC(true, false);
+#undef DCT_VEC
+        DECO_CHECK_LAUNCH("dct_fm_loss_vec_kernel");
+        return DECO_OK;
     }
 #undef DCT_LAUNCH
     DECO_CHECK_LAUNCH("dct_fm_loss_kernel");

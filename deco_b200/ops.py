@@ -318,6 +318,19 @@ def fp2uint8(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+_DCT_SCRATCH = {}
+
+
+def _dct_scratch(device) -> torch.Tensor:
+    """3 zeroed doubles per (device, stream): the kernel leaves them zero again (include/deco_b200.h)."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(device).cuda_stream)
+    buf = _DCT_SCRATCH.get(key)
+    if buf is None:
+        buf = _DCT_SCRATCH[key] = torch.zeros(3, dtype=torch.float64, device=device)
+    return buf
+
+
 def dct_fm_loss(out: torch.Tensor, v_t: torch.Tensor, freq_w: torch.Tensor, freq_loss_weight: float,
                 want_loss: bool = True, want_grad: bool = False, upstream: Optional[torch.Tensor] = None):
     """Returns (losses fp32[3] = fm, freq, total | None, grad | None)."""
@@ -329,7 +342,7 @@ def dct_fm_loss(out: torch.Tensor, v_t: torch.Tensor, freq_w: torch.Tensor, freq
     B, _, H, W = out.shape
     losses = torch.empty(3, dtype=torch.float32, device=out.device) if want_loss else None
     grad = torch.empty_like(out) if want_grad else None
-    accum = torch.empty(2, dtype=torch.float64, device=out.device)
+    accum = _dct_scratch(out.device)
     if upstream is not None:
         upstream = upstream.reshape(()).to(torch.float32)
     call("deco_dct_fm_loss", ptr(out), int(out.dtype == bf16), ptr(v_t), ptr(freq_w), B, H, W,

@@ -165,7 +165,8 @@ int deco_fp2uint8(const float* x, uint8_t* out, long long n, void* stream);
  * (flow_matching/training_repa_DeCo.py:106-136 _rgb2ycbcr/_dct, :138-195 weights, :273-285 loss):
  *   losses[0] = mean((out - v_t)^2), losses[1] = mean(freq_w * dct(ycbcr(out - v_t))^2), losses[2] = [0] + flw * [1]
  *   grad = upstream * d losses[2] / d out   (same dtype as out; fp32 required for ragged H/W)
- * out [B,3,H,W] fp32 or bf16; v_t fp32; freq_w fp32 [3,8,8]; accum = 2 doubles of scratch;
+ * out [B,3,H,W] fp32 or bf16; v_t fp32; freq_w fp32 [3,8,8]; accum = 3 doubles of scratch that must be ZERO on entry and
+ * are zero again on exit (the last CTA publishes the losses and clears them: forward + backward is one launch);
  * losses and/or grad may be NULL; upstream = device scalar or NULL (1.0). */
 int deco_dct_fm_loss(const void* out, int out_is_bf16, const float* v_t, const float* freq_w,
                      int B, int H, int W, float freq_loss_weight,
