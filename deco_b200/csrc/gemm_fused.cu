@@ -32,9 +32,11 @@ constexpr int kThreads = 256;
 constexpr int kAccStages = 2;
 constexpr int kMaxSsqParts = 16;   // column tiles of the producing FE_STREAM GEMM (hidden <= 16 x 128)
 
-// FE_STREAM_RING = FE_STREAM with a 3-deep ring of residual chunk buffers per warp instead of a whole staged tile: 48 KB
-// less staging = two more operand stages, for the deep-K (w2) GEMM whose main loop is latency-bound on operand loads
-// while its epilogue has time to spare; the K = hidden GEMMs keep the whole-tile prefetch (epilogue is HBM-bound there).
+// Both FE_STREAM variants stream the fp32 residual through a per-warp RING of 32 x 32 chunk buffers (TMA in, update in
+// place, TMA out): the load of chunk g + R - 1 is issued the moment the store of chunk g - 1 has released its buffer, so
+// residual traffic never stops at tile boundaries.  FE_STREAM: R = chunks per tile (a tile of look-ahead; the K = hidden
+// GEMMs, whose epilogue is HBM-bound).  FE_STREAM_RING: R = 3, 48 KB less staging = two more operand stages and
+// 256-wide tiles, for the deep-K (w2) GEMM whose main loop is latency-bound on operand loads.
 enum FusedEpi : int { FE_STREAM = 0, FE_NORM_QKV = 1, FE_NORM_SWIGLU = 2, FE_STREAM_RING = 3 };
 
 struct Maps { CUtensorMap a, b, r, o, x; };   // A, W, residual in (fp32), stream out (fp32) / qkv out (bf16), xg out (bf16)
@@ -84,9 +86,9 @@ template <int BN, int EPI> struct Cfg {
     //   FE_NORM_QKV    2 x bf16 [32 rows][d] (output) + [BN] fp32 shift product
     //   FE_NORM_SWIGLU [BN] fp32 shift product
     static constexpr bool kStream = EPI == FE_STREAM || EPI == FE_STREAM_RING;
-    static constexpr int kRing = 3;
+    static constexpr int kRing = EPI == FE_STREAM ? BN / 32 : 3;
     static constexpr int kVecBytes = kStream ? 3 * BN * 4 : kTileN * 4;
-    static constexpr int kOutStage = EPI == FE_STREAM ? (BN / 32) * 4096 : EPI == FE_STREAM_RING ? kRing * 4096
+    static constexpr int kOutStage = kStream ? kRing * 4096
                                    : EPI == FE_NORM_QKV ? 2 * 32 * kHeadDim * 2 : 0;
     // layout: 4 x kOutStage (1024-aligned buffers), then 4 x kVecBytes
     static constexpr int kWarpAll = ((4 * (kOutStage + kVecBytes) + 1023) / 1024) * 1024;
@@ -140,8 +142,8 @@ gemm_fused_kernel(const __grid_constant__ Maps maps, const Params P)
     auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * C::kStages + s); };
     auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * C::kStages + kAccStages + s); };
     auto resid_bar = [&](int w) { return bar_base + 8u * (2 * C::kStages + 2 * kAccStages + w); };
-    auto ring_bar = [&](int w, int b) { return bar_base + 8u * (2 * C::kStages + 2 * kAccStages + 4 + w * 3 + b); };
-    const uint32_t tmem_slot = bar_base + 8u * (2 * C::kStages + 2 * kAccStages + 16);
+    auto ring_bar = [&](int w, int b) { return bar_base + 8u * (2 * C::kStages + 2 * kAccStages + 4 + w * 8 + b); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * C::kStages + 2 * kAccStages + 4 + 32);
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -161,7 +163,7 @@ gemm_fused_kernel(const __grid_constant__ Maps maps, const Params P)
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < C::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         for (int s = 0; s < kAccStages; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8); }
-        for (int w = 0; w < 4; ++w) { mbar_init(resid_bar(w), 1); for (int b = 0; b < 3; ++b) mbar_init(ring_bar(w, b), 1); }
+        for (int w = 0; w < 4; ++w) { mbar_init(resid_bar(w), 1); for (int b = 0; b < 8; ++b) mbar_init(ring_bar(w, b), 1); }
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc_2sm(tmem_slot, C::kTmemCols);
@@ -237,23 +239,18 @@ gemm_fused_kernel(const __grid_constant__ Maps maps, const Params P)
         auto tile_row0 = [&](int tile) { return ((tile / num_n) * 2 + (int)cta_rank) * kBM + q * 32; };
 
         if constexpr (C::kStream) {
-            constexpr bool RING = EPI == FE_STREAM_RING;
+            constexpr int R = C::kRing;           // residual chunk buffers per warp
+            constexpr int PEND = R >= 4 ? 2 : 1;  // stores allowed in flight before a buffer is recycled
+            static_assert((BN / 32) % 2 == 0, "chunks are processed in pairs");
             constexpr int NC = BN / 32;
             constexpr int NV = BN / 64;        // column pairs per lane
             const bool fast = uni && P.has_resid;
-            uint32_t rphase = 0;
-            // whole-tile staging: all NC residual chunks of the next tile are requested when this tile's stores are out
-            auto issue_resid = [&](int tile) {
-                const int r0 = tile_row0(tile), n_blk = tile % num_n;
-                mbar_expect_tx(resid_bar(q), NC * 4096);
-                for (int c = 0; c < NC; ++c) tma_load_2d(wstg + c * 4096, &maps.r, resid_bar(q), n_blk * BN + c * 32, r0);
-            };
-            // ring staging: chunk sequence number g lives in buffer g % 3; the load of chunk g + 2 is issued when the
-            // store of chunk g - 1 has released that buffer
+            // chunk sequence number g lives in buffer g % R; the load of chunk g + R - 1 is issued when the store of
+            // chunk g - 1 has released that buffer
             int ltile = tile0, lc = 0, lseq = 0, gseq = 0;
             auto issue_next_chunk = [&]() {
                 if (ltile >= num_tiles) return;
-                const int b = lseq % 3;
+                const int b = lseq % R;
                 mbar_expect_tx(ring_bar(q, b), 4096);
                 tma_load_2d(wstg + b * 4096, &maps.r, ring_bar(q, b), (ltile % num_n) * BN + lc * 32, tile_row0(ltile));
                 ++lseq;
@@ -277,10 +274,8 @@ gemm_fused_kernel(const __grid_constant__ Maps maps, const Params P)
                 }
             };
             if (tile0 < num_tiles) {
-                if (P.has_resid && lane == 0) {
-                    if (RING) { issue_next_chunk(); issue_next_chunk(); issue_next_chunk(); }
-                    else issue_resid(tile0);
-                }
+                if (P.has_resid && lane == 0)
+                    for (int b = 0; b < R; ++b) issue_next_chunk();
                 if (uni) fetch(tile0);
             }
             for (int tile = tile0; tile < num_tiles; tile += tile_stride) {
@@ -306,97 +301,106 @@ gemm_fused_kernel(const __grid_constant__ Maps maps, const Params P)
                     __syncwarp();
                     if (tile + tile_stride < num_tiles) fetch(tile + tile_stride);
                 }
-                if (!RING && P.has_resid) { mbar_wait(resid_bar(q), rphase); rphase ^= 1; }
                 mbar_wait(tfull_bar(as), aphase);
                 tc_fence_after();
                 float ssq = 0.f;
                 auto body = [&](auto fast_tag) {
                     constexpr bool F = decltype(fast_tag)::value;
-#pragma unroll 1
-                    for (int c = 0; c < NC; ++c) {
-                        uint32_t acc[32];
-                        tmem_ld32(taddr + (uint32_t)(c * 32), acc);
-                        tmem_ld_wait();
-                        if (c == NC - 1) release_acc();          // accumulator stage is free for the next-but-one tile
+                    // one chunk: acc = 32 accumulator columns of this thread's row
+                    auto chunk = [&](const uint32_t (&acc)[32], int c) {
                         const int n0 = nbase + c * 32;           // may lie beyond N in a ragged last tile: zero operands, clipped stores
-                        const int buf = RING ? gseq % 3 : c;
-                        if (RING && P.has_resid) mbar_wait(ring_bar(q, buf), (uint32_t)((gseq / 3) & 1));
+                        const int buf = gseq % R;
+                        if (P.has_resid) mbar_wait(ring_bar(q, buf), (uint32_t)((gseq / R) & 1));
                         const uint32_t crow = wstg + buf * 4096 + lane * 128;
                         const bool live = n0 < P.N;              // warp-uniform (N % 32 == 0)
                         if (live) {
+                            // shared-memory loads are issued in batches ahead of their uses: the warp issues in order,
+                            // so a load consumed right away costs a full LDS latency per 4 columns
+                            float4 rr[8];
 #pragma unroll
-                        for (int j = 0; j < 8; j += 2) {
-                            uint32_t xb[4];
+                            for (int jq = 0; jq < 8; ++jq)
+                                rr[jq] = (F || P.has_resid) ? lds128(crow + ((uint32_t)(jq ^ (lane & 7)) << 4))
+                                                            : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                            for (int jj = 0; jj < 2; ++jj) {
-                                const int ci = c * 32 + 4 * (j + jj);    // column inside the tile
-                                const int col = nbase + ci;
-                                float4 g4, bg4, nc4;
-                                if (F || uni) {
-                                    g4 = lds128(vec + ci * 4);
-                                    bg4 = lds128(vec + BN * 4 + ci * 4);
-                                    nc4 = lds128(vec + 2 * BN * 4 + ci * 4);
-                                } else {
-                                    g4 = make_float4(1.f, 1.f, 1.f, 1.f); bg4 = make_float4(0.f, 0.f, 0.f, 0.f); nc4 = bg4;
-                                    if (grow) {
-                                        const uint2 gv = __ldg(reinterpret_cast<const uint2*>(grow + col));
-                                        const float2 g0 = unpack_bf2(gv.x), g1 = unpack_bf2(gv.y);
-                                        g4 = make_float4(g0.x, g0.y, g1.x, g1.y);
-                                    }
-                                    if (P.bias) {
-                                        const float4 b = __ldg(reinterpret_cast<const float4*>(P.bias + col));
-                                        bg4 = make_float4(b.x * g4.x, b.y * g4.y, b.z * g4.z, b.w * g4.w);
-                                    }
-                                    if (srow) {
-                                        const float4 w = __ldg(reinterpret_cast<const float4*>(P.next_w + col));
-                                        const uint2 sv = __ldg(reinterpret_cast<const uint2*>(srow + col));
-                                        const float2 s0 = unpack_bf2(sv.x), s1 = unpack_bf2(sv.y);
-                                        nc4 = make_float4(w.x * (1.0f + s0.x), w.y * (1.0f + s0.y), w.z * (1.0f + s1.x), w.w * (1.0f + s1.y));
+                            for (int h = 0; h < 2; ++h) {
+                                float4 g4[4], bg4[4], nc4[4];
+#pragma unroll
+                                for (int jj = 0; jj < 4; ++jj) {
+                                    const int ci = c * 32 + 4 * (4 * h + jj);    // column inside the tile
+                                    const int col = nbase + ci;
+                                    if (F || uni) {
+                                        g4[jj] = lds128(vec + ci * 4);
+                                        bg4[jj] = lds128(vec + BN * 4 + ci * 4);
+                                        nc4[jj] = lds128(vec + 2 * BN * 4 + ci * 4);
+                                    } else {
+                                        g4[jj] = make_float4(1.f, 1.f, 1.f, 1.f);
+                                        bg4[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                        nc4[jj] = bg4[jj];
+                                        if (grow) {
+                                            const uint2 gv = __ldg(reinterpret_cast<const uint2*>(grow + col));
+                                            const float2 g0 = unpack_bf2(gv.x), g1 = unpack_bf2(gv.y);
+                                            g4[jj] = make_float4(g0.x, g0.y, g1.x, g1.y);
+                                        }
+                                        if (P.bias) {
+                                            const float4 b = __ldg(reinterpret_cast<const float4*>(P.bias + col));
+                                            bg4[jj] = make_float4(b.x * g4[jj].x, b.y * g4[jj].y, b.z * g4[jj].z, b.w * g4[jj].w);
+                                        }
+                                        if (srow) {
+                                            const float4 w = __ldg(reinterpret_cast<const float4*>(P.next_w + col));
+                                            const uint2 sv = __ldg(reinterpret_cast<const uint2*>(srow + col));
+                                            const float2 s0 = unpack_bf2(sv.x), s1 = unpack_bf2(sv.y);
+                                            nc4[jj] = make_float4(w.x * (1.0f + s0.x), w.y * (1.0f + s0.y), w.z * (1.0f + s1.x), w.w * (1.0f + s1.y));
+                                        }
                                     }
                                 }
-                                float4 v;
-                                v.x = fmaf(__uint_as_float(acc[4 * (j + jj)]), g4.x, bg4.x);
-                                v.y = fmaf(__uint_as_float(acc[4 * (j + jj) + 1]), g4.y, bg4.y);
-                                v.z = fmaf(__uint_as_float(acc[4 * (j + jj) + 2]), g4.z, bg4.z);
-                                v.w = fmaf(__uint_as_float(acc[4 * (j + jj) + 3]), g4.w, bg4.w);
-                                const uint32_t sa = crow + ((uint32_t)((j + jj) ^ (lane & 7)) << 4);
-                                if (F || P.has_resid) {
-                                    const float4 r = lds128(sa);
-                                    v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+                                uint32_t xb[8];
+#pragma unroll
+                                for (int jj = 0; jj < 4; ++jj) {
+                                    const int jq = 4 * h + jj;
+                                    float4 v;
+                                    v.x = fmaf(__uint_as_float(acc[4 * jq]), g4[jj].x, bg4[jj].x) + rr[jq].x;
+                                    v.y = fmaf(__uint_as_float(acc[4 * jq + 1]), g4[jj].y, bg4[jj].y) + rr[jq].y;
+                                    v.z = fmaf(__uint_as_float(acc[4 * jq + 2]), g4[jj].z, bg4[jj].z) + rr[jq].z;
+                                    v.w = fmaf(__uint_as_float(acc[4 * jq + 3]), g4[jj].w, bg4[jj].w) + rr[jq].w;
+                                    ssq = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, ssq))));
+                                    sts128(crow + ((uint32_t)(jq ^ (lane & 7)) << 4), v);
+                                    xb[2 * jj] = pack_bf2(v.x * nc4[jj].x, v.y * nc4[jj].y);
+                                    xb[2 * jj + 1] = pack_bf2(v.z * nc4[jj].z, v.w * nc4[jj].w);
                                 }
-                                ssq = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, ssq))));
-                                sts128(sa, v);
-                                xb[2 * jj] = pack_bf2(v.x * nc4.x, v.y * nc4.y);
-                                xb[2 * jj + 1] = pack_bf2(v.z * nc4.z, v.w * nc4.w);
+                                if (srow && row < P.M) {
+                                    uint4* xp = reinterpret_cast<uint4*>(P.xg + row * P.ldx + n0 + 16 * h);
+                                    xp[0] = make_uint4(xb[0], xb[1], xb[2], xb[3]);
+                                    xp[1] = make_uint4(xb[4], xb[5], xb[6], xb[7]);
+                                }
                             }
-                            if (srow && row < P.M)
-                                *reinterpret_cast<uint4*>(P.xg + row * P.ldx + n0 + 4 * j) = make_uint4(xb[0], xb[1], xb[2], xb[3]);
-                        }
                         }
                         fence_proxy_async();
                         __syncwarp();
                         if (lane == 0) {
                             if (live) tma_store_2d(&maps.o, wstg + buf * 4096, n0, row0);
                             bulk_commit();                       // (an empty group for a dead chunk keeps the ring's group count)
-                            if (RING) {
-                                bulk_wait_read<1>();             // the store of chunk g - 1 has released its buffer
-                                if (P.has_resid && gseq >= 1) issue_next_chunk();
-                            }
+                            bulk_wait_read<PEND>();              // the store of chunk g - PEND has released its buffer
+                            if (P.has_resid && gseq >= PEND) issue_next_chunk();
                         }
-                        if (RING) { ++gseq; __syncwarp(); }
+                        ++gseq;
+                        __syncwarp();
+                    };
+                    // TMEM reads run one chunk ahead of the arithmetic (two register sets)
+                    uint32_t accA[32], accB[32];
+                    tmem_ld32(taddr, accA);
+#pragma unroll 1
+                    for (int c = 0; c < NC; c += 2) {
+                        tmem_ld_wait();
+                        tmem_ld32(taddr + (uint32_t)((c + 1) * 32), accB);
+                        chunk(accA, c);
+                        tmem_ld_wait();
+                        if (c + 2 < NC) tmem_ld32(taddr + (uint32_t)((c + 2) * 32), accA);
+                        else release_acc();                      // accumulator stage is free for the next-but-one tile
+                        chunk(accB, c + 1);
                     }
                 };
                 if (fast) body(std::true_type{}); else body(std::false_type{});
                 if (P.ssq_out && row < P.M) P.ssq_out[(long long)n_blk * P.M + row] = ssq;
-                if (!RING) {
-                    // the staging tile is reused by the next tile's residual prefetch once the stores have read it
-                    if (lane == 0) {
-                        bulk_wait_read<0>();
-                        const int next = tile + tile_stride;
-                        if (P.has_resid && next < num_tiles) issue_resid(next);
-                    }
-                    __syncwarp();
-                }
                 if (++as == kAccStages) { as = 0; aphase ^= 1; }
             }
             if (lane == 0) bulk_wait_all();
@@ -512,16 +516,30 @@ gemm_fused_kernel(const __grid_constant__ Maps maps, const Params P)
                         if (col0 >= P.N) continue;
                         float v[D];
                         float ss = 0.f;
+                        // shared-memory loads in batches ahead of their uses (in-order issue: see FE_STREAM)
 #pragma unroll
-                        for (int i = 0; i < D; i += 4) {
-                            float4 s4;
-                            if (F) s4 = lds128(vec + (hh * D + i) * 4);
-                            else s4 = shrow ? __ldg(reinterpret_cast<const float4*>(shrow + col0 + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                            v[i] = fmaf(rstd, __uint_as_float(acc[i]), s4.x);
-                            v[i + 1] = fmaf(rstd, __uint_as_float(acc[i + 1]), s4.y);
-                            v[i + 2] = fmaf(rstd, __uint_as_float(acc[i + 2]), s4.z);
-                            v[i + 3] = fmaf(rstd, __uint_as_float(acc[i + 3]), s4.w);
-                            ss = fmaf(v[i], v[i], fmaf(v[i + 1], v[i + 1], fmaf(v[i + 2], v[i + 2], fmaf(v[i + 3], v[i + 3], ss))));
+                        for (int i0 = 0; i0 < D; i0 += 24) {
+                            constexpr int kB = 6;
+                            float4 sv[kB];
+#pragma unroll
+                            for (int b = 0; b < kB; ++b) {
+                                const int i = i0 + 4 * b;
+                                if (i < D) {
+                                    if (F) sv[b] = lds128(vec + (hh * D + i) * 4);
+                                    else sv[b] = shrow ? __ldg(reinterpret_cast<const float4*>(shrow + col0 + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                }
+                            }
+#pragma unroll
+                            for (int b = 0; b < kB; ++b) {
+                                const int i = i0 + 4 * b;
+                                if (i < D) {
+                                    v[i] = fmaf(rstd, __uint_as_float(acc[i]), sv[b].x);
+                                    v[i + 1] = fmaf(rstd, __uint_as_float(acc[i + 1]), sv[b].y);
+                                    v[i + 2] = fmaf(rstd, __uint_as_float(acc[i + 2]), sv[b].z);
+                                    v[i + 3] = fmaf(rstd, __uint_as_float(acc[i + 3]), sv[b].w);
+                                    ss = fmaf(v[i], v[i], fmaf(v[i + 1], v[i + 1], fmaf(v[i + 2], v[i + 2], fmaf(v[i + 3], v[i + 3], ss))));
+                                }
+                            }
                         }
                         // staging buffer hb was last used two heads ago: that store must have finished reading
                         if (lane == 0) bulk_wait_read<1>();
@@ -623,12 +641,16 @@ gemm_fused_kernel(const __grid_constant__ Maps maps, const Params P)
                         if (c == BN / 32 - 1) release_acc();
                         const int n0 = nbase + c * 32;
                         if (n0 >= P.N || row >= P.M) continue;
+                        float4 sv[8];               // all shift loads first, then the arithmetic (in-order issue)
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            if (F) sv[i] = lds128(vec + (c * 32 + 4 * i) * 4);
+                            else sv[i] = shrow ? __ldg(reinterpret_cast<const float4*>(shrow + n0 + 4 * i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
                         float v[32];
 #pragma unroll
                         for (int i = 0; i < 32; i += 4) {
-                            float4 s4;
-                            if (F) s4 = lds128(vec + (c * 32 + i) * 4);
-                            else s4 = shrow ? __ldg(reinterpret_cast<const float4*>(shrow + n0 + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            const float4 s4 = sv[i >> 2];
                             v[i] = fmaf(rstd, __uint_as_float(acc[i]), s4.x);
                             v[i + 1] = fmaf(rstd, __uint_as_float(acc[i + 1]), s4.y);
                             v[i + 2] = fmaf(rstd, __uint_as_float(acc[i + 2]), s4.z);
