@@ -40,6 +40,21 @@ SIGNATURES = {
     "deco_cfg_step": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _f, _f, _f, _f, _f, _f, _vp, _vp, _vp, _vp, _ll, _vp]),
     "deco_fp2uint8": (_i, [_vp, _vp, _ll, _vp]),
     "deco_dct_fm_loss": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),
+    "deco_transpose_cast": (_i, [_vp, _i, _ll, _vp, _ll, _i, _i, _i, _vp]),
+    "deco_colsum": (_i, [_vp, _i, _ll, _vp, _ll, _i, _vp]),
+    "deco_gate_residual": (_i, [_vp, _vp, _vp, _ll, _vp, _i, _ll, _i, _vp]),
+    "deco_gate_bwd": (_i, [_vp, _vp, _vp, _ll, _vp, _vp, _ll, _vp, _i, _ll, _i, _vp]),
+    "deco_silu_add_rows_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _vp]),
+    "deco_swiglu_fwd": (_i, [_vp, _vp, _ll, _i, _vp]),
+    "deco_swiglu_bwd": (_i, [_vp, _vp, _vp, _ll, _i, _vp]),
+    "deco_rmsnorm_modulate_bwd": (_i, [_vp, _vp, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _ll, _i, _ll, _i, _f, _vp]),
+    "deco_headnorm_rope_bwd": (_i, [_vp, _ll, _vp, _ll, _i, _vp, _vp, _vp, _ll, _i, _i, _i, _f, _vp]),
+    "deco_cond_combine_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "deco_silu_bwd": (_i, [_vp, _vp, _vp, _ll, _vp]),
+    "deco_attention_bwd": (_i, [_vp, _ll, _vp, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _vp, _ll, _vp, _vp,
+                                _i, _i, _i, _i, _i, _f, _vp]),
+    "deco_decoder_train_blob_floats": (_i, [_i]),
+    "deco_pixel_decoder_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
 }
 
 _lib = None

@@ -1,0 +1,283 @@
+"""Training path of the class-conditional denoiser: forward that keeps what the backward needs, and the backward itself.
+
+The reference trains `PixNerDiT` with plain PyTorch autograd (`src/diffusion/flow_matching/training_repa_DeCo.py:257`
+calls `net(x_t, t, y)` and Lightning calls `loss.backward()`).  Here the whole denoiser is ONE autograd node
+(`DenoiserFn`): its forward runs one kernel per reference op and stashes the activations, its backward walks the graph by
+hand -- every contraction (dgrad `dX = dY.W`, wgrad `dW = dY^T.X`) on the tcgen05 GEMM, attention and the pixel decoder on
+their own backward kernels (csrc/attention_bwd.cu, csrc/decoder_bwd.cu), the memory-bound glue in csrc/backward.cu.
+PyTorch only allocates, slices and copies.  Gradients are returned per parameter in `named_parameters()` order.
+
+Per block (dit_c2i_DeCo.py:206-210), forward keeps: the stream before each branch (fp32), the two modulated norms h1/h2,
+the raw and the normalised+rotated qkv, the attention output o, the branch outputs a1/a2 (for the gate gradients), the
+SwiGLU pre-activation y13 and its output u.
+"""
+from __future__ import annotations
+
+from typing import Dict, List
+
+import torch
+
+from . import _lib, ops
+
+bf16 = torch.bfloat16
+F32 = torch.float32
+
+
+def _rb(t: torch.Tensor) -> torch.Tensor:
+    """fp32 copy holding bf16-rounded values (what the forward MMAs see)."""
+    return t.detach().to(bf16).to(F32)
+
+
+@torch.no_grad()
+def pack_decoder_train(module, device):
+    """fp32 weight blob of the pixel decoder in the layout of csrc/decoder_bwd.cu."""
+    C = module.in_channels
+    dn = module.dec_net
+    wx = _rb(module.x_embedder.embedder[0].weight)
+    parts = [wx[:, :C].reshape(-1), _rb(dn.input_proj.weight).reshape(-1), dn.input_proj.bias.detach().float()]
+    for blk in dn.res_blocks:
+        parts += [_rb(blk.adaLN_modulation[1].weight).reshape(-1), blk.adaLN_modulation[1].bias.detach().float(),
+                  blk.in_ln.weight.detach().float(), blk.in_ln.bias.detach().float(),
+                  _rb(blk.mlp[0].weight).reshape(-1), blk.mlp[0].bias.detach().float(),
+                  _rb(blk.mlp[2].weight).reshape(-1), blk.mlp[2].bias.detach().float()]
+    wf = torch.zeros(4, 32, device=wx.device)
+    wf[:C] = _rb(dn.final_layer.linear.weight)
+    bfin = torch.zeros(4, device=wx.device)
+    bfin[:C] = dn.final_layer.linear.bias.detach().float()
+    parts += [wf.reshape(-1), bfin]
+    blob = torch.cat([p.to(device=device, dtype=F32).reshape(-1) for p in parts]).contiguous()
+    assert blob.numel() == _lib.load().deco_decoder_train_blob_floats(len(dn.res_blocks)), blob.numel()
+    return blob
+
+
+@torch.no_grad()
+def prepare_train(module, P: dict, device) -> dict:
+    """Transposed bf16 weights for the dgrad GEMMs + the fp32 decoder blob; cached next to `prepare()`'s dict."""
+    if "train" in P:
+        return P["train"]
+    T = {}
+
+    def tr(w):   # [N, K] bf16 -> [K, N] bf16 (the "weight" operand of dX = dY . W)
+        return ops.transpose_cast(w, rows_pad=w.shape[0])
+
+    T["wt2T"], T["wadaT"], T["wcondT"] = tr(P["wt2"]), tr(P["wada"]), tr(P["wcond"])
+    T["blocks"] = [dict(wqkvT=tr(bp["wqkv"]), wprojT=tr(bp["wproj"]), w13T=tr(bp["w13"]), w2T=tr(bp["w2"]))
+                   for bp in P["blocks"]]
+    T["dec_blob"] = pack_decoder_train(module, device)
+    from .denoiser import nerf_pos_table
+    T["tabT"] = ops.transpose_cast(nerf_pos_table(module.patch_size, module.x_embedder.max_freqs).to(device))  # [64, 256]
+    P["train"] = T
+    return T
+
+
+def _wgrad(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """dW [N, K] fp32 = dy^T [N, M] . x [M, K]; both operands transposed to K-major (K = M padded to 8)."""
+    return ops.gemm(ops.transpose_cast(dy), ops.transpose_cast(x), None, ops.EPI_BIAS_F32)
+
+
+def _colsum(x: torch.Tensor) -> torch.Tensor:
+    return ops.colsum_(torch.zeros(x.shape[1], dtype=F32, device=x.device), x)
+
+
+def train_forward(module, x32, t, y):
+    """Returns (out fp32 [B,3,H,W], saved dict)."""
+    P = module.prepare(x32.device)
+    T = prepare_train(module, P, x32.device)
+    B, _, Hh, Ww = x32.shape
+    p, H, heads = module.patch_size, module.hidden_size, module.num_groups
+    d = H // heads
+    L = (Hh // p) * (Ww // p)
+    M = B * L
+    dev = x32.device
+    pos = module.fetch_pos(Hh // p, Ww // p, dev)
+    S = dict(B=B, L=L, shape=x32.shape, x32=x32, y=y, pos=pos)
+    xp = ops.patchify(x32, p)
+    tfreq = ops.timestep_freq(t, module.t_embedder.frequency_embedding_size)
+    z1 = ops.gemm(tfreq, P["wt0"], P["bt0"], ops.EPI_BIAS)
+    h1t = ops.gemm(tfreq, P["wt0"], P["bt0"], ops.EPI_BIAS_SILU)
+    temb = ops.gemm(h1t, P["wt2"], P["bt2"], ops.EPI_BIAS)
+    c = ops.cond_combine(temb, P["ytab"], y)
+    mod = ops.gemm(c, P["wada"], P["bada"], ops.EPI_BIAS)
+    s = ops.gemm(xp, P["ws"], P["bs"], ops.EPI_BIAS_F32)
+    S.update(xp=xp, tfreq=tfreq, z1=z1, h1t=h1t, temb=temb, c=c, mod=mod)
+    blocks = []
+    for i, bp in enumerate(P["blocks"]):
+        m = mod[:, i * 6 * H:(i + 1) * 6 * H]
+        sh1, sc1, g1, sh2, sc2, g2 = (m[:, j * H:(j + 1) * H] for j in range(6))
+        h1 = ops.rmsnorm_modulate(s, bp["n1"], sh1, sc1, L)
+        qkv_raw = ops.gemm(h1, bp["wqkv"], None, ops.EPI_BIAS)
+        qkv = qkv_raw.clone()
+        ops.qknorm_rope_(qkv, bp["qn"], bp["kn"], pos, heads, d, L)
+        o = ops.attention(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], B, heads, d)
+        a1 = ops.gemm(o, bp["wproj"], bp["bproj"], ops.EPI_BIAS)
+        s_mid = ops.gate_residual(s, a1, g1, L)
+        h2 = ops.rmsnorm_modulate(s_mid, bp["n2"], sh2, sc2, L)
+        y13 = ops.gemm(h2, bp["w13"], None, ops.EPI_BIAS)
+        u = ops.swiglu_fwd(y13)
+        a2 = ops.gemm(u, bp["w2"], None, ops.EPI_BIAS)
+        s_out = ops.gate_residual(s_mid, a2, g2, L)
+        blocks.append(dict(s_in=s, h1=h1, qkv_raw=qkv_raw, qkv=qkv, o=o, a1=a1, s_mid=s_mid, h2=h2, y13=y13, u=u, a2=a2))
+        s = s_out
+    s2 = ops.silu_add_rows(s, temb, L)
+    ycond = ops.gemm(s2, P["wcond"], P["bcond"], ops.EPI_BIAS)
+    R = module.num_blocks - module.num_cond_blocks
+    out = ops.pixel_decoder(x32, ycond, P["blob"], P["postab"], p, module.hidden_size_x, R, out_dtype=F32)
+    S.update(blocks=blocks, s_final=s, s2=s2, ycond=ycond)
+    return out, S
+
+
+def train_backward(module, S: dict, dout: torch.Tensor) -> Dict[str, torch.Tensor]:
+    """Gradients of every parameter (by name) for upstream gradient dout [B,3,H,W]."""
+    x32 = S["x32"]
+    dev = x32.device
+    P = module.prepare(dev)
+    T = P["train"]
+    B, L = S["B"], S["L"]
+    p, H, heads = module.patch_size, module.hidden_size, module.num_groups
+    d = H // heads
+    nb = len(P["blocks"])
+    R = module.num_blocks - module.num_cond_blocks
+    C = module.in_channels
+    G: Dict[str, torch.Tensor] = {}
+    z = lambda *shape: torch.zeros(shape, dtype=F32, device=dev)   # noqa: E731
+
+    # ---- pixel decoder (+ NerfEmbedder)
+    dycond, gdec = ops.pixel_decoder_bwd(x32, S["ycond"], dout.to(F32).contiguous(), T["dec_blob"], P["postab"], p,
+                                         module.hidden_size_x, R)
+    nW = T["dec_blob"].numel()
+    dpostab = gdec[nW:].view(p * p, 32)
+    gx = z(32, C + module.x_embedder.max_freqs ** 2)
+    gx[:, :C] = gdec[0:96].view(32, 3)[:, :C]
+    gx[:, C:] = ops.gemm(ops.transpose_cast(dpostab), T["tabT"], None, ops.EPI_BIAS_F32)      # [32, 64]
+    G["x_embedder.embedder.0.weight"] = gx
+    G["x_embedder.embedder.0.bias"] = _colsum(dpostab)
+    G["dec_net.input_proj.weight"] = gdec[96:1120].view(32, 32)
+    G["dec_net.input_proj.bias"] = gdec[1120:1152]
+    for j in range(R):
+        o0 = 1152 + j * 5344
+        pre = f"dec_net.res_blocks.{j}."
+        G[pre + "adaLN_modulation.1.weight"] = gdec[o0:o0 + 3072].view(96, 32)
+        G[pre + "adaLN_modulation.1.bias"] = gdec[o0 + 3072:o0 + 3168]
+        G[pre + "in_ln.weight"] = gdec[o0 + 3168:o0 + 3200]
+        G[pre + "in_ln.bias"] = gdec[o0 + 3200:o0 + 3232]
+        G[pre + "mlp.0.weight"] = gdec[o0 + 3232:o0 + 4256].view(32, 32)
+        G[pre + "mlp.0.bias"] = gdec[o0 + 4256:o0 + 4288]
+        G[pre + "mlp.2.weight"] = gdec[o0 + 4288:o0 + 5312].view(32, 32)
+        G[pre + "mlp.2.bias"] = gdec[o0 + 5312:o0 + 5344]
+    of = 1152 + R * 5344
+    G["dec_net.final_layer.linear.weight"] = gdec[of:of + 128].view(4, 32)[:C]
+    G["dec_net.final_layer.linear.bias"] = gdec[of + 128:of + 128 + C]
+
+    # ---- cond_embed: ycond = s2 . wcond^T + bcond
+    G["dec_net.cond_embed.weight"] = _wgrad(dycond, S["s2"])
+    G["dec_net.cond_embed.bias"] = _colsum(dycond)
+    ds2 = ops.gemm(dycond, T["wcondT"], None, ops.EPI_BIAS)
+    del dycond
+    # ---- s2 = silu(s + temb)
+    dtemb = z(B, H)
+    ds = ops.silu_add_rows_bwd(ds2, S["s_final"], S["temb"], dtemb, L)
+    del ds2
+
+    # ---- DiT blocks
+    dmod = z(B, nb * 6 * H)
+    mod = S["mod"]
+    for i in reversed(range(nb)):
+        bp, bt, sv = P["blocks"][i], T["blocks"][i], S["blocks"][i]
+        pre = f"blocks.{i}."
+        m = mod[:, i * 6 * H:(i + 1) * 6 * H]
+        dm = dmod[:, i * 6 * H:(i + 1) * 6 * H]
+        sc1, g1, sc2, g2 = m[:, H:2 * H], m[:, 2 * H:3 * H], m[:, 4 * H:5 * H], m[:, 5 * H:6 * H]
+        dsh1, dsc1, dg1, dsh2, dsc2, dg2 = (dm[:, j * H:(j + 1) * H] for j in range(6))
+        F_ = module.blocks[i].mlp.w1.weight.shape[0]
+        Fp = P["ffn_pad"]
+        # MLP branch
+        da2 = ops.gate_bwd(ds, sv["a2"], g2, dg2, L)
+        G[pre + "mlp.w2.weight"] = _wgrad(da2, sv["u"])[:, :F_]
+        du = ops.gemm(da2, bt["w2T"], None, ops.EPI_BIAS)
+        dy13 = ops.swiglu_bwd(sv["y13"], du)
+        dw13 = _wgrad(dy13, sv["h2"]).view(Fp // 16, 2, 16, H)
+        G[pre + "mlp.w1.weight"] = dw13[:, 0].reshape(Fp, H)[:F_]
+        G[pre + "mlp.w3.weight"] = dw13[:, 1].reshape(Fp, H)[:F_]
+        dh2 = ops.gemm(dy13, bt["w13T"], None, ops.EPI_BIAS)
+        dn2 = z(H)
+        ops.rmsnorm_modulate_bwd_(ds, dh2, sv["s_mid"], bp["n2"], sc2, dn2, dsh2, dsc2, L)
+        G[pre + "norm2.weight"] = dn2
+        del da2, du, dy13, dh2
+        # attention branch
+        dbproj = z(H)
+        da1 = ops.gate_bwd(ds, sv["a1"], g1, dg1, L, dbias=dbproj)
+        G[pre + "attn.proj.bias"] = dbproj
+        G[pre + "attn.proj.weight"] = _wgrad(da1, sv["o"])
+        do = ops.gemm(da1, bt["wprojT"], None, ops.EPI_BIAS)
+        qkv = sv["qkv"]
+        dqkv = torch.empty_like(qkv)
+        ops.attention_bwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], sv["o"], do,
+                          dqkv[:, :H], dqkv[:, H:2 * H], dqkv[:, 2 * H:], B, heads, d)
+        dqn, dkn = z(d), z(d)
+        ops.headnorm_rope_bwd_(dqkv, sv["qkv_raw"], 0, bp["qn"], S["pos"], dqn, heads, d, L)
+        ops.headnorm_rope_bwd_(dqkv, sv["qkv_raw"], H, bp["kn"], S["pos"], dkn, heads, d, L)
+        G[pre + "attn.q_norm.weight"], G[pre + "attn.k_norm.weight"] = dqn, dkn
+        G[pre + "attn.qkv.weight"] = _wgrad(dqkv, sv["h1"])
+        dh1 = ops.gemm(dqkv, bt["wqkvT"], None, ops.EPI_BIAS)
+        dn1 = z(H)
+        ops.rmsnorm_modulate_bwd_(ds, dh1, sv["s_in"], bp["n1"], sc1, dn1, dsh1, dsc1, L)
+        G[pre + "norm1.weight"] = dn1
+        del da1, do, dqkv, dh1
+        S["blocks"][i] = None   # release the block's activations
+
+    # ---- s_embedder: s0 = xp . ws^T + bs
+    G["s_embedder.proj.weight"] = _wgrad(ds, S["xp"])
+    G["s_embedder.proj.bias"] = _colsum(ds)
+    # ---- adaLN of all blocks: mod = c . wada^T + bada
+    if nb:
+        dwada = _wgrad(dmod, S["c"])                            # [nb*6H, H]
+        dbada = _colsum(dmod)
+        for i in range(nb):
+            G[f"blocks.{i}.adaLN_modulation.0.weight"] = dwada[i * 6 * H:(i + 1) * 6 * H]
+            G[f"blocks.{i}.adaLN_modulation.0.bias"] = dbada[i * 6 * H:(i + 1) * 6 * H]
+        dc = ops.gemm(ops.cast_bf16(dmod), T["wadaT"], None, ops.EPI_BIAS_F32)
+    else:
+        dc = z(B, H)
+    # ---- c = silu(temb + table[y])
+    dtab = torch.zeros_like(P["ytab"])
+    ops.cond_combine_bwd_(dc, S["temb"], P["ytab"], S["y"], dtemb, dtab)
+    G["y_embedder.embedding_table.weight"] = dtab
+    # ---- t_embedder: temb = silu(tfreq . wt0^T + bt0) . wt2^T + bt2
+    G["t_embedder.mlp.2.weight"] = _wgrad(dtemb, S["h1t"])
+    G["t_embedder.mlp.2.bias"] = _colsum(dtemb)
+    dh1t = ops.gemm(ops.cast_bf16(dtemb), T["wt2T"], None, ops.EPI_BIAS)
+    dz1 = ops.silu_bwd(S["z1"], dh1t)
+    G["t_embedder.mlp.0.weight"] = _wgrad(dz1, S["tfreq"])
+    G["t_embedder.mlp.0.bias"] = _colsum(dz1)
+    return G
+
+
+class DenoiserFn(torch.autograd.Function):
+    """out = PixNerDiT(x, t, y) as one autograd node; *params only tell autograd which leaves receive gradients."""
+
+    @staticmethod
+    def forward(ctx, module, names: List[str], x, t, y, *params):
+        x32 = x.detach().to(F32).contiguous()
+        out, S = train_forward(module, x32, t.detach().reshape(-1).to(F32), y.detach().reshape(-1))
+        ctx.module, ctx.names, ctx.S = module, names, S
+        ctx.meta = [(p.requires_grad, p.shape, p.dtype) for p in params]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        if ctx.S is None:
+            raise RuntimeError("deco_b200 denoiser: backward called twice (activations are released after one pass)")
+        G = train_backward(ctx.module, ctx.S, dout)
+        ctx.S = None
+        grads = []
+        for n, (need, shape, dtype) in zip(ctx.names, ctx.meta):
+            g = G.get(n) if need else None
+            if need and g is None:
+                raise RuntimeError(f"deco_b200 denoiser backward produced no gradient for {n}")
+            grads.append(None if g is None else g.reshape(shape).to(dtype))
+        return (None, None, None, None, None) + tuple(grads)
+
+
+def denoiser_train_apply(module, x, t, y):
+    names, params = zip(*module.named_parameters())
+    return DenoiserFn.apply(module, list(names), x, t, y, *params)

@@ -1,0 +1,576 @@
+// Backward of the memory-bound pieces of the DiT block (training step, SURVEY.md 8(f) rank 1 / BASELINE configs[3]).
+// The dense contractions of the backward pass (dgrad, wgrad) run on the tcgen05 GEMM of gemm_tcgen05.cu; this file holds
+// the glue around them: operand transposes for wgrad, gate / residual, SwiGLU, RMSNorm + modulate, per-head q/k RMSNorm +
+// RoPE, silu(t + s), embedding and bias reductions.  All HBM-bound, one pass each, fp32 math, bf16 operands for the GEMMs.
+//
+// Differentiates (reference, /root/reference/src/models/transformer/dit_c2i_DeCo.py):
+//   :11-12 modulate, :94-99 RMSNorm.forward, :112-114 FeedForward.forward, :134-145 apply_rotary_emb,
+//   :178-180 q_norm / k_norm, :206-210 FlattenDiTBlock.forward (gated residuals), :494 silu(t + y), :499 silu(t + s).
+#include "common.cuh"
+
+namespace deco {
+
+__device__ __forceinline__ float dsilu_f(float x) {
+    const float s = __fdividef(1.0f, 1.0f + __expf(-x));
+    return s * fmaf(x, 1.0f - s, 1.0f);
+}
+
+template <typename T> struct Pair;
+template <> struct Pair<float> {
+    static __device__ __forceinline__ float2 ld(const float* p) { return *reinterpret_cast<const float2*>(p); }
+};
+template <> struct Pair<__nv_bfloat16> {
+    static __device__ __forceinline__ float2 ld(const __nv_bfloat16* p) { return unpack_bf2(*reinterpret_cast<const uint32_t*>(p)); }
+};
+
+// ---------------------------------------------------------------- dst[c][r] = bf16(src[r][c]), rows r >= R zero-filled up to Rp
+// 64 x 64 tiles; 32-bit global accesses on both sides (two bf16 / one float2 per lane).  C even.
+template <typename TIn>
+__global__ void __launch_bounds__(256) transpose_cast_kernel(const TIn* __restrict__ src, long long lds,
+                                                             __nv_bfloat16* __restrict__ dst, long long ldd,
+                                                             int R, int C, int Rp)
+{
+    __shared__ __nv_bfloat16 tile[64][66];
+    const int c0 = blockIdx.x * 64, r0 = blockIdx.y * 64;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int i = ty; i < 64; i += 8) {
+        const int r = r0 + i, c = c0 + 2 * tx;
+        float2 v = make_float2(0.f, 0.f);
+        if (r < R && c < C) v = Pair<TIn>::ld(src + (long long)r * lds + c);
+        tile[i][2 * tx] = f2bf(v.x);
+        tile[i][2 * tx + 1] = f2bf(v.y);
+    }
+    __syncthreads();
+    for (int i = ty; i < 64; i += 8) {
+        const int c = c0 + i, r = r0 + 2 * tx;
+        if (c < C && r < Rp) {
+            __nv_bfloat162 o;
+            o.x = tile[2 * tx][i];
+            o.y = tile[2 * tx + 1][i];
+            *reinterpret_cast<__nv_bfloat162*>(dst + (long long)c * ldd + r) = o;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- out[c] += sum_r x[r][c]   (bias gradients)
+template <typename TIn>
+__global__ void __launch_bounds__(256) colsum_kernel(const TIn* __restrict__ x, long long ldx, float* __restrict__ out,
+                                                     long long M, int N, int rows_per_block)
+{
+    __shared__ float2 part[8][32];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 64 + 2 * tx;
+    const long long r0 = (long long)blockIdx.y * rows_per_block;
+    long long r1 = r0 + rows_per_block;
+    if (r1 > M) r1 = M;
+    float2 acc = make_float2(0.f, 0.f);
+    if (c < N)
+        for (long long r = r0 + ty; r < r1; r += 8) {
+            const float2 v = Pair<TIn>::ld(x + r * ldx + c);
+            acc.x += v.x; acc.y += v.y;
+        }
+    part[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && c < N) {
+        for (int j = 1; j < 8; ++j) { acc.x += part[j][tx].x; acc.y += part[j][tx].y; }
+        atomicAdd(out + c, acc.x);
+        atomicAdd(out + c + 1, acc.y);
+    }
+}
+
+// ---------------------------------------------------------------- out[r][c] = s[r][c] + gate[r / L][c] * a[r][c]
+__global__ void __launch_bounds__(256) gate_residual_kernel(const float* s, const __nv_bfloat16* __restrict__ a,
+                                                            const __nv_bfloat16* __restrict__ gate, long long gate_stride,
+                                                            float* out, int L, long long M, int Hd)
+{
+    const int npair = Hd >> 1;
+    const long long total = M * npair;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const long long r = i / npair;
+        const int c = 2 * (int)(i % npair);
+        const float2 av = Pair<__nv_bfloat16>::ld(a + r * Hd + c);
+        const float2 g = Pair<__nv_bfloat16>::ld(gate + (r / L) * gate_stride + c);
+        float2 v = *reinterpret_cast<const float2*>(s + r * Hd + c);
+        v.x = fmaf(g.x, av.x, v.x); v.y = fmaf(g.y, av.y, v.y);
+        *reinterpret_cast<float2*>(out + r * Hd + c) = v;
+    }
+}
+
+// ---------------------------------------------------------------- backward of s_out = s_in + gate[b] * a
+//   da = gate * ds (bf16), dgate[b] += sum_rows ds * a, dbias += sum_rows da (optional: a = x.W^T + bias)
+// Block = RB rows of one image (RB divides L); thread owns column pairs tid + 256 k.
+constexpr int kMaxPairIters = 4;   // hidden <= 2048
+__global__ void __launch_bounds__(256) gate_bwd_kernel(const float* __restrict__ ds, const __nv_bfloat16* __restrict__ a,
+                                                       const __nv_bfloat16* __restrict__ gate, long long gate_stride,
+                                                       __nv_bfloat16* __restrict__ da, float* __restrict__ dgate,
+                                                       long long dgate_stride, float* __restrict__ dbias,
+                                                       int L, int RB, int Hd)
+{
+    const long long r0 = (long long)blockIdx.x * RB;
+    const long long b = r0 / L;
+    const int npair = Hd >> 1;
+    float2 g[kMaxPairIters], accg[kMaxPairIters], accb[kMaxPairIters];
+#pragma unroll
+    for (int k = 0; k < kMaxPairIters; ++k) {
+        const int p = threadIdx.x + k * 256;
+        g[k] = p < npair ? Pair<__nv_bfloat16>::ld(gate + b * gate_stride + 2 * p) : make_float2(0.f, 0.f);
+        accg[k] = make_float2(0.f, 0.f);
+        accb[k] = make_float2(0.f, 0.f);
+    }
+    for (int i = 0; i < RB; ++i) {
+        const long long r = r0 + i;
+#pragma unroll
+        for (int k = 0; k < kMaxPairIters; ++k) {
+            const int p = threadIdx.x + k * 256;
+            if (p < npair) {
+                const float2 d = *reinterpret_cast<const float2*>(ds + r * Hd + 2 * p);
+                const float2 av = Pair<__nv_bfloat16>::ld(a + r * Hd + 2 * p);
+                const float2 o = make_float2(g[k].x * d.x, g[k].y * d.y);
+                *reinterpret_cast<uint32_t*>(da + r * Hd + 2 * p) = pack_bf2(o.x, o.y);
+                accg[k].x = fmaf(d.x, av.x, accg[k].x); accg[k].y = fmaf(d.y, av.y, accg[k].y);
+                accb[k].x += o.x; accb[k].y += o.y;
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kMaxPairIters; ++k) {
+        const int p = threadIdx.x + k * 256;
+        if (p < npair) {
+            atomicAdd(dgate + b * dgate_stride + 2 * p, accg[k].x);
+            atomicAdd(dgate + b * dgate_stride + 2 * p + 1, accg[k].y);
+            if (dbias) { atomicAdd(dbias + 2 * p, accb[k].x); atomicAdd(dbias + 2 * p + 1, accb[k].y); }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- backward of out = silu(x + row[b])  (dit_c2i_DeCo.py:499)
+//   dx = dout * silu'(x + row) (fp32), drow[b] += sum_rows dx
+__global__ void __launch_bounds__(256) silu_add_rows_bwd_kernel(const __nv_bfloat16* __restrict__ dout,
+                                                                const float* __restrict__ x,
+                                                                const __nv_bfloat16* __restrict__ rowv,
+                                                                float* __restrict__ dx, float* __restrict__ drow,
+                                                                int L, int RB, int Hd)
+{
+    const long long r0 = (long long)blockIdx.x * RB;
+    const long long b = r0 / L;
+    const int npair = Hd >> 1;
+    float2 rv[kMaxPairIters], acc[kMaxPairIters];
+#pragma unroll
+    for (int k = 0; k < kMaxPairIters; ++k) {
+        const int p = threadIdx.x + k * 256;
+        rv[k] = p < npair ? Pair<__nv_bfloat16>::ld(rowv + b * Hd + 2 * p) : make_float2(0.f, 0.f);
+        acc[k] = make_float2(0.f, 0.f);
+    }
+    for (int i = 0; i < RB; ++i) {
+        const long long r = r0 + i;
+#pragma unroll
+        for (int k = 0; k < kMaxPairIters; ++k) {
+            const int p = threadIdx.x + k * 256;
+            if (p < npair) {
+                const float2 d = Pair<__nv_bfloat16>::ld(dout + r * Hd + 2 * p);
+                const float2 xv = *reinterpret_cast<const float2*>(x + r * Hd + 2 * p);
+                const float2 o = make_float2(d.x * dsilu_f(xv.x + rv[k].x), d.y * dsilu_f(xv.y + rv[k].y));
+                *reinterpret_cast<float2*>(dx + r * Hd + 2 * p) = o;
+                acc[k].x += o.x; acc[k].y += o.y;
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kMaxPairIters; ++k) {
+        const int p = threadIdx.x + k * 256;
+        if (p < npair) { atomicAdd(drow + b * Hd + 2 * p, acc[k].x); atomicAdd(drow + b * Hd + 2 * p + 1, acc[k].y); }
+    }
+}
+
+// ---------------------------------------------------------------- SwiGLU on the interleaved [16 x w1 | 16 x w3] columns
+// forward:  u[r][16 g + i] = silu(y[r][32 g + i]) * y[r][32 g + 16 + i]
+// backward: dy[r][32 g + i] = du * b * silu'(a),  dy[r][32 g + 16 + i] = du * silu(a)
+// One thread per 8 output columns.
+template <bool BWD>
+__global__ void __launch_bounds__(256) swiglu_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ du,
+                                                     __nv_bfloat16* __restrict__ out, long long M, int Fp)
+{
+    const int nch = Fp >> 3;
+    const long long total = M * nch;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const long long r = i / nch;
+        const int ch = (int)(i % nch);           // 8 columns [8 ch, 8 ch + 8) of u
+        const int g = ch >> 1, half = ch & 1;
+        const __nv_bfloat16* ya = y + r * 2 * Fp + 32 * g + 8 * half;
+        const uint4 qa = *reinterpret_cast<const uint4*>(ya), qb = *reinterpret_cast<const uint4*>(ya + 16);
+        const uint32_t wa[4] = {qa.x, qa.y, qa.z, qa.w}, wb[4] = {qb.x, qb.y, qb.z, qb.w};
+        if (!BWD) {
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 av = unpack_bf2(wa[e]), bv = unpack_bf2(wb[e]);
+                o[e] = pack_bf2(silu_f(av.x) * bv.x, silu_f(av.y) * bv.y);
+            }
+            *reinterpret_cast<uint4*>(out + r * Fp + 8 * ch) = make_uint4(o[0], o[1], o[2], o[3]);
+        } else {
+            const uint4 qd = *reinterpret_cast<const uint4*>(du + r * Fp + 8 * ch);
+            const uint32_t wd[4] = {qd.x, qd.y, qd.z, qd.w};
+            uint32_t oa[4], ob[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 av = unpack_bf2(wa[e]), bv = unpack_bf2(wb[e]), d = unpack_bf2(wd[e]);
+                oa[e] = pack_bf2(d.x * bv.x * dsilu_f(av.x), d.y * bv.y * dsilu_f(av.y));
+                ob[e] = pack_bf2(d.x * silu_f(av.x), d.y * silu_f(av.y));
+            }
+            __nv_bfloat16* oy = out + r * 2 * Fp + 32 * g + 8 * half;
+            *reinterpret_cast<uint4*>(oy) = make_uint4(oa[0], oa[1], oa[2], oa[3]);
+            *reinterpret_cast<uint4*>(oy + 16) = make_uint4(ob[0], ob[1], ob[2], ob[3]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- backward of h = rms(x) * w * (1 + scale[b]) + shift[b]
+//   dxh = dh * w * (1 + scale);  dx = r * dxh - x * r^3 * mean(dxh * x);  ds += dx   (the residual stream gradient)
+//   dshift[b] += sum_rows dh;  dscale[b] += sum_rows dh * xhat * w;  dw += sum_rows dh * xhat * (1 + scale)
+// Block = RB rows of one image; thread owns 4 columns (blockDim = ceil32(hidden / 4)); one block reduction per row.
+__global__ void __launch_bounds__(512) rmsnorm_modulate_bwd_kernel(
+    const __nv_bfloat16* __restrict__ dh, const float* __restrict__ x, const float* __restrict__ w,
+    const __nv_bfloat16* __restrict__ scale, long long mod_stride, float* __restrict__ ds,
+    float* __restrict__ dw, float* __restrict__ dshift, float* __restrict__ dscale, long long dmod_stride,
+    int L, int RB, int Hd, float eps)
+{
+    __shared__ float2 red[2][16];
+    const long long r0 = (long long)blockIdx.x * RB;
+    const long long b = r0 / L;
+    const int c = 4 * threadIdx.x;
+    const bool act = c < Hd;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    float wv[4] = {0.f, 0.f, 0.f, 0.f}, sc1[4] = {0.f, 0.f, 0.f, 0.f};
+    if (act) {
+        const float4 w4 = __ldg(reinterpret_cast<const float4*>(w + c));
+        wv[0] = w4.x; wv[1] = w4.y; wv[2] = w4.z; wv[3] = w4.w;
+        const uint2 s2 = *reinterpret_cast<const uint2*>(scale + b * mod_stride + c);
+        const float2 s0 = unpack_bf2(s2.x), s1 = unpack_bf2(s2.y);
+        sc1[0] = 1.0f + s0.x; sc1[1] = 1.0f + s0.y; sc1[2] = 1.0f + s1.x; sc1[3] = 1.0f + s1.y;
+    }
+    float a_sh[4] = {0.f, 0.f, 0.f, 0.f}, a_sc[4] = {0.f, 0.f, 0.f, 0.f}, a_w[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int i = 0; i < RB; ++i) {
+        const long long r = r0 + i;
+        float xv[4] = {0.f, 0.f, 0.f, 0.f}, dv[4] = {0.f, 0.f, 0.f, 0.f};
+        if (act) {
+            const float4 x4 = *reinterpret_cast<const float4*>(x + r * Hd + c);
+            xv[0] = x4.x; xv[1] = x4.y; xv[2] = x4.z; xv[3] = x4.w;
+            const uint2 d2 = *reinterpret_cast<const uint2*>(dh + r * Hd + c);
+            const float2 d0 = unpack_bf2(d2.x), d1 = unpack_bf2(d2.y);
+            dv[0] = d0.x; dv[1] = d0.y; dv[2] = d1.x; dv[3] = d1.y;
+        }
+        float s1 = 0.f, s2 = 0.f;
+        float dxh[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            dxh[e] = dv[e] * wv[e] * sc1[e];
+            s1 = fmaf(xv[e], xv[e], s1);
+            s2 = fmaf(dxh[e], xv[e], s2);
+        }
+        s1 = warp_sum(s1); s2 = warp_sum(s2);
+        if (lane == 0) red[i & 1][warp] = make_float2(s1, s2);
+        __syncthreads();
+        s1 = 0.f; s2 = 0.f;
+        for (int j = 0; j < nwarp; ++j) { s1 += red[i & 1][j].x; s2 += red[i & 1][j].y; }
+        const float rs = rsqrtf(s1 / (float)Hd + eps);
+        const float k2 = rs * rs * rs * s2 / (float)Hd;
+        if (act) {
+            float4* dp = reinterpret_cast<float4*>(ds + r * Hd + c);
+            float4 d4 = *dp;
+            d4.x += rs * dxh[0] - xv[0] * k2; d4.y += rs * dxh[1] - xv[1] * k2;
+            d4.z += rs * dxh[2] - xv[2] * k2; d4.w += rs * dxh[3] - xv[3] * k2;
+            *dp = d4;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float xh = xv[e] * rs;
+                a_sh[e] += dv[e];
+                a_sc[e] = fmaf(dv[e] * xh, wv[e], a_sc[e]);
+                a_w[e] = fmaf(dv[e] * xh, sc1[e], a_w[e]);
+            }
+        }
+    }
+    if (act) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            atomicAdd(dshift + b * dmod_stride + c + e, a_sh[e]);
+            atomicAdd(dscale + b * dmod_stride + c + e, a_sc[e]);
+            atomicAdd(dw + c + e, a_w[e]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- backward of per-head RMSNorm (+ RoPE), in place on the
+// gradient buffer: g [M, g_stride] holds d(out) for the segment on entry and d(raw) on exit; raw [M, raw_stride] is the
+// GEMM output the forward normalised.  forward (elementwise.cu qknorm_rope_kernel): n = raw * rs, a = w * n,
+// out = rot(a).  One thread per (token, head) vector; weight gradient reduced warp -> block (smem) -> global atomics.
+template <int D>
+__global__ void __launch_bounds__(128) headnorm_rope_bwd_kernel(__nv_bfloat16* __restrict__ g, long long g_stride,
+                                                                const __nv_bfloat16* __restrict__ raw, long long raw_stride,
+                                                                int col, const float* __restrict__ wv,
+                                                                const float2* __restrict__ rope, float* __restrict__ dw,
+                                                                long long M, int heads, int L, float eps)
+{
+    __shared__ float sdw[D];
+    for (int i = threadIdx.x; i < D; i += blockDim.x) sdw[i] = 0.f;
+    __syncthreads();
+    const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool act = item < M * heads;
+    const long long tok = act ? item / heads : 0;
+    const int head = act ? (int)(item % heads) : 0;
+    __nv_bfloat16* gp = g + tok * g_stride + col + (long long)head * D;
+    const __nv_bfloat16* rp = raw + tok * raw_stride + col + (long long)head * D;
+    const float2* cs = rope ? rope + (long long)(tok % L) * (D / 2) : nullptr;
+    float v[D], da[D];
+    float ss = 0.f;
+    if (act) {
+#pragma unroll
+        for (int c = 0; c < D / 8; ++c) {
+            const uint4 q = *reinterpret_cast<const uint4*>(rp + c * 8);
+            const uint4 q2 = *reinterpret_cast<const uint4*>(gp + c * 8);
+            const uint32_t qa[4] = {q.x, q.y, q.z, q.w}, qg[4] = {q2.x, q2.y, q2.z, q2.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 a = unpack_bf2(qa[e]), gg = unpack_bf2(qg[e]);
+                const int j = c * 4 + e;
+                v[2 * j] = a.x; v[2 * j + 1] = a.y;
+                const float2 t = cs ? __ldg(cs + j) : make_float2(1.f, 0.f);
+                da[2 * j] = gg.x * t.x + gg.y * t.y;          // transpose of the rotation
+                da[2 * j + 1] = -gg.x * t.y + gg.y * t.x;
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < D; ++e) ss = fmaf(v[e], v[e], ss);
+    } else {
+#pragma unroll
+        for (int e = 0; e < D; ++e) { v[e] = 0.f; da[e] = 0.f; }
+    }
+    const float rs = rsqrtf(ss / (float)D + eps);
+    float dot = 0.f;
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int e = 0; e < D; ++e) {
+        const float n = v[e] * rs;
+        const float wgt = __ldg(wv + e);
+        float dwe = warp_sum(da[e] * n);
+        if (lane == 0) atomicAdd(&sdw[e], dwe);
+        da[e] *= wgt;                   // d n
+        dot = fmaf(da[e], n, dot);
+        v[e] = n;
+    }
+    dot /= (float)D;
+    if (act) {
+#pragma unroll
+        for (int c = 0; c < D / 8; ++c) {
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int j = c * 4 + e;
+                o[e] = pack_bf2(rs * (da[2 * j] - v[2 * j] * dot), rs * (da[2 * j + 1] - v[2 * j + 1] * dot));
+            }
+            *reinterpret_cast<uint4*>(gp + c * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < D; i += blockDim.x) atomicAdd(dw + i, sdw[i]);
+}
+
+// ---------------------------------------------------------------- backward of c = silu(temb + table[label])  (:493-494)
+//   dpre = dc * silu'(pre);  dtemb += dpre;  dtable[label] += dpre
+__global__ void cond_combine_bwd_kernel(const float* __restrict__ dc, const __nv_bfloat16* __restrict__ temb,
+                                        const float* __restrict__ table, const long long* __restrict__ labels,
+                                        float* __restrict__ dtemb, float* __restrict__ dtable, int B, int Hd, int num_rows)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * Hd) return;
+    const int b = i / Hd, h = i % Hd;
+    long long lab = labels[b];
+    if (lab < 0 || lab >= num_rows) lab = num_rows - 1;
+    const float pre = bf2f(temb[i]) + __ldg(table + lab * Hd + h);
+    const float d = dc[i] * dsilu_f(pre);
+    dtemb[i] += d;
+    atomicAdd(dtable + lab * Hd + h, d);
+}
+
+// ---------------------------------------------------------------- dz = dy * silu'(z)   (t_embedder.mlp[1], :55-57)
+__global__ void silu_bwd_kernel(const __nv_bfloat16* __restrict__ z, const __nv_bfloat16* __restrict__ dy,
+                                __nv_bfloat16* __restrict__ dz, long long n)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        dz[i] = f2bf(bf2f(dy[i]) * dsilu_f(bf2f(z[i])));
+}
+
+static inline unsigned bgrid(long long work, int threads) {
+    long long b = (work + threads - 1) / threads;
+    const long long cap = (long long)kNumSMs * 16;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (unsigned)b;
+}
+
+static inline int rows_block(int L) {   // largest power of two <= 32 dividing L
+    int rb = 32;
+    while (rb > 1 && L % rb) rb >>= 1;
+    return rb;
+}
+
+}  // namespace deco
+
+extern "C" int deco_transpose_cast(const void* src, int src_is_f32, long long lds, void* dst_bf16, long long ldd,
+                                   int R, int C, int Rp, void* stream)
+{
+    using namespace deco;
+    DECO_CHECK_ARG(src && dst_bf16 && R > 0 && C > 0 && Rp >= R, "transpose_cast: bad arguments");
+    DECO_CHECK_ARG(C % 2 == 0 && lds % 2 == 0 && ldd % 2 == 0 && Rp % 2 == 0 && ldd >= Rp,
+                   "transpose_cast: C, Rp and leading dimensions must be even (C=%d Rp=%d lds=%lld ldd=%lld)", C, Rp, lds, ldd);
+    dim3 grid((C + 63) / 64, (Rp + 63) / 64);
+    DECO_CHECK_ARG(grid.y <= 65535, "transpose_cast: too many rows (%d)", Rp);
+    if (src_is_f32)
+        transpose_cast_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)src, lds, (__nv_bfloat16*)dst_bf16, ldd, R, C, Rp);
+    else
+        transpose_cast_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, lds, (__nv_bfloat16*)dst_bf16, ldd, R, C, Rp);
+    DECO_CHECK_LAUNCH("transpose_cast_kernel");
+    return DECO_OK;
+}
+
+extern "C" int deco_colsum(const void* x, int x_is_f32, long long ldx, float* out_accum, long long M, int N, void* stream)
+{
+    using namespace deco;
+    DECO_CHECK_ARG(x && out_accum && M > 0 && N > 0 && N % 2 == 0 && ldx % 2 == 0, "colsum: bad arguments");
+    const int rpb = 256;
+    dim3 grid((N + 63) / 64, (unsigned)((M + rpb - 1) / rpb));
+    DECO_CHECK_ARG(grid.y <= 65535, "colsum: too many rows");
+    if (x_is_f32) colsum_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, ldx, out_accum, M, N, rpb);
+    else colsum_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, ldx, out_accum, M, N, rpb);
+    DECO_CHECK_LAUNCH("colsum_kernel");
+    return DECO_OK;
+}
+
+extern "C" int deco_gate_residual(const float* s, const void* a_bf16, const void* gate_bf16, long long gate_stride,
+                                  float* out, int rows_per_image, long long M, int hidden, void* stream)
+{
+    using namespace deco;
+    DECO_CHECK_ARG(s && out && a_bf16 && gate_bf16 && M > 0 && hidden > 0 && hidden % 2 == 0 && rows_per_image > 0 &&
+                   gate_stride % 2 == 0, "gate_residual: bad arguments");
+    gate_residual_kernel<<<bgrid(M * (hidden / 2), 256), 256, 0, (cudaStream_t)stream>>>(
+        s, (const __nv_bfloat16*)a_bf16, (const __nv_bfloat16*)gate_bf16, gate_stride, out, rows_per_image, M, hidden);
+    DECO_CHECK_LAUNCH("gate_residual_kernel");
+    return DECO_OK;
+}
+
+extern "C" int deco_gate_bwd(const float* ds, const void* a_bf16, const void* gate_bf16, long long gate_stride,
+                             void* da_bf16, float* dgate_accum, long long dgate_stride, float* dbias_accum,
+                             int rows_per_image, long long M, int hidden, void* stream)
+{
+    using namespace deco;
+    DECO_CHECK_ARG(ds && a_bf16 && gate_bf16 && da_bf16 && dgate_accum, "gate_bwd: null pointer");
+    DECO_CHECK_ARG(M > 0 && hidden > 0 && hidden % 2 == 0 && hidden <= 512 * kMaxPairIters && rows_per_image > 0 &&
+                   M % rows_per_image == 0 && gate_stride % 2 == 0, "gate_bwd: bad shape M=%lld hidden=%d L=%d", M, hidden, rows_per_image);
+    const int rb = rows_block(rows_per_image);
+    gate_bwd_kernel<<<(unsigned)(M / rb), 256, 0, (cudaStream_t)stream>>>(
+        ds, (const __nv_bfloat16*)a_bf16, (const __nv_bfloat16*)gate_bf16, gate_stride, (__nv_bfloat16*)da_bf16,
+        dgate_accum, dgate_stride, dbias_accum, rows_per_image, rb, hidden);
+    DECO_CHECK_LAUNCH("gate_bwd_kernel");
+    return DECO_OK;
+}
+
+extern "C" int deco_silu_add_rows_bwd(const void* dout_bf16, const float* x, const void* row_bf16, float* dx,
+                                      float* drow_accum, int rows_per_image, long long M, int hidden, void* stream)
+{
+    using namespace deco;
+    DECO_CHECK_ARG(dout_bf16 && x && row_bf16 && dx && drow_accum, "silu_add_rows_bwd: null pointer");
+    DECO_CHECK_ARG(M > 0 && hidden > 0 && hidden % 2 == 0 && hidden <= 512 * kMaxPairIters && rows_per_image > 0 &&
+                   M % rows_per_image == 0, "silu_add_rows_bwd: bad shape");
+    const int rb = rows_block(rows_per_image);
+    silu_add_rows_bwd_kernel<<<(unsigned)(M / rb), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)dout_bf16, x, (const __nv_bfloat16*)row_bf16, dx, drow_accum, rows_per_image, rb, hidden);
+    DECO_CHECK_LAUNCH("silu_add_rows_bwd_kernel");
+    return DECO_OK;
+}
+
+extern "C" int deco_swiglu_fwd(const void* y13_bf16, void* u_bf16, long long M, int ffn_pad, void* stream)
+{
+    using namespace deco;
+    DECO_CHECK_ARG(y13_bf16 && u_bf16 && M > 0 && ffn_pad > 0 && ffn_pad % 16 == 0, "swiglu_fwd: bad arguments");
+    swiglu_kernel<false><<<bgrid(M * (ffn_pad / 8), 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)y13_bf16, nullptr, (__nv_bfloat16*)u_bf16, M, ffn_pad);
+    DECO_CHECK_LAUNCH("swiglu_kernel<fwd>");
+    return DECO_OK;
+}
+
+extern "C" int deco_swiglu_bwd(const void* y13_bf16, const void* du_bf16, void* dy13_bf16, long long M, int ffn_pad,
+                               void* stream)
+{
+    using namespace deco;
+    DECO_CHECK_ARG(y13_bf16 && du_bf16 && dy13_bf16 && M > 0 && ffn_pad > 0 && ffn_pad % 16 == 0, "swiglu_bwd: bad arguments");
+    swiglu_kernel<true><<<bgrid(M * (ffn_pad / 8), 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)y13_bf16, (const __nv_bfloat16*)du_bf16, (__nv_bfloat16*)dy13_bf16, M, ffn_pad);
+    DECO_CHECK_LAUNCH("swiglu_kernel<bwd>");
+    return DECO_OK;
+}
+
+extern "C" int deco_rmsnorm_modulate_bwd(const void* dh_bf16, const float* x, const float* weight, const void* scale_bf16,
+                                         long long mod_row_stride, float* ds_accum, float* dweight_accum,
+                                         float* dshift_accum, float* dscale_accum, long long dmod_row_stride,
+                                         int rows_per_image, long long M, int hidden, float eps, void* stream)
+{
+    using namespace deco;
+    DECO_CHECK_ARG(dh_bf16 && x && weight && scale_bf16 && ds_accum && dweight_accum && dshift_accum && dscale_accum,
+                   "rmsnorm_modulate_bwd: null pointer");
+    DECO_CHECK_ARG(M > 0 && hidden > 0 && hidden % 4 == 0 && hidden <= 2048 && rows_per_image > 0 &&
+                   M % rows_per_image == 0 && mod_row_stride % 4 == 0, "rmsnorm_modulate_bwd: bad shape");
+    const int rb = rows_block(rows_per_image);
+    const int threads = ((hidden / 4) + 31) / 32 * 32;
+    rmsnorm_modulate_bwd_kernel<<<(unsigned)(M / rb), threads, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)dh_bf16, x, weight, (const __nv_bfloat16*)scale_bf16, mod_row_stride, ds_accum,
+        dweight_accum, dshift_accum, dscale_accum, dmod_row_stride, rows_per_image, rb, hidden, eps);
+    DECO_CHECK_LAUNCH("rmsnorm_modulate_bwd_kernel");
+    return DECO_OK;
+}
+
+extern "C" int deco_headnorm_rope_bwd(void* g_bf16, long long g_stride, const void* raw_bf16, long long raw_stride,
+                                      int col, const float* weight, const float* rope_cos_sin, float* dweight_accum,
+                                      long long M, int heads, int head_dim, int L, float eps, void* stream)
+{
+    using namespace deco;
+    DECO_CHECK_ARG(g_bf16 && raw_bf16 && weight && dweight_accum && M > 0 && heads > 0 && L > 0, "headnorm_rope_bwd: bad arguments");
+    DECO_CHECK_ARG(g_stride % 8 == 0 && raw_stride % 8 == 0 && col % 8 == 0, "headnorm_rope_bwd: strides / col must be multiples of 8");
+    const long long items = M * heads;
+    const unsigned grid = (unsigned)((items + 127) / 128);
+    const float2* rp = (const float2*)rope_cos_sin;
+    if (head_dim == 72)
+        headnorm_rope_bwd_kernel<72><<<grid, 128, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)g_bf16, g_stride, (const __nv_bfloat16*)raw_bf16, raw_stride, col, weight, rp, dweight_accum, M, heads, L, eps);
+    else if (head_dim == 64)
+        headnorm_rope_bwd_kernel<64><<<grid, 128, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)g_bf16, g_stride, (const __nv_bfloat16*)raw_bf16, raw_stride, col, weight, rp, dweight_accum, M, heads, L, eps);
+    else {
+        deco_set_error("headnorm_rope_bwd: head_dim %d not built (64, 72)", head_dim);
+        return DECO_ERR_UNSUPPORTED;
+    }
+    DECO_CHECK_LAUNCH("headnorm_rope_bwd_kernel");
+    return DECO_OK;
+}
+
+extern "C" int deco_cond_combine_bwd(const float* dc, const void* temb_bf16, const float* table, const long long* labels,
+                                     float* dtemb_accum, float* dtable_accum, int B, int hidden, int num_rows, void* stream)
+{
+    using namespace deco;
+    DECO_CHECK_ARG(dc && temb_bf16 && table && labels && dtemb_accum && dtable_accum && B > 0 && hidden > 0 && num_rows > 0,
+                   "cond_combine_bwd: bad arguments");
+    const int n = B * hidden;
+    cond_combine_bwd_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(dc, (const __nv_bfloat16*)temb_bf16, table, labels,
+                                                                               dtemb_accum, dtable_accum, B, hidden, num_rows);
+    DECO_CHECK_LAUNCH("cond_combine_bwd_kernel");
+    return DECO_OK;
+}
+
+extern "C" int deco_silu_bwd(const void* z_bf16, const void* dy_bf16, void* dz_bf16, long long n, void* stream)
+{
+    using namespace deco;
+    DECO_CHECK_ARG(z_bf16 && dy_bf16 && dz_bf16 && n > 0, "silu_bwd: bad arguments");
+    silu_bwd_kernel<<<bgrid(n, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)z_bf16, (const __nv_bfloat16*)dy_bf16,
+                                                                     (__nv_bfloat16*)dz_bf16, n);
+    DECO_CHECK_LAUNCH("silu_bwd_kernel");
+    return DECO_OK;
+}

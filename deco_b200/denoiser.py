@@ -428,9 +428,15 @@ class PixNerDiT(nn.Module):
             raise NotImplementedError("attention masks are not supported (the reference always passes mask=None)")
         if not x.is_cuda:
             raise RuntimeError("deco_b200.PixNerDiT runs on CUDA (sm_100a) only; there is no CPU fallback")
-        if torch.is_grad_enabled() and (x.requires_grad or (self.training and any(p.requires_grad for p in self.parameters()))):
-            raise NotImplementedError("backward kernels for the denoiser are not built yet (inference/eval only); "
-                                      "call under torch.no_grad() / .eval()")
+        if torch.is_grad_enabled() and x.requires_grad:
+            raise NotImplementedError("the denoiser backward yields parameter gradients only (the reference never "
+                                      "differentiates w.r.t. x_t); detach x")
+        if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
+            # training step (training_repa_DeCo.py:257 + loss.backward()): one autograd node, hand-written backward
+            if s is not None:
+                raise NotImplementedError("training with a precomputed s is not supported")
+            from .autograd import denoiser_train_apply
+            return denoiser_train_apply(self, x, t, y), None
         B, Cc, Hh, Ww = x.shape
         p, H = self.patch_size, self.hidden_size
         assert Cc == self.in_channels and Hh % p == 0 and Ww % p == 0
@@ -457,6 +463,8 @@ class PixNerDiT(nn.Module):
     def forward_sx(self, x, t, y, s=None, mask=None):
         """dit_c2i_DeCo.py:512-536: also returns s as [B, H, sqrt(L), sqrt(L)]."""
         out, s2 = self._forward_impl(x, t, y, s, mask)
+        if s2 is None:
+            raise NotImplementedError("forward_sx is inference-only")
         B, L, H = s2.shape
         r = int(math.sqrt(L))
         return out, s2.reshape(B, r, r, H).permute(0, 3, 1, 2)

@@ -348,3 +348,152 @@ def dct_fm_loss(out: torch.Tensor, v_t: torch.Tensor, freq_w: torch.Tensor, freq
     call("deco_dct_fm_loss", ptr(out), int(out.dtype == bf16), ptr(v_t), ptr(freq_w), B, H, W,
          float(freq_loss_weight), ptr(losses), ptr(grad), ptr(upstream), ptr(accum), _st(out))
     return losses, grad
+
+
+# ------------------------------------------------------------------------------------------------ backward (training)
+def transpose_cast(src: torch.Tensor, rows_pad: Optional[int] = None) -> torch.Tensor:
+    """[R, C] (fp32 or bf16, row stride free) -> bf16 [C, Rp] with rows R..Rp zero-filled (Rp = R rounded up to 8):
+    the K-major operands of a wgrad GEMM dW = dY^T . X."""
+    _cuda(src)
+    assert src.dim() == 2 and src.stride(1) == 1 and src.dtype in (bf16, torch.float32)
+    R, Cc = src.shape
+    Rp = (R + 7) // 8 * 8 if rows_pad is None else rows_pad
+    out = torch.empty((Cc, Rp), dtype=bf16, device=src.device)
+    call("deco_transpose_cast", ptr(src), int(src.dtype == torch.float32), src.stride(0), ptr(out), out.stride(0),
+         R, Cc, Rp, _st(src))
+    return out
+
+
+def colsum_(out: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """out[c] += sum_r x[r, c]; out fp32 [N] (caller zeroes it)."""
+    _cuda(out, x)
+    assert x.dim() == 2 and x.stride(1) == 1 and out.dtype == torch.float32 and out.numel() == x.shape[1]
+    call("deco_colsum", ptr(x), int(x.dtype == torch.float32), x.stride(0), ptr(out), x.shape[0], x.shape[1], _st(x))
+    return out
+
+
+def gate_residual(s: torch.Tensor, a: torch.Tensor, gate: torch.Tensor, L: int,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = s + gate[row // L] * a  (fp32 stream, bf16 branch output / gate); out may be s."""
+    _cuda(s, a, gate, out)
+    assert s.dtype == torch.float32 and s.is_contiguous() and a.dtype == bf16 and a.is_contiguous() and a.shape == s.shape
+    assert gate.dtype == bf16 and gate.stride(1) == 1 and gate.shape[1] == s.shape[1]
+    if out is None:
+        out = torch.empty_like(s)
+    assert out.dtype == torch.float32 and out.is_contiguous() and out.shape == s.shape
+    call("deco_gate_residual", ptr(s), ptr(a), ptr(gate), gate.stride(0), ptr(out), L, s.shape[0], s.shape[1], _st(s))
+    return out
+
+
+def gate_bwd(ds: torch.Tensor, a: torch.Tensor, gate: torch.Tensor, dgate: torch.Tensor, L: int,
+             dbias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """da = gate * ds (returned, bf16); dgate (fp32 view [B, H], row stride free) += sum_rows ds * a; dbias += sum da."""
+    _cuda(ds, a, gate, dgate, dbias)
+    assert ds.dtype == torch.float32 and ds.is_contiguous() and a.dtype == bf16 and a.is_contiguous() and a.shape == ds.shape
+    assert gate.dtype == bf16 and gate.stride(1) == 1 and dgate.dtype == torch.float32 and dgate.stride(1) == 1
+    da = torch.empty_like(a)
+    call("deco_gate_bwd", ptr(ds), ptr(a), ptr(gate), gate.stride(0), ptr(da), ptr(dgate), dgate.stride(0), ptr(dbias),
+         L, ds.shape[0], ds.shape[1], _st(ds))
+    return da
+
+
+def silu_add_rows_bwd(dout: torch.Tensor, x: torch.Tensor, row: torch.Tensor, drow: torch.Tensor, L: int) -> torch.Tensor:
+    _cuda(dout, x, row, drow)
+    assert dout.dtype == bf16 and dout.is_contiguous() and x.dtype == torch.float32 and x.is_contiguous()
+    assert row.dtype == bf16 and row.is_contiguous() and drow.dtype == torch.float32 and drow.is_contiguous()
+    dx = torch.empty_like(x)
+    call("deco_silu_add_rows_bwd", ptr(dout), ptr(x), ptr(row), ptr(dx), ptr(drow), L, x.shape[0], x.shape[1], _st(x))
+    return dx
+
+
+def swiglu_fwd(y13: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _cuda(y13)
+    assert y13.dtype == bf16 and y13.is_contiguous()
+    M, N2 = y13.shape
+    if out is None:
+        out = torch.empty((M, N2 // 2), dtype=bf16, device=y13.device)
+    call("deco_swiglu_fwd", ptr(y13), ptr(out), M, N2 // 2, _st(y13))
+    return out
+
+
+def swiglu_bwd(y13: torch.Tensor, du: torch.Tensor) -> torch.Tensor:
+    _cuda(y13, du)
+    assert y13.dtype == bf16 and y13.is_contiguous() and du.dtype == bf16 and du.is_contiguous()
+    M, N2 = y13.shape
+    assert du.shape == (M, N2 // 2)
+    dy = torch.empty_like(y13)
+    call("deco_swiglu_bwd", ptr(y13), ptr(du), ptr(dy), M, N2 // 2, _st(y13))
+    return dy
+
+
+def rmsnorm_modulate_bwd_(ds: torch.Tensor, dh: torch.Tensor, x: torch.Tensor, weight: torch.Tensor, scale: torch.Tensor,
+                          dweight: torch.Tensor, dshift: torch.Tensor, dscale: torch.Tensor, L: int,
+                          eps: float = 1e-6) -> torch.Tensor:
+    """ds += d x of h = rms(x) * w * (1 + scale) + shift; dweight / dshift / dscale accumulated (fp32)."""
+    _cuda(ds, dh, x, weight, scale, dweight, dshift, dscale)
+    assert ds.dtype == torch.float32 and ds.is_contiguous() and x.dtype == torch.float32 and x.is_contiguous()
+    assert dh.dtype == bf16 and dh.is_contiguous() and dh.shape == x.shape == ds.shape
+    assert scale.dtype == bf16 and scale.stride(1) == 1
+    assert dshift.dtype == torch.float32 and dshift.stride(1) == 1 and dshift.stride(0) == dscale.stride(0)
+    call("deco_rmsnorm_modulate_bwd", ptr(dh), ptr(x), ptr(weight), ptr(scale), scale.stride(0), ptr(ds), ptr(dweight),
+         ptr(dshift), ptr(dscale), dshift.stride(0), L, x.shape[0], x.shape[1], float(eps), _st(x))
+    return ds
+
+
+def headnorm_rope_bwd_(g: torch.Tensor, raw: torch.Tensor, col: int, weight: torch.Tensor, rope: Optional[torch.Tensor],
+                       dweight: torch.Tensor, heads: int, head_dim: int, L: int, eps: float = 1e-6) -> torch.Tensor:
+    _cuda(g, raw, weight, rope, dweight)
+    assert g.dtype == bf16 and raw.dtype == bf16 and g.stride(1) == 1 and raw.stride(1) == 1 and g.shape[0] == raw.shape[0]
+    assert dweight.dtype == torch.float32 and dweight.numel() == head_dim
+    call("deco_headnorm_rope_bwd", ptr(g), g.stride(0), ptr(raw), raw.stride(0), col, ptr(weight), ptr(rope), ptr(dweight),
+         g.shape[0], heads, head_dim, L, float(eps), _st(g))
+    return g
+
+
+def cond_combine_bwd_(dc: torch.Tensor, temb: torch.Tensor, table: torch.Tensor, labels: torch.Tensor,
+                      dtemb: torch.Tensor, dtable: torch.Tensor) -> None:
+    _cuda(dc, temb, table, labels, dtemb, dtable)
+    assert dc.dtype == torch.float32 and dc.is_contiguous() and temb.dtype == bf16 and temb.is_contiguous()
+    assert dtemb.dtype == torch.float32 and dtemb.is_contiguous() and dtable.dtype == torch.float32 and dtable.is_contiguous()
+    labels = labels.reshape(-1).to(torch.int64).contiguous()
+    B, Hd = temb.shape
+    call("deco_cond_combine_bwd", ptr(dc), ptr(temb), ptr(table), ptr(labels), ptr(dtemb), ptr(dtable), B, Hd,
+         table.shape[0], _st(dc))
+
+
+def silu_bwd(z: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:
+    _cuda(z, dy)
+    assert z.dtype == bf16 and dy.dtype == bf16 and z.is_contiguous() and dy.is_contiguous() and z.shape == dy.shape
+    dz = torch.empty_like(z)
+    call("deco_silu_bwd", ptr(z), ptr(dy), ptr(dz), z.numel(), _st(z))
+    return dz
+
+
+def attention_bwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, o: torch.Tensor, dout: torch.Tensor,
+                  dq: torch.Tensor, dk: torch.Tensor, dv: torch.Tensor, B: int, heads: int, head_dim: int) -> None:
+    """Gradients of deco_attention_fwd (one key segment) written into the strided views dq / dk / dv."""
+    _cuda(q, k, v, o, dout, dq, dk, dv)
+    Lq, Lk = q.shape[0] // B, k.shape[0] // B
+    for t in (q, k, v, o, dout, dq, dk, dv):
+        assert t.dtype == bf16 and t.stride(1) == 1
+    assert k.stride(0) == v.stride(0) and dk.stride(0) == dv.stride(0)
+    ws = torch.empty((2, B * heads * Lq), dtype=torch.float32, device=q.device)
+    call("deco_attention_bwd", ptr(q), q.stride(0), ptr(k), ptr(v), k.stride(0), ptr(o), o.stride(0), ptr(dout),
+         dout.stride(0), ptr(dq), dq.stride(0), ptr(dk), ptr(dv), dk.stride(0), ptr(ws[0]), ptr(ws[1]), B, heads, Lq, Lk,
+         head_dim, float(head_dim) ** -0.5, _st(q))
+
+
+def pixel_decoder_bwd(x: torch.Tensor, ycond: torch.Tensor, dout: torch.Tensor, blob_f32: torch.Tensor,
+                      postab: torch.Tensor, patch: int, hidden_x: int, num_res_blocks: int):
+    """Returns (dycond bf16 like ycond, grads fp32 [blob floats + p*p*32])."""
+    _cuda(x, ycond, dout, blob_f32, postab)
+    assert x.dtype == torch.float32 and x.is_contiguous() and dout.dtype == torch.float32 and dout.is_contiguous()
+    assert ycond.dtype == bf16 and ycond.is_contiguous() and blob_f32.dtype == torch.float32 and blob_f32.is_contiguous()
+    B, Cc, H, W = x.shape
+    n = _lib.load().deco_decoder_train_blob_floats(num_res_blocks)
+    assert blob_f32.numel() == n and Cc == 3
+    dy = torch.empty_like(ycond)
+    grads = torch.zeros(n + patch * patch * hidden_x, dtype=torch.float32, device=x.device)
+    call("deco_pixel_decoder_bwd", ptr(x), ptr(ycond), ptr(dout), ptr(blob_f32), ptr(postab), ptr(dy), ptr(grads),
+         B, H, W, patch, hidden_x, num_res_blocks, _st(x))
+    return dy, grads

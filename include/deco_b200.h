@@ -172,6 +172,77 @@ int deco_dct_fm_loss(const void* out, int out_is_bf16, const float* v_t, const f
                      int B, int H, int W, float freq_loss_weight,
                      float* losses, void* grad, const float* upstream, double* accum, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Backward of the denoiser (training step, BASELINE configs[3]; reference: PyTorch autograd over dit_c2i_DeCo.py).
+ * Dense dgrad / wgrad contractions reuse deco_gemm_bf16 (dX = dY.W with W^T as the "weight" operand; dW = dY^T.X with
+ * both operands transposed by deco_transpose_cast); the entry points below are the memory-bound glue, the attention
+ * backward and the pixel-decoder backward.  Arguments named *_accum are ACCUMULATED into (atomics): zero them first.
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+/* dst[c][r] = bf16(src[r][c]) for r < R, zero for R <= r < Rp: [R, C] (fp32 or bf16, row stride lds) -> [C, ldd] */
+int deco_transpose_cast(const void* src, int src_is_f32, long long lds, void* dst_bf16, long long ldd,
+                        int R, int C, int Rp, void* stream);
+
+/* out_accum[c] += sum_r x[r][c]  (bias gradients of nn.Linear) */
+int deco_colsum(const void* x, int x_is_f32, long long ldx, float* out_accum, long long M, int N, void* stream);
+
+/* out[m,:] = s[m,:] + gate[m / rows_per_image,:] * a[m,:]  (dit_c2i_DeCo.py:208-209 with the branch output a kept for
+ * backward); out may alias s */
+int deco_gate_residual(const float* s, const void* a_bf16, const void* gate_bf16, long long gate_stride,
+                       float* out, int rows_per_image, long long M, int hidden, void* stream);
+
+/* backward of the above: da = gate * ds (bf16); dgate[b,:] += sum_rows ds * a; dbias += sum_rows da (may be NULL) */
+int deco_gate_bwd(const float* ds, const void* a_bf16, const void* gate_bf16, long long gate_stride,
+                  void* da_bf16, float* dgate_accum, long long dgate_stride, float* dbias_accum,
+                  int rows_per_image, long long M, int hidden, void* stream);
+
+/* backward of out = silu(x + row[b]) (dit_c2i_DeCo.py:499): dx = dout * silu'(x + row) (fp32, written);
+ * drow[b,:] += sum_rows dx */
+int deco_silu_add_rows_bwd(const void* dout_bf16, const float* x, const void* row_bf16, float* dx,
+                           float* drow_accum, int rows_per_image, long long M, int hidden, void* stream);
+
+/* SwiGLU on the interleaved [16 x w1 | 16 x w3] columns of y13 [M, 2*ffn_pad] (dit_c2i_DeCo.py:112-114):
+ * forward u = silu(a) * b [M, ffn_pad]; backward dy13 from du (same interleaved layout as y13) */
+int deco_swiglu_fwd(const void* y13_bf16, void* u_bf16, long long M, int ffn_pad, void* stream);
+int deco_swiglu_bwd(const void* y13_bf16, const void* du_bf16, void* dy13_bf16, long long M, int ffn_pad, void* stream);
+
+/* backward of deco_rmsnorm_modulate on the fp32 stream (dit_c2i_DeCo.py:94-99, :11-12): ds_accum[m,:] += d x;
+ * dweight_accum[hidden], dshift_accum / dscale_accum [B, dmod_row_stride] */
+int deco_rmsnorm_modulate_bwd(const void* dh_bf16, const float* x, const float* weight, const void* scale_bf16,
+                              long long mod_row_stride, float* ds_accum, float* dweight_accum,
+                              float* dshift_accum, float* dscale_accum, long long dmod_row_stride,
+                              int rows_per_image, long long M, int hidden, float eps, void* stream);
+
+/* backward of per-head RMSNorm (+ RoPE when rope_cos_sin != NULL) for one segment (dit_c2i_DeCo.py:178-180, :134-145):
+ * g [M, g_stride] holds d(out) at columns [col, col + heads*head_dim) on entry and d(raw) on exit; raw = the QKV GEMM
+ * output the forward normalised; dweight_accum [head_dim] */
+int deco_headnorm_rope_bwd(void* g_bf16, long long g_stride, const void* raw_bf16, long long raw_stride,
+                           int col, const float* weight, const float* rope_cos_sin, float* dweight_accum,
+                           long long M, int heads, int head_dim, int L, float eps, void* stream);
+
+/* backward of deco_cond_combine (dit_c2i_DeCo.py:493-494): dpre = dc * silu'(temb + table[y]);
+ * dtemb_accum += dpre; dtable_accum[y] += dpre */
+int deco_cond_combine_bwd(const float* dc, const void* temb_bf16, const float* table, const long long* labels,
+                          float* dtemb_accum, float* dtable_accum, int B, int hidden, int num_rows, void* stream);
+
+/* dz = dy * silu'(z)  (t_embedder.mlp[1], dit_c2i_DeCo.py:55-57) */
+int deco_silu_bwd(const void* z_bf16, const void* dy_bf16, void* dz_bf16, long long n, void* stream);
+
+/* backward of deco_attention_fwd (single key segment): dq / dk / dv are strided views like q / k / v;
+ * lse2_ws and delta_ws are fp32 workspaces of B*heads*Lq elements (csrc/attention_bwd.cu) */
+int deco_attention_bwd(const void* q, long long q_stride, const void* k, const void* v, long long kv_stride,
+                       const void* o, long long o_stride, const void* dout, long long do_stride,
+                       void* dq, long long dq_stride, void* dk, void* dv, long long dkv_stride,
+                       float* lse2_ws, float* delta_ws, int B, int heads, int Lq, int Lk, int head_dim,
+                       float scale, void* stream);
+
+/* backward of deco_pixel_decoder: dycond bf16 [B*L, p*p*32]; grad_accum = deco_decoder_train_blob_floats(R) floats in
+ * the layout of blob_f32 (csrc/decoder_bwd.cu) followed by d postab [p*p, 32]; dout fp32 [B,3,H,W] */
+int deco_decoder_train_blob_floats(int num_res_blocks);
+int deco_pixel_decoder_bwd(const float* x, const void* ycond_bf16, const float* dout, const float* blob_f32,
+                           const float* postab, void* dycond_bf16, float* grad_accum, int B, int H, int W,
+                           int patch, int hidden_x, int num_res_blocks, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

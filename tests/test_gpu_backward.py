@@ -1,0 +1,345 @@
+"""GPU parity of the training-step backward (BASELINE configs[3]): every backward kernel against PyTorch autograd of the
+same op, then the whole denoiser + DCT/FM loss against autograd over the fp32 oracle.
+
+Tolerances: the kernels take / emit bf16 GEMM operands like the forward (reference: bf16 autocast), so element-wise
+outputs are compared at rel-L2 <= 1e-2 (bf16 rounding is 4e-3 worst case per element, ~2e-3 in L2) and fp32 reductions at
+<= 2e-3; whole-model parameter gradients at <= 3e-2 per tensor against the fp32 oracle (the reference's own bf16-autocast
+gradients sit at 1-2e-2 from its fp32 self on these sizes)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import build_module, rel_l2
+from oracle import deco_oracle as O
+
+pytestmark = pytest.mark.gpu
+bf16 = torch.bfloat16
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda:0")
+
+
+def _g(seed):
+    return torch.Generator(device="cuda").manual_seed(seed)
+
+
+def test_transpose_cast_and_colsum(dev):
+    from deco_b200 import ops
+    for dt in (torch.float32, bf16):
+        for R, C in [(70, 130), (256, 64), (5, 34)]:
+            x = torch.randn(R, C + 6, device=dev, generator=_g(R)).to(dt)[:, :C]
+            t = ops.transpose_cast(x)
+            Rp = (R + 7) // 8 * 8
+            assert t.shape == (C, Rp)
+            assert torch.equal(t[:, :R], x.to(bf16).t())
+            assert float(t[:, R:].abs().sum()) == 0.0
+            out = ops.colsum_(torch.zeros(C, device=dev), x)
+            assert rel_l2(out, x.float().sum(0)) < 1e-5
+
+
+def test_wgrad_dgrad_through_the_gemm(dev):
+    from deco_b200 import ops
+    from deco_b200.autograd import _wgrad
+    M, N, K = 520, 144, 264
+    x = torch.randn(M, K, device=dev, generator=_g(1)).to(bf16)
+    w = (torch.randn(N, K, device=dev, generator=_g(2)) * K ** -0.5).to(bf16)
+    dy = torch.randn(M, N, device=dev, generator=_g(3)).to(bf16)
+    dw = _wgrad(dy, x)
+    assert rel_l2(dw, dy.float().t() @ x.float()) < 2e-3
+    dx = ops.gemm(dy, ops.transpose_cast(w, rows_pad=N), None, ops.EPI_BIAS)
+    assert rel_l2(dx.float(), dy.float() @ w.float()) < 5e-3
+    # tiny reduction dimension (batch-sized wgrad: adaLN, t_embedder)
+    dy2 = torch.randn(4, N, device=dev, generator=_g(4))
+    x2 = torch.randn(4, K, device=dev, generator=_g(5)).to(bf16)
+    assert rel_l2(_wgrad(dy2, x2), dy2.to(bf16).float().t() @ x2.float()) < 2e-3
+
+
+@pytest.mark.parametrize("B,L,H", [(2, 16, 576), (3, 64, 1152), (2, 4, 144)])
+def test_gate_and_silu_rows_backward(dev, B, L, H):
+    from deco_b200 import ops
+    M = B * L
+    ds = torch.randn(M, H, device=dev, generator=_g(1))
+    a = torch.randn(M, H, device=dev, generator=_g(2)).to(bf16)
+    mod = torch.randn(B, 3 * H, device=dev, generator=_g(3)).to(bf16)
+    gate = mod[:, H:2 * H]
+    s = torch.randn(M, H, device=dev, generator=_g(4))
+    # forward
+    out = ops.gate_residual(s, a, gate, L)
+    ref = s + gate.float().repeat_interleave(L, 0) * a.float()
+    assert rel_l2(out, ref) < 1e-6
+    # backward
+    dmod = torch.zeros(B, 3 * H, device=dev)
+    dbias = torch.zeros(H, device=dev)
+    da = ops.gate_bwd(ds, a, gate, dmod[:, H:2 * H], L, dbias=dbias)
+    da_ref = gate.float().repeat_interleave(L, 0) * ds
+    assert rel_l2(da.float(), da_ref) < 5e-3
+    assert rel_l2(dmod[:, H:2 * H], (ds * a.float()).view(B, L, H).sum(1)) < 1e-4
+    assert float(dmod[:, :H].abs().sum()) == 0.0 and float(dmod[:, 2 * H:].abs().sum()) == 0.0
+    assert rel_l2(dbias, da_ref.sum(0)) < 1e-4
+    # silu(x + row)
+    row = torch.randn(B, H, device=dev, generator=_g(5)).to(bf16)
+    dout = torch.randn(M, H, device=dev, generator=_g(6)).to(bf16)
+    x = s.clone().requires_grad_(True)
+    r = row.float().clone().requires_grad_(True)
+    F.silu(x + r.repeat_interleave(L, 0)).backward(dout.float())
+    drow = torch.zeros(B, H, device=dev)
+    dx = ops.silu_add_rows_bwd(dout, s, row, drow, L)
+    assert rel_l2(dx, x.grad) < 1e-4 and rel_l2(drow, r.grad) < 1e-4
+
+
+def test_swiglu_forward_backward(dev):
+    from deco_b200 import ops
+    M, Fp = 130, 96
+    y13 = torch.randn(M, 2 * Fp, device=dev, generator=_g(1)).to(bf16)
+    du = torch.randn(M, Fp, device=dev, generator=_g(2)).to(bf16)
+    yy = y13.float().view(M, Fp // 16, 2, 16).clone().requires_grad_(True)
+    u_ref = (F.silu(yy[:, :, 0]) * yy[:, :, 1]).reshape(M, Fp)
+    u_ref.backward(du.float())
+    u = ops.swiglu_fwd(y13)
+    assert rel_l2(u.float(), u_ref) < 5e-3
+    dy = ops.swiglu_bwd(y13, du)
+    assert rel_l2(dy.float(), yy.grad.reshape(M, 2 * Fp)) < 5e-3
+
+
+@pytest.mark.parametrize("B,L,H", [(2, 16, 576), (2, 64, 1152), (1, 4, 1024)])
+def test_rmsnorm_modulate_backward(dev, B, L, H):
+    from deco_b200 import ops
+    M = B * L
+    x = torch.randn(M, H, device=dev, generator=_g(1)) * 1.7
+    w = (1 + 0.2 * torch.randn(H, device=dev, generator=_g(2)))
+    mod = (0.3 * torch.randn(B, 2 * H, device=dev, generator=_g(3))).to(bf16)
+    shift, scale = mod[:, :H], mod[:, H:]
+    dh = torch.randn(M, H, device=dev, generator=_g(4)).to(bf16)
+    xa, wa = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    sh, sc = shift.float().clone().requires_grad_(True), scale.float().clone().requires_grad_(True)
+    h = O.modulate(O.rmsnorm(xa.view(B, L, H), wa), sh.view(B, 1, H), sc.view(B, 1, H))
+    h.backward(dh.float().view(B, L, H))
+    ds0 = torch.randn(M, H, device=dev, generator=_g(5))
+    ds = ds0.clone()
+    dmod = torch.zeros(B, 2 * H, device=dev)
+    dw = torch.zeros(H, device=dev)
+    ops.rmsnorm_modulate_bwd_(ds, dh, x, w, scale, dw, dmod[:, :H], dmod[:, H:], L)
+    assert rel_l2(ds - ds0, xa.grad) < 1e-4
+    assert rel_l2(dw, wa.grad) < 1e-4
+    assert rel_l2(dmod[:, :H], sh.grad) < 1e-4 and rel_l2(dmod[:, H:], sc.grad) < 1e-4
+
+
+@pytest.mark.parametrize("heads,d,hw", [(8, 72, 4), (4, 64, 8)])
+def test_headnorm_rope_backward(dev, heads, d, hw):
+    from deco_b200 import ops
+    from deco_b200.denoiser import rope_cos_sin
+    B, L, H = 2, hw * hw, heads * d
+    M = B * L
+    raw = torch.randn(M, 3 * H, device=dev, generator=_g(1)).to(bf16)
+    qw = 1 + 0.2 * torch.randn(d, device=dev, generator=_g(2))
+    kw = 1 + 0.2 * torch.randn(d, device=dev, generator=_g(3))
+    g = torch.randn(M, 3 * H, device=dev, generator=_g(4)).to(bf16)
+    pos = rope_cos_sin(d, hw, hw).to(dev)
+    ang = O.rope_table_2d(d, hw, hw).to(dev)
+    ra = raw.float().clone().requires_grad_(True)
+    qa, ka = qw.clone().requires_grad_(True), kw.clone().requires_grad_(True)
+    q, k, v = ra.view(B, L, 3, heads, d).unbind(2)
+    q = O.apply_rope(O.rmsnorm(q, qa), ang)
+    k = O.apply_rope(O.rmsnorm(k, ka), ang)
+    out = torch.stack([q, k, v], 2).reshape(M, 3 * H)
+    out.backward(g.float())
+    # forward consistency of the convention
+    fw = raw.clone()
+    ops.qknorm_rope_(fw, qw, kw, pos, heads, d, L)
+    assert rel_l2(fw.float(), out) < 1e-2
+    gg = g.clone()
+    dq, dk = torch.zeros(d, device=dev), torch.zeros(d, device=dev)
+    ops.headnorm_rope_bwd_(gg, raw, 0, qw, pos, dq, heads, d, L)
+    ops.headnorm_rope_bwd_(gg, raw, H, kw, pos, dk, heads, d, L)
+    assert rel_l2(gg.float(), ra.grad) < 1e-2
+    assert rel_l2(dq, qa.grad) < 2e-3 and rel_l2(dk, ka.grad) < 2e-3
+
+
+def test_cond_combine_and_silu_backward(dev):
+    from deco_b200 import ops
+    B, H, ncls = 5, 576, 11
+    temb = torch.randn(B, H, device=dev, generator=_g(1)).to(bf16)
+    table = torch.randn(ncls, H, device=dev, generator=_g(2))
+    y = torch.tensor([1, 3, 3, 10, 0], device=dev)
+    dc = torch.randn(B, H, device=dev, generator=_g(3))
+    ta, tb = temb.float().clone().requires_grad_(True), table.clone().requires_grad_(True)
+    F.silu(ta + F.embedding(y, tb)).backward(dc)
+    dtemb0 = torch.randn(B, H, device=dev, generator=_g(4))
+    dtemb, dtab = dtemb0.clone(), torch.zeros_like(table)
+    ops.cond_combine_bwd_(dc, temb, table, y, dtemb, dtab)
+    assert rel_l2(dtemb - dtemb0, ta.grad) < 1e-4 and rel_l2(dtab, tb.grad) < 1e-4
+    z = torch.randn(B, H, device=dev, generator=_g(5)).to(bf16)
+    dy = torch.randn(B, H, device=dev, generator=_g(6)).to(bf16)
+    za = z.float().clone().requires_grad_(True)
+    F.silu(za).backward(dy.float())
+    assert rel_l2(ops.silu_bwd(z, dy).float(), za.grad) < 5e-3
+
+
+@pytest.mark.parametrize("B,heads,d,L", [(2, 4, 72, 16), (2, 2, 64, 256), (1, 3, 72, 80), (1, 2, 72, 1024)])
+def test_attention_backward(dev, B, heads, d, L):
+    from deco_b200 import ops
+    H = heads * d
+    M = B * L
+    qkv = torch.randn(M, 3 * H, device=dev, generator=_g(L)).to(bf16)
+    do = torch.randn(M, H, device=dev, generator=_g(L + 1)).to(bf16)
+    qa = qkv.float().clone().requires_grad_(True)
+    q, k, v = (t.transpose(1, 2) for t in qa.view(B, L, 3, heads, d).unbind(2))     # [B, heads, L, d]
+    o_ref = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(M, H)
+    o_ref.backward(do.float())
+    o = ops.attention(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], B, heads, d)
+    assert rel_l2(o.float(), o_ref) < 1e-2
+    dqkv = torch.zeros_like(qkv)
+    ops.attention_bwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], o, do,
+                      dqkv[:, :H], dqkv[:, H:2 * H], dqkv[:, 2 * H:], B, heads, d)
+    g = qa.grad
+    for name, sl in (("dq", slice(0, H)), ("dk", slice(H, 2 * H)), ("dv", slice(2 * H, 3 * H))):
+        e = rel_l2(dqkv[:, sl].float(), g[:, sl])
+        assert e < 1.5e-2, (name, e)
+
+
+def _decoder_ref(P, cfg, x, y):
+    """oracle pixel path with the per-pixel condition y [BL, p*p, 32] given (O.denoiser_forward + O.pixel_decoder minus
+    cond_embed), so that autograd yields d y."""
+    B, _, Hh, Ww = x.shape
+    p, Hx = cfg.patch_size, cfg.hidden_size_x
+    xp = F.unfold(x, kernel_size=p, stride=p).transpose(1, 2)
+    L = xp.shape[1]
+    px = xp.reshape(B * L, cfg.in_channels, p * p).transpose(1, 2)
+    tab = O.nerf_pos_table(p, cfg.max_freqs).to(x.device)
+    h = F.linear(torch.cat([px, tab[None].expand(B * L, -1, -1)], -1), P["x_embedder.embedder.0.weight"],
+                 P["x_embedder.embedder.0.bias"])
+    h = F.linear(h, P["dec_net.input_proj.weight"], P["dec_net.input_proj.bias"])
+    for j in range(cfg.num_res_blocks):
+        b = f"dec_net.res_blocks.{j}."
+        mod = F.linear(F.silu(y), P[b + "adaLN_modulation.1.weight"], P[b + "adaLN_modulation.1.bias"])
+        sh, sc, g = mod.chunk(3, dim=-1)
+        t = O.modulate(F.layer_norm(h, (Hx,), P[b + "in_ln.weight"], P[b + "in_ln.bias"], 1e-6), sh, sc)
+        t = F.linear(F.silu(F.linear(t, P[b + "mlp.0.weight"], P[b + "mlp.0.bias"])), P[b + "mlp.2.weight"], P[b + "mlp.2.bias"])
+        h = h + g * t
+    h = F.layer_norm(h, (Hx,), None, None, 1e-6)
+    out = F.linear(h, P["dec_net.final_layer.linear.weight"], P["dec_net.final_layer.linear.bias"])
+    out = out.transpose(1, 2).reshape(B, L, -1)
+    return F.fold(out.transpose(1, 2).contiguous(), (Hh, Ww), kernel_size=p, stride=p)
+
+
+@pytest.mark.parametrize("B,res", [(2, 64), (3, 32)])
+def test_pixel_decoder_backward(dev, B, res):
+    from deco_b200 import ops
+    from deco_b200.autograd import prepare_train
+    cfg = O.DenoiserCfg(num_groups=2, hidden_size=144, num_blocks=4, num_cond_blocks=1, num_classes=10)
+    m, P = build_module(cfg, dev)
+    prep = m.prepare(dev)
+    T = prepare_train(m, prep, dev)
+    L = (res // 16) ** 2
+    x = torch.randn(B, 3, res, res, device=dev, generator=_g(1))
+    ycond = torch.randn(B * L, 256 * 32, device=dev, generator=_g(2)).to(bf16)
+    dout = torch.randn(B, 3, res, res, device=dev, generator=_g(3))
+    # reference: autograd over the oracle with the same bf16-rounded weights / inputs the kernels see
+    names = [k for k in P if k.startswith("dec_net.") and "cond_embed" not in k] + ["x_embedder.embedder.0.weight", "x_embedder.embedder.0.bias"]
+    Pr = {k: P[k].to(dev).clone().requires_grad_(True) for k in names}
+    ya = ycond.float().view(B * L, 256, 32).clone().requires_grad_(True)
+    ref = _decoder_ref(Pr, cfg, x.to(bf16).float(), ya)
+    ref.backward(dout)
+    out = ops.pixel_decoder(x, ycond, prep["blob"], prep["postab"], 16, 32, 3, out_dtype=torch.float32)
+    assert rel_l2(out, ref) < 1e-2
+    dy, gdec = ops.pixel_decoder_bwd(x, ycond, dout, T["dec_blob"], prep["postab"], 16, 32, 3)
+    e = rel_l2(dy.float().view(B * L, 256, 32), ya.grad)
+    assert e < 1.5e-2, e
+    # parameter gradients via the module-level mapping
+    from deco_b200 import autograd as A
+    S = dict(x32=x, ycond=ycond, B=B, L=L)
+
+    def chk(name, got, tol=1.5e-2):
+        err = rel_l2(got, Pr[name].grad)
+        assert err < tol, (name, err)
+
+    chk("dec_net.input_proj.weight", gdec[96:1120].view(32, 32))
+    chk("dec_net.input_proj.bias", gdec[1120:1152])
+    for j in range(3):
+        o0 = 1152 + j * 5344
+        pre = f"dec_net.res_blocks.{j}."
+        chk(pre + "adaLN_modulation.1.weight", gdec[o0:o0 + 3072].view(96, 32))
+        chk(pre + "adaLN_modulation.1.bias", gdec[o0 + 3072:o0 + 3168])
+        chk(pre + "in_ln.weight", gdec[o0 + 3168:o0 + 3200])
+        chk(pre + "in_ln.bias", gdec[o0 + 3200:o0 + 3232])
+        chk(pre + "mlp.0.weight", gdec[o0 + 3232:o0 + 4256].view(32, 32))
+        chk(pre + "mlp.0.bias", gdec[o0 + 4256:o0 + 4288])
+        chk(pre + "mlp.2.weight", gdec[o0 + 4288:o0 + 5312].view(32, 32))
+        chk(pre + "mlp.2.bias", gdec[o0 + 5312:o0 + 5344])
+    of = 1152 + 3 * 5344
+    chk("dec_net.final_layer.linear.weight", gdec[of:of + 128].view(4, 32)[:3])
+    chk("dec_net.final_layer.linear.bias", gdec[of + 128:of + 131])
+    chk("x_embedder.embedder.0.weight", torch.cat([gdec[0:96].view(32, 3),
+        ops.gemm(ops.transpose_cast(gdec[T["dec_blob"].numel():].view(256, 32)), T["tabT"], None, ops.EPI_BIAS_F32)], 1), 2e-2)
+    chk("x_embedder.embedder.0.bias", gdec[T["dec_blob"].numel():].view(256, 32).sum(0))
+    assert A is not None and S is not None
+
+
+def _grad_check(dev, cfg, B, res, tol):
+    from deco_b200 import LinearScheduler, REPATrainer
+    m, P = build_module(cfg, dev)
+    m.train()
+    x = torch.tanh(torch.randn(B, 3, res, res, device=dev, generator=_g(11)))
+    noise = torch.randn(B, 3, res, res, device=dev, generator=_g(12))
+    t = torch.rand(B, device=dev, generator=_g(13))
+    y = torch.randint(0, cfg.num_classes + 1, (B,), device=dev, generator=_g(14))
+    x_t, v_t = O.make_xt_vt(x, noise, t)
+    tr = REPATrainer(scheduler=LinearScheduler()).to(dev)
+    out = m(x_t, t, y)
+    assert out.requires_grad and out.dtype == torch.float32
+    d = tr.loss(out, v_t)
+    d["loss"].backward()
+    # fp32 oracle under autograd
+    Pr = {k: v.to(dev).clone().requires_grad_(True) for k, v in P.items()}
+    ref = O.denoiser_forward(Pr, cfg, x_t, t, y)
+    dr = O.dct_fm_loss(ref, v_t)
+    dr["loss"].backward()
+    assert rel_l2(out, ref) < 1e-2
+    assert abs(float(d["loss"]) - float(dr["loss"])) <= 2e-2 * float(dr["loss"])
+    worst = []
+    num = den = 0.0
+    for name, prm in m.named_parameters():
+        assert prm.grad is not None, name
+        g, gr = prm.grad.double(), Pr[name].grad.double()
+        num += float((g - gr).pow(2).sum())
+        den += float(gr.pow(2).sum())
+        worst.append((rel_l2(g, gr), name))
+    worst.sort(reverse=True)
+    print("global grad rel-L2 %.3e; worst tensors: %s" % (math.sqrt(num / den), worst[:6]))
+    assert math.sqrt(num / den) < tol, worst[:6]
+    bad = [(e, n) for e, n in worst if e > 3 * tol]
+    assert not bad, bad
+
+
+def test_training_step_gradients_toy(dev):
+    cfg = O.DenoiserCfg(num_groups=2, hidden_size=144, num_blocks=5, num_cond_blocks=2, num_classes=10)
+    _grad_check(dev, cfg, B=3, res=64, tol=2e-2)
+
+
+def test_training_step_gradients_d64_ragged_ffn(dev):
+    # head_dim 64, hidden 256 -> FFN width int(2*1024/3) = 682 (padded to 688), 128 px -> 64 tokens
+    cfg = O.DenoiserCfg(num_groups=4, hidden_size=256, num_blocks=6, num_cond_blocks=3, num_classes=10)
+    _grad_check(dev, cfg, B=2, res=128, tol=2e-2)
+
+
+def test_optimizer_step_invalidates_weight_cache(dev):
+    """prepare() keys on parameter versions: after an optimizer step the next forward must see the new weights."""
+    cfg = O.DenoiserCfg(num_groups=2, hidden_size=144, num_blocks=4, num_cond_blocks=1, num_classes=10)
+    m, _ = build_module(cfg, dev)
+    m.train()
+    opt = torch.optim.SGD(m.parameters(), lr=0.5)
+    x = torch.randn(2, 3, 64, 64, device=dev, generator=_g(1))
+    t = torch.tensor([0.3, 0.8], device=dev)
+    y = torch.tensor([1, 10], device=dev)
+    out0 = m(x, t, y)
+    out0.square().mean().backward()
+    opt.step()
+    with torch.no_grad():
+        out1 = m(x, t, y).float()
+    assert rel_l2(out1, out0) > 1e-3
