@@ -51,6 +51,12 @@ WORKLOADS = {
                    metric="DeCo-XXL/16 512px text-to-image sampling throughput (AdamLM order 2, 25 steps x CFG, fixed NFE)",
                    name="DeCo-XXL/16 512px t2i (configs_t2i/sft_res512.yaml), AdamLM order 2, 25 steps x CFG 4.0, "
                         "timeshift 3, synthetic text-encoder states [128 x 2048]"),
+    # BASELINE configs[3]: training step (forward + backward of denoiser and DCT/FM loss), 32 images PER GPU (weak scaling)
+    "train256": dict(kind="train", model=XL, res=256, batch=32, gflop=3 * 244.9,
+                     metric="DeCo-XL/16 256px training step throughput (denoiser + DCT/FM loss, forward + backward)",
+                     name="DeCo-XL/16 256px training step (configs_c2i/DeCo_XL.yaml trainer: REPATrainer with the 8x8 "
+                          "block-DCT loss, null_condition_p 0.2), 32 synthetic images per GPU, forward + backward, "
+                          "no optimizer step"),
 }
 # the reference arm / cpu_baseline always time the headline workload's CPU restatement
 NUM_SAMPLING_STEPS = WORKLOADS["xl256"]["steps"]
@@ -453,9 +459,137 @@ def run_deco(args):
     finish()
 
 
+def run_train(args):
+    """BASELINE configs[3]: one training step = REPATrainer(net, ...) forward (denoiser + DCT/FM loss) + loss.backward()
+    on 32 synthetic images per GPU (weak scaling).  For N > 1 the parameter gradients are averaged with one NCCL
+    all-reduce per step (what DDP does in the reference, src/lightning_model.py under strategy ddp)."""
+    import torch
+    import torch.distributed as dist
+    from deco_b200 import LinearScheduler, PixNerDiT, REPATrainer, _lib, ops
+    from deco_b200 import distributed as D
+    from deco_b200.utils import GemmProbe, randomize_
+
+    wl = WORKLOADS[args.workload]
+    res = wl["res"]
+    rank, world, local = D.init_from_env("nccl" if int(os.environ.get("WORLD_SIZE", "1")) > 1 else None)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: deco_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    _lib.load()
+    B = args.global_batch // world if args.global_batch else wl["batch"]
+    with torch.device("meta"):
+        net = PixNerDiT(**wl["model"])
+    net = randomize_(net.to_empty(device=dev), seed=0).train()
+    trainer = REPATrainer(scheduler=LinearScheduler(), null_condition_p=0.2, freq_loss_weight=1, timeshift=1.0).to(dev)
+    params = [p for p in net.parameters() if p.requires_grad]
+    gen = torch.Generator().manual_seed(1234 + rank)
+    nbuf = 4
+    x_host = [torch.tanh(torch.randn((B, 3, res, res), generator=gen)).pin_memory() for _ in range(nbuf)]
+    y_host = [torch.randint(0, 1000, (B,), generator=gen).pin_memory() for _ in range(nbuf)]
+    unc = torch.full((B,), 1000, dtype=torch.int64, device=dev)
+    torch.manual_seed(4321 + rank)
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def step(x, y):
+        for p in params:
+            p.grad = None
+        d = trainer(net, None, None, x, y, unc)
+        d["loss"].backward()
+        if world > 1:
+            flat = torch._utils._flatten_dense_tensors([p.grad for p in params])
+            dist.all_reduce(flat)
+            flat.div_(world)
+        return d["loss"].detach()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    xd = [t.to(dev) for t in x_host]
+    yd = [t.to(dev) for t in y_host]
+    for i in range(args.warmup):
+        step(xd[i % nbuf], yd[i % nbuf])
+    barrier()
+    probe = GemmProbe()
+    ops.gemm_probe = probe
+    launches0 = _lib.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        if args.profile:
+            torch.cuda.profiler.start()
+        e0.record()
+        for i in range(args.steps):
+            step(xd[i % nbuf], yd[i % nbuf])
+        e1.record()
+        barrier()
+        if args.profile:
+            torch.cuda.profiler.stop()
+    ops.gemm_probe = None
+    launches = _lib.launch_count - launches0
+    ms_total = e0.elapsed_time(e1)
+    if world > 1:
+        tt = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_total = float(tt)
+    ms_per_step = ms_total / args.steps
+    value = B * world / (ms_per_step * 1e-3)
+    gs = probe.summary()
+    peaks = measured_peaks()
+
+    e2e = None
+    if not args.no_e2e:
+        k = max(2, min(args.steps, 5))
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for i in range(k):
+            x = x_host[i % nbuf].to(dev, non_blocking=True)
+            y = y_host[i % nbuf].to(dev, non_blocking=True)
+            loss_host.copy_(step(x, y), non_blocking=True)
+        t1.record()
+        barrier()
+        ms = t0.elapsed_time(t1) / k
+        if world > 1:
+            tt = torch.tensor([ms], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt)
+        e2e = dict(value=B * world / (ms * 1e-3), unit=UNIT, h2d_bytes_per_step=B * 3 * res * res * 4 + B * 8,
+                   d2h_bytes_per_step=4, ms_per_step=ms, loss=float(loss_host),
+                   note="trainer(net, ...) + backward per step with pinned host images/labels copied in and the loss read back")
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    flops_step = wl["gflop"] * 1e9 * B
+    line = dict(metric=wl["metric"], value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
+                data="synthetic",
+                config=dict(workload=wl["name"], global_batch=B * world, per_gpu_batch=B,
+                            step="trainer forward (denoiser + DCT/FM loss) + backward" + (" + gradient all-reduce" if world > 1 else ""),
+                            l2="inputs larger than L2 (>4 GB of weights + >10 GB of saved activations per step)",
+                            parallelism=f"dp{world}"),
+                clocks=clk.report(), e2e=e2e, gpu_launches=launches,
+                roofline=dict(kernel="gemm_bf16_tcgen05_kernel (forward, dgrad and wgrad GEMMs of the DiT blocks)", bound="tensor",
+                              achieved=gs["tflops"], peak=peaks["tf_sustained"], unit="TFLOP/s",
+                              frac=(gs["tflops"] / peaks["tf_sustained"]) if peaks["tf_sustained"] else None,
+                              traffic=None, peak_source=peaks["source"] + ", sustained bf16",
+                              launches=gs["launches"], avg_launch_ms=gs["avg_ms"],
+                              avg_launch_algorithmic_gflop=gs["total_flops"] / max(1, gs["launches"]) / 1e9,
+                              gemm_share_of_step=gs["total_ms"] / ms_total if ms_total else None,
+                              per_gpu_step_tflops_algorithmic=flops_step / (ms_per_step * 1e-3) / 1e12,
+                              step_frac_of_peak=flops_step / (ms_per_step * 1e-3) / 1e12 / peaks["tf_sustained"]),
+                hbm_kernels=None, cpu_baseline=None)
+    print(json.dumps(line), flush=True)
+
+
 if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif WORKLOADS[a.workload]["kind"] == "train":
+        run_train(a)
     else:
         run_deco(a)

@@ -55,6 +55,8 @@ SIGNATURES = {
                                 _i, _i, _i, _i, _i, _f, _vp]),
     "deco_decoder_train_blob_floats": (_i, [_i]),
     "deco_pixel_decoder_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "deco_decoder_bwd_blob_bytes": (_i, [_i]),
+    "deco_pixel_decoder_bwd_tc": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
 }
 
 _lib = None

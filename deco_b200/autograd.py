@@ -13,6 +13,7 @@ SwiGLU pre-activation y13 and its output u.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List
 
 import torch
@@ -21,6 +22,7 @@ from . import _lib, ops
 
 bf16 = torch.bfloat16
 F32 = torch.float32
+DECODER_BWD = os.environ.get("DECO_B200_DECODER_BWD", "mma")   # "mma" (product path) | "scalar" (A/B check)
 
 
 def _rb(t: torch.Tensor) -> torch.Tensor:
@@ -50,6 +52,43 @@ def pack_decoder_train(module, device):
     return blob
 
 
+def _frag_t(w: torch.Tensor, perm_n: bool = False) -> torch.Tensor:
+    """Pack the B operand of dX = dY . W, i.e. W^T given as wt [n = 32 inputs, K = outputs] (bf16), into m16n8k16
+    B-fragment order [n_tile, k_step, lane, 4] (see denoiser.py::_frag).  perm_n: n-tile j, column c <-> input channel
+    8 (c / 2) + 2 j + (c % 2), which makes a lane's four accumulator pairs the 16-byte chunk of the condition
+    (csrc/decoder_bwd_mma.cu)."""
+    n_out, K = w.shape
+    j = torch.arange(n_out // 8).view(-1, 1, 1, 1)
+    s = torch.arange(K // 16).view(1, -1, 1, 1)
+    lane = torch.arange(32).view(1, 1, -1, 1)
+    e = torch.arange(4).view(1, 1, 1, -1)
+    g, t = lane // 4, lane % 4
+    half, lo = e // 2, e % 2
+    k = 16 * s + 8 * half + 2 * t + lo
+    row = (8 * (g // 2) + 2 * j + (g % 2)) if perm_n else (8 * j + g)
+    shape = (n_out // 8, K // 16, 32, 4)
+    return w[row.expand(shape), k.expand(shape)].contiguous()
+
+
+@torch.no_grad()
+def pack_decoder_bwd(module, device):
+    """Backward blob of csrc/decoder_bwd_mma.cu: W^T fragments [WinT | R x (WadaT n-permuted, W0T, W2T)] then fp32 Wf[3][32]."""
+    dn = module.dec_net
+
+    def rb16(t):
+        return t.detach().float().cpu().to(bf16)
+
+    frags = [_frag_t(rb16(dn.input_proj.weight).t().contiguous())]
+    for blk in dn.res_blocks:
+        frags += [_frag_t(rb16(blk.adaLN_modulation[1].weight).t().contiguous(), perm_n=True),
+                  _frag_t(rb16(blk.mlp[0].weight).t().contiguous()), _frag_t(rb16(blk.mlp[2].weight).t().contiguous())]
+    wf = rb16(dn.final_layer.linear.weight).float()
+    assert wf.shape == (3, 32)
+    blob = torch.cat([torch.cat([f.reshape(-1) for f in frags]).view(torch.uint8), wf.reshape(-1).view(torch.uint8)])
+    assert blob.numel() == _lib.load().deco_decoder_bwd_blob_bytes(len(dn.res_blocks)), blob.numel()
+    return blob.contiguous().to(device)
+
+
 @torch.no_grad()
 def prepare_train(module, P: dict, device) -> dict:
     """Transposed bf16 weights for the dgrad GEMMs + the fp32 decoder blob; cached next to `prepare()`'s dict."""
@@ -64,6 +103,7 @@ def prepare_train(module, P: dict, device) -> dict:
     T["blocks"] = [dict(wqkvT=tr(bp["wqkv"]), wprojT=tr(bp["wproj"]), w13T=tr(bp["w13"]), w2T=tr(bp["w2"]))
                    for bp in P["blocks"]]
     T["dec_blob"] = pack_decoder_train(module, device)
+    T["dec_bwd_blob"] = pack_decoder_bwd(module, device)
     from .denoiser import nerf_pos_table
     T["tabT"] = ops.transpose_cast(nerf_pos_table(module.patch_size, module.x_embedder.max_freqs).to(device))  # [64, 256]
     P["train"] = T
@@ -142,8 +182,12 @@ def train_backward(module, S: dict, dout: torch.Tensor) -> Dict[str, torch.Tenso
     z = lambda *shape: torch.zeros(shape, dtype=F32, device=dev)   # noqa: E731
 
     # ---- pixel decoder (+ NerfEmbedder)
-    dycond, gdec = ops.pixel_decoder_bwd(x32, S["ycond"], dout.to(F32).contiguous(), T["dec_blob"], P["postab"], p,
-                                         module.hidden_size_x, R)
+    if DECODER_BWD == "scalar":     # fp32 scalar kernel (csrc/decoder_bwd.cu): the check the MMA kernel is validated against
+        dycond, gdec = ops.pixel_decoder_bwd(x32, S["ycond"], dout.to(F32).contiguous(), T["dec_blob"], P["postab"], p,
+                                             module.hidden_size_x, R)
+    else:
+        dycond, gdec = ops.pixel_decoder_bwd_tc(x32, S["ycond"], dout.to(F32).contiguous(), P["blob"], T["dec_bwd_blob"],
+                                                P["postab"], p, module.hidden_size_x, R)
     nW = T["dec_blob"].numel()
     dpostab = gdec[nW:].view(p * p, 32)
     gx = z(32, C + module.x_embedder.max_freqs ** 2)

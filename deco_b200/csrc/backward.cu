@@ -410,9 +410,11 @@ static inline unsigned bgrid(long long work, int threads) {
     return (unsigned)b;
 }
 
-static inline int rows_block(int L) {   // largest power of two <= 32 dividing L
+// rows per block of the per-image reductions: a power of two <= 32 dividing L, halved until the grid has >= 4 CTAs per SM
+// (each block ends with one atomic per column, so fewer rows per block = more atomics but enough warps to hide latency)
+static inline int rows_block(int L, long long M) {
     int rb = 32;
-    while (rb > 1 && L % rb) rb >>= 1;
+    while (rb > 1 && (L % rb || M / rb < 4LL * kNumSMs)) rb >>= 1;
     return rb;
 }
 
@@ -468,7 +470,7 @@ extern "C" int deco_gate_bwd(const float* ds, const void* a_bf16, const void* ga
     DECO_CHECK_ARG(ds && a_bf16 && gate_bf16 && da_bf16 && dgate_accum, "gate_bwd: null pointer");
     DECO_CHECK_ARG(M > 0 && hidden > 0 && hidden % 2 == 0 && hidden <= 512 * kMaxPairIters && rows_per_image > 0 &&
                    M % rows_per_image == 0 && gate_stride % 2 == 0, "gate_bwd: bad shape M=%lld hidden=%d L=%d", M, hidden, rows_per_image);
-    const int rb = rows_block(rows_per_image);
+    const int rb = rows_block(rows_per_image, M);
     gate_bwd_kernel<<<(unsigned)(M / rb), 256, 0, (cudaStream_t)stream>>>(
         ds, (const __nv_bfloat16*)a_bf16, (const __nv_bfloat16*)gate_bf16, gate_stride, (__nv_bfloat16*)da_bf16,
         dgate_accum, dgate_stride, dbias_accum, rows_per_image, rb, hidden);
@@ -483,7 +485,7 @@ extern "C" int deco_silu_add_rows_bwd(const void* dout_bf16, const float* x, con
     DECO_CHECK_ARG(dout_bf16 && x && row_bf16 && dx && drow_accum, "silu_add_rows_bwd: null pointer");
     DECO_CHECK_ARG(M > 0 && hidden > 0 && hidden % 2 == 0 && hidden <= 512 * kMaxPairIters && rows_per_image > 0 &&
                    M % rows_per_image == 0, "silu_add_rows_bwd: bad shape");
-    const int rb = rows_block(rows_per_image);
+    const int rb = rows_block(rows_per_image, M);
     silu_add_rows_bwd_kernel<<<(unsigned)(M / rb), 256, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)dout_bf16, x, (const __nv_bfloat16*)row_bf16, dx, drow_accum, rows_per_image, rb, hidden);
     DECO_CHECK_LAUNCH("silu_add_rows_bwd_kernel");
@@ -521,7 +523,7 @@ extern "C" int deco_rmsnorm_modulate_bwd(const void* dh_bf16, const float* x, co
                    "rmsnorm_modulate_bwd: null pointer");
     DECO_CHECK_ARG(M > 0 && hidden > 0 && hidden % 4 == 0 && hidden <= 2048 && rows_per_image > 0 &&
                    M % rows_per_image == 0 && mod_row_stride % 4 == 0, "rmsnorm_modulate_bwd: bad shape");
-    const int rb = rows_block(rows_per_image);
+    const int rb = rows_block(rows_per_image, M);
     const int threads = ((hidden / 4) + 31) / 32 * 32;
     rmsnorm_modulate_bwd_kernel<<<(unsigned)(M / rb), threads, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)dh_bf16, x, weight, (const __nv_bfloat16*)scale_bf16, mod_row_stride, ds_accum,

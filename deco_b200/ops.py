@@ -497,3 +497,21 @@ def pixel_decoder_bwd(x: torch.Tensor, ycond: torch.Tensor, dout: torch.Tensor, 
     call("deco_pixel_decoder_bwd", ptr(x), ptr(ycond), ptr(dout), ptr(blob_f32), ptr(postab), ptr(dy), ptr(grads),
          B, H, W, patch, hidden_x, num_res_blocks, _st(x))
     return dy, grads
+
+
+def pixel_decoder_bwd_tc(x: torch.Tensor, ycond: torch.Tensor, dout: torch.Tensor, fwd_blob: torch.Tensor,
+                         bwd_blob: torch.Tensor, postab: torch.Tensor, patch: int, hidden_x: int, num_res_blocks: int):
+    """Tensor-core version of pixel_decoder_bwd (csrc/decoder_bwd_mma.cu); same outputs."""
+    _cuda(x, ycond, dout, fwd_blob, bwd_blob, postab)
+    assert x.dtype == torch.float32 and x.is_contiguous() and dout.dtype == torch.float32 and dout.is_contiguous()
+    assert ycond.dtype == bf16 and ycond.is_contiguous() and x.shape[1] == 3
+    lib = _lib.load()
+    assert fwd_blob.numel() * fwd_blob.element_size() == lib.deco_decoder_blob_bytes(num_res_blocks)
+    assert bwd_blob.numel() * bwd_blob.element_size() == lib.deco_decoder_bwd_blob_bytes(num_res_blocks)
+    B, _, H, W = x.shape
+    n = lib.deco_decoder_train_blob_floats(num_res_blocks)
+    dy = torch.empty_like(ycond)
+    grads = torch.zeros(n + patch * patch * hidden_x, dtype=torch.float32, device=x.device)
+    call("deco_pixel_decoder_bwd_tc", ptr(x), ptr(ycond), ptr(dout), ptr(fwd_blob), ptr(bwd_blob), ptr(postab), ptr(dy),
+         ptr(grads), B, H, W, patch, hidden_x, num_res_blocks, _st(x))
+    return dy, grads

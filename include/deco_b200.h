@@ -243,6 +243,14 @@ int deco_pixel_decoder_bwd(const float* x, const void* ycond_bf16, const float* 
                            const float* postab, void* dycond_bf16, float* grad_accum, int B, int H, int W,
                            int patch, int hidden_x, int num_res_blocks, void* stream);
 
+/* Same contract on warp-level tensor-core MMAs (csrc/decoder_bwd_mma.cu, the product path): fwd_blob = the forward's packed
+ * weights (deco_decoder_blob_bytes), bwd_blob = transposed weights in fragment order + fp32 final layer
+ * (deco_decoder_bwd_blob_bytes; packed by deco_b200/autograd.py::pack_decoder_bwd); grad_accum as above */
+int deco_decoder_bwd_blob_bytes(int num_res_blocks);
+int deco_pixel_decoder_bwd_tc(const float* x, const void* ycond_bf16, const float* dout, const void* fwd_blob,
+                              const void* bwd_blob, const float* postab, void* dycond_bf16, float* grad_accum,
+                              int B, int H, int W, int patch, int hidden_x, int num_res_blocks, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

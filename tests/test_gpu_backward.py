@@ -228,8 +228,9 @@ def _decoder_ref(P, cfg, x, y):
     return F.fold(out.transpose(1, 2).contiguous(), (Hh, Ww), kernel_size=p, stride=p)
 
 
+@pytest.mark.parametrize("variant", ["mma", "scalar"])
 @pytest.mark.parametrize("B,res", [(2, 64), (3, 32)])
-def test_pixel_decoder_backward(dev, B, res):
+def test_pixel_decoder_backward(dev, B, res, variant):
     from deco_b200 import ops
     from deco_b200.autograd import prepare_train
     cfg = O.DenoiserCfg(num_groups=2, hidden_size=144, num_blocks=4, num_cond_blocks=1, num_classes=10)
@@ -248,7 +249,10 @@ def test_pixel_decoder_backward(dev, B, res):
     ref.backward(dout)
     out = ops.pixel_decoder(x, ycond, prep["blob"], prep["postab"], 16, 32, 3, out_dtype=torch.float32)
     assert rel_l2(out, ref) < 1e-2
-    dy, gdec = ops.pixel_decoder_bwd(x, ycond, dout, T["dec_blob"], prep["postab"], 16, 32, 3)
+    if variant == "scalar":
+        dy, gdec = ops.pixel_decoder_bwd(x, ycond, dout, T["dec_blob"], prep["postab"], 16, 32, 3)
+    else:
+        dy, gdec = ops.pixel_decoder_bwd_tc(x, ycond, dout, prep["blob"], T["dec_bwd_blob"], prep["postab"], 16, 32, 3)
     e = rel_l2(dy.float().view(B * L, 256, 32), ya.grad)
     assert e < 1.5e-2, e
     # parameter gradients via the module-level mapping
@@ -343,3 +347,8 @@ def test_optimizer_step_invalidates_weight_cache(dev):
     with torch.no_grad():
         out1 = m(x, t, y).float()
     assert rel_l2(out1, out0) > 1e-3
+
+
+def test_training_step_gradients_xl16(dev):
+    """DeCo-XL/16 at 256 px (configs_c2i/DeCo_XL.yaml architecture, BASELINE configs[3] shape at batch 2)."""
+    _grad_check(dev, O.CFG_XL, B=2, res=256, tol=2e-2)
