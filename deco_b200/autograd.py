@@ -22,6 +22,7 @@ from . import _lib, ops
 
 bf16 = torch.bfloat16
 F32 = torch.float32
+WGRAD = os.environ.get("DECO_B200_WGRAD", "tn")                # "tn" (product path) | "transpose" (A/B check)
 DECODER_BWD = os.environ.get("DECO_B200_DECODER_BWD", "mma")   # "mma" (product path) | "scalar" (A/B check)
 
 
@@ -111,7 +112,12 @@ def prepare_train(module, P: dict, device) -> dict:
 
 
 def _wgrad(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
-    """dW [N, K] fp32 = dy^T [N, M] . x [M, K]; both operands transposed to K-major (K = M padded to 8)."""
+    """dW [N, K] fp32 = dy^T [N, M] . x [M, K], M = tokens.  WGRAD = "tn": the GEMM reads dy and x as they lie in memory
+    (MN-major operands); "transpose": both operands are first copied K-major (K = M padded to 8)."""
+    if WGRAD == "tn":
+        if dy.dtype != bf16:
+            dy = ops.cast_bf16(dy.contiguous())
+        return ops.gemm_tn(dy, x)
     return ops.gemm(ops.transpose_cast(dy), ops.transpose_cast(x), None, ops.EPI_BIAS_F32)
 
 

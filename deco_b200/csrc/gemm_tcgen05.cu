@@ -224,7 +224,11 @@ __device__ __forceinline__ void epilogue_chunk_direct(const GemmParams& P, const
 
 // ------------------------------------------------------------------ kernel
 // CG = 1: one CTA per 128 x BN tile.   CG = 2: a 2-CTA cluster per 256 x BN tile (rank 0 = leader issues the MMAs).
-template <int BN, int EPI, int CG, bool STAGED>
+// TN = true: both operands are given TRANSPOSED in global memory -- At [K, M] and Wt [K, N], row-major -- and are staged
+// MN-major: a {64 (MN) x 64 (K)} TMA box lands as 64 K-rows of 128 bytes (SW128 atoms of 8 rows), 64-wide MN blocks
+// 8 KB apart (LBO), 8-row K groups 1 KB apart (SBO); the instruction descriptor flags both operands MN-major.  This is
+// the wgrad contraction dW = dY^T . X read straight from the row-major activations (no transposed copies).
+template <int BN, int EPI, int CG, bool STAGED, bool TN = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const GemmParams P)
@@ -280,7 +284,21 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
                     const uint32_t sb = sa + Cfg::kStageBytesA;
-                    if (CG == 1) {
+                    if (TN) {
+                        // MN-major staging: 64-wide MN blocks, each a {64 x 64} box at (MN coordinate, K row)
+                        if (CG == 1 || is_leader) mbar_expect_tx(full_bar(stage), CG * Cfg::kStageBytes);
+                        const uint32_t fb = CG == 2 ? mapa_shared(full_bar(stage), 0) : full_bar(stage);
+#pragma unroll
+                        for (int j = 0; j < kBM / 64; ++j) {
+                            if (CG == 2) tma_load_2d_2sm(sa + j * 8192, &tmap_a, fb, arow + 64 * j, kb * kBK);
+                            else tma_load_2d(sa + j * 8192, &tmap_a, fb, arow + 64 * j, kb * kBK);
+                        }
+#pragma unroll
+                        for (int j = 0; j < (BN / CG) / 64; ++j) {
+                            if (CG == 2) tma_load_2d_2sm(sb + j * 8192, &tmap_b, fb, brow + 64 * j, kb * kBK);
+                            else tma_load_2d(sb + j * 8192, &tmap_b, fb, brow + 64 * j, kb * kBK);
+                        }
+                    } else if (CG == 1) {
                         mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
                         tma_load_2d(sa, &tmap_a, full_bar(stage), kb * kBK, arow);
                         tma_load_2d(sb, &tmap_b, full_bar(stage), kb * kBK, brow);
@@ -298,7 +316,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA only) =====================
         if (lane == 0 && is_leader) {
-            constexpr uint32_t idesc = make_idesc(kBM * CG, BN);
+            constexpr uint32_t idesc = TN ? make_idesc_major(kBM * CG, BN, 1, 1) : make_idesc(kBM * CG, BN);
             int stage = 0; uint32_t phase = 0;
             int as = 0; uint32_t aphase = 0;
             for (int tile = tile0; tile < num_tiles; tile += tile_stride) {
@@ -309,12 +327,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
                     const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
-                    const uint64_t da = make_sw128_desc(sa), db = make_sw128_desc(sa + Cfg::kStageBytesA);
+                    const uint64_t da = TN ? make_umma_desc(sa, 8192, 1024, 2) : make_sw128_desc(sa);
+                    const uint64_t db = TN ? make_umma_desc(sa + Cfg::kStageBytesA, 8192, 1024, 2) : make_sw128_desc(sa + Cfg::kStageBytesA);
+                    // K-major: advance 16 elements = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field;
+                    // MN-major: 16 K rows of 128 bytes = two 1 KB atoms: +128
+                    constexpr uint64_t kstep = TN ? 128 : 2;
 #pragma unroll
                     for (int k = 0; k < kBK / kUmmaK; ++k) {
-                        // advance 16 elements = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
-                        if (CG == 2) umma_bf16_2sm(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
-                        else umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+                        if (CG == 2) umma_bf16_2sm(tmem_d, da + kstep * k, db + kstep * k, idesc, (kb | k) ? 1u : 0u);
+                        else umma_bf16(tmem_d, da + kstep * k, db + kstep * k, idesc, (kb | k) ? 1u : 0u);
                     }
                     // frees the smem stage (in both CTAs) once these MMAs retire
                     if (CG == 2) umma_commit_2sm(empty_bar(stage)); else umma_commit(empty_bar(stage));
@@ -405,10 +426,10 @@ static int make_tmap(CUtensorMap* map, const void* ptr, long long rows, long lon
     return DECO_OK;
 }
 
-template <int BN, int EPI, int CG, bool STAGED>
+template <int BN, int EPI, int CG, bool STAGED, bool TN = false>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& P, int max_ctas, cudaStream_t st) {
     using Cfg = GemmCfg<BN, CG>;
-    auto kern = gemm_bf16_tcgen05_kernel<BN, EPI, CG, STAGED>;
+    auto kern = gemm_bf16_tcgen05_kernel<BN, EPI, CG, STAGED, TN>;
     static bool attr_done = false;   // per instantiation
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
@@ -521,4 +542,36 @@ extern "C" int deco_gemm_set_tuning(int cta_group, int staged_epilogue) {
     g_force_cta_group = cta_group;
     g_force_staged = staged_epilogue;
     return DECO_OK;
+}
+
+// out[M, N] fp32 = At^T . Wt with At [K, M] and Wt [K, N] row-major bf16 (the wgrad contraction dW = dY^T . X on the
+// activations as they lie in memory).  M, N, lda, ldw, ldo multiples of 8.
+extern "C" int deco_gemm_bf16_tn(const void* At, long long lda, const void* Wt, long long ldw, float* out, long long ldo,
+                                 int M, int N, int K, int tile_n, void* stream)
+{
+    using namespace deco;
+    DECO_CHECK_ARG(At && Wt && out, "gemm_tn: null pointer");
+    DECO_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm_tn: bad shape M=%d N=%d K=%d", M, N, K);
+    DECO_CHECK_ARG(M % 8 == 0 && N % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldo % 4 == 0,
+                   "gemm_tn: M, N and leading dimensions must be multiples of 8 (M=%d N=%d lda=%lld ldw=%lld ldo=%lld)",
+                   M, N, lda, ldw, ldo);
+    DECO_CHECK_ARG((((uintptr_t)At | (uintptr_t)Wt | (uintptr_t)out) & 15) == 0, "gemm_tn: pointers must be 16-byte aligned");
+    int bn = tile_n ? tile_n : (N > 128 ? 256 : 128);
+    DECO_CHECK_ARG(bn == 128 || bn == 256, "gemm_tn: tile_n must be 128 or 256");
+    const int cg = (g_force_cta_group > 0) ? g_force_cta_group : (M > kBM ? 2 : 1);
+    CUtensorMap ta, tb;
+    int rc = make_tmap(&ta, At, K, M, lda, kBK);      // {64 (MN) x 64 (K rows)} boxes
+    if (rc) return rc;
+    rc = make_tmap(&tb, Wt, K, N, ldw, kBK);
+    if (rc) return rc;
+    GemmParams P;
+    P.out = out; P.ldo = ldo; P.bias = nullptr; P.resid = nullptr; P.ldr = 0;
+    P.gate = nullptr; P.gate_stride = 0; P.rows_per_gate = 1;
+    P.M = M; P.N = N; P.K = K;
+    const int ctas = num_sms();
+    cudaStream_t st = (cudaStream_t)stream;
+    if (bn == 256) return cg == 2 ? launch_gemm<256, EPI_BIAS_F32, 2, true, true>(ta, tb, P, ctas, st)
+                                  : launch_gemm<256, EPI_BIAS_F32, 1, true, true>(ta, tb, P, ctas, st);
+    return cg == 2 ? launch_gemm<128, EPI_BIAS_F32, 2, true, true>(ta, tb, P, ctas, st)
+                   : launch_gemm<128, EPI_BIAS_F32, 1, true, true>(ta, tb, P, ctas, st);
 }

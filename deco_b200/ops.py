@@ -515,3 +515,20 @@ def pixel_decoder_bwd_tc(x: torch.Tensor, ycond: torch.Tensor, dout: torch.Tenso
     call("deco_pixel_decoder_bwd_tc", ptr(x), ptr(ycond), ptr(dout), ptr(fwd_blob), ptr(bwd_blob), ptr(postab), ptr(dy),
          ptr(grads), B, H, W, patch, hidden_x, num_res_blocks, _st(x))
     return dy, grads
+
+
+def gemm_tn(at: torch.Tensor, wt: torch.Tensor, tile_n: int = 0) -> torch.Tensor:
+    """out [M, N] fp32 = at^T @ wt for at [K, M], wt [K, N] bf16 row-major (wgrad: dW = dY^T . X, K = tokens); no
+    transposed copies -- the GEMM stages both operands MN-major."""
+    _cuda(at, wt)
+    assert at.dtype == bf16 and wt.dtype == bf16 and at.dim() == 2 and wt.dim() == 2
+    assert at.stride(1) == 1 and wt.stride(1) == 1 and at.shape[0] == wt.shape[0]
+    K, M = at.shape
+    N = wt.shape[1]
+    out = torch.empty((M, N), dtype=torch.float32, device=at.device)
+    probe = gemm_probe
+    ev = probe.before() if probe is not None else None
+    call("deco_gemm_bf16_tn", ptr(at), at.stride(0), ptr(wt), wt.stride(0), ptr(out), out.stride(0), M, N, K, tile_n, _st(at))
+    if probe is not None:
+        probe.after(ev, 2.0 * M * N * K)
+    return out

@@ -251,6 +251,12 @@ int deco_pixel_decoder_bwd_tc(const float* x, const void* ycond_bf16, const floa
                               const void* bwd_blob, const float* postab, void* dycond_bf16, float* grad_accum,
                               int B, int H, int W, int patch, int hidden_x, int num_res_blocks, void* stream);
 
+/* wgrad contraction read straight from row-major activations: out[M, N] fp32 = At^T . Wt with At [K, M], Wt [K, N] bf16
+ * (dW = dY^T . X with K = tokens).  Operands are staged MN-major (csrc/gemm_tcgen05.cu, TN mode); M, N, lda, ldw multiples
+ * of 8; tile_n in {0 (auto), 128, 256}. */
+int deco_gemm_bf16_tn(const void* At, long long lda, const void* Wt, long long ldw, float* out, long long ldo,
+                      int M, int N, int K, int tile_n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

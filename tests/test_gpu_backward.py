@@ -43,6 +43,22 @@ def test_transpose_cast_and_colsum(dev):
             assert rel_l2(out, x.float().sum(0)) < 1e-5
 
 
+@pytest.mark.parametrize("M,N,K", [(256, 128, 64), (520, 144, 264), (3456, 1152, 2048), (96, 1152, 8), (72, 72, 1000)])
+def test_gemm_tn_mn_major_operands(dev, M, N, K):
+    """out = At^T . Wt with both operands MN-major in shared memory (wgrad without transposed copies)."""
+    from deco_b200 import ops
+    at = torch.randn(K, M, device=dev, generator=_g(M)).to(bf16)
+    wt = torch.randn(K, N, device=dev, generator=_g(N + 1)).to(bf16)
+    ref = at.float().t() @ wt.float()
+    for tile_n in (0, 128, 256):
+        out = ops.gemm_tn(at, wt, tile_n)
+        assert rel_l2(out, ref) < 2e-3, (tile_n, rel_l2(out, ref))
+    # strided operands (column slices of a wider buffer)
+    big = torch.randn(K, M + N + 16, device=dev, generator=_g(7)).to(bf16)
+    a2, w2 = big[:, 8:8 + M], big[:, 8 + M:8 + M + N]
+    assert rel_l2(ops.gemm_tn(a2, w2), a2.float().t() @ w2.float()) < 2e-3
+
+
 def test_wgrad_dgrad_through_the_gemm(dev):
     from deco_b200 import ops
     from deco_b200.autograd import _wgrad
