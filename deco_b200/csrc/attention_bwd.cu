@@ -45,6 +45,19 @@ __device__ __forceinline__ void load_tile(__nv_bfloat16* s, const __nv_bfloat16*
     }
 }
 
+// same, asynchronously (cp.async 16 B with zero-fill); completion via cp_async_wait + __syncthreads
+template <int D>
+__device__ __forceinline__ void load_tile_async(__nv_bfloat16* s, const __nv_bfloat16* g, long long stride, int row0, int nrows)
+{
+    using C = BwdCfg<D>;
+    constexpr int CH = C::DP / 8;
+    for (int i = threadIdx.x; i < 64 * CH; i += blockDim.x) {
+        const int r = i / CH, c = i % CH;
+        const bool ok = row0 + r < nrows && c * 8 < D;
+        cp_async16(s + r * C::LD + c * 8, ok ? g + (long long)(row0 + r) * stride + c * 8 : g, ok);
+    }
+}
+
 // A fragments (16 rows x DP) of rows [r0, r0 + 16) of a smem tile
 template <int D>
 __device__ __forceinline__ void load_afrags(uint32_t (&a)[BwdCfg<D>::KS][4], const __nv_bfloat16* s, int r0, int lane)
@@ -128,11 +141,12 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnBwdParams P)
 {
     using C = BwdCfg<D>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int TILE = 64 * C::LD;
     __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_raw);
-    __nv_bfloat16* sdO = sQ + 64 * C::LD;
-    __nv_bfloat16* sK = sdO + 64 * C::LD;
-    __nv_bfloat16* sV = sK + 64 * C::LD;
-    float* sDelta = reinterpret_cast<float*>(sV + 64 * C::LD);
+    __nv_bfloat16* sdO = sQ + TILE;
+    __nv_bfloat16* sKb = sdO + TILE;            // [2] double-buffered key tiles
+    __nv_bfloat16* sVb = sKb + 2 * TILE;        // [2] double-buffered value tiles
+    float* sDelta = reinterpret_cast<float*>(sVb + 2 * TILE);
 
     const int qb = blockIdx.x, bh = blockIdx.y;
     const int b = bh / P.heads, h = bh % P.heads;
@@ -176,13 +190,27 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnBwdParams P)
     load_afrags<D>(dof, sdO, warp * 16, lane);
     const float del0 = sDelta[warp * 16 + g], del1 = sDelta[warp * 16 + g + 8];
     const int nkb = (P.Lk + 63) / 64;
+    // K (and, in pass 2, V) tiles stream through a 2-deep cp.async pipeline: step st = pass * nkb + kb uses buffer st & 1
+    const int total = 2 * nkb;
+    int step = 0;
+    auto issue = [&](int st) {
+        const int kb = st % nkb, bsel = st & 1;
+        load_tile_async<D>(sKb + bsel * TILE, kg, P.kv_stride, kb * 64, P.Lk);
+        if (st >= nkb) load_tile_async<D>(sVb + bsel * TILE, vg, P.kv_stride, kb * 64, P.Lk);
+        cp_async_commit();
+    };
+    auto acquire = [&]() {
+        if (step + 1 < total) { issue(step + 1); cp_async_wait<1>(); } else cp_async_wait<0>();
+        __syncthreads();
+        return step & 1;
+    };
+    auto release = [&]() { __syncthreads(); ++step; };
+    issue(0);
 
     // ---- pass 1: softmax statistics of rows g and g + 8
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
     for (int kb = 0; kb < nkb; ++kb) {
-        __syncthreads();
-        load_tile<D>(sK, kg, P.kv_stride, kb * 64, P.Lk);
-        __syncthreads();
+        const __nv_bfloat16* sK = sKb + acquire() * TILE;
         float s[8][4];
         mma_a_tT<D>(s, qf, sK, lane);
         float mx0 = -INFINITY, mx1 = -INFINITY;
@@ -207,6 +235,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnBwdParams P)
         a0 = quad_sum(a0); a1 = quad_sum(a1);
         l0 = l0 * exp2f(m0 - n0) + a0; l1 = l1 * exp2f(m1 - n1) + a1;
         m0 = n0; m1 = n1;
+        release();
     }
     const float lse0 = m0 + log2f(l0), lse1 = m1 + log2f(l1);
     if (t == 0) {
@@ -220,10 +249,9 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnBwdParams P)
 #pragma unroll
     for (int j = 0; j < C::NT; ++j) { dq[j][0] = 0.f; dq[j][1] = 0.f; dq[j][2] = 0.f; dq[j][3] = 0.f; }
     for (int kb = 0; kb < nkb; ++kb) {
-        __syncthreads();
-        load_tile<D>(sK, kg, P.kv_stride, kb * 64, P.Lk);
-        load_tile<D>(sV, vg, P.kv_stride, kb * 64, P.Lk);
-        __syncthreads();
+        const int bsel = acquire();
+        const __nv_bfloat16* sK = sKb + bsel * TILE;
+        const __nv_bfloat16* sV = sVb + bsel * TILE;
         float s[8][4], dp[8][4];
         mma_a_tT<D>(s, qf, sK, lane);
         mma_a_tT<D>(dp, dof, sV, lane);
@@ -237,6 +265,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnBwdParams P)
             }
         }
         mma_p_t<D>(dq, s, sK, lane);
+        release();
     }
     __nv_bfloat16* dqg = P.dq + (long long)b * P.Lq * P.dq_stride + (long long)h * D;
     store_acc<D>(dq, dqg, P.dq_stride, q0 + warp * 16, P.Lq, lane);
@@ -247,12 +276,13 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnBwdParams P
 {
     using C = BwdCfg<D>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_raw);
-    __nv_bfloat16* sdO = sQ + 64 * C::LD;
-    __nv_bfloat16* sK = sdO + 64 * C::LD;
-    __nv_bfloat16* sV = sK + 64 * C::LD;
-    float* sLse = reinterpret_cast<float*>(sV + 64 * C::LD);
-    float* sDelta = sLse + 64;
+    constexpr int TILE = 64 * C::LD;
+    __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem_raw);
+    __nv_bfloat16* sV = sK + TILE;
+    __nv_bfloat16* sQb = sV + TILE;             // [2] double-buffered query tiles
+    __nv_bfloat16* sdOb = sQb + 2 * TILE;       // [2] double-buffered dO tiles
+    float* sLseb = reinterpret_cast<float*>(sdOb + 2 * TILE);   // [2][64]
+    float* sDeltab = sLseb + 128;                                // [2][64]
 
     const int kb = blockIdx.x, bh = blockIdx.y;
     const int b = bh / P.heads, h = bh % P.heads;
@@ -278,16 +308,25 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnBwdParams P
         for (int e = 0; e < 4; ++e) { dk[j][e] = 0.f; dv[j][e] = 0.f; }
 
     const int nqb = (P.Lq + 63) / 64;
-    for (int qb = 0; qb < nqb; ++qb) {
-        __syncthreads();
-        load_tile<D>(sQ, qg, P.q_stride, qb * 64, P.Lq);
-        load_tile<D>(sdO, dog, P.do_stride, qb * 64, P.Lq);
+    auto issue = [&](int qb) {
+        const int bsel = qb & 1;
+        load_tile_async<D>(sQb + bsel * TILE, qg, P.q_stride, qb * 64, P.Lq);
+        load_tile_async<D>(sdOb + bsel * TILE, dog, P.do_stride, qb * 64, P.Lq);
+        cp_async_commit();
         if (threadIdx.x < 64) {
             const int r = qb * 64 + threadIdx.x;
-            sLse[threadIdx.x] = r < P.Lq ? P.lse2[(long long)bh * P.Lq + r] : INFINITY;
-            sDelta[threadIdx.x] = r < P.Lq ? P.delta[(long long)bh * P.Lq + r] : 0.f;
+            sLseb[bsel * 64 + threadIdx.x] = r < P.Lq ? P.lse2[(long long)bh * P.Lq + r] : INFINITY;
+            sDeltab[bsel * 64 + threadIdx.x] = r < P.Lq ? P.delta[(long long)bh * P.Lq + r] : 0.f;
         }
+    };
+    issue(0);
+    for (int qb = 0; qb < nqb; ++qb) {
+        if (qb + 1 < nqb) { issue(qb + 1); cp_async_wait<1>(); } else cp_async_wait<0>();
         __syncthreads();
+        const __nv_bfloat16* sQ = sQb + (qb & 1) * TILE;
+        const __nv_bfloat16* sdO = sdOb + (qb & 1) * TILE;
+        const float* sLse = sLseb + (qb & 1) * 64;
+        const float* sDelta = sDeltab + (qb & 1) * 64;
         float s[8][4], dp[8][4];
         mma_a_tT<D>(s, kf, sQ, lane);      // S^T  : keys x queries
         mma_a_tT<D>(dp, vf, sdO, lane);    // dP^T : keys x queries
@@ -303,6 +342,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnBwdParams P
         }
         mma_p_t<D>(dv, s, sdO, lane);
         mma_p_t<D>(dk, dp, sQ, lane);
+        __syncthreads();     // everyone is done with buffer qb & 1 before the next-but-one tile lands in it
     }
     __nv_bfloat16* dkg = P.dk + (long long)b * P.Lk * P.dkv_stride + (long long)h * D;
     __nv_bfloat16* dvg = P.dv + (long long)b * P.Lk * P.dkv_stride + (long long)h * D;
@@ -314,7 +354,7 @@ template <int D>
 static int launch_attn_bwd(const AttnBwdParams& P, cudaStream_t st)
 {
     using C = BwdCfg<D>;
-    const int smem = 4 * 64 * C::LD * 2 + 2 * 64 * 4;
+    const int smem = 6 * 64 * C::LD * 2 + 4 * 64 * 4;
     cudaError_t e = cudaFuncSetAttribute(attn_bwd_dq_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_dkv_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) { deco_set_error("attention_bwd attr: %s", cudaGetErrorString(e)); return (int)e; }

@@ -229,75 +229,101 @@ __global__ void __launch_bounds__(256) swiglu_kernel(const __nv_bfloat16* __rest
 // ---------------------------------------------------------------- backward of h = rms(x) * w * (1 + scale[b]) + shift[b]
 //   dxh = dh * w * (1 + scale);  dx = r * dxh - x * r^3 * mean(dxh * x);  ds += dx   (the residual stream gradient)
 //   dshift[b] += sum_rows dh;  dscale[b] += sum_rows dh * xhat * w;  dw += sum_rows dh * xhat * (1 + scale)
-// Block = RB rows of one image; thread owns 4 columns (blockDim = ceil32(hidden / 4)); one block reduction per row.
-__global__ void __launch_bounds__(512) rmsnorm_modulate_bwd_kernel(
+// One WARP per row (lane owns float4 chunks lane + 32 k, row statistics by shuffles, no block barrier per row); a block =
+// 4 warps = RB rows of one image; the column sums live in registers until the block's rows are done, then go through
+// shared memory to one global atomic per column per block.
+template <int NV>
+__global__ void __launch_bounds__(128) rmsnorm_modulate_bwd_kernel(
     const __nv_bfloat16* __restrict__ dh, const float* __restrict__ x, const float* __restrict__ w,
     const __nv_bfloat16* __restrict__ scale, long long mod_stride, float* __restrict__ ds,
     float* __restrict__ dw, float* __restrict__ dshift, float* __restrict__ dscale, long long dmod_stride,
     int L, int RB, int Hd, float eps)
 {
-    __shared__ float2 red[2][16];
+    extern __shared__ float scol[];                 // [3][Hd]
     const long long r0 = (long long)blockIdx.x * RB;
     const long long b = r0 / L;
-    const int c = 4 * threadIdx.x;
-    const bool act = c < Hd;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    float wv[4] = {0.f, 0.f, 0.f, 0.f}, sc1[4] = {0.f, 0.f, 0.f, 0.f};
-    if (act) {
-        const float4 w4 = __ldg(reinterpret_cast<const float4*>(w + c));
-        wv[0] = w4.x; wv[1] = w4.y; wv[2] = w4.z; wv[3] = w4.w;
-        const uint2 s2 = *reinterpret_cast<const uint2*>(scale + b * mod_stride + c);
-        const float2 s0 = unpack_bf2(s2.x), s1 = unpack_bf2(s2.y);
-        sc1[0] = 1.0f + s0.x; sc1[1] = 1.0f + s0.y; sc1[2] = 1.0f + s1.x; sc1[3] = 1.0f + s1.y;
-    }
-    float a_sh[4] = {0.f, 0.f, 0.f, 0.f}, a_sc[4] = {0.f, 0.f, 0.f, 0.f}, a_w[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int i = 0; i < RB; ++i) {
-        const long long r = r0 + i;
-        float xv[4] = {0.f, 0.f, 0.f, 0.f}, dv[4] = {0.f, 0.f, 0.f, 0.f};
-        if (act) {
-            const float4 x4 = *reinterpret_cast<const float4*>(x + r * Hd + c);
-            xv[0] = x4.x; xv[1] = x4.y; xv[2] = x4.z; xv[3] = x4.w;
-            const uint2 d2 = *reinterpret_cast<const uint2*>(dh + r * Hd + c);
-            const float2 d0 = unpack_bf2(d2.x), d1 = unpack_bf2(d2.y);
-            dv[0] = d0.x; dv[1] = d0.y; dv[2] = d1.x; dv[3] = d1.y;
-        }
-        float s1 = 0.f, s2 = 0.f;
-        float dxh[4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 3 * Hd; i += blockDim.x) scol[i] = 0.f;
+    __syncthreads();
+    const int nch = Hd >> 2;
+    float4 a_sh[NV], a_sc[NV], a_w[NV];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            dxh[e] = dv[e] * wv[e] * sc1[e];
-            s1 = fmaf(xv[e], xv[e], s1);
-            s2 = fmaf(dxh[e], xv[e], s2);
+    for (int k = 0; k < NV; ++k) {
+        a_sh[k] = make_float4(0.f, 0.f, 0.f, 0.f); a_sc[k] = a_sh[k]; a_w[k] = a_sh[k];
+    }
+    const __nv_bfloat16* srow = scale + b * mod_stride;
+    for (int i = warp; i < RB; i += 4) {
+        const long long r = r0 + i;
+        float4 xv[NV], dv[NV];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const int c = lane + 32 * k;
+            if (c < nch) {
+                xv[k] = *reinterpret_cast<const float4*>(x + r * Hd + 4 * c);
+                const uint2 d2 = *reinterpret_cast<const uint2*>(dh + r * Hd + 4 * c);
+                const float2 d0 = unpack_bf2(d2.x), d1 = unpack_bf2(d2.y);
+                dv[k] = make_float4(d0.x, d0.y, d1.x, d1.y);
+            } else {
+                xv[k] = make_float4(0.f, 0.f, 0.f, 0.f); dv[k] = xv[k];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const int c = lane + 32 * k;
+            if (c < nch) {
+                const float4 w4 = __ldg(reinterpret_cast<const float4*>(w + 4 * c));
+                const uint2 q = __ldg(reinterpret_cast<const uint2*>(srow + 4 * c));
+                const float2 q0 = unpack_bf2(q.x), q1 = unpack_bf2(q.y);
+                // dv <- dxh = dh * w * (1 + scale); the plain dh is recovered below as dxh / (w (1 + scale)) is avoided by
+                // accumulating the dh-based sums first
+                a_sh[k].x += dv[k].x; a_sh[k].y += dv[k].y; a_sh[k].z += dv[k].z; a_sh[k].w += dv[k].w;
+                s1 = fmaf(xv[k].x, xv[k].x, fmaf(xv[k].y, xv[k].y, fmaf(xv[k].z, xv[k].z, fmaf(xv[k].w, xv[k].w, s1))));
+                const float4 m4 = make_float4(w4.x * (1.0f + q0.x), w4.y * (1.0f + q0.y), w4.z * (1.0f + q1.x), w4.w * (1.0f + q1.y));
+                s2 = fmaf(dv[k].x * m4.x, xv[k].x, fmaf(dv[k].y * m4.y, xv[k].y, fmaf(dv[k].z * m4.z, xv[k].z, fmaf(dv[k].w * m4.w, xv[k].w, s2))));
+            }
         }
         s1 = warp_sum(s1); s2 = warp_sum(s2);
-        if (lane == 0) red[i & 1][warp] = make_float2(s1, s2);
-        __syncthreads();
-        s1 = 0.f; s2 = 0.f;
-        for (int j = 0; j < nwarp; ++j) { s1 += red[i & 1][j].x; s2 += red[i & 1][j].y; }
         const float rs = rsqrtf(s1 / (float)Hd + eps);
         const float k2 = rs * rs * rs * s2 / (float)Hd;
-        if (act) {
-            float4* dp = reinterpret_cast<float4*>(ds + r * Hd + c);
-            float4 d4 = *dp;
-            d4.x += rs * dxh[0] - xv[0] * k2; d4.y += rs * dxh[1] - xv[1] * k2;
-            d4.z += rs * dxh[2] - xv[2] * k2; d4.w += rs * dxh[3] - xv[3] * k2;
-            *dp = d4;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const float xh = xv[e] * rs;
-                a_sh[e] += dv[e];
-                a_sc[e] = fmaf(dv[e] * xh, wv[e], a_sc[e]);
-                a_w[e] = fmaf(dv[e] * xh, sc1[e], a_w[e]);
+        for (int k = 0; k < NV; ++k) {
+            const int c = lane + 32 * k;
+            if (c < nch) {
+                const float4 w4 = __ldg(reinterpret_cast<const float4*>(w + 4 * c));
+                const uint2 q = __ldg(reinterpret_cast<const uint2*>(srow + 4 * c));
+                const float2 q0 = unpack_bf2(q.x), q1 = unpack_bf2(q.y);
+                const float4 sc1 = make_float4(1.0f + q0.x, 1.0f + q0.y, 1.0f + q1.x, 1.0f + q1.y);
+                float4* dp = reinterpret_cast<float4*>(ds + r * Hd + 4 * c);
+                float4 d4 = *dp;
+                d4.x += rs * dv[k].x * w4.x * sc1.x - xv[k].x * k2; d4.y += rs * dv[k].y * w4.y * sc1.y - xv[k].y * k2;
+                d4.z += rs * dv[k].z * w4.z * sc1.z - xv[k].z * k2; d4.w += rs * dv[k].w * w4.w * sc1.w - xv[k].w * k2;
+                *dp = d4;
+                const float4 xh = make_float4(xv[k].x * rs, xv[k].y * rs, xv[k].z * rs, xv[k].w * rs);
+                a_sc[k].x = fmaf(dv[k].x * xh.x, w4.x, a_sc[k].x); a_sc[k].y = fmaf(dv[k].y * xh.y, w4.y, a_sc[k].y);
+                a_sc[k].z = fmaf(dv[k].z * xh.z, w4.z, a_sc[k].z); a_sc[k].w = fmaf(dv[k].w * xh.w, w4.w, a_sc[k].w);
+                a_w[k].x = fmaf(dv[k].x * xh.x, sc1.x, a_w[k].x); a_w[k].y = fmaf(dv[k].y * xh.y, sc1.y, a_w[k].y);
+                a_w[k].z = fmaf(dv[k].z * xh.z, sc1.z, a_w[k].z); a_w[k].w = fmaf(dv[k].w * xh.w, sc1.w, a_w[k].w);
             }
         }
     }
-    if (act) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            atomicAdd(dshift + b * dmod_stride + c + e, a_sh[e]);
-            atomicAdd(dscale + b * dmod_stride + c + e, a_sc[e]);
-            atomicAdd(dw + c + e, a_w[e]);
+    for (int k = 0; k < NV; ++k) {
+        const int c = lane + 32 * k;
+        if (c < nch) {
+            float* p = scol + 4 * c;
+            atomicAdd(p, a_sh[k].x); atomicAdd(p + 1, a_sh[k].y); atomicAdd(p + 2, a_sh[k].z); atomicAdd(p + 3, a_sh[k].w);
+            p += Hd;
+            atomicAdd(p, a_sc[k].x); atomicAdd(p + 1, a_sc[k].y); atomicAdd(p + 2, a_sc[k].z); atomicAdd(p + 3, a_sc[k].w);
+            p += Hd;
+            atomicAdd(p, a_w[k].x); atomicAdd(p + 1, a_w[k].y); atomicAdd(p + 2, a_w[k].z); atomicAdd(p + 3, a_w[k].w);
         }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < Hd; i += blockDim.x) {
+        atomicAdd(dshift + b * dmod_stride + i, scol[i]);
+        atomicAdd(dscale + b * dmod_stride + i, scol[Hd + i]);
+        atomicAdd(dw + i, scol[2 * Hd + i]);
     }
 }
 
@@ -312,68 +338,61 @@ __global__ void __launch_bounds__(128) headnorm_rope_bwd_kernel(__nv_bfloat16* _
                                                                 const float2* __restrict__ rope, float* __restrict__ dw,
                                                                 long long M, int heads, int L, float eps)
 {
-    __shared__ float sdw[D];
-    for (int i = threadIdx.x; i < D; i += blockDim.x) sdw[i] = 0.f;
-    __syncthreads();
-    const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool act = item < M * heads;
-    const long long tok = act ? item / heads : 0;
-    const int head = act ? (int)(item % heads) : 0;
-    __nv_bfloat16* gp = g + tok * g_stride + col + (long long)head * D;
-    const __nv_bfloat16* rp = raw + tok * raw_stride + col + (long long)head * D;
-    const float2* cs = rope ? rope + (long long)(tok % L) * (D / 2) : nullptr;
-    float v[D], da[D];
-    float ss = 0.f;
-    if (act) {
+    __shared__ float sred[D][129];      // per-thread weight-gradient partials, reduced once per block
+    float dwacc[D];
+#pragma unroll
+    for (int e = 0; e < D; ++e) dwacc[e] = 0.f;
+    const long long total = M * heads;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x; item < total; item += stride) {
+        const long long tok = item / heads;
+        const int head = (int)(item % heads);
+        __nv_bfloat16* gp = g + tok * g_stride + col + (long long)head * D;
+        const __nv_bfloat16* rp = raw + tok * raw_stride + col + (long long)head * D;
+        const float2* cs = rope ? rope + (long long)(tok % L) * (D / 2) : nullptr;
+        uint32_t rw[D / 2], gw[D / 2];   // packed bf16 pairs: the raw vector and the incoming gradient
+        float ss = 0.f;
 #pragma unroll
         for (int c = 0; c < D / 8; ++c) {
             const uint4 q = *reinterpret_cast<const uint4*>(rp + c * 8);
             const uint4 q2 = *reinterpret_cast<const uint4*>(gp + c * 8);
-            const uint32_t qa[4] = {q.x, q.y, q.z, q.w}, qg[4] = {q2.x, q2.y, q2.z, q2.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const float2 a = unpack_bf2(qa[e]), gg = unpack_bf2(qg[e]);
-                const int j = c * 4 + e;
-                v[2 * j] = a.x; v[2 * j + 1] = a.y;
-                const float2 t = cs ? __ldg(cs + j) : make_float2(1.f, 0.f);
-                da[2 * j] = gg.x * t.x + gg.y * t.y;          // transpose of the rotation
-                da[2 * j + 1] = -gg.x * t.y + gg.y * t.x;
-            }
+            rw[4 * c] = q.x; rw[4 * c + 1] = q.y; rw[4 * c + 2] = q.z; rw[4 * c + 3] = q.w;
+            gw[4 * c] = q2.x; gw[4 * c + 1] = q2.y; gw[4 * c + 2] = q2.z; gw[4 * c + 3] = q2.w;
         }
 #pragma unroll
-        for (int e = 0; e < D; ++e) ss = fmaf(v[e], v[e], ss);
-    } else {
+        for (int j = 0; j < D / 2; ++j) { const float2 a = unpack_bf2(rw[j]); ss = fmaf(a.x, a.x, fmaf(a.y, a.y, ss)); }
+        const float rs = rsqrtf(ss / (float)D + eps);
+        float dot = 0.f;
 #pragma unroll
-        for (int e = 0; e < D; ++e) { v[e] = 0.f; da[e] = 0.f; }
-    }
-    const float rs = rsqrtf(ss / (float)D + eps);
-    float dot = 0.f;
-    const int lane = threadIdx.x & 31;
-#pragma unroll
-    for (int e = 0; e < D; ++e) {
-        const float n = v[e] * rs;
-        const float wgt = __ldg(wv + e);
-        float dwe = warp_sum(da[e] * n);
-        if (lane == 0) atomicAdd(&sdw[e], dwe);
-        da[e] *= wgt;                   // d n
-        dot = fmaf(da[e], n, dot);
-        v[e] = n;
-    }
-    dot /= (float)D;
-    if (act) {
-#pragma unroll
-        for (int c = 0; c < D / 8; ++c) {
-            uint32_t o[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int j = c * 4 + e;
-                o[e] = pack_bf2(rs * (da[2 * j] - v[2 * j] * dot), rs * (da[2 * j + 1] - v[2 * j + 1] * dot));
-            }
-            *reinterpret_cast<uint4*>(gp + c * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+        for (int j = 0; j < D / 2; ++j) {
+            const float2 a = unpack_bf2(rw[j]), gg = unpack_bf2(gw[j]);
+            const float2 t = cs ? __ldg(cs + j) : make_float2(1.f, 0.f);
+            const float da0 = gg.x * t.x + gg.y * t.y, da1 = -gg.x * t.y + gg.y * t.x;     // transpose of the rotation
+            const float n0 = a.x * rs, n1 = a.y * rs;
+            dwacc[2 * j] = fmaf(da0, n0, dwacc[2 * j]);
+            dwacc[2 * j + 1] = fmaf(da1, n1, dwacc[2 * j + 1]);
+            dot = fmaf(da0 * __ldg(wv + 2 * j), n0, fmaf(da1 * __ldg(wv + 2 * j + 1), n1, dot));
         }
+        dot /= (float)D;
+#pragma unroll
+        for (int j = 0; j < D / 2; ++j) {
+            const float2 a = unpack_bf2(rw[j]), gg = unpack_bf2(gw[j]);
+            const float2 t = cs ? __ldg(cs + j) : make_float2(1.f, 0.f);
+            const float dn0 = (gg.x * t.x + gg.y * t.y) * __ldg(wv + 2 * j), dn1 = (-gg.x * t.y + gg.y * t.x) * __ldg(wv + 2 * j + 1);
+            gw[j] = pack_bf2(rs * (dn0 - a.x * rs * dot), rs * (dn1 - a.y * rs * dot));
+        }
+#pragma unroll
+        for (int c = 0; c < D / 8; ++c)
+            *reinterpret_cast<uint4*>(gp + c * 8) = make_uint4(gw[4 * c], gw[4 * c + 1], gw[4 * c + 2], gw[4 * c + 3]);
     }
+#pragma unroll
+    for (int e = 0; e < D; ++e) sred[e][threadIdx.x] = dwacc[e];
     __syncthreads();
-    for (int i = threadIdx.x; i < D; i += blockDim.x) atomicAdd(dw + i, sdw[i]);
+    if (threadIdx.x < D) {
+        float a = 0.f;
+        for (int i = 0; i < 128; ++i) a += sred[threadIdx.x][i];
+        atomicAdd(dw + threadIdx.x, a);
+    }
 }
 
 // ---------------------------------------------------------------- backward of c = silu(temb + table[label])  (:493-494)
@@ -412,9 +431,9 @@ static inline unsigned bgrid(long long work, int threads) {
 
 // rows per block of the per-image reductions: a power of two <= 32 dividing L, halved until the grid has >= 4 CTAs per SM
 // (each block ends with one atomic per column, so fewer rows per block = more atomics but enough warps to hide latency)
-static inline int rows_block(int L, long long M) {
+static inline int rows_block(int L, long long M, int ctas_per_sm = 4) {
     int rb = 32;
-    while (rb > 1 && (L % rb || M / rb < 4LL * kNumSMs)) rb >>= 1;
+    while (rb > 1 && (L % rb || M / rb < (long long)ctas_per_sm * kNumSMs)) rb >>= 1;
     return rb;
 }
 
@@ -523,11 +542,21 @@ extern "C" int deco_rmsnorm_modulate_bwd(const void* dh_bf16, const float* x, co
                    "rmsnorm_modulate_bwd: null pointer");
     DECO_CHECK_ARG(M > 0 && hidden > 0 && hidden % 4 == 0 && hidden <= 2048 && rows_per_image > 0 &&
                    M % rows_per_image == 0 && mod_row_stride % 4 == 0, "rmsnorm_modulate_bwd: bad shape");
-    const int rb = rows_block(rows_per_image, M);
-    const int threads = ((hidden / 4) + 31) / 32 * 32;
-    rmsnorm_modulate_bwd_kernel<<<(unsigned)(M / rb), threads, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)dh_bf16, x, weight, (const __nv_bfloat16*)scale_bf16, mod_row_stride, ds_accum,
-        dweight_accum, dshift_accum, dscale_accum, dmod_row_stride, rows_per_image, rb, hidden, eps);
+    const int rb = rows_block(rows_per_image, M, 1);     // register-resident column sums: long row runs, one wave of CTAs
+    const unsigned grid = (unsigned)(M / rb);
+    const int smem = 3 * hidden * 4;
+    const __nv_bfloat16* dhp = (const __nv_bfloat16*)dh_bf16;
+    const __nv_bfloat16* scp = (const __nv_bfloat16*)scale_bf16;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (hidden <= 512)
+        rmsnorm_modulate_bwd_kernel<4><<<grid, 128, smem, st>>>(dhp, x, weight, scp, mod_row_stride, ds_accum, dweight_accum,
+                                                                 dshift_accum, dscale_accum, dmod_row_stride, rows_per_image, rb, hidden, eps);
+    else if (hidden <= 1152)
+        rmsnorm_modulate_bwd_kernel<9><<<grid, 128, smem, st>>>(dhp, x, weight, scp, mod_row_stride, ds_accum, dweight_accum,
+                                                                 dshift_accum, dscale_accum, dmod_row_stride, rows_per_image, rb, hidden, eps);
+    else
+        rmsnorm_modulate_bwd_kernel<16><<<grid, 128, smem, st>>>(dhp, x, weight, scp, mod_row_stride, ds_accum, dweight_accum,
+                                                                  dshift_accum, dscale_accum, dmod_row_stride, rows_per_image, rb, hidden, eps);
     DECO_CHECK_LAUNCH("rmsnorm_modulate_bwd_kernel");
     return DECO_OK;
 }
@@ -540,7 +569,9 @@ extern "C" int deco_headnorm_rope_bwd(void* g_bf16, long long g_stride, const vo
     DECO_CHECK_ARG(g_bf16 && raw_bf16 && weight && dweight_accum && M > 0 && heads > 0 && L > 0, "headnorm_rope_bwd: bad arguments");
     DECO_CHECK_ARG(g_stride % 8 == 0 && raw_stride % 8 == 0 && col % 8 == 0, "headnorm_rope_bwd: strides / col must be multiples of 8");
     const long long items = M * heads;
-    const unsigned grid = (unsigned)((items + 127) / 128);
+    long long nblk = (items + 127) / 128;
+    if (nblk > 3LL * kNumSMs) nblk = 3LL * kNumSMs;      // 3 resident blocks per SM; threads loop over their items
+    const unsigned grid = (unsigned)nblk;
     const float2* rp = (const float2*)rope_cos_sin;
     if (head_dim == 72)
         headnorm_rope_bwd_kernel<72><<<grid, 128, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)g_bf16, g_stride, (const __nv_bfloat16*)raw_bf16, raw_stride, col, weight, rp, dweight_accum, M, heads, L, eps);
