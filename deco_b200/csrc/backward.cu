@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(256) gate_bwd_kernel(const float* __restrict__
         accg[k] = make_float2(0.f, 0.f);
         accb[k] = make_float2(0.f, 0.f);
     }
+#pragma unroll 4
     for (int i = 0; i < RB; ++i) {
         const long long r = r0 + i;
 #pragma unroll
@@ -162,6 +163,7 @@ __global__ void __launch_bounds__(256) silu_add_rows_bwd_kernel(const __nv_bfloa
         rv[k] = p < npair ? Pair<__nv_bfloat16>::ld(rowv + b * Hd + 2 * p) : make_float2(0.f, 0.f);
         acc[k] = make_float2(0.f, 0.f);
     }
+#pragma unroll 4
     for (int i = 0; i < RB; ++i) {
         const long long r = r0 + i;
 #pragma unroll

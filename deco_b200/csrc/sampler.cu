@@ -26,6 +26,8 @@ struct StepArgs {
     float* v_out;            // optional: store combined v (fp32)
     uint8_t* u8_out;         // optional: fp2uint8(x_out)
     float g, dt, c0, c[3];
+    const float* dev;        // optional: {g, dt, c0, c1, c2, c3} in DEVICE memory (CUDA-graph replays: the step's scalars
+                             // change between replays without changing the kernel arguments)
     long long n;             // elements per CFG half (B*C*H*W)
 };
 
@@ -51,10 +53,14 @@ __device__ __forceinline__ uint8_t to_u8(float x) {
 
 template <typename TNet>
 __global__ void __launch_bounds__(256) cfg_step_kernel(StepArgs a) {
+    if (a.dev) {
+        a.g = __ldg(a.dev); a.dt = __ldg(a.dev + 1); a.c0 = __ldg(a.dev + 2);
+        a.c[0] = __ldg(a.dev + 3); a.c[1] = __ldg(a.dev + 4); a.c[2] = __ldg(a.dev + 5);
+    }
     const long long n4 = a.n >> 2;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-        const float4 x = __ldg(reinterpret_cast<const float4*>(a.x) + i);
+        const float4 x = reinterpret_cast<const float4*>(a.x)[i];     // plain loads: x_out / pred_out may alias x / p1
         const float4 u = Vec4<TNet>::load(a.net_out, i);
         const float4 c = Vec4<TNet>::load(a.net_out, i + n4);
         float4 pr;
@@ -66,7 +72,7 @@ __global__ void __launch_bounds__(256) cfg_step_kernel(StepArgs a) {
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
             if (a.p[j]) {
-                const float4 q = __ldg(reinterpret_cast<const float4*>(a.p[j]) + i);
+                const float4 q = reinterpret_cast<const float4*>(a.p[j])[i];
                 v.x = fmaf(a.c[j], q.x, v.x); v.y = fmaf(a.c[j], q.y, v.y);
                 v.z = fmaf(a.c[j], q.z, v.z); v.w = fmaf(a.c[j], q.w, v.w);
             }
@@ -80,6 +86,19 @@ __global__ void __launch_bounds__(256) cfg_step_kernel(StepArgs a) {
             reinterpret_cast<uchar4*>(a.u8_out)[i] = q;
         }
     }
+}
+
+// One replay of a graphed sampling step starts here: row (*counter % rows) of the host-precomputed schedule table
+// {g, dt, c0, c1, c2, c3, t, -} becomes the step's scalars, t is broadcast into the denoiser's timestep vector, and the
+// counter moves on -- so consecutive replays walk the schedule with no host work in between.
+__global__ void sampler_advance_kernel(const float* __restrict__ table, int rows, int* counter, float* cur, float* t_out, int nt) {
+    const int idx = *counter % rows;
+    const float* row = table + (size_t)idx * 8;
+    if (threadIdx.x < 8) cur[threadIdx.x] = row[threadIdx.x];
+    const float t = row[6];
+    for (int i = threadIdx.x; i < nt; i += blockDim.x) t_out[i] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) *counter = idx + 1;
 }
 
 __global__ void __launch_bounds__(256) fp2uint8_kernel(const float* __restrict__ x, uint8_t* __restrict__ o, long long n4) {
@@ -104,7 +123,7 @@ extern "C" int deco_cfg_step(const float* x, const void* net_out, int net_is_bf1
     StepArgs a;
     a.x = x; a.net_out = net_out; a.p[0] = p1; a.p[1] = p2; a.p[2] = p3;
     a.x_out = x_out; a.pred_out = pred_out; a.v_out = v_out; a.u8_out = u8_out;
-    a.g = g; a.dt = dt; a.c0 = c0; a.c[0] = c1; a.c[1] = c2; a.c[2] = c3; a.n = n;
+    a.g = g; a.dt = dt; a.c0 = c0; a.c[0] = c1; a.c[1] = c2; a.c[2] = c3; a.n = n; a.dev = nullptr;
     const long long n4 = n / 4;
     long long blocks = (n4 + 255) / 256;
     const long long cap = (long long)kNumSMs * 16;   // grid-stride: 16 CTAs of 256 threads per SM
@@ -124,5 +143,39 @@ extern "C" int deco_fp2uint8(const float* x, uint8_t* out, long long n, void* st
     if (blocks > cap) blocks = cap;
     fp2uint8_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, out, n4);
     DECO_CHECK_LAUNCH("fp2uint8_kernel");
+    return DECO_OK;
+}
+
+// deco_cfg_step with the step scalars {g, dt, c0, c1, c2, c3} read from device memory (dev_params), for CUDA-graph replays.
+// x_out may alias x and pred_out may alias p1 (element-wise, read before write).
+extern "C" int deco_cfg_step_dev(const float* x, const void* net_out, int net_is_bf16,
+                                 const float* p1, const float* p2, const float* p3, const float* dev_params,
+                                 float* x_out, float* pred_out, float* v_out, uint8_t* u8_out, long long n, void* stream)
+{
+    using namespace deco;
+    DECO_CHECK_ARG(x && net_out && dev_params, "cfg_step_dev: null input");
+    DECO_CHECK_ARG(n > 0 && (n % 4) == 0, "cfg_step_dev: element count %lld must be a positive multiple of 4", n);
+    StepArgs a;
+    a.x = x; a.net_out = net_out; a.p[0] = p1; a.p[1] = p2; a.p[2] = p3;
+    a.x_out = x_out; a.pred_out = pred_out; a.v_out = v_out; a.u8_out = u8_out;
+    a.g = 1.f; a.dt = 0.f; a.c0 = 1.f; a.c[0] = 0.f; a.c[1] = 0.f; a.c[2] = 0.f; a.n = n; a.dev = dev_params;
+    const long long n4 = n / 4;
+    long long blocks = (n4 + 255) / 256;
+    const long long cap = (long long)kNumSMs * 16;
+    if (blocks > cap) blocks = cap;
+    if (net_is_bf16) cfg_step_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+    else cfg_step_kernel<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+    DECO_CHECK_LAUNCH("cfg_step_kernel");
+    return DECO_OK;
+}
+
+// Head of a graphed sampling step: cur[0..8) = table[*counter % rows], t_out[0..nt) = that row's t, ++*counter.
+extern "C" int deco_sampler_advance(const float* table, int rows, int* counter, float* cur_params, float* t_out, int nt,
+                                    void* stream)
+{
+    using namespace deco;
+    DECO_CHECK_ARG(table && counter && cur_params && t_out && rows > 0 && nt > 0, "sampler_advance: bad arguments");
+    sampler_advance_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(table, rows, counter, cur_params, t_out, nt);
+    DECO_CHECK_LAUNCH("sampler_advance_kernel");
     return DECO_OK;
 }

@@ -279,6 +279,7 @@ def fused_blocks(blocks, mod: torch.Tensor, mod0: int, st: StreamState, a0: torc
 # ------------------------------------------------------------------------------------------------ the module
 class PixNerDiT(nn.Module):
     """Drop-in for src/models/transformer/dit_c2i_DeCo.py::PixNerDiT (constructor :417-433, forward :488-510)."""
+    cuda_graph_safe = True   # the inference forward makes no host-device synchronisation (samplers may capture it)
 
     def __init__(self, in_channels=4, num_groups=12, hidden_size=1152, hidden_size_x=64, nerf_mlpratio=4,
                  num_blocks=18, num_cond_blocks=4, patch_size=2, num_classes=1000, learn_sigma=True,

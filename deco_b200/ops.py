@@ -310,6 +310,27 @@ def cfg_step(x: torch.Tensor, net_out: torch.Tensor, g: float, dt: float, c0: fl
     return x_out, pred, v, u8
 
 
+def sampler_advance(table: torch.Tensor, counter: torch.Tensor, cur: torch.Tensor, t_out: torch.Tensor) -> None:
+    """Head of a graphed sampling step (csrc/sampler.cu): cur = table[counter % rows], t_out[:] = that row's t, ++counter."""
+    _cuda(table, counter, cur, t_out)
+    assert table.dtype == torch.float32 and table.is_contiguous() and table.dim() == 2 and table.shape[1] == 8
+    assert counter.dtype == torch.int32 and counter.numel() == 1 and cur.dtype == torch.float32 and cur.numel() == 8
+    assert t_out.dtype == torch.float32 and t_out.is_contiguous()
+    call("deco_sampler_advance", ptr(table), table.shape[0], ptr(counter), ptr(cur), ptr(t_out), t_out.numel(), _st(table))
+
+
+def cfg_step_dev(x: torch.Tensor, net_out: torch.Tensor, cur: torch.Tensor, x_out: torch.Tensor,
+                 p1: Optional[torch.Tensor] = None, pred_out: Optional[torch.Tensor] = None,
+                 u8_out: Optional[torch.Tensor] = None) -> None:
+    """cfg_step with {g, dt, c0, c1, ...} read from the device vector `cur` (graph replays); x_out may be x, pred_out may
+    be p1."""
+    _cuda(x, net_out, cur, x_out, p1, pred_out, u8_out)
+    assert x.dtype == torch.float32 and x.is_contiguous() and net_out.is_contiguous() and x_out.is_contiguous()
+    assert net_out.shape[0] == 2 * x.shape[0] and net_out.dtype in (bf16, torch.float32)
+    call("deco_cfg_step_dev", ptr(x), ptr(net_out), int(net_out.dtype == bf16), ptr(p1), None, None, ptr(cur),
+         ptr(x_out), ptr(pred_out), None, ptr(u8_out), x.numel(), _st(x))
+
+
 def fp2uint8(x: torch.Tensor) -> torch.Tensor:
     _cuda(x)
     x = x.to(torch.float32).contiguous()

@@ -17,12 +17,13 @@ the SDE step functions need on-device RNG and are out of scope.
 from __future__ import annotations
 
 import logging
+import os
 from typing import Callable, List, Optional, Union
 
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import _lib, ops
 from .scheduling import BaseScheduler
 
 logger = logging.getLogger(__name__)
@@ -97,6 +98,64 @@ def _prep_inputs(noise, condition, uncondition):
     return x, cfg_condition
 
 
+GRAPH = os.environ.get("DECO_B200_GRAPH", "1") != "0"
+
+
+class GraphedEulerStepper:
+    """One CFG Euler step -- schedule advance, denoiser forward, fused update -- captured ONCE into a CUDA graph and replayed
+    per step.  The step scalars (t, g, dt) live in a device table indexed by a device counter (csrc/sampler.cu
+    sampler_advance_kernel), so a whole trajectory is `num_steps` replays with no host work in between: at small per-GPU
+    batches (8-GPU sharding: 64 CFG rows) the ~210 Python/ctypes launches of a step cost as much host time as the step
+    takes on the GPU.  Same kernels, same order, same numerics as the eager loop (EulerSampler._impl_sampling)."""
+
+    def __init__(self, sampler, net, batch, shape, cond_like, to_uint8):
+        dev = cond_like.device
+        self.sampler, self.net, self.B = sampler, net, batch
+        ts = sampler.timesteps
+        rows = []
+        for i in range(sampler.num_steps):
+            t_cur, t_next = ts[i], ts[i + 1]
+            in_window = bool(t_cur > sampler.guidance_interval_min) and bool(t_cur <= sampler.guidance_interval_max)
+            rows.append([float(sampler.guidance) if in_window else 1.0, float(t_next - t_cur), 1.0, 0.0, 0.0, 0.0,
+                         float(t_cur), 0.0])
+        self.table = torch.tensor(rows, dtype=torch.float32).to(dev)
+        self.counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.cur = torch.zeros(8, dtype=torch.float32, device=dev)
+        self.t = torch.zeros(2 * batch, dtype=torch.float32, device=dev)
+        self.x = torch.zeros((batch,) + tuple(shape), dtype=torch.float32, device=dev)
+        self.cond = torch.zeros((2 * batch,) + tuple(cond_like.shape[1:]), dtype=cond_like.dtype, device=dev)
+        self.u8 = torch.zeros(self.x.shape, dtype=torch.uint8, device=dev) if to_uint8 else None
+        cur_stream = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(cur_stream)
+        with torch.cuda.stream(side):       # eager warm-up: lazily-set function attributes, weight / table caches
+            self._body()
+        cur_stream.wait_stream(side)
+        torch.cuda.synchronize(dev)
+        n0 = _lib.launch_count
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._body()
+        self.launches_per_step = _lib.launch_count - n0
+        self.prep_ref = getattr(net, "_prep", None)     # the graph reads these weight buffers: keep them alive
+
+    def _body(self):
+        ops.sampler_advance(self.table, self.counter, self.cur, self.t)
+        out = self.net(torch.cat([self.x, self.x], dim=0), self.t, self.cond)
+        if out.dtype not in (torch.bfloat16, torch.float32):
+            out = out.float()
+        ops.cfg_step_dev(self.x, out.contiguous(), self.cur, self.x, u8_out=self.u8)
+
+    def reset(self, x, cfg_condition):
+        self.x.copy_(x)
+        self.cond.copy_(cfg_condition)
+        self.counter.zero_()
+
+    def step(self):
+        self.graph.replay()
+        _lib.launch_count += self.launches_per_step
+
+
 def _net_eval(net, x, t_scalar: float, cfg_condition, batch_size):
     cfg_x = torch.cat([x, x], dim=0)
     cfg_t = torch.full((2 * batch_size,), t_scalar, dtype=torch.float32, device=x.device)
@@ -127,10 +186,35 @@ class EulerSampler(BaseSampler):
             if getattr(fn, "__name__", "") != "ode_step_fn":
                 raise NotImplementedError("only ode_step_fn is supported (SDE steps are out of scope)")
 
+    def graphed_stepper(self, net, noise, cfg_condition, to_uint8=False):
+        """GraphedEulerStepper for (net, batch shape), built once and cached; None when the step cannot be graphed (a net
+        that is not a deco_b200 denoiser, DECO_B200_GRAPH=0, or a capture failure -- the eager loop is used then)."""
+        if not GRAPH or not getattr(net, "cuda_graph_safe", False) or getattr(net, "training", False):
+            return None
+        prep = net.prepare(noise.device) if hasattr(net, "prepare") else None
+        key = (id(net), id(prep), tuple(noise.shape), tuple(cfg_condition.shape), cfg_condition.dtype, bool(to_uint8),
+               noise.device.index, float(self.guidance))
+        cache = self.__dict__.setdefault("_steppers", {})
+        if key not in cache:
+            try:
+                cache[key] = GraphedEulerStepper(self, net, noise.shape[0], noise.shape[1:], cfg_condition[: noise.shape[0]],
+                                                 to_uint8)
+            except Exception as e:   # noqa: BLE001 -- capture is an optimisation; the eager loop runs the same kernels
+                logger.warning("CUDA-graph capture of the sampling step failed (%s); using the eager loop", e)
+                cache[key] = None
+        return cache[key]
+
     def _impl_sampling(self, net, noise, condition, uncondition, keep_x=False, keep_v=False, to_uint8=False):
         B = noise.shape[0]
         x, cfg_condition = _prep_inputs(noise, condition, uncondition)
         steps = self.timesteps  # host fp32
+        if not keep_x and not keep_v:
+            st = self.graphed_stepper(net, x, cfg_condition, to_uint8)
+            if st is not None:
+                st.reset(x, cfg_condition)
+                for _ in range(self.num_steps):
+                    st.step()
+                return st.x.clone(), None, None, (st.u8.clone() if to_uint8 else None)
         x_trajs, v_trajs, u8 = ([x] if keep_x else None), ([] if keep_v else None), None
         for i in range(self.num_steps):
             t_cur, t_next = steps[i], steps[i + 1]

@@ -161,6 +161,16 @@ int deco_cfg_step(const float* x, const void* net_out, int net_is_bf16,
                   float* x_out, float* pred_out, float* v_out, uint8_t* u8_out, long long n, void* stream);
 int deco_fp2uint8(const float* x, uint8_t* out, long long n, void* stream);
 
+/* The same update for CUDA-graph replays of the sampling loop (sampling.py:89-104 without per-step host work):
+ * deco_sampler_advance copies row (*counter % rows) of the host-precomputed schedule table {g, dt, c0, c1, c2, c3, t, -}
+ * (fp32 [rows, 8], device) into cur_params[8], broadcasts its t into t_out[nt] (the denoiser's timestep vector) and
+ * increments the counter; deco_cfg_step_dev is deco_cfg_step with {g, dt, c0..c3} read from dev_params (= cur_params).
+ * x_out may alias x, pred_out may alias p1. */
+int deco_sampler_advance(const float* table, int rows, int* counter, float* cur_params, float* t_out, int nt, void* stream);
+int deco_cfg_step_dev(const float* x, const void* net_out, int net_is_bf16,
+                      const float* p1, const float* p2, const float* p3, const float* dev_params,
+                      float* x_out, float* pred_out, float* v_out, uint8_t* u8_out, long long n, void* stream);
+
 /* Frequency-aware FM loss, forward and/or backward in one pass
  * (flow_matching/training_repa_DeCo.py:106-136 _rgb2ycbcr/_dct, :138-195 weights, :273-285 loss):
  *   losses[0] = mean((out - v_t)^2), losses[1] = mean(freq_w * dct(ycbcr(out - v_t))^2), losses[2] = [0] + flw * [1]
