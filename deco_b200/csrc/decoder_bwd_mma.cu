@@ -13,8 +13,9 @@
 //   wgrad  dW = dY^T . X    : A = movmatrix(dY tiles), B = movmatrix(X tiles), K = the warp's 16 pixels; the bias
 //                              gradient rides along as one more n-tile whose B fragment is a column of ones
 // The forward of a res-block is recomputed from its saved input (kept per warp in shared memory); weight gradients are
-// accumulated per CTA in shared memory (fp32 atomics) and flushed once; a warp keeps ONE patch row ky for its whole
-// life so the positional-table gradient accumulates in 16 registers.
+// accumulated per CTA in shared memory by OWNER warps (the warps exchange operand tiles through a staging buffer instead
+// of atomically adding results, see wgrad_coop) and flushed once; a warp keeps ONE patch row ky for its whole life so the
+// positional-table gradient accumulates in 16 registers.
 #include "common.cuh"
 
 namespace deco {
@@ -116,47 +117,74 @@ __device__ __forceinline__ void ln_bwd_m(const float (&dhn)[4][4], const float (
         else { dh[j][0] += v0; dh[j][1] += v1; dh[j][2] += v2; dh[j][3] += v3; }
     }
 }
-// gW[row * 36 + col] += (dY^T . X) for one 16-row m-tile of dY^T (A fragment af) against four n-tiles of X^T (xT);
-// gb[row] += sum over pixels of dY (ones column).  PERM: n-tile q, column c <-> channel 8 (c / 2) + 2 q + (c % 2).
+// Cooperative wgrad of one 32-row slab: gW[(row0 + i) * 36 + col] += sum over the CTA's 8 x 16 pixels of dY[p][i] X[p][col],
+// gb[row0 + i] += sum_p dY[p][i].  Shared-memory fp32 atomicAdd is a compare-and-swap loop on this architecture (80 % of
+// the first version's stall samples), so instead of every warp adding its own 16-pixel products into the CTA's
+// accumulators, the warps EXCHANGE OPERANDS: each stages its transposed tiles (8 + 8 words per lane), and after one barrier
+// warp w -- the exclusive owner of output tile (m-tile w / 4, n-tile w % 4) -- runs the 8 MMAs of all eight warps' pixels
+// for that tile and adds the result to the accumulator it owns with plain loads and stores.  The bias gradient is a ninth
+// n-tile whose B fragment is a column of ones (owners: the n-tile 0 warps).  Two staging buffers alternate (parity), so one
+// barrier per call suffices.  PERM: n-tile q, column c <-> channel 8 (c / 2) + 2 q + (c % 2) (the adaLN input layout).
+// All 8 warps of a CTA run the same number of items (they share the token index), so the barriers are uniform.
+constexpr int kStageWords = 8 * 16 * 32;     // one staging buffer: [warp][16 words][lane]
 template <bool PERM>
-__device__ __forceinline__ void wgrad_mtile(float* gW, float* gb, int row0, const uint32_t (&af)[4], const Tiles& xT, int lane) {
-    const int g = lane >> 2, t = lane & 3;
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-        float c[4] = {0.f, 0.f, 0.f, 0.f};
-        const uint32_t bb[2] = {xT.lo[nt], xT.hi[nt]};
-        mma_bf16_16816(c, af, bb);
-        const int col = PERM ? 8 * t + 2 * nt : 8 * nt + 2 * t;
-        float* p0 = gW + (row0 + g) * kS + col;
-        atomicAdd(p0, c[0]); atomicAdd(p0 + 1, c[1]);
-        atomicAdd(p0 + 8 * kS, c[2]); atomicAdd(p0 + 8 * kS + 1, c[3]);
-    }
-    if (gb) {
-        float c[4] = {0.f, 0.f, 0.f, 0.f};
-        const uint32_t one = g == 0 ? 0x3F803F80u : 0u;          // bf16 (1, 1) in column n = 0
-        const uint32_t bb[2] = {one, one};
-        mma_bf16_16816(c, af, bb);
-        if (t == 0) { atomicAdd(gb + row0 + g, c[0]); atomicAdd(gb + row0 + g + 8, c[2]); }
-    }
-}
-// all m-tiles of a 16 x 32 gradient
-template <bool PERM>
-__device__ __forceinline__ void wgrad32(float* gW, float* gb, int row0, const Tiles& dyT, const Tiles& xT, int lane) {
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
-        const uint32_t af[4] = {dyT.lo[2 * mt], dyT.lo[2 * mt + 1], dyT.hi[2 * mt], dyT.hi[2 * mt + 1]};
-        wgrad_mtile<PERM>(gW, gb, row0 + 16 * mt, af, xT, lane);
-    }
-}
-// column sums over the warp's 16 pixels of an accumulator-layout tensor -> g[channel] (atomics by the g == 0 lanes)
-__device__ __forceinline__ void colsum16(float* gvec, const float (&v)[4][4], int lane) {
-    const int t = lane & 3;
+__device__ __forceinline__ void wgrad_coop(uint32_t* stage, int& parity, float* gW, float* gb, int row0,
+                                           const Tiles& dyT, const Tiles& xT, int warp, int lane) {
+    uint32_t* buf = stage + parity * kStageWords;
+    parity ^= 1;
+    uint32_t* my = buf + warp * 16 * 32 + lane;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        float a = v[j][0] + v[j][2], b = v[j][1] + v[j][3];
+        my[j * 32] = dyT.lo[j]; my[(4 + j) * 32] = dyT.hi[j];
+        my[(8 + j) * 32] = xT.lo[j]; my[(12 + j) * 32] = xT.hi[j];
+    }
+    __syncthreads();
+    const int g = lane >> 2, t = lane & 3;
+    const int mt = warp >> 2, nt = warp & 3;
+    float c[4] = {0.f, 0.f, 0.f, 0.f}, cb[4] = {0.f, 0.f, 0.f, 0.f};
+    const uint32_t one = g == 0 ? 0x3F803F80u : 0u;          // bf16 (1, 1) in column n = 0
+    const uint32_t ones[2] = {one, one};
 #pragma unroll
-        for (int o = 4; o < 32; o <<= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
-        if (lane < 4) { atomicAdd(gvec + 8 * j + 2 * t, a); atomicAdd(gvec + 8 * j + 2 * t + 1, b); }
+    for (int w = 0; w < 8; ++w) {
+        const uint32_t* src = buf + w * 16 * 32 + lane;
+        const uint32_t af[4] = {src[(2 * mt) * 32], src[(2 * mt + 1) * 32], src[(4 + 2 * mt) * 32], src[(4 + 2 * mt + 1) * 32]};
+        const uint32_t bb[2] = {src[(8 + nt) * 32], src[(12 + nt) * 32]};
+        mma_bf16_16816(c, af, bb);
+        if (nt == 0) mma_bf16_16816(cb, af, ones);
+    }
+    const int col = PERM ? 8 * t + 2 * nt : 8 * nt + 2 * t;
+    float* p0 = gW + (row0 + 16 * mt + g) * kS + col;
+    p0[0] += c[0]; p0[1] += c[1]; p0[8 * kS] += c[2]; p0[8 * kS + 1] += c[3];
+    if (nt == 0 && t == 0) { gb[row0 + 16 * mt + g] += cb[0]; gb[row0 + 16 * mt + g + 8] += cb[2]; }
+}
+// Column sums over the CTA's pixels of two 16 x 32 tensors (LayerNorm weight / bias gradients) by the same exchange:
+// v1 tiles travel in the A slots (owners: warps 0 and 4), v2 tiles in the B slots (owners: warps 1 and 5).
+__device__ __forceinline__ void vecsum_coop(uint32_t* stage, int& parity, float* g1, float* g2,
+                                            const Tiles& v1T, const Tiles& v2T, int warp, int lane) {
+    uint32_t* buf = stage + parity * kStageWords;
+    parity ^= 1;
+    uint32_t* my = buf + warp * 16 * 32 + lane;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        my[j * 32] = v1T.lo[j]; my[(4 + j) * 32] = v1T.hi[j];
+        my[(8 + j) * 32] = v2T.lo[j]; my[(12 + j) * 32] = v2T.hi[j];
+    }
+    __syncthreads();
+    const int g = lane >> 2, t = lane & 3;
+    const int mt = warp >> 2, which = warp & 3;
+    if (which < 2) {
+        float cb[4] = {0.f, 0.f, 0.f, 0.f};
+        const uint32_t one = g == 0 ? 0x3F803F80u : 0u;
+        const uint32_t ones[2] = {one, one};
+        const int o = which * 8;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const uint32_t* src = buf + w * 16 * 32 + lane;
+            const uint32_t af[4] = {src[(o + 2 * mt) * 32], src[(o + 2 * mt + 1) * 32], src[(o + 4 + 2 * mt) * 32], src[(o + 4 + 2 * mt + 1) * 32]};
+            mma_bf16_16816(cb, af, ones);
+        }
+        float* gv = which == 0 ? g1 : g2;
+        if (t == 0) { gv[16 * mt + g] += cb[0]; gv[16 * mt + g + 8] += cb[2]; }
     }
 }
 __device__ __forceinline__ float dsilu_m(float x) {
@@ -184,6 +212,8 @@ __global__ void __launch_bounds__(256, 1) pixel_decoder_bwd_mma_kernel(DecBwdMma
     uint32_t* sBw = sF + ((nff + nfv + 3) & ~3);          // backward frags + Wf
     float* sG = reinterpret_cast<float*>(sBw + ((nbw + 3) & ~3));
     float* sH = sG + ((ng + 3) & ~3);                     // block inputs: [warp][R][16][32]
+    uint32_t* sStage = reinterpret_cast<uint32_t*>(sH + 8 * R * 16 * 32);   // operand exchange, 2 x kStageWords
+    int parity = 0;
     for (int i = threadIdx.x; i < nff + nfv; i += blockDim.x) sF[i] = __ldg(P.fblob + i);
     for (int i = threadIdx.x; i < nbw; i += blockDim.x) sBw[i] = __ldg(P.bblob + i);
     for (int i = threadIdx.x; i < ng; i += blockDim.x) sG[i] = 0.f;
@@ -439,7 +469,7 @@ __global__ void __launch_bounds__(256, 1) pixel_decoder_bwd_mma_kernel(DecBwdMma
                 for (int e = 0; e < 4; ++e) { const float d = dh[j][e]; gt[j][e] *= d; h[j][e] *= d; }   // gt = d mm, h = d gate
             dmodP[2] = pack_tiles(h);
             const Tiles dmmP = pack_tiles(gt);
-            wgrad32<false>(gB + kHW2, gB + kHb2, 0, transpose_tiles(dmmP), transpose_tiles(actP), lane);
+            wgrad_coop<false>(sStage, parity, gB + kHW2, gB + kHb2, 0, transpose_tiles(dmmP), transpose_tiles(actP), warp, lane);
 #pragma unroll
             for (int j = 0; j < 4; ++j) { h[j][0] = 0.f; h[j][1] = 0.f; h[j][2] = 0.f; h[j][3] = 0.f; }
             mma_t<4>(h, dmmP, w2T, 0, lane);                // h = d act
@@ -448,7 +478,7 @@ __global__ void __launch_bounds__(256, 1) pixel_decoder_bwd_mma_kernel(DecBwdMma
 #pragma unroll
                 for (int e = 0; e < 4; ++e) h[j][e] *= dsilu_m(z[j][e]);                                  // h = d z
             const Tiles dzP = pack_tiles(h);
-            wgrad32<false>(gB + kHW0, gB + kHb0, 0, transpose_tiles(dzP), transpose_tiles(hmP), lane);
+            wgrad_coop<false>(sStage, parity, gB + kHW0, gB + kHb0, 0, transpose_tiles(dzP), transpose_tiles(hmP), warp, lane);
 #pragma unroll
             for (int j = 0; j < 4; ++j) { h[j][0] = 0.f; h[j][1] = 0.f; h[j][2] = 0.f; h[j][3] = 0.f; }
             mma_t<4>(h, dzP, w0T, 0, lane);                 // h = d hm
@@ -470,8 +500,8 @@ __global__ void __launch_bounds__(256, 1) pixel_decoder_bwd_mma_kernel(DecBwdMma
                 for (int j = 0; j < 4; ++j)
 #pragma unroll
                     for (int e = 0; e < 4; ++e) { h[j][e] *= 1.0f + ss[4 + j][e]; tmp[j][e] = h[j][e] * hn[j][e]; }   // h = d hl
-                colsum16(gB + kHlng, tmp, lane);
-                colsum16(gB + kHlnb, h, lane);
+                vecsum_coop(sStage, parity, gB + kHlng, gB + kHlnb, transpose_tiles(pack_tiles(tmp)),
+                            transpose_tiles(pack_tiles(h)), warp, lane);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const float2 gm = *reinterpret_cast<const float2*>(vB + 96 + 8 * j + 2 * t);
@@ -482,7 +512,7 @@ __global__ void __launch_bounds__(256, 1) pixel_decoder_bwd_mma_kernel(DecBwdMma
             // adaLN: mod = Wada . silu(y) + bada
 #pragma unroll
             for (int part = 0; part < 3; ++part)
-                wgrad32<true>(gB + kHWada, gB + kHbada, 32 * part, transpose_tiles(dmodP[part]), ysT, lane);
+                wgrad_coop<true>(sStage, parity, gB + kHWada, gB + kHbada, 32 * part, transpose_tiles(dmodP[part]), ysT, warp, lane);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
 #pragma unroll
@@ -501,7 +531,7 @@ __global__ void __launch_bounds__(256, 1) pixel_decoder_bwd_mma_kernel(DecBwdMma
         {
             const Tiles dhP = pack_tiles(dh);
             const Tiles dhT = transpose_tiles(dhP);
-            wgrad32<false>(sG + kGWin, sG + kGbin, 0, dhT, transpose_tiles(e0), lane);
+            wgrad_coop<false>(sStage, parity, sG + kGWin, sG + kGbin, 0, dhT, transpose_tiles(e0), warp, lane);
             float de[4][4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) { de[j][0] = 0.f; de[j][1] = 0.f; de[j][2] = 0.f; de[j][3] = 0.f; }
@@ -610,7 +640,7 @@ extern "C" int deco_pixel_decoder_bwd_tc(const float* x, const void* ycond_bf16,
     P.M = (long long)B * P.Hp * P.Wp;
     const int R = P.R;
     const int words = ((mf_frag_words(R) + mf_vec_floats(R) + 3) & ~3) + ((mb_words(R) + 3) & ~3) + ((mg_floats(R) + 3) & ~3) +
-                      8 * R * 16 * 32;
+                      8 * R * 16 * 32 + 2 * kStageWords;
     const int smem_bytes = words * 4;
     cudaError_t e = cudaFuncSetAttribute(pixel_decoder_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) { deco_set_error("pixel_decoder_bwd_tc attr: %s", cudaGetErrorString(e)); return (int)e; }
