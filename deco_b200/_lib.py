@@ -18,7 +18,8 @@ SIGNATURES = {
     "deco_last_error": (C.c_char_p, []),
     "deco_abi_version": (_i, []),
     "deco_gemm_bf16": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _vp, _vp, _ll, _vp, _ll, _i, _i, _vp]),
-    "deco_gemm_bf16_tn": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _vp]),
+    "deco_gemm_bf16_tn": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _i, _vp]),
+    "deco_gemm_bf16_f32_splitk": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _vp]),
     "deco_gemm_stream_parts": (_i, [_i, _i]),
     "deco_gemm_stream": (_i, [_vp, _ll, _vp, _ll, _i, _i, _i, _vp, _vp, _ll, _vp, _ll, _vp, _ll, _i, _vp, _vp, _ll, _vp, _ll,
                               _vp, _vp]),
@@ -32,6 +33,7 @@ SIGNATURES = {
     "deco_rmsnorm_modulate": (_i, [_vp, _i, _vp, _vp, _vp, _ll, _i, _vp, _ll, _i, _f, _vp]),
     "deco_qknorm_rope": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _i, _i, _f, _vp]),
     "deco_headnorm_rope": (_i, [_vp, _ll, _i, _i, _i, _vp, _vp, _vp, _ll, _i, _i, _i, _f, _vp]),
+    "deco_headnorm_rope_to": (_i, [_vp, _vp, _ll, _i, _i, _i, _vp, _vp, _vp, _ll, _i, _i, _i, _f, _vp]),
     "deco_rmsnorm_addpos": (_i, [_vp, _vp, _vp, _i, _vp, _ll, _i, _f, _vp]),
     "deco_cast_f32_bf16": (_i, [_vp, _vp, _ll, _vp]),
     "deco_attention_fwd": (_i, [_vp, _ll, _vp, _vp, _ll, _i, _vp, _vp, _ll, _i, _vp, _ll, _i, _i, _i, _i, _f, _vp]),

@@ -152,9 +152,9 @@ def train_forward(module, x32, t, y):
         sh1, sc1, g1, sh2, sc2, g2 = (m[:, j * H:(j + 1) * H] for j in range(6))
         h1 = ops.rmsnorm_modulate(s, bp["n1"], sh1, sc1, L)
         qkv_raw = ops.gemm(h1, bp["wqkv"], None, ops.EPI_BIAS)
-        qkv = qkv_raw.clone()
-        ops.qknorm_rope_(qkv, bp["qn"], bp["kn"], pos, heads, d, L)
-        o = ops.attention(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], B, heads, d)
+        qkv = torch.empty_like(qkv_raw)          # q, k normalised + rotated here; v is read from the raw GEMM output
+        ops.qknorm_rope_to(qkv_raw, qkv, bp["qn"], bp["kn"], pos, heads, d, L)
+        o = ops.attention(qkv[:, :H], qkv[:, H:2 * H], qkv_raw[:, 2 * H:], B, heads, d)
         a1 = ops.gemm(o, bp["wproj"], bp["bproj"], ops.EPI_BIAS)
         s_mid = ops.gate_residual(s, a1, g1, L)
         h2 = ops.rmsnorm_modulate(s_mid, bp["n2"], sh2, sc2, L)
@@ -231,6 +231,7 @@ def train_backward(module, S: dict, dout: torch.Tensor) -> Dict[str, torch.Tenso
     # ---- DiT blocks
     dmod = z(B, nb * 6 * H)
     mod = S["mod"]
+    zblk = z(max(nb, 1), 3 * H + 2 * d)       # one fill for the per-block vector gradients (norm1/2, proj bias, q/k-norm)
     for i in reversed(range(nb)):
         bp, bt, sv = P["blocks"][i], T["blocks"][i], S["blocks"][i]
         pre = f"blocks.{i}."
@@ -249,27 +250,24 @@ def train_backward(module, S: dict, dout: torch.Tensor) -> Dict[str, torch.Tenso
         G[pre + "mlp.w1.weight"] = dw13[:, 0].reshape(Fp, H)[:F_]
         G[pre + "mlp.w3.weight"] = dw13[:, 1].reshape(Fp, H)[:F_]
         dh2 = ops.gemm(dy13, bt["w13T"], None, ops.EPI_BIAS)
-        dn2 = z(H)
+        dn2, dn1, dbproj, dqn, dkn = zblk[i, :H], zblk[i, H:2 * H], zblk[i, 2 * H:3 * H], zblk[i, 3 * H:3 * H + d], zblk[i, 3 * H + d:]
         ops.rmsnorm_modulate_bwd_(ds, dh2, sv["s_mid"], bp["n2"], sc2, dn2, dsh2, dsc2, L)
         G[pre + "norm2.weight"] = dn2
         del da2, du, dy13, dh2
         # attention branch
-        dbproj = z(H)
         da1 = ops.gate_bwd(ds, sv["a1"], g1, dg1, L, dbias=dbproj)
         G[pre + "attn.proj.bias"] = dbproj
         G[pre + "attn.proj.weight"] = _wgrad(da1, sv["o"])
         do = ops.gemm(da1, bt["wprojT"], None, ops.EPI_BIAS)
         qkv = sv["qkv"]
         dqkv = torch.empty_like(qkv)
-        ops.attention_bwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], sv["o"], do,
+        ops.attention_bwd(qkv[:, :H], qkv[:, H:2 * H], sv["qkv_raw"][:, 2 * H:], sv["o"], do,
                           dqkv[:, :H], dqkv[:, H:2 * H], dqkv[:, 2 * H:], B, heads, d)
-        dqn, dkn = z(d), z(d)
         ops.headnorm_rope_bwd_(dqkv, sv["qkv_raw"], 0, bp["qn"], S["pos"], dqn, heads, d, L)
         ops.headnorm_rope_bwd_(dqkv, sv["qkv_raw"], H, bp["kn"], S["pos"], dkn, heads, d, L)
         G[pre + "attn.q_norm.weight"], G[pre + "attn.k_norm.weight"] = dqn, dkn
         G[pre + "attn.qkv.weight"] = _wgrad(dqkv, sv["h1"])
         dh1 = ops.gemm(dqkv, bt["wqkvT"], None, ops.EPI_BIAS)
-        dn1 = z(H)
         ops.rmsnorm_modulate_bwd_(ds, dh1, sv["s_in"], bp["n1"], sc1, dn1, dsh1, dsc1, L)
         G[pre + "norm1.weight"] = dn1
         del da1, do, dqkv, dh1
@@ -285,7 +283,7 @@ def train_backward(module, S: dict, dout: torch.Tensor) -> Dict[str, torch.Tenso
         for i in range(nb):
             G[f"blocks.{i}.adaLN_modulation.0.weight"] = dwada[i * 6 * H:(i + 1) * 6 * H]
             G[f"blocks.{i}.adaLN_modulation.0.bias"] = dbada[i * 6 * H:(i + 1) * 6 * H]
-        dc = ops.gemm(ops.cast_bf16(dmod), T["wadaT"], None, ops.EPI_BIAS_F32)
+        dc = ops.gemm_f32_splitk(ops.cast_bf16(dmod), T["wadaT"])          # M = batch, K = nb*6H: split-K
     else:
         dc = z(B, H)
     # ---- c = silu(temb + table[y])

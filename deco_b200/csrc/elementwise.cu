@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(256) rmsnorm_modulate_kernel(
 // segment is heads x D.  One thread per (token, segment, head) vector of D elements.
 // rope: [L, D/2] float2 (cos, sin) or NULL (norm only -- the t2i text keys); token position = row % L.
 template <int D>
-__global__ void __launch_bounds__(128) qknorm_rope_kernel(__nv_bfloat16* __restrict__ qkv, long long row_stride,
+__global__ void __launch_bounds__(128) qknorm_rope_kernel(const __nv_bfloat16* src, __nv_bfloat16* qkv, long long row_stride,
                                                           int nseg, int col0, int col1, const float* __restrict__ qw,
                                                           const float* __restrict__ kw, const float2* __restrict__ rope,
                                                           long long M, int heads, int L, float eps)
@@ -149,14 +149,16 @@ __global__ void __launch_bounds__(128) qknorm_rope_kernel(__nv_bfloat16* __restr
     const long long tok = item / per_tok;
     const int r = (int)(item % per_tok);
     const int is_k = r / heads, head = r % heads;
-    __nv_bfloat16* p = qkv + tok * row_stride + (is_k ? col1 : col0) + (long long)head * D;
+    const long long off = tok * row_stride + (is_k ? col1 : col0) + (long long)head * D;
+    __nv_bfloat16* p = qkv + off;
+    const __nv_bfloat16* sp = src + off;            // src == qkv: in place
     const float* wv = is_k ? kw : qw;
     const float2* rp = rope ? rope + (long long)(tok % L) * (D / 2) : nullptr;
     float v[D];
     float ss = 0.f;
 #pragma unroll
     for (int c = 0; c < D / 8; ++c) {
-        const uint4 q = *reinterpret_cast<const uint4*>(p + c * 8);
+        const uint4 q = *reinterpret_cast<const uint4*>(sp + c * 8);
         const float2 a = unpack_bf2(q.x), b = unpack_bf2(q.y), cc = unpack_bf2(q.z), d = unpack_bf2(q.w);
         v[c * 8 + 0] = a.x; v[c * 8 + 1] = a.y; v[c * 8 + 2] = b.x; v[c * 8 + 3] = b.y;
         v[c * 8 + 4] = cc.x; v[c * 8 + 5] = cc.y; v[c * 8 + 6] = d.x; v[c * 8 + 7] = d.y;
@@ -326,20 +328,21 @@ extern "C" int deco_rmsnorm_modulate(const void* x, int x_is_f32, const float* w
     return DECO_OK;
 }
 
-extern "C" int deco_headnorm_rope(void* buf_bf16, long long row_stride, int nseg, int col0, int col1,
-                                  const float* w0, const float* w1, const float* rope_cos_sin,
-                                  long long M, int heads, int head_dim, int L, float eps, void* stream) {
+static int headnorm_rope_launch(const void* src_bf16, void* buf_bf16, long long row_stride, int nseg, int col0, int col1,
+                                const float* w0, const float* w1, const float* rope_cos_sin,
+                                long long M, int heads, int head_dim, int L, float eps, void* stream) {
     using namespace deco;
-    DECO_CHECK_ARG(buf_bf16 && w0 && (nseg == 1 || (nseg == 2 && w1)), "headnorm_rope: null pointer / bad nseg");
+    DECO_CHECK_ARG(src_bf16 && buf_bf16 && w0 && (nseg == 1 || (nseg == 2 && w1)), "headnorm_rope: null pointer / bad nseg");
     DECO_CHECK_ARG(M > 0 && heads > 0 && L > 0 && row_stride % 8 == 0 && col0 % 8 == 0 && col1 % 8 == 0 && col0 >= 0 && col1 >= 0,
                    "headnorm_rope: bad shape");
     const long long items = M * nseg * heads;
     const unsigned grid = (unsigned)((items + 127) / 128);
+    const __nv_bfloat16* sp = (const __nv_bfloat16*)src_bf16;
     if (head_dim == 72)
-        qknorm_rope_kernel<72><<<grid, 128, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)buf_bf16, row_stride, nseg, col0, col1,
+        qknorm_rope_kernel<72><<<grid, 128, 0, (cudaStream_t)stream>>>(sp, (__nv_bfloat16*)buf_bf16, row_stride, nseg, col0, col1,
                                                                       w0, w1, (const float2*)rope_cos_sin, M, heads, L, eps);
     else if (head_dim == 64)
-        qknorm_rope_kernel<64><<<grid, 128, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)buf_bf16, row_stride, nseg, col0, col1,
+        qknorm_rope_kernel<64><<<grid, 128, 0, (cudaStream_t)stream>>>(sp, (__nv_bfloat16*)buf_bf16, row_stride, nseg, col0, col1,
                                                                       w0, w1, (const float2*)rope_cos_sin, M, heads, L, eps);
     else {
         deco_set_error("headnorm_rope: head_dim %d not built (64, 72)", head_dim);
@@ -347,6 +350,22 @@ extern "C" int deco_headnorm_rope(void* buf_bf16, long long row_stride, int nseg
     }
     DECO_CHECK_LAUNCH("qknorm_rope_kernel");
     return DECO_OK;
+}
+
+extern "C" int deco_headnorm_rope(void* buf_bf16, long long row_stride, int nseg, int col0, int col1,
+                                  const float* w0, const float* w1, const float* rope_cos_sin,
+                                  long long M, int heads, int head_dim, int L, float eps, void* stream) {
+    return headnorm_rope_launch(buf_bf16, buf_bf16, row_stride, nseg, col0, col1, w0, w1, rope_cos_sin, M, heads, head_dim, L,
+                                eps, stream);
+}
+
+// out-of-place form: reads the segments from src, writes them to dst (same row stride and columns); the training forward
+// keeps the raw QKV GEMM output for the backward of the norm and gets the normalised copy without a memcpy
+extern "C" int deco_headnorm_rope_to(const void* src_bf16, void* dst_bf16, long long row_stride, int nseg, int col0, int col1,
+                                     const float* w0, const float* w1, const float* rope_cos_sin,
+                                     long long M, int heads, int head_dim, int L, float eps, void* stream) {
+    return headnorm_rope_launch(src_bf16, dst_bf16, row_stride, nseg, col0, col1, w0, w1, rope_cos_sin, M, heads, head_dim, L,
+                                eps, stream);
 }
 
 extern "C" int deco_qknorm_rope(void* qkv_bf16, const float* q_weight, const float* k_weight, const float* rope_cos_sin,

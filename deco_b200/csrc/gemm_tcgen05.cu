@@ -45,6 +45,8 @@ struct GemmParams {
     long long gate_stride;
     int rows_per_gate;
     int M, N, K;
+    int split_k;                     // > 1 (EPI_BIAS_F32 only): the K loop is cut into split_k slices, one tile each, and the
+                                     // partial products are reduced with fp32 atomics into a pre-zeroed output
 };
 
 template <int BN, int CG> struct GemmCfg {
@@ -144,7 +146,12 @@ __device__ __forceinline__ void epilogue_chunk_staged(const GemmParams& P, const
                     *reinterpret_cast<float4*>(reinterpret_cast<float*>(P.out) + row * P.ldo + n) =
                         make_float4(fmaf(g0.x, v.x, rv.x), fmaf(g0.y, v.y, rv.y), fmaf(g1.x, v.z, rv.z), fmaf(g1.y, v.w, rv.w));
                 } else if (EPI == EPI_BIAS_F32) {
-                    *reinterpret_cast<float4*>(reinterpret_cast<float*>(P.out) + row * P.ldo + n) = v;
+                    float* o = reinterpret_cast<float*>(P.out) + row * P.ldo + n;
+                    if (P.split_k > 1) {        // partial product of one K slice (output zeroed by the launcher)
+                        atomicAdd(o, v.x); atomicAdd(o + 1, v.y); atomicAdd(o + 2, v.z); atomicAdd(o + 3, v.w);
+                    } else {
+                        *reinterpret_cast<float4*>(o) = v;
+                    }
                 } else {
                     if (EPI == EPI_BIAS_SILU) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
                     uint2 w;
@@ -250,8 +257,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
     const bool is_leader = cta_rank == 0;
     const int num_m = (P.M + kBM * CG - 1) / (kBM * CG), num_n = (P.N + BN - 1) / BN;
-    const int num_tiles = num_m * num_n;
+    const int num_mn = num_m * num_n;
+    const int split_k = (EPI == EPI_BIAS_F32 && P.split_k > 1) ? P.split_k : 1;
+    const int num_tiles = num_mn * split_k;
     const int num_k = (P.K + kBK - 1) / kBK;
+    const int k_per = (num_k + split_k - 1) / split_k;      // host guarantees every slice is non-empty
     const int tile0 = blockIdx.x / CG, tile_stride = gridDim.x / CG;
 
     if (warp == 0 && lane == 0) {
@@ -277,10 +287,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int tile = tile0; tile < num_tiles; tile += tile_stride) {
-                const int m_blk = tile / num_n, n_blk = tile % num_n;
+                const int mn = tile % num_mn, ks = tile / num_mn;
+                const int m_blk = mn / num_n, n_blk = mn % num_n;
                 const int arow = (m_blk * CG + (int)cta_rank) * kBM;
                 const int brow = n_blk * BN + (int)cta_rank * (BN / CG);
-                for (int kb = 0; kb < num_k; ++kb) {
+                const int kb0 = ks * k_per, kb1 = min(num_k, kb0 + k_per);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
                     const uint32_t sb = sa + Cfg::kStageBytesA;
@@ -323,7 +335,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 mbar_wait(tempty_bar(as), aphase ^ 1);   // epilogues (of both CTAs) have drained this accumulator stage
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
-                for (int kb = 0; kb < num_k; ++kb) {
+                const int kb0 = (tile / num_mn) * k_per, kb1 = min(num_k, kb0 + k_per);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
                     const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
@@ -334,8 +347,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     constexpr uint64_t kstep = TN ? 128 : 2;
 #pragma unroll
                     for (int k = 0; k < kBK / kUmmaK; ++k) {
-                        if (CG == 2) umma_bf16_2sm(tmem_d, da + kstep * k, db + kstep * k, idesc, (kb | k) ? 1u : 0u);
-                        else umma_bf16(tmem_d, da + kstep * k, db + kstep * k, idesc, (kb | k) ? 1u : 0u);
+                        if (CG == 2) umma_bf16_2sm(tmem_d, da + kstep * k, db + kstep * k, idesc, ((kb - kb0) | k) ? 1u : 0u);
+                        else umma_bf16(tmem_d, da + kstep * k, db + kstep * k, idesc, ((kb - kb0) | k) ? 1u : 0u);
                     }
                     // frees the smem stage (in both CTAs) once these MMAs retire
                     if (CG == 2) umma_commit_2sm(empty_bar(stage)); else umma_commit(empty_bar(stage));
@@ -351,7 +364,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         int as = 0; uint32_t aphase = 0;
         float* stg = reinterpret_cast<float*>(smem_raw + (epi_stage_base - smem_u32(smem_raw))) + q * kStageFloatsPerWarp;
         for (int tile = tile0; tile < num_tiles; tile += tile_stride) {
-            const int m_blk = tile / num_n, n_blk = tile % num_n;
+            const int m_blk = (tile % num_mn) / num_n, n_blk = (tile % num_mn) % num_n;
             const long long row0 = (long long)(m_blk * CG + (int)cta_rank) * kBM + q * 32;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
             const int nbase = n_blk * BN;
@@ -436,7 +449,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
         if (e != cudaSuccess) { deco_set_error("gemm smem attr: %s", cudaGetErrorString(e)); return (int)e; }
         attr_done = true;
     }
-    const int tiles = ((P.M + kBM * CG - 1) / (kBM * CG)) * ((P.N + BN - 1) / BN);
+    const int tiles = ((P.M + kBM * CG - 1) / (kBM * CG)) * ((P.N + BN - 1) / BN) * (EPI == EPI_BIAS_F32 && P.split_k > 1 ? P.split_k : 1);
     int groups = max_ctas / CG;
     if (tiles < groups) groups = tiles;
     cudaLaunchConfig_t cfg = {};
@@ -527,7 +540,7 @@ extern "C" int deco_gemm_bf16(const void* A, long long lda, const void* W, long 
     GemmParams P;
     P.out = out; P.ldo = ldo; P.bias = bias; P.resid = (const float*)resid; P.ldr = ldr;
     P.gate = (const __nv_bfloat16*)gate; P.gate_stride = gate_stride; P.rows_per_gate = rows_per_gate > 0 ? rows_per_gate : 1;
-    P.M = M; P.N = N; P.K = K;
+    P.M = M; P.N = N; P.K = K; P.split_k = 1;
     const int ctas = num_sms();
     cudaStream_t st = (cudaStream_t)stream;
     if (bn == 256) return dispatch_variant<256>(cg, staged, epilogue, ta, tb, P, ctas, st);
@@ -544,10 +557,41 @@ extern "C" int deco_gemm_set_tuning(int cta_group, int staged_epilogue) {
     return DECO_OK;
 }
 
+namespace deco {
+// K slices for an fp32-output GEMM whose M x N tiles alone would leave most CTA groups idle: as many slices as fit in one
+// wave, each at least 4 K-blocks (256 elements) deep.  0 / 1 = no split.
+static int auto_split_k(int M, int N, int K, int bn, int cg, int ctas) {
+    const int tiles = ((M + kBM * cg - 1) / (kBM * cg)) * ((N + bn - 1) / bn);
+    const int groups = ctas / cg;
+    const int num_k = (K + kBK - 1) / kBK;
+    if (tiles * 2 > groups || num_k < 8) return 1;
+    int s = groups / tiles;
+    if (s > num_k / 4) s = num_k / 4;
+    if (s > 32) s = 32;
+    while (s > 1 && ((num_k + s - 1) / s) * (s - 1) >= num_k) --s;     // no empty slice
+    return s < 1 ? 1 : s;
+}
+
+// largest s' <= s whose ceil(num_k / s')-deep slices are all non-empty
+static int legal_split_k(int s, int K) {
+    const int num_k = (K + kBK - 1) / kBK;
+    if (s > num_k) s = num_k;
+    while (s > 1 && ((num_k + s - 1) / s) * (s - 1) >= num_k) --s;
+    return s < 1 ? 1 : s;
+}
+
+static int zero_output(float* out, long long ldo, int M, int N, cudaStream_t st) {
+    cudaError_t e = (ldo == N) ? cudaMemsetAsync(out, 0, (size_t)M * N * 4, st)
+                               : cudaMemset2DAsync(out, (size_t)ldo * 4, 0, (size_t)N * 4, (size_t)M, st);
+    if (e != cudaSuccess) { deco_set_error("gemm split-K: memset failed: %s", cudaGetErrorString(e)); return (int)e; }
+    return DECO_OK;
+}
+}  // namespace deco
+
 // out[M, N] fp32 = At^T . Wt with At [K, M] and Wt [K, N] row-major bf16 (the wgrad contraction dW = dY^T . X on the
 // activations as they lie in memory).  M, N, lda, ldw, ldo multiples of 8.
 extern "C" int deco_gemm_bf16_tn(const void* At, long long lda, const void* Wt, long long ldw, float* out, long long ldo,
-                                 int M, int N, int K, int tile_n, void* stream)
+                                 int M, int N, int K, int tile_n, int split_k, void* stream)
 {
     using namespace deco;
     DECO_CHECK_ARG(At && Wt && out, "gemm_tn: null pointer");
@@ -570,8 +614,41 @@ extern "C" int deco_gemm_bf16_tn(const void* At, long long lda, const void* Wt, 
     P.M = M; P.N = N; P.K = K;
     const int ctas = num_sms();
     cudaStream_t st = (cudaStream_t)stream;
+    P.split_k = legal_split_k(split_k > 0 ? split_k : auto_split_k(M, N, K, bn, cg, ctas), K);
+    if (P.split_k > 1) { rc = zero_output(out, ldo, M, N, st); if (rc) return rc; }
     if (bn == 256) return cg == 2 ? launch_gemm<256, EPI_BIAS_F32, 2, true, true>(ta, tb, P, ctas, st)
                                   : launch_gemm<256, EPI_BIAS_F32, 1, true, true>(ta, tb, P, ctas, st);
     return cg == 2 ? launch_gemm<128, EPI_BIAS_F32, 2, true, true>(ta, tb, P, ctas, st)
                    : launch_gemm<128, EPI_BIAS_F32, 1, true, true>(ta, tb, P, ctas, st);
+}
+
+// out[M, N] fp32 = A . W^T (K-major operands as deco_gemm_bf16 with DECO_EPI_BIAS_F32 and no bias) with the K loop split
+// over split_k tiles (0 = automatic) and reduced with fp32 atomics: for skinny problems whose M x N tiles cannot fill the
+// GPU, e.g. d c = d mod . Wada with M = batch, K = 6 x hidden x blocks.
+extern "C" int deco_gemm_bf16_f32_splitk(const void* A, long long lda, const void* W, long long ldw, float* out, long long ldo,
+                                         int M, int N, int K, int split_k, void* stream)
+{
+    using namespace deco;
+    DECO_CHECK_ARG(A && W && out, "gemm_splitk: null pointer");
+    DECO_CHECK_ARG(M > 0 && N > 0 && K > 0 && K % 8 == 0 && N % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldo % 4 == 0,
+                   "gemm_splitk: bad shape / alignment (M=%d N=%d K=%d)", M, N, K);
+    DECO_CHECK_ARG((((uintptr_t)A | (uintptr_t)W | (uintptr_t)out) & 15) == 0, "gemm_splitk: pointers must be 16-byte aligned");
+    const int bn = (N % 256 == 0) ? 256 : ((N % 192 == 0) ? 192 : 128);
+    const int cg = M > kBM ? 2 : 1;
+    CUtensorMap ta, tb;
+    int rc = make_tmap(&ta, A, M, K, lda, kBM);
+    if (rc) return rc;
+    rc = make_tmap(&tb, W, N, K, ldw, bn / cg);
+    if (rc) return rc;
+    GemmParams P;
+    P.out = out; P.ldo = ldo; P.bias = nullptr; P.resid = nullptr; P.ldr = 0;
+    P.gate = nullptr; P.gate_stride = 0; P.rows_per_gate = 1;
+    P.M = M; P.N = N; P.K = K;
+    const int ctas = num_sms();
+    cudaStream_t st = (cudaStream_t)stream;
+    P.split_k = legal_split_k(split_k > 0 ? split_k : auto_split_k(M, N, K, bn, cg, ctas), K);
+    if (P.split_k > 1) { rc = zero_output(out, ldo, M, N, st); if (rc) return rc; }
+    if (bn == 256) return dispatch_variant<256>(cg, 1, EPI_BIAS_F32, ta, tb, P, ctas, st);
+    if (bn == 192) return dispatch_variant<192>(cg, 1, EPI_BIAS_F32, ta, tb, P, ctas, st);
+    return dispatch_variant<128>(cg, 1, EPI_BIAS_F32, ta, tb, P, ctas, st);
 }

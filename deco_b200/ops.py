@@ -222,6 +222,17 @@ def headnorm_rope_(buf: torch.Tensor, col0: int, w0: torch.Tensor, heads: int, h
     return buf
 
 
+def qknorm_rope_to(raw: torch.Tensor, dst: torch.Tensor, q_weight: torch.Tensor, k_weight: torch.Tensor, rope: torch.Tensor,
+                   heads: int, head_dim: int, L: int, eps: float = 1e-6) -> torch.Tensor:
+    """dst[:, :2H] = q/k-norm + RoPE of raw[:, :2H] (raw, dst: [M, 3H] bf16, same layout); the v columns are not touched."""
+    _cuda(raw, dst, q_weight, k_weight, rope)
+    assert raw.dtype == bf16 and dst.dtype == bf16 and raw.is_contiguous() and dst.is_contiguous() and raw.shape == dst.shape
+    assert raw.shape[1] == 3 * heads * head_dim
+    call("deco_headnorm_rope_to", ptr(raw), ptr(dst), raw.stride(0), 2, 0, heads * head_dim, ptr(q_weight), ptr(k_weight),
+         ptr(rope), raw.shape[0], heads, head_dim, L, float(eps), _st(raw))
+    return dst
+
+
 def rmsnorm_addpos(x: torch.Tensor, weight: torch.Tensor, pos: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
     """out[m] = weight * rms(x[m]) + pos[m % T]; x fp32 [M,H], pos fp32 [T,H]; fp32 output."""
     _cuda(x, weight, pos)
@@ -538,7 +549,23 @@ def pixel_decoder_bwd_tc(x: torch.Tensor, ycond: torch.Tensor, dout: torch.Tenso
     return dy, grads
 
 
-def gemm_tn(at: torch.Tensor, wt: torch.Tensor, tile_n: int = 0) -> torch.Tensor:
+def gemm_f32_splitk(a: torch.Tensor, w: torch.Tensor, split_k: int = 0) -> torch.Tensor:
+    """out [M, N] fp32 = a @ w.T (a [M, K], w [N, K] bf16) with the K loop split over CTAs (0 = automatic) and reduced with
+    fp32 atomics: skinny problems (M = batch) with a very long K."""
+    _cuda(a, w)
+    assert a.dtype == bf16 and w.dtype == bf16 and a.stride(1) == 1 and w.stride(1) == 1 and a.shape[1] == w.shape[1]
+    M, K = a.shape
+    N = w.shape[0]
+    out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    probe = gemm_probe
+    ev = probe.before() if probe is not None else None
+    call("deco_gemm_bf16_f32_splitk", ptr(a), a.stride(0), ptr(w), w.stride(0), ptr(out), out.stride(0), M, N, K, split_k, _st(a))
+    if probe is not None:
+        probe.after(ev, 2.0 * M * N * K)
+    return out
+
+
+def gemm_tn(at: torch.Tensor, wt: torch.Tensor, tile_n: int = 0, split_k: int = 0) -> torch.Tensor:
     """out [M, N] fp32 = at^T @ wt for at [K, M], wt [K, N] bf16 row-major (wgrad: dW = dY^T . X, K = tokens); no
     transposed copies -- the GEMM stages both operands MN-major."""
     _cuda(at, wt)
@@ -549,7 +576,8 @@ def gemm_tn(at: torch.Tensor, wt: torch.Tensor, tile_n: int = 0) -> torch.Tensor
     out = torch.empty((M, N), dtype=torch.float32, device=at.device)
     probe = gemm_probe
     ev = probe.before() if probe is not None else None
-    call("deco_gemm_bf16_tn", ptr(at), at.stride(0), ptr(wt), wt.stride(0), ptr(out), out.stride(0), M, N, K, tile_n, _st(at))
+    call("deco_gemm_bf16_tn", ptr(at), at.stride(0), ptr(wt), wt.stride(0), ptr(out), out.stride(0), M, N, K, tile_n, split_k,
+         _st(at))
     if probe is not None:
         probe.after(ev, 2.0 * M * N * K)
     return out

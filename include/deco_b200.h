@@ -118,6 +118,11 @@ int deco_headnorm_rope(void* buf_bf16, long long row_stride, int nseg, int col0,
                        const float* w0, const float* w1, const float* rope_cos_sin,
                        long long M, int heads, int head_dim, int L, float eps, void* stream);
 
+/* Out-of-place form of deco_headnorm_rope (training forward: the raw GEMM output is kept for the backward of the norm) */
+int deco_headnorm_rope_to(const void* src_bf16, void* dst_bf16, long long row_stride, int nseg, int col0, int col1,
+                          const float* w0, const float* w1, const float* rope_cos_sin,
+                          long long M, int heads, int head_dim, int L, float eps, void* stream);
+
 /* Text embedder tail (dit_t2i_pixnerd.py:280 with layers/patch_embed.py:19-22, layers/rmsnorm.py:15-20):
  * out[m,:] = weight * rms(x[m,:]) + pos[m % T,:]; x = y_embedder.proj output, pos = y_pos_embedding; all fp32. */
 int deco_rmsnorm_addpos(const float* x, const float* weight, const float* pos, int T, float* out,
@@ -265,7 +270,14 @@ int deco_pixel_decoder_bwd_tc(const float* x, const void* ycond_bf16, const floa
  * (dW = dY^T . X with K = tokens).  Operands are staged MN-major (csrc/gemm_tcgen05.cu, TN mode); M, N, lda, ldw multiples
  * of 8; tile_n in {0 (auto), 128, 256}. */
 int deco_gemm_bf16_tn(const void* At, long long lda, const void* Wt, long long ldw, float* out, long long ldo,
-                      int M, int N, int K, int tile_n, void* stream);
+                      int M, int N, int K, int tile_n, int split_k, void* stream);
+
+/* Split-K: when the M x N tiles alone cannot fill the GPU (small weight matrices with a long token reduction; d c = d mod .
+ * Wada with M = batch), the K loop is cut into split_k slices (0 = automatic, 1 = off) that run as separate tiles and are
+ * reduced with fp32 atomics into the (zeroed) output.  deco_gemm_bf16_f32_splitk is deco_gemm_bf16 with
+ * DECO_EPI_BIAS_F32, no bias. */
+int deco_gemm_bf16_f32_splitk(const void* A, long long lda, const void* W, long long ldw, float* out, long long ldo,
+                              int M, int N, int K, int split_k, void* stream);
 
 #ifdef __cplusplus
 }

@@ -51,12 +51,27 @@ def test_gemm_tn_mn_major_operands(dev, M, N, K):
     wt = torch.randn(K, N, device=dev, generator=_g(N + 1)).to(bf16)
     ref = at.float().t() @ wt.float()
     for tile_n in (0, 128, 256):
-        out = ops.gemm_tn(at, wt, tile_n)
+        out = ops.gemm_tn(at, wt, tile_n, split_k=1)
         assert rel_l2(out, ref) < 2e-3, (tile_n, rel_l2(out, ref))
+    for split_k in (0, 2, 5):
+        if split_k <= max(1, (K + 63) // 64):
+            out = ops.gemm_tn(at, wt, 0, split_k=split_k)
+            assert rel_l2(out, ref) < 2e-3, (split_k, rel_l2(out, ref))
     # strided operands (column slices of a wider buffer)
     big = torch.randn(K, M + N + 16, device=dev, generator=_g(7)).to(bf16)
     a2, w2 = big[:, 8:8 + M], big[:, 8 + M:8 + M + N]
     assert rel_l2(ops.gemm_tn(a2, w2), a2.float().t() @ w2.float()) < 2e-3
+
+
+def test_gemm_split_k_skinny(dev):
+    """d c = d mod . Wada: M = batch rows, K = 6 x hidden x blocks; K slices reduced with fp32 atomics."""
+    from deco_b200 import ops
+    M, N, K = 32, 1152, 6912 * 4
+    a = torch.randn(M, K, device=dev, generator=_g(1)).to(bf16)
+    w = (torch.randn(N, K, device=dev, generator=_g(2)) * K ** -0.5).to(bf16)
+    ref = a.float() @ w.float().t()
+    for split_k in (0, 1, 7):
+        assert rel_l2(ops.gemm_f32_splitk(a, w, split_k), ref) < 2e-3
 
 
 def test_wgrad_dgrad_through_the_gemm(dev):
