@@ -56,8 +56,9 @@ SIGNATURES = {
     "deco_headnorm_rope_bwd": (_i, [_vp, _ll, _vp, _ll, _i, _vp, _vp, _vp, _ll, _i, _i, _i, _f, _vp]),
     "deco_cond_combine_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "deco_silu_bwd": (_i, [_vp, _vp, _vp, _ll, _vp]),
+    "deco_attention_fwd_lse": (_i, [_vp, _ll, _vp, _vp, _ll, _i, _vp, _ll, _vp, _i, _i, _i, _i, _f, _vp]),
     "deco_attention_bwd": (_i, [_vp, _ll, _vp, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _vp, _ll, _vp, _vp,
-                                _i, _i, _i, _i, _i, _f, _vp]),
+                                _i, _i, _i, _i, _i, _i, _f, _vp]),
     "deco_decoder_train_blob_floats": (_i, [_i]),
     "deco_pixel_decoder_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "deco_decoder_bwd_blob_bytes": (_i, [_i]),

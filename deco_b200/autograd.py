@@ -154,7 +154,7 @@ def train_forward(module, x32, t, y):
         qkv_raw = ops.gemm(h1, bp["wqkv"], None, ops.EPI_BIAS)
         qkv = torch.empty_like(qkv_raw)          # q, k normalised + rotated here; v is read from the raw GEMM output
         ops.qknorm_rope_to(qkv_raw, qkv, bp["qn"], bp["kn"], pos, heads, d, L)
-        o = ops.attention(qkv[:, :H], qkv[:, H:2 * H], qkv_raw[:, 2 * H:], B, heads, d)
+        o, lse = ops.attention_lse(qkv[:, :H], qkv[:, H:2 * H], qkv_raw[:, 2 * H:], B, heads, d)
         a1 = ops.gemm(o, bp["wproj"], bp["bproj"], ops.EPI_BIAS)
         s_mid = ops.gate_residual(s, a1, g1, L)
         h2 = ops.rmsnorm_modulate(s_mid, bp["n2"], sh2, sc2, L)
@@ -162,7 +162,7 @@ def train_forward(module, x32, t, y):
         u = ops.swiglu_fwd(y13)
         a2 = ops.gemm(u, bp["w2"], None, ops.EPI_BIAS)
         s_out = ops.gate_residual(s_mid, a2, g2, L)
-        blocks.append(dict(s_in=s, h1=h1, qkv_raw=qkv_raw, qkv=qkv, o=o, a1=a1, s_mid=s_mid, h2=h2, y13=y13, u=u, a2=a2))
+        blocks.append(dict(s_in=s, h1=h1, qkv_raw=qkv_raw, qkv=qkv, o=o, lse=lse, a1=a1, s_mid=s_mid, h2=h2, y13=y13, u=u, a2=a2))
         s = s_out
     s2 = ops.silu_add_rows(s, temb, L)
     ycond = ops.gemm(s2, P["wcond"], P["bcond"], ops.EPI_BIAS)
@@ -262,7 +262,7 @@ def train_backward(module, S: dict, dout: torch.Tensor) -> Dict[str, torch.Tenso
         qkv = sv["qkv"]
         dqkv = torch.empty_like(qkv)
         ops.attention_bwd(qkv[:, :H], qkv[:, H:2 * H], sv["qkv_raw"][:, 2 * H:], sv["o"], do,
-                          dqkv[:, :H], dqkv[:, H:2 * H], dqkv[:, 2 * H:], B, heads, d)
+                          dqkv[:, :H], dqkv[:, H:2 * H], dqkv[:, 2 * H:], B, heads, d, lse=sv["lse"])
         ops.headnorm_rope_bwd_(dqkv, sv["qkv_raw"], 0, bp["qn"], S["pos"], dqn, heads, d, L)
         ops.headnorm_rope_bwd_(dqkv, sv["qkv_raw"], H, bp["kn"], S["pos"], dkn, heads, d, L)
         G[pre + "attn.q_norm.weight"], G[pre + "attn.k_norm.weight"] = dqn, dkn

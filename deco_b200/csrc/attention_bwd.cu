@@ -29,6 +29,7 @@ struct AttnBwdParams {
     long long q_stride, kv_stride, o_stride, do_stride, dq_stride, dkv_stride;
     int B, heads, Lq, Lk;
     float scale, scale_log2;
+    int have_lse;                              // lse2 was written by the forward (deco_attention_fwd_lse): skip pass 1
 };
 
 // 64 x DP tile of rows [row0, row0 + 64) of a [rows, stride] matrix (columns [0, D)), zero-filled outside
@@ -191,12 +192,13 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnBwdParams P)
     const float del0 = sDelta[warp * 16 + g], del1 = sDelta[warp * 16 + g + 8];
     const int nkb = (P.Lk + 63) / 64;
     // K (and, in pass 2, V) tiles stream through a 2-deep cp.async pipeline: step st = pass * nkb + kb uses buffer st & 1
-    const int total = 2 * nkb;
+    const int npass1 = P.have_lse ? 0 : nkb;
+    const int total = npass1 + nkb;
     int step = 0;
     auto issue = [&](int st) {
-        const int kb = st % nkb, bsel = st & 1;
+        const int kb = st < npass1 ? st : st - npass1, bsel = st & 1;
         load_tile_async<D>(sKb + bsel * TILE, kg, P.kv_stride, kb * 64, P.Lk);
-        if (st >= nkb) load_tile_async<D>(sVb + bsel * TILE, vg, P.kv_stride, kb * 64, P.Lk);
+        if (st >= npass1) load_tile_async<D>(sVb + bsel * TILE, vg, P.kv_stride, kb * 64, P.Lk);
         cp_async_commit();
     };
     auto acquire = [&]() {
@@ -209,7 +211,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnBwdParams P)
 
     // ---- pass 1: softmax statistics of rows g and g + 8
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-    for (int kb = 0; kb < nkb; ++kb) {
+    for (int kb = 0; kb < npass1; ++kb) {
         const __nv_bfloat16* sK = sKb + acquire() * TILE;
         float s[8][4];
         mma_a_tT<D>(s, qf, sK, lane);
@@ -237,11 +239,16 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnBwdParams P)
         m0 = n0; m1 = n1;
         release();
     }
-    const float lse0 = m0 + log2f(l0), lse1 = m1 + log2f(l1);
-    if (t == 0) {
+    float lse0 = m0 + log2f(l0), lse1 = m1 + log2f(l1);
+    {
         const int r = q0 + warp * 16 + g;
-        if (r < P.Lq) P.lse2[(long long)bh * P.Lq + r] = lse0;
-        if (r + 8 < P.Lq) P.lse2[(long long)bh * P.Lq + r + 8] = lse1;
+        if (P.have_lse) {
+            lse0 = r < P.Lq ? P.lse2[(long long)bh * P.Lq + r] : 0.f;
+            lse1 = r + 8 < P.Lq ? P.lse2[(long long)bh * P.Lq + r + 8] : 0.f;
+        } else if (t == 0) {
+            if (r < P.Lq) P.lse2[(long long)bh * P.Lq + r] = lse0;
+            if (r + 8 < P.Lq) P.lse2[(long long)bh * P.Lq + r + 8] = lse1;
+        }
     }
 
     // ---- pass 2: dQ
@@ -371,7 +378,7 @@ static int launch_attn_bwd(const AttnBwdParams& P, cudaStream_t st)
 extern "C" int deco_attention_bwd(const void* q, long long q_stride, const void* k, const void* v, long long kv_stride,
                                   const void* o, long long o_stride, const void* dout, long long do_stride,
                                   void* dq, long long dq_stride, void* dk, void* dv, long long dkv_stride,
-                                  float* lse2_ws, float* delta_ws, int B, int heads, int Lq, int Lk, int head_dim,
+                                  float* lse2_ws, float* delta_ws, int have_lse, int B, int heads, int Lq, int Lk, int head_dim,
                                   float scale, void* stream)
 {
     using namespace deco;
@@ -389,7 +396,7 @@ extern "C" int deco_attention_bwd(const void* q, long long q_stride, const void*
     P.q_stride = q_stride; P.kv_stride = kv_stride; P.o_stride = o_stride; P.do_stride = do_stride;
     P.dq_stride = dq_stride; P.dkv_stride = dkv_stride;
     P.B = B; P.heads = heads; P.Lq = Lq; P.Lk = Lk;
-    P.scale = scale; P.scale_log2 = scale * 1.4426950408889634f;
+    P.scale = scale; P.scale_log2 = scale * 1.4426950408889634f; P.have_lse = have_lse;
     if (head_dim == 72) return launch_attn_bwd<72>(P, (cudaStream_t)stream);
     if (head_dim == 64) return launch_attn_bwd<64>(P, (cudaStream_t)stream);
     deco_set_error("attention_bwd: head_dim %d not built (64, 72)", head_dim);

@@ -54,6 +54,7 @@ struct TcAttnParams {
     int Lq, heads, B;
     int Lk[2];
     float scale_log2;
+    float* lse2;             // optional [B * heads, Lq]: log2-sum-exp2 of the scaled scores per query (for the backward)
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -386,6 +387,12 @@ attention_tc_kernel(const __grid_constant__ TcAttnMaps M, const TcAttnParams P)
             mbar_arrive(o_empty(t));
             if (r == 0) ATTN_TRACE(t, 6);
             const float inv = 1.0f / l;
+            if (P.lse2) {            // softmax statistics for attention_bwd.cu: log2(sum_k exp2(c s_k)) = c m + log2(l)
+                int b_, h_, pair_;
+                decode(n, b_, h_, pair_);
+                const int qrow = pair_ * 256 + t * kTcRows + r;
+                if (qrow < P.Lq) P.lse2[((long long)b_ * P.heads + h_) * P.Lq + qrow] = fmaf(m_used, c, log2f(l));
+            }
             // staging tile: the item's last K/V stage is dead once its P V has completed (K half for tile 0, V half for
             // tile 1); dense [128][D] bf16 rows, written out by one TMA store
             const int st_last = (n * nblk + nblk - 1) % C::kKvStages;
@@ -455,11 +462,11 @@ static int launch_attention_tc(const TcAttnMaps& M, const TcAttnParams& P, cudaS
 
 }  // namespace deco
 
-extern "C" int deco_attention_fwd(const void* q, long long q_stride,
-                                  const void* k0, const void* v0, long long kv0_stride, int Lk0,
-                                  const void* k1, const void* v1, long long kv1_stride, int Lk1,
-                                  void* out, long long out_stride,
-                                  int B, int heads, int Lq, int head_dim, float scale, void* stream)
+static int attention_fwd_impl(const void* q, long long q_stride,
+                              const void* k0, const void* v0, long long kv0_stride, int Lk0,
+                              const void* k1, const void* v1, long long kv1_stride, int Lk1,
+                              void* out, long long out_stride, float* lse2_out,
+                              int B, int heads, int Lq, int head_dim, float scale, void* stream)
 {
     using namespace deco;
     DECO_CHECK_ARG(q && k0 && v0 && out, "attention: null pointer");
@@ -486,6 +493,28 @@ extern "C" int deco_attention_fwd(const void* q, long long q_stride,
     TcAttnParams P;
     P.Lq = Lq; P.heads = heads; P.B = B; P.Lk[0] = Lk0; P.Lk[1] = Lk1;
     P.scale_log2 = scale * 1.4426950408889634f;
+    P.lse2 = lse2_out;
     if (head_dim == 72) return launch_attention_tc<72>(M, P, (cudaStream_t)stream);
     return launch_attention_tc<64>(M, P, (cudaStream_t)stream);
+}
+
+extern "C" int deco_attention_fwd(const void* q, long long q_stride,
+                                  const void* k0, const void* v0, long long kv0_stride, int Lk0,
+                                  const void* k1, const void* v1, long long kv1_stride, int Lk1,
+                                  void* out, long long out_stride,
+                                  int B, int heads, int Lq, int head_dim, float scale, void* stream)
+{
+    return attention_fwd_impl(q, q_stride, k0, v0, kv0_stride, Lk0, k1, v1, kv1_stride, Lk1, out, out_stride, nullptr,
+                              B, heads, Lq, head_dim, scale, stream);
+}
+
+// Training forward: also writes lse2_out [B * heads, Lq] = log2 sum_k exp2(scale log2(e) q.k), which lets the backward
+// (deco_attention_bwd with have_lse = 1) skip rebuilding the softmax statistics.
+extern "C" int deco_attention_fwd_lse(const void* q, long long q_stride, const void* k, const void* v, long long kv_stride,
+                                      int Lk, void* out, long long out_stride, float* lse2_out,
+                                      int B, int heads, int Lq, int head_dim, float scale, void* stream)
+{
+    if (!lse2_out) { deco_set_error("attention_fwd_lse: null lse pointer"); return DECO_ERR_ARG; }
+    return attention_fwd_impl(q, q_stride, k, v, kv_stride, Lk, nullptr, nullptr, 0, 0, out, out_stride, lse2_out,
+                              B, heads, Lq, head_dim, scale, stream);
 }

@@ -501,18 +501,37 @@ def silu_bwd(z: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:
     return dz
 
 
+def attention_lse(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, heads: int, head_dim: int):
+    """attention() for the training forward: returns (out, lse2 fp32 [B*heads*Lq]) -- the softmax statistics the backward
+    would otherwise rebuild."""
+    _cuda(q, k, v)
+    Hd = heads * head_dim
+    Lq, Lk = q.shape[0] // B, k.shape[0] // B
+    assert q.dtype == bf16 and q.shape[1] == Hd and k.shape[1] == Hd and v.shape == k.shape and k.stride(0) == v.stride(0)
+    out = torch.empty((q.shape[0], Hd), dtype=bf16, device=q.device)
+    lse = torch.empty(B * heads * Lq, dtype=torch.float32, device=q.device)
+    call("deco_attention_fwd_lse", ptr(q), q.stride(0), ptr(k), ptr(v), k.stride(0), Lk, ptr(out), out.stride(0), ptr(lse),
+         B, heads, Lq, head_dim, float(head_dim) ** -0.5, _st(q))
+    return out, lse
+
+
 def attention_bwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, o: torch.Tensor, dout: torch.Tensor,
-                  dq: torch.Tensor, dk: torch.Tensor, dv: torch.Tensor, B: int, heads: int, head_dim: int) -> None:
-    """Gradients of deco_attention_fwd (one key segment) written into the strided views dq / dk / dv."""
-    _cuda(q, k, v, o, dout, dq, dk, dv)
+                  dq: torch.Tensor, dk: torch.Tensor, dv: torch.Tensor, B: int, heads: int, head_dim: int,
+                  lse: Optional[torch.Tensor] = None) -> None:
+    """Gradients of deco_attention_fwd (one key segment) written into the strided views dq / dk / dv.  lse = the forward's
+    statistics (attention_lse) or None (rebuilt here)."""
+    _cuda(q, k, v, o, dout, dq, dk, dv, lse)
     Lq, Lk = q.shape[0] // B, k.shape[0] // B
     for t in (q, k, v, o, dout, dq, dk, dv):
         assert t.dtype == bf16 and t.stride(1) == 1
     assert k.stride(0) == v.stride(0) and dk.stride(0) == dv.stride(0)
-    ws = torch.empty((2, B * heads * Lq), dtype=torch.float32, device=q.device)
+    n = B * heads * Lq
+    if lse is not None:
+        assert lse.dtype == torch.float32 and lse.is_contiguous() and lse.numel() == n
+    ws = torch.empty((2, n), dtype=torch.float32, device=q.device)
     call("deco_attention_bwd", ptr(q), q.stride(0), ptr(k), ptr(v), k.stride(0), ptr(o), o.stride(0), ptr(dout),
-         dout.stride(0), ptr(dq), dq.stride(0), ptr(dk), ptr(dv), dk.stride(0), ptr(ws[0]), ptr(ws[1]), B, heads, Lq, Lk,
-         head_dim, float(head_dim) ** -0.5, _st(q))
+         dout.stride(0), ptr(dq), dq.stride(0), ptr(dk), ptr(dv), dk.stride(0), ptr(lse if lse is not None else ws[0]),
+         ptr(ws[1]), int(lse is not None), B, heads, Lq, Lk, head_dim, float(head_dim) ** -0.5, _st(q))
 
 
 def pixel_decoder_bwd(x: torch.Tensor, ycond: torch.Tensor, dout: torch.Tensor, blob_f32: torch.Tensor,

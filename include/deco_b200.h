@@ -243,12 +243,18 @@ int deco_cond_combine_bwd(const float* dc, const void* temb_bf16, const float* t
 /* dz = dy * silu'(z)  (t_embedder.mlp[1], dit_c2i_DeCo.py:55-57) */
 int deco_silu_bwd(const void* z_bf16, const void* dy_bf16, void* dz_bf16, long long n, void* stream);
 
+/* deco_attention_fwd (one key segment) that also writes lse2_out [B*heads, Lq] = log2 sum_k exp2(scale log2(e) q.k) */
+int deco_attention_fwd_lse(const void* q, long long q_stride, const void* k, const void* v, long long kv_stride,
+                           int Lk, void* out, long long out_stride, float* lse2_out,
+                           int B, int heads, int Lq, int head_dim, float scale, void* stream);
+
 /* backward of deco_attention_fwd (single key segment): dq / dk / dv are strided views like q / k / v;
- * lse2_ws and delta_ws are fp32 workspaces of B*heads*Lq elements (csrc/attention_bwd.cu) */
+ * lse2_ws and delta_ws are fp32 buffers of B*heads*Lq elements (csrc/attention_bwd.cu); have_lse = 1: lse2_ws holds
+ * deco_attention_fwd_lse's output (the dQ kernel then skips rebuilding the softmax statistics), 0: it is scratch */
 int deco_attention_bwd(const void* q, long long q_stride, const void* k, const void* v, long long kv_stride,
                        const void* o, long long o_stride, const void* dout, long long do_stride,
                        void* dq, long long dq_stride, void* dk, void* dv, long long dkv_stride,
-                       float* lse2_ws, float* delta_ws, int B, int heads, int Lq, int Lk, int head_dim,
+                       float* lse2_ws, float* delta_ws, int have_lse, int B, int heads, int Lq, int Lk, int head_dim,
                        float scale, void* stream);
 
 /* backward of deco_pixel_decoder: dycond bf16 [B*L, p*p*32]; grad_accum = deco_decoder_train_blob_floats(R) floats in

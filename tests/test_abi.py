@@ -58,3 +58,18 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libdeco_b200.so")
     with pytest.raises(_lib.DecoLibraryError, match="no CPU or PyTorch fallback"):
         _lib.load()
+
+
+def test_backward_entry_points_validate_arguments_without_a_gpu(lib):
+    """Training-path entry points: host-only size queries and argument checks that run before any launch."""
+    assert lib.deco_decoder_train_blob_floats(3) == 1152 + 3 * 5344 + 132
+    assert lib.deco_decoder_bwd_blob_bytes(3) == 4 * (512 + 3 * 2560 + 96)
+    p = ctypes.c_void_p(16)
+    rc = lib.deco_gemm_bf16_tn(p, 8, p, 8, p, 8, 12, 8, 64, 0, 0, None)       # M not a multiple of 8
+    assert rc == -1 and b"multiples of 8" in lib.deco_last_error()
+    rc = lib.deco_pixel_decoder_bwd_tc(p, p, p, p, p, p, p, p, 1, 64, 64, 16, 32, 4, None)   # 4 res-blocks: not built
+    assert rc == -1 and b"R <= 3" in lib.deco_last_error()
+    rc = lib.deco_attention_bwd(p, 8, p, p, 8, p, 8, p, 8, p, 8, p, p, 8, p, p, 0, 1, 2, 16, 16, 48, 0.1, None)
+    assert rc == -2 and b"head_dim" in lib.deco_last_error()
+    rc = lib.deco_transpose_cast(p, 0, 8, p, 8, 4, 3, 4, None)               # odd column count
+    assert rc == -1 and b"even" in lib.deco_last_error()

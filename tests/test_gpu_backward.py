@@ -232,6 +232,16 @@ def test_attention_backward(dev, B, heads, d, L):
     for name, sl in (("dq", slice(0, H)), ("dk", slice(H, 2 * H)), ("dv", slice(2 * H, 3 * H))):
         e = rel_l2(dqkv[:, sl].float(), g[:, sl])
         assert e < 1.5e-2, (name, e)
+    # with the forward's softmax statistics (the training path): same gradients, no statistics pass in the dQ kernel
+    o2, lse = ops.attention_lse(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], B, heads, d)
+    assert torch.equal(o2, o)
+    s_ref = (q.detach() @ k.detach().transpose(-1, -2)) * d ** -0.5                    # [B, heads, L, L]
+    lse_ref = torch.logsumexp(s_ref, -1) / math.log(2.0)
+    assert rel_l2(lse.view(B, heads, L), lse_ref) < 1e-3
+    dqkv2 = torch.zeros_like(qkv)
+    ops.attention_bwd(qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:], o, do,
+                      dqkv2[:, :H], dqkv2[:, H:2 * H], dqkv2[:, 2 * H:], B, heads, d, lse=lse)
+    assert rel_l2(dqkv2.float(), g) < 1.5e-2
 
 
 def _decoder_ref(P, cfg, x, y):

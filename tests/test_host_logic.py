@@ -283,3 +283,35 @@ def test_image_sink_png_and_npz(tmp_path):
         pos += 12 + n
     raw = np.frombuffer(zlib.decompress(idat), dtype=np.uint8).reshape(16, 1 + 24 * 3)
     assert np.array_equal(raw[:, 1:].reshape(16, 24, 3), imgs[4].permute(1, 2, 0).numpy())
+
+
+def test_backward_fragment_packing_places_transposed_weights():
+    """_frag_t packs W^T for the decoder dgrad MMAs: lane (g, t) of (n-tile j, k-step s) must hold
+    W^T[n][16s + 2t (+1), 16s + 8 + 2t (+1)] with n = 8j + g, or the permuted input channel 8 (g / 2) + 2 j + g % 2."""
+    from deco_b200.autograd import _frag_t
+    for K in (32, 96):
+        wt = torch.arange(32 * K, dtype=torch.float32).reshape(32, K).to(torch.bfloat16)   # [n = inputs, k = outputs]
+        for perm in (False, True):
+            f = _frag_t(wt, perm_n=perm)
+            assert f.shape == (4, K // 16, 32, 4)
+            for j, s, lane in [(0, 0, 0), (1, 1, 5), (3, K // 16 - 1, 31), (2, 0, 18)]:
+                g, t = lane // 4, lane % 4
+                n = 8 * (g // 2) + 2 * j + g % 2 if perm else 8 * j + g
+                ks = [16 * s + 2 * t, 16 * s + 2 * t + 1, 16 * s + 8 + 2 * t, 16 * s + 9 + 2 * t]
+                assert f[j, s, lane].tolist() == [wt[n, k].item() for k in ks]
+    # every element of W^T appears exactly once
+    wt = torch.randperm(32 * 96).reshape(32, 96).to(torch.float32)
+    assert sorted(_frag_t(wt, perm_n=True).reshape(-1).tolist()) == sorted(wt.reshape(-1).tolist())
+
+
+def test_training_blobs_have_the_sizes_the_kernels_expect():
+    from deco_b200 import PixNerDiT
+    from deco_b200.autograd import pack_decoder_bwd, pack_decoder_train
+    m = PixNerDiT(in_channels=3, num_groups=2, hidden_size=144, hidden_size_x=32, num_blocks=4, num_cond_blocks=1,
+                  patch_size=16, num_classes=10)
+    blob = pack_decoder_train(m, "cpu")
+    assert blob.dtype == torch.float32 and blob.numel() == 1152 + 3 * 5344 + 132
+    # input_proj bias sits at [1120, 1152); the final layer's fourth row is padding
+    assert torch.equal(blob[1120:1152], m.dec_net.input_proj.bias.detach())
+    assert float(blob[1152 + 3 * 5344 + 96:1152 + 3 * 5344 + 128].abs().sum()) == 0.0
+    assert pack_decoder_bwd(m, "cpu").numel() == 4 * (512 + 3 * 2560 + 96)
