@@ -411,6 +411,8 @@ def run_deco(args):
         out_host = torch.empty((gbatch if world > 1 else B, 3, res, res), dtype=torch.uint8).pin_memory()
         if wl["sampler"] == "euler":    # build (capture) the uint8 variant of the graphed step outside the timed region
             sampler.graphed_stepper(net, x, cfg_cond, to_uint8=True)
+        if world > 1:                   # NCCL sets up its all-gather channels on first use: not part of a trajectory
+            D.all_gather_images(torch.zeros((B, 3, 8, 8), dtype=torch.uint8, device=dev), world)
         barrier()
         t0 = torch.cuda.Event(enable_timing=True)
         t1 = torch.cuda.Event(enable_timing=True)

@@ -29,8 +29,11 @@ def all_gather_images(local_u8: torch.Tensor, world_size: int, total: Optional[i
     index r + i * world_size."""
     if world_size == 1:
         return local_u8
-    bufs = [torch.empty_like(local_u8) for _ in range(world_size)]
-    dist.all_gather(bufs, local_u8.contiguous())
-    stacked = torch.stack(bufs, dim=1)                       # [B_local, world, ...]
-    out = stacked.reshape((-1,) + tuple(local_u8.shape[1:]))  # global order r + i*world
+    local_u8 = local_u8.contiguous()
+    gathered = torch.empty((world_size,) + tuple(local_u8.shape), dtype=local_u8.dtype, device=local_u8.device)
+    if dist.get_backend() == "nccl":
+        dist.all_gather_into_tensor(gathered, local_u8)      # one collective straight into the [world, B_local, ...] buffer
+    else:
+        dist.all_gather(list(gathered.unbind(0)), local_u8)
+    out = gathered.transpose(0, 1).reshape((-1,) + tuple(local_u8.shape[1:]))   # global order r + i*world
     return out if total is None else out[:total]
