@@ -23,6 +23,7 @@ import torch.nn as nn
 from . import ops
 
 bf16 = torch.bfloat16
+COMPOSITE_SHIFT = os.environ.get("DECO_B200_COMPOSITE_SHIFT", "1") != "0"
 
 
 # ------------------------------------------------------------------------------------------------ parameter holders
@@ -233,7 +234,8 @@ class StreamState:
 
 
 def fused_blocks(blocks, mod: torch.Tensor, mod0: int, st: StreamState, a0: torch.Tensor, w0: torch.Tensor,
-                 b0: torch.Tensor, B: int, L: int, H: int, heads: int, pos, wp: int, ytxt=None, T: int = 0):
+                 b0: torch.Tensor, B: int, L: int, H: int, heads: int, pos, wp: int, ytxt=None, T: int = 0,
+                 shw_all: Optional[torch.Tensor] = None):
     """s = a0 @ w0.T + b0, then every AdaLN block of `blocks` on the fp32 stream, with no stand-alone norm / modulate /
     q-k-norm / RoPE pass: see csrc/gemm_fused.cu.  mod [B, *] is the batched adaLN output; block i uses the six H-wide
     column groups starting at (mod0 + i) * 6H (shift, scale, gate) x (attention, MLP) (dit_c2i_DeCo.py:207).
@@ -245,11 +247,17 @@ def fused_blocks(blocks, mod: torch.Tensor, mod0: int, st: StreamState, a0: torc
         k = (mod0 + i) * 6 + j
         return mod[:, k * H:(k + 1) * H]
 
-    # shift products sh @ W^T of every block: tiny GEMMs ([B, H] x [H, N]) that depend on the modulation only
-    shw_qkv = [ops.gemm(sl(i, 0), bp["wqkv"], None, ops.EPI_BIAS_F32) for i, bp in enumerate(blocks)]
-    shw_13 = [ops.gemm(sl(i, 3), bp["w13"], None, ops.EPI_BIAS_F32) for i, bp in enumerate(blocks)]
     s, xg = st.s, st.xg
     ffn = st.u.shape[1]
+    # shift products sh @ W^T of every block ([B, H] x [H, N], functions of the modulation only): either one column slice
+    # each of shw_all (ONE GEMM against composite weights, PixNerDiT.prepare) or two tiny GEMMs per block
+    if shw_all is not None:
+        S_ = 3 * H + 2 * ffn
+        shw_qkv = [shw_all[:, i * S_:i * S_ + 3 * H] for i in range(nb)]
+        shw_13 = [shw_all[:, i * S_ + 3 * H:(i + 1) * S_] for i in range(nb)]
+    else:
+        shw_qkv = [ops.gemm(sl(i, 0), bp["wqkv"], None, ops.EPI_BIAS_F32) for i, bp in enumerate(blocks)]
+        shw_13 = [ops.gemm(sl(i, 3), bp["w13"], None, ops.EPI_BIAS_F32) for i, bp in enumerate(blocks)]
     q0 = st.ssq(0, H, a0.shape[1])      # statistics of the stream entering block 0 (producer: the embedding GEMM)
     q_attn = st.ssq(1, H, H)            # ... after the attention branch (producer: proj, K = H)
     q_mlp = st.ssq(0, H, ffn)           # ... after the MLP branch (producer: w2, K = ffn)
@@ -367,6 +375,19 @@ class PixNerDiT(nn.Module):
                                kn=Fv(b.attn.k_norm.weight), wproj=W(b.attn.proj.weight), bproj=Fv(b.attn.proj.bias),
                                n2=Fv(b.norm2.weight), w13=w13, w2=w2))
         P["blocks"] = blocks
+        if COMPOSITE_SHIFT and blocks and H % 32 == 0:
+            # shift_i . W^T = (c . Wada_shift^T + bada_shift) . W^T = c . (W . Wada_shift)^T + W . bada_shift: the 2 x nb
+            # batch-sized shift products of a forward collapse into ONE GEMM of c against these composite weights
+            # (at 8-GPU sharding the 56 tiny launches were 4 % of a step)
+            wc, bc = [], []
+            for b, bp in zip(self.blocks, blocks):
+                wa = b.adaLN_modulation[0].weight.detach().to(device=device, dtype=torch.float32)
+                ba = b.adaLN_modulation[0].bias.detach().to(device=device, dtype=torch.float32)
+                for wmat, lo in ((bp["wqkv"], 0), (bp["w13"], 3 * H)):
+                    wf = wmat.float()
+                    wc.append((wf @ wa[lo:lo + H]).to(bf16))
+                    bc.append(wf @ ba[lo:lo + H])
+            P["wshift"], P["bshift"] = torch.cat(wc, 0).contiguous(), torch.cat(bc, 0).contiguous()
         P["wcond"], P["bcond"] = W(self.dec_net.cond_embed.weight), Fv(self.dec_net.cond_embed.bias)
         P["blob"], P["postab"] = self._pack_decoder(device)
         self._prep, self._prep_key = P, key
@@ -402,7 +423,8 @@ class PixNerDiT(nn.Module):
         if nb and self.fused and H % 32 == 0:
             mod = ops.gemm(c, P["wada"], P["bada"], ops.EPI_BIAS)                   # [B, nb*6H]
             st = StreamState(B * L, H, P["ffn_pad"], xp.device)
-            s = fused_blocks(P["blocks"], mod, 0, st, xp, P["ws"], P["bs"], B, L, H, heads, pos, wp)
+            shw_all = ops.gemm(c, P["wshift"], P["bshift"], ops.EPI_BIAS_F32) if "wshift" in P else None
+            s = fused_blocks(P["blocks"], mod, 0, st, xp, P["ws"], P["bs"], B, L, H, heads, pos, wp, shw_all=shw_all)
             return ops.silu_add_rows(s, temb, L, out=st.o)
         s = ops.gemm(xp, P["ws"], P["bs"], ops.EPI_BIAS_F32)                        # [B*L, H] fp32
         if nb:
