@@ -101,47 +101,61 @@ __global__ void __launch_bounds__(256) gate_residual_kernel(const float* s, cons
 //   da = gate * ds (bf16), dgate[b] += sum_rows ds * a, dbias += sum_rows da (optional: a = x.W^T + bias)
 // Block = RB rows of one image (RB divides L); thread owns column pairs tid + 256 k.
 constexpr int kMaxPairIters = 4;   // hidden <= 2048
-__global__ void __launch_bounds__(256) gate_bwd_kernel(const float* __restrict__ ds, const __nv_bfloat16* __restrict__ a,
+// thread owns 4 consecutive columns (blockDim = ceil32(hidden / 4)): 16-byte stream loads, 8-byte bf16 loads / stores
+__global__ void __launch_bounds__(512) gate_bwd_kernel(const float* __restrict__ ds, const __nv_bfloat16* __restrict__ a,
                                                        const __nv_bfloat16* __restrict__ gate, long long gate_stride,
                                                        __nv_bfloat16* __restrict__ da, float* __restrict__ dgate,
-                                                       long long dgate_stride, float* __restrict__ dbias,
+                                                       long long dgate_stride, float* __restrict__ usum,
                                                        int L, int RB, int Hd)
 {
+    // usum [B, Hd] (optional): per-image column sums of ds, from which gate_bias_finalize_kernel forms the bias gradient
+    // sum_b gate[b] * usum[b] -- adding every block's partial straight into dbias[Hd] put 1024 atomics on each of 1152
+    // addresses and tripled the kernel time (19.9 -> 54.5 us)
+    const int c = 4 * threadIdx.x;
+    if (c >= Hd) return;
     const long long r0 = (long long)blockIdx.x * RB;
     const long long b = r0 / L;
-    const int npair = Hd >> 1;
-    float2 g[kMaxPairIters], accg[kMaxPairIters], accb[kMaxPairIters];
-#pragma unroll
-    for (int k = 0; k < kMaxPairIters; ++k) {
-        const int p = threadIdx.x + k * 256;
-        g[k] = p < npair ? Pair<__nv_bfloat16>::ld(gate + b * gate_stride + 2 * p) : make_float2(0.f, 0.f);
-        accg[k] = make_float2(0.f, 0.f);
-        accb[k] = make_float2(0.f, 0.f);
+    float g[4];
+    {
+        const uint2 q = *reinterpret_cast<const uint2*>(gate + b * gate_stride + c);
+        const float2 g0 = unpack_bf2(q.x), g1 = unpack_bf2(q.y);
+        g[0] = g0.x; g[1] = g0.y; g[2] = g1.x; g[3] = g1.y;
     }
+    float accg[4] = {0.f, 0.f, 0.f, 0.f}, accb[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 4
     for (int i = 0; i < RB; ++i) {
         const long long r = r0 + i;
-#pragma unroll
-        for (int k = 0; k < kMaxPairIters; ++k) {
-            const int p = threadIdx.x + k * 256;
-            if (p < npair) {
-                const float2 d = *reinterpret_cast<const float2*>(ds + r * Hd + 2 * p);
-                const float2 av = Pair<__nv_bfloat16>::ld(a + r * Hd + 2 * p);
-                const float2 o = make_float2(g[k].x * d.x, g[k].y * d.y);
-                *reinterpret_cast<uint32_t*>(da + r * Hd + 2 * p) = pack_bf2(o.x, o.y);
-                accg[k].x = fmaf(d.x, av.x, accg[k].x); accg[k].y = fmaf(d.y, av.y, accg[k].y);
-                accb[k].x += o.x; accb[k].y += o.y;
-            }
-        }
+        const float4 d = *reinterpret_cast<const float4*>(ds + r * Hd + c);
+        const uint2 q = *reinterpret_cast<const uint2*>(a + r * Hd + c);
+        const float2 a0 = unpack_bf2(q.x), a1 = unpack_bf2(q.y);
+        const float o0 = g[0] * d.x, o1 = g[1] * d.y, o2 = g[2] * d.z, o3 = g[3] * d.w;
+        *reinterpret_cast<uint2*>(da + r * Hd + c) = make_uint2(pack_bf2(o0, o1), pack_bf2(o2, o3));
+        accg[0] = fmaf(d.x, a0.x, accg[0]); accg[1] = fmaf(d.y, a0.y, accg[1]);
+        accg[2] = fmaf(d.z, a1.x, accg[2]); accg[3] = fmaf(d.w, a1.y, accg[3]);
+        accb[0] += d.x; accb[1] += d.y; accb[2] += d.z; accb[3] += d.w;
     }
 #pragma unroll
-    for (int k = 0; k < kMaxPairIters; ++k) {
-        const int p = threadIdx.x + k * 256;
-        if (p < npair) {
-            atomicAdd(dgate + b * dgate_stride + 2 * p, accg[k].x);
-            atomicAdd(dgate + b * dgate_stride + 2 * p + 1, accg[k].y);
-            if (dbias) { atomicAdd(dbias + 2 * p, accb[k].x); atomicAdd(dbias + 2 * p + 1, accb[k].y); }
-        }
+    for (int e = 0; e < 4; ++e) {
+        atomicAdd(dgate + b * dgate_stride + c + e, accg[e]);
+        if (usum) atomicAdd(usum + b * Hd + c + e, accb[e]);
+    }
+}
+
+// dbias[c] += sum_b gate[b][c] * usum[b][c];  block = 32 columns x 32 image lanes
+__global__ void __launch_bounds__(1024) gate_bias_finalize_kernel(const __nv_bfloat16* __restrict__ gate, long long gate_stride,
+                                                                  const float* __restrict__ usum, float* __restrict__ dbias,
+                                                                  int B, int Hd)
+{
+    __shared__ float red[32][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    float acc = 0.f;
+    if (c < Hd)
+        for (int b = threadIdx.y; b < B; b += 32) acc = fmaf(bf2f(gate[b * gate_stride + c]), usum[(size_t)b * Hd + c], acc);
+    red[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < Hd) {
+        for (int j = 1; j < 32; ++j) acc += red[j][threadIdx.x];
+        dbias[c] += acc;
     }
 }
 
@@ -231,101 +245,111 @@ __global__ void __launch_bounds__(256) swiglu_kernel(const __nv_bfloat16* __rest
 // ---------------------------------------------------------------- backward of h = rms(x) * w * (1 + scale[b]) + shift[b]
 //   dxh = dh * w * (1 + scale);  dx = r * dxh - x * r^3 * mean(dxh * x);  ds += dx   (the residual stream gradient)
 //   dshift[b] += sum_rows dh;  dscale[b] += sum_rows dh * xhat * w;  dw += sum_rows dh * xhat * (1 + scale)
-// One WARP per row (lane owns float4 chunks lane + 32 k, row statistics by shuffles, no block barrier per row); a block =
-// 4 warps = RB rows of one image; the column sums live in registers until the block's rows are done, then go through
-// shared memory to one global atomic per column per block.
+// Two streaming passes instead of one latency-bound one: (1) a warp per row reduces the two row scalars r and
+// k2 = r^3 mean(dxh x) (low register count, full occupancy); (2) a thread per 4 columns applies them, updates ds in place and
+// keeps the per-image column sums in registers (no row reduction left, so no barrier or shuffle in the loop).
 template <int NV>
-__global__ void __launch_bounds__(128) rmsnorm_modulate_bwd_kernel(
+__global__ void __launch_bounds__(256) rmsnorm_bwd_rowstats_kernel(
     const __nv_bfloat16* __restrict__ dh, const float* __restrict__ x, const float* __restrict__ w,
-    const __nv_bfloat16* __restrict__ scale, long long mod_stride, float* __restrict__ ds,
-    float* __restrict__ dw, float* __restrict__ dshift, float* __restrict__ dscale, long long dmod_stride,
-    int L, int RB, int Hd, float eps)
+    const __nv_bfloat16* __restrict__ scale, long long mod_stride, float2* __restrict__ stats, int L, long long M, int Hd, float eps)
 {
-    extern __shared__ float scol[];                 // [3][Hd]
-    const long long r0 = (long long)blockIdx.x * RB;
-    const long long b = r0 / L;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < 3 * Hd; i += blockDim.x) scol[i] = 0.f;
-    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= M) return;
+    const __nv_bfloat16* srow = scale + (r / L) * mod_stride;
     const int nch = Hd >> 2;
-    float4 a_sh[NV], a_sc[NV], a_w[NV];
-#pragma unroll
-    for (int k = 0; k < NV; ++k) {
-        a_sh[k] = make_float4(0.f, 0.f, 0.f, 0.f); a_sc[k] = a_sh[k]; a_w[k] = a_sh[k];
-    }
-    const __nv_bfloat16* srow = scale + b * mod_stride;
-    for (int i = warp; i < RB; i += 4) {
-        const long long r = r0 + i;
-        float4 xv[NV], dv[NV];
-        float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-        for (int k = 0; k < NV; ++k) {
-            const int c = lane + 32 * k;
-            if (c < nch) {
-                xv[k] = *reinterpret_cast<const float4*>(x + r * Hd + 4 * c);
-                const uint2 d2 = *reinterpret_cast<const uint2*>(dh + r * Hd + 4 * c);
-                const float2 d0 = unpack_bf2(d2.x), d1 = unpack_bf2(d2.y);
-                dv[k] = make_float4(d0.x, d0.y, d1.x, d1.y);
-            } else {
-                xv[k] = make_float4(0.f, 0.f, 0.f, 0.f); dv[k] = xv[k];
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < NV; ++k) {
-            const int c = lane + 32 * k;
-            if (c < nch) {
-                const float4 w4 = __ldg(reinterpret_cast<const float4*>(w + 4 * c));
-                const uint2 q = __ldg(reinterpret_cast<const uint2*>(srow + 4 * c));
-                const float2 q0 = unpack_bf2(q.x), q1 = unpack_bf2(q.y);
-                // dv <- dxh = dh * w * (1 + scale); the plain dh is recovered below as dxh / (w (1 + scale)) is avoided by
-                // accumulating the dh-based sums first
-                a_sh[k].x += dv[k].x; a_sh[k].y += dv[k].y; a_sh[k].z += dv[k].z; a_sh[k].w += dv[k].w;
-                s1 = fmaf(xv[k].x, xv[k].x, fmaf(xv[k].y, xv[k].y, fmaf(xv[k].z, xv[k].z, fmaf(xv[k].w, xv[k].w, s1))));
-                const float4 m4 = make_float4(w4.x * (1.0f + q0.x), w4.y * (1.0f + q0.y), w4.z * (1.0f + q1.x), w4.w * (1.0f + q1.y));
-                s2 = fmaf(dv[k].x * m4.x, xv[k].x, fmaf(dv[k].y * m4.y, xv[k].y, fmaf(dv[k].z * m4.z, xv[k].z, fmaf(dv[k].w * m4.w, xv[k].w, s2))));
-            }
-        }
-        s1 = warp_sum(s1); s2 = warp_sum(s2);
-        const float rs = rsqrtf(s1 / (float)Hd + eps);
-        const float k2 = rs * rs * rs * s2 / (float)Hd;
-#pragma unroll
-        for (int k = 0; k < NV; ++k) {
-            const int c = lane + 32 * k;
-            if (c < nch) {
-                const float4 w4 = __ldg(reinterpret_cast<const float4*>(w + 4 * c));
-                const uint2 q = __ldg(reinterpret_cast<const uint2*>(srow + 4 * c));
-                const float2 q0 = unpack_bf2(q.x), q1 = unpack_bf2(q.y);
-                const float4 sc1 = make_float4(1.0f + q0.x, 1.0f + q0.y, 1.0f + q1.x, 1.0f + q1.y);
-                float4* dp = reinterpret_cast<float4*>(ds + r * Hd + 4 * c);
-                float4 d4 = *dp;
-                d4.x += rs * dv[k].x * w4.x * sc1.x - xv[k].x * k2; d4.y += rs * dv[k].y * w4.y * sc1.y - xv[k].y * k2;
-                d4.z += rs * dv[k].z * w4.z * sc1.z - xv[k].z * k2; d4.w += rs * dv[k].w * w4.w * sc1.w - xv[k].w * k2;
-                *dp = d4;
-                const float4 xh = make_float4(xv[k].x * rs, xv[k].y * rs, xv[k].z * rs, xv[k].w * rs);
-                a_sc[k].x = fmaf(dv[k].x * xh.x, w4.x, a_sc[k].x); a_sc[k].y = fmaf(dv[k].y * xh.y, w4.y, a_sc[k].y);
-                a_sc[k].z = fmaf(dv[k].z * xh.z, w4.z, a_sc[k].z); a_sc[k].w = fmaf(dv[k].w * xh.w, w4.w, a_sc[k].w);
-                a_w[k].x = fmaf(dv[k].x * xh.x, sc1.x, a_w[k].x); a_w[k].y = fmaf(dv[k].y * xh.y, sc1.y, a_w[k].y);
-                a_w[k].z = fmaf(dv[k].z * xh.z, sc1.z, a_w[k].z); a_w[k].w = fmaf(dv[k].w * xh.w, sc1.w, a_w[k].w);
-            }
-        }
-    }
+    float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
         const int c = lane + 32 * k;
         if (c < nch) {
-            float* p = scol + 4 * c;
-            atomicAdd(p, a_sh[k].x); atomicAdd(p + 1, a_sh[k].y); atomicAdd(p + 2, a_sh[k].z); atomicAdd(p + 3, a_sh[k].w);
-            p += Hd;
-            atomicAdd(p, a_sc[k].x); atomicAdd(p + 1, a_sc[k].y); atomicAdd(p + 2, a_sc[k].z); atomicAdd(p + 3, a_sc[k].w);
-            p += Hd;
-            atomicAdd(p, a_w[k].x); atomicAdd(p + 1, a_w[k].y); atomicAdd(p + 2, a_w[k].z); atomicAdd(p + 3, a_w[k].w);
+            const float4 xv = *reinterpret_cast<const float4*>(x + r * Hd + 4 * c);
+            const uint2 d2 = *reinterpret_cast<const uint2*>(dh + r * Hd + 4 * c);
+            const float4 w4 = __ldg(reinterpret_cast<const float4*>(w + 4 * c));
+            const uint2 q = __ldg(reinterpret_cast<const uint2*>(srow + 4 * c));
+            const float2 d0 = unpack_bf2(d2.x), d1 = unpack_bf2(d2.y), q0 = unpack_bf2(q.x), q1 = unpack_bf2(q.y);
+            s1 = fmaf(xv.x, xv.x, fmaf(xv.y, xv.y, fmaf(xv.z, xv.z, fmaf(xv.w, xv.w, s1))));
+            s2 = fmaf(d0.x * w4.x * (1.0f + q0.x), xv.x, fmaf(d0.y * w4.y * (1.0f + q0.y), xv.y,
+                 fmaf(d1.x * w4.z * (1.0f + q1.x), xv.z, fmaf(d1.y * w4.w * (1.0f + q1.y), xv.w, s2))));
         }
     }
+    s1 = warp_sum(s1); s2 = warp_sum(s2);
+    if (lane == 0) {
+        const float rs = rsqrtf(s1 / (float)Hd + eps);
+        stats[r] = make_float2(rs, rs * rs * rs * s2 / (float)Hd);
+    }
+}
+
+__global__ void __launch_bounds__(512) rmsnorm_modulate_bwd_kernel(
+    const __nv_bfloat16* __restrict__ dh, const float* __restrict__ x, const float* __restrict__ w,
+    const __nv_bfloat16* __restrict__ scale, long long mod_stride, const float2* __restrict__ stats, float* __restrict__ ds,
+    float* __restrict__ tsum, float* __restrict__ dshift, long long dmod_stride,
+    int L, int RB, int Hd)
+{
+    // tsum [B, Hd]: per-image sums T = sum_rows dh * xhat; d scale = w * T and d w = sum_b (1 + scale[b]) * T are formed
+    // by rmsnorm_bwd_finalize_kernel (one atomic target per (image, column) instead of 1024 blocks hammering dw[Hd])
+    const int c = 4 * threadIdx.x;
+    if (c >= Hd) return;
+    const long long r0 = (long long)blockIdx.x * RB;
+    const long long b = r0 / L;
+    float wv[4], sc1[4];
+    {
+        const float4 w4 = __ldg(reinterpret_cast<const float4*>(w + c));
+        wv[0] = w4.x; wv[1] = w4.y; wv[2] = w4.z; wv[3] = w4.w;
+        const uint2 q = *reinterpret_cast<const uint2*>(scale + b * mod_stride + c);
+        const float2 q0 = unpack_bf2(q.x), q1 = unpack_bf2(q.y);
+        sc1[0] = 1.0f + q0.x; sc1[1] = 1.0f + q0.y; sc1[2] = 1.0f + q1.x; sc1[3] = 1.0f + q1.y;
+    }
+    float a_sh[4] = {0.f, 0.f, 0.f, 0.f}, a_t[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int i = 0; i < RB; ++i) {
+        const long long r = r0 + i;
+        const float2 st = __ldg(stats + r);
+        const float4 x4 = *reinterpret_cast<const float4*>(x + r * Hd + c);
+        const uint2 d2 = *reinterpret_cast<const uint2*>(dh + r * Hd + c);
+        float4* dp = reinterpret_cast<float4*>(ds + r * Hd + c);
+        float4 d4 = *dp;
+        const float2 d0 = unpack_bf2(d2.x), d1 = unpack_bf2(d2.y);
+        const float xv[4] = {x4.x, x4.y, x4.z, x4.w}, dv[4] = {d0.x, d0.y, d1.x, d1.y};
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            o[e] = st.x * dv[e] * wv[e] * sc1[e] - xv[e] * st.y;
+            a_sh[e] += dv[e];
+            a_t[e] = fmaf(dv[e] * xv[e], st.x, a_t[e]);
+        }
+        d4.x += o[0]; d4.y += o[1]; d4.z += o[2]; d4.w += o[3];
+        *dp = d4;
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        atomicAdd(dshift + b * dmod_stride + c + e, a_sh[e]);
+        atomicAdd(tsum + b * Hd + c + e, a_t[e]);
+    }
+}
+
+// dscale[b][c] += w[c] * T[b][c];  dw[c] += sum_b (1 + scale[b][c]) * T[b][c];  block = 32 columns x 32 image lanes
+__global__ void __launch_bounds__(1024) rmsnorm_bwd_finalize_kernel(const float* __restrict__ tsum, const float* __restrict__ w,
+                                                                    const __nv_bfloat16* __restrict__ scale, long long mod_stride,
+                                                                    float* __restrict__ dscale, long long dmod_stride,
+                                                                    float* __restrict__ dw, int B, int Hd)
+{
+    __shared__ float red[32][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    float acc = 0.f;
+    if (c < Hd) {
+        const float wc = __ldg(w + c);
+        for (int b = threadIdx.y; b < B; b += 32) {
+            const float t = tsum[(size_t)b * Hd + c];
+            dscale[b * dmod_stride + c] += wc * t;
+            acc = fmaf(1.0f + bf2f(scale[b * mod_stride + c]), t, acc);
+        }
+    }
+    red[threadIdx.y][threadIdx.x] = acc;
     __syncthreads();
-    for (int i = threadIdx.x; i < Hd; i += blockDim.x) {
-        atomicAdd(dshift + b * dmod_stride + i, scol[i]);
-        atomicAdd(dscale + b * dmod_stride + i, scol[Hd + i]);
-        atomicAdd(dw + i, scol[2 * Hd + i]);
+    if (threadIdx.y == 0 && c < Hd) {
+        for (int j = 1; j < 32; ++j) acc += red[j][threadIdx.x];
+        dw[c] += acc;
     }
 }
 
@@ -484,18 +508,24 @@ extern "C" int deco_gate_residual(const float* s, const void* a_bf16, const void
 }
 
 extern "C" int deco_gate_bwd(const float* ds, const void* a_bf16, const void* gate_bf16, long long gate_stride,
-                             void* da_bf16, float* dgate_accum, long long dgate_stride, float* dbias_accum,
+                             void* da_bf16, float* dgate_accum, long long dgate_stride, float* dbias_accum, float* img_ws,
                              int rows_per_image, long long M, int hidden, void* stream)
 {
     using namespace deco;
     DECO_CHECK_ARG(ds && a_bf16 && gate_bf16 && da_bf16 && dgate_accum, "gate_bwd: null pointer");
-    DECO_CHECK_ARG(M > 0 && hidden > 0 && hidden % 2 == 0 && hidden <= 512 * kMaxPairIters && rows_per_image > 0 &&
-                   M % rows_per_image == 0 && gate_stride % 2 == 0, "gate_bwd: bad shape M=%lld hidden=%d L=%d", M, hidden, rows_per_image);
+    DECO_CHECK_ARG(!dbias_accum || img_ws, "gate_bwd: the bias gradient needs the zeroed [B, hidden] workspace");
+    DECO_CHECK_ARG(M > 0 && hidden > 0 && hidden % 4 == 0 && hidden <= 2048 && rows_per_image > 0 &&
+                   M % rows_per_image == 0 && gate_stride % 4 == 0, "gate_bwd: bad shape M=%lld hidden=%d L=%d", M, hidden, rows_per_image);
     const int rb = rows_block(rows_per_image, M);
-    gate_bwd_kernel<<<(unsigned)(M / rb), 256, 0, (cudaStream_t)stream>>>(
+    gate_bwd_kernel<<<(unsigned)(M / rb), ((hidden / 4) + 31) / 32 * 32, 0, (cudaStream_t)stream>>>(
         ds, (const __nv_bfloat16*)a_bf16, (const __nv_bfloat16*)gate_bf16, gate_stride, (__nv_bfloat16*)da_bf16,
-        dgate_accum, dgate_stride, dbias_accum, rows_per_image, rb, hidden);
+        dgate_accum, dgate_stride, dbias_accum ? img_ws : nullptr, rows_per_image, rb, hidden);
     DECO_CHECK_LAUNCH("gate_bwd_kernel");
+    if (dbias_accum) {
+        gate_bias_finalize_kernel<<<(hidden + 31) / 32, dim3(32, 32), 0, (cudaStream_t)stream>>>(
+            (const __nv_bfloat16*)gate_bf16, gate_stride, img_ws, dbias_accum, (int)(M / rows_per_image), hidden);
+        DECO_CHECK_LAUNCH("gate_bias_finalize_kernel");
+    }
     return DECO_OK;
 }
 
@@ -537,29 +567,33 @@ extern "C" int deco_swiglu_bwd(const void* y13_bf16, const void* du_bf16, void* 
 extern "C" int deco_rmsnorm_modulate_bwd(const void* dh_bf16, const float* x, const float* weight, const void* scale_bf16,
                                          long long mod_row_stride, float* ds_accum, float* dweight_accum,
                                          float* dshift_accum, float* dscale_accum, long long dmod_row_stride,
-                                         int rows_per_image, long long M, int hidden, float eps, void* stream)
+                                         float* row_ws, float* img_ws, int rows_per_image, long long M, int hidden, float eps,
+                                         void* stream)
 {
     using namespace deco;
-    DECO_CHECK_ARG(dh_bf16 && x && weight && scale_bf16 && ds_accum && dweight_accum && dshift_accum && dscale_accum,
-                   "rmsnorm_modulate_bwd: null pointer");
+    DECO_CHECK_ARG(dh_bf16 && x && weight && scale_bf16 && ds_accum && dweight_accum && dshift_accum && dscale_accum && row_ws &&
+                   img_ws, "rmsnorm_modulate_bwd: null pointer");
     DECO_CHECK_ARG(M > 0 && hidden > 0 && hidden % 4 == 0 && hidden <= 2048 && rows_per_image > 0 &&
-                   M % rows_per_image == 0 && mod_row_stride % 4 == 0, "rmsnorm_modulate_bwd: bad shape");
-    const int rb = rows_block(rows_per_image, M, 1);     // register-resident column sums: long row runs, one wave of CTAs
-    const unsigned grid = (unsigned)(M / rb);
-    const int smem = 3 * hidden * 4;
+                   M % rows_per_image == 0 && mod_row_stride % 4 == 0 && ((uintptr_t)row_ws & 7) == 0,
+                   "rmsnorm_modulate_bwd: bad shape");
     const __nv_bfloat16* dhp = (const __nv_bfloat16*)dh_bf16;
     const __nv_bfloat16* scp = (const __nv_bfloat16*)scale_bf16;
+    float2* stats = reinterpret_cast<float2*>(row_ws);
     cudaStream_t st = (cudaStream_t)stream;
-    if (hidden <= 512)
-        rmsnorm_modulate_bwd_kernel<4><<<grid, 128, smem, st>>>(dhp, x, weight, scp, mod_row_stride, ds_accum, dweight_accum,
-                                                                 dshift_accum, dscale_accum, dmod_row_stride, rows_per_image, rb, hidden, eps);
-    else if (hidden <= 1152)
-        rmsnorm_modulate_bwd_kernel<9><<<grid, 128, smem, st>>>(dhp, x, weight, scp, mod_row_stride, ds_accum, dweight_accum,
-                                                                 dshift_accum, dscale_accum, dmod_row_stride, rows_per_image, rb, hidden, eps);
+    const unsigned g1 = (unsigned)((M + 7) / 8);
+    if (hidden <= 1024)
+        rmsnorm_bwd_rowstats_kernel<8><<<g1, 256, 0, st>>>(dhp, x, weight, scp, mod_row_stride, stats, rows_per_image, M, hidden, eps);
     else
-        rmsnorm_modulate_bwd_kernel<16><<<grid, 128, smem, st>>>(dhp, x, weight, scp, mod_row_stride, ds_accum, dweight_accum,
-                                                                  dshift_accum, dscale_accum, dmod_row_stride, rows_per_image, rb, hidden, eps);
+        rmsnorm_bwd_rowstats_kernel<16><<<g1, 256, 0, st>>>(dhp, x, weight, scp, mod_row_stride, stats, rows_per_image, M, hidden, eps);
+    DECO_CHECK_LAUNCH("rmsnorm_bwd_rowstats_kernel");
+    const int rb = rows_block(rows_per_image, M);
+    rmsnorm_modulate_bwd_kernel<<<(unsigned)(M / rb), ((hidden / 4) + 31) / 32 * 32, 0, st>>>(
+        dhp, x, weight, scp, mod_row_stride, stats, ds_accum, img_ws, dshift_accum, dmod_row_stride, rows_per_image, rb, hidden);
     DECO_CHECK_LAUNCH("rmsnorm_modulate_bwd_kernel");
+    rmsnorm_bwd_finalize_kernel<<<(hidden + 31) / 32, dim3(32, 32), 0, st>>>(img_ws, weight, scp, mod_row_stride, dscale_accum,
+                                                                       dmod_row_stride, dweight_accum,
+                                                                       (int)(M / rows_per_image), hidden);
+    DECO_CHECK_LAUNCH("rmsnorm_bwd_finalize_kernel");
     return DECO_OK;
 }
 

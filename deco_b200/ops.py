@@ -424,8 +424,9 @@ def gate_bwd(ds: torch.Tensor, a: torch.Tensor, gate: torch.Tensor, dgate: torch
     assert ds.dtype == torch.float32 and ds.is_contiguous() and a.dtype == bf16 and a.is_contiguous() and a.shape == ds.shape
     assert gate.dtype == bf16 and gate.stride(1) == 1 and dgate.dtype == torch.float32 and dgate.stride(1) == 1
     da = torch.empty_like(a)
+    ws = torch.zeros((ds.shape[0] // L, ds.shape[1]), dtype=torch.float32, device=ds.device) if dbias is not None else None
     call("deco_gate_bwd", ptr(ds), ptr(a), ptr(gate), gate.stride(0), ptr(da), ptr(dgate), dgate.stride(0), ptr(dbias),
-         L, ds.shape[0], ds.shape[1], _st(ds))
+         ptr(ws), L, ds.shape[0], ds.shape[1], _st(ds))
     return da
 
 
@@ -467,8 +468,10 @@ def rmsnorm_modulate_bwd_(ds: torch.Tensor, dh: torch.Tensor, x: torch.Tensor, w
     assert dh.dtype == bf16 and dh.is_contiguous() and dh.shape == x.shape == ds.shape
     assert scale.dtype == bf16 and scale.stride(1) == 1
     assert dshift.dtype == torch.float32 and dshift.stride(1) == 1 and dshift.stride(0) == dscale.stride(0)
+    ws = torch.empty(2 * x.shape[0], dtype=torch.float32, device=x.device)     # per-row (rstd, k2) of the first pass
+    iws = torch.zeros((x.shape[0] // L, x.shape[1]), dtype=torch.float32, device=x.device)   # per-image partial sums
     call("deco_rmsnorm_modulate_bwd", ptr(dh), ptr(x), ptr(weight), ptr(scale), scale.stride(0), ptr(ds), ptr(dweight),
-         ptr(dshift), ptr(dscale), dshift.stride(0), L, x.shape[0], x.shape[1], float(eps), _st(x))
+         ptr(dshift), ptr(dscale), dshift.stride(0), ptr(ws), ptr(iws), L, x.shape[0], x.shape[1], float(eps), _st(x))
     return ds
 
 

@@ -206,9 +206,10 @@ int deco_colsum(const void* x, int x_is_f32, long long ldx, float* out_accum, lo
 int deco_gate_residual(const float* s, const void* a_bf16, const void* gate_bf16, long long gate_stride,
                        float* out, int rows_per_image, long long M, int hidden, void* stream);
 
-/* backward of the above: da = gate * ds (bf16); dgate[b,:] += sum_rows ds * a; dbias += sum_rows da (may be NULL) */
+/* backward of the above: da = gate * ds (bf16); dgate[b,:] += sum_rows ds * a; dbias += sum_rows da (may be NULL; else
+ * img_ws = ZEROED fp32 [B, hidden] scratch for the per-image partial sums) */
 int deco_gate_bwd(const float* ds, const void* a_bf16, const void* gate_bf16, long long gate_stride,
-                  void* da_bf16, float* dgate_accum, long long dgate_stride, float* dbias_accum,
+                  void* da_bf16, float* dgate_accum, long long dgate_stride, float* dbias_accum, float* img_ws,
                   int rows_per_image, long long M, int hidden, void* stream);
 
 /* backward of out = silu(x + row[b]) (dit_c2i_DeCo.py:499): dx = dout * silu'(x + row) (fp32, written);
@@ -222,11 +223,13 @@ int deco_swiglu_fwd(const void* y13_bf16, void* u_bf16, long long M, int ffn_pad
 int deco_swiglu_bwd(const void* y13_bf16, const void* du_bf16, void* dy13_bf16, long long M, int ffn_pad, void* stream);
 
 /* backward of deco_rmsnorm_modulate on the fp32 stream (dit_c2i_DeCo.py:94-99, :11-12): ds_accum[m,:] += d x;
- * dweight_accum[hidden], dshift_accum / dscale_accum [B, dmod_row_stride] */
+ * dweight_accum[hidden], dshift_accum / dscale_accum [B, dmod_row_stride]; row_ws = 2*M floats of scratch (8-byte aligned)
+ * for the per-row scalars of the first pass; img_ws = ZEROED fp32 [B, hidden] scratch for per-image partial sums */
 int deco_rmsnorm_modulate_bwd(const void* dh_bf16, const float* x, const float* weight, const void* scale_bf16,
                               long long mod_row_stride, float* ds_accum, float* dweight_accum,
                               float* dshift_accum, float* dscale_accum, long long dmod_row_stride,
-                              int rows_per_image, long long M, int hidden, float eps, void* stream);
+                              float* row_ws, float* img_ws, int rows_per_image, long long M, int hidden, float eps,
+                              void* stream);
 
 /* backward of per-head RMSNorm (+ RoPE when rope_cos_sin != NULL) for one segment (dit_c2i_DeCo.py:178-180, :134-145):
  * g [M, g_stride] holds d(out) at columns [col, col + heads*head_dim) on entry and d(raw) on exit; raw = the QKV GEMM

@@ -296,9 +296,7 @@ def test_pixel_decoder_backward(dev, B, res, variant):
         dy, gdec = ops.pixel_decoder_bwd_tc(x, ycond, dout, prep["blob"], T["dec_bwd_blob"], prep["postab"], 16, 32, 3)
     e = rel_l2(dy.float().view(B * L, 256, 32), ya.grad)
     assert e < 1.5e-2, e
-    # parameter gradients via the module-level mapping
-    from deco_b200 import autograd as A
-    S = dict(x32=x, ycond=ycond, B=B, L=L)
+    # parameter gradients, read out of the blob layout (csrc/decoder_bwd.cu) the way deco_b200/autograd.py does
 
     def chk(name, got, tol=1.5e-2):
         err = rel_l2(got, Pr[name].grad)
@@ -323,7 +321,6 @@ def test_pixel_decoder_backward(dev, B, res, variant):
     chk("x_embedder.embedder.0.weight", torch.cat([gdec[0:96].view(32, 3),
         ops.gemm(ops.transpose_cast(gdec[T["dec_blob"].numel():].view(256, 32)), T["tabT"], None, ops.EPI_BIAS_F32)], 1), 2e-2)
     chk("x_embedder.embedder.0.bias", gdec[T["dec_blob"].numel():].view(256, 32).sum(0))
-    assert A is not None and S is not None
 
 
 def _grad_check(dev, cfg, B, res, tol):

@@ -291,3 +291,40 @@ def test_graphed_sampling_step_equals_eager_loop(cuda_dev, monkeypatch):
     se = EulerSampler(**kw)
     xe, ue = se.sample_uint8(m, noise, cond, unc)
     assert torch.equal(xg, xe) and torch.equal(ug, ue) and torch.equal(xg2, xe)
+
+
+def test_step_time_vs_pytorch_eager_on_the_same_gpu(cuda_dev):
+    """Not a parity test: times one CFG-batched XL/16 denoiser step (64 rows of 256 x 256 = the 8-GPU shard of BASELINE
+    configs[1]) through deco_b200 and through the oracle's plain PyTorch ops under bf16 autocast -- the numerics and library
+    kernels (cuBLAS, SDPA, eager element-wise) the reference runs on a GPU -- on the same device, and prints both.  The
+    assertion is deliberately loose (the hand-written path must not be slower)."""
+    cfg = O.CFG_XL
+    m, P = build_module(cfg, cuda_dev)
+    Pd = {k: v.to(cuda_dev) for k, v in P.items()}
+    B2 = 64
+    x = torch.randn(B2, 3, 256, 256, device=cuda_dev)
+    t = torch.full((B2,), 0.4, device=cuda_dev)
+    y = torch.randint(0, 1001, (B2,), device=cuda_dev)
+
+    def timed(fn, iters):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    with torch.no_grad():
+        ours = timed(lambda: m(x, t, y), 5)
+
+        def eager():
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                return O.denoiser_forward(Pd, cfg, x, t, y)
+        ref = timed(eager, 3)
+    print(f"XL/16 step, 64 CFG rows: deco_b200 {ours:.2f} ms, PyTorch eager bf16-autocast (reference numerics) {ref:.2f} ms, "
+          f"ratio {ref / ours:.2f}x")
+    assert ours < ref
