@@ -598,6 +598,37 @@ def run_train(args):
         e2e = dict(value=B * world / (ms * 1e-3), unit=UNIT, h2d_bytes_per_step=B * 3 * res * res * 4 + B * 8,
                    d2h_bytes_per_step=4, ms_per_step=ms, loss=float(loss_host),
                    note="trainer(net, ...) + backward per step with pinned host images/labels copied in and the loss read back")
+    # optimizer tail (not part of `value`: BASELINE configs[3] names forward + backward): the fused AdamW + EMA kernel
+    # alone, and a full iteration = step + optimizer + re-preparation of the bf16 / packed weights the next forward needs
+    from deco_b200 import FusedAdamWEMA
+    ema = [p.detach().clone() for p in params]
+    opt = FusedAdamWEMA(params, ema, lr=1e-4, weight_decay=0.0, ema_decay=0.9999)
+    opt.step()
+    barrier()
+    o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    o0.record()
+    for _ in range(5):
+        opt.step()
+    o1.record()
+    barrier()
+    opt_ms = o0.elapsed_time(o1) / 5
+    nparam = sum(p.numel() for p in params)
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    step(xd[0], yd[0]); opt.step()
+    barrier()
+    f0.record()
+    for i in range(3):
+        step(xd[i % nbuf], yd[i % nbuf])
+        opt.step()
+    f1.record()
+    barrier()
+    full_ms = f0.elapsed_time(f1) / 3
+    optimizer = dict(kernel="adamw_ema_kernel (fused multi-tensor AdamW + EMA)", ms=opt_ms, parameters=nparam,
+                     algorithmic_bytes=36.0 * nparam, achieved=36.0 * nparam / (opt_ms * 1e-3) / 1e9,
+                     peak=measured_peaks()["hbm_gbs"], unit="GB/s",
+                     frac=36.0 * nparam / (opt_ms * 1e-3) / 1e9 / measured_peaks()["hbm_gbs"],
+                     iteration_with_optimizer_ms=full_ms,
+                     note="iteration = forward + backward + optimizer + weight re-preparation (bf16 / packed copies)")
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -622,7 +653,7 @@ def run_train(args):
                               measured="second pass of the same steps with CUDA events around every GEMM launch",
                               per_gpu_step_tflops_algorithmic=flops_step / (ms_per_step * 1e-3) / 1e12,
                               step_frac_of_peak=flops_step / (ms_per_step * 1e-3) / 1e12 / peaks["tf_sustained"]),
-                hbm_kernels=None, cpu_baseline=None)
+                hbm_kernels=None, cpu_baseline=None, optimizer=optimizer)
     print(json.dumps(line), flush=True)
 
 

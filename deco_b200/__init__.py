@@ -8,6 +8,7 @@ from .denoiser import PixNerDiT  # noqa: F401
 from .sampling import (AdamLMSampler, BaseSampler, EulerSampler, HeunSampler, ode_step_fn,  # noqa: F401
                        shift_respace_fn, simple_guidance_fn)
 from .scheduling import BaseScheduler, LinearScheduler  # noqa: F401
+from .optim import FusedAdamWEMA  # noqa: F401
 from .training import BaseTrainer, REPATrainer  # noqa: F401
 
 __version__ = "0.1.0"

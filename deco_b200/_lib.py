@@ -44,6 +44,8 @@ SIGNATURES = {
     "deco_fp2uint8": (_i, [_vp, _vp, _ll, _vp]),
     "deco_sampler_advance": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp]),
     "deco_cfg_step_dev": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _vp]),
+    "deco_opt_chunk_elems": (_i, []),
+    "deco_adamw_ema_step": (_i, [_vp, _vp, _i, _f, _f, _f, _f, _f, _f, _f, _f, _vp]),
     "deco_dct_fm_loss": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),
     "deco_transpose_cast": (_i, [_vp, _i, _ll, _vp, _ll, _i, _i, _i, _vp]),
     "deco_colsum": (_i, [_vp, _i, _ll, _vp, _ll, _i, _vp]),

@@ -375,23 +375,27 @@ class PixNerDiT(nn.Module):
                                kn=Fv(b.attn.k_norm.weight), wproj=W(b.attn.proj.weight), bproj=Fv(b.attn.proj.bias),
                                n2=Fv(b.norm2.weight), w13=w13, w2=w2))
         P["blocks"] = blocks
-        if COMPOSITE_SHIFT and blocks and H % 32 == 0:
-            # shift_i . W^T = (c . Wada_shift^T + bada_shift) . W^T = c . (W . Wada_shift)^T + W . bada_shift: the 2 x nb
-            # batch-sized shift products of a forward collapse into ONE GEMM of c against these composite weights
-            # (at 8-GPU sharding the 56 tiny launches were 4 % of a step)
-            wc, bc = [], []
-            for b, bp in zip(self.blocks, blocks):
-                wa = b.adaLN_modulation[0].weight.detach().to(device=device, dtype=torch.float32)
-                ba = b.adaLN_modulation[0].bias.detach().to(device=device, dtype=torch.float32)
-                for wmat, lo in ((bp["wqkv"], 0), (bp["w13"], 3 * H)):
-                    wf = wmat.float()
-                    wc.append((wf @ wa[lo:lo + H]).to(bf16))
-                    bc.append(wf @ ba[lo:lo + H])
-            P["wshift"], P["bshift"] = torch.cat(wc, 0).contiguous(), torch.cat(bc, 0).contiguous()
         P["wcond"], P["bcond"] = W(self.dec_net.cond_embed.weight), Fv(self.dec_net.cond_embed.bias)
         P["blob"], P["postab"] = self._pack_decoder(device)
         self._prep, self._prep_key = P, key
         return P
+
+    @torch.no_grad()
+    def _composite_shift(self, P, device):
+        """shift_i . W^T = (c . Wada_shift^T + bada_shift) . W^T = c . (W . Wada_shift)^T + W . bada_shift: the 2 x nb
+        batch-sized shift products of a forward collapse into ONE GEMM of c against these composite weights (at 8-GPU
+        sharding the 56 tiny launches were 4 % of a step).  Built on first use by the fused inference path and cached with
+        the prepared weights (a training loop that changes the weights every step never pays for it)."""
+        H = self.hidden_size
+        wc, bc = [], []
+        for b, bp in zip(self.blocks, P["blocks"]):
+            wa = b.adaLN_modulation[0].weight.detach().to(device=device, dtype=torch.float32)
+            ba = b.adaLN_modulation[0].bias.detach().to(device=device, dtype=torch.float32)
+            for wmat, lo in ((bp["wqkv"], 0), (bp["w13"], 3 * H)):
+                wf = wmat.float()
+                wc.append((wf @ wa[lo:lo + H]).to(bf16))
+                bc.append(wf @ ba[lo:lo + H])
+        return torch.cat(wc, 0).contiguous(), torch.cat(bc, 0).contiguous()
 
     def _pack_decoder(self, device):
         tab = nerf_pos_table(self.patch_size, self.x_embedder.max_freqs)
@@ -423,6 +427,8 @@ class PixNerDiT(nn.Module):
         if nb and self.fused and H % 32 == 0:
             mod = ops.gemm(c, P["wada"], P["bada"], ops.EPI_BIAS)                   # [B, nb*6H]
             st = StreamState(B * L, H, P["ffn_pad"], xp.device)
+            if COMPOSITE_SHIFT and "wshift" not in P:
+                P["wshift"], P["bshift"] = self._composite_shift(P, xp.device)
             shw_all = ops.gemm(c, P["wshift"], P["bshift"], ops.EPI_BIAS_F32) if "wshift" in P else None
             s = fused_blocks(P["blocks"], mod, 0, st, xp, P["ws"], P["bs"], B, L, H, heads, pos, wp, shw_all=shw_all)
             return ops.silu_add_rows(s, temb, L, out=st.o)

@@ -1,0 +1,78 @@
+"""Fused AdamW + EMA step (csrc/optimizer.cu): one launch over every parameter tensor.
+
+Mirrors `torch.optim.AdamW` as configured by the reference (`configs_c2i/DeCo_XL.yaml:89-93`) and the `SimpleEMA` callback
+(`src/callbacks/simple_ema.py:27-39`: `ema = decay * ema + (1 - decay) * param` after every optimizer step).  fp32
+parameters / gradients / moments, CUDA only (no fallback)."""
+from __future__ import annotations
+
+import math
+from typing import Iterable, Optional
+
+import torch
+
+from . import _lib
+from ._lib import call, ptr
+
+
+class FusedAdamWEMA:
+    def __init__(self, params: Iterable[torch.nn.Parameter], ema_params: Optional[Iterable[torch.Tensor]] = None,
+                 lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
+                 ema_decay: float = 0.9999):
+        self.params = [p for p in params if p.requires_grad]
+        self.ema = list(ema_params) if ema_params is not None else None
+        if not self.params:
+            raise ValueError("no trainable parameters")
+        if self.ema is not None and len(self.ema) != len(self.params):
+            raise ValueError("ema_params must pair up with the trainable parameters")
+        for p in self.params:
+            if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
+                raise RuntimeError("FusedAdamWEMA needs contiguous fp32 CUDA parameters (no CPU fallback)")
+        self.lr, self.betas, self.eps, self.weight_decay, self.ema_decay = lr, betas, eps, weight_decay, ema_decay
+        self.step_count = 0
+        self.exp_avg = [torch.zeros_like(p) for p in self.params]
+        self.exp_avg_sq = [torch.zeros_like(p) for p in self.params]
+        self._tables = None
+        self._grad_ptrs = None
+
+    def _build_tables(self):
+        dev = self.params[0].device
+        chunk = _lib.load().deco_opt_chunk_elems()
+        rows, chunks = [], []
+        for i, p in enumerate(self.params):
+            e = self.ema[i] if self.ema is not None else None
+            if e is not None and (e.shape != p.shape or e.dtype != torch.float32 or not e.is_contiguous() or e.device != dev):
+                raise RuntimeError("EMA tensors must match their parameters (fp32, contiguous, same device)")
+            rows.append([p.data_ptr(), p.grad.data_ptr(), self.exp_avg[i].data_ptr(), self.exp_avg_sq[i].data_ptr(),
+                         e.data_ptr() if e is not None else 0, p.numel()])
+            chunks += [[i, c] for c in range((p.numel() + chunk - 1) // chunk)]
+        self._grad_ptrs = [p.grad.data_ptr() for p in self.params]
+        self._tables = (torch.tensor(rows, dtype=torch.int64).to(dev), torch.tensor(chunks, dtype=torch.int32).to(dev))
+
+    @torch.no_grad()
+    def step(self):
+        for p in self.params:
+            if p.grad is None:
+                raise RuntimeError("FusedAdamWEMA.step(): a parameter has no gradient")
+            if p.grad.dtype != torch.float32 or not p.grad.is_contiguous():
+                p.grad = p.grad.float().contiguous()
+        if self._tables is None or self._grad_ptrs != [p.grad.data_ptr() for p in self.params]:
+            self._build_tables()          # gradient buffers moved (first step, or .grad was re-created)
+        self.step_count += 1
+        b1, b2 = self.betas
+        tens, chunks = self._tables
+        call("deco_adamw_ema_step", ptr(tens), ptr(chunks), chunks.shape[0], float(self.lr), float(b1), float(b2),
+             float(self.eps), float(self.weight_decay), 1.0 - math.pow(b1, self.step_count),
+             1.0 - math.pow(b2, self.step_count), float(self.ema_decay),
+             torch.cuda.current_stream(self.params[0].device).cuda_stream)
+        # the kernel wrote the parameters behind autograd's back: bump their version counters (no kernel) so that caches
+        # keyed on them -- PixNerDiT.prepare()'s bf16 / packed weights -- are rebuilt
+        torch.autograd.graph.increment_version(self.params)
+        if self.ema is not None:
+            torch.autograd.graph.increment_version(self.ema)
+
+    def zero_grad(self, set_to_none: bool = True):
+        for p in self.params:
+            if set_to_none:
+                p.grad = None
+            elif p.grad is not None:
+                p.grad.zero_()

@@ -288,6 +288,16 @@ int deco_gemm_bf16_tn(const void* At, long long lda, const void* Wt, long long l
 int deco_gemm_bf16_f32_splitk(const void* A, long long lda, const void* W, long long ldw, float* out, long long ldo,
                               int M, int N, int K, int split_k, void* stream);
 
+/* Fused multi-tensor AdamW + EMA update (csrc/optimizer.cu): torch.optim.AdamW semantics (configs_c2i/DeCo_XL.yaml:89-93)
+ * followed by ema = decay * ema + (1 - decay) * p (src/callbacks/simple_ema.py:27-39), one launch for all tensors.
+ * tensor_table: device array of {float* p, const float* g, float* m, float* v, float* ema (or NULL), int64 n};
+ * chunk_table: device array of int32 pairs (tensor index, chunk index), one per CTA, chunks of deco_opt_chunk_elems()
+ * elements; bias_correction{1,2} = 1 - beta^t. */
+int deco_opt_chunk_elems(void);
+int deco_adamw_ema_step(const void* tensor_table, const void* chunk_table, int num_chunks,
+                        float lr, float beta1, float beta2, float eps, float weight_decay,
+                        float bias_correction1, float bias_correction2, float ema_decay, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
