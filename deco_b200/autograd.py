@@ -53,31 +53,39 @@ def pack_decoder_train(module, device):
     return blob
 
 
+_FRAG_T_INDEX: dict = {}
+
+
 def _frag_t(w: torch.Tensor, perm_n: bool = False) -> torch.Tensor:
     """Pack the B operand of dX = dY . W, i.e. W^T given as wt [n = 32 inputs, K = outputs] (bf16), into m16n8k16
     B-fragment order [n_tile, k_step, lane, 4] (see denoiser.py::_frag).  perm_n: n-tile j, column c <-> input channel
     8 (c / 2) + 2 j + (c % 2), which makes a lane's four accumulator pairs the 16-byte chunk of the condition
-    (csrc/decoder_bwd_mma.cu)."""
+    (csrc/decoder_bwd_mma.cu).  The gather runs on w's device (index tensors cached)."""
     n_out, K = w.shape
-    j = torch.arange(n_out // 8).view(-1, 1, 1, 1)
-    s = torch.arange(K // 16).view(1, -1, 1, 1)
-    lane = torch.arange(32).view(1, 1, -1, 1)
-    e = torch.arange(4).view(1, 1, 1, -1)
-    g, t = lane // 4, lane % 4
-    half, lo = e // 2, e % 2
-    k = 16 * s + 8 * half + 2 * t + lo
-    row = (8 * (g // 2) + 2 * j + (g % 2)) if perm_n else (8 * j + g)
-    shape = (n_out // 8, K // 16, 32, 4)
-    return w[row.expand(shape), k.expand(shape)].contiguous()
+    key = (n_out, K, perm_n, str(w.device))
+    if key not in _FRAG_T_INDEX:
+        j = torch.arange(n_out // 8).view(-1, 1, 1, 1)
+        s = torch.arange(K // 16).view(1, -1, 1, 1)
+        lane = torch.arange(32).view(1, 1, -1, 1)
+        e = torch.arange(4).view(1, 1, 1, -1)
+        g, t = lane // 4, lane % 4
+        half, lo = e // 2, e % 2
+        k = 16 * s + 8 * half + 2 * t + lo
+        row = (8 * (g // 2) + 2 * j + (g % 2)) if perm_n else (8 * j + g)
+        shape = (n_out // 8, K // 16, 32, 4)
+        _FRAG_T_INDEX[key] = (row.expand(shape).contiguous().to(w.device), k.expand(shape).contiguous().to(w.device))
+    row, k = _FRAG_T_INDEX[key]
+    return w[row, k].contiguous()
 
 
 @torch.no_grad()
 def pack_decoder_bwd(module, device):
-    """Backward blob of csrc/decoder_bwd_mma.cu: W^T fragments [WinT | R x (WadaT n-permuted, W0T, W2T)] then fp32 Wf[3][32]."""
+    """Backward blob of csrc/decoder_bwd_mma.cu: W^T fragments [WinT | R x (WadaT n-permuted, W0T, W2T)] then fp32 Wf[3][32].
+    Packed on `device` (no host synchronisation: a training loop re-packs after every optimizer step)."""
     dn = module.dec_net
 
     def rb16(t):
-        return t.detach().float().cpu().to(bf16)
+        return t.detach().to(device=device, dtype=torch.float32).to(bf16)
 
     frags = [_frag_t(rb16(dn.input_proj.weight).t().contiguous())]
     for blk in dn.res_blocks:
@@ -85,9 +93,9 @@ def pack_decoder_bwd(module, device):
                   _frag_t(rb16(blk.mlp[0].weight).t().contiguous()), _frag_t(rb16(blk.mlp[2].weight).t().contiguous())]
     wf = rb16(dn.final_layer.linear.weight).float()
     assert wf.shape == (3, 32)
-    blob = torch.cat([torch.cat([f.reshape(-1) for f in frags]).view(torch.uint8), wf.reshape(-1).view(torch.uint8)])
+    blob = torch.cat([torch.cat([f.reshape(-1) for f in frags]).view(torch.uint8), wf.reshape(-1).contiguous().view(torch.uint8)])
     assert blob.numel() == _lib.load().deco_decoder_bwd_blob_bytes(len(dn.res_blocks)), blob.numel()
-    return blob.contiguous().to(device)
+    return blob.contiguous()
 
 
 @torch.no_grad()
@@ -105,8 +113,11 @@ def prepare_train(module, P: dict, device) -> dict:
                    for bp in P["blocks"]]
     T["dec_blob"] = pack_decoder_train(module, device)
     T["dec_bwd_blob"] = pack_decoder_bwd(module, device)
-    from .denoiser import nerf_pos_table
-    T["tabT"] = ops.transpose_cast(nerf_pos_table(module.patch_size, module.x_embedder.max_freqs).to(device))  # [64, 256]
+    key = ("nerf_tabT", str(device))
+    if key not in module.precompute_pos:        # constant: transposed positional table [64, 256] bf16, cached on the device
+        from .denoiser import nerf_pos_table
+        module.precompute_pos[key] = ops.transpose_cast(nerf_pos_table(module.patch_size, module.x_embedder.max_freqs).to(device))
+    T["tabT"] = module.precompute_pos[key]
     P["train"] = T
     return T
 

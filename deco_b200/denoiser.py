@@ -153,57 +153,69 @@ def nerf_pos_table(patch_size: int, max_freqs: int) -> torch.Tensor:
             ).view(-1, max_freqs ** 2)
 
 
+def _frag_index(n_out: int, permuted: bool, device):
+    """(rows, cols) gather indices of the mma.m16n8k16 B-fragment order [n_tile, k_step, lane, 4] for W [n_out, 32]:
+    lane = 4*g + t holds W[8j+g][k0], W[8j+g][k0+1], W[8j+g][k1], W[8j+g][k1+1] with (k0, k1) = (16s+2t, 16s+8+2t), or --
+    for the adaLN layers whose A operand is the 16-byte condition chunk -- the permuted (8t+4s, 8t+4s+2).
+    See csrc/decoder.cu."""
+    key = (n_out, permuted, str(device))
+    if key not in _FRAG_INDEX:
+        j = torch.arange(n_out // 8).view(-1, 1, 1, 1)
+        s = torch.arange(2).view(1, -1, 1, 1)
+        lane = torch.arange(32).view(1, 1, -1, 1)
+        e = torch.arange(4).view(1, 1, 1, -1)
+        g, t = lane // 4, lane % 4
+        half, lo = e // 2, e % 2
+        k = (8 * t + 4 * s + 2 * half + lo) if permuted else (16 * s + 8 * half + 2 * t + lo)
+        shape = (n_out // 8, 2, 32, 4)
+        _FRAG_INDEX[key] = ((8 * j + g).expand(shape).contiguous().to(device), k.expand(shape).contiguous().to(device))
+    return _FRAG_INDEX[key]
+
+
+_FRAG_INDEX: dict = {}
+
+
 def _frag(w: torch.Tensor, permuted: bool) -> torch.Tensor:
-    """Pack W [n_out, 32] (bf16) into mma.m16n8k16 B-fragment order: [n_tile, k_step, lane, 4] bf16.
-    lane = 4*g + t holds W[8j+g][k0], W[8j+g][k0+1], W[8j+g][k1], W[8j+g][k1+1] with (k0, k1) =
-    (16s+2t, 16s+8+2t), or -- for the adaLN layers whose A operand is the 16-byte condition chunk --
-    the permuted (8t+4s, 8t+4s+2).  See csrc/decoder.cu."""
-    n_out = w.shape[0]
-    j = torch.arange(n_out // 8).view(-1, 1, 1, 1)
-    s = torch.arange(2).view(1, -1, 1, 1)
-    lane = torch.arange(32).view(1, 1, -1, 1)
-    e = torch.arange(4).view(1, 1, 1, -1)
-    g, t = lane // 4, lane % 4
-    half, lo = e // 2, e % 2
-    if permuted:
-        k = 8 * t + 4 * s + 2 * half + lo
-    else:
-        k = 16 * s + 8 * half + 2 * t + lo
-    rows = (8 * j + g).expand(n_out // 8, 2, 32, 4)
-    return w[rows, k.expand_as(rows)].contiguous()
+    """Pack W [n_out, 32] (bf16) into B-fragment order (gather on W's own device, no host round trip)."""
+    rows, k = _frag_index(w.shape[0], permuted, w.device)
+    return w[rows, k].contiguous()
 
 
 def pack_decoder(embed_linear: nn.Linear, dn: "_PixelDecoder", C: int, pos_table: torch.Tensor, device):
     """Weights of NerfEmbedder / input_proj / ResBlocks / final layer in the layout csrc/decoder.cu expects.
     pos_table [p*p, max_freqs^2] is the model's constant positional input of the NerfEmbedder; it is folded with the
-    embedder weight into postab [p*p, 32] (fp32)."""
+    embedder weight into postab [p*p, 32] (fp32).  Everything stays on `device`: a training loop re-packs after every
+    optimizer step and must not synchronise with the host."""
     R = len(dn.res_blocks)
 
-    def rb(t):  # bf16-rounded fp32 copy on the host
-        return t.detach().float().cpu().to(bf16)
+    def rb(t):  # bf16-rounded copy on the device
+        return t.detach().to(device=device, dtype=torch.float32).to(bf16)
+
+    def fv(t):
+        return t.detach().to(device=device, dtype=torch.float32).reshape(-1)
 
     wx = rb(embed_linear.weight)                                     # [32, C + 64]
-    bx = embed_linear.bias.detach().float().cpu()
-    tab = pos_table.to(bf16).float()                                 # Linear input cast
-    postab = tab @ wx[:, C:].float().t() + bx                        # [p*p, 32] fp32
+    tab = pos_table.to(device=device, dtype=torch.float32).to(bf16).float()          # Linear input cast
+    postab = tab @ wx[:, C:].float().t() + fv(embed_linear.bias)     # [p*p, 32] fp32
     frags = [_frag(rb(dn.input_proj.weight), False)]
-    vec = [wx[:, :C].float().reshape(-1), torch.zeros(96 - 32 * C), dn.input_proj.bias.detach().float().cpu()]
+    vec = [wx[:, :C].float().reshape(-1), torch.zeros(96 - 32 * C, device=device), fv(dn.input_proj.bias)]
     for blk in dn.res_blocks:
         frags += [_frag(rb(blk.adaLN_modulation[1].weight), True), _frag(rb(blk.mlp[0].weight), False),
                   _frag(rb(blk.mlp[2].weight), False)]
-        vec += [blk.adaLN_modulation[1].bias, blk.in_ln.weight, blk.in_ln.bias, blk.mlp[0].bias, blk.mlp[2].bias]
-    wf = torch.zeros(8, 32, dtype=bf16)
+        vec += [fv(blk.adaLN_modulation[1].bias), fv(blk.in_ln.weight), fv(blk.in_ln.bias), fv(blk.mlp[0].bias),
+                fv(blk.mlp[2].bias)]
+    wf = torch.zeros(8, 32, dtype=bf16, device=device)
     wf[:C] = rb(dn.final_layer.linear.weight)
     frags.append(_frag(wf, False))
-    bf = torch.zeros(8)
-    bf[:C] = dn.final_layer.linear.bias.detach().float().cpu()
+    bf = torch.zeros(8, device=device)
+    bf[:C] = fv(dn.final_layer.linear.bias)
     vec.append(bf)
     frag_bytes = torch.cat([f.reshape(-1) for f in frags]).view(torch.uint8)
-    vec_bytes = torch.cat([v.detach().float().cpu().reshape(-1) for v in vec]).view(torch.uint8)
+    vec_bytes = torch.cat(vec).view(torch.uint8)
     blob = torch.cat([frag_bytes, vec_bytes]).contiguous()
     from . import _lib
     assert blob.numel() == _lib.load().deco_decoder_blob_bytes(R), (blob.numel(), R)
-    return blob.to(device), postab.contiguous().to(device)
+    return blob, postab.contiguous()
 
 
 def interleave_w13(w1: torch.Tensor, w3: torch.Tensor, Fp: int) -> torch.Tensor:
@@ -398,8 +410,10 @@ class PixNerDiT(nn.Module):
         return torch.cat(wc, 0).contiguous(), torch.cat(bc, 0).contiguous()
 
     def _pack_decoder(self, device):
-        tab = nerf_pos_table(self.patch_size, self.x_embedder.max_freqs)
-        return pack_decoder(self.x_embedder.embedder[0], self.dec_net, self.in_channels, tab, device)
+        key = ("nerf_tab", str(device))
+        if key not in self.precompute_pos:      # constant table, cached on the device (no per-step host -> device copy)
+            self.precompute_pos[key] = nerf_pos_table(self.patch_size, self.x_embedder.max_freqs).to(device)
+        return pack_decoder(self.x_embedder.embedder[0], self.dec_net, self.in_channels, self.precompute_pos[key], device)
 
     def fetch_pos(self, height, width, device):
         """RoPE table cache per (h, w) (dit_c2i_DeCo.py:467-473); here as real (cos, sin)."""

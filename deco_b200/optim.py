@@ -33,20 +33,29 @@ class FusedAdamWEMA:
         self.exp_avg_sq = [torch.zeros_like(p) for p in self.params]
         self._tables = None
         self._grad_ptrs = None
+        self._chunks = None
 
     def _build_tables(self):
+        """Device tables of tensor pointers / CTA chunks.  Rebuilt when a gradient buffer moved (autograd hands out new
+        .grad tensors every step); the upload goes through a persistent pinned buffer so that it never synchronises."""
         dev = self.params[0].device
-        chunk = _lib.load().deco_opt_chunk_elems()
-        rows, chunks = [], []
-        for i, p in enumerate(self.params):
-            e = self.ema[i] if self.ema is not None else None
-            if e is not None and (e.shape != p.shape or e.dtype != torch.float32 or not e.is_contiguous() or e.device != dev):
-                raise RuntimeError("EMA tensors must match their parameters (fp32, contiguous, same device)")
-            rows.append([p.data_ptr(), p.grad.data_ptr(), self.exp_avg[i].data_ptr(), self.exp_avg_sq[i].data_ptr(),
-                         e.data_ptr() if e is not None else 0, p.numel()])
-            chunks += [[i, c] for c in range((p.numel() + chunk - 1) // chunk)]
+        if self._chunks is None:
+            chunk = _lib.load().deco_opt_chunk_elems()
+            chunks = []
+            for i, p in enumerate(self.params):
+                e = self.ema[i] if self.ema is not None else None
+                if e is not None and (e.shape != p.shape or e.dtype != torch.float32 or not e.is_contiguous() or e.device != dev):
+                    raise RuntimeError("EMA tensors must match their parameters (fp32, contiguous, same device)")
+                chunks += [[i, c] for c in range((p.numel() + chunk - 1) // chunk)]
+            self._chunks = torch.tensor(chunks, dtype=torch.int32).to(dev)
+            self._rows_host = torch.empty((len(self.params), 6), dtype=torch.int64).pin_memory()
+            self._rows_dev = torch.empty((len(self.params), 6), dtype=torch.int64, device=dev)
+        rows = [[p.data_ptr(), p.grad.data_ptr(), self.exp_avg[i].data_ptr(), self.exp_avg_sq[i].data_ptr(),
+                 self.ema[i].data_ptr() if self.ema is not None else 0, p.numel()] for i, p in enumerate(self.params)]
+        self._rows_host.copy_(torch.tensor(rows, dtype=torch.int64))
+        self._rows_dev.copy_(self._rows_host, non_blocking=True)
         self._grad_ptrs = [p.grad.data_ptr() for p in self.params]
-        self._tables = (torch.tensor(rows, dtype=torch.int64).to(dev), torch.tensor(chunks, dtype=torch.int32).to(dev))
+        self._tables = (self._rows_dev, self._chunks)
 
     @torch.no_grad()
     def step(self):
