@@ -144,10 +144,9 @@ def train_forward(module, x32, t, y):
     p, H, heads = module.patch_size, module.hidden_size, module.num_groups
     d = H // heads
     L = (Hh // p) * (Ww // p)
-    M = B * L
     dev = x32.device
     pos = module.fetch_pos(Hh // p, Ww // p, dev)
-    S = dict(B=B, L=L, shape=x32.shape, x32=x32, y=y, pos=pos)
+    S = dict(B=B, L=L, x32=x32, y=y, pos=pos)
     xp = ops.patchify(x32, p)
     tfreq = ops.timestep_freq(t, module.t_embedder.frequency_embedding_size)
     z1 = ops.gemm(tfreq, P["wt0"], P["bt0"], ops.EPI_BIAS)
