@@ -332,7 +332,7 @@ def run_deco(args):
     ts = sampler.timesteps
     state = dict(pred=None)
 
-    stepper = sampler.graphed_stepper(net, x, cfg_cond) if wl["sampler"] == "euler" else None
+    stepper = sampler.graphed_stepper(net, x, cfg_cond)
     if stepper is not None:
         stepper.reset(x, cfg_cond)
 
@@ -409,8 +409,7 @@ def run_deco(args):
     e2e = None
     if not args.no_e2e:
         out_host = torch.empty((gbatch if world > 1 else B, 3, res, res), dtype=torch.uint8).pin_memory()
-        if wl["sampler"] == "euler":    # build (capture) the uint8 variant of the graphed step outside the timed region
-            sampler.graphed_stepper(net, x, cfg_cond, to_uint8=True)
+        sampler.graphed_stepper(net, x, cfg_cond, to_uint8=True)   # capture the uint8 variant outside the timed region
         if world > 1:                   # NCCL sets up its all-gather channels on first use: not part of a trajectory
             D.all_gather_images(torch.zeros((B, 3, 8, 8), dtype=torch.uint8, device=dev), world)
         barrier()

@@ -93,6 +93,7 @@ def rope_cos_sin_ex2d(head_dim: int, height: int, width: int, theta: float = 100
 
 class PixNerDiT(nn.Module):
     """Original text-to-image denoiser (constructor per the bytecode / dit_t2i_pixnerd.py:202-216)."""
+    cuda_graph_safe = True   # no host-device synchronisation in the forward (samplers may capture it)
 
     def __init__(self, in_channels=4, num_groups=12, hidden_size=1152, decoder_hidden_size=64, num_encoder_blocks=18,
                  num_decoder_blocks=4, num_text_blocks=4, patch_size=2, txt_embed_dim=1024, txt_max_length=100,

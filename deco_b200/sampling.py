@@ -61,6 +61,41 @@ class BaseSampler(nn.Module):
     def _impl_sampling(self, net, noise, condition, uncondition, keep_x=False, keep_v=False, to_uint8=False):
         raise NotImplementedError
 
+    def _graph_rows(self):
+        """(rows, use_pred) for GraphedStepper, or None when this sampler's step cannot be replayed from a table."""
+        return None
+
+    def graphed_stepper(self, net, noise, cfg_condition, to_uint8=False):
+        """GraphedStepper for (net, batch shape), built once and cached; None when the step cannot be graphed (a net that
+        is not a deco_b200 denoiser, DECO_B200_GRAPH=0, an unsupported sampler, or a capture failure -- the eager loop is
+        used then)."""
+        if not GRAPH or not getattr(net, "cuda_graph_safe", False) or getattr(net, "training", False):
+            return None
+        spec = self._graph_rows()
+        if spec is None:
+            return None
+        prep = net.prepare(noise.device) if hasattr(net, "prepare") else None
+        key = (id(net), id(prep), tuple(noise.shape), tuple(cfg_condition.shape), cfg_condition.dtype, bool(to_uint8),
+               noise.device.index, float(self.guidance))
+        cache = self.__dict__.setdefault("_steppers", {})
+        if key not in cache:
+            try:
+                cache[key] = GraphedStepper(self, net, noise.shape[0], noise.shape[1:], cfg_condition[: noise.shape[0]],
+                                            to_uint8, spec[0], spec[1])
+            except Exception as e:   # noqa: BLE001 -- capture is an optimisation; the eager loop runs the same kernels
+                logger.warning("CUDA-graph capture of the sampling step failed (%s); using the eager loop", e)
+                cache[key] = None
+        return cache[key]
+
+    def _run_graphed(self, net, x, cfg_condition, to_uint8):
+        st = self.graphed_stepper(net, x, cfg_condition, to_uint8)
+        if st is None:
+            return None
+        st.reset(x, cfg_condition)
+        for _ in range(self.num_steps):
+            st.step()
+        return st.x.clone(), None, None, (st.u8.clone() if to_uint8 else None)
+
     def _check(self):
         if self.guidance_fn is not None and self.guidance_fn is not simple_guidance_fn \
                 and getattr(self.guidance_fn, "__name__", "") != "simple_guidance_fn":
@@ -101,23 +136,18 @@ def _prep_inputs(noise, condition, uncondition):
 GRAPH = os.environ.get("DECO_B200_GRAPH", "1") != "0"
 
 
-class GraphedEulerStepper:
-    """One CFG Euler step -- schedule advance, denoiser forward, fused update -- captured ONCE into a CUDA graph and replayed
+class GraphedStepper:
+    """One CFG sampling step -- schedule advance, denoiser forward, fused update -- captured ONCE into a CUDA graph and replayed
     per step.  The step scalars (t, g, dt) live in a device table indexed by a device counter (csrc/sampler.cu
     sampler_advance_kernel), so a whole trajectory is `num_steps` replays with no host work in between: at small per-GPU
     batches (8-GPU sharding: 64 CFG rows) the ~210 Python/ctypes launches of a step cost as much host time as the step
-    takes on the GPU.  Same kernels, same order, same numerics as the eager loop (EulerSampler._impl_sampling)."""
+    takes on the GPU.  Same kernels, same order, same numerics as the eager loops (Euler; Adams order <= 2, whose previous
+    prediction lives in one buffer that the update kernel reads and overwrites in place).
+    rows: per step {g, dt, c0, c1, 0, 0, t, 0} (the sampler's `_graph_rows`)."""
 
-    def __init__(self, sampler, net, batch, shape, cond_like, to_uint8):
+    def __init__(self, sampler, net, batch, shape, cond_like, to_uint8, rows, use_pred=False):
         dev = cond_like.device
         self.sampler, self.net, self.B = sampler, net, batch
-        ts = sampler.timesteps
-        rows = []
-        for i in range(sampler.num_steps):
-            t_cur, t_next = ts[i], ts[i + 1]
-            in_window = bool(t_cur > sampler.guidance_interval_min) and bool(t_cur <= sampler.guidance_interval_max)
-            rows.append([float(sampler.guidance) if in_window else 1.0, float(t_next - t_cur), 1.0, 0.0, 0.0, 0.0,
-                         float(t_cur), 0.0])
         self.table = torch.tensor(rows, dtype=torch.float32).to(dev)
         self.counter = torch.zeros(1, dtype=torch.int32, device=dev)
         self.cur = torch.zeros(8, dtype=torch.float32, device=dev)
@@ -125,6 +155,7 @@ class GraphedEulerStepper:
         self.x = torch.zeros((batch,) + tuple(shape), dtype=torch.float32, device=dev)
         self.cond = torch.zeros((2 * batch,) + tuple(cond_like.shape[1:]), dtype=cond_like.dtype, device=dev)
         self.u8 = torch.zeros(self.x.shape, dtype=torch.uint8, device=dev) if to_uint8 else None
+        self.pred = torch.zeros_like(self.x) if use_pred else None
         cur_stream = torch.cuda.current_stream(dev)
         side = torch.cuda.Stream(dev)
         side.wait_stream(cur_stream)
@@ -144,12 +175,14 @@ class GraphedEulerStepper:
         out = self.net(torch.cat([self.x, self.x], dim=0), self.t, self.cond)
         if out.dtype not in (torch.bfloat16, torch.float32):
             out = out.float()
-        ops.cfg_step_dev(self.x, out.contiguous(), self.cur, self.x, u8_out=self.u8)
+        ops.cfg_step_dev(self.x, out.contiguous(), self.cur, self.x, p1=self.pred, pred_out=self.pred, u8_out=self.u8)
 
     def reset(self, x, cfg_condition):
         self.x.copy_(x)
         self.cond.copy_(cfg_condition)
         self.counter.zero_()
+        if self.pred is not None:
+            self.pred.zero_()
 
     def step(self):
         self.graph.replay()
@@ -186,35 +219,22 @@ class EulerSampler(BaseSampler):
             if getattr(fn, "__name__", "") != "ode_step_fn":
                 raise NotImplementedError("only ode_step_fn is supported (SDE steps are out of scope)")
 
-    def graphed_stepper(self, net, noise, cfg_condition, to_uint8=False):
-        """GraphedEulerStepper for (net, batch shape), built once and cached; None when the step cannot be graphed (a net
-        that is not a deco_b200 denoiser, DECO_B200_GRAPH=0, or a capture failure -- the eager loop is used then)."""
-        if not GRAPH or not getattr(net, "cuda_graph_safe", False) or getattr(net, "training", False):
-            return None
-        prep = net.prepare(noise.device) if hasattr(net, "prepare") else None
-        key = (id(net), id(prep), tuple(noise.shape), tuple(cfg_condition.shape), cfg_condition.dtype, bool(to_uint8),
-               noise.device.index, float(self.guidance))
-        cache = self.__dict__.setdefault("_steppers", {})
-        if key not in cache:
-            try:
-                cache[key] = GraphedEulerStepper(self, net, noise.shape[0], noise.shape[1:], cfg_condition[: noise.shape[0]],
-                                                 to_uint8)
-            except Exception as e:   # noqa: BLE001 -- capture is an optimisation; the eager loop runs the same kernels
-                logger.warning("CUDA-graph capture of the sampling step failed (%s); using the eager loop", e)
-                cache[key] = None
-        return cache[key]
+    def _graph_rows(self):
+        rows, ts = [], self.timesteps
+        for i in range(self.num_steps):
+            t_cur, t_next = ts[i], ts[i + 1]
+            in_window = bool(t_cur > self.guidance_interval_min) and bool(t_cur <= self.guidance_interval_max)
+            rows.append([float(self.guidance) if in_window else 1.0, float(t_next - t_cur), 1.0, 0.0, 0.0, 0.0, float(t_cur), 0.0])
+        return rows, False
 
     def _impl_sampling(self, net, noise, condition, uncondition, keep_x=False, keep_v=False, to_uint8=False):
         B = noise.shape[0]
         x, cfg_condition = _prep_inputs(noise, condition, uncondition)
         steps = self.timesteps  # host fp32
         if not keep_x and not keep_v:
-            st = self.graphed_stepper(net, x, cfg_condition, to_uint8)
-            if st is not None:
-                st.reset(x, cfg_condition)
-                for _ in range(self.num_steps):
-                    st.step()
-                return st.x.clone(), None, None, (st.u8.clone() if to_uint8 else None)
+            res = self._run_graphed(net, x, cfg_condition, to_uint8)
+            if res is not None:
+                return res
         x_trajs, v_trajs, u8 = ([x] if keep_x else None), ([] if keep_v else None), None
         for i in range(self.num_steps):
             t_cur, t_next = steps[i], steps[i + 1]
@@ -360,9 +380,26 @@ class AdamLMSampler(BaseSampler):
             coeffs.append(_lagrange_coeffs(min(self.order, i + 1), pre_ts, t0, t1))
         self.solver_coeffs = coeffs
 
+    def _graph_rows(self):
+        if self.order > 2:
+            return None               # one in-place prediction buffer = order <= 2 (every DeCo config uses order 2)
+        rows = []
+        t_cur = torch.zeros((), dtype=torch.float32)
+        for i in range(self.num_steps):
+            in_window = bool(t_cur > self.guidance_interval_min) and bool(t_cur < self.guidance_interval_max)
+            cs = self.solver_coeffs[i]
+            rows.append([float(self.guidance) if in_window else 1.0, float(self.timedeltas[i]), float(cs[-1]),
+                         float(cs[0]) if len(cs) > 1 else 0.0, 0.0, 0.0, float(t_cur), 0.0])
+            t_cur = t_cur + self.timedeltas[i]
+        return rows, self.order > 1
+
     def _impl_sampling(self, net, noise, condition, uncondition, keep_x=False, keep_v=False, to_uint8=False):
         B = noise.shape[0]
         x, cfg_condition = _prep_inputs(noise, condition, uncondition)
+        if not keep_x and not keep_v:
+            res = self._run_graphed(net, x, cfg_condition, to_uint8)
+            if res is not None:
+                return res
         x_trajs, v_trajs, u8 = ([x] if keep_x else None), ([] if keep_v else None), None
         preds: List[torch.Tensor] = []
         # the reference accumulates t_cur += dt in fp32 on the device (adam_sampling.py:96,118); same sums here

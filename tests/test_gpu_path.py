@@ -328,3 +328,23 @@ def test_step_time_vs_pytorch_eager_on_the_same_gpu(cuda_dev):
     print(f"XL/16 step, 64 CFG rows: deco_b200 {ours:.2f} ms, PyTorch eager bf16-autocast (reference numerics) {ref:.2f} ms, "
           f"ratio {ref / ours:.2f}x")
     assert ours < ref
+
+
+def test_graphed_adams_step_equals_eager_loop(cuda_dev, monkeypatch):
+    """AdamLMSampler order 2 through the CUDA-graphed stepper (previous prediction updated in place) vs the eager loop."""
+    from deco_b200 import AdamLMSampler, LinearScheduler, simple_guidance_fn
+    from deco_b200 import sampling as S
+    cfg = O.DenoiserCfg(num_groups=8, hidden_size=576, num_blocks=5, num_cond_blocks=3, num_classes=10)
+    m, _ = build_module(cfg, cuda_dev)
+    noise = seeded_noise(2, (3, 64, 64), 9).to(cuda_dev)
+    cond = torch.tensor([3, 6], device=cuda_dev)
+    unc = torch.full((2,), 10, device=cuda_dev)
+    kw = dict(order=2, timeshift=3.0, scheduler=LinearScheduler(), guidance_fn=simple_guidance_fn, num_steps=7, guidance=4.0,
+              guidance_interval_min=0.1, guidance_interval_max=0.9)
+    monkeypatch.setattr(S, "GRAPH", True)
+    sg = AdamLMSampler(**kw)
+    xg, ug = sg.sample_uint8(m, noise, cond, unc)
+    assert any(v is not None for v in sg._steppers.values()), "the sampling step was not captured into a CUDA graph"
+    monkeypatch.setattr(S, "GRAPH", False)
+    xe, ue = AdamLMSampler(**kw).sample_uint8(m, noise, cond, unc)
+    assert torch.equal(xg, xe) and torch.equal(ug, ue)
