@@ -411,7 +411,7 @@ def run_deco(args):
         out_host = torch.empty((gbatch if world > 1 else B, 3, res, res), dtype=torch.uint8).pin_memory()
         sampler.graphed_stepper(net, x, cfg_cond, to_uint8=True)   # capture the uint8 variant outside the timed region
         if world > 1:                   # NCCL sets up its all-gather channels on first use: not part of a trajectory
-            D.all_gather_images(torch.zeros((B, 3, 8, 8), dtype=torch.uint8, device=dev), world)
+            D.all_gather_images(torch.zeros((B, 3, res, res), dtype=torch.uint8, device=dev), world)   # same size = same algorithm
         barrier()
         t0 = torch.cuda.Event(enable_timing=True)
         t1 = torch.cuda.Event(enable_timing=True)
