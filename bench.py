@@ -525,11 +525,7 @@ def run_train(args):
             p.grad = None
         d = trainer(net, None, None, x, y, unc)
         d["loss"].backward()
-        if world > 1:      # what DDP does, in one bucket: flatten, average over ranks, scatter back into the .grad tensors
-            grads = [p.grad for p in params]
-            flat = torch._utils._flatten_dense_tensors(grads)
-            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
-            torch._foreach_copy_(grads, torch._utils._unflatten_dense_tensors(flat, grads))
+        D.all_reduce_gradients(params, world)      # what DDP does, in one bucket
         return d["loss"].detach()
 
     def barrier():

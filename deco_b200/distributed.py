@@ -37,3 +37,20 @@ def all_gather_images(local_u8: torch.Tensor, world_size: int, total: Optional[i
         dist.all_gather(list(gathered.unbind(0)), local_u8)
     out = gathered.transpose(0, 1).reshape((-1,) + tuple(local_u8.shape[1:]))   # global order r + i*world
     return out if total is None else out[:total]
+
+
+def all_reduce_gradients(params, world_size: int) -> None:
+    """Average the .grad tensors of `params` over the ranks in ONE collective (what DDP does for the reference's
+    training step, src/lightning_model.py under `strategy: ddp`): flatten, all-reduce, scatter back in place."""
+    if world_size == 1:
+        return
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return
+    flat = torch._utils._flatten_dense_tensors(grads)
+    if dist.get_backend() == "nccl":
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+    else:
+        dist.all_reduce(flat)
+        flat.div_(world_size)
+    torch._foreach_copy_(grads, torch._utils._unflatten_dense_tensors(flat, grads))

@@ -231,6 +231,36 @@ def test_all_gather_restores_global_order_gloo_world2():
     assert got == list(range(10))
 
 
+def _grad_worker(rank, world, port, ret):
+    import torch.distributed as dist
+    from deco_b200 import distributed as D
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    D.init_from_env("gloo")
+    ps = [torch.nn.Parameter(torch.zeros(s)) for s in [(3,), (2, 5), (1,)]]
+    for i, p in enumerate(ps):
+        p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
+    D.all_reduce_gradients(ps, world)
+    if rank == 0:
+        ret.put([float(p.grad.mean()) for p in ps] + [float(p.grad.min()) for p in ps])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gradient_all_reduce_averages_over_ranks_gloo_world2():
+    """Data-parallel training step (bench.py --workload train256 at N > 1): .grad <- mean over ranks, in place."""
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = ret.get(timeout=120)
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert got == [1.5, 3.0, 4.5, 1.5, 3.0, 4.5]
+
+
 def test_model_loader_prefix_contract(tmp_path):
     """ModelLoader (src/utils/model_loader.py:10-28): `ema_denoiser.` / `denoiser.` prefixed Lightning checkpoints."""
     from deco_b200 import PixNerDiT
