@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 static thread_local char g_err[512] = "";
 
@@ -17,3 +18,14 @@ extern "C" const char* deco_last_error(void) { return g_err; }
 extern "C" int deco_abi_version(void) { return 1; }
 
 // Number of kernels the library has launched since load is not tracked here; bench.py counts launches on the host side.
+
+// Programmatic dependent launch for the big kernels of the sampling step (GEMMs, attention, pixel decoder): on by default,
+// DECO_B200_PDL=0 turns it off (A/B measurements).
+bool deco_pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DECO_B200_PDL");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
+}

@@ -150,6 +150,8 @@ attention_tc_kernel(const __grid_constant__ TcAttnMaps M, const TcAttnParams P)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_wait();                   // prologue overlapped the previous kernel's tail; q / k / v are visible from here
+    pdl_launch_dependents();
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen + (slot - base));
 
     auto decode = [&](int n, int& b, int& h, int& pair) {
@@ -455,7 +457,18 @@ static int launch_attention_tc(const TcAttnMaps& M, const TcAttnParams& P, cudaS
     if (sms <= 0) sms = kNumSMs;
     const long long items = (long long)P.B * P.heads * ((P.Lq + 2 * kTcRows - 1) / (2 * kTcRows));
     const int grid = (int)(items < sms ? items : sms);
-    attention_tc_kernel<D><<<grid, kTcThreads, C::SMEM, st>>>(M, P);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kTcThreads);
+    cfg.dynamicSmemBytes = C::SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = deco_pdl_enabled() ? 1 : 0;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, attention_tc_kernel<D>, M, P);
+    if (le != cudaSuccess) { deco_set_error("attention launch failed: %s", cudaGetErrorString(le)); return (int)le; }
     DECO_CHECK_LAUNCH("attention_tc_kernel");
     return DECO_OK;
 }

@@ -28,6 +28,9 @@ void deco_set_error(const char* fmt, ...);
         }                                                                     \
     } while (0)
 
+// process-wide switch for programmatic dependent launch (DECO_B200_PDL=0 disables it); defined in api.cu
+bool deco_pdl_enabled();
+
 namespace deco {
 
 constexpr int kNumSMs = 148;
@@ -76,6 +79,13 @@ __device__ __forceinline__ void st_stream16(void* p, uint4 v) {
     asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
                  :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while
+// its predecessor in the stream drains -- its prologue (barrier init, TMEM allocation, descriptor prefetch, constant
+// weights) overlaps the predecessor's tail -- and must call pdl_wait() before touching anything the predecessor wrote or
+// still reads; pdl_launch_dependents() lets the NEXT kernel be scheduled as soon as SMs free up.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);

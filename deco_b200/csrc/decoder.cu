@@ -103,9 +103,11 @@ __global__ void __launch_bounds__(256, 2) pixel_decoder_kernel(DecParams P)
         const uint4* src = reinterpret_cast<const uint4*>(P.blob);
         uint4* dst = reinterpret_cast<uint4*>(smem);
         const int n16 = (nfrag + nvec) / 4;
-        for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
+        for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);   // weights: constants, not a predecessor's output
     }
     __syncthreads();
+    pdl_wait();                   // the weight staging above overlapped the cond_embed GEMM's tail; ycond is visible from here
+    pdl_launch_dependents();
     const uint32_t* sW = smem;
     const float* sV = reinterpret_cast<const float*>(smem + nfrag);
 
@@ -292,16 +294,27 @@ extern "C" int deco_pixel_decoder(const float* x, const void* ycond_bf16, const 
     const long long warps_needed = P.M * 16;
     long long grid = (warps_needed + 7) / 8;
     if (grid > 2LL * kNumSMs) grid = 2LL * kNumSMs;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = deco_pdl_enabled() ? 1 : 0;
     cudaError_t e;
     if (out_is_bf16) {
         e = cudaFuncSetAttribute(pixel_decoder_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
         if (e != cudaSuccess) { deco_set_error("pixel_decoder attr: %s", cudaGetErrorString(e)); return (int)e; }
-        pixel_decoder_kernel<__nv_bfloat16><<<(unsigned)grid, 256, smem_bytes, (cudaStream_t)stream>>>(P);
+        e = cudaLaunchKernelEx(&cfg, pixel_decoder_kernel<__nv_bfloat16>, P);
     } else {
         e = cudaFuncSetAttribute(pixel_decoder_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
         if (e != cudaSuccess) { deco_set_error("pixel_decoder attr: %s", cudaGetErrorString(e)); return (int)e; }
-        pixel_decoder_kernel<float><<<(unsigned)grid, 256, smem_bytes, (cudaStream_t)stream>>>(P);
+        e = cudaLaunchKernelEx(&cfg, pixel_decoder_kernel<float>, P);
     }
+    if (e != cudaSuccess) { deco_set_error("pixel_decoder launch failed: %s", cudaGetErrorString(e)); return (int)e; }
     DECO_CHECK_LAUNCH("pixel_decoder_kernel");
     return DECO_OK;
 }

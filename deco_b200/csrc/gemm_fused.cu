@@ -171,6 +171,8 @@ gemm_fused_kernel(const __grid_constant__ Maps maps, const Params P)
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_wait();                   // everything above overlapped the previous kernel's tail; its outputs are visible from here
+    pdl_launch_dependents();
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -721,11 +723,13 @@ static int launch(const Maps& maps, const Params& P, cudaStream_t st) {
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = C::kSmemBytes;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = deco_pdl_enabled() ? 2 : 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, maps, P);
     if (e != cudaSuccess) { deco_set_error("fused gemm launch failed: %s", cudaGetErrorString(e)); return (int)e; }
     return DECO_OK;

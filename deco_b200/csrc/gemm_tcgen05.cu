@@ -281,6 +281,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     if (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_wait();                   // prologue overlapped the previous kernel's tail; its outputs are visible from here
+    pdl_launch_dependents();
 
     if (warp == 0) {
         // ===================== TMA producer (every CTA loads its own A rows and its share of W) =====================
@@ -457,11 +459,13 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
     cfg.blockDim = dim3(kGemmThreads);
     cfg.dynamicSmemBytes = Cfg::kSmemBytes;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = deco_pdl_enabled() ? 2 : 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, P);
     if (e != cudaSuccess) { deco_set_error("gemm launch failed: %s", cudaGetErrorString(e)); return (int)e; }
     return DECO_OK;
