@@ -237,8 +237,8 @@ class PixNerDiT(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("deco_b200 t2i PixNerDiT runs on CUDA (sm_100a) only; there is no CPU fallback")
         if torch.is_grad_enabled() and (x.requires_grad or (self.training and any(p.requires_grad for p in self.parameters()))):
-            raise NotImplementedError("backward kernels for the denoiser are not built yet (inference/eval only); "
-                                      "call under torch.no_grad() / .eval()")
+            raise NotImplementedError("the text-to-image denoiser has no backward yet (the class-conditional PixNerDiT does: "
+                                      "deco_b200/autograd.py); call under torch.no_grad() / .eval()")
         B, Cc, Hh, Ww = x.shape
         p, H = self.patch_size, self.hidden_size
         assert Cc == self.in_channels and Hh % p == 0 and Ww % p == 0
