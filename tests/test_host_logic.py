@@ -345,3 +345,35 @@ def test_training_blobs_have_the_sizes_the_kernels_expect():
     assert torch.equal(blob[1120:1152], m.dec_net.input_proj.bias.detach())
     assert float(blob[1152 + 3 * 5344 + 96:1152 + 3 * 5344 + 128].abs().sum()) == 0.0
     assert pack_decoder_bwd(m, "cpu").numel() == 4 * (512 + 3 * 2560 + 96)
+
+
+def test_graph_schedule_tables_match_the_eager_loops():
+    """The device tables the CUDA-graphed stepper walks (deco_b200/sampling.py::_graph_rows) hold exactly the per-step
+    scalars of the eager loops: Euler (window test `min < t <= max`, sampling.py:93) and Adams order 2 (strict upper bound,
+    fp32-accumulated t, adam_sampling.py:96-118)."""
+    from deco_b200 import AdamLMSampler, EulerSampler, HeunSampler, LinearScheduler, ode_step_fn, simple_guidance_fn
+    sch = LinearScheduler()
+    e = EulerSampler(scheduler=sch, w_scheduler=sch, guidance_fn=simple_guidance_fn, num_steps=100, guidance=3.2,
+                     guidance_interval_min=0.1, guidance_interval_max=1.0, step_fn=ode_step_fn)
+    rows, use_pred = e._graph_rows()
+    assert not use_pred and len(rows) == 100
+    ts = e.timesteps
+    for i, r in enumerate(rows):
+        g = 3.2 if (bool(ts[i] > 0.1) and bool(ts[i] <= 1.0)) else 1.0
+        assert r[0] == g and r[1] == float(ts[i + 1] - ts[i]) and r[2] == 1.0 and r[3] == 0.0 and r[6] == float(ts[i])
+    assert rows[10][0] == 1.0 and rows[11][0] == 3.2        # ts[10] = 0.0999999940 is NOT > 0.1 (SURVEY.md section 4)
+    a = AdamLMSampler(order=2, timeshift=3.0, scheduler=sch, guidance_fn=simple_guidance_fn, num_steps=25, guidance=4.0,
+                      guidance_interval_min=0.0, guidance_interval_max=1.0)
+    rows, use_pred = a._graph_rows()
+    assert use_pred and len(rows) == 25
+    t = torch.zeros((), dtype=torch.float32)
+    for i, r in enumerate(rows):
+        cs = a.solver_coeffs[i]
+        assert r[0] == (4.0 if (bool(t > 0.0) and bool(t < 1.0)) else 1.0)
+        assert r[1] == float(a.timedeltas[i]) and r[2] == float(cs[-1]) and r[3] == (float(cs[0]) if len(cs) > 1 else 0.0)
+        assert r[6] == float(t)
+        t = t + a.timedeltas[i]
+    assert rows[0][0] == 1.0 and rows[0][3] == 0.0          # first step: t = 0 is outside the open window, order 1
+    assert AdamLMSampler(order=3, scheduler=sch, guidance_fn=simple_guidance_fn, num_steps=8)._graph_rows() is None
+    assert HeunSampler(scheduler=sch, w_scheduler=sch, guidance_fn=simple_guidance_fn, num_steps=4,
+                       step_fn=ode_step_fn)._graph_rows() is None
