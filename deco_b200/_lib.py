@@ -44,6 +44,10 @@ SIGNATURES = {
     "deco_fp2uint8": (_i, [_vp, _vp, _ll, _vp]),
     "deco_sampler_advance": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp]),
     "deco_cfg_step_dev": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _vp]),
+    "deco_cfg_step_ex": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _vp,
+                              _vp, _vp, _vp, _vp, _ll, _vp]),
+    "deco_layernorm_modulate": (_i, [_vp, _vp, _vp, _ll, _i, _vp, _ll, _i, _f, _vp]),
+    "deco_unpatchify": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "deco_opt_chunk_elems": (_i, []),
     "deco_adamw_ema_step": (_i, [_vp, _vp, _i, _f, _f, _f, _f, _f, _f, _f, _f, _vp]),
     "deco_dct_fm_loss": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),

@@ -15,12 +15,19 @@ CLASS_MAP = {
     "src.models.transformer.dit_c2i_DeCo.PixNerDiT": "deco_b200.denoiser.PixNerDiT",
     "src.models.transformer.dit_t2i_DeCo.PixNerDiT": "deco_b200.denoiser_t2i.PixNerDiT",
     "src.diffusion.flow_matching.sampling.EulerSampler": "deco_b200.sampling.EulerSampler",
+    "src.diffusion.flow_matching.sampling.EulerSamplerJiT": "deco_b200.sampling.EulerSamplerJiT",
+    "src.models.transformer.dit_c2i_baseline.FlattenDiT": "deco_b200.denoiser_baseline.FlattenDiT",
     "src.diffusion.flow_matching.sampling.HeunSampler": "deco_b200.sampling.HeunSampler",
     "src.diffusion.flow_matching.adam_sampling.AdamLMSampler": "deco_b200.sampling.AdamLMSampler",
     "src.diffusion.flow_matching.scheduling.LinearScheduler": "deco_b200.scheduling.LinearScheduler",
     "src.diffusion.flow_matching.training_repa_DeCo.REPATrainer": "deco_b200.training.REPATrainer",
     "src.diffusion.base.guidance.simple_guidance_fn": "deco_b200.sampling.simple_guidance_fn",
     "src.diffusion.flow_matching.sampling.ode_step_fn": "deco_b200.sampling.ode_step_fn",
+    "src.diffusion.flow_matching.sampling.sde_mean_step_fn": "deco_b200.sampling.sde_mean_step_fn",
+    "src.diffusion.flow_matching.sampling.sde_step_fn": "deco_b200.sampling.sde_step_fn",
+    "src.diffusion.flow_matching.sampling.sde_preserve_step_fn": "deco_b200.sampling.sde_preserve_step_fn",
+    "src.diffusion.flow_matching.scheduling.GVPScheduler": "deco_b200.scheduling.GVPScheduler",
+    "src.diffusion.flow_matching.scheduling.ConstScheduler": "deco_b200.scheduling.ConstScheduler",
     "src.diffusion.flow_matching.adam_sampling.ode_step_fn": "deco_b200.sampling.ode_step_fn",
     "src.utils.model_loader.ModelLoader": "deco_b200.io.ModelLoader",
     "src.models.autoencoder.pixel.PixelAE": "deco_b200.data.PixelAE",

@@ -12,6 +12,14 @@
 //   v     = c0 * pred + c1 * p1 + c2 * p2 + c3 * p3          (p_j = earlier predictions, fp32)
 //   x_out = x + dt * v
 // Euler: c0 = 1.  Heun corrector: c0 = c1 = 1/2 with p1 = predictor velocity.  Adams order k: c_j from the host.
+//
+// Extended form (EXT = true; deco_cfg_step_ex), the other step functions / samplers that share this pass:
+//   src/diffusion/flow_matching/sampling.py:170            EulerSamplerJiT: the net predicts x, u' = (u - x) / den,
+//                                                          c' = (c - x) / den with den = clamp_min(1 - t, 0.05)
+//   src/diffusion/flow_matching/sampling.py:17-24, :98     sde_mean / sde / sde_preserve step functions:
+//       s     = (kd * v - x) / sden          kd = 1 / dalpha_over_alpha(t), sden = sigma^2 - kd * dsigma_mul_sigma(t)
+//       x_out = x + dt * v + a_s * s + a_n * noise        (a_s, a_n) = (w dt, 0) | (w dt, sqrt(2 w dt)) | (w dt / 2, sqrt(w dt))
+//   noise = the caller's torch.randn_like(x) (same CUDA Philox stream as the reference's call at :21,:24)
 // Bound: HBM.  Euler algorithmic bytes / element: 4 (x) + 2*sizeof(net out) + 4 (x_out) = 12 B with bf16 net output.
 #include "common.cuh"
 
@@ -29,6 +37,10 @@ struct StepArgs {
     const float* dev;        // optional: {g, dt, c0, c1, c2, c3} in DEVICE memory (CUDA-graph replays: the step's scalars
                              // change between replays without changing the kernel arguments)
     long long n;             // elements per CFG half (B*C*H*W)
+    // extended form only
+    float xpred_den;         // > 0: the net predicts x (EulerSamplerJiT); dev[7] when dev != NULL
+    float kd, sden, a_s, a_n;
+    const float* noise;      // required when a_n != 0
 };
 
 template <typename T> struct Vec4;
@@ -54,18 +66,24 @@ __device__ __forceinline__ uint8_t to_u8(float x) {
 // INPLACE = false: inputs are read through the non-coherent path (ld.global.nc), which lets the compiler hoist the loads of
 // later grid-stride iterations above earlier stores (94 % of the HBM peak vs 76 % with plain loads); INPLACE = true (graph
 // replays update the state in place: x_out == x, pred_out == p1) must use plain loads.
-template <typename TNet, bool INPLACE>
+template <typename TNet, bool INPLACE, bool EXT = false>
 __global__ void __launch_bounds__(256) cfg_step_kernel(StepArgs a) {
     if (a.dev) {
         a.g = __ldg(a.dev); a.dt = __ldg(a.dev + 1); a.c0 = __ldg(a.dev + 2);
         a.c[0] = __ldg(a.dev + 3); a.c[1] = __ldg(a.dev + 4); a.c[2] = __ldg(a.dev + 5);
+        if (EXT) a.xpred_den = __ldg(a.dev + 7);
     }
     const long long n4 = a.n >> 2;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
         const float4 x = INPLACE ? reinterpret_cast<const float4*>(a.x)[i] : __ldg(reinterpret_cast<const float4*>(a.x) + i);
-        const float4 u = Vec4<TNet>::load(a.net_out, i);
-        const float4 c = Vec4<TNet>::load(a.net_out, i + n4);
+        float4 u = Vec4<TNet>::load(a.net_out, i);
+        float4 c = Vec4<TNet>::load(a.net_out, i + n4);
+        if (EXT && a.xpred_den > 0.f) {       // x-prediction -> velocity, each CFG half against its own copy of x
+            const float den = a.xpred_den;
+            u.x = (u.x - x.x) / den; u.y = (u.y - x.y) / den; u.z = (u.z - x.z) / den; u.w = (u.w - x.w) / den;
+            c.x = (c.x - x.x) / den; c.y = (c.y - x.y) / den; c.z = (c.z - x.z) / den; c.w = (c.w - x.w) / den;
+        }
         float4 pr;
         pr.x = u.x + a.g * (c.x - u.x);
         pr.y = u.y + a.g * (c.y - u.y);
@@ -81,6 +99,14 @@ __global__ void __launch_bounds__(256) cfg_step_kernel(StepArgs a) {
             }
         }
         float4 xo = make_float4(fmaf(a.dt, v.x, x.x), fmaf(a.dt, v.y, x.y), fmaf(a.dt, v.z, x.z), fmaf(a.dt, v.w, x.w));
+        if (EXT && a.a_s != 0.f) {            // score term of the SDE step functions
+            xo.x = fmaf(a.a_s, (a.kd * v.x - x.x) / a.sden, xo.x); xo.y = fmaf(a.a_s, (a.kd * v.y - x.y) / a.sden, xo.y);
+            xo.z = fmaf(a.a_s, (a.kd * v.z - x.z) / a.sden, xo.z); xo.w = fmaf(a.a_s, (a.kd * v.w - x.w) / a.sden, xo.w);
+        }
+        if (EXT && a.a_n != 0.f) {
+            const float4 z = __ldg(reinterpret_cast<const float4*>(a.noise) + i);
+            xo.x = fmaf(a.a_n, z.x, xo.x); xo.y = fmaf(a.a_n, z.y, xo.y); xo.z = fmaf(a.a_n, z.z, xo.z); xo.w = fmaf(a.a_n, z.w, xo.w);
+        }
         if (a.x_out) reinterpret_cast<float4*>(a.x_out)[i] = xo;
         if (a.pred_out) reinterpret_cast<float4*>(a.pred_out)[i] = pr;
         if (a.v_out) reinterpret_cast<float4*>(a.v_out)[i] = v;
@@ -127,6 +153,7 @@ extern "C" int deco_cfg_step(const float* x, const void* net_out, int net_is_bf1
     a.x = x; a.net_out = net_out; a.p[0] = p1; a.p[1] = p2; a.p[2] = p3;
     a.x_out = x_out; a.pred_out = pred_out; a.v_out = v_out; a.u8_out = u8_out;
     a.g = g; a.dt = dt; a.c0 = c0; a.c[0] = c1; a.c[1] = c2; a.c[2] = c3; a.n = n; a.dev = nullptr;
+    a.xpred_den = 0.f; a.kd = 0.f; a.sden = 1.f; a.a_s = 0.f; a.a_n = 0.f; a.noise = nullptr;
     const long long n4 = n / 4;
     long long blocks = (n4 + 255) / 256;
     const long long cap = (long long)kNumSMs * 16;   // grid-stride: 16 CTAs of 256 threads per SM
@@ -170,6 +197,7 @@ extern "C" int deco_cfg_step_dev(const float* x, const void* net_out, int net_is
     a.x = x; a.net_out = net_out; a.p[0] = p1; a.p[1] = p2; a.p[2] = p3;
     a.x_out = x_out; a.pred_out = pred_out; a.v_out = v_out; a.u8_out = u8_out;
     a.g = 1.f; a.dt = 0.f; a.c0 = 1.f; a.c[0] = 0.f; a.c[1] = 0.f; a.c[2] = 0.f; a.n = n; a.dev = dev_params;
+    a.xpred_den = 0.f; a.kd = 0.f; a.sden = 1.f; a.a_s = 0.f; a.a_n = 0.f; a.noise = nullptr;
     const long long n4 = n / 4;
     long long blocks = (n4 + 255) / 256;
     const long long cap = (long long)kNumSMs * 16;
@@ -184,6 +212,44 @@ extern "C" int deco_cfg_step_dev(const float* x, const void* net_out, int net_is
         else cfg_step_kernel<float, false><<<(unsigned)blocks, 256, 0, st>>>(a);
     }
     DECO_CHECK_LAUNCH("cfg_step_kernel");
+    return DECO_OK;
+}
+
+// Extended update (see the top of the file): x-prediction nets and the SDE step functions.  dev_params (optional, device)
+// = {g, dt, c0, c1, c2, c3, t, xpred_den} as written by deco_sampler_advance; NULL = the scalar arguments are used.
+// noise fp32 [n] is read only when a_n != 0.  x_out may alias x, pred_out may alias p1.
+extern "C" int deco_cfg_step_ex(const float* x, const void* net_out, int net_is_bf16,
+                                const float* p1, const float* p2, const float* p3, const float* dev_params,
+                                float g, float dt, float c0, float c1, float c2, float c3,
+                                float xpred_den, float kd, float sden, float a_s, float a_n, const float* noise,
+                                float* x_out, float* pred_out, float* v_out, uint8_t* u8_out, long long n, void* stream)
+{
+    using namespace deco;
+    DECO_CHECK_ARG(x && net_out, "cfg_step_ex: null input");
+    DECO_CHECK_ARG(n > 0 && (n % 4) == 0, "cfg_step_ex: element count %lld must be a positive multiple of 4", n);
+    DECO_CHECK_ARG(a_n == 0.f || noise, "cfg_step_ex: a_n != 0 needs a noise tensor");
+    DECO_CHECK_ARG(a_s == 0.f || sden != 0.f, "cfg_step_ex: zero score denominator");
+    DECO_CHECK_ARG(xpred_den >= 0.f, "cfg_step_ex: negative x-prediction denominator");
+    StepArgs a;
+    a.x = x; a.net_out = net_out; a.p[0] = p1; a.p[1] = p2; a.p[2] = p3;
+    a.x_out = x_out; a.pred_out = pred_out; a.v_out = v_out; a.u8_out = u8_out;
+    a.g = g; a.dt = dt; a.c0 = c0; a.c[0] = c1; a.c[1] = c2; a.c[2] = c3; a.n = n; a.dev = dev_params;
+    a.xpred_den = xpred_den; a.kd = kd; a.sden = sden; a.a_s = a_s; a.a_n = a_n; a.noise = noise;
+    const long long n4 = n / 4;
+    long long blocks = (n4 + 255) / 256;
+    const long long cap = (long long)kNumSMs * 16;
+    if (blocks > cap) blocks = cap;
+    const bool inplace = x_out == x || (pred_out && (pred_out == p1 || pred_out == p2 || pred_out == p3)) ||
+                         (v_out && (v_out == p1 || v_out == p2 || v_out == p3));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (net_is_bf16) {
+        if (inplace) cfg_step_kernel<__nv_bfloat16, true, true><<<(unsigned)blocks, 256, 0, st>>>(a);
+        else cfg_step_kernel<__nv_bfloat16, false, true><<<(unsigned)blocks, 256, 0, st>>>(a);
+    } else {
+        if (inplace) cfg_step_kernel<float, true, true><<<(unsigned)blocks, 256, 0, st>>>(a);
+        else cfg_step_kernel<float, false, true><<<(unsigned)blocks, 256, 0, st>>>(a);
+    }
+    DECO_CHECK_LAUNCH("cfg_step_kernel<ext>");
     return DECO_OK;
 }
 

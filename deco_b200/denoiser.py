@@ -296,6 +296,49 @@ def fused_blocks(blocks, mod: torch.Tensor, mod0: int, st: StreamState, a0: torc
     return s
 
 
+@torch.no_grad()
+def prepare_dit_blocks(blocks, H: int, device):
+    """bf16 / fp32 device copies of the AdaLN DiT blocks' weights in the layouts the fused GEMMs expect (shared by the DeCo
+    and the patch-linear baseline denoisers, whose FlattenDiTBlock is the same module: dit_c2i_DeCo.py:194-210,
+    dit_c2i_baseline.py:194-210).  Returns (list of per-block dicts, padded FFN width)."""
+    def W(t):
+        return t.detach().to(device=device, dtype=bf16).contiguous()
+
+    def Fv(t):
+        return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+    F = blocks[0].mlp.w1.weight.shape[0] if len(blocks) else 0
+    Fp = (F + 15) // 16 * 16     # pad the FFN width (L/16: 2730 -> 2736) with zero rows / columns
+    out = []
+    for b in blocks:
+        w1 = torch.zeros(Fp, H, device=device, dtype=bf16)
+        w3 = torch.zeros(Fp, H, device=device, dtype=bf16)
+        w1[:F], w3[:F] = W(b.mlp.w1.weight), W(b.mlp.w3.weight)
+        # interleave 16 rows of w1 with 16 rows of w3 so that one 32-column accumulator chunk holds matching pairs
+        w13 = torch.stack([w1.view(Fp // 16, 16, H), w3.view(Fp // 16, 16, H)], dim=1).reshape(2 * Fp, H).contiguous()
+        w2 = torch.zeros(H, Fp, device=device, dtype=bf16)
+        w2[:, :F] = W(b.mlp.w2.weight)
+        out.append(dict(n1=Fv(b.norm1.weight), wqkv=W(b.attn.qkv.weight), qn=Fv(b.attn.q_norm.weight),
+                        kn=Fv(b.attn.k_norm.weight), wproj=W(b.attn.proj.weight), bproj=Fv(b.attn.proj.bias),
+                        n2=Fv(b.norm2.weight), w13=w13, w2=w2))
+    return out, Fp
+
+
+@torch.no_grad()
+def composite_shift_weights(blocks, prepared, H: int, device):
+    """(W . Wada_shift, W . bada_shift) for W = wqkv and w13 of every block, concatenated in block order: see
+    PixNerDiT._composite_shift."""
+    wc, bc = [], []
+    for b, bp in zip(blocks, prepared):
+        wa = b.adaLN_modulation[0].weight.detach().to(device=device, dtype=torch.float32)
+        ba = b.adaLN_modulation[0].bias.detach().to(device=device, dtype=torch.float32)
+        for wmat, lo in ((bp["wqkv"], 0), (bp["w13"], 3 * H)):
+            wf = wmat.float()
+            wc.append((wf @ wa[lo:lo + H]).to(bf16))
+            bc.append(wf @ ba[lo:lo + H])
+    return torch.cat(wc, 0).contiguous(), torch.cat(bc, 0).contiguous()
+
+
 # ------------------------------------------------------------------------------------------------ the module
 class PixNerDiT(nn.Module):
     """Drop-in for src/models/transformer/dit_c2i_DeCo.py::PixNerDiT (constructor :417-433, forward :488-510)."""
@@ -371,22 +414,7 @@ class PixNerDiT(nn.Module):
         P["ytab"] = Fv(self.y_embedder.embedding_table.weight)
         P["wada"] = W(torch.cat([b.adaLN_modulation[0].weight for b in self.blocks], 0))
         P["bada"] = Fv(torch.cat([b.adaLN_modulation[0].bias for b in self.blocks], 0))
-        F = self.blocks[0].mlp.w1.weight.shape[0] if len(self.blocks) else 0
-        Fp = (F + 15) // 16 * 16     # pad the FFN width (L/16: 2730 -> 2736) with zero rows / columns
-        P["ffn_pad"] = Fp
-        blocks = []
-        for b in self.blocks:
-            w1 = torch.zeros(Fp, H, device=device, dtype=bf16)
-            w3 = torch.zeros(Fp, H, device=device, dtype=bf16)
-            w1[:F], w3[:F] = W(b.mlp.w1.weight), W(b.mlp.w3.weight)
-            # interleave 16 rows of w1 with 16 rows of w3 so that one 32-column accumulator chunk holds matching pairs
-            w13 = torch.stack([w1.view(Fp // 16, 16, H), w3.view(Fp // 16, 16, H)], dim=1).reshape(2 * Fp, H).contiguous()
-            w2 = torch.zeros(H, Fp, device=device, dtype=bf16)
-            w2[:, :F] = W(b.mlp.w2.weight)
-            blocks.append(dict(n1=Fv(b.norm1.weight), wqkv=W(b.attn.qkv.weight), qn=Fv(b.attn.q_norm.weight),
-                               kn=Fv(b.attn.k_norm.weight), wproj=W(b.attn.proj.weight), bproj=Fv(b.attn.proj.bias),
-                               n2=Fv(b.norm2.weight), w13=w13, w2=w2))
-        P["blocks"] = blocks
+        P["blocks"], P["ffn_pad"] = prepare_dit_blocks(self.blocks, H, device)
         P["wcond"], P["bcond"] = W(self.dec_net.cond_embed.weight), Fv(self.dec_net.cond_embed.bias)
         P["blob"], P["postab"] = self._pack_decoder(device)
         self._prep, self._prep_key = P, key
@@ -398,16 +426,7 @@ class PixNerDiT(nn.Module):
         batch-sized shift products of a forward collapse into ONE GEMM of c against these composite weights (at 8-GPU
         sharding the 56 tiny launches were 4 % of a step).  Built on first use by the fused inference path and cached with
         the prepared weights (a training loop that changes the weights every step never pays for it)."""
-        H = self.hidden_size
-        wc, bc = [], []
-        for b, bp in zip(self.blocks, P["blocks"]):
-            wa = b.adaLN_modulation[0].weight.detach().to(device=device, dtype=torch.float32)
-            ba = b.adaLN_modulation[0].bias.detach().to(device=device, dtype=torch.float32)
-            for wmat, lo in ((bp["wqkv"], 0), (bp["w13"], 3 * H)):
-                wf = wmat.float()
-                wc.append((wf @ wa[lo:lo + H]).to(bf16))
-                bc.append(wf @ ba[lo:lo + H])
-        return torch.cat(wc, 0).contiguous(), torch.cat(bc, 0).contiguous()
+        return composite_shift_weights(self.blocks, P["blocks"], self.hidden_size, device)
 
     def _pack_decoder(self, device):
         key = ("nerf_tab", str(device))

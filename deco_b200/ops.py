@@ -342,6 +342,62 @@ def cfg_step_dev(x: torch.Tensor, net_out: torch.Tensor, cur: torch.Tensor, x_ou
          ptr(x_out), ptr(pred_out), None, ptr(u8_out), x.numel(), _st(x))
 
 
+def cfg_step_ex(x: torch.Tensor, net_out: torch.Tensor, g: float = 1.0, dt: float = 0.0, c0: float = 1.0,
+                prev=(), coeffs=(), dev: Optional[torch.Tensor] = None, xpred_den: float = 0.0,
+                kd: float = 0.0, sden: float = 1.0, a_s: float = 0.0, a_n: float = 0.0,
+                noise: Optional[torch.Tensor] = None, x_out: Optional[torch.Tensor] = None,
+                pred_out: Optional[torch.Tensor] = None, want_pred: bool = False, want_v: bool = False,
+                want_u8: bool = False, u8_out: Optional[torch.Tensor] = None):
+    """Extended sampler update (csrc/sampler.cu, deco_cfg_step_ex): x-prediction nets (xpred_den > 0, EulerSamplerJiT) and
+    the SDE step functions (score coefficient a_s, noise coefficient a_n).  dev: device vector {g, dt, c0, c1, c2, c3, t,
+    xpred_den} for graph replays (then g .. c0 / xpred_den are ignored).  Returns (x_out, pred, v, u8)."""
+    _cuda(x, net_out, noise, dev, x_out, pred_out, u8_out)
+    assert x.dtype == torch.float32 and x.is_contiguous() and net_out.is_contiguous()
+    assert net_out.shape[0] == 2 * x.shape[0] and net_out.shape[1:] == x.shape[1:]
+    assert net_out.dtype in (bf16, torch.float32)
+    assert len(prev) == len(coeffs) <= 3
+    if noise is not None:
+        assert noise.dtype == torch.float32 and noise.is_contiguous() and noise.shape == x.shape
+    if x_out is None:
+        x_out = torch.empty_like(x)
+    pred = pred_out if pred_out is not None else (torch.empty_like(x) if want_pred else None)
+    v = torch.empty_like(x) if want_v else None
+    u8 = u8_out if u8_out is not None else (torch.empty(x.shape, dtype=torch.uint8, device=x.device) if want_u8 else None)
+    ps = [None, None, None]
+    cs = [0.0, 0.0, 0.0]
+    for j, (p, c) in enumerate(zip(prev, coeffs)):
+        assert p.dtype == torch.float32 and p.is_contiguous() and p.shape == x.shape
+        ps[j], cs[j] = p, float(c)
+    call("deco_cfg_step_ex", ptr(x), ptr(net_out), int(net_out.dtype == bf16), ptr(ps[0]), ptr(ps[1]), ptr(ps[2]), ptr(dev),
+         float(g), float(dt), float(c0), cs[0], cs[1], cs[2], float(xpred_den), float(kd), float(sden), float(a_s),
+         float(a_n), ptr(noise), ptr(x_out), ptr(pred), ptr(v), ptr(u8), x.numel(), _st(x))
+    return x_out, pred, v, u8
+
+
+def layernorm_modulate(x: torch.Tensor, shift: torch.Tensor, scale: torch.Tensor, rows_per_mod: int, eps: float = 1e-6,
+                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """LayerNorm (no affine) + modulate of the fp32 stream x [M, H] -> bf16 (dit_c2i_baseline.py:76-82); shift / scale: bf16
+    views [M / rows_per_mod, H] sharing one row stride."""
+    _cuda(x, shift, scale)
+    assert x.dtype == torch.float32 and x.is_contiguous() and shift.dtype == bf16 and scale.dtype == bf16
+    M, Hd = x.shape
+    assert shift.stride(0) == scale.stride(0) and shift.stride(1) == 1 and scale.stride(1) == 1
+    if out is None:
+        out = torch.empty(x.shape, dtype=bf16, device=x.device)
+    call("deco_layernorm_modulate", ptr(x), ptr(shift), ptr(scale), shift.stride(0), rows_per_mod, ptr(out), M, Hd,
+         float(eps), _st(x))
+    return out
+
+
+def unpatchify(tok: torch.Tensor, B: int, C: int, H: int, W: int, p: int) -> torch.Tensor:
+    """F.fold(kernel = stride = p) of bf16 tokens [B*L, C*p*p] -> [B, C, H, W] (dit_c2i_baseline.py:378)."""
+    _cuda(tok)
+    assert tok.dtype == bf16 and tok.is_contiguous() and tok.shape == (B * (H // p) * (W // p), C * p * p)
+    out = torch.empty((B, C, H, W), dtype=bf16, device=tok.device)
+    call("deco_unpatchify", ptr(tok), ptr(out), B, C, H, W, p, _st(tok))
+    return out
+
+
 def fp2uint8(x: torch.Tensor) -> torch.Tensor:
     _cuda(x)
     x = x.to(torch.float32).contiguous()

@@ -6,13 +6,17 @@ Mirrors (reference paths):
   src/diffusion/base/guidance.py:3-6                 simple_guidance_fn
   src/diffusion/flow_matching/sampling.py:11-15      shift_respace_fn, ode_step_fn
   src/diffusion/flow_matching/sampling.py:30-107     EulerSampler
+  src/diffusion/flow_matching/sampling.py:17-24      sde_mean_step_fn, sde_step_fn, sde_preserve_step_fn (Euler only)
+  src/diffusion/flow_matching/sampling.py:109-188    EulerSamplerJiT (x-prediction nets: configs_c2i/Baseline_DiT_JiT.yaml)
   src/diffusion/flow_matching/sampling.py:190-296    HeunSampler
   src/diffusion/flow_matching/adam_sampling.py:39-122 AdamLMSampler (+ src/diffusion/pre_integral.py:103-125)
 
 The schedule is precomputed on the host in fp32 with the same torch ops as the reference (so e.g.
 ts[10] = 0.09999999403953552 is *not* > 0.1) and the guidance-window test happens on the host
-copy: no per-step synchronisation.  Only ODE stepping (`ode_step_fn`) is supported, as in every DeCo config;
-the SDE step functions need on-device RNG and are out of scope.
+copy: no per-step synchronisation.  The Euler samplers also take the SDE step functions: the score coefficients are
+host scalars from the scheduler, the Gaussian increment is `torch.randn_like(x)` (torch's CUDA generator, the very call the
+reference makes, so a seeded run consumes the same Philox stream) and everything else is the same fused update kernel
+(csrc/sampler.cu, extended form).  Heun and Adams stay ODE-only, as in every config of the reference.
 """
 from __future__ import annotations
 
@@ -41,6 +45,28 @@ def shift_respace_fn(t, shift=3.0):
 
 def ode_step_fn(x, v, dt, s, w):
     return x + v * dt
+
+
+def sde_mean_step_fn(x, v, dt, s, w):
+    return x + v * dt + s * w * dt
+
+
+def sde_step_fn(x, v, dt, s, w):
+    return x + v * dt + s * w * dt + torch.sqrt(2 * w * dt) * torch.randn_like(x)
+
+
+def sde_preserve_step_fn(x, v, dt, s, w):
+    return x + v * dt + 0.5 * s * w * dt + torch.sqrt(w * dt) * torch.randn_like(x)
+
+
+_STEP_FNS = ("ode_step_fn", "sde_mean_step_fn", "sde_step_fn", "sde_preserve_step_fn")
+
+
+def _step_kind(fn) -> str:
+    name = getattr(fn, "__name__", "")
+    if name not in _STEP_FNS:
+        raise NotImplementedError(f"step function {name or fn!r} is not one of {_STEP_FNS}")
+    return name
 
 
 def _make_timesteps(num_steps, last_step, timeshift):
@@ -156,6 +182,7 @@ class GraphedStepper:
         self.cond = torch.zeros((2 * batch,) + tuple(cond_like.shape[1:]), dtype=cond_like.dtype, device=dev)
         self.u8 = torch.zeros(self.x.shape, dtype=torch.uint8, device=dev) if to_uint8 else None
         self.pred = torch.zeros_like(self.x) if use_pred else None
+        self.xpred = bool(getattr(sampler, "x_prediction", False))
         cur_stream = torch.cuda.current_stream(dev)
         side = torch.cuda.Stream(dev)
         side.wait_stream(cur_stream)
@@ -175,7 +202,10 @@ class GraphedStepper:
         out = self.net(torch.cat([self.x, self.x], dim=0), self.t, self.cond)
         if out.dtype not in (torch.bfloat16, torch.float32):
             out = out.float()
-        ops.cfg_step_dev(self.x, out.contiguous(), self.cur, self.x, p1=self.pred, pred_out=self.pred, u8_out=self.u8)
+        if self.xpred:      # EulerSamplerJiT: column 7 of the schedule row is the x-prediction denominator
+            ops.cfg_step_ex(self.x, out.contiguous(), dev=self.cur, x_out=self.x, u8_out=self.u8)
+        else:
+            ops.cfg_step_dev(self.x, out.contiguous(), self.cur, self.x, p1=self.pred, pred_out=self.pred, u8_out=self.u8)
 
     def reset(self, x, cfg_condition):
         self.x.copy_(x)
@@ -199,6 +229,8 @@ def _net_eval(net, x, t_scalar: float, cfg_condition, batch_size):
 
 
 class EulerSampler(BaseSampler):
+    x_prediction = False    # EulerSamplerJiT: the net predicts x instead of v
+
     def __init__(self, w_scheduler: BaseScheduler = None, timeshift=1.0, guidance_interval_min: float = 0.0,
                  guidance_interval_max: float = 1.0, step_fn: Callable = ode_step_fn, last_step=None,
                  last_step_fn: Callable = ode_step_fn, *args, **kwargs):
@@ -215,16 +247,44 @@ class EulerSampler(BaseSampler):
         self.timesteps = _make_timesteps(self.num_steps, self.last_step, self.timeshift)
         assert self.last_step > 0.0
         assert self.scheduler is not None
-        for fn in (self.step_fn, self.last_step_fn):
-            if getattr(fn, "__name__", "") != "ode_step_fn":
-                raise NotImplementedError("only ode_step_fn is supported (SDE steps are out of scope)")
+        self._kinds = (_step_kind(self.step_fn), _step_kind(self.last_step_fn))
+        assert self.w_scheduler is not None or self._kinds[0] == "ode_step_fn"      # sampling.py:61
+        if self.w_scheduler is not None and self._kinds[0] == "ode_step_fn":
+            logger.warning("current sampler is ODE sampler, but w_scheduler is enabled")
+
+    def _xpred_den(self, t_cur) -> float:
+        """(1 - t).clamp_min(5e-2) in fp32 (sampling.py:170); 0 = the net already predicts v."""
+        return float((1.0 - t_cur).clamp_min(5e-2)) if self.x_prediction else 0.0
+
+    def _sde_scalars(self, t_cur, dt, kind):
+        """(kd, sden, a_s, a_n) of one step: the score s = (kd v - x) / sden (sampling.py:98) and the coefficients of s and
+        of the Gaussian increment in `kind` (:17-24), evaluated with the reference's fp32 torch expressions on the
+        scheduler's own methods."""
+        if kind == "ode_step_fn":
+            return 0.0, 1.0, 0.0, 0.0
+        tt = t_cur.reshape(1)
+        sigma = self.scheduler.sigma(tt)
+        kd = 1 / self.scheduler.dalpha_over_alpha(tt)
+        sden = sigma ** 2 - kd * self.scheduler.dsigma_mul_sigma(tt)
+        w = self.w_scheduler.w(tt) if self.w_scheduler else torch.zeros(1)
+        w = torch.as_tensor(w, dtype=torch.float32).reshape(-1)[:1]
+        if kind == "sde_mean_step_fn":
+            a_s, a_n = w * dt, torch.zeros(1)
+        elif kind == "sde_step_fn":
+            a_s, a_n = w * dt, torch.sqrt(2 * w * dt)
+        else:
+            a_s, a_n = 0.5 * w * dt, torch.sqrt(w * dt)
+        return float(kd.reshape(-1)[0]), float(sden.reshape(-1)[0]), float(a_s.reshape(-1)[0]), float(a_n.reshape(-1)[0])
 
     def _graph_rows(self):
+        if self._kinds != ("ode_step_fn", "ode_step_fn"):
+            return None               # SDE steps draw fresh noise per step: eager loop
         rows, ts = [], self.timesteps
         for i in range(self.num_steps):
             t_cur, t_next = ts[i], ts[i + 1]
             in_window = bool(t_cur > self.guidance_interval_min) and bool(t_cur <= self.guidance_interval_max)
-            rows.append([float(self.guidance) if in_window else 1.0, float(t_next - t_cur), 1.0, 0.0, 0.0, 0.0, float(t_cur), 0.0])
+            rows.append([float(self.guidance) if in_window else 1.0, float(t_next - t_cur), 1.0, 0.0, 0.0, 0.0, float(t_cur),
+                         self._xpred_den(t_cur)])
         return rows, False
 
     def _impl_sampling(self, net, noise, condition, uncondition, keep_x=False, keep_v=False, to_uint8=False):
@@ -236,6 +296,7 @@ class EulerSampler(BaseSampler):
             if res is not None:
                 return res
         x_trajs, v_trajs, u8 = ([x] if keep_x else None), ([] if keep_v else None), None
+        plain = not self.x_prediction and self._kinds == ("ode_step_fn", "ode_step_fn")
         for i in range(self.num_steps):
             t_cur, t_next = steps[i], steps[i + 1]
             dt = float(t_next - t_cur)
@@ -243,7 +304,13 @@ class EulerSampler(BaseSampler):
             in_window = bool(t_cur > self.guidance_interval_min) and bool(t_cur <= self.guidance_interval_max)
             g = float(self.guidance) if in_window else 1.0
             last = i == self.num_steps - 1
-            x, _, v, u = ops.cfg_step(x, out, g, dt, want_v=keep_v, want_u8=(to_uint8 and last))
+            if plain:
+                x, _, v, u = ops.cfg_step(x, out, g, dt, want_v=keep_v, want_u8=(to_uint8 and last))
+            else:
+                kd, sden, a_s, a_n = self._sde_scalars(t_cur, t_next - t_cur, self._kinds[1 if last else 0])
+                z = torch.randn_like(x) if a_n != 0.0 else None
+                x, _, v, u = ops.cfg_step_ex(x, out, g, dt, xpred_den=self._xpred_den(t_cur), kd=kd, sden=sden, a_s=a_s,
+                                             a_n=a_n, noise=z, want_v=keep_v, want_u8=(to_uint8 and last))
             if keep_x:
                 x_trajs.append(x)
             if keep_v:
@@ -253,6 +320,12 @@ class EulerSampler(BaseSampler):
         if keep_v:
             v_trajs.append(torch.zeros_like(x))
         return x, x_trajs, v_trajs, u8
+
+
+class EulerSamplerJiT(EulerSampler):
+    """src/diffusion/flow_matching/sampling.py:109-188: the Euler loop for a net that predicts the clean image; the
+    velocity is (out - x) / clamp_min(1 - t, 0.05) per CFG half (:170), folded into the update kernel."""
+    x_prediction = True
 
 
 class HeunSampler(BaseSampler):

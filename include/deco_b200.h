@@ -176,6 +176,29 @@ int deco_cfg_step_dev(const float* x, const void* net_out, int net_is_bf16,
                       const float* p1, const float* p2, const float* p3, const float* dev_params,
                       float* x_out, float* pred_out, float* v_out, uint8_t* u8_out, long long n, void* stream);
 
+/* The same pass for the other samplers / step functions that share it (flow_matching/sampling.py):
+ *   xpred_den > 0 (EulerSamplerJiT, :170): the net predicts x; u' = (u - x) / xpred_den, c' = (c - x) / xpred_den with
+ *     xpred_den = clamp_min(1 - t, 0.05), then pred = u' + g (c' - u')
+ *   SDE step functions (:17-24, score at :98): s = (kd v - x) / sden, kd = 1 / dalpha_over_alpha(t),
+ *     sden = sigma(t)^2 - kd dsigma_mul_sigma(t);  x_out = x + dt v + a_s s + a_n noise with
+ *     (a_s, a_n) = (w dt, 0) sde_mean | (w dt, sqrt(2 w dt)) sde | (w dt / 2, sqrt(w dt)) sde_preserve; noise fp32 [n]
+ *     (caller-generated N(0,1)), read only when a_n != 0
+ * dev_params: NULL, or the device vector {g, dt, c0, c1, c2, c3, t, xpred_den} written by deco_sampler_advance (then the
+ * scalar g..c3 and xpred_den arguments are ignored).  x_out may alias x, pred_out may alias p1. */
+int deco_cfg_step_ex(const float* x, const void* net_out, int net_is_bf16,
+                     const float* p1, const float* p2, const float* p3, const float* dev_params,
+                     float g, float dt, float c0, float c1, float c2, float c3,
+                     float xpred_den, float kd, float sden, float a_s, float a_n, const float* noise,
+                     float* x_out, float* pred_out, float* v_out, uint8_t* u8_out, long long n, void* stream);
+
+/* Output head of the patch-linear baseline denoiser (models/transformer/dit_c2i_baseline.py):
+ * deco_layernorm_modulate = FinalLayer's LayerNorm(no affine) + modulate (:76-82) on the fp32 stream x [M, hidden]
+ *   -> bf16 [M, hidden]; shift / scale bf16 rows (one per rows_per_mod stream rows) sharing mod_row_stride;
+ * deco_unpatchify = F.fold(kernel = stride = p) (:378): tokens bf16 [B*L, C*p*p] -> image bf16 [B, C, H, W]. */
+int deco_layernorm_modulate(const float* x, const void* shift_bf16, const void* scale_bf16, long long mod_row_stride,
+                            int rows_per_mod, void* out_bf16, long long M, int hidden, float eps, void* stream);
+int deco_unpatchify(const void* tok_bf16, void* out_bf16, int B, int C, int H, int W, int p, void* stream);
+
 /* Frequency-aware FM loss, forward and/or backward in one pass
  * (flow_matching/training_repa_DeCo.py:106-136 _rgb2ycbcr/_dct, :138-195 weights, :273-285 loss):
  *   losses[0] = mean((out - v_t)^2), losses[1] = mean(freq_w * dct(ycbcr(out - v_t))^2), losses[2] = [0] + flw * [1]

@@ -717,3 +717,147 @@ def t2i_forward(P: Params, cfg: T2ICfg, x: torch.Tensor, t: torch.Tensor, y: tor
     out = pixel_decoder(P, dcfg, px, s.reshape(B * L, H))
     out = out.transpose(1, 2).reshape(B, L, -1)
     return F.fold(out.transpose(1, 2).contiguous(), (Hh, Ww), kernel_size=p, stride=p)
+
+
+# --------------------------------------------------------------------------- patch-linear baseline denoiser
+@dataclass(frozen=True)
+class BaselineCfg:
+    """Constructor arguments of FlattenDiT (src/models/transformer/dit_c2i_baseline.py:290-303;
+    configs_c2i/Baseline_DiT_JiT.yaml:46-54)."""
+    in_channels: int = 3
+    num_groups: int = 16
+    hidden_size: int = 1024
+    num_blocks: int = 24
+    patch_size: int = 16
+    num_classes: int = 1000
+
+    @property
+    def head_dim(self) -> int:
+        return self.hidden_size // self.num_groups
+
+    @property
+    def ffn_hidden(self) -> int:
+        return int(2 * int(self.hidden_size * 4.0) / 3)      # dit_c2i_baseline.py:200, :108
+
+
+def baseline_param_shapes(cfg: BaselineCfg) -> Dict[str, Tuple[int, ...]]:
+    """state_dict names and shapes of FlattenDiT (dit_c2i_baseline.py:312-322)."""
+    H, p, C = cfg.hidden_size, cfg.patch_size, cfg.in_channels
+    d, ffn = cfg.head_dim, cfg.ffn_hidden
+    s: Dict[str, Tuple[int, ...]] = {
+        "x_embedder.proj.weight": (H, C * p * p),
+        "x_embedder.proj.bias": (H,),
+        "t_embedder.mlp.0.weight": (H, 256),
+        "t_embedder.mlp.0.bias": (H,),
+        "t_embedder.mlp.2.weight": (H, H),
+        "t_embedder.mlp.2.bias": (H,),
+        "y_embedder.embedding_table.weight": (cfg.num_classes + 1, H),
+        "final_layer.linear.weight": (C * p * p, H),
+        "final_layer.linear.bias": (C * p * p,),
+        "final_layer.adaLN_modulation.0.weight": (2 * H, H),
+        "final_layer.adaLN_modulation.0.bias": (2 * H,),
+    }
+    for i in range(cfg.num_blocks):
+        b = f"blocks.{i}."
+        s[b + "norm1.weight"] = (H,)
+        s[b + "attn.qkv.weight"] = (3 * H, H)
+        s[b + "attn.q_norm.weight"] = (d,)
+        s[b + "attn.k_norm.weight"] = (d,)
+        s[b + "attn.proj.weight"] = (H, H)
+        s[b + "attn.proj.bias"] = (H,)
+        s[b + "norm2.weight"] = (H,)
+        s[b + "mlp.w1.weight"] = (ffn, H)
+        s[b + "mlp.w3.weight"] = (ffn, H)
+        s[b + "mlp.w2.weight"] = (H, ffn)
+        s[b + "adaLN_modulation.0.weight"] = (6 * H, H)
+        s[b + "adaLN_modulation.0.bias"] = (6 * H,)
+    return s
+
+
+def baseline_seeded_params(cfg: BaselineCfg, seed: int = 2468, device="cpu") -> Params:
+    """Fully non-zero seeded weights (the default init zeroes the whole final layer, dit_c2i_baseline.py:351-355)."""
+    out: Params = {}
+    for idx, (name, shape) in enumerate(sorted(baseline_param_shapes(cfg).items())):
+        g = torch.Generator().manual_seed(seed * 100003 + idx)
+        if name.startswith("y_embedder"):
+            w = torch.randn(shape, generator=g) * 0.5
+        elif len(shape) == 2:
+            std = 1.0 / math.sqrt(shape[1])
+            if "adaLN_modulation" in name:
+                std *= 0.5
+            w = torch.randn(shape, generator=g) * std
+        elif name.endswith("norm.weight") or name.endswith("norm1.weight") or name.endswith("norm2.weight"):
+            w = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        else:
+            w = 0.05 * torch.randn(shape, generator=g)
+        out[name] = w.to(device)
+    return out
+
+
+def baseline_forward(P: Params, cfg: BaselineCfg, x: torch.Tensor, t: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """FlattenDiT.forward (dit_c2i_baseline.py:357-379) with FinalLayer (:70-83); the blocks are `dit_block`
+    (dit_c2i_baseline.py:194-210 is the module of dit_c2i_DeCo.py:194-210)."""
+    B, _, Hh, Ww = x.shape
+    p, H = cfg.patch_size, cfg.hidden_size
+    angles = rope_table_2d(cfg.head_dim, Hh // p, Ww // p).to(x.device)
+    h = F.unfold(x, kernel_size=p, stride=p).transpose(1, 2)
+    h = F.linear(h, P["x_embedder.proj.weight"], P["x_embedder.proj.bias"])
+    tf = timestep_embedding(t.view(-1))
+    te = F.linear(F.silu(F.linear(tf, P["t_embedder.mlp.0.weight"], P["t_embedder.mlp.0.bias"])),
+                  P["t_embedder.mlp.2.weight"], P["t_embedder.mlp.2.bias"]).view(B, -1, H)
+    ye = F.embedding(y, P["y_embedder.embedding_table.weight"]).view(B, 1, H)
+    c = F.silu(te + ye)
+    for i in range(cfg.num_blocks):
+        h = dit_block(P, i, h, c, angles, cfg.num_groups)
+    shift, scale = F.linear(c, P["final_layer.adaLN_modulation.0.weight"],
+                            P["final_layer.adaLN_modulation.0.bias"]).chunk(2, dim=-1)
+    h = modulate(F.layer_norm(h, (H,), None, None, 1e-6), shift, scale)
+    h = F.linear(h, P["final_layer.linear.weight"], P["final_layer.linear.bias"])
+    return F.fold(h.transpose(1, 2).contiguous(), (Hh, Ww), kernel_size=p, stride=p)
+
+
+# --------------------------------------------------------------------------- Euler variants: x-prediction and SDE steps
+def linear_score_terms(t: torch.Tensor):
+    """LinearScheduler (flow_matching/scheduling.py:6-14): returns (1/dalpha_over_alpha, sigma, dsigma_mul_sigma) at
+    scalar t, as the sampler evaluates them (sampling.py:81-83)."""
+    alpha, sigma = t, 1 - t
+    return 1 / (1.0 / alpha), sigma, -1.0 * sigma
+
+
+def euler_sample_ex(net: Callable, noise: torch.Tensor, cond: torch.Tensor, uncond: torch.Tensor, num_steps: int,
+                    guidance: float, gmin: float = 0.0, gmax: float = 1.0, timeshift: float = 1.0,
+                    last_step: Optional[float] = None, x_prediction: bool = False, step: str = "ode",
+                    last: str = "ode", w_fn: Optional[Callable] = None, randn: Optional[Callable] = None):
+    """EulerSampler / EulerSamplerJiT._impl_sampling with LinearScheduler and any step function
+    (flow_matching/sampling.py:66-107, :144-188; step functions :14-24).  step / last in {"ode", "sde_mean", "sde",
+    "sde_preserve"}; w_fn(t) = w_scheduler.w (default: sigma = 1 - t, base/scheduling.py:31-32); randn(x) supplies the
+    Gaussian increments (default torch.randn_like: the reference's own call)."""
+    steps = make_timesteps(num_steps, timeshift, last_step).to(noise.device, noise.dtype)
+    B = noise.shape[0]
+    cfg_c = torch.cat([uncond, cond], dim=0)
+    randn = randn or torch.randn_like
+    w_fn = w_fn or (lambda t: 1 - t)
+    x = noise
+    for i, (t_cur, t_next) in enumerate(zip(steps[:-1], steps[1:])):
+        dt = t_next - t_cur
+        cfg_x = torch.cat([x, x], 0)
+        out = net(cfg_x, t_cur.repeat(2 * B), cfg_c)
+        if x_prediction:
+            out = (out - cfg_x) / (1.0 - t_cur).clamp_min(5e-2)                      # sampling.py:170
+        g = guidance if (t_cur > gmin and t_cur <= gmax) else 1.0
+        v = cfg_combine(out, g)
+        kd, sigma, dms = linear_score_terms(t_cur)
+        s = (kd * v - x) / (sigma ** 2 - kd * dms)                                     # sampling.py:98
+        w = w_fn(t_cur)
+        kind = step if i < num_steps - 1 else last
+        if kind == "ode":
+            x = x + v * dt
+        elif kind == "sde_mean":
+            x = x + v * dt + s * w * dt
+        elif kind == "sde":
+            x = x + v * dt + s * w * dt + torch.sqrt(2 * w * dt) * randn(x)
+        elif kind == "sde_preserve":
+            x = x + v * dt + 0.5 * s * w * dt + torch.sqrt(w * dt) * randn(x)
+        else:
+            raise ValueError(kind)
+    return x

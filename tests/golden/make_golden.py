@@ -34,6 +34,10 @@ from src.diffusion.flow_matching.scheduling import LinearScheduler as RefSched  
 from src.diffusion.base.guidance import simple_guidance_fn as ref_guidance  # noqa: E402
 from src.diffusion.flow_matching.training_repa_DeCo import REPATrainer as RefTrainer  # noqa: E402
 
+from src.models.transformer.dit_c2i_baseline import FlattenDiT as RefFlattenDiT  # noqa: E402
+from src.diffusion.flow_matching.sampling import (EulerSamplerJiT as RefEulerJiT, sde_mean_step_fn, sde_step_fn,  # noqa: E402
+                                                  sde_preserve_step_fn)
+
 from oracle import deco_oracle as O  # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
@@ -283,8 +287,90 @@ def golden_t2i(name, cfg, B, res, seed):
                                       cfg.patch_size, cfg.txt_embed_dim, cfg.txt_max_length]))
 
 
+def golden_baseline(name, cfg, B, res, seed):
+    """Patch-linear baseline denoiser (dit_c2i_baseline.FlattenDiT): oracle pinned, fixture written."""
+    m = RefFlattenDiT(in_channels=cfg.in_channels, num_groups=cfg.num_groups, hidden_size=cfg.hidden_size,
+                      num_blocks=cfg.num_blocks, patch_size=cfg.patch_size, num_classes=cfg.num_classes)
+    P = O.baseline_seeded_params(cfg)
+    sd = m.state_dict()
+    assert set(sd.keys()) == set(P.keys()), set(sd.keys()) ^ set(P.keys())
+    for k in sd:
+        assert tuple(sd[k].shape) == tuple(P[k].shape), k
+    m.load_state_dict(P)
+    m.eval()
+    x = seeded_noise(B, (cfg.in_channels, res, res), seed)
+    t = torch.linspace(0.05, 0.95, B)
+    y = torch.tensor([(5 * i + 2) % (cfg.num_classes + 1) for i in range(B)])
+    y[-1] = cfg.num_classes
+    ref = m(x, t, y)
+    e = rel_l2(O.baseline_forward(P, cfg, x, t, y), ref)
+    print(f"[{name}] oracle vs reference FlattenDiT forward rel-L2 = {e:.3e}")
+    assert e < 2e-6, e
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        ref_bf = m(x, t, y).float()
+    print(f"[{name}] reference bf16-autocast vs fp32 rel-L2 = {rel_l2(ref_bf, ref):.3e} (noise floor)")
+    np.savez_compressed(os.path.join(OUT, f"{name}.npz"), x=x.numpy(), t=t.numpy(), y=y.numpy(), out=ref.numpy(),
+                        cfg=np.array([cfg.in_channels, cfg.num_groups, cfg.hidden_size, cfg.num_blocks, cfg.patch_size,
+                                      cfg.num_classes]), bf16_floor=np.float64(rel_l2(ref_bf, ref)))
+
+
+def golden_samplers_ext():
+    """EulerSamplerJiT and the SDE step functions of EulerSampler, pinned with analytic 'networks'.  The Gaussian increments
+    of sde_step_fn / sde_preserve_step_fn are the reference's own torch.randn_like calls under torch.manual_seed; they are
+    recorded so a consumer can replay them."""
+    def toy_net(x, t, y):
+        return torch.tanh(x * (0.5 + t.view(-1, 1, 1, 1))) - 0.1 * y.view(-1, 1, 1, 1).float()
+
+    def toy_xnet(x, t, y):      # an x-prediction: bounded image estimate
+        return torch.tanh(0.7 * x + 0.3 * t.view(-1, 1, 1, 1)) - 0.05 * y.view(-1, 1, 1, 1).float()
+
+    noise = seeded_noise(3, (3, 8, 8), 200)
+    cond, unc = torch.tensor([1, 2, 3]), torch.tensor([10, 10, 10])
+    sch = RefSched()
+    out = {"noise": noise.numpy()}
+    for n, g, lo, hi, shift in [(12, 2.5, 0.1, 1.0, 1.0), (30, 1.5, 0.0, 0.8, 2.0)]:
+        j = RefEulerJiT(scheduler=sch, w_scheduler=sch, guidance_fn=ref_guidance, num_steps=n, guidance=g,
+                        guidance_interval_min=lo, guidance_interval_max=hi, timeshift=shift, step_fn=ode_step_fn)
+        r = j(toy_xnet, noise, cond, unc)
+        o = O.euler_sample_ex(toy_xnet, noise, cond, unc, n, g, lo, hi, shift, x_prediction=True)
+        assert rel_l2(o, r) < 1e-6, rel_l2(o, r)
+        out[f"jit_{n}"] = r.numpy()
+    fns = {"sde_mean": sde_mean_step_fn, "sde": sde_step_fn, "sde_preserve": sde_preserve_step_fn}
+    for kind, fn in fns.items():
+        for n, g, shift, last in [(10, 2.0, 1.0, "ode"), (6, 1.0, 2.0, kind)]:
+            e = RefEuler(scheduler=sch, w_scheduler=sch, guidance_fn=ref_guidance, num_steps=n, guidance=g,
+                         guidance_interval_min=0.1, guidance_interval_max=1.0, timeshift=shift, step_fn=fn,
+                         last_step_fn=(ode_step_fn if last == "ode" else fn))
+            incs = []
+            real = torch.randn_like
+
+            def rec(x):
+                z = real(x)
+                incs.append(z)
+                return z
+            torch.manual_seed(77)
+            torch.randn_like = rec
+            try:
+                r = e(toy_net, noise, cond, unc)
+            finally:
+                torch.randn_like = real
+            torch.manual_seed(77)
+            o = O.euler_sample_ex(toy_net, noise, cond, unc, n, g, 0.1, 1.0, shift, step=kind, last=last)
+            assert rel_l2(o, r) < 1e-6, (kind, rel_l2(o, r))
+            out[f"{kind}_{n}"] = r.numpy()
+            if incs:
+                out[f"{kind}_{n}_increments"] = torch.stack(incs).numpy()
+    np.savez_compressed(os.path.join(OUT, "samplers_ext_toy.npz"), **out)
+    print("[samplers-ext] EulerSamplerJiT / sde_mean / sde / sde_preserve oracle == reference")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["dct", "samplers", "tiny", "t2i", "cfg1"]
+    which = sys.argv[1:] or ["dct", "samplers", "tiny", "t2i", "cfg1", "baseline", "samplers_ext"]
+    if "baseline" in which:
+        golden_baseline("baseline_d64", O.BaselineCfg(num_groups=4, hidden_size=256, num_blocks=3, num_classes=10),
+                        B=3, res=64, seed=41)
+    if "samplers_ext" in which:
+        golden_samplers_ext()
     if "dct" in which:
         golden_dct()
     if "samplers" in which:

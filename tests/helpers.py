@@ -71,3 +71,26 @@ def build_t2i_module(cfg: O.T2ICfg, device, seed=4321):
     m = m.to_empty(device=device)
     m.load_state_dict({k: v.to(device) for k, v in P.items()})
     return m.eval(), P
+
+
+def toy_xnet(x, t, y):
+    """Analytic x-prediction stand-in used for the EulerSamplerJiT fixtures (tests/golden/make_golden.py)."""
+    return torch.tanh(0.7 * x + 0.3 * t.view(-1, 1, 1, 1)) - 0.05 * y.view(-1, 1, 1, 1).float()
+
+
+def baseline_cfg_from_array(a) -> O.BaselineCfg:
+    a = [int(v) for v in a]
+    return O.BaselineCfg(in_channels=a[0], num_groups=a[1], hidden_size=a[2], num_blocks=a[3], patch_size=a[4],
+                         num_classes=a[5])
+
+
+def build_baseline_module(cfg: O.BaselineCfg, device, seed=2468):
+    """deco_b200 FlattenDiT holding oracle.baseline_seeded_params(cfg)."""
+    from deco_b200.denoiser_baseline import FlattenDiT
+    with torch.device("meta"):
+        m = FlattenDiT(in_channels=cfg.in_channels, num_groups=cfg.num_groups, hidden_size=cfg.hidden_size,
+                       num_blocks=cfg.num_blocks, patch_size=cfg.patch_size, num_classes=cfg.num_classes)
+    P = O.baseline_seeded_params(cfg, seed)
+    m = m.to_empty(device=device)
+    m.load_state_dict({k: v.to(device) for k, v in P.items()})
+    return m.eval(), P

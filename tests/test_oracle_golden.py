@@ -117,3 +117,38 @@ def test_cfg1_first_step_matches_reference_fixture():
         out = O.denoiser_forward(P, O.CFG_L, torch.cat([noise, noise]), torch.zeros(8), torch.cat([unc, cond]))
     v0 = O.cfg_combine(out, 1.0)   # t = 0 is outside the (0.1, 1] guidance window
     assert rel_l2(v0[:, :, ::4, ::4], torch.from_numpy(g["v0_sub"])) < 1e-5
+
+
+def test_baseline_forward_matches_reference_fixture():
+    """FlattenDiT (dit_c2i_baseline.py) restatement against the live reference's output (make_golden.py::golden_baseline)."""
+    from helpers import baseline_cfg_from_array
+    g = load_golden("baseline_d64.npz")
+    cfg = baseline_cfg_from_array(g["cfg"])
+    P = O.baseline_seeded_params(cfg)
+    out = O.baseline_forward(P, cfg, torch.from_numpy(g["x"]), torch.from_numpy(g["t"]), torch.from_numpy(g["y"]))
+    assert rel_l2(out, torch.from_numpy(g["out"])) < 2e-6
+    assert float(torch.from_numpy(g["out"]).abs().mean()) > 1e-2
+    # known answers: configs_c2i/Baseline_DiT_JiT.yaml (hidden 1024, 24 blocks, 16 heads of 64, FFN 2730)
+    big = O.BaselineCfg()
+    assert big.head_dim == 64 and big.ffn_hidden == 2730
+    n = sum(int(np.prod(s)) for s in O.baseline_param_shapes(big).values())
+    assert 4.5e8 < n < 4.7e8, n
+
+
+def test_extended_euler_samplers_match_reference_fixtures():
+    """EulerSamplerJiT and the SDE step functions (sampling.py:17-24, :109-188); the stochastic ones replay the reference's
+    recorded Gaussian increments."""
+    from helpers import toy_xnet
+    g = load_golden("samplers_ext_toy.npz")
+    noise = torch.from_numpy(g["noise"])
+    cond, unc = torch.tensor([1, 2, 3]), torch.tensor([10, 10, 10])
+    for n, gd, lo, hi, shift in [(12, 2.5, 0.1, 1.0, 1.0), (30, 1.5, 0.0, 0.8, 2.0)]:
+        o = O.euler_sample_ex(toy_xnet, noise, cond, unc, n, gd, lo, hi, shift, x_prediction=True)
+        assert rel_l2(o, torch.from_numpy(g[f"jit_{n}"])) < 1e-6
+    for kind in ("sde_mean", "sde", "sde_preserve"):
+        for n, gd, shift, last in [(10, 2.0, 1.0, "ode"), (6, 1.0, 2.0, kind)]:
+            incs = list(torch.from_numpy(g[f"{kind}_{n}_increments"])) if f"{kind}_{n}_increments" in g else []
+            o = O.euler_sample_ex(toy_net, noise, cond, unc, n, gd, 0.1, 1.0, shift, step=kind, last=last,
+                                  randn=lambda x: incs.pop(0))
+            assert rel_l2(o, torch.from_numpy(g[f"{kind}_{n}"])) < 1e-6, kind
+            assert not incs
