@@ -30,6 +30,7 @@ XL = dict(in_channels=3, num_groups=16, hidden_size=1152, hidden_size_x=32, num_
 LARGE = dict(XL, hidden_size=1024, num_blocks=25, num_cond_blocks=22)
 XXL_T2I = dict(in_channels=3, patch_size=16, num_groups=24, hidden_size=1536, txt_embed_dim=2048, txt_max_length=128,
                num_text_blocks=4, decoder_hidden_size=32, num_encoder_blocks=16, num_decoder_blocks=3)
+BASELINE_JIT = dict(in_channels=3, patch_size=16, num_groups=16, hidden_size=1024, num_blocks=24, num_classes=1000)
 UNIT = "images/s"
 # BASELINE.json configs; "xl256" (configs[1]) is the one the headline metric is quoted on and the default.
 # gflop = algorithmic GFLOP per image-forward (2*MAC, no padding counted).
@@ -51,6 +52,13 @@ WORKLOADS = {
                    metric="DeCo-XXL/16 512px text-to-image sampling throughput (AdamLM order 2, 25 steps x CFG, fixed NFE)",
                    name="DeCo-XXL/16 512px t2i (configs_t2i/sft_res512.yaml), AdamLM order 2, 25 steps x CFG 4.0, "
                         "timeshift 3, synthetic text-encoder states [128 x 2048]"),
+    # the patch-linear baseline (FlattenDiT) with the x-prediction Euler sampler; not a BASELINE.json config
+    "jit256": dict(kind="baseline", model=BASELINE_JIT, res=256, batch=256, sampler="euler_jit", steps=50, guidance=1.0,
+                   gmin=0.1, gmax=1.0, timeshift=1.0, gflop=162.2,
+                   metric="Baseline DiT-L/16 (patch-linear head, x-prediction) 256px sampling throughput (EulerSamplerJiT 50 "
+                          "steps x CFG, fixed NFE)",
+                   name="FlattenDiT 1024 x 24 blocks /16 256px c2i (configs_c2i/Baseline_DiT_JiT.yaml denoiser and sampler "
+                        "settings), EulerSamplerJiT 50 steps x CFG rows (guidance 1.0 as configured)"),
     # BASELINE configs[3]: training step (forward + backward of denoiser and DCT/FM loss), 32 images PER GPU (weak scaling)
     "train256": dict(kind="train", model=XL, res=256, batch=32, gflop=3 * 244.9,
                      metric="DeCo-XL/16 256px training step throughput (denoiser + DCT/FM loss, forward + backward)",
@@ -280,10 +288,46 @@ def hbm_kernel_rooflines(torch, ops, net, dev, B2, res, hbm_gbs):
     return out
 
 
+def baseline_head_rooflines(torch, ops, net, dev, B2, res, hbm_gbs):
+    """Achieved HBM GB/s of the patch-linear head's memory-bound kernels and of the extended sampler update at the bench
+    shape (jit256 workload), timed like hbm_kernel_rooflines."""
+    bf = torch.bfloat16
+    out = []
+    H, p = net.hidden_size, net.patch_size
+    M = B2 * (res // p) ** 2
+    B = B2 // 2
+    npx = 3 * res * res
+
+    def add(name, ms, nbytes, note):
+        out.append(dict(kernel=name, bound="hbm", ms=ms, algorithmic_bytes=nbytes, achieved=nbytes / (ms * 1e-3) / 1e9,
+                        peak=hbm_gbs, unit="GB/s", frac=nbytes / (ms * 1e-3) / 1e9 / hbm_gbs, note=note))
+
+    x = torch.randn(B, 3, res, res, device=dev)
+    v = torch.randn(2 * B, 3, res, res, device=dev).to(bf)
+    z = torch.randn_like(x)
+    xo = torch.empty_like(x)
+    ms = _time_kernel(lambda i: ops.cfg_step_ex(x, v, 1.0, 0.02, xpred_den=0.5, x_out=xo), 20, torch)
+    add("cfg_step_kernel<ext> (x-prediction)", ms, 12.0 * B * npx, "x fp32 read+write, uncond/cond bf16 read")
+    ms = _time_kernel(lambda i: ops.cfg_step_ex(x, v, 1.0, 0.02, kd=0.5, sden=0.5, a_s=0.01, a_n=0.2, noise=z, x_out=xo), 20, torch)
+    add("cfg_step_kernel<ext> (sde_step_fn)", ms, 16.0 * B * npx, "x fp32 read+write, noise fp32 read, uncond/cond bf16 read")
+    del x, v, z, xo
+    s = torch.randn(M, H, device=dev)
+    mod = torch.randn(B2, 2 * H, device=dev).to(bf)
+    hb = torch.empty(M, H, device=dev, dtype=bf)
+    ms = _time_kernel(lambda i: ops.layernorm_modulate(s, mod[:, :H], mod[:, H:], M // B2, out=hb), 20, torch)
+    add("layernorm_modulate_kernel", ms, 6.0 * M * H, "fp32 stream read, bf16 write")
+    del s, hb
+    toks = [torch.randn(M, 3 * p * p, device=dev).to(bf) for _ in range(2)]
+    ms = _time_kernel(lambda i: ops.unpatchify(toks[i % 2], B2, 3, res, res, p), 20, torch)
+    add("unpatchify_kernel", ms, 4.0 * B2 * npx, "bf16 tokens read, bf16 image write, 2 rotating inputs")
+    return out
+
+
 def run_deco(args):
     import torch
     import torch.distributed as dist
-    from deco_b200 import AdamLMSampler, EulerSampler, LinearScheduler, PixNerDiT, _lib, ode_step_fn, ops, simple_guidance_fn
+    from deco_b200 import (AdamLMSampler, EulerSampler, EulerSamplerJiT, FlattenDiT, LinearScheduler, PixNerDiT, _lib,
+                           ode_step_fn, ops, simple_guidance_fn)
     from deco_b200 import distributed as D
     from deco_b200.data import rank_indices, seeded_noise
     from deco_b200.denoiser_t2i import PixNerDiT as PixNerDiTT2I
@@ -303,14 +347,15 @@ def run_deco(args):
     idx = rank_indices(gbatch, rank, world)          # DistributedSampler(shuffle=False) shard
     B = len(idx)
     with torch.device("meta"):
-        net = (PixNerDiTT2I if wl["kind"] == "t2i" else PixNerDiT)(**wl["model"])
+        net = {"t2i": PixNerDiTT2I, "baseline": FlattenDiT}.get(wl["kind"], PixNerDiT)(**wl["model"])
     net = randomize_(net.to_empty(device=dev), seed=0).eval()
     net.prepare(dev)
     sch = LinearScheduler()
-    if wl["sampler"] == "euler":
-        sampler = EulerSampler(scheduler=sch, w_scheduler=sch, guidance_fn=simple_guidance_fn, num_steps=nsteps,
-                               guidance=wl["guidance"], guidance_interval_min=wl["gmin"], guidance_interval_max=wl["gmax"],
-                               timeshift=wl["timeshift"], step_fn=ode_step_fn)
+    if wl["sampler"] in ("euler", "euler_jit"):
+        cls = EulerSamplerJiT if wl["sampler"] == "euler_jit" else EulerSampler
+        sampler = cls(scheduler=sch, w_scheduler=sch, guidance_fn=simple_guidance_fn, num_steps=nsteps,
+                      guidance=wl["guidance"], guidance_interval_min=wl["gmin"], guidance_interval_max=wl["gmax"],
+                      timeshift=wl["timeshift"], step_fn=ode_step_fn)
     else:
         sampler = AdamLMSampler(order=2, timeshift=wl["timeshift"], scheduler=sch, guidance_fn=simple_guidance_fn,
                                 num_steps=nsteps, guidance=wl["guidance"], guidance_interval_min=wl["gmin"],
@@ -347,8 +392,10 @@ def run_deco(args):
         k = i % nsteps
         t_cur, t_next = ts[k], ts[k + 1]
         out = net(torch.cat([x, x]), torch.full((2 * B,), float(t_cur), device=dev), cfg_cond)
-        if wl["sampler"] == "euler":
+        if wl["sampler"] in ("euler", "euler_jit"):
             g = wl["guidance"] if (bool(t_cur > wl["gmin"]) and bool(t_cur <= wl["gmax"])) else 1.0
+            if wl["sampler"] == "euler_jit":
+                return ops.cfg_step_ex(x, out, g, float(t_next - t_cur), xpred_den=sampler._xpred_den(t_cur))[0]
             return ops.cfg_step(x, out, g, float(t_next - t_cur))[0]
         g = wl["guidance"] if (bool(t_cur > wl["gmin"]) and bool(t_cur < wl["gmax"])) else 1.0
         cs = sampler.solver_coeffs[k] if state["pred"] is not None else (1.0,)
@@ -451,7 +498,8 @@ def run_deco(args):
     if not args.no_hbm_kernels and world == 1 and not args.profile:
         del x
         torch.cuda.empty_cache()
-        hbm = hbm_kernel_rooflines(torch, ops, net, dev, 2 * B, res, peaks["hbm_gbs"])
+        fn = baseline_head_rooflines if wl["kind"] == "baseline" else hbm_kernel_rooflines
+        hbm = fn(torch, ops, net, dev, 2 * B, res, peaks["hbm_gbs"])
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
