@@ -565,16 +565,38 @@ def run_train(args):
     x_host = [torch.tanh(torch.randn((B, 3, res, res), generator=gen)).pin_memory() for _ in range(nbuf)]
     y_host = [torch.randint(0, 1000, (B,), generator=gen).pin_memory() for _ in range(nbuf)]
     unc = torch.full((B,), 1000, dtype=torch.int64, device=dev)
-    torch.manual_seed(4321 + rank)
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
 
-    def step(x, y):
+    # N > 1: gradients are averaged like DDP does for the reference -- by default overlapped with the backward (per-block
+    # asynchronous all-reduces started from inside the denoiser's backward), DECO_B200_OVERLAP=0 = one flat all-reduce after it
+    overlap = world > 1 and os.environ.get("DECO_B200_OVERLAP", "1") != "0"
+
+    def step(x, y, overlap=overlap):
         for p in params:
             p.grad = None
         d = trainer(net, None, None, x, y, unc)
-        d["loss"].backward()
-        D.all_reduce_gradients(params, world)      # what DDP does, in one bucket
+        if overlap:
+            with D.overlap_gradient_average(world):
+                d["loss"].backward()
+        else:
+            d["loss"].backward()
+            D.all_reduce_gradients(params, world)      # one bucket after the backward
         return d["loss"].detach()
+
+    overlap_check = None
+    if overlap:       # same seeded step through both averaging paths: the gradients must agree (fp32 atomics aside)
+        got = []
+        for mode in (True, False):
+            torch.manual_seed(777 + rank)
+            step(x_host[0].to(dev), y_host[0].to(dev), overlap=mode)
+            got.append([p.grad.detach().clone() for p in params])
+        num = sum(float(((a.double() - b.double()) ** 2).sum()) for a, b in zip(*got))
+        den = sum(float((b.double() ** 2).sum()) for b in got[1])
+        overlap_check = (num / max(den, 1e-300)) ** 0.5
+        del got
+        if not overlap_check < 1e-4:
+            raise SystemExit(f"overlapped gradient averaging disagrees with the flat all-reduce: rel-L2 {overlap_check:.3e}")
+    torch.manual_seed(4321 + rank)
 
     def barrier():
         if world > 1:
@@ -710,7 +732,10 @@ def run_train(args):
                 ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
                 data="synthetic",
                 config=dict(workload=wl["name"], global_batch=B * world, per_gpu_batch=B,
-                            step="trainer forward (denoiser + DCT/FM loss) + backward" + (" + gradient all-reduce" if world > 1 else ""),
+                            step="trainer forward (denoiser + DCT/FM loss) + backward" + (
+                                "" if world == 1 else " + gradient averaging: per-block asynchronous NCCL all-reduces overlapped "
+                                "with the backward" if overlap else " + one flat NCCL all-reduce after the backward"),
+                            overlap_check_rel_l2=overlap_check,
                             launch=launch_mode,
                             l2="inputs larger than L2 (>4 GB of weights + >10 GB of saved activations per step)",
                             parallelism=f"dp{world}"),

@@ -26,6 +26,17 @@ WGRAD = os.environ.get("DECO_B200_WGRAD", "tn")                # "tn" (product p
 DECODER_BWD = os.environ.get("DECO_B200_DECODER_BWD", "mma")   # "mma" (product path) | "scalar" (A/B check)
 
 
+# Called with lists of gradient tensors the moment they are final (per DiT block, walking backwards, then the tail): lets a
+# data-parallel trainer start averaging them while the rest of the backward still runs (DDP's bucketed overlap for the
+# reference; deco_b200.distributed.OverlappedGradientAverager).  None = no hook.
+GRAD_READY_HOOK = None
+
+
+def _grads_ready(tensors) -> None:
+    if GRAD_READY_HOOK is not None:
+        GRAD_READY_HOOK([t for t in tensors if t is not None])
+
+
 def _rb(t: torch.Tensor) -> torch.Tensor:
     """fp32 copy holding bf16-rounded values (what the forward MMAs see)."""
     return t.detach().to(bf16).to(F32)
@@ -253,7 +264,8 @@ def train_backward(module, S: dict, dout: torch.Tensor) -> Dict[str, torch.Tenso
         Fp = P["ffn_pad"]
         # MLP branch
         da2 = ops.gate_bwd(ds, sv["a2"], g2, dg2, L)
-        G[pre + "mlp.w2.weight"] = _wgrad(da2, sv["u"])[:, :F_]
+        gw2 = _wgrad(da2, sv["u"])
+        G[pre + "mlp.w2.weight"] = gw2 if F_ == Fp else gw2[:, :F_].contiguous()
         du = ops.gemm(da2, bt["w2T"], None, ops.EPI_BIAS)
         dy13 = ops.swiglu_bwd(sv["y13"], du)
         dw13 = _wgrad(dy13, sv["h2"]).view(Fp // 16, 2, 16, H)
@@ -282,6 +294,9 @@ def train_backward(module, S: dict, dout: torch.Tensor) -> Dict[str, torch.Tenso
         G[pre + "norm1.weight"] = dn1
         del da1, do, dqkv, dh1
         S["blocks"][i] = None   # release the block's activations
+        # the block's matrix gradients are final (the vector gradients live in zblk / dmod and follow with the tail)
+        _grads_ready([G[pre + k] for k in ("mlp.w2.weight", "mlp.w1.weight", "mlp.w3.weight", "attn.proj.weight",
+                                           "attn.qkv.weight")])
 
     # ---- s_embedder: s0 = xp . ws^T + bs
     G["s_embedder.proj.weight"] = _wgrad(ds, S["xp"])
@@ -307,6 +322,7 @@ def train_backward(module, S: dict, dout: torch.Tensor) -> Dict[str, torch.Tenso
     dz1 = ops.silu_bwd(S["z1"], dh1t)
     G["t_embedder.mlp.0.weight"] = _wgrad(dz1, S["tfreq"])
     G["t_embedder.mlp.0.bias"] = _colsum(dz1)
+    _grads_ready(list(G.values()))      # the tail: everything not announced yet (the hook skips what it has seen)
     return G
 
 
@@ -327,6 +343,11 @@ class DenoiserFn(torch.autograd.Function):
             raise RuntimeError("deco_b200 denoiser: backward called twice (activations are released after one pass)")
         G = train_backward(ctx.module, ctx.S, dout)
         ctx.S = None
+        # an overlapped gradient averager reduces G's buffers in place on another stream: order this stream behind it
+        # before autograd reads (or clones) them
+        finish = getattr(GRAD_READY_HOOK, "finish", None)
+        if finish is not None:
+            finish()
         grads = []
         for n, (need, shape, dtype) in zip(ctx.names, ctx.meta):
             g = G.get(n) if need else None

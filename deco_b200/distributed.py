@@ -54,3 +54,62 @@ def all_reduce_gradients(params, world_size: int) -> None:
         dist.all_reduce(flat)
         flat.div_(world_size)
     torch._foreach_copy_(grads, torch._utils._unflatten_dense_tensors(flat, grads))
+
+
+class OverlappedGradientAverager:
+    """Average gradients over the ranks WHILE the backward runs: installed as `deco_b200.autograd.GRAD_READY_HOOK`, it
+    receives each group of final gradient tensors (one DiT block at a time, then the tail) and starts an asynchronous
+    all-reduce of every distinct underlying buffer on NCCL's own stream; `finish()` makes the current stream wait for all
+    of them.  Same result as `all_reduce_gradients` (DDP's average, src/lightning_model.py under `strategy: ddp`) without
+    the flatten / unflatten copies and with the transfer hidden behind the remaining dgrad / wgrad GEMMs.  Views are
+    reduced through their base tensor once (e.g. the per-block slices of the batched adaLN gradient)."""
+
+    def __init__(self, world_size: int):
+        self.world = world_size
+        self._seen = set()
+        self._work = []
+        self._avg = dist.is_initialized() and dist.get_backend() == "nccl"
+
+    def __call__(self, tensors) -> None:
+        if self.world == 1:
+            return
+        for t in tensors:
+            base = t._base if t._base is not None else t
+            key = (base.data_ptr(), base.numel())
+            if key in self._seen or base.numel() == 0:
+                continue
+            if not base.is_contiguous():
+                raise RuntimeError("OverlappedGradientAverager needs contiguous gradient buffers")
+            self._seen.add(key)
+            if self._avg:
+                self._work.append((dist.all_reduce(base, op=dist.ReduceOp.AVG, async_op=True), None))
+            else:
+                self._work.append((dist.all_reduce(base, async_op=True), base))
+
+    def finish(self) -> None:
+        for work, base in self._work:
+            work.wait()
+            if base is not None:
+                base.div_(self.world)
+        self._work.clear()
+        self._seen.clear()
+
+
+class overlap_gradient_average:
+    """`with overlap_gradient_average(world): loss.backward()` -- installs the averager for the deco_b200 denoiser's backward
+    and waits for the collectives on exit; afterwards every `param.grad` holds the rank average."""
+
+    def __init__(self, world_size: int):
+        self.avg = OverlappedGradientAverager(world_size)
+
+    def __enter__(self):
+        from . import autograd
+        self._prev = autograd.GRAD_READY_HOOK
+        autograd.GRAD_READY_HOOK = self.avg
+        return self.avg
+
+    def __exit__(self, *exc):
+        from . import autograd
+        autograd.GRAD_READY_HOOK = self._prev
+        self.avg.finish()
+        return False

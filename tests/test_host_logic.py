@@ -377,3 +377,49 @@ def test_graph_schedule_tables_match_the_eager_loops():
     assert AdamLMSampler(order=3, scheduler=sch, guidance_fn=simple_guidance_fn, num_steps=8)._graph_rows() is None
     assert HeunSampler(scheduler=sch, w_scheduler=sch, guidance_fn=simple_guidance_fn, num_steps=4,
                        step_fn=ode_step_fn)._graph_rows() is None
+
+
+def _overlap_avg_worker(rank, world, port, q):
+    import os
+    import torch
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    from deco_b200 import autograd as A
+    from deco_b200 import distributed as D
+    import torch.distributed as dist
+    D.init_from_env("gloo")
+    big = torch.arange(24, dtype=torch.float32).reshape(4, 6) * (rank + 1)       # a batched buffer announced through views
+    lone = torch.full((5,), float(rank + 1))
+    late = torch.full((3,), 10.0 * (rank + 1))
+    with D.overlap_gradient_average(world) as avg:
+        assert A.GRAD_READY_HOOK is avg
+        A._grads_ready([big[1], lone])          # "block" group: big is reduced once, through its base
+        A._grads_ready([big[2:], lone, late, None])   # "tail": repeats are skipped
+        n_started = len(avg._work)
+    assert A.GRAD_READY_HOOK is None
+    q.put((rank, n_started, big.tolist(), lone.tolist(), late.tolist()))
+    dist.destroy_process_group()
+
+
+def test_overlapped_gradient_averager_gloo_world2():
+    """The hook path the denoiser backward drives (autograd._grads_ready -> OverlappedGradientAverager): every distinct
+    buffer is all-reduced exactly once (views through their base) and holds the rank average after the context exits."""
+    import socket
+    import torch
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_overlap_avg_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, n_started, big, lone, late in res:
+        assert n_started == 3
+        assert torch.allclose(torch.tensor(big), torch.arange(24, dtype=torch.float32).reshape(4, 6) * 1.5)
+        assert lone == [1.5] * 5 and late == [15.0] * 3
