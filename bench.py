@@ -707,7 +707,8 @@ def run_train(args):
     opt_ms = o0.elapsed_time(o1) / 5
     nparam = sum(p.numel() for p in params)
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    eager_step(xd[0], yd[0]); opt.step()
+    for i in range(2):
+        eager_step(xd[i % nbuf], yd[i % nbuf]); opt.step()
     barrier()
     f0.record()
     for i in range(3):
