@@ -423,3 +423,110 @@ def test_overlapped_gradient_averager_gloo_world2():
         assert n_started == 3
         assert torch.allclose(torch.tensor(big), torch.arange(24, dtype=torch.float32).reshape(4, 6) * 1.5)
         assert lone == [1.5] * 5 and late == [15.0] * 3
+
+
+def _torch_cfg_step_ex(x, net_out, g=1.0, dt=0.0, c0=1.0, prev=(), coeffs=(), dev=None, xpred_den=0.0, kd=0.0, sden=1.0,
+                       a_s=0.0, a_n=0.0, noise=None, x_out=None, pred_out=None, want_pred=False, want_v=False,
+                       want_u8=False, u8_out=None):
+    """Test-only torch statement of the extended form of csrc/sampler.cu (deco_cfg_step_ex)."""
+    u, c = net_out.float().chunk(2)
+    if xpred_den > 0:
+        u, c = (u - x) / xpred_den, (c - x) / xpred_den
+    pred = u + g * (c - u)
+    v = c0 * pred
+    for p, cf in zip(prev, coeffs):
+        v = v + cf * p
+    xo = x + dt * v
+    if a_s != 0.0:
+        xo = xo + a_s * (kd * v - x) / sden
+    if a_n != 0.0:
+        xo = xo + a_n * noise
+    return xo, (pred if want_pred else None), (v if want_v else None), (O.fp2uint8(xo) if want_u8 else None)
+
+
+def test_extended_sampler_control_flow_matches_reference(monkeypatch):
+    """EulerSamplerJiT and the SDE step functions: host schedule / score scalars / step-function selection against the
+    fixtures from the real reference, replaying its recorded Gaussian increments through torch.randn_like."""
+    from helpers import toy_xnet
+    from deco_b200 import (ConstScheduler, EulerSampler, EulerSamplerJiT, GVPScheduler, HeunSampler, LinearScheduler, ode_step_fn,
+                           ops, sampling, sde_mean_step_fn, sde_preserve_step_fn, sde_step_fn, simple_guidance_fn)
+    monkeypatch.setattr(ops, "cfg_step", _torch_cfg_step)
+    monkeypatch.setattr(ops, "cfg_step_ex", _torch_cfg_step_ex)
+    monkeypatch.setattr(sampling, "_prep_inputs", lambda n, c, u: (n.float().contiguous(), torch.cat([u, c], 0)))
+    g = load_golden("samplers_ext_toy.npz")
+    noise = torch.from_numpy(g["noise"])
+    cond, unc = torch.tensor([1, 2, 3]), torch.tensor([10, 10, 10])
+    sch = LinearScheduler()
+    for n, gd, lo, hi, shift in [(12, 2.5, 0.1, 1.0, 1.0), (30, 1.5, 0.0, 0.8, 2.0)]:
+        s = EulerSamplerJiT(scheduler=sch, w_scheduler=sch, guidance_fn=simple_guidance_fn, num_steps=n, guidance=gd,
+                            guidance_interval_min=lo, guidance_interval_max=hi, timeshift=shift, step_fn=ode_step_fn)
+        assert rel_l2(s(toy_xnet, noise, cond, unc), torch.from_numpy(g[f"jit_{n}"])) < 1e-6
+        rows, use_pred = s._graph_rows()
+        assert not use_pred and len(rows) == n
+        for i, r in enumerate(rows):        # column 7 = clamp_min(1 - t, 0.05) in fp32 (sampling.py:170)
+            assert r[7] == float((1.0 - s.timesteps[i]).clamp_min(5e-2)) and r[6] == float(s.timesteps[i])
+    fns = {"sde_mean": sde_mean_step_fn, "sde": sde_step_fn, "sde_preserve": sde_preserve_step_fn}
+    for kind, fn in fns.items():
+        for n, gd, shift, last in [(10, 2.0, 1.0, "ode"), (6, 1.0, 2.0, kind)]:
+            s = EulerSampler(scheduler=sch, w_scheduler=sch, guidance_fn=simple_guidance_fn, num_steps=n, guidance=gd,
+                             guidance_interval_min=0.1, guidance_interval_max=1.0, timeshift=shift, step_fn=fn,
+                             last_step_fn=(ode_step_fn if last == "ode" else fn))
+            assert s._graph_rows() is None          # fresh noise per step: no graph replay
+            incs = list(torch.from_numpy(g[f"{kind}_{n}_increments"])) if f"{kind}_{n}_increments" in g else []
+            monkeypatch.setattr(torch, "randn_like", lambda x: incs.pop(0))
+            out = s(toy_net, noise, cond, unc)
+            monkeypatch.undo()
+            monkeypatch.setattr(ops, "cfg_step", _torch_cfg_step)
+            monkeypatch.setattr(ops, "cfg_step_ex", _torch_cfg_step_ex)
+            monkeypatch.setattr(sampling, "_prep_inputs", lambda n, c, u: (n.float().contiguous(), torch.cat([u, c], 0)))
+            assert not incs and rel_l2(out, torch.from_numpy(g[f"{kind}_{n}"])) < 2e-6, kind
+    # score scalars of the other schedulers (flow_matching/scheduling.py:17-32): GVP at t = 0.5, constant w
+    e = EulerSampler(scheduler=GVPScheduler(), w_scheduler=ConstScheduler(), step_fn=sde_step_fn, num_steps=4)
+    kd, sden, a_s, a_n = e._sde_scalars(torch.tensor(0.5), torch.tensor(0.25), "sde_step_fn")
+    # the reference's GVP derivatives carry no pi/2 factor: dalpha/alpha = -tan(pi/4) = -1, sden = sin^2 + sin cos = 1
+    assert abs(kd + 1.0) < 1e-6 and abs(sden - 1.0) < 1e-6
+    assert abs(a_s - 0.25) < 1e-7 and abs(a_n - np.sqrt(0.5)) < 1e-6
+    # the reference's guards: an SDE step needs a w_scheduler (sampling.py:61); Heun / Adams stay ODE-only here
+    with pytest.raises(AssertionError):
+        EulerSampler(scheduler=sch, step_fn=sde_step_fn, num_steps=2)
+    with pytest.raises(NotImplementedError):
+        HeunSampler(scheduler=sch, w_scheduler=sch, step_fn=sde_step_fn, num_steps=2)
+
+
+BASELINE_JIT_YAML = """
+model:
+  denoiser:
+    class_path: src.models.transformer.dit_c2i_baseline.FlattenDiT
+    init_args: {in_channels: 3, patch_size: 16, num_groups: 4, hidden_size: 256, num_blocks: 2, num_classes: 10}
+  diffusion_sampler:
+    class_path: src.diffusion.flow_matching.sampling.EulerSamplerJiT
+    init_args:
+      num_steps: 50
+      guidance: 1.0
+      guidance_interval_min: 0.1
+      guidance_interval_max: 1.0
+      scheduler: src.diffusion.flow_matching.scheduling.LinearScheduler
+      w_scheduler: src.diffusion.flow_matching.scheduling.LinearScheduler
+      guidance_fn: src.diffusion.base.guidance.simple_guidance_fn
+      step_fn: src.diffusion.flow_matching.sampling.sde_step_fn
+      last_step_fn: src.diffusion.flow_matching.sampling.ode_step_fn
+"""
+
+
+def test_baseline_yaml_wiring_and_checkpoint_contract(tmp_path):
+    """configs_c2i/Baseline_DiT_JiT.yaml-shaped model section through the class map; FlattenDiT's state_dict is the
+    reference's (names and shapes from oracle.baseline_param_shapes, pinned by make_golden.py::golden_baseline)."""
+    from deco_b200 import EulerSamplerJiT, FlattenDiT, config, ode_step_fn, sde_step_fn
+    p = tmp_path / "cfg.yaml"
+    p.write_text(BASELINE_JIT_YAML)
+    parts = config.load_model_section(str(p))
+    m, s = parts["denoiser"], parts["diffusion_sampler"]
+    assert isinstance(m, FlattenDiT) and isinstance(s, EulerSamplerJiT) and s.x_prediction
+    assert s.step_fn is sde_step_fn and s.last_step_fn is ode_step_fn and s._kinds == ("sde_step_fn", "ode_step_fn")
+    want = O.baseline_param_shapes(O.BaselineCfg(num_groups=4, hidden_size=256, num_blocks=2, num_classes=10))
+    got = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert got == want
+    # default init zeroes the whole output layer (dit_c2i_baseline.py:351-355)
+    assert float(m.final_layer.linear.weight.abs().max()) == 0.0 and float(m.final_layer.adaLN_modulation[0].weight.abs().max()) == 0.0
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.eval()(torch.zeros(1, 3, 32, 32), torch.zeros(1), torch.zeros(1, dtype=torch.long))
