@@ -548,6 +548,9 @@ def run_train(args):
 
     wl = WORKLOADS[args.workload]
     res = wl["res"]
+    # overlapped gradient averaging (N > 1): the GEMMs leave DECO_B200_RESERVE_SMS SMs free and NCCL is kept inside them
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and int(os.environ.get("DECO_B200_RESERVE_SMS", "0")) > 0:
+        os.environ.setdefault("NCCL_MAX_CTAS", os.environ["DECO_B200_RESERVE_SMS"])
     rank, world, local = D.init_from_env("nccl" if int(os.environ.get("WORLD_SIZE", "1")) > 1 else None)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: deco_b200 has no CPU path")
@@ -737,6 +740,8 @@ def run_train(args):
                                 "" if world == 1 else " + gradient averaging: per-block asynchronous NCCL all-reduces overlapped "
                                 "with the backward" if overlap else " + one flat NCCL all-reduce after the backward"),
                             overlap_check_rel_l2=overlap_check,
+                            reserved_sms=int(os.environ.get("DECO_B200_RESERVE_SMS", "0")) if overlap else None,
+                            nccl_max_ctas=os.environ.get("NCCL_MAX_CTAS"),
                             launch=launch_mode,
                             l2="inputs larger than L2 (>4 GB of weights + >10 GB of saved activations per step)",
                             parallelism=f"dp{world}"),

@@ -27,6 +27,7 @@ SIGNATURES = {
                                 _i, _vp, _i, _f, _vp]),
     "deco_gemm_norm_swiglu": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _vp, _i, _i, _f, _vp, _ll, _vp]),
     "deco_gemm_set_tuning": (_i, [_i, _i]),
+    "deco_gemm_reserve_sms": (_i, [_i]),
     "deco_patchify": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "deco_timestep_freq": (_i, [_vp, _vp, _i, _i, _f, _vp]),
     "deco_cond_combine": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),

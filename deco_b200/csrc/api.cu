@@ -29,3 +29,14 @@ bool deco_pdl_enabled() {
     }
     return v != 0;
 }
+
+// SMs the persistent GEMM kernels leave free (process-wide, default 0): while NCCL's kernels average gradients on another
+// stream (deco_b200.distributed.OverlappedGradientAverager) a persistent GEMM sized for every SM would wait, with its static
+// tile order, for the SMs NCCL holds; sized for (SMs - reserved) the two run side by side.
+static int g_reserved_sms = 0;
+int deco_reserved_sms() { return g_reserved_sms; }
+extern "C" int deco_gemm_reserve_sms(int n) {
+    if (n < 0 || n > 64) { deco_set_error("gemm_reserve_sms: %d out of range [0, 64]", n); return DECO_ERR_ARG; }
+    g_reserved_sms = n & ~1;
+    return DECO_OK;
+}

@@ -30,6 +30,8 @@ void deco_set_error(const char* fmt, ...);
 
 // process-wide switch for programmatic dependent launch (DECO_B200_PDL=0 disables it); defined in api.cu
 bool deco_pdl_enabled();
+// SMs the persistent GEMMs leave to concurrent kernels (deco_gemm_reserve_sms); defined in api.cu
+int deco_reserved_sms();
 
 namespace deco {
 

@@ -702,7 +702,7 @@ static int sm_count() {
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         if (n <= 0) n = kNumSMs;
     }
-    return n;
+    return n - deco_reserved_sms();
 }
 
 template <int BN, int EPI>

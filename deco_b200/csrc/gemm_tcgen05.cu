@@ -505,7 +505,7 @@ static int num_sms() {
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         g_num_sms_cached = n > 0 ? n : kNumSMs;
     }
-    return g_num_sms_cached;
+    return g_num_sms_cached - deco_reserved_sms();
 }
 
 }  // namespace deco

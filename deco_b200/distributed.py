@@ -103,17 +103,26 @@ class overlap_gradient_average:
     """`with overlap_gradient_average(world): loss.backward()` -- installs the averager for the deco_b200 denoiser's backward
     and waits for the collectives on exit; afterwards every `param.grad` holds the rank average."""
 
-    def __init__(self, world_size: int):
+    def __init__(self, world_size: int, reserve_sms: Optional[int] = None):
         self.avg = OverlappedGradientAverager(world_size)
+        # SMs the persistent GEMMs leave to NCCL's kernels while the context is active (include/deco_b200.h,
+        # deco_gemm_reserve_sms); pair it with NCCL_MAX_CTAS so NCCL stays inside the reservation
+        if reserve_sms is None:
+            reserve_sms = int(os.environ.get("DECO_B200_RESERVE_SMS", "0"))
+        self.reserve = reserve_sms if world_size > 1 else 0
 
     def __enter__(self):
-        from . import autograd
+        from . import _lib, autograd
         self._prev = autograd.GRAD_READY_HOOK
         autograd.GRAD_READY_HOOK = self.avg
+        if self.reserve:
+            _lib.load().deco_gemm_reserve_sms(self.reserve)
         return self.avg
 
     def __exit__(self, *exc):
-        from . import autograd
+        from . import _lib, autograd
         autograd.GRAD_READY_HOOK = self._prev
+        if self.reserve:
+            _lib.load().deco_gemm_reserve_sms(0)
         self.avg.finish()
         return False

@@ -88,6 +88,9 @@ int deco_gemm_norm_swiglu(const void* A, long long lda, const void* W, long long
 /* Tuning knob (process-wide, for A/B measurements): cta_group -1 = auto (2-CTA pairs when M > 128), 1, 2;
  * staged_epilogue -1 = auto (staged with 2-CTA), 0 = direct row-per-thread stores, 1 = shared-memory staged. */
 int deco_gemm_set_tuning(int cta_group, int staged_epilogue);
+/* Process-wide: the persistent GEMM kernels size their grids for (SM count - n) SMs (n even, 0..64; default 0), leaving
+ * room for kernels on other streams -- NCCL's, while gradients are averaged during the backward. */
+int deco_gemm_reserve_sms(int n);
 
 /* F.unfold + transpose (dit_c2i_DeCo.py:491): fp32 [B,C,H,W] -> bf16 [B*L, C*p*p], feature order c*p*p + ky*p + kx */
 int deco_patchify(const float* x, void* out_bf16, int B, int C, int H, int W, int p, void* stream);

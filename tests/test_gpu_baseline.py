@@ -137,3 +137,26 @@ def test_sde_step_statistics_full_size(cuda_dev):
     r = xo - x * (1 - a_s / sden)
     assert abs(float(r.mean())) < 1e-3 and abs(float(r.var()) - a_n * a_n) < 1e-3
     assert rel_l2(r, a_n * z) < 1e-5
+
+
+@pytest.mark.parametrize("hw", [(32, 96), (80, 48)])
+def test_non_square_images_both_denoisers(cuda_dev, hw):
+    """Edge case the reference supports (any H, W divisible by the patch size; the RoPE table is per (h, w),
+    dit_c2i_DeCo.py:467-473): non-square token grids, for the DeCo denoiser and the patch-linear baseline, one image."""
+    from helpers import build_module
+    Hh, Ww = hw
+    x = seeded_noise(1, (3, Hh, Ww), 77).to(cuda_dev)
+    t = torch.tensor([0.35], device=cuda_dev)
+    y = torch.tensor([4], device=cuda_dev)
+    cfg = O.DenoiserCfg(num_groups=4, hidden_size=256, num_blocks=4, num_cond_blocks=2, num_classes=10)
+    m, P = build_module(cfg, cuda_dev)
+    ref = O.denoiser_forward({k: v.to(cuda_dev) for k, v in P.items()}, cfg, x, t, y)
+    e = rel_l2(m(x, t, y).float(), ref)
+    print(f"PixNerDiT {Hh}x{Ww}: rel-L2 vs fp32 oracle = {e:.3e}")
+    assert e <= 1e-2
+    bcfg = O.BaselineCfg(num_groups=4, hidden_size=256, num_blocks=2, num_classes=10)
+    mb, Pb = build_baseline_module(bcfg, cuda_dev)
+    refb = O.baseline_forward({k: v.to(cuda_dev) for k, v in Pb.items()}, bcfg, x, t, y)
+    eb = rel_l2(mb(x, t, y).float(), refb)
+    print(f"FlattenDiT {Hh}x{Ww}: rel-L2 vs fp32 oracle = {eb:.3e}")
+    assert eb <= 1e-2
