@@ -861,3 +861,131 @@ def euler_sample_ex(net: Callable, noise: torch.Tensor, cond: torch.Tensor, unco
         else:
             raise ValueError(kind)
     return x
+
+
+# --------------------------------------------------------------------------- PixNerd baseline (hyper-network decoder)
+# Restated ahead of its CUDA path (DESIGN.md section 8, rank-4 leftovers): configs_c2i/Baseline_PixNerd.yaml.
+@dataclass(frozen=True)
+class PixNerdCfg:
+    """Constructor arguments of dit_c2i_pixnerd.PixNerDiT (src/models/transformer/dit_c2i_pixnerd.py:288-303;
+    configs_c2i/Baseline_PixNerd.yaml:44-55)."""
+    in_channels: int = 3
+    num_groups: int = 16
+    hidden_size: int = 1024
+    hidden_size_x: int = 64
+    nerf_mlpratio: int = 2
+    num_blocks: int = 24
+    num_cond_blocks: int = 22
+    patch_size: int = 16
+    num_classes: int = 1000
+    max_freqs: int = 8
+
+    @property
+    def head_dim(self) -> int:
+        return self.hidden_size // self.num_groups
+
+    @property
+    def ffn_hidden(self) -> int:
+        return int(2 * int(self.hidden_size * 4.0) / 3)
+
+
+def pixnerd_param_shapes(cfg: PixNerdCfg) -> Dict[str, Tuple[int, ...]]:
+    """state_dict names and shapes of dit_c2i_pixnerd.PixNerDiT: DiT blocks 0..num_cond_blocks-1 and NerfBlocks
+    num_cond_blocks..num_blocks-1 share ONE ModuleList (dit_c2i_pixnerd.py:325-330)."""
+    H, Hx, p, C = cfg.hidden_size, cfg.hidden_size_x, cfg.patch_size, cfg.in_channels
+    d, ffn = cfg.head_dim, cfg.ffn_hidden
+    s: Dict[str, Tuple[int, ...]] = {
+        "x_embedder.embedder.0.weight": (Hx, C + cfg.max_freqs ** 2),
+        "x_embedder.embedder.0.bias": (Hx,),
+        "s_embedder.proj.weight": (H, C * p * p),
+        "s_embedder.proj.bias": (H,),
+        "t_embedder.mlp.0.weight": (H, 256),
+        "t_embedder.mlp.0.bias": (H,),
+        "t_embedder.mlp.2.weight": (H, H),
+        "t_embedder.mlp.2.bias": (H,),
+        "y_embedder.embedding_table.weight": (cfg.num_classes + 1, H),
+        "final_layer.norm.weight": (Hx,),
+        "final_layer.linear.weight": (C, Hx),
+        "final_layer.linear.bias": (C,),
+    }
+    for i in range(cfg.num_cond_blocks):
+        b = f"blocks.{i}."
+        s[b + "norm1.weight"] = (H,)
+        s[b + "attn.qkv.weight"] = (3 * H, H)
+        s[b + "attn.q_norm.weight"] = (d,)
+        s[b + "attn.k_norm.weight"] = (d,)
+        s[b + "attn.proj.weight"] = (H, H)
+        s[b + "attn.proj.bias"] = (H,)
+        s[b + "norm2.weight"] = (H,)
+        s[b + "mlp.w1.weight"] = (ffn, H)
+        s[b + "mlp.w3.weight"] = (ffn, H)
+        s[b + "mlp.w2.weight"] = (H, ffn)
+        s[b + "adaLN_modulation.0.weight"] = (6 * H, H)
+        s[b + "adaLN_modulation.0.bias"] = (6 * H,)
+    for i in range(cfg.num_cond_blocks, cfg.num_blocks):
+        b = f"blocks.{i}."
+        s[b + "param_generator1.0.weight"] = (2 * Hx * Hx * cfg.nerf_mlpratio, H)
+        s[b + "param_generator1.0.bias"] = (2 * Hx * Hx * cfg.nerf_mlpratio,)
+        s[b + "norm.weight"] = (Hx,)
+    return s
+
+
+def pixnerd_seeded_params(cfg: PixNerdCfg, seed: int = 1357, device="cpu") -> Params:
+    """Fully non-zero seeded weights (the default init zeroes final_layer.linear, dit_c2i_pixnerd.py:353-355)."""
+    out: Params = {}
+    for idx, (name, shape) in enumerate(sorted(pixnerd_param_shapes(cfg).items())):
+        g = torch.Generator().manual_seed(seed * 100003 + idx)
+        if name.startswith("y_embedder"):
+            w = torch.randn(shape, generator=g) * 0.5
+        elif len(shape) == 2:
+            std = 1.0 / math.sqrt(shape[1])
+            if "adaLN_modulation" in name:
+                std *= 0.5
+            w = torch.randn(shape, generator=g) * std
+        elif name.endswith("norm.weight") or name.endswith("norm1.weight") or name.endswith("norm2.weight"):
+            w = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        else:
+            w = 0.05 * torch.randn(shape, generator=g)
+        out[name] = w.to(device)
+    return out
+
+
+def nerf_block(P: Params, pre: str, x: torch.Tensor, s: torch.Tensor, mlp_ratio: int) -> torch.Tensor:
+    """NerfBlock.forward (dit_c2i_pixnerd.py:250-273): a per-patch MLP whose weights are generated from the patch's DiT
+    condition and L2-normalised over their input dimension.  x [BL, p*p, Hx], s [BL, H]."""
+    n, _, Hx = x.shape
+    params = F.linear(s, P[pre + "param_generator1.0.weight"], P[pre + "param_generator1.0.bias"])
+    fc1, fc2 = params.chunk(2, dim=-1)
+    fc1 = F.normalize(fc1.view(n, Hx, Hx * mlp_ratio), dim=-2)
+    fc2 = F.normalize(fc2.view(n, Hx * mlp_ratio, Hx), dim=-2)
+    h = rmsnorm(x, P[pre + "norm.weight"])
+    h = torch.bmm(F.silu(torch.bmm(h, fc1)), fc2)
+    return h + x
+
+
+def pixnerd_forward(P: Params, cfg: PixNerdCfg, x: torch.Tensor, t: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """dit_c2i_pixnerd.PixNerDiT.forward (dit_c2i_pixnerd.py:358-381)."""
+    B, _, Hh, Ww = x.shape
+    p, H = cfg.patch_size, cfg.hidden_size
+    angles = rope_table_2d(cfg.head_dim, Hh // p, Ww // p).to(x.device)
+    xp = F.unfold(x, kernel_size=p, stride=p).transpose(1, 2)
+    tf = timestep_embedding(t.view(-1))
+    te = F.linear(F.silu(F.linear(tf, P["t_embedder.mlp.0.weight"], P["t_embedder.mlp.0.bias"])),
+                  P["t_embedder.mlp.2.weight"], P["t_embedder.mlp.2.bias"]).view(B, -1, H)
+    ye = F.embedding(y, P["y_embedder.embedding_table.weight"]).view(B, 1, H)
+    c = F.silu(te + ye)
+    s = F.linear(xp, P["s_embedder.proj.weight"], P["s_embedder.proj.bias"])
+    for i in range(cfg.num_cond_blocks):
+        s = dit_block(P, i, s, c, angles, cfg.num_groups)
+    s = F.silu(te + s)
+    L = s.shape[1]
+    px = xp.reshape(B * L, cfg.in_channels, p * p).transpose(1, 2)
+    sf = s.reshape(B * L, H)
+    tab = nerf_pos_table(p, cfg.max_freqs).to(device=px.device, dtype=px.dtype)
+    h = F.linear(torch.cat([px, tab[None].expand(B * L, -1, -1)], dim=-1),
+                 P["x_embedder.embedder.0.weight"], P["x_embedder.embedder.0.bias"])
+    for i in range(cfg.num_cond_blocks, cfg.num_blocks):
+        h = nerf_block(P, f"blocks.{i}.", h, sf, cfg.nerf_mlpratio)
+    h = F.linear(rmsnorm(h, P["final_layer.norm.weight"]), P["final_layer.linear.weight"], P["final_layer.linear.bias"])
+    out = h.transpose(1, 2).reshape(B, L, -1)
+    return F.fold(out.transpose(1, 2).contiguous(), (Hh, Ww), kernel_size=p, stride=p)

@@ -35,6 +35,7 @@ from src.diffusion.base.guidance import simple_guidance_fn as ref_guidance  # no
 from src.diffusion.flow_matching.training_repa_DeCo import REPATrainer as RefTrainer  # noqa: E402
 
 from src.models.transformer.dit_c2i_baseline import FlattenDiT as RefFlattenDiT  # noqa: E402
+from src.models.transformer.dit_c2i_pixnerd import PixNerDiT as RefPixNerd  # noqa: E402
 from src.diffusion.flow_matching.sampling import (EulerSamplerJiT as RefEulerJiT, sde_mean_step_fn, sde_step_fn,  # noqa: E402
                                                   sde_preserve_step_fn)
 
@@ -314,6 +315,31 @@ def golden_baseline(name, cfg, B, res, seed):
                                       cfg.num_classes]), bf16_floor=np.float64(rel_l2(ref_bf, ref)))
 
 
+def golden_pixnerd(name, cfg, B, res, seed):
+    """PixNerd baseline (dit_c2i_pixnerd.PixNerDiT: hyper-network NerfBlock decoder): oracle pinned ahead of its CUDA path."""
+    m = RefPixNerd(in_channels=cfg.in_channels, num_groups=cfg.num_groups, hidden_size=cfg.hidden_size,
+                   hidden_size_x=cfg.hidden_size_x, nerf_mlpratio=cfg.nerf_mlpratio, num_blocks=cfg.num_blocks,
+                   num_cond_blocks=cfg.num_cond_blocks, patch_size=cfg.patch_size, num_classes=cfg.num_classes)
+    P = O.pixnerd_seeded_params(cfg)
+    sd = m.state_dict()
+    assert set(sd.keys()) == set(P.keys()), set(sd.keys()) ^ set(P.keys())
+    for k in sd:
+        assert tuple(sd[k].shape) == tuple(P[k].shape), k
+    m.load_state_dict(P)
+    m.eval()
+    x = seeded_noise(B, (cfg.in_channels, res, res), seed)
+    t = torch.linspace(0.1, 0.9, B)
+    y = torch.tensor([(3 * i + 1) % (cfg.num_classes + 1) for i in range(B)])
+    y[-1] = cfg.num_classes
+    ref = m(x, t, y)
+    e = rel_l2(O.pixnerd_forward(P, cfg, x, t, y), ref)
+    print(f"[{name}] oracle vs reference PixNerd forward rel-L2 = {e:.3e}")
+    assert e < 2e-6, e
+    np.savez_compressed(os.path.join(OUT, f"{name}.npz"), x=x.numpy(), t=t.numpy(), y=y.numpy(), out=ref.numpy(),
+                        cfg=np.array([cfg.in_channels, cfg.num_groups, cfg.hidden_size, cfg.hidden_size_x, cfg.nerf_mlpratio,
+                                      cfg.num_blocks, cfg.num_cond_blocks, cfg.patch_size, cfg.num_classes]))
+
+
 def golden_samplers_ext():
     """EulerSamplerJiT and the SDE step functions of EulerSampler, pinned with analytic 'networks'.  The Gaussian increments
     of sde_step_fn / sde_preserve_step_fn are the reference's own torch.randn_like calls under torch.manual_seed; they are
@@ -365,7 +391,10 @@ def golden_samplers_ext():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["dct", "samplers", "tiny", "t2i", "cfg1", "baseline", "samplers_ext"]
+    which = sys.argv[1:] or ["dct", "samplers", "tiny", "t2i", "cfg1", "baseline", "samplers_ext", "pixnerd"]
+    if "pixnerd" in which:
+        golden_pixnerd("pixnerd_d64", O.PixNerdCfg(num_groups=4, hidden_size=256, hidden_size_x=64, nerf_mlpratio=2, num_blocks=4,
+                                                   num_cond_blocks=2, num_classes=10), B=2, res=64, seed=51)
     if "baseline" in which:
         golden_baseline("baseline_d64", O.BaselineCfg(num_groups=4, hidden_size=256, num_blocks=3, num_classes=10),
                         B=3, res=64, seed=41)

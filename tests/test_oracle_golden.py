@@ -152,3 +152,21 @@ def test_extended_euler_samplers_match_reference_fixtures():
                                   randn=lambda x: incs.pop(0))
             assert rel_l2(o, torch.from_numpy(g[f"{kind}_{n}"])) < 1e-6, kind
             assert not incs
+
+
+def test_pixnerd_forward_matches_reference_fixture():
+    """dit_c2i_pixnerd.PixNerDiT (hyper-network NerfBlock decoder, configs_c2i/Baseline_PixNerd.yaml) restated ahead of its
+    CUDA path: the oracle against the live reference's output (make_golden.py::golden_pixnerd)."""
+    g = load_golden("pixnerd_d64.npz")
+    a = [int(v) for v in g["cfg"]]
+    cfg = O.PixNerdCfg(in_channels=a[0], num_groups=a[1], hidden_size=a[2], hidden_size_x=a[3], nerf_mlpratio=a[4],
+                       num_blocks=a[5], num_cond_blocks=a[6], patch_size=a[7], num_classes=a[8])
+    P = O.pixnerd_seeded_params(cfg)
+    out = O.pixnerd_forward(P, cfg, torch.from_numpy(g["x"]), torch.from_numpy(g["t"]), torch.from_numpy(g["y"]))
+    assert rel_l2(out, torch.from_numpy(g["out"])) < 2e-6
+    assert float(torch.from_numpy(g["out"]).abs().mean()) > 1e-2
+    # known answers: Baseline_PixNerd.yaml sizes -- each NerfBlock generates 2 * 64 * 128 weights per patch from H = 1024
+    big = O.PixNerdCfg()
+    sh = O.pixnerd_param_shapes(big)
+    assert sh["blocks.22.param_generator1.0.weight"] == (16384, 1024) and "blocks.21.attn.qkv.weight" in sh
+    assert "blocks.22.attn.qkv.weight" not in sh and sh["final_layer.linear.weight"] == (3, 64)
