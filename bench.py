@@ -85,14 +85,31 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-steps", type=int, default=2)
+    ap.add_argument("--cpu-batch", type=int, default=4, help="images per CFG-batched step of the CPU arm (configs[0] uses 4)")
+    ap.add_argument("--torch-baseline", default="both", choices=["none", "eager", "both"],
+                    help="time the reference's own GPU path (PyTorch bf16 autocast; eager and torch.compile) on this GPU")
+    ap.add_argument("--torch-baseline-batch", type=int, default=0, help="images per step of that arm (0 = the bench batch)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the in-run parity check against the fp32 oracle")
     ap.add_argument("--profile", action="store_true",
                     help="bracket the timed steps with cudaProfilerStart/Stop (use with ncu --profile-from-start off)")
     return ap.parse_args()
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the GEMM kernel, averaged over the launches of one step
-# (ncu --set full capture, profiles/): filled in from the capture of the same command, None until captured.
-GEMM_TRAFFIC = {"xl256": 1.0619e9}   # profiles/traffic_r1.txt: 173 GEMM launches of one step, 183.7 GB in total
+def gemm_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum per GEMM launch, averaged over the GEMM launches of ONE step, and the
+    per-kernel table it comes from: parsed from the committed ncu summary profiles/traffic_r2_<workload>.txt (written by
+    profiles/agg_traffic.py from `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum` over
+    `bench.py --workload <workload> --steps 1 --profile`).  (None, None) until that capture exists for the workload."""
+    path = os.path.join(ROOT, "profiles", f"traffic_r2_{workload}.txt")
+    if not os.path.exists(path):
+        return None, None
+    for ln in open(path):
+        if ln.startswith("#json "):
+            d = json.loads(ln[6:])
+            top = sorted(d["kernels"].items(), key=lambda kv: -kv[1]["ms"])[:8]
+            return d["gemm_dram_bytes_per_launch"], dict(source=os.path.relpath(path, ROOT), gemm_launches=d["gemm_launches"],
+                                                         kernels={k: v for k, v in top})
+    return None, None
 
 
 def measured_peaks():
@@ -184,19 +201,118 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    batch = 1
+    batch = args.cpu_batch
     sec, cores = cpu_reference_step_seconds(None, max(1, args.steps), max(0, args.warmup), batch)
     value = batch / (sec * NUM_SAMPLING_STEPS)
-    sample = (f"{batch} image, {args.steps} CFG-batched Euler steps of the 100 timed after {args.warmup} warm-up; "
+    sample = (f"{batch} images, {args.steps} CFG-batched Euler steps of the 100 timed after {args.warmup} warm-up; "
               f"images/s extrapolated linearly to 100 steps")
     line = dict(impl="reference", metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=sec * 1e3, higher_is_better=True, scaling="strong", vs_baseline=None,
                 dtype="fp32", data="synthetic",
-                config=dict(workload="DeCo-XL/16 256px c2i, Euler 100 x CFG 3.2 on (0.1,1]; CPU sample batch 1",
+                config=dict(workload=f"DeCo-XL/16 256px c2i, Euler 100 x CFG 3.2 on (0.1,1]; CPU sample batch {batch}",
                             global_batch=batch, num_sampling_steps=NUM_SAMPLING_STEPS),
                 cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port", sample=sample),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line), flush=True)
+
+
+def _oracle_forward(wl, net, dev):
+    """(fn(x, t, cond) -> velocity, fp32 parameter dict): the oracle restatement of this workload's denoiser, holding the
+    bench network's own weights (state_dict keys are the reference's, which is what the oracle indexes by)."""
+    import torch
+    from oracle import deco_oracle as O
+    P = {k: v.detach().to(device=dev, dtype=torch.float32) for k, v in net.state_dict().items()}
+    m = wl["model"]
+    if wl["kind"] == "t2i":
+        cfg = O.T2ICfg(in_channels=m["in_channels"], num_groups=m["num_groups"], hidden_size=m["hidden_size"],
+                       decoder_hidden_size=m["decoder_hidden_size"], num_encoder_blocks=m["num_encoder_blocks"],
+                       num_decoder_blocks=m["num_decoder_blocks"], num_text_blocks=m["num_text_blocks"],
+                       patch_size=m["patch_size"], txt_embed_dim=m["txt_embed_dim"], txt_max_length=m["txt_max_length"])
+        return (lambda x, t, c: O.t2i_forward(P, cfg, x, t, c.float())), P
+    if wl["kind"] == "baseline":
+        cfg = O.BaselineCfg(in_channels=m["in_channels"], num_groups=m["num_groups"], hidden_size=m["hidden_size"],
+                            num_blocks=m["num_blocks"], patch_size=m["patch_size"], num_classes=m["num_classes"])
+        return (lambda x, t, c: O.baseline_forward(P, cfg, x, t, c)), P
+    cfg = O.DenoiserCfg(in_channels=m["in_channels"], num_groups=m["num_groups"], hidden_size=m["hidden_size"],
+                        hidden_size_x=m["hidden_size_x"], num_blocks=m["num_blocks"], num_cond_blocks=m["num_cond_blocks"],
+                        patch_size=m["patch_size"], num_classes=m["num_classes"])
+    return (lambda x, t, c: O.denoiser_forward(P, cfg, x, t, c)), P
+
+
+def parity_check(torch, wl, net, dev, x, t_cur, cfg_cond, B, tol=1e-2):
+    """The number and the parity evidence on the SAME shape: one denoiser evaluation of the full bench batch (2B CFG rows)
+    through the product path, and the fp32 oracle (checker only) on image 0's two CFG rows [uncond, cond]; rel-L2 of
+    those two rows.  The bench aborts above the north_star tolerance (1e-2)."""
+    fwd, _ = _oracle_forward(wl, net, dev)
+    tt = torch.full((2 * B,), float(t_cur), device=dev)
+    with torch.no_grad():
+        out = net(torch.cat([x, x]), tt, cfg_cond).float()
+        rows = [0, B]
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            ref = fwd(x[[0, 0]].float(), tt[rows], cfg_cond[rows]).float()
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
+    got = out[rows]
+    e = float((got.double() - ref.double()).norm() / ref.double().norm())
+    res = dict(rel_l2=e, tol=tol, rows="image 0: [uncond, cond] of the full-batch forward", t=float(t_cur),
+               against="fp32 oracle (oracle/deco_oracle.py) on the same GPU, same weights", ok=bool(e <= tol))
+    if not e <= tol:
+        raise SystemExit(f"bench: parity check failed: rel-L2 {e:.3e} > {tol} -- refusing to report a throughput")
+    return res
+
+
+def torch_gpu_baseline(torch, args, wl, net, dev, x, t_cur, cfg_cond, B, nsteps):
+    """The reference's own GPU path on THIS GPU (src/lightning_model.py:94-97 compiles the denoiser,
+    src/diffusion/base/sampling.py:27 runs it under bf16 autocast): the oracle issues the reference's F.linear / SDPA /
+    layer_norm calls, so under torch.autocast(bf16) it is the library-kernel implementation (cuBLAS, flash SDPA, eager or
+    Inductor element-wise kernels) of the same step.  One CFG-batched denoiser evaluation + guidance + Euler update per step,
+    the same batch as the timed product path when it fits."""
+    import time as _time
+    from oracle import deco_oracle as O
+    fwd, _ = _oracle_forward(wl, net, dev)
+    Bt = args.torch_baseline_batch or B
+    Bt = min(Bt, B)
+    xb = x[:Bt].clone()
+    cond = torch.cat([cfg_cond[:Bt], cfg_cond[B:B + Bt]])
+    tt = torch.full((2 * Bt,), float(t_cur), device=dev)
+    g = float(wl["guidance"])
+
+    def step(f):
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            out = f(torch.cat([xb, xb]), tt, cond)
+        return xb + O.cfg_combine(out.float(), g) * 0.01
+
+    def timed(f, iters):
+        for _ in range(2):
+            step(f)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            step(f)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    res = dict(batch=Bt, cfg_rows=2 * Bt, dtype="bf16 autocast (fp32 master weights)", unit=UNIT,
+               note="oracle = the reference's torch calls; value = batch / (num_sampling_steps x seconds per step)")
+    try:
+        ms = timed(fwd, 3)
+        res["eager"] = dict(ms_per_step=ms, value=Bt / (ms * 1e-3 * nsteps))
+    except Exception as e:   # noqa: BLE001  (e.g. out of memory at the full batch)
+        res["eager"] = dict(error=str(e)[:200])
+    if args.torch_baseline == "both":
+        try:
+            t0 = _time.perf_counter()
+            cf = torch.compile(fwd)
+            ms = timed(cf, 3)
+            res["compiled"] = dict(ms_per_step=ms, value=Bt / (ms * 1e-3 * nsteps),
+                                   compile_seconds=_time.perf_counter() - t0)
+        except Exception as e:   # noqa: BLE001
+            res["compiled"] = dict(error=str(e)[:200])
+    return res
 
 
 # ----------------------------------------------------------------------------------------------- deco_b200 arm
@@ -410,6 +526,9 @@ def run_deco(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    parity = None
+    if not args.no_parity and not args.profile:
+        parity = parity_check(torch, wl, net, dev, x, ts[min(len(ts) - 2, nsteps // 3)], cfg_cond, B)
     for i in range(args.warmup):
         x = one_step(x, i)
     barrier()
@@ -451,6 +570,7 @@ def run_deco(args):
     value = gbatch / (ms_per_step * 1e-3 * nsteps)
     gs = probe.summary()
     peaks = measured_peaks()
+    traffic, traffic_tab = gemm_traffic(args.workload)
 
     # ---- e2e: public sampler API, host buffers in, uint8 images out (+ all-gather)
     e2e = None
@@ -501,15 +621,23 @@ def run_deco(args):
         fn = baseline_head_rooflines if wl["kind"] == "baseline" else hbm_kernel_rooflines
         hbm = fn(torch, ops, net, dev, 2 * B, res, peaks["hbm_gbs"])
 
+    tgb = None
+    if args.torch_baseline != "none" and world == 1 and not args.profile:
+        torch.cuda.empty_cache()
+        xb = noise_host.to(dev)
+        tgb = torch_gpu_baseline(torch, args, wl, net, dev, xb, ts[nsteps // 3], cfg_cond, B, nsteps)
+        del xb
+        torch.cuda.empty_cache()
+
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         sd = None
         if args.workload == "xl256":
             sd = {k: v.detach().float().cpu() for k, v in net.state_dict().items()}
-        sec, cores = cpu_reference_step_seconds(sd, args.cpu_sample_steps, 1, 1)
-        cpu = dict(value=1.0 / (sec * NUM_SAMPLING_STEPS), unit=UNIT, cores=cores, kind="port",
-                   sample=f"XL/16 256px: 1 image, {args.cpu_sample_steps} CFG-batched Euler steps (fp32 oracle port) timed "
-                          f"after 1 warm-up, extrapolated linearly to 100 steps; {sec:.2f} s per step")
+        sec, cores = cpu_reference_step_seconds(sd, args.cpu_sample_steps, 1, args.cpu_batch)
+        cpu = dict(value=args.cpu_batch / (sec * NUM_SAMPLING_STEPS), unit=UNIT, cores=cores, kind="port",
+                   sample=f"XL/16 256px: {args.cpu_batch} images, {args.cpu_sample_steps} CFG-batched Euler steps (fp32 oracle "
+                          f"port) timed after 1 warm-up, extrapolated linearly to 100 steps; {sec:.2f} s per step")
 
     line = dict(metric=wl["metric"], value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms_per_step, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="bf16",
@@ -524,14 +652,16 @@ def run_deco(args):
                 roofline=dict(kernel="gemm_bf16_tcgen05_kernel (all DiT / embed / cond_embed GEMMs)", bound="tensor",
                               achieved=gs["tflops"], peak=peaks["tf_sustained"], unit="TFLOP/s",
                               frac=(gs["tflops"] / peaks["tf_sustained"]) if peaks["tf_sustained"] else None,
-                              traffic=GEMM_TRAFFIC.get(args.workload), peak_source=peaks["source"] + ", sustained bf16",
+                              traffic=traffic, traffic_source=traffic_tab, peak_source=peaks["source"] + ", sustained bf16",
                               launches=gs["launches"], avg_launch_ms=gs["avg_ms"],
                               avg_launch_algorithmic_gflop=gs["total_flops"] / max(1, gs["launches"]) / 1e9,
-                              gemm_share_of_step=gs["total_ms"] / ms_probe_total if ms_probe_total else None,
-                              measured="second pass of the same steps with CUDA events around every GEMM launch",
+                              gemm_ms_per_step=gs["total_ms"] / args.steps,
+                              gemm_share_of_step=(gs["total_ms"] / args.steps) / ms_per_step if ms_per_step else None,
+                              measured="second pass of the same steps with CUDA events around every GEMM launch; "
+                                       "share = GEMM ms per step of that pass / the timed ms_per_step",
                               per_gpu_step_tflops_algorithmic=(wl["gflop"] * 1e9 * 2 * B) / (ms_per_step * 1e-3) / 1e12,
                               step_frac_of_peak=(wl["gflop"] * 1e9 * 2 * B) / (ms_per_step * 1e-3) / 1e12 / peaks["tf_sustained"]),
-                hbm_kernels=hbm, cpu_baseline=cpu)
+                parity=parity, torch_gpu_baseline=tgb, hbm_kernels=hbm, cpu_baseline=cpu)
     print(json.dumps(line), flush=True)
     finish()
 

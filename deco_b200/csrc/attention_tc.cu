@@ -445,11 +445,11 @@ static int make_attn_tmap(CUtensorMap* map, const void* ptr, int D, long long L,
 template <int D>
 static int launch_attention_tc(const TcAttnMaps& M, const TcAttnParams& P, cudaStream_t st) {
     using C = TcAttnCfg<D>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static unsigned long long attr_done = 0;
+    if (!device_setup_done(attr_done)) {
         cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
         if (e != cudaSuccess) { deco_set_error("attention attr: %s", cudaGetErrorString(e)); return (int)e; }
-        attr_done = true;
+        mark_device_setup(attr_done);
     }
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);

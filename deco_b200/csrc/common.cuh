@@ -37,6 +37,26 @@ namespace deco {
 
 constexpr int kNumSMs = 148;
 
+// One-time per-DEVICE host setup (cudaFuncSetAttribute, SM count): a process may drive several GPUs, and function
+// attributes / device properties belong to the current device's context, not to the process.
+inline int current_device_slot() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev & 63;
+}
+inline bool device_setup_done(const unsigned long long& mask) { return (mask >> current_device_slot()) & 1ull; }
+inline void mark_device_setup(unsigned long long& mask) { mask |= 1ull << current_device_slot(); }
+inline int device_sm_count() {
+    static int cached[64] = {0};
+    const int slot = current_device_slot();
+    if (!cached[slot]) {
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, slot);
+        cached[slot] = n > 0 ? n : kNumSMs;
+    }
+    return cached[slot];
+}
+
 __device__ __forceinline__ float bf2f(__nv_bfloat16 v) { return __bfloat162float(v); }
 __device__ __forceinline__ __nv_bfloat16 f2bf(float v) { return __float2bfloat16_rn(v); }
 __device__ __forceinline__ float round_bf(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }

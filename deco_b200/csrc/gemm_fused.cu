@@ -694,26 +694,17 @@ static int make_map(CUtensorMap* map, CUtensorMapDataType dt, int esize, const v
     return DECO_OK;
 }
 
-static int sm_count() {
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = kNumSMs;
-    }
-    return n - deco_reserved_sms();
-}
+static int sm_count() { return device_sm_count() - deco_reserved_sms(); }
 
 template <int BN, int EPI>
 static int launch(const Maps& maps, const Params& P, cudaStream_t st) {
     using C = Cfg<BN, EPI>;
     auto kern = gemm_fused_kernel<BN, EPI>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static unsigned long long attr_done = 0;
+    if (!device_setup_done(attr_done)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
         if (e != cudaSuccess) { deco_set_error("fused gemm smem attr: %s", cudaGetErrorString(e)); return (int)e; }
-        attr_done = true;
+        mark_device_setup(attr_done);
     }
     const int tiles = ((P.M + 2 * kBM - 1) / (2 * kBM)) * ((P.N + BN - 1) / BN);
     int groups = sm_count() / 2;

@@ -445,11 +445,11 @@ template <int BN, int EPI, int CG, bool STAGED, bool TN = false>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& P, int max_ctas, cudaStream_t st) {
     using Cfg = GemmCfg<BN, CG>;
     auto kern = gemm_bf16_tcgen05_kernel<BN, EPI, CG, STAGED, TN>;
-    static bool attr_done = false;   // per instantiation
-    if (!attr_done) {
+    static unsigned long long attr_done = 0;   // per instantiation
+    if (!device_setup_done(attr_done)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
         if (e != cudaSuccess) { deco_set_error("gemm smem attr: %s", cudaGetErrorString(e)); return (int)e; }
-        attr_done = true;
+        mark_device_setup(attr_done);
     }
     const int tiles = ((P.M + kBM * CG - 1) / (kBM * CG)) * ((P.N + BN - 1) / BN) * (EPI == EPI_BIAS_F32 && P.split_k > 1 ? P.split_k : 1);
     int groups = max_ctas / CG;
@@ -497,16 +497,7 @@ static int dispatch_variant(int cg, int staged, int epi, const CUtensorMap& ta, 
 static int g_force_cta_group = -1;
 static int g_force_staged = -1;
 
-static int g_num_sms_cached = 0;
-static int num_sms() {
-    if (!g_num_sms_cached) {
-        int dev = 0, n = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        g_num_sms_cached = n > 0 ? n : kNumSMs;
-    }
-    return g_num_sms_cached - deco_reserved_sms();
-}
+static int num_sms() { return device_sm_count() - deco_reserved_sms(); }
 
 }  // namespace deco
 

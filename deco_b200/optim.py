@@ -34,6 +34,7 @@ class FusedAdamWEMA:
         self._tables = None
         self._grad_ptrs = None
         self._chunks = None
+        self._upload_done = None      # CUDA event after the last pointer-table upload (guards the pinned staging buffer)
 
     def _build_tables(self):
         """Device tables of tensor pointers / CTA chunks.  Rebuilt when a gradient buffer moved (autograd hands out new
@@ -52,8 +53,16 @@ class FusedAdamWEMA:
             self._rows_dev = torch.empty((len(self.params), 6), dtype=torch.int64, device=dev)
         rows = [[p.data_ptr(), p.grad.data_ptr(), self.exp_avg[i].data_ptr(), self.exp_avg_sq[i].data_ptr(),
                  self.ema[i].data_ptr() if self.ema is not None else 0, p.numel()] for i, p in enumerate(self.params)]
+        # The eager loop may run more than one step ahead of the GPU: the previous asynchronous upload must have READ the
+        # pinned buffer before the host rewrites it (otherwise step N's kernel would dereference step N+1's gradient
+        # pointers).  Normally the event has long completed and the wait is free.  The device table itself is ordered
+        # by the stream (the previous step's kernel precedes this copy).
+        if self._upload_done is not None:
+            self._upload_done.synchronize()
         self._rows_host.copy_(torch.tensor(rows, dtype=torch.int64))
         self._rows_dev.copy_(self._rows_host, non_blocking=True)
+        self._upload_done = torch.cuda.Event()
+        self._upload_done.record(torch.cuda.current_stream(dev))
         self._grad_ptrs = [p.grad.data_ptr() for p in self.params]
         self._tables = (self._rows_dev, self._chunks)
 
@@ -78,6 +87,43 @@ class FusedAdamWEMA:
         torch.autograd.graph.increment_version(self.params)
         if self.ema is not None:
             torch.autograd.graph.increment_version(self.ema)
+
+    # ------------------------------------------------------------------ checkpointing (torch.optim.AdamW layout)
+    def state_dict(self) -> dict:
+        """Same layout as `torch.optim.AdamW.state_dict()` (what Lightning writes into `optimizer_states[0]`): `state` =
+        {index: {step, exp_avg, exp_avg_sq}} over the trainable parameters in order, one `param_groups` entry."""
+        state = {i: dict(step=torch.tensor(float(self.step_count)), exp_avg=self.exp_avg[i], exp_avg_sq=self.exp_avg_sq[i])
+                 for i in range(len(self.params))}
+        group = dict(lr=self.lr, betas=tuple(self.betas), eps=self.eps, weight_decay=self.weight_decay, amsgrad=False,
+                     maximize=False, foreach=None, capturable=False, differentiable=False, fused=None,
+                     params=list(range(len(self.params))))
+        return dict(state=state, param_groups=[group])
+
+    @torch.no_grad()
+    def load_state_dict(self, sd: dict) -> None:
+        """Accepts this class's `state_dict()` or one written by `torch.optim.AdamW` over the same parameter list."""
+        groups = sd["param_groups"]
+        order = [i for g in groups for i in g["params"]]
+        if len(order) != len(self.params):
+            raise ValueError(f"optimizer state has {len(order)} parameters, this optimizer {len(self.params)}")
+        g0 = groups[0]
+        self.lr, self.betas, self.eps = g0["lr"], tuple(g0["betas"]), g0["eps"]
+        self.weight_decay = g0["weight_decay"]
+        steps = set()
+        for slot, idx in enumerate(order):
+            st = sd["state"].get(idx)
+            if st is None:                      # a parameter that never received a gradient
+                self.exp_avg[slot].zero_()
+                self.exp_avg_sq[slot].zero_()
+                continue
+            if st["exp_avg"].shape != self.params[slot].shape:
+                raise ValueError(f"optimizer state {idx}: shape {tuple(st['exp_avg'].shape)} != {tuple(self.params[slot].shape)}")
+            self.exp_avg[slot].copy_(st["exp_avg"])
+            self.exp_avg_sq[slot].copy_(st["exp_avg_sq"])
+            steps.add(int(float(st["step"])))
+        if len(steps) > 1:
+            raise ValueError(f"per-parameter step counts differ ({sorted(steps)}): the fused kernel keeps one")
+        self.step_count = steps.pop() if steps else 0
 
     def zero_grad(self, set_to_none: bool = True):
         for p in self.params:

@@ -100,18 +100,29 @@ class BaseSampler(nn.Module):
         spec = self._graph_rows()
         if spec is None:
             return None
+        if not isinstance(self.guidance, (int, float)):
+            return None               # per-sample guidance lists: eager loop (the graphed table holds one scalar per step)
         prep = net.prepare(noise.device) if hasattr(net, "prepare") else None
-        key = (id(net), id(prep), tuple(noise.shape), tuple(cfg_condition.shape), cfg_condition.dtype, bool(to_uint8),
-               noise.device.index, float(self.guidance))
+        # one stepper per (net, batch shape, output kind): a new weight version (id(prep) changes after an optimizer step
+        # or a checkpoint load) REPLACES the entry, so the old graph, its memory pool and its bf16 weight copies are freed
+        slot = (id(net), tuple(noise.shape), tuple(cfg_condition.shape), cfg_condition.dtype, bool(to_uint8),
+                noise.device.index)
+        version = (id(prep), float(self.guidance))
         cache = self.__dict__.setdefault("_steppers", {})
-        if key not in cache:
-            try:
-                cache[key] = GraphedStepper(self, net, noise.shape[0], noise.shape[1:], cfg_condition[: noise.shape[0]],
-                                            to_uint8, spec[0], spec[1])
-            except Exception as e:   # noqa: BLE001 -- capture is an optimisation; the eager loop runs the same kernels
-                logger.warning("CUDA-graph capture of the sampling step failed (%s); using the eager loop", e)
-                cache[key] = None
-        return cache[key]
+        hit = cache.get(slot)
+        if hit is not None and hit[0] == version:
+            return hit[1]
+        cache.pop(slot, None)
+        while len(cache) >= MAX_STEPPERS:
+            cache.pop(next(iter(cache)))
+        try:
+            st = GraphedStepper(self, net, noise.shape[0], noise.shape[1:], cfg_condition[: noise.shape[0]],
+                                to_uint8, spec[0], spec[1])
+        except Exception as e:   # noqa: BLE001 -- capture is an optimisation; the eager loop runs the same kernels
+            logger.warning("CUDA-graph capture of the sampling step failed (%s); using the eager loop", e)
+            st = None
+        cache[slot] = (version, st)
+        return st
 
     def _run_graphed(self, net, x, cfg_condition, to_uint8):
         st = self.graphed_stepper(net, x, cfg_condition, to_uint8)
@@ -160,6 +171,7 @@ def _prep_inputs(noise, condition, uncondition):
 
 
 GRAPH = os.environ.get("DECO_B200_GRAPH", "1") != "0"
+MAX_STEPPERS = 4     # captured graphs kept per sampler (distinct batch shapes / output kinds)
 
 
 class GraphedStepper:

@@ -421,6 +421,66 @@ def test_fused_adamw_ema_matches_torch(dev):
             assert torch.allclose(e, er, rtol=2e-6, atol=2e-7)
 
 
+def test_fused_adamw_unsynced_steps_with_moving_grad_buffers(dev):
+    """the pointer table is re-uploaded through ONE pinned staging buffer whenever a .grad tensor moved.  With
+    the host running ahead of the GPU (a long kernel queued first, no synchronisation between steps) every step must still
+    see ITS gradients: compare with torch.optim.AdamW fed the same gradients."""
+    from deco_b200 import FusedAdamWEMA
+    g = _g(11)
+    shapes = [(1 << 16,), (257, 129), (5,)]
+    ps = [torch.nn.Parameter(torch.randn(s, device=dev, generator=g)) for s in shapes]
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    kw = dict(lr=1e-2, betas=(0.9, 0.99), eps=1e-8, weight_decay=0.01)
+    opt, topt = FusedAdamWEMA(ps, None, **kw), torch.optim.AdamW(ref, **kw)
+    nstep = 6
+    grads = [[torch.randn(s, device=dev, generator=g) for s in shapes] for _ in range(nstep)]
+    keep = [[gr.clone() for gr in row] for row in grads]          # distinct buffers per step: the pointers move every step
+    big = torch.randn(8192, 8192, device=dev)
+    torch.cuda.synchronize()
+    for _ in range(6):
+        big = big @ big * 1e-4          # ~tens of ms of queued GPU work: the host loop below runs ahead of the device
+    for it in range(nstep):
+        for p, gr in zip(ps, keep[it]):
+            p.grad = gr
+        opt.step()
+    torch.cuda.synchronize()
+    for it in range(nstep):
+        for r, gr in zip(ref, grads[it]):
+            r.grad = gr
+        topt.step()
+    for p, r in zip(ps, ref):
+        assert torch.allclose(p, r, rtol=5e-6, atol=5e-7), float((p - r).abs().max())
+
+
+def test_fused_adamw_state_dict_roundtrip_with_torch(dev):
+    """state_dict() has torch.optim.AdamW's layout (what Lightning stores in `optimizer_states`): load it into torch's
+    AdamW and back, continue both, same parameters."""
+    from deco_b200 import FusedAdamWEMA
+    g = _g(5)
+    shapes = [(33, 5), (4097,)]
+    ps = [torch.nn.Parameter(torch.randn(s, device=dev, generator=g)) for s in shapes]
+    kw = dict(lr=3e-3, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.05)
+    opt = FusedAdamWEMA(ps, None, **kw)
+    for _ in range(2):
+        for p in ps:
+            p.grad = torch.randn(p.shape, device=dev, generator=g)
+        opt.step()
+    sd = opt.state_dict()
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    topt = torch.optim.AdamW(ref, **kw)
+    topt.load_state_dict(sd)
+    ps2 = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    opt2 = FusedAdamWEMA(ps2, None, lr=1.0)
+    opt2.load_state_dict(topt.state_dict())
+    assert opt2.step_count == 2 and opt2.lr == kw["lr"] and opt2.betas == kw["betas"]
+    for p, r, q in zip(ps, ref, ps2):
+        gr = torch.randn(p.shape, device=dev, generator=g)
+        p.grad, r.grad, q.grad = gr.clone(), gr.clone(), gr.clone()
+    opt.step(); topt.step(); opt2.step()
+    for p, r, q in zip(ps, ref, ps2):
+        assert torch.allclose(p, r, rtol=2e-6, atol=2e-7) and torch.equal(p, q)
+
+
 def test_training_loop_with_fused_optimizer_reduces_loss(dev):
     """forward + backward + FusedAdamWEMA for a few steps on one fixed batch: the weight caches follow the parameters and
     the loss goes down."""

@@ -77,7 +77,7 @@ def test_baseline_jit_config_shape_vs_oracle(cuda_dev):
         S.GRAPH = True
         sg = EulerSamplerJiT(**kw)
         xg, ug = sg.sample_uint8(m, x, cond, unc)
-        assert any(v is not None for v in sg._steppers.values()), "the JiT step was not captured into a CUDA graph"
+        assert any(v[1] is not None for v in sg._steppers.values()), "the JiT step was not captured into a CUDA graph"
         S.GRAPH = False
         xe, ue = EulerSamplerJiT(**kw).sample_uint8(m, x, cond, unc)
     finally:

@@ -52,6 +52,52 @@ def test_xl16_forward_vs_oracle(cuda_dev):
     assert e <= 1e-2
 
 
+def _fp32_oracle(Pd, cfg, x, t, y):
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        return O.denoiser_forward(Pd, cfg, x, t, y)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+def test_xl16_512px_forward_vs_oracle(cuda_dev):
+    """BASELINE.json configs[2] end to end (configs_c2i/DeCo_XL_512.yaml; dit_c2i_DeCo.py:488-510): XL/16 at 512 px =
+    1024 tokens per image, axial RoPE over a 32 x 32 grid, 262 144 decoder pixels per image; 2 CFG rows against the
+    fp32 oracle on the GPU.  Tolerance (north_star): rel-L2 <= 1e-2."""
+    cfg = O.CFG_XL
+    m, P = build_module(cfg, cuda_dev)
+    Pd = {k: v.to(cuda_dev) for k, v in P.items()}
+    x = seeded_noise(1, (3, 512, 512), 11).to(cuda_dev).repeat(2, 1, 1, 1)
+    t = torch.tensor([0.63, 0.63], device=cuda_dev)
+    y = torch.tensor([1000, 417], device=cuda_dev)
+    ref = _fp32_oracle(Pd, cfg, x, t, y)
+    out = m(x, t, y)
+    e = rel_l2(out.float(), ref)
+    print(f"XL/16 512px c2i: rel-L2 vs fp32 oracle = {e:.3e}")
+    assert out.shape == x.shape and e <= 1e-2
+
+
+def test_xl16_forward_t_sweep_vs_oracle(cuda_dev):
+    """XL/16 256 px over the whole time range and both label kinds: t in {0, 0.1, 0.5, 0.99} x {class label, null label}
+    as one 8-row batch (every row has its own t: the per-image modulation path), each row within rel-L2 <= 1e-2 of the
+    fp32 oracle (north_star tolerance); the worst row is printed."""
+    cfg = O.CFG_XL
+    m, P = build_module(cfg, cuda_dev)
+    Pd = {k: v.to(cuda_dev) for k, v in P.items()}
+    ts = [0.0, 0.1, 0.5, 0.99]
+    x = seeded_noise(8, (3, 256, 256), 21).to(cuda_dev)
+    t = torch.tensor([v for v in ts for _ in range(2)], device=cuda_dev)
+    y = torch.tensor([207, 1000] * 4, device=cuda_dev)
+    ref = _fp32_oracle(Pd, cfg, x, t, y)
+    out = m(x, t, y).float()
+    errs = [rel_l2(out[i], ref[i]) for i in range(8)]
+    for i, e in enumerate(errs):
+        print(f"XL/16 t={float(t[i]):.2f} y={int(y[i])}: rel-L2 vs fp32 oracle = {e:.3e}")
+    print(f"XL/16 t-sweep worst row: {max(errs):.3e}")
+    assert max(errs) <= 1e-2
+
+
 def test_t2i_forward_vs_reference_golden(cuda_dev):
     """Text-to-image denoiser (joint [image || text] attention, text-refine blocks) against the fixture produced by the
     composed reference classes.  Tolerance (north_star): rel-L2 <= 1e-2 per bf16 forward vs the fp32 reference."""
@@ -285,7 +331,7 @@ def test_graphed_sampling_step_equals_eager_loop(cuda_dev, monkeypatch):
     monkeypatch.setattr(S, "GRAPH", True)
     sg = EulerSampler(**kw)
     xg, ug = sg.sample_uint8(m, noise, cond, unc)
-    assert any(v is not None for v in sg._steppers.values()), "the sampling step was not captured into a CUDA graph"
+    assert any(v[1] is not None for v in sg._steppers.values()), "the sampling step was not captured into a CUDA graph"
     xg2 = sg(m, noise, cond, unc)                     # second trajectory through the cached graph (no uint8 variant)
     monkeypatch.setattr(S, "GRAPH", False)
     se = EulerSampler(**kw)
@@ -344,7 +390,7 @@ def test_graphed_adams_step_equals_eager_loop(cuda_dev, monkeypatch):
     monkeypatch.setattr(S, "GRAPH", True)
     sg = AdamLMSampler(**kw)
     xg, ug = sg.sample_uint8(m, noise, cond, unc)
-    assert any(v is not None for v in sg._steppers.values()), "the sampling step was not captured into a CUDA graph"
+    assert any(v[1] is not None for v in sg._steppers.values()), "the sampling step was not captured into a CUDA graph"
     monkeypatch.setattr(S, "GRAPH", False)
     xe, ue = AdamLMSampler(**kw).sample_uint8(m, noise, cond, unc)
     assert torch.equal(xg, xe) and torch.equal(ug, ue)
