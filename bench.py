@@ -305,6 +305,11 @@ def torch_gpu_baseline(torch, args, wl, net, dev, x, t_cur, cfg_cond, B, nsteps)
         res["eager"] = dict(error=str(e)[:200])
     if args.torch_baseline == "both":
         try:
+            # Inductor's C++ wrapper is built with -fopenmp; this image keeps libgomp.spec under gcc's own library directory,
+            # which /opt/gcc/bin/g++ does not search by itself
+            gomp = "/usr/lib/gcc/x86_64-linux-gnu/13"
+            if os.path.exists(os.path.join(gomp, "libgomp.spec")) and gomp not in os.environ.get("LIBRARY_PATH", ""):
+                os.environ["LIBRARY_PATH"] = gomp + (":" + os.environ["LIBRARY_PATH"] if os.environ.get("LIBRARY_PATH") else "")
             t0 = _time.perf_counter()
             cf = torch.compile(fwd)
             ms = timed(cf, 3)

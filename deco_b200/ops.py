@@ -438,6 +438,42 @@ def dct_fm_loss(out: torch.Tensor, v_t: torch.Tensor, freq_w: torch.Tensor, freq
     return losses, grad
 
 
+# ------------------------------------------------------------------------------------------------ training-step inputs
+def train_timesteps(nt: torch.Tensor, u_uniform: torch.Tensor, u_select: torch.Tensor, timeshift: float, linear: bool):
+    """t = time_shift(where(u_select <= 0.9, sigmoid(nt), u_uniform)) and, for the LinearScheduler, the per-image
+    coefficients (alpha, sigma, dalpha, dsigma) [B, 4] (csrc/train_inputs.cu).  Returns (t, coef | None)."""
+    _cuda(nt, u_uniform, u_select)
+    for v in (nt, u_uniform, u_select):
+        assert v.dtype == torch.float32 and v.is_contiguous() and v.shape == nt.shape and v.dim() == 1
+    B = nt.numel()
+    t = torch.empty_like(nt)
+    coef = torch.empty((B, 4), dtype=torch.float32, device=nt.device) if linear else None
+    call("deco_train_timesteps", ptr(nt), ptr(u_uniform), ptr(u_select), float(timeshift), int(linear), ptr(t), ptr(coef), B,
+         _st(nt))
+    return t, coef
+
+
+def flow_pair(x: torch.Tensor, eps: torch.Tensor, coef: torch.Tensor):
+    """(x_t, v_t) = (alpha x + sigma eps, dalpha x + dsigma eps) with coef [B, 4] = per-image (alpha, sigma, dalpha, dsigma)."""
+    _cuda(x, eps, coef)
+    assert x.dtype == torch.float32 and x.is_contiguous() and eps.dtype == torch.float32 and eps.is_contiguous()
+    assert eps.shape == x.shape and coef.dtype == torch.float32 and coef.is_contiguous() and coef.shape == (x.shape[0], 4)
+    x_t, v_t = torch.empty_like(x), torch.empty_like(x)
+    call("deco_flow_pair", ptr(x), ptr(eps), ptr(coef), ptr(x_t), ptr(v_t), x.shape[0], x.numel() // x.shape[0], _st(x))
+    return x_t, v_t
+
+
+def label_dropout(cond: torch.Tensor, uncond: torch.Tensor, u: torch.Tensor, p: float) -> torch.Tensor:
+    """out[i] = uncond[i] if u[i] < p else cond[i] (int64 labels; base/training.py:14-20)."""
+    _cuda(cond, uncond, u)
+    assert cond.dtype == torch.int64 and uncond.dtype == torch.int64 and cond.dim() == 1 and uncond.shape == cond.shape
+    assert u.dtype == torch.float32 and u.shape == cond.shape
+    cond, uncond, u = cond.contiguous(), uncond.contiguous(), u.contiguous()
+    out = torch.empty_like(cond)
+    call("deco_label_dropout", ptr(cond), ptr(uncond), ptr(u), float(p), ptr(out), cond.numel(), _st(cond))
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ backward (training)
 def transpose_cast(src: torch.Tensor, rows_pad: Optional[int] = None) -> torch.Tensor:
     """[R, C] (fp32 or bf16, row stride free) -> bf16 [C, Rp] with rows R..Rp zero-filled (Rp = R rounded up to 8):

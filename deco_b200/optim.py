@@ -96,6 +96,7 @@ class FusedAdamWEMA:
                  for i in range(len(self.params))}
         group = dict(lr=self.lr, betas=tuple(self.betas), eps=self.eps, weight_decay=self.weight_decay, amsgrad=False,
                      maximize=False, foreach=None, capturable=False, differentiable=False, fused=None,
+                     decoupled_weight_decay=True,
                      params=list(range(len(self.params))))
         return dict(state=state, param_groups=[group])
 

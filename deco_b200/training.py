@@ -93,9 +93,13 @@ class BaseTrainer(nn.Module):
     def preproprocess(self, x, condition, uncondition, metadata):
         bsz = x.shape[0]
         if self.null_condition_p > 0:
-            mask = torch.rand((bsz), device=condition.device) < self.null_condition_p
-            mask = mask.view(-1, *([1] * (len(condition.shape) - 1))).to(condition.dtype)
-            condition = condition * (1 - mask) + uncondition * mask
+            u = torch.rand((bsz), device=condition.device)          # the reference's draw (base/training.py:17)
+            if condition.is_cuda and condition.dtype == torch.int64 and condition.dim() == 1 \
+                    and uncondition.shape == condition.shape:
+                condition = ops.label_dropout(condition, uncondition, u, self.null_condition_p)
+            else:       # embedding-valued conditions (t2i text states): the reference's own tensor arithmetic
+                mask = (u < self.null_condition_p).view(-1, *([1] * (len(condition.shape) - 1))).to(condition.dtype)
+                condition = condition * (1 - mask) + uncondition * mask
         return x, condition, metadata
 
     def _impl_trainstep(self, net, ema_net, solver, x, y, metadata=None):
@@ -129,21 +133,31 @@ class REPATrainer(BaseTrainer):
         """dict(fm_loss, fm_loss_freq, loss) for network output `out` and target `v_t` (both [B,3,H,W])."""
         fw = self.freq_w.reshape(3, 8, 8).to(device=out.device, dtype=torch.float32).contiguous()
         total, losses = _DctFmLoss.apply(out, v_t, fw, float(self.freq_loss_weight))
+        if not self.freq_loss_weight:
+            # reference-parity mode: the checked-in fork trains loss = fm_loss.mean() and returns exactly these two keys
+            # (training_repa_DeCo.py:276-288; its DCT term is commented out) -- see INTEGRATION.md "objective"
+            return dict(fm_loss=losses[0], loss=total)
         return dict(fm_loss=losses[0], fm_loss_freq=losses[1], loss=total)
 
     def _impl_trainstep(self, net, ema_net, solver, x, y, metadata=None):
+        if not x.is_cuda:
+            raise RuntimeError("deco_b200.REPATrainer runs on CUDA tensors only (no CPU fallback)")
         batch_size = x.shape[0]
-        # mixed timestep distribution: 90 % sigmoid(randn), 10 % uniform (training_repa_DeCo.py:222-229)
+        x = x.detach().to(torch.float32).contiguous()
+        # mixed timestep distribution: 90 % sigmoid(randn), 10 % uniform (training_repa_DeCo.py:222-229).  The four draws
+        # are torch's, in the reference's order (same Philox stream under a fixed seed); everything after them is three
+        # kernels of csrc/train_inputs.cu instead of ~15 eager element-wise launches
         nt = torch.randn((batch_size,), device=x.device, dtype=torch.float32)
-        t_lognorm = torch.sigmoid(nt)
         t_uniform = torch.rand((batch_size,), device=x.device, dtype=torch.float32)
-        base_t = torch.where(torch.rand((batch_size,), device=x.device) <= 0.9, t_lognorm, t_uniform)
-        t = time_shift_fn(base_t, self.timeshift)
+        u_select = torch.rand((batch_size,), device=x.device)
+        linear = type(self.scheduler).__name__ == "LinearScheduler"
+        t, coef = ops.train_timesteps(nt, t_uniform, u_select, self.timeshift, linear)
         noise = torch.randn_like(x)
-        alpha, dalpha = self.scheduler.alpha(t), self.scheduler.dalpha(t)
-        sigma, dsigma = self.scheduler.sigma(t), self.scheduler.dsigma(t)
-        x_t = alpha * x + noise * sigma
-        v_t = dalpha * x + dsigma * noise
+        if coef is None:      # other schedulers: their own (batch-sized) coefficient expressions
+            sch = self.scheduler
+            coef = torch.stack([torch.as_tensor(f(t), dtype=torch.float32, device=x.device).reshape(-1).expand(batch_size)
+                                for f in (sch.alpha, sch.sigma, sch.dalpha, sch.dsigma)], dim=1).contiguous()
+        x_t, v_t = ops.flow_pair(x, noise, coef)
         out = net(x_t, t, y)
         return self.loss(out, v_t)
 

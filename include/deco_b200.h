@@ -145,6 +145,19 @@ int deco_attention_fwd(const void* q, long long q_stride,
                        void* out, long long out_stride,
                        int B, int heads, int Lq, int head_dim, float scale, void* stream);
 
+/* Training-step inputs (src/diffusion/flow_matching/training_repa_DeCo.py:222-237, src/diffusion/base/training.py:14-20).
+ * The random draws stay the caller's (torch's CUDA generator, reference order); these fuse what follows them.
+ * deco_train_timesteps: t = time_shift(where(u_select <= 0.9, sigmoid(nt), u_uniform)) (fp32 [B]); with
+ *   linear_scheduler != 0 also coef[B][4] = (alpha, sigma, dalpha, dsigma) = (t, 1-t, 1, -1) (scheduling.py:6-14).
+ * deco_flow_pair: x_t = alpha x + sigma eps, v_t = dalpha x + dsigma eps with per-image coef[B][4]; fp32 [B, per_image].
+ * deco_label_dropout: out[i] = u[i] < p ? uncond[i] : cond[i] (int64 labels). */
+int deco_train_timesteps(const float* nt, const float* u_uniform, const float* u_select, float timeshift,
+                         int linear_scheduler, float* t_out, float* coef_out, int B, void* stream);
+int deco_flow_pair(const float* x, const float* eps, const float* coef, float* x_t, float* v_t,
+                   int B, long long per_image, void* stream);
+int deco_label_dropout(const long long* cond, const long long* uncond, const float* u, float p,
+                       long long* out, int B, void* stream);
+
 /* s = silu(t + s) (dit_c2i_DeCo.py:499): out[m,:] = silu(x[m,:] + row[m / rows_per,:]); out may alias x */
 int deco_silu_add_rows(const void* x, int x_is_f32, const void* row_bf16, void* out_bf16, long long M, int hidden,
                        int rows_per, void* stream);

@@ -501,6 +501,49 @@ def make_xt_vt(x: torch.Tensor, noise: torch.Tensor, t: torch.Tensor):
     return a * x + (1 - a) * noise, x - noise
 
 
+def label_dropout(condition: torch.Tensor, uncondition: torch.Tensor, null_condition_p: float) -> torch.Tensor:
+    """BaseTrainer.preproprocess (src/diffusion/base/training.py:14-20): one torch.rand(bsz) draw on the condition's device,
+    rows with u < p take the null condition."""
+    if null_condition_p <= 0:
+        return condition
+    bsz = condition.shape[0]
+    mask = torch.rand((bsz), device=condition.device) < null_condition_p
+    mask = mask.view(-1, *([1] * (len(condition.shape) - 1))).to(condition.dtype)
+    return condition * (1 - mask) + uncondition * mask
+
+
+def trainstep_inputs(x: torch.Tensor, timeshift: float = 1.0):
+    """REPATrainer._impl_trainstep up to the network call (training_repa_DeCo.py:222-237), LinearScheduler
+    (scheduling.py:6-14: alpha = t, sigma = 1 - t, dalpha = 1, dsigma = -1), drawing from torch's global generator of
+    x's device in the reference's order: randn(B) -> rand(B) [uniform t] -> rand(B) [90/10 selector] -> randn_like(x).
+    Returns (t [B], x_t, v_t)."""
+    B = x.shape[0]
+    nt = torch.randn((B,), device=x.device, dtype=torch.float32)
+    t_lognorm = torch.sigmoid(nt)
+    t_uniform = torch.rand((B,), device=x.device, dtype=torch.float32)
+    base_t = torch.where(torch.rand((B,), device=x.device) <= 0.9, t_lognorm, t_uniform)
+    t = time_shift(base_t, timeshift)
+    noise = torch.randn_like(x)
+    a = t.view(-1, 1, 1, 1)
+    alpha, sigma = a, 1.0 - a
+    dalpha, dsigma = torch.full_like(a, 1.0), torch.full_like(a, -1.0)
+    return t, alpha * x + noise * sigma, dalpha * x + dsigma * noise
+
+
+def trainstep(net: Callable, x: torch.Tensor, condition: torch.Tensor, uncondition: torch.Tensor,
+              null_condition_p: float = 0.1, timeshift: float = 1.0, freq_loss_weight: float = 0.0) -> Dict[str, torch.Tensor]:
+    """BaseTrainer.__call__ + REPATrainer._impl_trainstep (base/training.py:25-28, training_repa_DeCo.py:216-288).
+    freq_loss_weight = 0 is the objective of the checked-in fork (loss = fm_loss.mean(), :276-288); > 0 adds the block-DCT
+    term of the original trainer (the formula kept in the comment at :276-285)."""
+    y = label_dropout(condition, uncondition, null_condition_p)
+    t, x_t, v_t = trainstep_inputs(x, timeshift)
+    out = net(x_t, t, y)
+    if freq_loss_weight:
+        return dct_fm_loss(out.float(), v_t, freq_loss_weight)
+    fm = ((out.float() - v_t) ** 2).mean()
+    return dict(fm_loss=fm, loss=fm)
+
+
 # --------------------------------------------------------------------------- text-to-image denoiser (config 5)
 # The original `src/models/transformer/dit_t2i_DeCo.py` survives only as CPython-3.10 bytecode in the checkout
 # (SURVEY.md 8c); its encoder is the logic of `src/models/transformer/dit_t2i_pixnerd.py` (Attention :16-63,

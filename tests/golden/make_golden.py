@@ -390,8 +390,43 @@ def golden_samplers_ext():
     print("[samplers-ext] EulerSamplerJiT / sde_mean / sde / sde_preserve oracle == reference")
 
 
+def golden_trainstep():
+    """BaseTrainer.__call__ + REPATrainer._impl_trainstep of the reference (label dropout, the 90/10 timestep mixture,
+    time shift, x_t / v_t, FM loss) on CPU under fixed seeds, with an analytic recording net: pins oracle.trainstep (same
+    global-generator draw order) and stores t / labels / the loss as a fixture."""
+    def make_net(rec):
+        def net(x_t, t, y):
+            rec.update(x_t=x_t.clone(), t=t.clone(), y=y.clone())
+            return torch.tanh(x_t * (0.5 + t.view(-1, 1, 1, 1))) - 0.1 * y.view(-1, 1, 1, 1).float()
+        return net
+    res = {}
+    for name, B, shape, p, shift, seed in [("a", 6, (3, 16, 24), 0.5, 1.0, 101), ("b", 4, (3, 8, 8), 0.2, 2.5, 202)]:
+        x = torch.tanh(torch.randn((B,) + shape, generator=torch.Generator().manual_seed(seed)))
+        cond = torch.arange(B) % 10
+        unc = torch.full((B,), 10)
+        tr = RefTrainer(scheduler=RefSched(), encoder=torch.nn.Identity(), null_condition_p=p, timeshift=shift)
+        rec, rec_o = {}, {}
+        torch.manual_seed(seed)
+        ref = tr(make_net(rec), None, None, x, cond, unc, metadata=dict(raw_image=x))
+        torch.manual_seed(seed)
+        got = O.trainstep(make_net(rec_o), x, cond, unc, null_condition_p=p, timeshift=shift, freq_loss_weight=0.0)
+        for k in ("x_t", "t", "y"):
+            assert torch.equal(rec[k], rec_o[k]), k
+        assert torch.equal(ref["loss"], got["loss"]) and torch.equal(ref["fm_loss"], got["fm_loss"])
+        print(f"[trainstep {name}] oracle == reference (t, y, x_t bit-equal); loss {float(ref['loss']):.6f}")
+        res[f"{name}_cfg"] = np.array([B, *shape, seed])
+        res[f"{name}_p_shift"] = np.array([p, shift])
+        res[f"{name}_t"] = rec["t"].numpy()
+        res[f"{name}_y"] = rec["y"].numpy()
+        res[f"{name}_xt_sub"] = rec["x_t"][:, :, ::4, ::4].numpy()
+        res[f"{name}_loss"] = np.float64(ref["loss"])
+    np.savez_compressed(os.path.join(OUT, "trainstep.npz"), **res)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["dct", "samplers", "tiny", "t2i", "cfg1", "baseline", "samplers_ext", "pixnerd"]
+    which = sys.argv[1:] or ["dct", "samplers", "tiny", "t2i", "cfg1", "baseline", "samplers_ext", "pixnerd", "trainstep"]
+    if "trainstep" in which:
+        golden_trainstep()
     if "pixnerd" in which:
         golden_pixnerd("pixnerd_d64", O.PixNerdCfg(num_groups=4, hidden_size=256, hidden_size_x=64, nerf_mlpratio=2, num_blocks=4,
                                                    num_cond_blocks=2, num_classes=10), B=2, res=64, seed=51)

@@ -481,6 +481,80 @@ def test_fused_adamw_state_dict_roundtrip_with_torch(dev):
         assert torch.allclose(p, r, rtol=2e-6, atol=2e-7) and torch.equal(p, q)
 
 
+def test_train_input_kernels_vs_reference_expressions(dev):
+    """csrc/train_inputs.cu against the reference's tensor expressions (training_repa_DeCo.py:222-237,
+    base/training.py:14-20) on the same draws: t within 1 ulp-level tolerance, x_t / v_t bit-exact given t, labels exact."""
+    from deco_b200 import GVPScheduler, LinearScheduler, ops
+    g = _g(21)
+    B = 37
+    nt = torch.randn(B, device=dev, generator=g)
+    uu = torch.rand(B, device=dev, generator=g)
+    us = torch.rand(B, device=dev, generator=g)
+    us[:4] = torch.tensor([0.9, 0.90001, 0.0, 1.0], device=dev)            # the <= 0.9 boundary
+    for shift in (1.0, 2.5):
+        t, coef = ops.train_timesteps(nt, uu, us, shift, True)
+        ref = O.time_shift(torch.where(us <= 0.9, torch.sigmoid(nt), uu), shift)
+        assert torch.allclose(t, ref, rtol=3e-7, atol=1e-7), float((t - ref).abs().max())
+        assert torch.equal(coef[:, 0], t) and torch.equal(coef[:, 1], 1 - t)
+        assert float((coef[:, 2] - 1).abs().max()) == 0 and float((coef[:, 3] + 1).abs().max()) == 0
+        t2, c2 = ops.train_timesteps(nt, uu, us, shift, False)
+        assert c2 is None and torch.equal(t2, t)
+    x = torch.tanh(torch.randn(B, 3, 24, 40, device=dev, generator=g))
+    eps = torch.randn(x.shape, device=dev, generator=g)
+    for sch in (LinearScheduler(), GVPScheduler()):
+        coef = torch.stack([f(t).reshape(-1) for f in (sch.alpha, sch.sigma, sch.dalpha, sch.dsigma)], 1).contiguous()
+        x_t, v_t = ops.flow_pair(x, eps, coef)
+        assert torch.equal(x_t, sch.alpha(t) * x + eps * sch.sigma(t))
+        assert torch.equal(v_t, sch.dalpha(t) * x + sch.dsigma(t) * eps)
+    cond = torch.arange(B, device=dev) % 10
+    unc = torch.full((B,), 10, device=dev)
+    u = torch.rand(B, device=dev, generator=g)
+    got = ops.label_dropout(cond, unc, u, 0.3)
+    mask = (u < 0.3).to(cond.dtype)
+    assert torch.equal(got, cond * (1 - mask) + unc * mask)
+    with pytest.raises(Exception):
+        ops.flow_pair(x[:, :, :, :3].contiguous(), eps[:, :, :, :3].contiguous(), coef)     # per-image size % 4 != 0
+
+
+@pytest.mark.parametrize("flw", [0.0, 1.0])
+def test_impl_trainstep_vs_oracle_under_fixed_generator(dev, flw):
+    """REPATrainer.__call__ (label dropout -> t mixture -> x_t / v_t -> denoiser -> loss) against the oracle restatement
+    of base/training.py:25-28 + training_repa_DeCo.py:216-288 (pinned to the reference by tests/golden/trainstep.npz) under
+    the same CUDA generator seed: same labels, same t, same x_t handed to the net, loss within the forward tolerance.
+    flw = 0 is the fork's objective (fm only, two dict keys), flw = 1 adds the block-DCT term."""
+    from deco_b200 import LinearScheduler, REPATrainer
+    cfg = O.DenoiserCfg(num_groups=2, hidden_size=144, num_blocks=4, num_cond_blocks=2, num_classes=10)
+    m, P = build_module(cfg, dev)
+    Pd = {k: v.to(dev) for k, v in P.items()}
+    B = 6
+    x = torch.tanh(torch.randn(B, 3, 64, 64, device=dev, generator=_g(31)))
+    cond = torch.arange(B, device=dev) % 10
+    unc = torch.full((B,), 10, device=dev)
+    tr = REPATrainer(scheduler=LinearScheduler(), null_condition_p=0.5, timeshift=1.7, freq_loss_weight=flw).to(dev)
+    seen = {}
+
+    def rec_net(x_t, t, y):
+        seen.update(x_t=x_t.clone(), t=t.clone(), y=y.clone())
+        return m(x_t, t, y)
+    torch.manual_seed(99)
+    with torch.no_grad():
+        d = tr(rec_net, None, None, x, cond, unc)
+    seen_o = {}
+
+    def onet(x_t, t, y):
+        seen_o.update(x_t=x_t.clone(), t=t.clone(), y=y.clone())
+        return O.denoiser_forward(Pd, cfg, x_t, t, y)
+    torch.manual_seed(99)
+    do = O.trainstep(onet, x, cond, unc, null_condition_p=0.5, timeshift=1.7, freq_loss_weight=flw)
+    assert torch.equal(seen["y"], seen_o["y"]) and 0 < int((seen["y"] == 10).sum()) < B
+    assert torch.allclose(seen["t"], seen_o["t"], rtol=3e-7, atol=1e-7)
+    assert rel_l2(seen["x_t"], seen_o["x_t"]) < 1e-6
+    assert set(d) == ({"fm_loss", "loss"} if flw == 0 else {"fm_loss", "fm_loss_freq", "loss"})
+    for k in d:
+        assert abs(float(d[k]) - float(do[k])) <= 2e-2 * abs(float(do[k])), (k, float(d[k]), float(do[k]))
+    print(f"trainstep flw={flw}: loss {float(d['loss']):.6f} vs oracle {float(do['loss']):.6f}")
+
+
 def test_training_loop_with_fused_optimizer_reduces_loss(dev):
     """forward + backward + FusedAdamWEMA for a few steps on one fixed batch: the weight caches follow the parameters and
     the loss goes down."""

@@ -170,3 +170,25 @@ def test_pixnerd_forward_matches_reference_fixture():
     sh = O.pixnerd_param_shapes(big)
     assert sh["blocks.22.param_generator1.0.weight"] == (16384, 1024) and "blocks.21.attn.qkv.weight" in sh
     assert "blocks.22.attn.qkv.weight" not in sh and sh["final_layer.linear.weight"] == (3, 64)
+
+
+def test_trainstep_oracle_vs_reference_fixture():
+    """oracle.trainstep (label dropout, 90/10 timestep mixture, time shift, x_t / v_t, FM loss) reproduces what the
+    reference's BaseTrainer.__call__ + REPATrainer._impl_trainstep drew and computed under the same CPU seeds
+    (tests/golden/make_golden.py::golden_trainstep)."""
+    g = load_golden("trainstep.npz")
+    for name in ("a", "b"):
+        B, c, h, w, seed = (int(v) for v in g[f"{name}_cfg"])
+        p, shift = (float(v) for v in g[f"{name}_p_shift"])
+        x = torch.tanh(torch.randn((B, c, h, w), generator=torch.Generator().manual_seed(seed)))
+        cond, unc = torch.arange(B) % 10, torch.full((B,), 10)
+        rec = {}
+
+        def net(x_t, t, y):
+            rec.update(x_t=x_t, t=t, y=y)
+            return torch.tanh(x_t * (0.5 + t.view(-1, 1, 1, 1))) - 0.1 * y.view(-1, 1, 1, 1).float()
+        torch.manual_seed(seed)
+        d = O.trainstep(net, x, cond, unc, null_condition_p=p, timeshift=shift, freq_loss_weight=0.0)
+        assert np.array_equal(rec["t"].numpy(), g[f"{name}_t"]) and np.array_equal(rec["y"].numpy(), g[f"{name}_y"])
+        assert np.array_equal(rec["x_t"][:, :, ::4, ::4].numpy(), g[f"{name}_xt_sub"])
+        assert abs(float(d["loss"]) - float(g[f"{name}_loss"])) <= 1e-7 * abs(float(g[f"{name}_loss"]))
