@@ -4,6 +4,10 @@ Mirrors (reference paths):
   src/utils/model_loader.py:10-28          ModelLoader.load: copy `ema_denoiser.*` / `denoiser.*` entries of a Lightning
                                            checkpoint's `state_dict` into the denoiser by parameter name
   app.py:56-63                             load_model (always the EMA weights)
+  src/lightning_model.py:322-368           LightningModel.state_dict / load_state_dict: checkpoint keys are
+                                           `denoiser.*`, `ema_denoiser.*`, `diffusion_trainer.*` (the trainer contributes
+                                           nothing, training_repa_DeCo.py:290-291); `_orig_mod.` (torch.compile) and
+                                           `.module.` (DDP) fragments are stripped from incoming keys
   src/callbacks/save_images.py:31-64       SaveImagesHook: NHWC uint8 samples -> per-image files on a thread pool and/or
                                            one `output.npz` (`arr_0`) for the ADM FID suite
   src/data/dataset/randn.py:34-36          save_fn: `{target_dir}/{filename}.png`
@@ -50,6 +54,66 @@ def load_prefixed_state_dict(module: torch.nn.Module, state_dict: Dict[str, torc
             logger.warning("Failed to copy %s to denoiser weight", prefix + k)
             failed.append(k)
     return failed
+
+
+def clean_checkpoint_keys(state_dict: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """src/lightning_model.py:322-331 and :352-368: checkpoints written while the denoiser was wrapped by torch.compile
+    (`denoiser._orig_mod.blocks...`) or DDP (`denoiser.module.blocks...`) load into the bare modules."""
+    return {k.replace("_orig_mod.", "").replace(".module.", "."): v for k, v in state_dict.items()}
+
+
+def lightning_state_dict(denoiser: torch.nn.Module, ema_denoiser: torch.nn.Module,
+                         diffusion_trainer: Optional[torch.nn.Module] = None) -> Dict[str, torch.Tensor]:
+    """The `state_dict` entry of a reference checkpoint (src/lightning_model.py:333-350): `denoiser.` + `ema_denoiser.` +
+    `diffusion_trainer.` prefixed entries, in that order."""
+    out: Dict[str, torch.Tensor] = {}
+    for prefix, mod in (("denoiser.", denoiser), ("ema_denoiser.", ema_denoiser)):
+        for k, v in mod.state_dict().items():
+            out[prefix + k] = v
+    if diffusion_trainer is not None:
+        sd = diffusion_trainer.state_dict()          # REPATrainer: None (its buffers are rebuilt from the config)
+        for k, v in (sd or {}).items():
+            out["diffusion_trainer." + k] = v
+    return out
+
+
+def save_checkpoint(path: str, denoiser, ema_denoiser, diffusion_trainer=None, optimizer=None, global_step: int = 0,
+                    epoch: int = 0, ema_decay: Optional[float] = None, extra: Optional[Dict] = None) -> str:
+    """Write a checkpoint in the layout Lightning gives the reference's LightningModel: `state_dict` (keys as above, CPU
+    tensors), `optimizer_states` (torch.optim.AdamW layout), `global_step`, `epoch` and the SimpleEMA callback state
+    (src/callbacks/simple_ema.py:51-55).  `ModelLoader` / `app.py:56-63` read `state_dict` only."""
+    sd = {k: v.detach().to("cpu", copy=True) for k, v in lightning_state_dict(denoiser, ema_denoiser, diffusion_trainer).items()}
+    ckpt = dict(state_dict=sd, global_step=int(global_step), epoch=int(epoch))
+    if optimizer is not None:
+        osd = optimizer.state_dict()
+        osd["state"] = {i: {k: (v.detach().to("cpu", copy=True) if torch.is_tensor(v) else v) for k, v in st.items()}
+                        for i, st in osd["state"].items()}
+        ckpt["optimizer_states"] = [osd]
+    if ema_decay is not None:
+        ckpt["callbacks"] = {"SimpleEMA": dict(decay=float(ema_decay), every_n_steps=1)}
+    if extra:
+        ckpt.update(extra)
+    tmp = path + ".tmp"
+    torch.save(ckpt, tmp)
+    os.replace(tmp, path)          # never leave a half-written checkpoint under the final name
+    return path
+
+
+def load_checkpoint(path_or_dict, denoiser, ema_denoiser=None, optimizer=None, strict: bool = True) -> Dict:
+    """Inverse of save_checkpoint; also accepts the reference's own checkpoints (keys cleaned as in
+    src/lightning_model.py:322-368).  Returns the checkpoint dict (for `global_step`, `epoch`, callbacks)."""
+    ckpt = path_or_dict if isinstance(path_or_dict, dict) else torch.load(path_or_dict, map_location="cpu")
+    sd = clean_checkpoint_keys(ckpt["state_dict"])
+    for prefix, mod in (("denoiser.", denoiser), ("ema_denoiser.", ema_denoiser)):
+        if mod is None:
+            continue
+        sub = {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+        if not sub and prefix == "ema_denoiser.":
+            sub = {k[len("denoiser."):]: v for k, v in sd.items() if k.startswith("denoiser.")}   # no EMA stored yet
+        mod.load_state_dict(sub, strict=strict)
+    if optimizer is not None and ckpt.get("optimizer_states"):
+        optimizer.load_state_dict(ckpt["optimizer_states"][0])
+    return ckpt
 
 
 def encode_png(img: np.ndarray) -> bytes:

@@ -9,6 +9,18 @@
 
 One process per GPU; rank r owns dataset indices r, r + W, ... (DistributedSampler(shuffle=False),
 src/lightning_data.py:142-144); no collective inside the sampling loop.
+
+`TrainingPipeline` is the same for the ORIGINAL `LightningModel.training_step` (pyc source lines 105-113):
+
+    x, y, metadata = batch
+    x = vae.encode(x)                                   # PixelAE: identity for scale 1, shift 0
+    condition, uncondition = conditioner(y, metadata)
+    loss = diffusion_trainer(denoiser, ema_denoiser, diffusion_sampler, x, condition, uncondition, metadata)
+    loss["loss"].backward() -> [DDP gradient average] -> AdamW step -> SimpleEMA.ema_step
+
+plus what Lightning does around it (configure_optimizers over the denoiser's trainable parameters, src/lightning_model.py:
+163-177; `ema_denoiser = deepcopy(denoiser)` kept in fp32 and excluded from gradients, :48,:85-92; checkpoints in the
+`denoiser. / ema_denoiser. / diffusion_trainer.` layout, :333-350).
 """
 from __future__ import annotations
 
@@ -18,7 +30,7 @@ import torch
 
 from . import config, distributed
 from .data import ClassLabelRandomNDataset, rank_indices
-from .io import ImageSink, ModelLoader
+from .io import ImageSink, ModelLoader, load_checkpoint, save_checkpoint
 
 
 class SamplingPipeline:
@@ -63,3 +75,77 @@ class SamplingPipeline:
             if sink is not None:
                 sink.process_batch(u8, md, gathered_u8=gathered, is_global_zero=(rank == 0))
             yield gathered, md
+
+
+class TrainingPipeline:
+    """One optimisation step of the class-conditional model without Lightning (see the module docstring).  AdamW and the
+    EMA update are ONE fused kernel (deco_b200.optim.FusedAdamWEMA = torch.optim.AdamW + SimpleEMA.ema_step); with
+    world_size > 1 gradients are averaged like DDP does (deco_b200.distributed.all_reduce_gradients)."""
+
+    def __init__(self, denoiser, diffusion_trainer, diffusion_sampler=None, conditioner=None, vae=None, lr: float = 1e-4,
+                 betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0, ema_decay: float = 0.9999,
+                 device="cuda", world_size: int = 1):
+        import copy
+        from .optim import FusedAdamWEMA
+        self.device = torch.device(device)
+        self.denoiser = ModelLoader().load(denoiser).to(self.device).train()
+        self.ema_denoiser = copy.deepcopy(self.denoiser).to(torch.float32).eval()      # lightning_model.py:48, :193-203
+        for p in self.ema_denoiser.parameters():
+            p.requires_grad_(False)                                                     # no_grad(ema_denoiser), :91
+        self.diffusion_trainer = diffusion_trainer.to(self.device)
+        self.diffusion_sampler = diffusion_sampler
+        self.conditioner = conditioner
+        self.vae = vae
+        self.world_size = world_size
+        self.ema_decay = ema_decay
+        self.params = [p for p in self.denoiser.parameters() if p.requires_grad]       # filter_nograd_tensors, :164
+        pairs = dict(self.ema_denoiser.named_parameters())
+        ema = [pairs[n] for n, p in self.denoiser.named_parameters() if p.requires_grad]
+        self.optimizer = FusedAdamWEMA(self.params, ema, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay,
+                                       ema_decay=ema_decay)
+        self.global_step = 0
+
+    @classmethod
+    def from_yaml(cls, yaml_path: str, device="cuda", **kw) -> "TrainingPipeline":
+        parts = config.load_model_section(yaml_path, parts=("vae", "denoiser", "conditioner", "diffusion_trainer",
+                                                            "diffusion_sampler"))
+        return cls(parts["denoiser"], parts["diffusion_trainer"], parts.get("diffusion_sampler"), parts.get("conditioner"),
+                   parts.get("vae"), device=device, **kw)
+
+    def training_step(self, batch) -> Dict[str, torch.Tensor]:
+        """(images [B,C,H,W] in [-1, 1], labels, metadata) -> the trainer's loss dict (detached); parameters, EMA and
+        optimizer state are updated in place."""
+        x, y, metadata = batch
+        x = x.to(self.device, non_blocking=True)
+        if self.vae is not None:
+            with torch.no_grad():
+                x = self.vae.encode(x)
+        if self.conditioner is not None:
+            condition, uncondition = self.conditioner(y, metadata, device=self.device)
+        else:
+            condition, uncondition = y
+        self.optimizer.zero_grad(set_to_none=True)
+        loss = self.diffusion_trainer(self.denoiser, self.ema_denoiser, self.diffusion_sampler, x, condition, uncondition,
+                                      metadata)
+        loss["loss"].backward()
+        if self.world_size > 1:
+            distributed.all_reduce_gradients(self.params, self.world_size)
+        self.optimizer.step()
+        self.global_step += 1
+        return {k: v.detach() for k, v in loss.items()}
+
+    # ---------------------------------------------------------------------------------------- checkpoints
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        from .io import lightning_state_dict
+        return lightning_state_dict(self.denoiser, self.ema_denoiser, self.diffusion_trainer)
+
+    def save_checkpoint(self, path: str) -> str:
+        return save_checkpoint(path, self.denoiser, self.ema_denoiser, self.diffusion_trainer, self.optimizer,
+                               global_step=self.global_step, ema_decay=self.ema_decay)
+
+    def load_checkpoint(self, path_or_dict, strict: bool = True) -> None:
+        ckpt = load_checkpoint(path_or_dict, self.denoiser, self.ema_denoiser, self.optimizer, strict=strict)
+        self.global_step = int(ckpt.get("global_step", 0))
+        cb = (ckpt.get("callbacks") or {}).get("SimpleEMA")
+        if cb:
+            self.ema_decay = self.optimizer.ema_decay = float(cb["decay"])

@@ -530,3 +530,58 @@ def test_baseline_yaml_wiring_and_checkpoint_contract(tmp_path):
     assert float(m.final_layer.linear.weight.abs().max()) == 0.0 and float(m.final_layer.adaLN_modulation[0].weight.abs().max()) == 0.0
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m.eval()(torch.zeros(1, 3, 32, 32), torch.zeros(1), torch.zeros(1, dtype=torch.long))
+
+
+def test_checkpoint_layout_and_prefix_cleaning(tmp_path):
+    """src/lightning_model.py:322-368: checkpoints hold `denoiser.*` then `ema_denoiser.*` (the trainer contributes nothing,
+    training_repa_DeCo.py:290-291); keys written under torch.compile (`_orig_mod.`) or DDP (`.module.`) load into the bare
+    modules; the optimizer state travels in torch.optim.AdamW's layout; `ModelLoader` reads the same file."""
+    import copy
+    from deco_b200 import LinearScheduler, PixNerDiT, REPATrainer
+    from deco_b200.io import ModelLoader, clean_checkpoint_keys, lightning_state_dict, load_checkpoint, save_checkpoint
+    kw = dict(in_channels=3, num_groups=2, hidden_size=64, hidden_size_x=32, num_blocks=3, num_cond_blocks=1, patch_size=16,
+              num_classes=10)
+    torch.manual_seed(0)
+    net = PixNerDiT(**kw)
+    ema = copy.deepcopy(net)
+    with torch.no_grad():
+        for p in ema.parameters():
+            p.add_(0.25)
+    tr = REPATrainer(scheduler=LinearScheduler())
+    sd = lightning_state_dict(net, ema, tr)
+    names = list(net.state_dict())
+    assert list(sd) == ["denoiser." + n for n in names] + ["ema_denoiser." + n for n in names]
+    assert not any(k.startswith("diffusion_trainer.") for k in sd)
+
+    class FakeOpt:      # torch.optim.AdamW layout, as FusedAdamWEMA.state_dict() (GPU) produces it
+        def __init__(self):
+            self.loaded = None
+
+        def state_dict(self):
+            return dict(state={0: dict(step=torch.tensor(3.0), exp_avg=torch.ones(2), exp_avg_sq=torch.ones(2))},
+                        param_groups=[dict(lr=1e-4, params=[0])])
+
+        def load_state_dict(self, s):
+            self.loaded = s
+    path = save_checkpoint(str(tmp_path / "last.ckpt"), net, ema, tr, FakeOpt(), global_step=7, ema_decay=0.999)
+    ck = torch.load(path, map_location="cpu")
+    assert ck["global_step"] == 7 and ck["callbacks"]["SimpleEMA"] == dict(decay=0.999, every_n_steps=1)
+    assert list(ck["state_dict"]) == list(sd) and float(ck["optimizer_states"][0]["state"][0]["step"]) == 3.0
+    # the reference's own writers: torch.compile'd denoiser under DDP
+    dirty = {}
+    for k, v in ck["state_dict"].items():
+        head, rest = k.split(".", 1)
+        dirty[f"{head}.module._orig_mod.{rest}" if head == "denoiser" else f"{head}._orig_mod.{rest}"] = v
+    assert list(clean_checkpoint_keys(dirty)) == list(sd)
+    net2, ema2, opt2 = PixNerDiT(**kw), PixNerDiT(**kw), FakeOpt()
+    out = load_checkpoint(dict(ck, state_dict=dirty), net2, ema2, opt2)
+    assert out["global_step"] == 7 and opt2.loaded is not None
+    for a, b in ((net, net2), (ema, ema2)):
+        for (n1, p1), (n2, p2) in zip(a.state_dict().items(), b.state_dict().items()):
+            assert n1 == n2 and torch.equal(p1, p2)
+    # the sampling side reads the same file (src/utils/model_loader.py:14-27; app.py:56-63 always takes the EMA weights)
+    net3 = PixNerDiT(weight_path=path, load_ema=True, **kw)
+    ModelLoader().load(net3)
+    assert torch.equal(net3.blocks[0].attn.qkv.weight, ema.blocks[0].attn.qkv.weight)
+    with pytest.raises(RuntimeError):
+        load_checkpoint(dict(state_dict={"denoiser.nope": torch.zeros(1)}), PixNerDiT(**kw))
