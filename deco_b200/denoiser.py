@@ -24,6 +24,9 @@ from . import ops
 
 bf16 = torch.bfloat16
 COMPOSITE_SHIFT = os.environ.get("DECO_B200_COMPOSITE_SHIFT", "1") != "0"
+# pixel decoder: "tc" = tcgen05 kernel (csrc/decoder_tc.cu), "legacy" = register-resident mma.sync kernel (csrc/decoder.cu,
+# kept for A/B measurements and as the forward of the training path, whose backward consumes the pre-activation ycond)
+DECODER = os.environ.get("DECO_B200_DECODER", "tc")
 
 
 # ------------------------------------------------------------------------------------------------ parameter holders
@@ -216,6 +219,78 @@ def pack_decoder(embed_linear: nn.Linear, dn: "_PixelDecoder", C: int, pos_table
     from . import _lib
     assert blob.numel() == _lib.load().deco_decoder_blob_bytes(R), (blob.numel(), R)
     return blob, postab.contiguous()
+
+
+def _sw32_tile(mat: torch.Tensor) -> torch.Tensor:
+    """bf16 [rows, cols] (cols a multiple of 16, rows of 8) -> the 32-byte-swizzled K-major operand image csrc/decoder_tc.cu
+    keeps in shared memory (csrc/tcgen05.cuh::sw32_offset: [16-column chunk][row][32 B], 16-byte halves swapped in rows
+    4..7 of every 8-row group); returned as a flat bf16 tensor of rows * cols elements."""
+    rows, cols = mat.shape
+    assert cols % 16 == 0 and rows % 8 == 0
+    r = torch.arange(rows, device=mat.device).view(-1, 1)
+    c = torch.arange(cols, device=mat.device).view(1, -1)
+    off = (c >> 4) * rows * 32 + r * 32 + ((((c >> 3) & 1) ^ ((r >> 2) & 1)) << 4) + (c & 7) * 2
+    out = torch.zeros(rows * cols, dtype=bf16, device=mat.device)
+    out[(off // 2).reshape(-1)] = mat.to(bf16).reshape(-1)
+    return out
+
+
+def _bias_tile(bias: torch.Tensor, rows: int) -> torch.Tensor:
+    """fp32 [n <= rows] -> B operand [rows x 16] of the bias MMA: column 0 = bf16(bias), column 1 = bf16(bias - hi)."""
+    t = torch.zeros(rows, 16, dtype=torch.float32, device=bias.device)
+    hi = bias.to(bf16).float()
+    t[: bias.numel(), 0] = hi
+    t[: bias.numel(), 1] = (bias - hi).to(bf16).float()
+    return _sw32_tile(t.to(bf16))
+
+
+@torch.no_grad()
+def pack_decoder_tc(embed_linear: nn.Linear, dn: "_PixelDecoder", C: int, pos_table: torch.Tensor, device) -> torch.Tensor:
+    """Weight image of the tcgen05 pixel decoder (csrc/decoder_tc.cu; the algebra is spelled out in its header): per res
+    block the scale|gate rows of adaLN, W0 diag(g) / 2, the composite (W0 diag(b) Wscale + W0 Wshift) / 2, W2 and the
+    (hi, lo) bias tiles; the final linear; then the fp32 tables T' = Win (Wpos table + bx) + bin and W' = Win Wrgb that
+    replace NerfEmbedder + input_proj.  Matrices are the bf16-rounded weights the reference multiplies with under autocast;
+    composites are formed in fp32 and rounded once."""
+    def rb(t):
+        return t.detach().to(device=device, dtype=torch.float32).to(bf16).float()
+
+    def fv(t):
+        return t.detach().to(device=device, dtype=torch.float32)
+
+    H = dn.input_proj.weight.shape[0]
+    assert H == 32 and C == 3
+    ones = torch.zeros(128, 16, dtype=bf16, device=device)
+    ones[:, :2] = 1
+    parts = [_sw32_tile(ones)]
+    for blk in dn.res_blocks:
+        wa, ba = rb(blk.adaLN_modulation[1].weight), fv(blk.adaLN_modulation[1].bias)       # rows: shift | scale | gate
+        wsh, wsc, wgt = wa[:H], wa[H:2 * H], wa[2 * H:]
+        bsh, bsc, bgt = ba[:H], ba[H:2 * H], ba[2 * H:]
+        gm, bt = fv(blk.in_ln.weight), fv(blk.in_ln.bias)
+        w0, b0 = rb(blk.mlp[0].weight), fv(blk.mlp[0].bias)
+        w2, b2 = rb(blk.mlp[2].weight), fv(blk.mlp[2].bias)
+        w0g = 0.5 * w0 * gm.view(1, -1)
+        c0 = 0.5 * ((w0 * bt.view(1, -1)) @ wsc + w0 @ wsh)
+        bias0 = 0.5 * (b0 + w0 @ (bt * (1.0 + bsc)) + w0 @ bsh)
+        parts += [_sw32_tile(torch.cat([wsc, wgt], 0)), _sw32_tile(w0g), _sw32_tile(c0), _sw32_tile(w2),
+                  _bias_tile(torch.cat([1.0 + bsc, bgt]), 64), _bias_tile(bias0, 32), _bias_tile(b2, 32)]
+    wf = torch.zeros(16, H, device=device)
+    wf[:C] = rb(dn.final_layer.linear.weight)
+    parts += [_sw32_tile(wf), _bias_tile(fv(dn.final_layer.linear.bias), 16),
+              torch.zeros(256, dtype=bf16, device=device)]                                   # pad the final section to 2048 B
+    wx = rb(embed_linear.weight)                                                             # [32, C + 64]
+    win, b_in = rb(dn.input_proj.weight), fv(dn.input_proj.bias)
+    tab = pos_table.to(device=device, dtype=torch.float32).to(bf16).float()
+    x_pos = tab @ wx[:, C:].t() + fv(embed_linear.bias)                                      # [256, 32]
+    tprime = torch.zeros(256, 36, device=device)
+    tprime[:, :H] = x_pos @ win.t() + b_in
+    wrgb = torch.zeros(H, 4, device=device)
+    wrgb[:, :C] = win @ wx[:, :C]
+    blob = torch.cat([torch.cat(parts).view(torch.uint8), tprime.reshape(-1).view(torch.uint8),
+                      wrgb.reshape(-1).view(torch.uint8)]).contiguous()
+    from . import _lib
+    assert blob.numel() == _lib.load().deco_decoder_tc_blob_bytes(len(dn.res_blocks)), blob.numel()
+    return blob
 
 
 def interleave_w13(w1: torch.Tensor, w3: torch.Tensor, Fp: int) -> torch.Tensor:
@@ -417,6 +492,8 @@ class PixNerDiT(nn.Module):
         P["blocks"], P["ffn_pad"] = prepare_dit_blocks(self.blocks, H, device)
         P["wcond"], P["bcond"] = W(self.dec_net.cond_embed.weight), Fv(self.dec_net.cond_embed.bias)
         P["blob"], P["postab"] = self._pack_decoder(device)
+        P["blob_tc"] = pack_decoder_tc(self.x_embedder.embedder[0], self.dec_net, self.in_channels,
+                                       self.precompute_pos[("nerf_tab", str(device))], device)
         self._prep, self._prep_key = P, key
         return P
 
@@ -512,10 +589,46 @@ class PixNerDiT(nn.Module):
                 s2 = self._encode(P, xp, t.reshape(-1).to(torch.float32), y.reshape(-1), B, L, pos, Ww // p)
             else:
                 s2 = s.detach().reshape(B * L, H).to(bf16).contiguous()
-            ycond = ops.gemm(s2, P["wcond"], P["bcond"], ops.EPI_BIAS)
-            out = ops.pixel_decoder(x32, ycond, P["blob"], P["postab"], p, self.hidden_size_x,
-                                    self.num_blocks - self.num_cond_blocks)
+            out = self._decode(P, x32, s2)
         return out, s2.view(B, L, H)
+
+    def _decode(self, P, x32, s2, out_dtype=bf16):
+        """cond_embed + per-pixel AdaLN-MLP decoder + fold (dit_c2i_DeCo.py:501-509)."""
+        R = self.num_blocks - self.num_cond_blocks
+        if DECODER == "tc":
+            ysilu = ops.gemm(s2, P["wcond"], P["bcond"], ops.EPI_BIAS_SILU)      # silu(cond_embed(s)): the adaLN input
+            return ops.pixel_decoder_tc(x32, ysilu, P["blob_tc"], self.patch_size, self.hidden_size_x, R, out_dtype=out_dtype)
+        ycond = ops.gemm(s2, P["wcond"], P["bcond"], ops.EPI_BIAS)
+        return ops.pixel_decoder(x32, ycond, P["blob"], P["postab"], self.patch_size, self.hidden_size_x, R, out_dtype=out_dtype)
+
+    supports_fused_cfg_step = True
+
+    @torch.no_grad()
+    def cfg_step(self, x, t2, cfg_condition, dev=None, g=1.0, dt=0.0, c0=1.0, c1=0.0, p1=None, x_out=None,
+                 pred_out=None, u8_out=None):
+        """One CFG-batched sampler step with the update fused into the decoder epilogue (north_star (4)): evaluates the
+        rows [uncond || cond] = net(cat[x, x], t2, cfg_condition) (sampling.py:89-97) WITHOUT materialising cat[x, x] or
+        the bf16 network output, and writes x_out = x + dt (c0 pred + c1 p1), pred = u + g (c - u) (guidance.py:3-6,
+        sampling.py:100-104, adam_sampling.py:104-117).  x fp32 [B,C,H,W]; t2 [2B]; cfg_condition [2B]; dev = device
+        vector {g, dt, c0, c1} (graph replays) else the host scalars.  Returns x_out."""
+        if not x.is_cuda:
+            raise RuntimeError("deco_b200.PixNerDiT runs on CUDA (sm_100a) only; there is no CPU fallback")
+        if DECODER != "tc":
+            raise NotImplementedError("the fused sampler step needs the tcgen05 decoder (DECO_B200_DECODER=tc)")
+        B, Cc, Hh, Ww = x.shape
+        p, H = self.patch_size, self.hidden_size
+        L = (Hh // p) * (Ww // p)
+        P = self.prepare(x.device)
+        x32 = x.detach().to(torch.float32).contiguous()
+        pos = self.fetch_pos(Hh // p, Ww // p, x.device)
+        xp = torch.empty((2 * B * L, Cc * p * p), dtype=bf16, device=x.device)
+        ops.patchify(x32, p, out=xp[: B * L])          # both CFG halves see the same image: patchify it into each half
+        ops.patchify(x32, p, out=xp[B * L:])
+        s2 = self._encode(P, xp, t2.reshape(-1).to(torch.float32), cfg_condition.reshape(-1), 2 * B, L, pos, Ww // p)
+        ysilu = ops.gemm(s2, P["wcond"], P["bcond"], ops.EPI_BIAS_SILU)
+        return ops.pixel_decoder_tc_step(x32, ysilu, P["blob_tc"], p, self.hidden_size_x, self.num_blocks - self.num_cond_blocks,
+                                         dev=dev, g=g, dt=dt, c0=c0, c1=c1, p1=p1, x_out=x_out, pred_out=pred_out,
+                                         u8_out=u8_out)
 
     def forward(self, x, t, y, s=None, mask=None):
         """x [B,C,H,W], t [B] in [0,1], y [B] int64 (num_classes = null) -> velocity [B,C,H,W] (bf16, as the

@@ -154,11 +154,13 @@ def gemm_norm_swiglu(a: torch.Tensor, w13: torch.Tensor, out: torch.Tensor, rows
     return out
 
 
-def patchify(x: torch.Tensor, p: int) -> torch.Tensor:
-    _cuda(x)
+def patchify(x: torch.Tensor, p: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _cuda(x, out)
     assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4
     B, Cc, H, W = x.shape
-    out = torch.empty((B * (H // p) * (W // p), Cc * p * p), dtype=bf16, device=x.device)
+    if out is None:
+        out = torch.empty((B * (H // p) * (W // p), Cc * p * p), dtype=bf16, device=x.device)
+    assert out.dtype == bf16 and out.is_contiguous() and out.shape == (B * (H // p) * (W // p), Cc * p * p)
     call("deco_patchify", ptr(x), ptr(out), B, Cc, H, W, p, _st(x))
     return out
 
@@ -294,6 +296,44 @@ def pixel_decoder(x: torch.Tensor, ycond: torch.Tensor, blob: torch.Tensor, post
     call("deco_pixel_decoder", ptr(x), ptr(ycond), ptr(blob), ptr(postab), ptr(out), int(out_dtype == bf16),
          B, H, W, patch, hidden_x, num_res_blocks, _st(x))
     return out
+
+
+def pixel_decoder_tc(x: torch.Tensor, ysilu: torch.Tensor, blob: torch.Tensor, patch: int, hidden_x: int,
+                     num_res_blocks: int, out_dtype=bf16) -> torch.Tensor:
+    """tcgen05 pixel decoder (csrc/decoder_tc.cu): x fp32 [rows,3,H,W], ysilu = silu(cond_embed(s)) bf16 [rows*L, p*p*32]."""
+    _cuda(x, ysilu, blob)
+    assert x.dtype == torch.float32 and x.is_contiguous() and ysilu.dtype == bf16 and ysilu.is_contiguous()
+    B, Cc, H, W = x.shape
+    assert Cc == 3, "pixel decoder is built for 3 image channels"
+    assert ysilu.shape == (B * (H // patch) * (W // patch), patch * patch * hidden_x)
+    assert blob.numel() * blob.element_size() == _lib.load().deco_decoder_tc_blob_bytes(num_res_blocks)
+    out = torch.empty((B, Cc, H, W), dtype=out_dtype, device=x.device)
+    call("deco_pixel_decoder_tc", ptr(x), ptr(ysilu), ptr(blob), ptr(out), int(out_dtype == bf16), B, H, W, patch, hidden_x,
+         num_res_blocks, 0, None, 0.0, 0.0, 0.0, 0.0, None, None, None, None, _st(x))
+    return out
+
+
+def pixel_decoder_tc_step(x: torch.Tensor, ysilu: torch.Tensor, blob: torch.Tensor, patch: int, hidden_x: int,
+                          num_res_blocks: int, dev: Optional[torch.Tensor] = None, g: float = 1.0, dt: float = 0.0,
+                          c0: float = 1.0, c1: float = 0.0, p1: Optional[torch.Tensor] = None,
+                          x_out: Optional[torch.Tensor] = None, pred_out: Optional[torch.Tensor] = None,
+                          u8_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Decoder of both CFG rows [uncond || cond] of the image state x [B,3,H,W] + guidance + multistep update in one kernel:
+    x_out = x + dt (c0 pred + c1 p1), pred = u + g (c - u).  dev = device {g, dt, c0, c1, ...} for graph replays."""
+    _cuda(x, ysilu, blob, dev, p1, x_out, pred_out, u8_out)
+    assert x.dtype == torch.float32 and x.is_contiguous() and ysilu.dtype == bf16 and ysilu.is_contiguous()
+    B, Cc, H, W = x.shape
+    assert Cc == 3 and ysilu.shape == (2 * B * (H // patch) * (W // patch), patch * patch * hidden_x)
+    assert blob.numel() * blob.element_size() == _lib.load().deco_decoder_tc_blob_bytes(num_res_blocks)
+    if x_out is None:
+        x_out = torch.empty_like(x)
+    for t_, dt_ in ((p1, torch.float32), (x_out, torch.float32), (pred_out, torch.float32), (u8_out, torch.uint8)):
+        assert t_ is None or (t_.dtype == dt_ and t_.is_contiguous() and t_.shape == x.shape)
+    if dev is not None:
+        assert dev.dtype == torch.float32 and dev.numel() >= 4 and dev.is_contiguous()
+    call("deco_pixel_decoder_tc", ptr(x), ptr(ysilu), ptr(blob), None, 0, 2 * B, H, W, patch, hidden_x, num_res_blocks, 1,
+         ptr(dev), float(g), float(dt), float(c0), float(c1), ptr(p1), ptr(x_out), ptr(pred_out), ptr(u8_out), _st(x))
+    return x_out
 
 
 def cfg_step(x: torch.Tensor, net_out: torch.Tensor, g: float, dt: float, c0: float = 1.0,

@@ -211,6 +211,11 @@ class GraphedStepper:
 
     def _body(self):
         ops.sampler_advance(self.table, self.counter, self.cur, self.t)
+        if not self.xpred and _fused_step_ok(self.net):
+            # decoder epilogue = guidance + update (csrc/decoder_tc.cu): no cat[x, x], no bf16 network output, no step kernel
+            self.net.cfg_step(self.x, self.t, self.cond, dev=self.cur, p1=self.pred, x_out=self.x, pred_out=self.pred,
+                              u8_out=self.u8)
+            return
         out = self.net(torch.cat([self.x, self.x], dim=0), self.t, self.cond)
         if out.dtype not in (torch.bfloat16, torch.float32):
             out = out.float()
@@ -229,6 +234,17 @@ class GraphedStepper:
     def step(self):
         self.graph.replay()
         _lib.launch_count += self.launches_per_step
+
+
+FUSED_STEP = os.environ.get("DECO_B200_FUSED_STEP", "1") != "0"
+
+
+def _fused_step_ok(net) -> bool:
+    """The denoiser can run guidance + update inside its decoder epilogue (PixNerDiT.cfg_step)."""
+    if not FUSED_STEP or not getattr(net, "supports_fused_cfg_step", False) or getattr(net, "training", False):
+        return False
+    from . import denoiser
+    return denoiser.DECODER == "tc"
 
 
 def _net_eval(net, x, t_scalar: float, cfg_condition, batch_size):
@@ -309,13 +325,23 @@ class EulerSampler(BaseSampler):
                 return res
         x_trajs, v_trajs, u8 = ([x] if keep_x else None), ([] if keep_v else None), None
         plain = not self.x_prediction and self._kinds == ("ode_step_fn", "ode_step_fn")
+        fused = plain and not keep_v and _fused_step_ok(net)      # guidance + update inside the decoder epilogue
         for i in range(self.num_steps):
             t_cur, t_next = steps[i], steps[i + 1]
             dt = float(t_next - t_cur)
-            out = _net_eval(net, x, float(t_cur), cfg_condition, B)
             in_window = bool(t_cur > self.guidance_interval_min) and bool(t_cur <= self.guidance_interval_max)
             g = float(self.guidance) if in_window else 1.0
             last = i == self.num_steps - 1
+            if fused:
+                cfg_t = torch.full((2 * B,), float(t_cur), dtype=torch.float32, device=x.device)
+                u = torch.empty(x.shape, dtype=torch.uint8, device=x.device) if (to_uint8 and last) else None
+                x = net.cfg_step(x, cfg_t, cfg_condition, g=g, dt=dt, u8_out=u)
+                if keep_x:
+                    x_trajs.append(x)
+                if u is not None:
+                    u8 = u
+                continue
+            out = _net_eval(net, x, float(t_cur), cfg_condition, B)
             if plain:
                 x, _, v, u = ops.cfg_step(x, out, g, dt, want_v=keep_v, want_u8=(to_uint8 and last))
             else:
@@ -489,8 +515,8 @@ class AdamLMSampler(BaseSampler):
         preds: List[torch.Tensor] = []
         # the reference accumulates t_cur += dt in fp32 on the device (adam_sampling.py:96,118); same sums here
         t_cur = torch.zeros((), dtype=torch.float32)
+        fused = self.order <= 2 and not keep_v and _fused_step_ok(net)
         for i in range(self.num_steps):
-            out = _net_eval(net, x, float(t_cur), cfg_condition, B)
             in_window = bool(t_cur > self.guidance_interval_min) and bool(t_cur < self.guidance_interval_max)
             g = float(self.guidance) if in_window else 1.0
             cs = self.solver_coeffs[i]
@@ -498,6 +524,21 @@ class AdamLMSampler(BaseSampler):
             prev = preds[-(order - 1):] if order > 1 else []
             last = i == self.num_steps - 1
             dt = float(self.timedeltas[i])
+            if fused:       # decoder epilogue = guidance + multistep update (previous prediction read, new one written)
+                cfg_t = torch.full((2 * B,), float(t_cur), dtype=torch.float32, device=x.device)
+                u = torch.empty(x.shape, dtype=torch.uint8, device=x.device) if (to_uint8 and last) else None
+                pred = torch.empty_like(x) if self.order > 1 else None
+                x = net.cfg_step(x, cfg_t, cfg_condition, g=g, dt=dt, c0=float(cs[-1]), c1=float(cs[0]) if order > 1 else 0.0,
+                                 p1=prev[0] if order > 1 else None, pred_out=pred, u8_out=u)
+                if self.order > 1:
+                    preds = [pred]
+                t_cur = t_cur + self.timedeltas[i]
+                if keep_x:
+                    x_trajs.append(x)
+                if u is not None:
+                    u8 = u
+                continue
+            out = _net_eval(net, x, float(t_cur), cfg_condition, B)
             # v = sum_j cs[j] * pred[-order:][j]; the newest prediction (cs[-1]) comes straight from the net output
             x, pred, v, u = ops.cfg_step(x, out, g, dt, c0=cs[-1], prev=tuple(prev), coeffs=tuple(cs[:-1]),
                                          want_pred=(self.order > 1), want_v=keep_v, want_u8=(to_uint8 and last))

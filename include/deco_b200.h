@@ -145,6 +145,21 @@ int deco_attention_fwd(const void* q, long long q_stride,
                        void* out, long long out_stride,
                        int B, int heads, int Lq, int head_dim, float scale, void* stream);
 
+/* Pixel decoder on tcgen05 / TMEM, optionally with the CFG-batched sampler update fused into its epilogue
+ * (csrc/decoder_tc.cu; reference: dit_c2i_DeCo.py:212-248, :313-332, :395-415, :501-509; sampler fusion:
+ * base/guidance.py:3-6, flow_matching/sampling.py:89-104, adam_sampling.py:104-117, autoencoder/base.py:32-34).
+ * ysilu = silu(cond_embed(s)) bf16 [rows * L, p*p*32] (deco_gemm_bf16 with the bias + SiLU epilogue); blob = weight image
+ * of deco_decoder_tc_blob_bytes(R) bytes (deco_b200/denoiser.py::pack_decoder_tc).
+ * pair == 0: out [rows,3,H,W] (bf16 / fp32) = decoder(x [rows,3,H,W] fp32).
+ * pair != 0: rows = 2B stacked [uncond || cond] over ONE image state x [B,3,H,W] fp32:
+ *   pred = u + g (c - u); v = c0 pred + c1 p1; x_out = x + dt v (x_out may be x); optional pred_out (may be p1), u8_out.
+ *   {g, dt, c0, c1} come from dev_scalars (device memory, CUDA-graph replays) when it is non-NULL. */
+int deco_decoder_tc_blob_bytes(int num_res_blocks);
+int deco_pixel_decoder_tc(const float* x, const void* ysilu_bf16, const void* blob, void* out, int out_is_bf16,
+                          int rows, int H, int W, int patch, int hidden_x, int num_res_blocks,
+                          int pair, const float* dev_scalars, float g, float dt, float c0, float c1,
+                          const float* p1, float* x_out, float* pred_out, void* u8_out, void* stream);
+
 /* Training-step inputs (src/diffusion/flow_matching/training_repa_DeCo.py:222-237, src/diffusion/base/training.py:14-20).
  * The random draws stay the caller's (torch's CUDA generator, reference order); these fuse what follows them.
  * deco_train_timesteps: t = time_shift(where(u_select <= 0.9, sigmoid(nt), u_uniform)) (fp32 [B]); with

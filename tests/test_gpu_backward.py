@@ -465,7 +465,8 @@ def test_fused_adamw_state_dict_roundtrip_with_torch(dev):
         for p in ps:
             p.grad = torch.randn(p.shape, device=dev, generator=g)
         opt.step()
-    sd = opt.state_dict()
+    import copy
+    sd = copy.deepcopy(opt.state_dict())     # torch's load_state_dict keeps same-device tensors by reference: no aliasing
     ref = [torch.nn.Parameter(p.detach().clone()) for p in ps]
     topt = torch.optim.AdamW(ref, **kw)
     topt.load_state_dict(sd)

@@ -379,3 +379,79 @@ def test_gemm_norm_swiglu(cuda_dev, M, F_, K, L):
     assert rel_l2(out[:, :F_].float(), ref) < 6e-3
     if Fp > F_:
         assert float(out[:, F_:].float().abs().max()) == 0.0
+
+
+def _decoder_module(cuda_dev, R=3, H=256):
+    from helpers import build_module
+    cfg = O.DenoiserCfg(num_groups=4, hidden_size=H, num_blocks=R + 1, num_cond_blocks=1, num_classes=10)
+    m, P = build_module(cfg, cuda_dev)
+    return cfg, m, {k: v.to(cuda_dev) for k, v in P.items()}
+
+
+@pytest.mark.parametrize("B,res,R", [(1, 16, 3), (3, 48, 3), (2, 64, 1), (8, 256, 3), (5, 128, 6)])
+def test_pixel_decoder_tc_vs_oracle_and_legacy(cuda_dev, B, res, R):
+    """csrc/decoder_tc.cu (tcgen05 / TMEM, folded weights, SiLU via tanh) against the oracle's pixel decoder
+    (dit_c2i_DeCo.py:212-248, :313-332, :395-415) on the same condition s, and against the register-resident mma.sync kernel
+    it replaces.  Sizes: one token (2 tiles), ragged token counts, 1 / 3 / 6 res blocks, 2048 tokens = 28 tiles per CTA (every
+    slot pipelines several tiles, both condition buffers recycle)."""
+    from deco_b200 import ops
+    cfg, m, Pd = _decoder_module(cuda_dev, R)
+    P = m.prepare(cuda_dev)
+    g = torch.Generator().manual_seed(B * 1000 + res)
+    L = (res // 16) ** 2
+    x = torch.randn(B, 3, res, res, generator=g).to(cuda_dev)
+    s = (torch.randn(B * L, cfg.hidden_size, generator=g) * 0.7).to(cuda_dev).to(torch.bfloat16)
+    ref = O.denoiser_forward(Pd, cfg, x, torch.zeros(B, device=cuda_dev), torch.zeros(B, dtype=torch.long, device=cuda_dev),
+                             s=s.float().view(B, L, -1))
+    ysilu = ops.gemm(s, P["wcond"], P["bcond"], ops.EPI_BIAS_SILU)
+    for odt in (torch.float32, torch.bfloat16):
+        got = ops.pixel_decoder_tc(x, ysilu, P["blob_tc"], 16, 32, R, out_dtype=odt)
+        e = rel_l2(got.float(), ref)
+        assert e < 6e-3, (str(odt), e)
+    ycond = ops.gemm(s, P["wcond"], P["bcond"], ops.EPI_BIAS)
+    old = ops.pixel_decoder(x, ycond, P["blob"], P["postab"], 16, 32, R, out_dtype=torch.float32)
+    got = ops.pixel_decoder_tc(x, ysilu, P["blob_tc"], 16, 32, R, out_dtype=torch.float32)
+    print(f"decoder_tc B={B} res={res} R={R}: rel-L2 vs oracle {rel_l2(got, ref):.3e} (legacy kernel {rel_l2(old, ref):.3e}), "
+          f"tc vs legacy {rel_l2(got, old):.3e}")
+    assert rel_l2(got, old) < 8e-3
+    # guard band: nothing outside the output tensor was written
+    big = torch.full((B * 3 * res * res + 512,), 7.0, device=cuda_dev)
+    from deco_b200._lib import call, ptr
+    call("deco_pixel_decoder_tc", ptr(x), ptr(ysilu), ptr(P["blob_tc"]), big[256:].data_ptr(), 0, B, res, res, 16, 32, R, 0,
+         None, 0.0, 0.0, 0.0, 0.0, None, None, None, None, torch.cuda.current_stream().cuda_stream)
+    assert torch.equal(big[256:-256].view(B, 3, res, res), got)
+    assert float((big[:256] - 7).abs().max()) == 0 and float((big[-256:] - 7).abs().max()) == 0
+
+
+@pytest.mark.parametrize("B,res,order2", [(2, 32, False), (3, 64, True), (16, 128, True)])
+def test_pixel_decoder_tc_fused_sampler_step(cuda_dev, B, res, order2):
+    """pair mode of csrc/decoder_tc.cu: decoder of the rows [uncond || cond] + guidance (base/guidance.py:3-6) + the
+    Euler / Adams update (sampling.py:100-104, adam_sampling.py:109-117) + fp2uint8, against the same decoder's fp32 output
+    pushed through the reference formulas; host scalars and the device-table form agree bit for bit; in-place update."""
+    from deco_b200 import ops
+    cfg, m, _ = _decoder_module(cuda_dev, 3)
+    P = m.prepare(cuda_dev)
+    g = torch.Generator().manual_seed(res + B)
+    L = (res // 16) ** 2
+    x = torch.randn(B, 3, res, res, generator=g).to(cuda_dev)
+    s = (torch.randn(2 * B * L, cfg.hidden_size, generator=g) * 0.7).to(cuda_dev).to(torch.bfloat16)
+    ysilu = ops.gemm(s, P["wcond"], P["bcond"], ops.EPI_BIAS_SILU)
+    out = ops.pixel_decoder_tc(torch.cat([x, x]), ysilu, P["blob_tc"], 16, 32, 3, out_dtype=torch.float32)
+    gd, dt, c0, c1 = 3.2, 0.013, (1.5 if order2 else 1.0), (-0.5 if order2 else 0.0)
+    p1 = torch.randn(x.shape, generator=g).to(cuda_dev) if order2 else None
+    u, c = out[:B], out[B:]
+    pred = u + gd * (c - u)
+    v = c0 * pred + (c1 * p1 if order2 else 0)
+    x_ref = x + dt * v
+    pred_o = torch.empty_like(x)
+    u8_o = torch.empty(x.shape, dtype=torch.uint8, device=cuda_dev)
+    xo = ops.pixel_decoder_tc_step(x, ysilu, P["blob_tc"], 16, 32, 3, g=gd, dt=dt, c0=c0, c1=c1, p1=p1, pred_out=pred_o, u8_out=u8_o)
+    assert rel_l2(xo, x_ref) < 2e-6 and rel_l2(pred_o, pred) < 2e-6
+    assert int((u8_o.int() - O.fp2uint8(xo).int()).abs().max()) == 0
+    dev = torch.tensor([gd, dt, c0, c1, 0, 0, 0.5, 0], dtype=torch.float32, device=cuda_dev)
+    x2 = x.clone()
+    p2 = p1.clone() if order2 else None
+    ops.pixel_decoder_tc_step(x2, ysilu, P["blob_tc"], 16, 32, 3, dev=dev, p1=p2, x_out=x2, pred_out=p2)     # in place
+    assert torch.equal(x2, xo)
+    if order2:
+        assert torch.equal(p2, pred_o)
