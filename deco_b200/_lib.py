@@ -9,7 +9,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_C", "libdeco_b200.so")
+LIB_PATH = os.environ.get("DECO_B200_LIB") or os.path.join(_HERE, "_C", "libdeco_b200.so")   # override: instrumented builds
 
 _vp, _ll, _i, _f = C.c_void_p, C.c_longlong, C.c_int, C.c_float
 

@@ -35,11 +35,13 @@
 // per channel for SiLU, one FMA per channel for the gated residual -- ~7 FP32 operations per channel and res block.
 //
 // Pipeline.  Persistent kernel, one CTA per SM, 20 warps: 4 SLOTS of 4 epilogue warps (a slot works on one tile at a time;
-// its 128 TMEM columns hold SC | GT | H | the bf16 A operand), one TMA producer warp (condition tiles, double buffered per
-// slot), one MMA issuer warp.  A tile is 2R + 1 MMA <-> epilogue round trips (R res blocks); the four slots interleave so
-// that one slot's round trip latency (~0.5 us) hides behind the other three slots' arithmetic.  The issuer walks
-// (stage, slot) in a fixed round-robin order and pre-issues whatever no longer depends on the epilogue (next block's
-// scale MMA as soon as the current one has been read, next tile's scale / gate MMAs together with the final layer).
+// its 128 TMEM columns hold SC | GT | H | the bf16 A operand) and one MMA issuer warp PER SLOT, which also fetches the
+// slot's condition tiles by TMA (double buffered, two tiles ahead).  A tile is 2R + 1 MMA <-> epilogue round trips (R res blocks); the four
+// slots interleave so that one slot's round trip latency hides behind the other three slots' arithmetic.  One thread can
+// issue a tcgen05.mma only every ~58 clocks whatever its size (scripts/tmem_bench.cu: N = 32 runs at its 16-clock floor
+// only when four warps issue), hence one issuer per slot; each issuer commits the MMAs the waiting epilogue needs FIRST
+// and then pre-issues whatever no longer depends on the epilogue (next block's scale MMA as soon as the current one has
+// been read, next tile's scale / gate MMAs after the final layer), with descriptors precomputed outside the loop.
 //
 // Sampler fusion (mode "pair"): rows b (uncond) and b + B (cond) of the CFG batch share the image x; a slot runs the two
 // tiles back to back, keeps the first result in 3 registers and applies guidance + the multistep update to the fp32
@@ -52,7 +54,8 @@ namespace dtc {
 
 constexpr int kSlots = 4;
 constexpr int kEpiWarps = 16;
-constexpr int kThreads = (kEpiWarps + 4) * 32;       // + producer, MMA issuer, TMEM allocator, spare
+constexpr int kThreads = (kEpiWarps + kSlots) * 32;  // + one MMA issuer per slot (which also fetches its slot's condition tiles)
+// (20 warps: registers are allocated to warps in groups of four, a 21st warp would cost every thread 16 registers)
 constexpr int kMaxR = 6;
 constexpr int kHx = 32;
 
@@ -116,6 +119,21 @@ __device__ __forceinline__ uint8_t to_u8(float v) {
     return (uint8_t)y;
 }
 
+#ifdef DECO_DTC_TRACE
+// clock stamps of CTA 0 / slot 0: region 0 = epilogue thread 0, region 1 = the slot's MMA issuer (scripts/dtc_trace.py)
+__device__ long long g_dtc_trace[2 * 4096];
+#define DTC_TRACE(region, code)                                                                   \
+    do {                                                                                          \
+        if (blockIdx.x == 0 && trace_on && trace_n < 2047) {                                      \
+            g_dtc_trace[(region) * 4096 + 2 * trace_n] = clock64();                               \
+            g_dtc_trace[(region) * 4096 + 2 * trace_n + 1] = (code);                              \
+            ++trace_n;                                                                            \
+        }                                                                                         \
+    } while (0)
+#else
+#define DTC_TRACE(region, code) do {} while (0)
+#endif
+
 __global__ void __launch_bounds__(kThreads, 1)
 pixel_decoder_tc_kernel(const __grid_constant__ CUtensorMap ymap, const Params P)
 {
@@ -133,29 +151,32 @@ pixel_decoder_tc_kernel(const __grid_constant__ CUtensorMap ymap, const Params P
     auto a_bar = [&](int k) { return bars + 32u + 8u * k; };                    // slot k's A operand / accumulators released
     auto y_full = [&](int k, int b) { return bars + 64u + 8u * (2 * k + b); };
     auto y_empty = [&](int k, int b) { return bars + 128u + 8u * (2 * k + b); };
-    const uint32_t tslot = bars + 192u;
+    auto p_bar = [&](int k) { return bars + 192u + 8u * k; };                   // scale' | gate of a tile's first block ready
+    const uint32_t tslot = bars + 224u;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nstage = 2 * R + 1;                               // epilogue -> issuer hand-overs per tile
 
-    // work: items (token, half) dealt to CTAs round-robin, then to the CTA's slots round-robin; pair mode: two tiles per item
-    const long long item_tokens = P.pair ? P.tokens_half : P.tokens;
-    const long long nitems = item_tokens * 2;
-    const long long first = blockIdx.x, step = gridDim.x;
-    const long long nlocal = first < nitems ? (nitems - first + step - 1) / step : 0;
+    // work: items (token, half) dealt to CTAs round-robin, then to the CTA's slots round-robin; pair mode: two tiles per item.
+    // All of it is 32-bit arithmetic (tokens * 256 < 2^31 is checked on the host): 64-bit divisions cost hundreds of clocks.
+    const int item_tokens = (int)(P.pair ? P.tokens_half : P.tokens);
+    const int nitems = item_tokens * 2;
+    const int first = blockIdx.x, step = gridDim.x;
+    const int nlocal = first < nitems ? (nitems - first + step - 1) / step : 0;
     const int tpi = P.pair ? 2 : 1;                             // tiles per item
-    auto slot_tiles = [&](int k) -> long long { return nlocal > k ? ((nlocal - k + kSlots - 1) / kSlots) * tpi : 0; };
+    auto slot_tiles = [&](int k) -> int { return nlocal > k ? ((nlocal - k + kSlots - 1) / kSlots) * tpi : 0; };
     // tile ts of slot k -> token row m (in ycond / out rows) and half
-    auto tile_of = [&](int k, long long ts, long long& m, int& half) {
-        const long long q = (ts / tpi) * kSlots + k;            // CTA-local item
-        const long long it = first + q * step;
-        half = (int)(it & 1);
-        m = (it >> 1) + ((P.pair && (ts & 1)) ? P.tokens_half : 0);
+    auto tile_of = [&](int k, int ts, int& m, int& half) {
+        const int q = (P.pair ? (ts >> 1) : ts) * kSlots + k;   // CTA-local item
+        const int it = first + q * step;
+        half = it & 1;
+        m = (it >> 1) + ((P.pair && (ts & 1)) ? item_tokens : 0);
     };
 
     if (tid == 0) {
         for (int k = 0; k < kSlots; ++k) {
             mbar_init(d_bar(k), 1);
+            mbar_init(p_bar(k), 1);
             mbar_init(a_bar(k), 4);
             for (int b = 0; b < 2; ++b) { mbar_init(y_full(k, b), 1); mbar_init(y_empty(k, b), 1); }
         }
@@ -168,7 +189,7 @@ pixel_decoder_tc_kernel(const __grid_constant__ CUtensorMap ymap, const Params P
         const int n16 = (int)(blob_bytes(R) / 16);
         for (int i = tid; i < n16; i += kThreads) dst[i] = __ldg(src + i);
     }
-    if (warp == kEpiWarps + 2) tmem_alloc(tslot, 512);
+    if (warp == kEpiWarps) tmem_alloc(tslot, 512);
     fence_proxy_async();          // the generic-proxy weight stores above are read by the tensor core (async proxy)
     tc_fence_before();
     __syncthreads();
@@ -177,111 +198,130 @@ pixel_decoder_tc_kernel(const __grid_constant__ CUtensorMap ymap, const Params P
     pdl_launch_dependents();
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen + (tslot - base));
 
-    if (warp == kEpiWarps) {
-        // ================================================================== TMA producer: condition tiles
-        long long nt[kSlots], maxt = 0;
-        for (int k = 0; k < kSlots; ++k) { nt[k] = slot_tiles(k); maxt = nt[k] > maxt ? nt[k] : maxt; }
-        for (long long ts = 0; ts < maxt; ++ts) {
-            const int b = (int)(ts & 1);
-            for (int k = 0; k < kSlots; ++k) {
-                if (ts >= nt[k]) continue;
-                if (ts >= 2) mbar_wait(y_empty(k, b), (uint32_t)(((ts >> 1) - 1) & 1));
-                if (elect_one()) {
-                    long long m; int half;
-                    tile_of(k, ts, m, half);
-                    const uint32_t dst = sY + (uint32_t)(2 * k + b) * kYTile;
-                    mbar_expect_tx(y_full(k, b), kYTile);
-                    // ycond viewed as [tokens * 256 pixel rows, 32 channels]; two 16-channel boxes = the two K chunks
-                    const long long row = m * 256 + half * 128;
-                    tma_load_2d(dst, &ymap, y_full(k, b), 0, (int)row);
-                    tma_load_2d(dst + 128 * 32, &ymap, y_full(k, b), 16, (int)row);
-                }
-                __syncwarp();
-            }
-        }
-    } else if (warp == kEpiWarps + 1) {
-        // ================================================================== MMA issuer
+    if (warp >= kEpiWarps) {
+        // ================================================================== MMA issuer of slot k (one elected lane issues)
+        const int k = warp - kEpiWarps;
+        const int nt = slot_tiles(k);
+#ifdef DECO_DTC_TRACE
+        int trace_n = 0;
+        const bool trace_on = k == 0 && lane == 0;
+#endif
         constexpr uint32_t id16 = make_idesc_major(128, 16, 0, 0), id32 = make_idesc_major(128, 32, 0, 0),
                            id64 = make_idesc_major(128, 64, 0, 0);
         auto desc = [&](uint32_t addr) { return make_umma_desc(addr, 16, 256, 6); };
-        const uint64_t dOnes = desc(sW + kOnes);
-        long long nt[kSlots], maxt = 0;
-        for (int k = 0; k < kSlots; ++k) { nt[k] = slot_tiles(k); maxt = nt[k] > maxt ? nt[k] : maxt; }
-        // D (+)= Atile[128 x 32] (smem, 2 chunks of 4096 B) . B^T, B = rows [row0, row0 + N) of a K-major tile with
-        // `brows` rows per chunk, then the bias MMA against the ones tile
-        auto mma_ss = [&](uint32_t dcol, uint32_t idesc, uint32_t a_addr, uint32_t b_addr, uint32_t brows, uint32_t row0, bool acc) {
-            umma_bf16(dcol, desc(a_addr), desc(b_addr + row0 * 32), idesc, acc ? 1u : 0u);
-            umma_bf16(dcol, desc(a_addr + 128 * 32), desc(b_addr + brows * 32 + row0 * 32), idesc, 1u);
+        // descriptors are affine in the shared-memory address: one base per operand kind, the rest is integer offsets in
+        // 16-byte units (the address field of the descriptor)
+        const uint64_t dW = desc(sW);                                       // weight image base
+        const uint64_t dY0 = desc(sY + (uint32_t)(2 * k) * kYTile);         // condition tile, buffer 0 (buffer 1: + kYTile)
+        auto wd = [&](uint32_t off) { return dW + (uint64_t)(off >> 4); };
+        const uint64_t dOnes = wd(kOnes);
+        const uint32_t tcol = tmem + (uint32_t)k * kSlotCols;
+        const uint32_t acol = tcol + kColA;
+        // D (+)= Y[128 x 32] (2 chunks of 4096 B) . B^T with B = rows [row0, row0 + N) of a K-major tile of `brows` rows per
+        // chunk at weight offset boff
+        auto mma_y = [&](uint32_t dcol, uint32_t idesc, uint64_t dy, uint32_t boff, uint32_t brows, uint32_t row0, uint32_t acc) {
+            umma_bf16(dcol, dy, wd(boff + row0 * 32), idesc, acc);
+            umma_bf16(dcol, dy + ((128 * 32) >> 4), wd(boff + brows * 32 + row0 * 32), idesc, 1u);
         };
-        auto mma_ts = [&](uint32_t dcol, uint32_t idesc, uint32_t acol, uint32_t b_addr, uint32_t brows) {
-            umma_bf16_ts(dcol, acol, desc(b_addr), idesc, 0u);
-            umma_bf16_ts(dcol, acol + 8u, desc(b_addr + brows * 32), idesc, 1u);
+        auto mma_a = [&](uint32_t dcol, uint32_t idesc, uint32_t boff, uint32_t brows, uint32_t acc) {     // A operand in TMEM
+            umma_bf16_ts(dcol, acol, wd(boff), idesc, acc);
+            umma_bf16_ts(dcol, acol + 8u, wd(boff + brows * 32), idesc, 1u);
         };
-        auto mma_bias = [&](uint32_t dcol, uint32_t idesc, uint32_t b_addr, uint32_t row0) {
-            umma_bf16(dcol, dOnes, desc(b_addr + row0 * 32), idesc, 1u);
+        auto mma_bias = [&](uint32_t dcol, uint32_t idesc, uint32_t boff, uint32_t row0, uint32_t acc) {
+            umma_bf16(dcol, dOnes, wd(boff + row0 * 32), idesc, acc);
         };
-        // scale' / gate accumulators of block j from the condition tile at `ya`
-        auto issue_sc = [&](uint32_t tcol, uint32_t ya, int j) {
-            const uint32_t wb = sW + kBlock0 + (uint32_t)j * kBlockBytes;
-            mma_ss(tcol + kColSC, id32, ya, wb + kWsg, 64, 0, false);
-            mma_bias(tcol + kColSC, id32, wb + kBsg, 0);
+        auto blk = [&](int j) { return kBlock0 + (uint32_t)j * kBlockBytes; };
+        // condition tile of this slot's tile ts -> buffer ts & 1 (ycond viewed as [tokens * 256 pixel rows, 32 channels];
+        // two 16-channel boxes = the two K chunks of the operand)
+        auto load_y = [&](int ts) {
+            int m, half;
+            tile_of(k, ts, m, half);
+            const int b = ts & 1;
+            const uint32_t dst = sY + (uint32_t)(2 * k + b) * kYTile;
+            const int row = m * 256 + half * 128;
+            mbar_expect_tx(y_full(k, b), kYTile);
+            tma_load_2d(dst, &ymap, y_full(k, b), 0, row);
+            tma_load_2d(dst + 128 * 32, &ymap, y_full(k, b), 16, row);
         };
-        auto issue_gt = [&](uint32_t tcol, uint32_t ya, int j) {
-            const uint32_t wb = sW + kBlock0 + (uint32_t)j * kBlockBytes;
-            mma_ss(tcol + kColGT, id32, ya, wb + kWsg, 64, 32, false);
-            mma_bias(tcol + kColGT, id32, wb + kBsg, 32);
-        };
-        auto issue_scgt0 = [&](uint32_t tcol, uint32_t ya) {          // block 0: both at once (SC | GT are adjacent columns)
-            const uint32_t wb = sW + kBlock0;
-            mma_ss(tcol + kColSC, id64, ya, wb + kWsg, 64, 0, false);
-            mma_bias(tcol + kColSC, id64, wb + kBsg, 0);
-        };
-        // prologue: first tile of every slot
-        for (int k = 0; k < kSlots; ++k) {
-            if (nt[k] == 0) continue;
+        if (elect_one()) {
+            if (nt > 0) load_y(0);
+            if (nt > 1) load_y(1);
+        }
+        __syncwarp();
+        if (nt > 0) {           // prologue: scale' | gate of the first tile's block 0 (SC | GT are adjacent columns: N = 64)
             mbar_wait(y_full(k, 0), 0);
             tc_fence_after();
             if (elect_one()) {
-                issue_scgt0(tmem + (uint32_t)k * kSlotCols, sY + (uint32_t)(2 * k) * kYTile);
-                umma_commit(d_bar(k));
+                mma_bias(tcol + kColSC, id64, blk(0) + kBsg, 0, 0u);
+                mma_y(tcol + kColSC, id64, dY0, blk(0) + kWsg, 64, 0, 1u);
+                umma_commit(p_bar(k));
             }
             __syncwarp();
         }
-        for (long long ts = 0; ts < maxt; ++ts) {
-            const int yb = (int)(ts & 1);
+        uint32_t aphase = 0;
+        for (int ts = 0; ts < nt; ++ts) {
+            const int yb = ts & 1;
+            const uint64_t dy = dY0 + (uint64_t)(yb ? (kYTile >> 4) : 0);
             for (int s = 0; s < nstage; ++s) {
-                for (int k = 0; k < kSlots; ++k) {
-                    if (ts >= nt[k]) continue;
-                    const long long narr = ts * nstage + s;                 // index of the arrival this stage waits for
-                    mbar_wait(a_bar(k), (uint32_t)(narr & 1));
-                    const bool last = s == nstage - 1;
-                    const bool next = last && ts + 1 < nt[k];
-                    if (next) mbar_wait(y_full(k, yb ^ 1), (uint32_t)(((ts + 1) >> 1) & 1));
-                    tc_fence_after();
+                mbar_wait(a_bar(k), aphase);
+                aphase ^= 1;
+                DTC_TRACE(1, 100 + s);
+                const bool last = s == nstage - 1;
+                const bool next = last && ts + 1 < nt;
+                tc_fence_after();
+                if (last) {
                     if (elect_one()) {
-                        const uint32_t tcol = tmem + (uint32_t)k * kSlotCols;
-                        const uint32_t ya = sY + (uint32_t)(2 * k + yb) * kYTile;
-                        if (last) {
-                            const uint32_t wf = sW + kBlock0 + (uint32_t)R * kBlockBytes;
-                            mma_ts(tcol + kColH, id16, tcol + kColA, wf + kWf, 16);
-                            mma_bias(tcol + kColH, id16, wf + kBf, 0);
-                            if (next) issue_scgt0(tcol, sY + (uint32_t)(2 * k + (yb ^ 1)) * kYTile);
-                        } else if ((s & 1) == 0) {
-                            const int j = s >> 1;
-                            const uint32_t wb = sW + kBlock0 + (uint32_t)j * kBlockBytes;
-                            mma_ts(tcol + kColH, id32, tcol + kColA, wb + kW0, 32);
-                            mma_ss(tcol + kColH, id32, ya, wb + kC0, 32, 0, true);
-                            mma_bias(tcol + kColH, id32, wb + kB0, 0);
-                            if (j + 1 < R) issue_sc(tcol, ya, j + 1);       // SC_j has been read (stage s arrival)
-                            if (j >= 1) issue_gt(tcol, ya, j);              // GT_{j-1} has been read (same arrival)
-                            if (j == R - 1) umma_commit(y_empty(k, yb));    // last readers of this condition tile
-                        } else {
-                            const int j = s >> 1;
-                            const uint32_t wb = sW + kBlock0 + (uint32_t)j * kBlockBytes;
-                            mma_ts(tcol + kColH, id32, tcol + kColA, wb + kW2, 32);
-                            mma_bias(tcol + kColH, id32, wb + kB2, 0);
-                        }
+                        mma_a(tcol + kColH, id16, blk(R) + kWf, 16, 0u);
+                        mma_bias(tcol + kColH, id16, blk(R) + kBf, 0, 1u);
                         umma_commit(d_bar(k));
+                    }
+                    __syncwarp();
+                    if (next) {         // next tile's scale' | gate: SC and GT were last read two / zero stages ago
+                        mbar_wait(y_full(k, yb ^ 1), (uint32_t)(((ts + 1) >> 1) & 1));
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const uint64_t dyn = dY0 + (uint64_t)(yb ? 0 : (kYTile >> 4));
+                            mma_bias(tcol + kColSC, id64, blk(0) + kBsg, 0, 0u);
+                            mma_y(tcol + kColSC, id64, dyn, blk(0) + kWsg, 64, 0, 1u);
+                            umma_commit(p_bar(k));      // its own barrier: d_bar must never run two phases ahead of its waiters
+                        }
+                        __syncwarp();
+                    }
+                    if (ts + 2 < nt) {  // refill this tile's buffer (its last readers were committed two stages ago)
+                        mbar_wait(y_empty(k, yb), (uint32_t)((ts >> 1) & 1));
+                        if (elect_one()) load_y(ts + 2);
+                        __syncwarp();
+                    }
+                } else if ((s & 1) == 0) {
+                    const int j = s >> 1;
+                    if (elect_one()) {
+                        // H = 1/2 W0 h: the activation-dependent product last, so the accumulator's other addends are
+                        // already in flight; the waiting epilogue needs only this group
+                        mma_bias(tcol + kColH, id32, blk(j) + kB0, 0, 0u);
+                        mma_y(tcol + kColH, id32, dy, blk(j) + kC0, 32, 0, 1u);
+                        mma_a(tcol + kColH, id32, blk(j) + kW0, 32, 1u);
+                        umma_commit(d_bar(k));
+                        DTC_TRACE(1, 200 + s);
+                        // not on the critical path (needed two stages later); covered by the next commit
+                        if (j + 1 < R) {                    // SC_j has been read (this stage's arrival)
+                            mma_bias(tcol + kColSC, id32, blk(j + 1) + kBsg, 0, 0u);
+                            mma_y(tcol + kColSC, id32, dy, blk(j + 1) + kWsg, 64, 0, 1u);
+                        }
+                        if (j >= 1) {                       // GT_{j-1} has been read (same arrival)
+                            mma_bias(tcol + kColGT, id32, blk(j) + kBsg, 32, 0u);
+                            mma_y(tcol + kColGT, id32, dy, blk(j) + kWsg, 64, 32, 1u);
+                        }
+                        if (j == R - 1) umma_commit(y_empty(k, yb));        // last readers of this condition tile
+                        DTC_TRACE(1, 300 + s);
+                    }
+                    __syncwarp();
+                } else {
+                    const int j = s >> 1;
+                    if (elect_one()) {
+                        mma_bias(tcol + kColH, id32, blk(j) + kB2, 0, 0u);
+                        mma_a(tcol + kColH, id32, blk(j) + kW2, 32, 1u);
+                        umma_commit(d_bar(k));
+                        DTC_TRACE(1, 200 + s);
                     }
                     __syncwarp();
                 }
@@ -292,10 +332,16 @@ pixel_decoder_tc_kernel(const __grid_constant__ CUtensorMap ymap, const Params P
         const int k = warp >> 2;
         const int l = (warp & 3) * 32 + lane;                   // lane inside the tile
         const uint32_t tcol = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)k * kSlotCols;
-        const long long nt = slot_tiles(k);
+        const int nt = slot_tiles(k);
         const size_t plane = (size_t)P.H * P.W;
         const int L = P.Hp * P.Wp;
+        const int Bimg = P.pair ? item_tokens / L : 0;          // images of the shared state (pair mode)
         uint32_t dphase = 0;
+        uint32_t pphase = 0;
+#ifdef DECO_DTC_TRACE
+        int trace_n = 0;
+        const bool trace_on = k == 0 && l == 0;
+#endif
         auto wait_d = [&]() { mbar_wait(d_bar(k), dphase); dphase ^= 1; tc_fence_after(); };
         auto release = [&]() {                                  // TMEM stores / loads of this warp are complete and fenced
             tc_fence_before();
@@ -305,20 +351,35 @@ pixel_decoder_tc_kernel(const __grid_constant__ CUtensorMap ymap, const Params P
         float g_ = P.g, dt_ = P.dt, c0_ = P.c0, c1_ = P.c1;
         if (P.pair && P.dev) { g_ = __ldg(P.dev); dt_ = __ldg(P.dev + 1); c0_ = __ldg(P.dev + 2); c1_ = __ldg(P.dev + 3); }
         float u_keep[3] = {0.f, 0.f, 0.f};
-        if (nt > 0) wait_d();                                   // prologue: SC | GT of the first tile
-        for (long long ts = 0; ts < nt; ++ts) {
-            long long m; int half;
+        // pixel of this thread in tile ts: offsets of its image row (x / out) and inside the plane
+        auto locate = [&](int ts, size_t& xoff, size_t& ooff) {
+            int m, half;
             tile_of(k, ts, m, half);
             const int pix = half * 128 + l;                     // pixel inside the patch: ky = pix / 16, kx = pix % 16
-            const long long img_row = m / L;                    // row of the CFG batch
-            const int tok = (int)(m % L);
-            const int py = tok / P.Wp, px = tok % P.Wp;
+            const int img_row = m / L;                          // row of the CFG batch
+            const int tok = m - img_row * L;
+            const int py = tok / P.Wp, px = tok - py * P.Wp;
             const size_t pix_off = (size_t)(py * 16 + (pix >> 4)) * P.W + (size_t)px * 16 + (pix & 15);
-            const long long xrow = P.pair ? (img_row % (P.tokens_half / L)) : img_row;
-            const float* xb = P.x + (size_t)xrow * 3 * plane + pix_off;
-            float rgb[3];
+            const int xrow = P.pair ? (img_row >= Bimg ? img_row - Bimg : img_row) : img_row;
+            xoff = (size_t)xrow * 3 * plane + pix_off;
+            ooff = (size_t)img_row * 3 * plane + pix_off;
+        };
+        // the image samples of a tile are fetched one tile ahead (plain loads: pair mode rewrites x in place later)
+        float rgb[3] = {0.f, 0.f, 0.f}, rgb_next[3] = {0.f, 0.f, 0.f};
+        size_t xoff = 0, ooff = 0, xoff_next = 0, ooff_next = 0;
+        if (nt > 0) {
+            locate(0, xoff_next, ooff_next);
 #pragma unroll
-            for (int c = 0; c < 3; ++c) rgb[c] = xb[c * plane];       // plain loads: pair mode rewrites x in place later
+            for (int c = 0; c < 3; ++c) rgb_next[c] = P.x[xoff_next + c * plane];
+        }
+        for (int ts = 0; ts < nt; ++ts) {
+            DTC_TRACE(0, 1);
+            const int pix = (((first + ((P.pair ? (ts >> 1) : ts) * kSlots + k) * step) & 1) << 7) + l;
+            xoff = xoff_next; ooff = ooff_next;
+            if (!(P.pair && (ts & 1))) {                        // pair mode: the cond tile re-uses the uncond tile's samples
+#pragma unroll
+                for (int c = 0; c < 3; ++c) rgb[c] = rgb_next[c];
+            }
             // ---- x = T'[pixel] + W' bf16(rgb)   (NerfEmbedder + input_proj, fp32)
             float x[kHx];
             {
@@ -338,14 +399,14 @@ pixel_decoder_tc_kernel(const __grid_constant__ CUtensorMap ymap, const Params P
             }
             // LayerNorm of x times `mul` (per channel, 32 raw fp32 words or null = 1) -> bf16 A operand
             auto norm_to_a = [&](const uint32_t* mul) {
-                float mean = 0.f;
+                // single pass: sum and sum of squares (|mean| is a few sigma at most here: the cancellation in
+                // E[x^2] - mean^2 stays ~1e-6 relative, far below the bf16 rounding of the result)
+                float sm = 0.f, sq = 0.f;
 #pragma unroll
-                for (int c = 0; c < kHx; ++c) mean += x[c];
-                mean *= (1.0f / kHx);
-                float var = 0.f;
-#pragma unroll
-                for (int c = 0; c < kHx; ++c) { const float d = x[c] - mean; var = fmaf(d, d, var); }
-                const float r = rsqrtf(var * (1.0f / kHx) + 1e-6f);
+                for (int c = 0; c < kHx; ++c) { sm += x[c]; sq = fmaf(x[c], x[c], sq); }
+                const float mean = sm * (1.0f / kHx);
+                const float var = fmaxf(fmaf(-mean, mean, sq * (1.0f / kHx)), 0.f);
+                const float r = rsqrtf(var + 1e-6f);
                 const float nmr = -mean * r;
                 uint32_t pk[16];
 #pragma unroll
@@ -357,21 +418,38 @@ pixel_decoder_tc_kernel(const __grid_constant__ CUtensorMap ymap, const Params P
                 tmem_st16(tcol + kColA, pk);
                 tmem_st_wait();
             };
-            // ---- stage 0: h~ = LN(x) . sc'
+            // ---- stage 0: h~ = LN(x) . sc'   (scale' | gate of block 0 were issued with the previous tile's final layer)
+            DTC_TRACE(0, 2);
+            mbar_wait(p_bar(k), pphase);
+            pphase ^= 1;
+            tc_fence_after();
+            DTC_TRACE(0, 3);
             {
                 uint32_t sc[32];
                 tmem_ld32(tcol + kColSC, sc);
                 tmem_ld_wait();
+                DTC_TRACE(0, 4);
                 norm_to_a(sc);
+                DTC_TRACE(0, 5);
                 release();
+                DTC_TRACE(0, 6);
+            }
+            if (ts + 1 < nt) {      // next tile's pixel: its global loads fly while this tile runs
+                locate(ts + 1, xoff_next, ooff_next);
+                if (!(P.pair && !(ts & 1))) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) rgb_next[c] = P.x[xoff_next + c * plane];
+                }
             }
             for (int j = 0; j < R; ++j) {
                 // ---- stage 2j + 1: u = silu(H) with H = v / 2 -> A operand
                 wait_d();
+                DTC_TRACE(0, 10);
                 {
                     uint32_t h[32];
                     tmem_ld32(tcol + kColH, h);
                     tmem_ld_wait();
+                    DTC_TRACE(0, 11);
                     uint32_t pk[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
@@ -380,10 +458,13 @@ pixel_decoder_tc_kernel(const __grid_constant__ CUtensorMap ymap, const Params P
                     }
                     tmem_st16(tcol + kColA, pk);
                     tmem_st_wait();
+                    DTC_TRACE(0, 12);
                     release();
+                    DTC_TRACE(0, 13);
                 }
                 // ---- stage 2j + 2: x += gate . H2, then the next block's modulated norm (or the final norm)
                 wait_d();
+                DTC_TRACE(0, 20);
                 {
 #pragma unroll
                     for (int hf = 0; hf < 2; ++hf) {
@@ -403,11 +484,14 @@ pixel_decoder_tc_kernel(const __grid_constant__ CUtensorMap ymap, const Params P
                     } else {
                         norm_to_a(nullptr);
                     }
+                    DTC_TRACE(0, 21);
                     release();
+                    DTC_TRACE(0, 22);
                 }
             }
             // ---- output stage: 3 channels of the final linear
             wait_d();
+            DTC_TRACE(0, 30);
             float o[3];
             {
                 uint32_t f[8];
@@ -416,13 +500,12 @@ pixel_decoder_tc_kernel(const __grid_constant__ CUtensorMap ymap, const Params P
                 o[0] = __uint_as_float(f[0]); o[1] = __uint_as_float(f[1]); o[2] = __uint_as_float(f[2]);
             }
             if (!P.pair) {
-                const size_t ob = (size_t)img_row * 3 * plane + pix_off;
                 if (P.out_bf16) {
-                    __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(P.out) + ob;
+                    __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(P.out) + ooff;
 #pragma unroll
                     for (int c = 0; c < 3; ++c) op[c * plane] = f2bf(o[c]);
                 } else {
-                    float* op = reinterpret_cast<float*>(P.out) + ob;
+                    float* op = reinterpret_cast<float*>(P.out) + ooff;
 #pragma unroll
                     for (int c = 0; c < 3; ++c) op[c * plane] = o[c];
                 }
@@ -431,23 +514,23 @@ pixel_decoder_tc_kernel(const __grid_constant__ CUtensorMap ymap, const Params P
                 for (int c = 0; c < 3; ++c) u_keep[c] = o[c];
             } else {
                 // guidance + multistep update of the fp32 state (csrc/sampler.cu, same expression order)
-                const size_t ob = (size_t)xrow * 3 * plane + pix_off;
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
+                    const size_t ob = xoff + c * plane;
                     const float pred = fmaf(g_, o[c] - u_keep[c], u_keep[c]);
                     float v = c0_ * pred;
-                    if (P.p1) v = fmaf(c1_, P.p1[ob + c * plane], v);
+                    if (P.p1) v = fmaf(c1_, P.p1[ob], v);
                     const float xn = fmaf(dt_, v, rgb[c]);
-                    P.x_out[ob + c * plane] = xn;
-                    if (P.pred_out) P.pred_out[ob + c * plane] = pred;
-                    if (P.u8_out) P.u8_out[ob + c * plane] = to_u8(xn);
+                    P.x_out[ob] = xn;
+                    if (P.pred_out) P.pred_out[ob] = pred;
+                    if (P.u8_out) P.u8_out[ob] = to_u8(xn);
                 }
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == kEpiWarps + 2) tmem_dealloc(tmem, 512);
+    if (warp == kEpiWarps) tmem_dealloc(tmem, 512);
 }
 
 }  // namespace dtc
@@ -524,3 +607,9 @@ extern "C" int deco_pixel_decoder_tc(const float* x, const void* ysilu_bf16, con
     if (e != cudaSuccess) { deco_set_error("pixel_decoder_tc launch failed: %s", cudaGetErrorString(e)); return (int)e; }
     return DECO_OK;
 }
+
+#ifdef DECO_DTC_TRACE
+extern "C" int deco_dtc_trace_copy(long long* host_buf) {
+    return (int)cudaMemcpyFromSymbol(host_buf, deco::dtc::g_dtc_trace, sizeof(long long) * 2 * 4096);
+}
+#endif

@@ -153,7 +153,7 @@ __device__ __forceinline__ void epilogue_chunk_staged(const GemmParams& P, const
                         *reinterpret_cast<float4*>(o) = v;
                     }
                 } else {
-                    if (EPI == EPI_BIAS_SILU) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
+                    if (EPI == EPI_BIAS_SILU) { v.x = silu_fast(v.x); v.y = silu_fast(v.y); v.z = silu_fast(v.z); v.w = silu_fast(v.w); }
                     uint2 w;
                     w.x = pack_bf2(v.x, v.y); w.y = pack_bf2(v.z, v.w);
                     *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(P.out) + row * P.ldo + n) = w;
@@ -217,7 +217,7 @@ __device__ __forceinline__ void epilogue_chunk_direct(const GemmParams& P, const
     }
     if (EPI == EPI_BIAS_SILU) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = silu_f(v[i]);
+        for (int i = 0; i < 32; ++i) v[i] = silu_fast(v[i]);
     }
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(P.out) + row * P.ldo + n0;
 #pragma unroll

@@ -5,11 +5,12 @@
 #include "tcgen05.cuh"
 #include <cstdlib>
 #include <vector>
+#include <type_traits>
 
 void deco_set_error(const char*, ...) {}
 using namespace deco;
 
-struct Res { long long ld[5], st[5], mma_ts[4], mma_ss[4]; };
+struct Res { long long ld[5], st[5], mma[24], multi[3]; };
 
 template <int WARPS>
 __device__ void bench_ld_st(uint32_t tmem, int warp, int lane, long long* ld_out, long long* st_out, int iters, float* sink) {
@@ -49,10 +50,10 @@ __global__ void __launch_bounds__(512, 1) bench_kernel(Res* out, int iters, floa
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-    const uint32_t sB = base, sA = base + 16384, bar = base + 65536, slot = bar + 16;
+    const uint32_t sB = base, sA = base + 16384, bar = base + 65536, slot = bar + 64;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int i = tid; i < 16384; i += blockDim.x) reinterpret_cast<uint32_t*>(gen)[i] = 0x3c003c00u;   // small bf16 values
-    if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+    if (tid == 0) { for (int i = 0; i < 6; ++i) mbar_init(bar + 8u * i, 1); fence_barrier_init(); }
     if (warp == 0) tmem_alloc(slot, 512);
     fence_proxy_async();
     tc_fence_before();
@@ -66,32 +67,66 @@ __global__ void __launch_bounds__(512, 1) bench_kernel(Res* out, int iters, floa
     bench_ld_st<8>(tmem, warp, lane, &out->ld[3], &out->st[3], iters, sink);
     bench_ld_st<16>(tmem, warp, lane, &out->ld[4], &out->st[4], iters, sink);
 
-    // ---- MMA issue rate
+    // ---- MMA issue rate: unrolled groups of 8 instructions with precomputed descriptors, (a) round-robin over independent
+    // accumulators, (b) all accumulating into ONE accumulator (dependent chain), TS and SS forms
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     if (tid == 0) {
-        const int Ns[4] = {16, 32, 64, 96};
         uint32_t phase = 0;
-        for (int mode = 0; mode < 2; ++mode)
-            for (int ni = 0; ni < 4; ++ni) {
-                const uint32_t idesc = make_idesc_major(128, Ns[ni], 0, 0);
-                const uint64_t db = make_umma_desc(sB, 16, 256, 6);
-                const uint64_t da = make_umma_desc(sA, 16, 256, 6);
-                long long t0 = clock64();
-                for (int it = 0; it < iters; ++it) {
-                    // round-robin over independent accumulators (as many as fit in 256 columns): issue rate, not latency
-                    const int nacc = 256 / Ns[ni];
-                    const uint32_t d = tmem + 256u + (uint32_t)((it % nacc) * Ns[ni]);
-                    if (mode == 0) umma_bf16_ts(d, tmem + (uint32_t)((it & 3) * 8), db, idesc, 1u);
+        const uint64_t db = make_umma_desc(sB, 16, 256, 6);
+        const uint64_t da = make_umma_desc(sA, 16, 256, 6);
+        auto run = [&](auto ntag, int mode, bool chain, long long* dst) {
+            constexpr int N = decltype(ntag)::value;
+            constexpr uint32_t idesc = make_idesc_major(128, N, 0, 0);
+            constexpr int nacc = 256 / N > 8 ? 8 : (256 / N < 1 ? 1 : 256 / N);
+            long long t0 = clock64();
+            for (int it = 0; it < iters / 8; ++it) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const uint32_t d = tmem + 256u + (chain ? 0u : (uint32_t)((u % nacc) * N));
+                    if (mode == 0) umma_bf16_ts(d, tmem + (uint32_t)((u & 3) * 8), db, idesc, 1u);
                     else umma_bf16(d, da, db, idesc, 1u);
                 }
-                umma_commit(bar);
-                mbar_wait(bar, phase);
-                phase ^= 1;
-                long long t1 = clock64();
-                (mode == 0 ? out->mma_ts : out->mma_ss)[ni] = t1 - t0;
             }
+            umma_commit(bar);
+            mbar_wait(bar, phase);
+            phase ^= 1;
+            *dst = clock64() - t0;
+        };
+        int o = 0;
+        for (int mode = 0; mode < 2; ++mode)
+            for (int chain = 0; chain < 2; ++chain) {
+                run(std::integral_constant<int, 16>{}, mode, chain, &out->mma[o++]);
+                run(std::integral_constant<int, 32>{}, mode, chain, &out->mma[o++]);
+                run(std::integral_constant<int, 64>{}, mode, chain, &out->mma[o++]);
+                run(std::integral_constant<int, 96>{}, mode, chain, &out->mma[o++]);
+                run(std::integral_constant<int, 128>{}, mode, chain, &out->mma[o++]);
+                run(std::integral_constant<int, 256>{}, mode, chain, &out->mma[o++]);
+            }
+    }
+    // ---- is the ~94 clk per instruction a per-THREAD issue cost or a tensor-pipe cost?  1 / 2 / 4 warps issue N = 32 TS MMAs
+    // at the same time (own accumulators, own barriers)
+    int uses = 0;
+    for (int nw = 1; nw <= 4; nw *= 2) {
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        long long t0 = clock64();
+        if (warp < nw && lane == 0) {
+            constexpr uint32_t idesc = make_idesc_major(128, 32, 0, 0);
+            const uint64_t db = make_umma_desc(sB, 16, 256, 6);
+            for (int it = 0; it < iters / 8; ++it) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    umma_bf16_ts(tmem + 256u + (uint32_t)(warp * 64 + (u & 1) * 32), tmem + (uint32_t)((u & 3) * 8), db, idesc, 1u);
+            }
+            umma_commit(bar + 8u * (1 + warp));
+            mbar_wait(bar + 8u * (1 + warp), (uint32_t)(uses & 1));
+            ++uses;
+        }
+        __syncthreads();
+        if (tid == 0) out->multi[nw == 1 ? 0 : nw == 2 ? 1 : 2] = clock64() - t0;
     }
     tc_fence_before();
     __syncthreads();
@@ -113,10 +148,16 @@ int main() {
         printf("warps %2d: tcgen05.ld 32x32b.x32  %7.1f B/clk/SM (%5.1f clk per instr per warp)   tcgen05.st %7.1f B/clk/SM\n",
                W[i], bytes / h.ld[i], (double)h.ld[i] / iters, bytes / h.st[i]);
     }
-    const int Ns[4] = {16, 32, 64, 96};
-    for (int i = 0; i < 4; ++i)
-        printf("tcgen05.mma M128 N%-2d K16: TS %6.1f clk/instr (%6.0f MAC/clk)   SS %6.1f clk/instr (%6.0f MAC/clk)\n", Ns[i],
-               (double)h.mma_ts[i] / iters, 128.0 * Ns[i] * 16 * iters / h.mma_ts[i],
-               (double)h.mma_ss[i] / iters, 128.0 * Ns[i] * 16 * iters / h.mma_ss[i]);
+    const int Ns[6] = {16, 32, 64, 96, 128, 256};
+    const char* names[4] = {"TS independent", "TS chained    ", "SS independent", "SS chained    "};
+    for (int m = 0; m < 4; ++m)
+        for (int i = 0; i < 6; ++i) {
+            const double clk = (double)h.mma[m * 6 + i] / iters;
+            printf("tcgen05.mma M128 N%-3d K16 %s: %6.1f clk/instr  (%5.0f MAC/clk; floor 128*N/256 = %d clk)\n", Ns[i], names[m], clk,
+                   128.0 * Ns[i] * 16 / clk, 128 * Ns[i] / 256);
+        }
+    for (int i = 0; i < 3; ++i)
+        printf("N32 TS MMAs issued by %d warps concurrently: %6.1f clk per instruction per warp, %6.1f clk per instruction overall\n",
+               1 << i, (double)h.multi[i] / iters, (double)h.multi[i] / iters / (1 << i));
     return 0;
 }

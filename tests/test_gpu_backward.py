@@ -514,7 +514,7 @@ def test_train_input_kernels_vs_reference_expressions(dev):
     mask = (u < 0.3).to(cond.dtype)
     assert torch.equal(got, cond * (1 - mask) + unc * mask)
     with pytest.raises(Exception):
-        ops.flow_pair(x[:, :, :, :3].contiguous(), eps[:, :, :, :3].contiguous(), coef)     # per-image size % 4 != 0
+        ops.flow_pair(x[:, :, :3, :3].contiguous(), eps[:, :, :3, :3].contiguous(), coef)     # 27 elements per image: % 4 != 0
 
 
 @pytest.mark.parametrize("flw", [0.0, 1.0])
