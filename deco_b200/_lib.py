@@ -24,7 +24,7 @@ SIGNATURES = {
     "deco_gemm_stream": (_i, [_vp, _ll, _vp, _ll, _i, _i, _i, _vp, _vp, _ll, _vp, _ll, _vp, _ll, _i, _vp, _vp, _ll, _vp, _ll,
                               _vp, _vp]),
     "deco_gemm_norm_qkv": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _vp, _i, _i, _f, _vp, _ll, _i, _i, _vp, _vp, _vp,
-                                _i, _vp, _i, _f, _vp]),
+                                _i, _vp, _i, _f, _i, _vp]),
     "deco_gemm_norm_swiglu": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _vp, _i, _i, _f, _vp, _ll, _vp]),
     "deco_gemm_set_tuning": (_i, [_i, _i]),
     "deco_gemm_reserve_sms": (_i, [_i]),
@@ -38,6 +38,7 @@ SIGNATURES = {
     "deco_rmsnorm_addpos": (_i, [_vp, _vp, _vp, _i, _vp, _ll, _i, _f, _vp]),
     "deco_cast_f32_bf16": (_i, [_vp, _vp, _ll, _vp]),
     "deco_attention_fwd": (_i, [_vp, _ll, _vp, _vp, _ll, _i, _vp, _vp, _ll, _i, _vp, _ll, _i, _i, _i, _i, _f, _vp]),
+    "deco_attention_fwd_pitched": (_i, [_vp, _ll, _i, _vp, _vp, _ll, _i, _i, _vp, _vp, _ll, _i, _i, _vp, _ll, _i, _i, _i, _i, _f, _vp]),
     "deco_silu_add_rows": (_i, [_vp, _i, _vp, _vp, _ll, _i, _i, _vp]),
     "deco_decoder_blob_bytes": (_i, [_i]),
     "deco_pixel_decoder": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),

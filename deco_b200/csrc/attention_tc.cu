@@ -26,6 +26,7 @@
 // Operand layouts were validated stand-alone by scripts/umma_probe.cu.
 #include "tcgen05.cuh"
 #include "tma_host.cuh"
+#include <cstdlib>
 
 namespace deco {
 
@@ -428,16 +429,23 @@ attention_tc_kernel(const __grid_constant__ TcAttnMaps M, const TcAttnParams P)
 }
 
 // 4-D view (d, token, head, batch) of a strided [B*L, row_stride] bf16 matrix whose columns are [head][d]
+// head_pitch = elements between consecutive heads inside a row (head_dim for a dense [head][d] row; 80 for the padded
+// layout the QKV GEMM writes for head_dim 72, which keeps every 16-column TMA box inside one 32-byte sector)
 static int make_attn_tmap(CUtensorMap* map, const void* ptr, int D, long long L, int heads, int B, long long row_stride,
-                          int box_d, CUtensorMapSwizzle swz) {
+                          int box_d, CUtensorMapSwizzle swz, long long head_pitch = 0) {
+    if (head_pitch <= 0) head_pitch = D;
+    static int promo = -1;
+    if (promo < 0) { const char* e = getenv("DECO_ATTN_L2PROMO"); promo = e ? atoi(e) : 128; }
+    const CUtensorMapL2promotion l2p = promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : promo == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                     : promo == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
     PFN_encodeTiled enc = get_tensormap_encoder();
     if (!enc) { deco_set_error("cuTensorMapEncodeTiled entry point not available"); return DECO_ERR_DRIVER; }
     cuuint64_t dims[4] = {(cuuint64_t)D, (cuuint64_t)L, (cuuint64_t)heads, (cuuint64_t)B};
-    cuuint64_t strides[3] = {(cuuint64_t)row_stride * 2, (cuuint64_t)D * 2, (cuuint64_t)L * (cuuint64_t)row_stride * 2};
+    cuuint64_t strides[3] = {(cuuint64_t)row_stride * 2, (cuuint64_t)head_pitch * 2, (cuuint64_t)L * (cuuint64_t)row_stride * 2};
     cuuint32_t box[4] = {(cuuint32_t)box_d, (cuuint32_t)kTcRows, 1, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult rc = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz, l2p, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) { deco_set_error("attention: cuTensorMapEncodeTiled failed: %d", (int)rc); return DECO_ERR_DRIVER; }
     return DECO_OK;
 }
@@ -479,7 +487,8 @@ static int attention_fwd_impl(const void* q, long long q_stride,
                               const void* k0, const void* v0, long long kv0_stride, int Lk0,
                               const void* k1, const void* v1, long long kv1_stride, int Lk1,
                               void* out, long long out_stride, float* lse2_out,
-                              int B, int heads, int Lq, int head_dim, float scale, void* stream)
+                              int B, int heads, int Lq, int head_dim, float scale, void* stream,
+                              int q_pitch = 0, int kv0_pitch = 0, int kv1_pitch = 0)
 {
     using namespace deco;
     DECO_CHECK_ARG(q && k0 && v0 && out, "attention: null pointer");
@@ -493,12 +502,14 @@ static int attention_fwd_impl(const void* q, long long q_stride,
     TcAttnMaps M;
     int rc;
     const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_32B;
-    if ((rc = make_attn_tmap(&M.q, q, head_dim, Lq, heads, B, q_stride, 16, sw))) return rc;
-    if ((rc = make_attn_tmap(&M.k0, k0, head_dim, Lk0, heads, B, kv0_stride, 16, sw))) return rc;
-    if ((rc = make_attn_tmap(&M.v0, v0, head_dim, Lk0, heads, B, kv0_stride, 16, sw))) return rc;
+    DECO_CHECK_ARG((q_pitch == 0 || (q_pitch >= head_dim && q_pitch % 8 == 0)) && (kv0_pitch == 0 || (kv0_pitch >= head_dim && kv0_pitch % 8 == 0)) &&
+                   (kv1_pitch == 0 || (kv1_pitch >= head_dim && kv1_pitch % 8 == 0)), "attention: head pitch must be >= head_dim and a multiple of 8");
+    if ((rc = make_attn_tmap(&M.q, q, head_dim, Lq, heads, B, q_stride, 16, sw, q_pitch))) return rc;
+    if ((rc = make_attn_tmap(&M.k0, k0, head_dim, Lk0, heads, B, kv0_stride, 16, sw, kv0_pitch))) return rc;
+    if ((rc = make_attn_tmap(&M.v0, v0, head_dim, Lk0, heads, B, kv0_stride, 16, sw, kv0_pitch))) return rc;
     if (Lk1) {
-        if ((rc = make_attn_tmap(&M.k1, k1, head_dim, Lk1, heads, B, kv1_stride, 16, sw))) return rc;
-        if ((rc = make_attn_tmap(&M.v1, v1, head_dim, Lk1, heads, B, kv1_stride, 16, sw))) return rc;
+        if ((rc = make_attn_tmap(&M.k1, k1, head_dim, Lk1, heads, B, kv1_stride, 16, sw, kv1_pitch))) return rc;
+        if ((rc = make_attn_tmap(&M.v1, v1, head_dim, Lk1, heads, B, kv1_stride, 16, sw, kv1_pitch))) return rc;
     } else {
         M.k1 = M.k0; M.v1 = M.v0;
     }
@@ -519,6 +530,18 @@ extern "C" int deco_attention_fwd(const void* q, long long q_stride,
 {
     return attention_fwd_impl(q, q_stride, k0, v0, kv0_stride, Lk0, k1, v1, kv1_stride, Lk1, out, out_stride, nullptr,
                               B, heads, Lq, head_dim, scale, stream);
+}
+
+// The same with explicit head pitches (elements between consecutive heads of a q / k / v row; 0 = head_dim): the fused QKV
+// GEMM writes head_dim-72 heads at a pitch of 80 so that every 16-column operand box is one aligned 32-byte sector.
+extern "C" int deco_attention_fwd_pitched(const void* q, long long q_stride, int q_head_pitch,
+                                          const void* k0, const void* v0, long long kv0_stride, int kv0_head_pitch, int Lk0,
+                                          const void* k1, const void* v1, long long kv1_stride, int kv1_head_pitch, int Lk1,
+                                          void* out, long long out_stride,
+                                          int B, int heads, int Lq, int head_dim, float scale, void* stream)
+{
+    return attention_fwd_impl(q, q_stride, k0, v0, kv0_stride, Lk0, k1, v1, kv1_stride, Lk1, out, out_stride, nullptr,
+                              B, heads, Lq, head_dim, scale, stream, q_head_pitch, kv0_head_pitch, kv1_head_pitch);
 }
 
 // Training forward: also writes lse2_out [B * heads, Lq] = log2 sum_k exp2(scale log2(e) q.k), which lets the backward

@@ -65,6 +65,7 @@ struct Params {
     int seg_cols;                   // heads * head_dim: columns per q / k / v segment
     const float* seg_w[3];          // head-norm weight [d] of the segment, null = pass through
     int seg_rope[3];
+    int out_pitch;                  // output columns per head (>= head_dim; 80 for head_dim 72 keeps q / k / v sector-aligned)
     const float2* rope;             // [L][d / 2] (cos, sin)
     int rope_wp;                    // > 0: axial table, tokens per image row (position = (tok / wp, tok % wp)); 0: generic
     float eps_head;
@@ -88,8 +89,10 @@ template <int BN, int EPI> struct Cfg {
     static constexpr bool kStream = EPI == FE_STREAM || EPI == FE_STREAM_RING;
     static constexpr int kRing = EPI == FE_STREAM ? BN / 32 : 3;
     static constexpr int kVecBytes = kStream ? 3 * BN * 4 : kTileN * 4;
+    // FE_NORM_QKV stages whole heads; a head_dim-72 head may be written at a pitch of 80 columns (zero padded)
+    static constexpr int kHeadPitchMax = kHeadDim == 72 ? 80 : kHeadDim;
     static constexpr int kOutStage = kStream ? kRing * 4096
-                                   : EPI == FE_NORM_QKV ? 2 * 32 * kHeadDim * 2 : 0;
+                                   : EPI == FE_NORM_QKV ? 2 * 32 * kHeadPitchMax * 2 : 0;
     // layout: 4 x kOutStage (1024-aligned buffers), then 4 x kVecBytes
     static constexpr int kWarpAll = ((4 * (kOutStage + kVecBytes) + 1023) / 1024) * 1024;
     static_assert(kOutStage % 1024 == 0, "TMA staging buffers must stay 1024-byte aligned");
@@ -410,7 +413,7 @@ gemm_fused_kernel(const __grid_constant__ Maps maps, const Params P)
             constexpr int D = C::kHeadDim;
             constexpr int HPT = C::kHeadsPerTile;
             constexpr int TN = C::kTileN;
-            constexpr int kRowBytes = D * 2;
+            const int kRowBytes = P.out_pitch * 2;    // staged row = one head at the output pitch (D or, for D = 72, 80 columns)
             constexpr int NV4 = (TN / 4 + 31) / 32;   // float4 of the shift product per lane
             // ---- CTA-wide tables: axial RoPE rows (x positions, y positions, one identity row), head-norm weights
             const uint32_t tbl = epi_base + C::kWarpAll;
@@ -579,10 +582,11 @@ gemm_fused_kernel(const __grid_constant__ Maps maps, const Params P)
                             const int cpos = (D == 64) ? (c8 ^ (lane & 7)) : c8;
                             sts128u(srow + cpos * 16, make_uint4(o[0], o[1], o[2], o[3]));
                         }
+                        if (D == 72 && P.out_pitch == 80) sts128u(srow + 9 * 16, make_uint4(0u, 0u, 0u, 0u));   // pad columns 72..79
                         fence_proxy_async();
                         __syncwarp();
                         if (lane == 0) {
-                            tma_store_2d(&maps.o, wstg + hb * (32 * kRowBytes), col0, row0);
+                            tma_store_2d(&maps.o, wstg + hb * (32 * kRowBytes), (col0 / D) * P.out_pitch, row0);
                             bulk_commit();
                         }
                     }
@@ -735,6 +739,9 @@ static bool stream_uses_ring(int K) {
 // Column tile: the ring variant affords 256-wide tiles (a ragged last tile is cheaper than narrow MMAs); whole-tile
 // staging fits 192.
 static int stream_tile_n(int N, int K) {
+    static int ring_bn = -1;      // DECO_STREAM_RING_BN = 128 / 192 / 256 overrides the ring variant's tile width (A/B measurements)
+    if (ring_bn < 0) { const char* e = getenv("DECO_STREAM_RING_BN"); ring_bn = e ? atoi(e) : 0; }
+    if (stream_uses_ring(K) && ring_bn > 0 && N % ring_bn == 0) return ring_bn;
     if (stream_uses_ring(K) && N >= 256) return 256;
     return (N % 192 == 0) ? 192 : 128;
 }
@@ -798,9 +805,13 @@ extern "C" int deco_gemm_norm_qkv(const void* A, long long lda, const void* W, l
                                   const float* ssq_in, int ssq_parts, int norm_hidden, float norm_eps,
                                   const float* shw, long long shw_stride,
                                   int heads, int head_dim, const float* w_seg0, const float* w_seg1, const float* w_seg2,
-                                  int rope_mask, const float* rope_cos_sin, int rope_tokens_per_row, float head_eps, void* stream)
+                                  int rope_mask, const float* rope_cos_sin, int rope_tokens_per_row, float head_eps,
+                                  int out_head_pitch, void* stream)
 {
     int rc = check_ab(A, lda, W, ldw, M, N, K, 8);
+    if (out_head_pitch <= 0) out_head_pitch = head_dim;
+    DECO_CHECK_ARG(out_head_pitch == head_dim || (head_dim == 72 && out_head_pitch == 80),
+                   "gemm_norm_qkv: output head pitch %d not built (head_dim, or 80 for head_dim 72)", out_head_pitch);
     if (rc) return rc;
     DECO_CHECK_ARG(out && ldo % 8 == 0 && ((uintptr_t)out & 15) == 0, "gemm_norm_qkv: bad output");
     DECO_CHECK_ARG(head_dim == 64 || head_dim == 72, "gemm_norm_qkv: head_dim %d not built (64, 72)", head_dim);
@@ -814,14 +825,15 @@ extern "C" int deco_gemm_norm_qkv(const void* A, long long lda, const void* W, l
     Maps maps;
     if ((rc = make_map(&maps.a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, A, M, K, lda, kBK, kBM, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
     if ((rc = make_map(&maps.b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, W, N, K, ldw, kBK, bn / 2, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-    if ((rc = make_map(&maps.o, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, out, M, N, ldo, head_dim, 32,
-                       head_dim == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
+    if ((rc = make_map(&maps.o, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, out, M, (long long)(N / head_dim) * out_head_pitch, ldo,
+                       out_head_pitch, 32, head_dim == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
     maps.r = maps.o; maps.x = maps.o;
     Params P = {};
     P.M = M; P.N = N; P.K = K; P.L = rows_per_image;
     P.ssq_in = ssq_in; P.ssq_parts = ssq_parts; P.inv_hidden = norm_hidden > 0 ? 1.0f / (float)norm_hidden : 0.f; P.eps = norm_eps;
     P.shw = shw; P.shw_stride = shw_stride;
     P.seg_cols = seg;
+    P.out_pitch = out_head_pitch;
     P.seg_w[0] = w_seg0; P.seg_w[1] = w_seg1; P.seg_w[2] = w_seg2;
     for (int i = 0; i < 3; ++i) P.seg_rope[i] = (rope_mask >> i) & 1;
     P.rope = (const float2*)rope_cos_sin; P.rope_wp = rope_tokens_per_row; P.eps_head = head_eps;

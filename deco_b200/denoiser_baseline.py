@@ -143,7 +143,7 @@ class FlattenDiT(nn.Module):
             temb = ops.gemm(h1, P["wt2"], P["bt2"], ops.EPI_BIAS)                         # [B, H]
             c = ops.cond_combine(temb, P["ytab"], y.reshape(-1))                          # silu(t + y) (:368)
             mod = ops.gemm(c, P["wada"], P["bada"], ops.EPI_BIAS)                         # [B, nb*6H + 2H]
-            st = StreamState(B * L, H, P["ffn_pad"], x.device)
+            st = StreamState(B * L, H, P["ffn_pad"], x.device, heads=heads)
             if COMPOSITE_SHIFT and "wshift" not in P:
                 P["wshift"], P["bshift"] = composite_shift_weights(self.blocks, P["blocks"], H, x.device)
             shw_all = ops.gemm(c, P["wshift"], P["bshift"], ops.EPI_BIAS_F32) if "wshift" in P else None

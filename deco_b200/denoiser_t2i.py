@@ -25,7 +25,8 @@ import torch.nn as nn
 
 from . import ops
 from .denoiser import (StreamState, _Embed, _NerfEmbedder, _PixelDecoder, _TimestepEmbedder, _Weight, fused_blocks,
-                       interleave_w13, pack_decoder)
+                       interleave_w13, pack_decoder, pack_decoder_tc)
+from . import denoiser as denoiser_mod
 
 bf16 = torch.bfloat16
 
@@ -193,6 +194,7 @@ class PixNerDiT(nn.Module):
         # NerfEmbedder.fetch_pos of the t2i model (dit_t2i_pixnerd.py:92-96): real part of the complex ex2d table
         tab = rope_cos_sin_ex2d(self.x_embedder.max_freqs ** 2 * 2, p, p)[..., 0]
         P["blob"], P["postab"] = pack_decoder(self.x_embedder.embedder[0], self.dec_net, self.in_channels, tab, device)
+        P["blob_tc"] = pack_decoder_tc(self.x_embedder.embedder[0], self.dec_net, self.in_channels, tab, device)
         self._prep, self._prep_key = P, key
         return P
 
@@ -240,46 +242,79 @@ class PixNerDiT(nn.Module):
             raise NotImplementedError("the text-to-image denoiser has no backward yet (the class-conditional PixNerDiT does: "
                                       "deco_b200/autograd.py); call under torch.no_grad() / .eval()")
         B, Cc, Hh, Ww = x.shape
-        p, H = self.patch_size, self.hidden_size
+        p = self.patch_size
         assert Cc == self.in_channels and Hh % p == 0 and Ww % p == 0
+        with torch.no_grad():
+            P = self.prepare(x.device)
+            x32 = x.detach().to(torch.float32).contiguous()
+            s2 = self._encode(P, ops.patchify(x32, p), t, y, B, Hh, Ww)
+            R = self.num_decoder_blocks
+            if denoiser_mod.DECODER == "tc":
+                ysilu = ops.gemm(s2, P["wcond"], P["bcond"], ops.EPI_BIAS_SILU)
+                return ops.pixel_decoder_tc(x32, ysilu, P["blob_tc"], p, self.decoder_hidden_size, R)
+            ycond = ops.gemm(s2, P["wcond"], P["bcond"], ops.EPI_BIAS)
+            return ops.pixel_decoder(x32, ycond, P["blob"], P["postab"], p, self.decoder_hidden_size, R)
+
+    supports_fused_cfg_step = True
+
+    @torch.no_grad()
+    def cfg_step(self, x, t2, cfg_condition, dev=None, g=1.0, dt=0.0, c0=1.0, c1=0.0, p1=None, x_out=None,
+                 pred_out=None, u8_out=None):
+        """CFG-batched sampler step with guidance + multistep update fused into the decoder epilogue (see
+        deco_b200.denoiser.PixNerDiT.cfg_step): x fp32 [B,C,H,W], t2 [2B], cfg_condition [2B, T, txt_embed_dim] stacked
+        [uncond || cond] (adam_sampling.py:101-117)."""
+        if not x.is_cuda:
+            raise RuntimeError("deco_b200 t2i PixNerDiT runs on CUDA (sm_100a) only; there is no CPU fallback")
+        if denoiser_mod.DECODER != "tc":
+            raise NotImplementedError("the fused sampler step needs the tcgen05 decoder (DECO_B200_DECODER=tc)")
+        B, Cc, Hh, Ww = x.shape
+        p = self.patch_size
+        L = (Hh // p) * (Ww // p)
+        P = self.prepare(x.device)
+        x32 = x.detach().to(torch.float32).contiguous()
+        xp = torch.empty((2 * B * L, Cc * p * p), dtype=bf16, device=x.device)
+        ops.patchify(x32, p, out=xp[: B * L])
+        ops.patchify(x32, p, out=xp[B * L:])
+        s2 = self._encode(P, xp, t2, cfg_condition, 2 * B, Hh, Ww)
+        ysilu = ops.gemm(s2, P["wcond"], P["bcond"], ops.EPI_BIAS_SILU)
+        return ops.pixel_decoder_tc_step(x32, ysilu, P["blob_tc"], p, self.decoder_hidden_size, self.num_decoder_blocks,
+                                         dev=dev, g=g, dt=dt, c0=c0, c1=c1, p1=p1, x_out=x_out, pred_out=pred_out,
+                                         u8_out=u8_out)
+
+    def _encode(self, P, xp, t, y, B, Hh, Ww):
+        """Patch tokens xp [B*L, C*p*p] + text states -> decoder condition s2 [B*L, H] (dit_t2i_pixnerd.py:276-297)."""
+        p, H = self.patch_size, self.hidden_size
         assert y.dim() == 3 and y.shape[0] == B and y.shape[2] == self.txt_embed_dim
         T = y.shape[1]
         assert T == self.txt_max_length, "y_pos_embedding is added without slicing: T must equal txt_max_length"
         L = (Hh // p) * (Ww // p)
-        dev = x.device
-        with torch.no_grad():
-            P = self.prepare(dev)
-            x32 = x.detach().to(torch.float32).contiguous()
-            pos = self.fetch_pos(Hh // p, Ww // p, dev)
-            tfreq = ops.timestep_freq(t.reshape(-1).to(torch.float32), self.t_embedder.frequency_embedding_size)
-            h1 = ops.gemm(tfreq, P["wt0"], P["bt0"], ops.EPI_BIAS_SILU)
-            temb = ops.gemm(h1, P["wt2"], P["bt2"], ops.EPI_BIAS)                                   # [B, H]
-            c = ops.cond_combine(temb, P["zero_row"], torch.zeros(B, dtype=torch.int64, device=dev))  # silu(t)
-            nt, ni = len(P["text"]), len(P["blocks"])
-            mod = ops.gemm(c, P["wada"], P["bada"], ops.EPI_BIAS) if nt + ni else None              # [B, (nt+ni)*6H]
-            # ---- text path
-            y16 = y.detach().reshape(B * T, self.txt_embed_dim).to(bf16).contiguous()
-            yraw = ops.gemm(y16, P["wy"], P["by"], ops.EPI_BIAS_F32)
-            ys = ops.rmsnorm_addpos(yraw, P["yn"], P["ypos"])                                       # fp32 [B*T, H]
-            if nt:
-                bufs = self._bufs(B * T, P, dev)
-                for i, bp in enumerate(P["text"]):
-                    self._block(bp, mod[:, i * 6 * H:(i + 1) * 6 * H], ys, T, B, bufs)
-            ytxt = ops.cast_bf16(ys)
-            # ---- image path
-            xp = ops.patchify(x32, p)
-            if ni and self.fused and H % 32 == 0:
-                st = StreamState(B * L, H, P["ffn"], dev)
-                s = fused_blocks(P["blocks"], mod, nt, st, xp, P["ws"], P["bs"], B, L, H, self.num_groups, pos,
-                                 Ww // p, ytxt=ytxt, T=T)
-                ni = 0
-            else:
-                s = ops.gemm(xp, P["ws"], P["bs"], ops.EPI_BIAS_F32)
-            if ni:
-                bufs = self._bufs(B * L, P, dev)
-                for i, bp in enumerate(P["blocks"]):
-                    self._block(bp, mod[:, (nt + i) * 6 * H:(nt + i + 1) * 6 * H], s, L, B, bufs, pos=pos, ytxt=ytxt, T=T)
-            s2 = ops.silu_add_rows(s, temb, L)
-            ycond = ops.gemm(s2, P["wcond"], P["bcond"], ops.EPI_BIAS)
-            return ops.pixel_decoder(x32, ycond, P["blob"], P["postab"], p, self.decoder_hidden_size,
-                                     self.num_decoder_blocks)
+        dev = xp.device
+        pos = self.fetch_pos(Hh // p, Ww // p, dev)
+        tfreq = ops.timestep_freq(t.reshape(-1).to(torch.float32), self.t_embedder.frequency_embedding_size)
+        h1 = ops.gemm(tfreq, P["wt0"], P["bt0"], ops.EPI_BIAS_SILU)
+        temb = ops.gemm(h1, P["wt2"], P["bt2"], ops.EPI_BIAS)                                   # [B, H]
+        c = ops.cond_combine(temb, P["zero_row"], torch.zeros(B, dtype=torch.int64, device=dev))  # silu(t)
+        nt, ni = len(P["text"]), len(P["blocks"])
+        mod = ops.gemm(c, P["wada"], P["bada"], ops.EPI_BIAS) if nt + ni else None              # [B, (nt+ni)*6H]
+        # ---- text path
+        y16 = y.detach().reshape(B * T, self.txt_embed_dim).to(bf16).contiguous()
+        yraw = ops.gemm(y16, P["wy"], P["by"], ops.EPI_BIAS_F32)
+        ys = ops.rmsnorm_addpos(yraw, P["yn"], P["ypos"])                                       # fp32 [B*T, H]
+        if nt:
+            bufs = self._bufs(B * T, P, dev)
+            for i, bp in enumerate(P["text"]):
+                self._block(bp, mod[:, i * 6 * H:(i + 1) * 6 * H], ys, T, B, bufs)
+        ytxt = ops.cast_bf16(ys)
+        # ---- image path
+        if ni and self.fused and H % 32 == 0:
+            st = StreamState(B * L, H, P["ffn"], dev, heads=self.num_groups)
+            s = fused_blocks(P["blocks"], mod, nt, st, xp, P["ws"], P["bs"], B, L, H, self.num_groups, pos,
+                             Ww // p, ytxt=ytxt, T=T)
+            ni = 0
+        else:
+            s = ops.gemm(xp, P["ws"], P["bs"], ops.EPI_BIAS_F32)
+        if ni:
+            bufs = self._bufs(B * L, P, dev)
+            for i, bp in enumerate(P["blocks"]):
+                self._block(bp, mod[:, (nt + i) * 6 * H:(nt + i + 1) * 6 * H], s, L, B, bufs, pos=pos, ytxt=ytxt, T=T)
+        return ops.silu_add_rows(s, temb, L)

@@ -104,13 +104,16 @@ def gemm_stream(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], 
 def gemm_norm_qkv(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, rows_per_image: int, heads: int, head_dim: int,
                   seg_w=(None, None, None), rope_mask: int = 0, rope: Optional[torch.Tensor] = None,
                   rope_tokens_per_row: int = 0, ssq: Optional[torch.Tensor] = None, norm_hidden: int = 0, shw: Optional[torch.Tensor] = None,
-                  norm_eps: float = 1e-6, head_eps: float = 1e-6) -> torch.Tensor:
-    """out = headnorm/rope(rstd * (a @ w.T) + shw[row // rows_per_image]) (csrc/gemm_fused.cu FE_NORM_QKV)."""
+                  norm_eps: float = 1e-6, head_eps: float = 1e-6, out_head_pitch: int = 0) -> torch.Tensor:
+    """out = headnorm/rope(rstd * (a @ w.T) + shw[row // rows_per_image]) (csrc/gemm_fused.cu FE_NORM_QKV).
+    out_head_pitch: output columns per head (0 = head_dim); 80 for head_dim 72 writes zero-padded, sector-aligned heads
+    (out is then [M, N / head_dim * 80])."""
     _cuda(a, w, out, rope, ssq, shw, *seg_w)
     assert a.dtype == bf16 and w.dtype == bf16 and a.stride(1) == 1 and w.stride(1) == 1
     M, K = a.shape
     N = w.shape[0]
-    assert w.shape[1] == K and out.dtype == bf16 and out.shape == (M, N) and out.stride(1) == 1
+    n_out = N // head_dim * (out_head_pitch or head_dim)
+    assert w.shape[1] == K and out.dtype == bf16 and out.shape == (M, n_out) and out.stride(1) == 1
     if ssq is not None:
         assert ssq.dtype == torch.float32 and ssq.is_contiguous() and ssq.dim() == 2 and ssq.shape[1] == M
     if shw is not None:
@@ -125,7 +128,7 @@ def gemm_norm_qkv(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, rows_per_
     call("deco_gemm_norm_qkv", ptr(a), a.stride(0), ptr(w), w.stride(0), ptr(out), out.stride(0), M, N, K, rows_per_image,
          ptr(ssq), ssq.shape[0] if ssq is not None else 0, norm_hidden, float(norm_eps), ptr(shw),
          shw.stride(0) if shw is not None else 0, heads, head_dim, ptr(sw[0]), ptr(sw[1]), ptr(sw[2]), rope_mask,
-         ptr(rope), int(rope_tokens_per_row), float(head_eps), _st(a))
+         ptr(rope), int(rope_tokens_per_row), float(head_eps), int(out_head_pitch), _st(a))
     if probe is not None:
         probe.after(ev, 2.0 * M * N * K)
     return out
@@ -256,13 +259,15 @@ def cast_bf16(x: torch.Tensor) -> torch.Tensor:
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, heads: int, head_dim: int,
               k2: Optional[torch.Tensor] = None, v2: Optional[torch.Tensor] = None,
-              out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """q [B*Lq, heads*d] view, k/v [B*Lk, heads*d] views (row strides free), optional second KV segment.
-    Returns out [B*Lq, heads*d]."""
+              out: Optional[torch.Tensor] = None, head_pitch: int = 0, head_pitch2: int = 0) -> torch.Tensor:
+    """q [B*Lq, heads*pitch] view, k/v [B*Lk, heads*pitch] views (row strides free), optional second KV segment.
+    head_pitch: elements between consecutive heads of a q / k / v row (0 = head_dim, dense heads); head_pitch2: the same
+    for k2 / v2.  Returns out [B*Lq, heads*d] (dense)."""
     _cuda(q, k, v, k2, v2)
     Hd = heads * head_dim
+    Hp = heads * (head_pitch or head_dim)
     Lq, Lk = q.shape[0] // B, k.shape[0] // B
-    assert q.dtype == bf16 and q.shape[1] == Hd and k.shape[1] == Hd and v.shape == k.shape
+    assert q.dtype == bf16 and q.shape[1] == Hp and k.shape[1] == Hp and v.shape == k.shape
     assert k.stride(0) == v.stride(0)
     if out is None:
         out = torch.empty((q.shape[0], Hd), dtype=bf16, device=q.device)
@@ -270,6 +275,11 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, B: int, heads: 
     if k2 is not None:
         Lk2, s2 = k2.shape[0] // B, k2.stride(0)
         assert v2 is not None and v2.stride(0) == s2
+    if head_pitch or head_pitch2:
+        call("deco_attention_fwd_pitched", ptr(q), q.stride(0), head_pitch, ptr(k), ptr(v), k.stride(0), head_pitch, Lk,
+             ptr(k2), ptr(v2), s2, head_pitch2, Lk2, ptr(out), out.stride(0), B, heads, Lq, head_dim,
+             float(head_dim) ** -0.5, _st(q))
+        return out
     call("deco_attention_fwd", ptr(q), q.stride(0), ptr(k), ptr(v), k.stride(0), Lk, ptr(k2), ptr(v2), s2, Lk2,
          ptr(out), out.stride(0), B, heads, Lq, head_dim, float(head_dim) ** -0.5, _st(q))
     return out

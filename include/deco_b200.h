@@ -76,7 +76,9 @@ int deco_gemm_norm_qkv(const void* A, long long lda, const void* W, long long ld
                        const float* ssq_in, int ssq_parts, int norm_hidden, float norm_eps,
                        const float* shw, long long shw_stride,
                        int heads, int head_dim, const float* w_seg0, const float* w_seg1, const float* w_seg2,
-                       int rope_mask, const float* rope_cos_sin, int rope_tokens_per_row, float head_eps, void* stream);
+                       int rope_mask, const float* rope_cos_sin, int rope_tokens_per_row, float head_eps,
+                       int out_head_pitch /* output columns per head: 0 = head_dim (dense); 80 for head_dim 72 (zero padded) */,
+                       void* stream);
 
 /* SwiGLU up-projection of a normalised + modulated stream (dit_c2i_DeCo.py:113 on :209's modulate input): W rows
  * interleaved [16 x w1 | 16 x w3] as for DECO_EPI_SWIGLU; out bf16 [M, N/2]. */
@@ -172,6 +174,15 @@ int deco_flow_pair(const float* x, const float* eps, const float* coef, float* x
                    int B, long long per_image, void* stream);
 int deco_label_dropout(const long long* cond, const long long* uncond, const float* u, float p,
                        long long* out, int B, void* stream);
+
+/* deco_attention_fwd with explicit head pitches: heads of a q / k / v row sit *_head_pitch elements apart (0 = head_dim,
+ * the dense [head][d] row).  The fused QKV GEMM (deco_gemm_norm_qkv with out_head_pitch = 80) writes head_dim-72 heads at a
+ * pitch of 80 so that the 16-column TMA boxes of the attention operands are aligned 32-byte sectors. */
+int deco_attention_fwd_pitched(const void* q, long long q_stride, int q_head_pitch,
+                               const void* k0, const void* v0, long long kv0_stride, int kv0_head_pitch, int Lk0,
+                               const void* k1, const void* v1, long long kv1_stride, int kv1_head_pitch, int Lk1,
+                               void* out, long long out_stride,
+                               int B, int heads, int Lq, int head_dim, float scale, void* stream);
 
 /* s = silu(t + s) (dit_c2i_DeCo.py:499): out[m,:] = silu(x[m,:] + row[m / rows_per,:]); out may alias x */
 int deco_silu_add_rows(const void* x, int x_is_f32, const void* row_bf16, void* out_bf16, long long M, int hidden,

@@ -353,6 +353,18 @@ def test_gemm_norm_qkv(cuda_dev, heads, d, hw, B, K, nseg, normed, axial):
     g = out.view(ref.shape).float()
     for s in range(nseg):
         assert rel_l2(g[:, :, s], ref[:, :, s]) < 6e-3, s
+    if normed and d == 72:
+        # the padded layout the sampling path uses: heads at a pitch of 80 columns, columns 72..79 zero, values identical;
+        # and the attention kernel reads it through its pitched tensor maps with the same result as from the dense layout
+        outp = torch.full((M, nseg * heads * 80), 7.0, device=cuda_dev, dtype=bf16)
+        ops.gemm_norm_qkv(xg, w, outp, L, heads, d, seg_w=(qw, kw, None), rope_mask=3, rope=rope,
+                          rope_tokens_per_row=(hw[1] if axial else 0), ssq=ssq, norm_hidden=K, shw=shw, out_head_pitch=80)
+        gp = outp.view(M, nseg, heads, 80)
+        assert torch.equal(gp[..., :72].reshape(M, N), out) and float(gp[..., 72:].abs().max()) == 0.0
+        Hd, Hp = heads * d, heads * 80
+        o_dense = ops.attention(out[:, :Hd], out[:, Hd:2 * Hd], out[:, 2 * Hd:], B, heads, d)
+        o_pitch = ops.attention(outp[:, :Hp], outp[:, Hp:2 * Hp], outp[:, 2 * Hp:], B, heads, d, head_pitch=80)
+        assert torch.equal(o_dense, o_pitch)
 
 
 @pytest.mark.parametrize("M,F_,K,L", [(512, 3072, 1152, 256), (300, 592, 576, 100), (640, 2736, 1024, 64), (256, 6144, 1536, 128)])
