@@ -52,6 +52,7 @@ SIGNATURES = {
     "deco_unpatchify": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "deco_opt_chunk_elems": (_i, []),
     "deco_adamw_ema_step": (_i, [_vp, _vp, _i, _f, _f, _f, _f, _f, _f, _f, _f, _vp]),
+    "deco_dct_scratch_doubles": (_i, []),
     "deco_dct_fm_loss": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp]),
     "deco_transpose_cast": (_i, [_vp, _i, _ll, _vp, _ll, _i, _i, _i, _vp]),
     "deco_colsum": (_i, [_vp, _i, _ll, _vp, _ll, _i, _vp]),

@@ -239,22 +239,43 @@ template <> __device__ __forceinline__ void store_row8<__nv_bfloat16>(__nv_bfloa
     *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf2(v[0], v[1]), pack_bf2(v[2], v[3]), pack_bf2(v[4], v[5]), pack_bf2(v[6], v[7]));
 }
 
+constexpr int kDctMaxCtas = 148 * 8 * 2;          // per-CTA partial-sum slots in the scratch (grid never exceeds 8 CTAs per SM)
+
+// Persistent, balanced grid: the 8 x 128 strips are dealt to the CTAs in equal shares (launch_dct sizes the grid so that
+// every CTA gets the same number of strips whenever the strip count allows it: no partial last wave), a CTA accumulates its
+// partial sums in registers over all its strips and leaves them in ITS slot of the scratch -- no floating-point atomics, so
+// the loss is bit-reproducible run to run -- and takes a ticket; the last CTA adds the slots up in a fixed order,
+// publishes the three losses and clears the ticket: forward + backward stay ONE launch.  (The first version did two double
+// atomicAdds and a ticket per strip on the same three addresses: at 32 images the 6144 serialised L2 atomics, not HBM,
+// set the kernel's duration.)
 template <typename TOut, bool kLoss, bool kGrad>
 __global__ void __launch_bounds__(kTileW, 8) dct_fm_loss_vec_kernel(
     const TOut* __restrict__ out, const float* __restrict__ vt, const float* __restrict__ freq_w,
     TOut* __restrict__ grad, double* __restrict__ accum, float* __restrict__ losses, const float* __restrict__ upstream,
-    int H, int W, float fm_scale, float freq_scale, float freq_loss_weight, double inv_fm, double inv_fq)
+    int H, int W, int tiles_x, int tiles_y, int ntiles, int tiles_per_cta,
+    float fm_scale, float freq_scale, float freq_loss_weight, double inv_fm, double inv_fq)
 {
     __shared__ __align__(16) float Z[3][8][kZs];
     __shared__ float red[2][kTileW / 32];
+    __shared__ float fw[3 * 64];
+    __shared__ int is_last;
 
     const int tid = threadIdx.x;
-    const int b = blockIdx.z;
-    const int r0 = blockIdx.y * 8;
     const int r = tid >> 4, bx = tid & 15;
-    const int c0 = blockIdx.x * kTileW + bx * 8;
-    const bool ok = c0 < W;                       // W % 8 == 0: a block is inside or outside as a whole
     const size_t plane = (size_t)H * W;
+    for (int i = tid; i < 3 * 64; i += kTileW) fw[i] = __ldg(freq_w + i);
+    float fm_part = 0.f, fq_part = 0.f;
+    const int t_begin = blockIdx.x * tiles_per_cta;
+    const int t_end = min(ntiles, t_begin + tiles_per_cta);
+
+    for (int tile = t_begin; tile < t_end; ++tile) {
+    const int txy = tiles_x * tiles_y;
+    const int b = tile / txy;
+    const int rem = tile - b * txy;
+    const int ty = rem / tiles_x, tx = rem - ty * tiles_x;
+    const int r0 = ty * 8;
+    const int c0 = tx * kTileW + bx * 8;
+    const bool ok = c0 < W;                       // W % 8 == 0: a block is inside or outside as a whole
     const size_t o = (size_t)b * 3 * plane + (size_t)(r0 + r) * W + c0;
 
     float d[3][8];                                // out - v_t per RGB plane, kept for the FM gradient
@@ -272,11 +293,11 @@ __global__ void __launch_bounds__(kTileW, 8) dct_fm_loss_vec_kernel(
 #pragma unroll
             for (int j = 0; j < 8; ++j) d[ch][j] = a[ch][j] - v[ch][j];
     }
-    float fm_part = 0.f;
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch)
 #pragma unroll
         for (int j = 0; j < 8; ++j) fm_part = fmaf(d[ch][j], d[ch][j], fm_part);
+    __syncthreads();                              // the previous strip's pass 3 has finished reading Z (and fw is staged)
     {
         float ycc[3][8];
 #pragma unroll
@@ -296,7 +317,6 @@ __global__ void __launch_bounds__(kTileW, 8) dct_fm_loss_vec_kernel(
     }
     __syncthreads();
     // ---- pass 2: vertical transform on column tid (horizontal frequency l = tid % 8)
-    float fq_part = 0.f;
     {
         const int l = tid & 7;
 #pragma unroll
@@ -308,7 +328,7 @@ __global__ void __launch_bounds__(kTileW, 8) dct_fm_loss_vec_kernel(
             float g[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                const float w = __ldg(freq_w + ch * 64 + k * 8 + l);
+                const float w = fw[ch * 64 + k * 8 + l];
                 fq_part = fmaf(w * y[k], y[k], fq_part);
                 g[k] = w * y[k];
             }
@@ -320,54 +340,72 @@ __global__ void __launch_bounds__(kTileW, 8) dct_fm_loss_vec_kernel(
             }
         }
     }
+    if (kGrad) {
+        __syncthreads();
+        if (ok) {
+            const float up = upstream ? __ldg(upstream) : 1.0f;
+            const float kf = up * freq_loss_weight * 2.0f * freq_scale;
+            const float km = up * 2.0f * fm_scale;
+            float gy[3][8];
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                const float4* zp = reinterpret_cast<const float4*>(&Z[ch][r][bx * 8]);
+                const float4 z0 = zp[0], z1 = zp[1];
+                const float y[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+                dct8_bwd(y, gy[ch]);
+            }
+            float gr[8], gg[8], gb[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float a0 = gy[0][j] * kf, a1 = gy[1][j] * kf, a2 = gy[2][j] * kf;
+                gr[j] = fmaf(km, d[0][j], 0.299f * a0 - 0.168736f * a1 + 0.5f * a2);
+                gg[j] = fmaf(km, d[1][j], 0.587f * a0 - 0.331264f * a1 - 0.418688f * a2);
+                gb[j] = fmaf(km, d[2][j], 0.114f * a0 + 0.5f * a1 - 0.081312f * a2);
+            }
+            store_row8<TOut>(grad + o, gr);
+            store_row8<TOut>(grad + o + plane, gg);
+            store_row8<TOut>(grad + o + 2 * plane, gb);
+        }
+    }
+    }   // strips of this CTA
+
     if (kLoss) {
         fm_part = warp_sum(fm_part);
         fq_part = warp_sum(fq_part);
         if ((tid & 31) == 0) { red[0][tid >> 5] = fm_part; red[1][tid >> 5] = fq_part; }
-    }
-    __syncthreads();
-    if (kGrad && ok) {
-        const float up = upstream ? __ldg(upstream) : 1.0f;
-        const float kf = up * freq_loss_weight * 2.0f * freq_scale;
-        const float km = up * 2.0f * fm_scale;
-        float gy[3][8];
+        __syncthreads();
+        double* slots = accum + 4;                // [gridDim.x][2]
+        if (tid == 0) {
+            float a = 0.f, q = 0.f;
 #pragma unroll
-        for (int ch = 0; ch < 3; ++ch) {
-            const float4* zp = reinterpret_cast<const float4*>(&Z[ch][r][bx * 8]);
-            const float4 z0 = zp[0], z1 = zp[1];
-            const float y[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
-            dct8_bwd(y, gy[ch]);
-        }
-        float gr[8], gg[8], gb[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float a0 = gy[0][j] * kf, a1 = gy[1][j] * kf, a2 = gy[2][j] * kf;
-            gr[j] = fmaf(km, d[0][j], 0.299f * a0 - 0.168736f * a1 + 0.5f * a2);
-            gg[j] = fmaf(km, d[1][j], 0.587f * a0 - 0.331264f * a1 - 0.418688f * a2);
-            gb[j] = fmaf(km, d[2][j], 0.114f * a0 + 0.5f * a1 - 0.081312f * a2);
-        }
-        store_row8<TOut>(grad + o, gr);
-        store_row8<TOut>(grad + o + plane, gg);
-        store_row8<TOut>(grad + o + 2 * plane, gb);
-    }
-    if (kLoss && tid == 0) {
-        float a = 0.f, q = 0.f;
-#pragma unroll
-        for (int i = 0; i < kTileW / 32; ++i) { a += red[0][i]; q += red[1][i]; }
-        atomicAdd(accum + 0, (double)a);
-        atomicAdd(accum + 1, (double)q);
-        __threadfence();
-        unsigned int* ticket = reinterpret_cast<unsigned int*>(accum + 2);
-        const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
-        if (atomicAdd(ticket, 1u) == total - 1) {
-            // last CTA: every partial sum is visible (fence + atomic ticket); publish and leave the scratch zeroed
+            for (int i = 0; i < kTileW / 32; ++i) { a += red[0][i]; q += red[1][i]; }
+            slots[2 * blockIdx.x] = (double)a;
+            slots[2 * blockIdx.x + 1] = (double)q;
             __threadfence();
-            const double fm = atomicAdd(accum + 0, 0.0) * inv_fm, fq = atomicAdd(accum + 1, 0.0) * inv_fq;
-            losses[0] = (float)fm;
-            losses[1] = (float)fq;
-            losses[2] = (float)(fm + (double)freq_loss_weight * fq);
-            accum[0] = 0.0; accum[1] = 0.0;
-            *ticket = 0u;
+            unsigned int* ticket = reinterpret_cast<unsigned int*>(accum + 2);
+            is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+        }
+        __syncthreads();
+        if (is_last) {
+            // every CTA's slot is visible (fence + atomic ticket); fixed summation order: thread-strided, then a tree
+            __threadfence();
+            __shared__ double part[2][kTileW];
+            double a = 0.0, q = 0.0;
+            const volatile double* vs = slots;
+            for (int i = tid; i < (int)gridDim.x; i += kTileW) { a += vs[2 * i]; q += vs[2 * i + 1]; }
+            part[0][tid] = a; part[1][tid] = q;
+            __syncthreads();
+            for (int sft = kTileW / 2; sft > 0; sft >>= 1) {
+                if (tid < sft) { part[0][tid] += part[0][tid + sft]; part[1][tid] += part[1][tid + sft]; }
+                __syncthreads();
+            }
+            if (tid == 0) {
+                const double fm = part[0][0] * inv_fm, fq = part[1][0] * inv_fq;
+                losses[0] = (float)fm;
+                losses[1] = (float)fq;
+                losses[2] = (float)(fm + (double)freq_loss_weight * fq);
+                *reinterpret_cast<unsigned int*>(accum + 2) = 0u;      // scratch contract: zero again on exit
+            }
         }
     }
 }
@@ -423,8 +461,17 @@ static int launch_dct(const TOut* out, const float* vt, const float* freq_w, TOu
         else DCT_LAUNCH(true, true, false);
     } else {
         // scratch contract of the one-launch path: accum[0..2] are zero on entry and zero again on exit
-#define DCT_VEC(L, G) dct_fm_loss_vec_kernel<TOut, L, G><<<grid, block, 0, st>>>( \
-        out, vt, freq_w, grad, accum, losses, upstream, H, W, fms, fqs, flw, 1.0 / n_fm, 1.0 / n_fq)
+        // equal shares: t strips per CTA with t = ceil(strips / resident CTA slots); grid = ceil(strips / t)
+        const int tiles_x = (W2 + kTileW - 1) / kTileW, tiles_y = H2 / 8;
+        const long long ntiles_ll = (long long)tiles_x * tiles_y * B;
+        if (ntiles_ll > 0x7fffffffLL) { deco_set_error("dct_fm_loss: too many strips"); return DECO_ERR_ARG; }
+        const int ntiles = (int)ntiles_ll;
+        const int resident = device_sm_count() * 8;
+        const int per = (ntiles + resident - 1) / resident;
+        const int nctas = (ntiles + per - 1) / per;               // <= resident <= kDctMaxCtas
+        if (nctas > kDctMaxCtas) { deco_set_error("dct_fm_loss: grid exceeds the scratch slots"); return DECO_ERR_ARG; }
+#define DCT_VEC(L, G) dct_fm_loss_vec_kernel<TOut, L, G><<<nctas, block, 0, st>>>( \
+        out, vt, freq_w, grad, accum, losses, upstream, H, W, tiles_x, tiles_y, ntiles, per, fms, fqs, flw, 1.0 / n_fm, 1.0 / n_fq)
         if (want_loss && want_grad) DCT_VEC(true, true);
         else if (want_grad) DCT_VEC(false, true);
         else DCT_VEC(true, false);
@@ -442,6 +489,10 @@ static int launch_dct(const TOut* out, const float* vt, const float* freq_w, TOu
 }
 
 }  // namespace deco
+
+// doubles of scratch deco_dct_fm_loss needs: {fm, freq} accumulators of the ragged path, the ticket, padding, then one
+// {fm, freq} slot per CTA of the persistent kernel
+extern "C" int deco_dct_scratch_doubles(void) { return 4 + 2 * deco::kDctMaxCtas; }
 
 extern "C" int deco_dct_fm_loss(const void* out, int out_is_bf16, const float* v_t, const float* freq_w,
                                 int B, int H, int W, float freq_loss_weight,

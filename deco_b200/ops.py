@@ -460,12 +460,13 @@ _DCT_SCRATCH = {}
 
 
 def _dct_scratch(device) -> torch.Tensor:
-    """3 zeroed doubles per (device, stream): the kernel leaves them zero again (include/deco_b200.h)."""
+    """Zeroed scratch (deco_dct_scratch_doubles doubles) per (device, stream): the kernel leaves its first three words zero
+    again (include/deco_b200.h)."""
     key = (device.index if device.index is not None else torch.cuda.current_device(),
            torch.cuda.current_stream(device).cuda_stream)
     buf = _DCT_SCRATCH.get(key)
     if buf is None:
-        buf = _DCT_SCRATCH[key] = torch.zeros(3, dtype=torch.float64, device=device)
+        buf = _DCT_SCRATCH[key] = torch.zeros(_lib.load().deco_dct_scratch_doubles(), dtype=torch.float64, device=device)
     return buf
 
 

@@ -245,9 +245,11 @@ int deco_unpatchify(const void* tok_bf16, void* out_bf16, int B, int C, int H, i
  * (flow_matching/training_repa_DeCo.py:106-136 _rgb2ycbcr/_dct, :138-195 weights, :273-285 loss):
  *   losses[0] = mean((out - v_t)^2), losses[1] = mean(freq_w * dct(ycbcr(out - v_t))^2), losses[2] = [0] + flw * [1]
  *   grad = upstream * d losses[2] / d out   (same dtype as out; fp32 required for ragged H/W)
- * out [B,3,H,W] fp32 or bf16; v_t fp32; freq_w fp32 [3,8,8]; accum = 3 doubles of scratch that must be ZERO on entry and
- * are zero again on exit (the last CTA publishes the losses and clears them: forward + backward is one launch);
- * losses and/or grad may be NULL; upstream = device scalar or NULL (1.0). */
+ * out [B,3,H,W] fp32 or bf16; v_t fp32; freq_w fp32 [3,8,8]; accum = deco_dct_scratch_doubles() doubles of scratch whose
+ * first three must be ZERO on entry and are zero again on exit (every CTA leaves its partial sums in its own slot, the last
+ * one adds them in a fixed order -- the losses are bit-reproducible -- publishes and clears the ticket: forward + backward
+ * is one launch); losses and/or grad may be NULL; upstream = device scalar or NULL (1.0). */
+int deco_dct_scratch_doubles(void);
 int deco_dct_fm_loss(const void* out, int out_is_bf16, const float* v_t, const float* freq_w,
                      int B, int H, int W, float freq_loss_weight,
                      float* losses, void* grad, const float* upstream, double* accum, void* stream);

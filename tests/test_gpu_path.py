@@ -246,6 +246,9 @@ def test_dct_loss_full_size_properties(cuda_dev):
     a = torch.randn((32, 3, 256, 256), generator=gen).to(cuda_dev)
     b = torch.randn((32, 3, 256, 256), generator=gen).to(cuda_dev)
     l_ab, g_ab = ops.dct_fm_loss(a, b, fw, 1.0, want_grad=True)
+    for _ in range(3):                                                 # no floating-point atomics: bit-reproducible losses
+        l_rep, g_rep = ops.dct_fm_loss(a, b, fw, 1.0, want_grad=True)
+        assert torch.equal(l_rep, l_ab) and torch.equal(g_rep, g_ab)
     l_ba, g_ba = ops.dct_fm_loss(b, a, fw, 1.0, want_grad=True)
     assert torch.allclose(l_ab, l_ba, rtol=1e-6)                       # symmetry
     assert rel_l2(g_ab, -g_ba) < 1e-6                                  # antisymmetric gradient
