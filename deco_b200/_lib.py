@@ -48,6 +48,8 @@ SIGNATURES = {
     "deco_cfg_step_dev": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _vp]),
     "deco_cfg_step_ex": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _f, _vp,
                               _vp, _vp, _vp, _vp, _ll, _vp]),
+    "deco_heun_sde_step": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _f, _f, _f, _f, _f, _f, _f, _f, _i, _vp, _vp, _vp, _vp, _vp,
+                                _ll, _vp]),
     "deco_layernorm_modulate": (_i, [_vp, _vp, _vp, _ll, _i, _vp, _ll, _i, _f, _vp]),
     "deco_unpatchify": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "deco_opt_chunk_elems": (_i, []),
@@ -69,7 +71,8 @@ SIGNATURES = {
     "deco_attention_bwd": (_i, [_vp, _ll, _vp, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _vp, _ll, _vp, _vp,
                                 _i, _i, _i, _i, _i, _i, _f, _vp]),
     "deco_decoder_tc_blob_bytes": (_i, [_i]),
-    "deco_pixel_decoder_tc": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _f, _f, _f, _f, _vp, _vp, _vp, _vp, _vp]),
+    "deco_pixel_decoder_tc": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _f, _f, _f, _f, _vp, _vp, _vp, _vp, _vp,
+                                   _vp]),
     "deco_train_timesteps": (_i, [_vp, _vp, _vp, _f, _i, _vp, _vp, _i, _vp]),
     "deco_flow_pair": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _ll, _vp]),
     "deco_label_dropout": (_i, [_vp, _vp, _vp, _f, _vp, _i, _vp]),

@@ -97,7 +97,9 @@ struct Params {
     long long tokens_half;       // B * L
     const float* dev;            // device {g, dt, c0, c1} or null (then the host scalars below)
     float g, dt, c0, c1;
-    const float* p1;             // previous prediction (Adams order 2) or null
+    const float* x_base;         // state the update is applied to, or null (= x).  Heun corrector: the net sees x_hat, the
+                                 // update x + dt (v + v_hat) / 2 starts from x (sampling.py:289-291)
+    const float* p1;             // previous prediction (Adams order 2, Heun predictor velocity) or null
     float* x_out;                // new state (may alias x)
     float* pred_out;             // optional: guided prediction (may alias p1)
     uint8_t* u8_out;             // optional: fp2uint8(new state)
@@ -520,7 +522,7 @@ pixel_decoder_tc_kernel(const __grid_constant__ CUtensorMap ymap, const Params P
                     const float pred = fmaf(g_, o[c] - u_keep[c], u_keep[c]);
                     float v = c0_ * pred;
                     if (P.p1) v = fmaf(c1_, P.p1[ob], v);
-                    const float xn = fmaf(dt_, v, rgb[c]);
+                    const float xn = fmaf(dt_, v, P.x_base ? P.x_base[ob] : rgb[c]);
                     P.x_out[ob] = xn;
                     if (P.pred_out) P.pred_out[ob] = pred;
                     if (P.u8_out) P.u8_out[ob] = to_u8(xn);
@@ -542,11 +544,13 @@ extern "C" int deco_decoder_tc_blob_bytes(int num_res_blocks) { return (int)dtc:
 
 // ysilu: bf16 [tokens, 256 * 32] = silu(cond_embed(s)) (the cond_embed GEMM with the SiLU epilogue); blob: packed by
 // deco_b200/denoiser.py::pack_decoder_tc.  pair = 0: out [rows, 3, H, W] = decoder(x rows).  pair != 0: rows = 2B stacked
-// [uncond || cond] over the SAME image state x [B, 3, H, W]; the guided multistep update is applied to x (-> x_out).
+// [uncond || cond] over the SAME image state x [B, 3, H, W]; the guided multistep update is applied to x_base (NULL = x)
+// and written to x_out.
 extern "C" int deco_pixel_decoder_tc(const float* x, const void* ysilu_bf16, const void* blob, void* out, int out_is_bf16,
                                      int rows, int H, int W, int patch, int hidden_x, int num_res_blocks,
                                      int pair, const float* dev_scalars, float g, float dt, float c0, float c1,
-                                     const float* p1, float* x_out, float* pred_out, void* u8_out, void* stream)
+                                     const float* x_base, const float* p1, float* x_out, float* pred_out, void* u8_out,
+                                     void* stream)
 {
     using namespace deco::dtc;
     DECO_CHECK_ARG(x && ysilu_bf16 && blob, "pixel_decoder_tc: null pointer");
@@ -566,7 +570,7 @@ extern "C" int deco_pixel_decoder_tc(const float* x, const void* ysilu_bf16, con
     P.pair = pair ? 1 : 0;
     P.tokens_half = P.tokens / 2;
     P.dev = dev_scalars; P.g = g; P.dt = dt; P.c0 = c0; P.c1 = c1;
-    P.p1 = p1; P.x_out = x_out; P.pred_out = pred_out; P.u8_out = (uint8_t*)u8_out;
+    P.x_base = x_base; P.p1 = p1; P.x_out = x_out; P.pred_out = pred_out; P.u8_out = (uint8_t*)u8_out;
     DECO_CHECK_ARG(P.tokens * 256 < (1LL << 31), "pixel_decoder_tc: too many pixel rows for one launch (%lld tokens)", P.tokens);
 
     PFN_encodeTiled enc = get_tensormap_encoder();

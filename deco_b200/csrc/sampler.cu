@@ -138,7 +138,99 @@ __global__ void __launch_bounds__(256) fp2uint8_kernel(const float* __restrict__
     }
 }
 
+// Heun predictor / corrector with the SDE step functions (src/diffusion/flow_matching/sampling.py:17-24, :266-293):
+//   s      = s_in ? s_in : (kd v - x) / sden                       score at (x, t_cur), or the one kept from the last corrector
+//   predictor:  x_out = x + dt v + a_s s + a_n z
+//   corrector:  v_hat = u + g (c - u);  s_hat = (kdh v_hat - x_hat) / sdenh        (network evaluated at (x_hat, t_next))
+//               x_out = x + dt (v + v_hat) / 2 + a_s (s + s_hat) / 2 + a_n z ;  v_hat, s_hat stored for the next predictor
+// Bound: HBM (corrector: x, x_hat, v fp32 + 2 x bf16 net rows + z read, x_out / v_hat / s_hat written = 36 B per element).
+struct HeunSdeArgs {
+    const float* x; const float* v; const float* s_in; const void* net_out; const float* x_hat; const float* noise;
+    float g, dt, kd, sden, kdh, sdenh, a_s, a_n;
+    int corrector;
+    float* x_out; float* v_hat_out; float* s_hat_out; float* v_avg_out; uint8_t* u8_out;
+    long long n;
+};
+
+template <typename TNet>
+__global__ void __launch_bounds__(256) heun_sde_step_kernel(HeunSdeArgs a) {
+    const long long n4 = a.n >> 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 x4 = reinterpret_cast<const float4*>(a.x)[i];
+        const float4 v4 = reinterpret_cast<const float4*>(a.v)[i];
+        const float xs[4] = {x4.x, x4.y, x4.z, x4.w}, vs[4] = {v4.x, v4.y, v4.z, v4.w};
+        float ss[4];
+        if (a.s_in) {
+            const float4 s4 = reinterpret_cast<const float4*>(a.s_in)[i];
+            ss[0] = s4.x; ss[1] = s4.y; ss[2] = s4.z; ss[3] = s4.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) ss[e] = (a.kd * vs[e] - xs[e]) / a.sden;
+        }
+        float zs[4] = {0.f, 0.f, 0.f, 0.f};
+        if (a.a_n != 0.f) {
+            const float4 z4 = __ldg(reinterpret_cast<const float4*>(a.noise) + i);
+            zs[0] = z4.x; zs[1] = z4.y; zs[2] = z4.z; zs[3] = z4.w;
+        }
+        float ve[4], se[4], vh[4], sh[4];
+        if (a.corrector) {
+            const float4 u4 = Vec4<TNet>::load(a.net_out, i), c4 = Vec4<TNet>::load(a.net_out, i + n4);
+            const float4 h4 = reinterpret_cast<const float4*>(a.x_hat)[i];
+            const float us[4] = {u4.x, u4.y, u4.z, u4.w}, cs[4] = {c4.x, c4.y, c4.z, c4.w}, hs[4] = {h4.x, h4.y, h4.z, h4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                vh[e] = us[e] + a.g * (cs[e] - us[e]);
+                sh[e] = (a.kdh * vh[e] - hs[e]) / a.sdenh;
+                ve[e] = (vs[e] + vh[e]) * 0.5f;
+                se[e] = (ss[e] + sh[e]) * 0.5f;
+            }
+            if (a.v_hat_out) reinterpret_cast<float4*>(a.v_hat_out)[i] = make_float4(vh[0], vh[1], vh[2], vh[3]);
+            if (a.s_hat_out) reinterpret_cast<float4*>(a.s_hat_out)[i] = make_float4(sh[0], sh[1], sh[2], sh[3]);
+            if (a.v_avg_out) reinterpret_cast<float4*>(a.v_avg_out)[i] = make_float4(ve[0], ve[1], ve[2], ve[3]);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { ve[e] = vs[e]; se[e] = ss[e]; }
+        }
+        float xo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) xo[e] = fmaf(a.a_n, zs[e], fmaf(a.a_s, se[e], fmaf(a.dt, ve[e], xs[e])));
+        reinterpret_cast<float4*>(a.x_out)[i] = make_float4(xo[0], xo[1], xo[2], xo[3]);
+        if (a.u8_out) reinterpret_cast<uchar4*>(a.u8_out)[i] = make_uchar4(to_u8(xo[0]), to_u8(xo[1]), to_u8(xo[2]), to_u8(xo[3]));
+    }
+}
+
 }  // namespace deco
+
+// Heun step with an SDE step function (see heun_sde_step_kernel).  corrector == 0: predictor / last step from (x, v, s);
+// corrector != 0: net_out [2n] rows [uncond || cond] evaluated at (x_hat, t_next).  s_in NULL = score from (x, v, kd, sden).
+// x_out must not alias x when the caller still needs x (the corrector of the same step does).
+extern "C" int deco_heun_sde_step(const float* x, const float* v, const float* s_in, const void* net_out, int net_is_bf16,
+                                  const float* x_hat, const float* noise, float g, float dt, float kd, float sden,
+                                  float kdh, float sdenh, float a_s, float a_n, int corrector,
+                                  float* x_out, float* v_hat_out, float* s_hat_out, float* v_avg_out, uint8_t* u8_out,
+                                  long long n, void* stream)
+{
+    using namespace deco;
+    DECO_CHECK_ARG(x && v && x_out, "heun_sde_step: null input");
+    DECO_CHECK_ARG(n > 0 && (n % 4) == 0, "heun_sde_step: element count %lld must be a positive multiple of 4", n);
+    DECO_CHECK_ARG(!corrector || (net_out && x_hat && sdenh != 0.f), "heun_sde_step: the corrector needs net_out, x_hat, sdenh");
+    DECO_CHECK_ARG(a_n == 0.f || noise, "heun_sde_step: a_n != 0 needs a noise tensor");
+    DECO_CHECK_ARG(s_in || sden != 0.f, "heun_sde_step: zero score denominator");
+    HeunSdeArgs a;
+    a.x = x; a.v = v; a.s_in = s_in; a.net_out = net_out; a.x_hat = x_hat; a.noise = noise;
+    a.g = g; a.dt = dt; a.kd = kd; a.sden = sden; a.kdh = kdh; a.sdenh = sdenh; a.a_s = a_s; a.a_n = a_n;
+    a.corrector = corrector ? 1 : 0;
+    a.x_out = x_out; a.v_hat_out = v_hat_out; a.s_hat_out = s_hat_out; a.v_avg_out = v_avg_out; a.u8_out = u8_out; a.n = n;
+    const long long n4 = n / 4;
+    long long blocks = (n4 + 255) / 256;
+    const long long cap = (long long)kNumSMs * 16;
+    if (blocks > cap) blocks = cap;
+    if (net_is_bf16) heun_sde_step_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+    else heun_sde_step_kernel<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+    DECO_CHECK_LAUNCH("heun_sde_step_kernel");
+    return DECO_OK;
+}
 
 extern "C" int deco_cfg_step(const float* x, const void* net_out, int net_is_bf16,
                              const float* p1, const float* p2, const float* p3,

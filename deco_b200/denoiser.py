@@ -614,7 +614,7 @@ class PixNerDiT(nn.Module):
 
     @torch.no_grad()
     def cfg_step(self, x, t2, cfg_condition, dev=None, g=1.0, dt=0.0, c0=1.0, c1=0.0, p1=None, x_out=None,
-                 pred_out=None, u8_out=None):
+                 pred_out=None, u8_out=None, x_base=None):
         """One CFG-batched sampler step with the update fused into the decoder epilogue (north_star (4)): evaluates the
         rows [uncond || cond] = net(cat[x, x], t2, cfg_condition) (sampling.py:89-97) WITHOUT materialising cat[x, x] or
         the bf16 network output, and writes x_out = x + dt (c0 pred + c1 p1), pred = u + g (c - u) (guidance.py:3-6,
@@ -637,7 +637,7 @@ class PixNerDiT(nn.Module):
         ysilu = ops.gemm(s2, P["wcond"], P["bcond"], ops.EPI_BIAS_SILU)
         return ops.pixel_decoder_tc_step(x32, ysilu, P["blob_tc"], p, self.hidden_size_x, self.num_blocks - self.num_cond_blocks,
                                          dev=dev, g=g, dt=dt, c0=c0, c1=c1, p1=p1, x_out=x_out, pred_out=pred_out,
-                                         u8_out=u8_out)
+                                         u8_out=u8_out, x_base=x_base)
 
     def forward(self, x, t, y, s=None, mask=None):
         """x [B,C,H,W], t [B] in [0,1], y [B] int64 (num_classes = null) -> velocity [B,C,H,W] (bf16, as the

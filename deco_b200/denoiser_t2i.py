@@ -259,7 +259,7 @@ class PixNerDiT(nn.Module):
 
     @torch.no_grad()
     def cfg_step(self, x, t2, cfg_condition, dev=None, g=1.0, dt=0.0, c0=1.0, c1=0.0, p1=None, x_out=None,
-                 pred_out=None, u8_out=None):
+                 pred_out=None, u8_out=None, x_base=None):
         """CFG-batched sampler step with guidance + multistep update fused into the decoder epilogue (see
         deco_b200.denoiser.PixNerDiT.cfg_step): x fp32 [B,C,H,W], t2 [2B], cfg_condition [2B, T, txt_embed_dim] stacked
         [uncond || cond] (adam_sampling.py:101-117)."""
@@ -279,7 +279,7 @@ class PixNerDiT(nn.Module):
         ysilu = ops.gemm(s2, P["wcond"], P["bcond"], ops.EPI_BIAS_SILU)
         return ops.pixel_decoder_tc_step(x32, ysilu, P["blob_tc"], p, self.decoder_hidden_size, self.num_decoder_blocks,
                                          dev=dev, g=g, dt=dt, c0=c0, c1=c1, p1=p1, x_out=x_out, pred_out=pred_out,
-                                         u8_out=u8_out)
+                                         u8_out=u8_out, x_base=x_base)
 
     def _encode(self, P, xp, t, y, B, Hh, Ww):
         """Patch tokens xp [B*L, C*p*p] + text states -> decoder condition s2 [B*L, H] (dit_t2i_pixnerd.py:276-297)."""

@@ -319,7 +319,7 @@ def pixel_decoder_tc(x: torch.Tensor, ysilu: torch.Tensor, blob: torch.Tensor, p
     assert blob.numel() * blob.element_size() == _lib.load().deco_decoder_tc_blob_bytes(num_res_blocks)
     out = torch.empty((B, Cc, H, W), dtype=out_dtype, device=x.device)
     call("deco_pixel_decoder_tc", ptr(x), ptr(ysilu), ptr(blob), ptr(out), int(out_dtype == bf16), B, H, W, patch, hidden_x,
-         num_res_blocks, 0, None, 0.0, 0.0, 0.0, 0.0, None, None, None, None, _st(x))
+         num_res_blocks, 0, None, 0.0, 0.0, 0.0, 0.0, None, None, None, None, None, _st(x))
     return out
 
 
@@ -327,22 +327,25 @@ def pixel_decoder_tc_step(x: torch.Tensor, ysilu: torch.Tensor, blob: torch.Tens
                           num_res_blocks: int, dev: Optional[torch.Tensor] = None, g: float = 1.0, dt: float = 0.0,
                           c0: float = 1.0, c1: float = 0.0, p1: Optional[torch.Tensor] = None,
                           x_out: Optional[torch.Tensor] = None, pred_out: Optional[torch.Tensor] = None,
-                          u8_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                          u8_out: Optional[torch.Tensor] = None, x_base: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Decoder of both CFG rows [uncond || cond] of the image state x [B,3,H,W] + guidance + multistep update in one kernel:
-    x_out = x + dt (c0 pred + c1 p1), pred = u + g (c - u).  dev = device {g, dt, c0, c1, ...} for graph replays."""
-    _cuda(x, ysilu, blob, dev, p1, x_out, pred_out, u8_out)
+    x_out = x_base + dt (c0 pred + c1 p1), pred = u + g (c - u), x_base = x unless given (Heun corrector: the net sees
+    x = x_hat, the update starts from x_base).  dev = device {g, dt, c0, c1, ...} for graph replays."""
+    _cuda(x, ysilu, blob, dev, p1, x_out, pred_out, u8_out, x_base)
     assert x.dtype == torch.float32 and x.is_contiguous() and ysilu.dtype == bf16 and ysilu.is_contiguous()
     B, Cc, H, W = x.shape
     assert Cc == 3 and ysilu.shape == (2 * B * (H // patch) * (W // patch), patch * patch * hidden_x)
     assert blob.numel() * blob.element_size() == _lib.load().deco_decoder_tc_blob_bytes(num_res_blocks)
     if x_out is None:
         x_out = torch.empty_like(x)
-    for t_, dt_ in ((p1, torch.float32), (x_out, torch.float32), (pred_out, torch.float32), (u8_out, torch.uint8)):
+    for t_, dt_ in ((p1, torch.float32), (x_out, torch.float32), (pred_out, torch.float32), (u8_out, torch.uint8),
+                    (x_base, torch.float32)):
         assert t_ is None or (t_.dtype == dt_ and t_.is_contiguous() and t_.shape == x.shape)
     if dev is not None:
         assert dev.dtype == torch.float32 and dev.numel() >= 4 and dev.is_contiguous()
     call("deco_pixel_decoder_tc", ptr(x), ptr(ysilu), ptr(blob), None, 0, 2 * B, H, W, patch, hidden_x, num_res_blocks, 1,
-         ptr(dev), float(g), float(dt), float(c0), float(c1), ptr(p1), ptr(x_out), ptr(pred_out), ptr(u8_out), _st(x))
+         ptr(dev), float(g), float(dt), float(c0), float(c1), ptr(x_base), ptr(p1), ptr(x_out), ptr(pred_out), ptr(u8_out),
+         _st(x))
     return x_out
 
 
@@ -422,6 +425,30 @@ def cfg_step_ex(x: torch.Tensor, net_out: torch.Tensor, g: float = 1.0, dt: floa
          float(g), float(dt), float(c0), cs[0], cs[1], cs[2], float(xpred_den), float(kd), float(sden), float(a_s),
          float(a_n), ptr(noise), ptr(x_out), ptr(pred), ptr(v), ptr(u8), x.numel(), _st(x))
     return x_out, pred, v, u8
+
+
+def heun_sde_step(x: torch.Tensor, v: torch.Tensor, dt: float, a_s: float, a_n: float, kd: float = 0.0, sden: float = 1.0,
+                  s_in: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None,
+                  net_out: Optional[torch.Tensor] = None, x_hat: Optional[torch.Tensor] = None, g: float = 1.0,
+                  kdh: float = 0.0, sdenh: float = 1.0, want_v_avg: bool = False, want_u8: bool = False):
+    """Heun predictor (net_out None) / corrector with an SDE step function (csrc/sampler.cu heun_sde_step_kernel).
+    Returns (x_out, v_hat, s_hat, v_avg, u8); the middle three are None for a predictor."""
+    _cuda(x, v, s_in, noise, net_out, x_hat)
+    for t_ in (x, v, s_in, noise, x_hat):
+        assert t_ is None or (t_.dtype == torch.float32 and t_.is_contiguous() and t_.shape == x.shape)
+    corr = net_out is not None
+    if corr:
+        assert net_out.is_contiguous() and net_out.shape[0] == 2 * x.shape[0] and net_out.dtype in (bf16, torch.float32)
+        assert x_hat is not None
+    x_out = torch.empty_like(x)
+    v_hat = torch.empty_like(x) if corr else None
+    s_hat = torch.empty_like(x) if corr else None
+    v_avg = torch.empty_like(x) if (corr and want_v_avg) else None
+    u8 = torch.empty(x.shape, dtype=torch.uint8, device=x.device) if want_u8 else None
+    call("deco_heun_sde_step", ptr(x), ptr(v), ptr(s_in), ptr(net_out), int(corr and net_out.dtype == bf16), ptr(x_hat),
+         ptr(noise), float(g), float(dt), float(kd), float(sden), float(kdh), float(sdenh), float(a_s), float(a_n), int(corr),
+         ptr(x_out), ptr(v_hat), ptr(s_hat), ptr(v_avg), ptr(u8), x.numel(), _st(x))
+    return x_out, v_hat, s_hat, v_avg, u8
 
 
 def layernorm_modulate(x: torch.Tensor, shift: torch.Tensor, scale: torch.Tensor, rows_per_mod: int, eps: float = 1e-6,

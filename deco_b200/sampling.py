@@ -69,6 +69,28 @@ def _step_kind(fn) -> str:
     return name
 
 
+def sde_scalars(scheduler, w_scheduler, t_cur, dt, kind, t_w=None):
+    """(kd, sden, a_s, a_n) of one step: the score s = (kd v - x) / sden (sampling.py:98) at t_cur and the coefficients of s
+    and of the Gaussian increment in step function `kind` (:17-24) with w = w_scheduler.w(t_w or t_cur), evaluated with the
+    reference's fp32 torch expressions on the scheduler's own methods."""
+    tt = t_cur.reshape(1)
+    sigma = scheduler.sigma(tt)
+    kd = 1 / scheduler.dalpha_over_alpha(tt)
+    sden = sigma ** 2 - kd * scheduler.dsigma_mul_sigma(tt)
+    if kind == "ode_step_fn":
+        return float(kd.reshape(-1)[0]), float(sden.reshape(-1)[0]), 0.0, 0.0
+    tw = (t_cur if t_w is None else t_w).reshape(1)
+    w = w_scheduler.w(tw) if w_scheduler else torch.zeros(1)
+    w = torch.as_tensor(w, dtype=torch.float32).reshape(-1)[:1]
+    if kind == "sde_mean_step_fn":
+        a_s, a_n = w * dt, torch.zeros(1)
+    elif kind == "sde_step_fn":
+        a_s, a_n = w * dt, torch.sqrt(2 * w * dt)
+    else:
+        a_s, a_n = 0.5 * w * dt, torch.sqrt(w * dt)
+    return float(kd.reshape(-1)[0]), float(sden.reshape(-1)[0]), float(a_s.reshape(-1)[0]), float(a_n.reshape(-1)[0])
+
+
 def _make_timesteps(num_steps, last_step, timeshift):
     timesteps = torch.linspace(0.0, 1 - last_step, num_steps)
     timesteps = torch.cat([timesteps, torch.tensor([1.0])], dim=0)
@@ -285,24 +307,7 @@ class EulerSampler(BaseSampler):
         return float((1.0 - t_cur).clamp_min(5e-2)) if self.x_prediction else 0.0
 
     def _sde_scalars(self, t_cur, dt, kind):
-        """(kd, sden, a_s, a_n) of one step: the score s = (kd v - x) / sden (sampling.py:98) and the coefficients of s and
-        of the Gaussian increment in `kind` (:17-24), evaluated with the reference's fp32 torch expressions on the
-        scheduler's own methods."""
-        if kind == "ode_step_fn":
-            return 0.0, 1.0, 0.0, 0.0
-        tt = t_cur.reshape(1)
-        sigma = self.scheduler.sigma(tt)
-        kd = 1 / self.scheduler.dalpha_over_alpha(tt)
-        sden = sigma ** 2 - kd * self.scheduler.dsigma_mul_sigma(tt)
-        w = self.w_scheduler.w(tt) if self.w_scheduler else torch.zeros(1)
-        w = torch.as_tensor(w, dtype=torch.float32).reshape(-1)[:1]
-        if kind == "sde_mean_step_fn":
-            a_s, a_n = w * dt, torch.zeros(1)
-        elif kind == "sde_step_fn":
-            a_s, a_n = w * dt, torch.sqrt(2 * w * dt)
-        else:
-            a_s, a_n = 0.5 * w * dt, torch.sqrt(w * dt)
-        return float(kd.reshape(-1)[0]), float(sden.reshape(-1)[0]), float(a_s.reshape(-1)[0]), float(a_n.reshape(-1)[0])
+        return sde_scalars(self.scheduler, self.w_scheduler, t_cur, dt, kind)
 
     def _graph_rows(self):
         if self._kinds != ("ode_step_fn", "ode_step_fn"):
@@ -386,36 +391,52 @@ class HeunSampler(BaseSampler):
         self.timesteps = _make_timesteps(self.num_steps, self.last_step, self.timeshift)
         assert self.last_step > 0.0
         assert self.scheduler is not None
-        for fn in (self.step_fn, self.last_step_fn):
-            if getattr(fn, "__name__", "") != "ode_step_fn":
-                raise NotImplementedError("only ode_step_fn is supported (SDE steps are out of scope)")
+        self._kinds = (_step_kind(self.step_fn), _step_kind(self.last_step_fn))
+        assert self.w_scheduler is not None or self._kinds[0] == "ode_step_fn"      # sampling.py:225
 
     def _impl_sampling(self, net, noise, condition, uncondition, keep_x=False, keep_v=False, to_uint8=False):
         B = noise.shape[0]
         x, cfg_condition = _prep_inputs(noise, condition, uncondition)
         steps = self.timesteps
         x_trajs, v_trajs, u8 = ([x] if keep_x else None), ([] if keep_v else None), None
+        if self._kinds != ("ode_step_fn", "ode_step_fn"):
+            return self._impl_sampling_sde(net, x, cfg_condition, B, keep_x, keep_v, to_uint8)
         v_hat = None  # fp32 guided velocity at (x_hat, t_next) of the previous step
+        fused = not keep_v and _fused_step_ok(net)     # guidance + predictor / corrector update inside the decoder epilogue
+
+        def full(t_scalar):
+            return torch.full((2 * B,), float(t_scalar), dtype=torch.float32, device=x.device)
         for i in range(self.num_steps):
             t_cur, t_next = steps[i], steps[i + 1]
             dt = float(t_next - t_cur)
             in_window = bool(t_cur > self.guidance_interval_min) and bool(t_cur <= self.guidance_interval_max)
             g = float(self.guidance) if in_window else 1.0
             last = i == self.num_steps - 1
+            u = None
             if i == 0 or self.exact_henu:
-                out = _net_eval(net, x, float(t_cur), cfg_condition, B)
-                x_hat, v, _, u = ops.cfg_step(x, out, g, dt, want_pred=True, want_u8=(to_uint8 and last))
+                if fused:       # predictor: x_hat = x + dt pred, pred kept in fp32 for the corrector
+                    v = torch.empty_like(x)
+                    u = torch.empty(x.shape, dtype=torch.uint8, device=x.device) if (to_uint8 and last) else None
+                    x_hat = net.cfg_step(x, full(t_cur), cfg_condition, g=g, dt=dt, pred_out=v, u8_out=u)
+                else:
+                    out = _net_eval(net, x, float(t_cur), cfg_condition, B)
+                    x_hat, v, _, u = ops.cfg_step(x, out, g, dt, want_pred=True, want_u8=(to_uint8 and last))
             else:
                 # predictor re-uses the corrector's velocity: x_hat = x + dt * v_hat  (c0 = 0 drops the net term)
                 v = v_hat
-                x_hat, _, _, u = ops.cfg_step(x, out, 1.0, dt, c0=0.0, prev=(v,), coeffs=(1.0,),
+                x_hat, _, _, u = ops.cfg_step(x, _zero_net_like(x), 1.0, dt, c0=0.0, prev=(v,), coeffs=(1.0,),
                                               want_u8=(to_uint8 and last))
             if not last:
-                out = _net_eval(net, x_hat, float(t_next), cfg_condition, B)
-                # x = x + dt * (v + v_hat) / 2 ; v_hat is kept (fp32) for the next predictor
-                x, v_hat, v_avg, _ = ops.cfg_step(x, out, g, dt, c0=0.5, prev=(v,), coeffs=(0.5,), want_pred=True,
-                                                  want_v=keep_v)
-                v = v_avg if keep_v else v
+                if fused:       # corrector: the net sees x_hat, x = x + dt (v + v_hat) / 2; v_hat kept for the next predictor
+                    v_hat = torch.empty_like(x)
+                    x = net.cfg_step(x_hat, full(t_next), cfg_condition, g=g, dt=dt, c0=0.5, c1=0.5, p1=v, pred_out=v_hat,
+                                     x_base=x)
+                else:
+                    out = _net_eval(net, x_hat, float(t_next), cfg_condition, B)
+                    # x = x + dt * (v + v_hat) / 2 ; v_hat is kept (fp32) for the next predictor
+                    x, v_hat, v_avg, _ = ops.cfg_step(x, out, g, dt, c0=0.5, prev=(v,), coeffs=(0.5,), want_pred=True,
+                                                      want_v=keep_v)
+                    v = v_avg if keep_v else v
             else:
                 x = x_hat
                 u8 = u
@@ -426,6 +447,63 @@ class HeunSampler(BaseSampler):
         if keep_v:
             v_trajs.append(torch.zeros_like(x))
         return x, x_trajs, v_trajs, u8
+
+
+    def _impl_sampling_sde(self, net, x, cfg_condition, B, keep_x, keep_v, to_uint8):
+        """Heun with an SDE step function (sampling.py:266-293): velocities AND scores of the two evaluations are averaged
+        (csrc/sampler.cu heun_sde_step_kernel); the Gaussian increments are torch.randn_like draws in the reference's order
+        (predictor, then corrector / last step), so a seeded run consumes the same Philox stream."""
+        steps = self.timesteps
+        x_trajs, v_trajs, u8 = ([x] if keep_x else None), ([] if keep_v else None), None
+        v_hat = s_hat = None
+        for i in range(self.num_steps):
+            t_cur, t_next = steps[i], steps[i + 1]
+            dtt = t_next - t_cur
+            dt = float(dtt)
+            in_window = bool(t_cur > self.guidance_interval_min) and bool(t_cur <= self.guidance_interval_max)
+            g = float(self.guidance) if in_window else 1.0
+            last = i == self.num_steps - 1
+            kd, sden, a_s, a_n = sde_scalars(self.scheduler, self.w_scheduler, t_cur, dtt, self._kinds[0])
+            kdh, sdenh, _, _ = sde_scalars(self.scheduler, self.w_scheduler, t_next, dtt, "ode_step_fn")
+            if i == 0 or self.exact_henu:
+                out = _net_eval(net, x, float(t_cur), cfg_condition, B)
+                _, v, _, _ = ops.cfg_step(x, out, g, 0.0, want_pred=True)       # guided velocity in fp32
+                s_in = None
+            else:
+                v, s_in = v_hat, s_hat
+            z = torch.randn_like(x) if a_n != 0.0 else None
+            x_hat, _, _, _, _ = ops.heun_sde_step(x, v, dt, a_s, a_n, kd, sden, s_in=s_in, noise=z)
+            if not last:
+                out = _net_eval(net, x_hat, float(t_next), cfg_condition, B)
+                z = torch.randn_like(x) if a_n != 0.0 else None
+                x, v_hat, s_hat, v_avg, _ = ops.heun_sde_step(x, v, dt, a_s, a_n, kd, sden, s_in=s_in, noise=z, net_out=out,
+                                                              x_hat=x_hat, g=g, kdh=kdh, sdenh=sdenh, want_v_avg=keep_v)
+                v = v_avg if keep_v else v
+            else:
+                _, _, a_sl, a_nl = sde_scalars(self.scheduler, self.w_scheduler, t_cur, dtt, self._kinds[1])
+                z = torch.randn_like(x) if a_nl != 0.0 else None
+                x, _, _, _, u8 = ops.heun_sde_step(x, v, dt, a_sl, a_nl, kd, sden, s_in=s_in, noise=z, want_u8=to_uint8)
+            if keep_x:
+                x_trajs.append(x)
+            if keep_v:
+                v_trajs.append(v)
+        if keep_v:
+            v_trajs.append(torch.zeros_like(x))
+        return x, x_trajs, v_trajs, u8
+
+
+_ZERO_NET = {}
+
+
+def _zero_net_like(x):
+    """A cached all-zero [2B, ...] bf16 tensor: the `net_out` argument of an update that drops the network term (c0 = 0)."""
+    key = (tuple(x.shape), x.device)
+    z = _ZERO_NET.get(key)
+    if z is None:
+        if len(_ZERO_NET) > 4:
+            _ZERO_NET.clear()
+        z = _ZERO_NET[key] = torch.zeros((2 * x.shape[0],) + tuple(x.shape[1:]), dtype=torch.bfloat16, device=x.device)
+    return z
 
 
 # ------------------------------------------------------------------ Adams linear multistep

@@ -154,13 +154,25 @@ int deco_attention_fwd(const void* q, long long q_stride,
  * of deco_decoder_tc_blob_bytes(R) bytes (deco_b200/denoiser.py::pack_decoder_tc).
  * pair == 0: out [rows,3,H,W] (bf16 / fp32) = decoder(x [rows,3,H,W] fp32).
  * pair != 0: rows = 2B stacked [uncond || cond] over ONE image state x [B,3,H,W] fp32:
- *   pred = u + g (c - u); v = c0 pred + c1 p1; x_out = x + dt v (x_out may be x); optional pred_out (may be p1), u8_out.
+ *   pred = u + g (c - u); v = c0 pred + c1 p1; x_out = x_base + dt v (x_base NULL = x; x_out may be x / x_base); optional
+ *   pred_out (may be p1), u8_out.  x_base != x is the Heun corrector: the net sees x_hat, the update starts from x.
  *   {g, dt, c0, c1} come from dev_scalars (device memory, CUDA-graph replays) when it is non-NULL. */
 int deco_decoder_tc_blob_bytes(int num_res_blocks);
 int deco_pixel_decoder_tc(const float* x, const void* ysilu_bf16, const void* blob, void* out, int out_is_bf16,
                           int rows, int H, int W, int patch, int hidden_x, int num_res_blocks,
                           int pair, const float* dev_scalars, float g, float dt, float c0, float c1,
-                          const float* p1, float* x_out, float* pred_out, void* u8_out, void* stream);
+                          const float* x_base, const float* p1, float* x_out, float* pred_out, void* u8_out, void* stream);
+
+/* Heun predictor / corrector with the SDE step functions (flow_matching/sampling.py:17-24, :266-293): the score
+ * s = (kd v - x) / sden at (x, t_cur) and s_hat = (kdh v_hat - x_hat) / sdenh at (x_hat, t_next) are averaged like the
+ * velocities.  corrector == 0: x_out = x + dt v + a_s s + a_n z.  corrector != 0: v_hat = cfg(net_out, g) and
+ * x_out = x + dt (v + v_hat)/2 + a_s (s + s_hat)/2 + a_n z; v_hat / s_hat (fp32) are stored for the next predictor.
+ * s_in NULL = s computed from (x, v, kd, sden).  All tensors fp32 [n] except net_out ([2n] rows [uncond || cond]). */
+int deco_heun_sde_step(const float* x, const float* v, const float* s_in, const void* net_out, int net_is_bf16,
+                       const float* x_hat, const float* noise, float g, float dt, float kd, float sden,
+                       float kdh, float sdenh, float a_s, float a_n, int corrector,
+                       float* x_out, float* v_hat_out, float* s_hat_out, float* v_avg_out, unsigned char* u8_out,
+                       long long n, void* stream);
 
 /* Training-step inputs (src/diffusion/flow_matching/training_repa_DeCo.py:222-237, src/diffusion/base/training.py:14-20).
  * The random draws stay the caller's (torch's CUDA generator, reference order); these fuse what follows them.

@@ -906,6 +906,58 @@ def euler_sample_ex(net: Callable, noise: torch.Tensor, cond: torch.Tensor, unco
     return x
 
 
+def _sde_step(kind: str, x, v, dt, s, w, randn):
+    """Step functions of flow_matching/sampling.py:14-24."""
+    if kind == "ode":
+        return x + v * dt
+    if kind == "sde_mean":
+        return x + v * dt + s * w * dt
+    if kind == "sde":
+        return x + v * dt + s * w * dt + torch.sqrt(2 * w * dt) * randn(x)
+    if kind == "sde_preserve":
+        return x + v * dt + 0.5 * s * w * dt + torch.sqrt(w * dt) * randn(x)
+    raise ValueError(kind)
+
+
+def heun_sample_ex(net: Callable, noise, cond, uncond, num_steps: int, guidance: float, gmin: float = 0.0,
+                   gmax: float = 1.0, timeshift: float = 1.0, last_step: Optional[float] = None, exact_henu: bool = False,
+                   step: str = "ode", last: str = "ode", w_fn: Optional[Callable] = None, randn: Optional[Callable] = None):
+    """HeunSampler._impl_sampling with LinearScheduler and any step function (flow_matching/sampling.py:230-296): the
+    score s = (kd v - x) / (sigma^2 - kd dsigma sigma) is evaluated at (x, t_cur) and at (x_hat, t_next) and AVERAGED like
+    the velocity (:283-291); with exact_henu=False both are re-used as the next predictor (:273-275); the last step
+    re-applies last_step_fn to x (not x_hat) with the predictor's (v, s) (:293); the guidance window of both evaluations is
+    tested on t_cur (:263, :280).  Every step_fn call with a noise term draws one randn_like(x) -- also the predictor of the
+    last step, whose x_hat is discarded."""
+    steps = make_timesteps(num_steps, timeshift, last_step).to(noise.device, noise.dtype)
+    B = noise.shape[0]
+    cfg_c = torch.cat([uncond, cond], dim=0)
+    randn = randn or torch.randn_like
+    w_fn = w_fn or (lambda t: 1 - t)
+    x = noise
+    v_hat = s_hat = None
+    for i, (t_cur, t_next) in enumerate(zip(steps[:-1], steps[1:])):
+        dt = t_next - t_cur
+        kd, sigma, dms = linear_score_terms(t_cur)
+        kdh, sigmah, dmsh = linear_score_terms(t_next)
+        w = w_fn(t_cur)
+        g = guidance if (t_cur > gmin and t_cur <= gmax) else 1.0
+        if i == 0 or exact_henu:
+            v = cfg_combine(net(torch.cat([x, x], 0), t_cur.repeat(2 * B), cfg_c), g)
+            s = (kd * v - x) / (sigma ** 2 - kd * dms)
+        else:
+            v, s = v_hat, s_hat
+        x_hat = _sde_step(step, x, v, dt, s, w, randn)
+        if i < num_steps - 1:
+            v_hat = cfg_combine(net(torch.cat([x_hat, x_hat], 0), t_next.repeat(2 * B), cfg_c), g)
+            s_hat = (kdh * v_hat - x_hat) / (sigmah ** 2 - kdh * dmsh)
+            v = (v + v_hat) / 2
+            s = (s + s_hat) / 2
+            x = _sde_step(step, x, v, dt, s, w, randn)
+        else:
+            x = _sde_step(last, x, v, dt, s, w, randn)
+    return x
+
+
 # --------------------------------------------------------------------------- PixNerd baseline (hyper-network decoder)
 # Restated ahead of its CUDA path (DESIGN.md section 8, rank-4 leftovers): configs_c2i/Baseline_PixNerd.yaml.
 @dataclass(frozen=True)

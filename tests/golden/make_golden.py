@@ -386,8 +386,20 @@ def golden_samplers_ext():
             out[f"{kind}_{n}"] = r.numpy()
             if incs:
                 out[f"{kind}_{n}_increments"] = torch.stack(incs).numpy()
+    # HeunSampler with the SDE step functions: scores at (x, t_cur) and (x_hat, t_next) averaged (sampling.py:283-291)
+    for kind, fn in fns.items():
+        for n, g, shift, last, exact in [(8, 2.0, 1.0, "ode", False), (5, 1.5, 2.0, kind, True)]:
+            h = RefHeun(scheduler=sch, w_scheduler=sch, exact_henu=exact, guidance_fn=ref_guidance, num_steps=n, guidance=g,
+                        guidance_interval_min=0.1, guidance_interval_max=1.0, timeshift=shift, step_fn=fn,
+                        last_step_fn=(ode_step_fn if last == "ode" else fn))
+            torch.manual_seed(99)
+            r = h(toy_net, noise, cond, unc)
+            torch.manual_seed(99)
+            o = O.heun_sample_ex(toy_net, noise, cond, unc, n, g, 0.1, 1.0, shift, exact_henu=exact, step=kind, last=last)
+            assert rel_l2(o, r) < 1e-6, ("heun", kind, rel_l2(o, r))
+            out[f"heun_{kind}_{n}"] = r.numpy()
     np.savez_compressed(os.path.join(OUT, "samplers_ext_toy.npz"), **out)
-    print("[samplers-ext] EulerSamplerJiT / sde_mean / sde / sde_preserve oracle == reference")
+    print("[samplers-ext] EulerSamplerJiT / sde_mean / sde / sde_preserve (Euler and Heun) oracle == reference")
 
 
 def golden_trainstep():

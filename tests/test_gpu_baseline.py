@@ -124,6 +124,38 @@ def test_extended_samplers_vs_reference_golden(cuda_dev):
                 assert rel_l2(s(toy_net, noise, cond, unc), xo) > 1e-3
 
 
+def test_heun_sde_samplers_vs_oracle(cuda_dev):
+    """HeunSampler with sde_mean / sde / sde_preserve step functions (flow_matching/sampling.py:266-293): velocities and
+    scores of the predictor and corrector evaluations are averaged, exact and re-use variants, SDE or ODE last step;
+    against the oracle (pinned to the reference on CPU) consuming the same CUDA generator stream; the deterministic
+    sde_mean runs also against the reference fixture itself."""
+    from deco_b200 import (HeunSampler, LinearScheduler, ode_step_fn, sde_mean_step_fn, sde_preserve_step_fn, sde_step_fn,
+                           simple_guidance_fn)
+    g = load_golden("samplers_ext_toy.npz")
+    noise = torch.from_numpy(g["noise"]).to(cuda_dev)
+    cond, unc = torch.tensor([1, 2, 3], device=cuda_dev), torch.tensor([10, 10, 10], device=cuda_dev)
+    sch = LinearScheduler()
+    fns = {"sde_mean": sde_mean_step_fn, "sde": sde_step_fn, "sde_preserve": sde_preserve_step_fn}
+    for kind, fn in fns.items():
+        for n, gd, shift, last, exact in [(8, 2.0, 1.0, "ode", False), (5, 1.5, 2.0, kind, True)]:
+            s = HeunSampler(scheduler=sch, w_scheduler=sch, exact_henu=exact, guidance_fn=simple_guidance_fn, num_steps=n,
+                            guidance=gd, guidance_interval_min=0.1, guidance_interval_max=1.0, timeshift=shift, step_fn=fn,
+                            last_step_fn=(ode_step_fn if last == "ode" else fn))
+            torch.manual_seed(321)
+            x = s(toy_net, noise, cond, unc)
+            torch.manual_seed(321)
+            xo = O.heun_sample_ex(toy_net, noise, cond, unc, n, gd, 0.1, 1.0, shift, exact_henu=exact, step=kind, last=last)
+            assert rel_l2(x, xo) < 5e-6, (kind, n, rel_l2(x, xo))
+            if kind == "sde_mean":
+                assert rel_l2(x, torch.from_numpy(g[f"heun_{kind}_{n}"])) < 5e-6
+            else:
+                torch.manual_seed(322)
+                assert rel_l2(s(toy_net, noise, cond, unc), xo) > 1e-3
+            x2, u8 = s.sample_uint8(toy_net, noise, cond, unc) if kind == "sde_mean" else (None, None)
+            if x2 is not None:
+                assert torch.equal(x2, x) and torch.equal(u8, O.fp2uint8(x))
+
+
 def test_sde_step_statistics_full_size(cuda_dev):
     """Size-independent property at the bench shape (256 x 3 x 256 x 256 elements): one sde_step_fn update with a zero
     network output and g = 1 is x_out = x (1 - a_s / sden) + a_n z, so the residual has mean 0 and variance a_n^2."""

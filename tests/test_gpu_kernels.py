@@ -430,7 +430,7 @@ def test_pixel_decoder_tc_vs_oracle_and_legacy(cuda_dev, B, res, R):
     big = torch.full((B * 3 * res * res + 512,), 7.0, device=cuda_dev)
     from deco_b200._lib import call, ptr
     call("deco_pixel_decoder_tc", ptr(x), ptr(ysilu), ptr(P["blob_tc"]), big[256:].data_ptr(), 0, B, res, res, 16, 32, R, 0,
-         None, 0.0, 0.0, 0.0, 0.0, None, None, None, None, torch.cuda.current_stream().cuda_stream)
+         None, 0.0, 0.0, 0.0, 0.0, None, None, None, None, None, torch.cuda.current_stream().cuda_stream)
     assert torch.equal(big[256:-256].view(B, 3, res, res), got)
     assert float((big[:256] - 7).abs().max()) == 0 and float((big[-256:] - 7).abs().max()) == 0
 
@@ -467,3 +467,7 @@ def test_pixel_decoder_tc_fused_sampler_step(cuda_dev, B, res, order2):
     assert torch.equal(x2, xo)
     if order2:
         assert torch.equal(p2, pred_o)
+    # Heun corrector form: the network saw x (= x_hat), the update starts from another state x_base
+    xb = torch.randn(x.shape, generator=g).to(cuda_dev)
+    xh = ops.pixel_decoder_tc_step(x, ysilu, P["blob_tc"], 16, 32, 3, g=gd, dt=dt, c0=c0, c1=c1, p1=p1, x_base=xb)
+    assert rel_l2(xh, xb + dt * v) < 2e-6

@@ -154,6 +154,19 @@ def test_extended_euler_samplers_match_reference_fixtures():
             assert not incs
 
 
+def test_heun_sde_oracle_matches_reference_fixtures():
+    """HeunSampler with the SDE step functions (sampling.py:266-293: scores averaged like velocities): the oracle under the
+    seed the fixture was made with (CPU generator: the same draws as the reference's torch.randn_like calls)."""
+    g = load_golden("samplers_ext_toy.npz")
+    noise = torch.from_numpy(g["noise"])
+    cond, unc = torch.tensor([1, 2, 3]), torch.tensor([10, 10, 10])
+    for kind in ("sde_mean", "sde", "sde_preserve"):
+        for n, gd, shift, last, exact in [(8, 2.0, 1.0, "ode", False), (5, 1.5, 2.0, kind, True)]:
+            torch.manual_seed(99)
+            o = O.heun_sample_ex(toy_net, noise, cond, unc, n, gd, 0.1, 1.0, shift, exact_henu=exact, step=kind, last=last)
+            assert rel_l2(o, torch.from_numpy(g[f"heun_{kind}_{n}"])) < 1e-6, (kind, n)
+
+
 def test_pixnerd_forward_matches_reference_fixture():
     """dit_c2i_pixnerd.PixNerDiT (hyper-network NerfBlock decoder, configs_c2i/Baseline_PixNerd.yaml) restated ahead of its
     CUDA path: the oracle against the live reference's output (make_golden.py::golden_pixnerd)."""
