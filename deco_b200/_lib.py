@@ -73,6 +73,8 @@ SIGNATURES = {
     "deco_decoder_tc_blob_bytes": (_i, [_i]),
     "deco_pixel_decoder_tc": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _f, _f, _f, _f, _vp, _vp, _vp, _vp, _vp,
                                    _vp]),
+    "deco_nerf_decoder_blob_bytes": (_i, [_i]),
+    "deco_nerf_decoder": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "deco_train_timesteps": (_i, [_vp, _vp, _vp, _f, _i, _vp, _vp, _i, _vp]),
     "deco_flow_pair": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _ll, _vp]),
     "deco_label_dropout": (_i, [_vp, _vp, _vp, _f, _vp, _i, _vp]),

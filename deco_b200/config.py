@@ -17,6 +17,7 @@ CLASS_MAP = {
     "src.diffusion.flow_matching.sampling.EulerSampler": "deco_b200.sampling.EulerSampler",
     "src.diffusion.flow_matching.sampling.EulerSamplerJiT": "deco_b200.sampling.EulerSamplerJiT",
     "src.models.transformer.dit_c2i_baseline.FlattenDiT": "deco_b200.denoiser_baseline.FlattenDiT",
+    "src.models.transformer.dit_c2i_pixnerd.PixNerDiT": "deco_b200.denoiser_pixnerd.PixNerDiT",
     "src.diffusion.flow_matching.sampling.HeunSampler": "deco_b200.sampling.HeunSampler",
     "src.diffusion.flow_matching.adam_sampling.AdamLMSampler": "deco_b200.sampling.AdamLMSampler",
     "src.diffusion.flow_matching.scheduling.LinearScheduler": "deco_b200.scheduling.LinearScheduler",

@@ -349,6 +349,25 @@ def pixel_decoder_tc_step(x: torch.Tensor, ysilu: torch.Tensor, blob: torch.Tens
     return x_out
 
 
+def nerf_decoder(x: torch.Tensor, params, blob: torch.Tensor, patch: int, hidden_x: int, mlp_ratio: int,
+                 out_dtype=bf16) -> torch.Tensor:
+    """PixNerd hyper-network decoder (csrc/nerf_decoder.cu): x fp32 [B,3,H,W]; params = list of bf16 [B*L, 2*Hx*Hx*ratio]
+    generated weights, one per NerfBlock."""
+    import ctypes
+    _cuda(x, blob, *params)
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.shape[1] == 3
+    B, _, H, W = x.shape
+    M = B * (H // patch) * (W // patch)
+    for t_ in params:
+        assert t_.dtype == bf16 and t_.is_contiguous() and t_.shape == (M, 2 * hidden_x * hidden_x * mlp_ratio)
+    assert blob.numel() * blob.element_size() == _lib.load().deco_nerf_decoder_blob_bytes(len(params))
+    out = torch.empty((B, 3, H, W), dtype=out_dtype, device=x.device)
+    ptrs = (ctypes.c_void_p * len(params))(*[t_.data_ptr() for t_ in params])
+    call("deco_nerf_decoder", ptr(x), ctypes.cast(ptrs, ctypes.c_void_p), len(params), ptr(blob), ptr(out),
+         int(out_dtype == bf16), B, H, W, patch, hidden_x, mlp_ratio, _st(x))
+    return out
+
+
 def cfg_step(x: torch.Tensor, net_out: torch.Tensor, g: float, dt: float, c0: float = 1.0,
              prev=(), coeffs=(), x_out: Optional[torch.Tensor] = None, want_pred: bool = False,
              want_v: bool = False, want_u8: bool = False):

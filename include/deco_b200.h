@@ -174,6 +174,15 @@ int deco_heun_sde_step(const float* x, const float* v, const float* s_in, const 
                        float* x_out, float* v_hat_out, float* s_hat_out, float* v_avg_out, unsigned char* u8_out,
                        long long n, void* stream);
 
+/* Hyper-network pixel decoder of the PixNerd baseline (csrc/nerf_decoder.cu; src/models/transformer/dit_c2i_pixnerd.py:
+ * 212-283, :376-380).  params[j] = output of NerfBlock j's param_generator1 (bf16 [B*L, 2*64*128]: fc1 [64 x 128] | fc2
+ * [128 x 64] per token, un-normalised); the kernel applies F.normalize(dim=-2) as reciprocal column norms on the fp32
+ * accumulators.  blob: deco_nerf_decoder_blob_bytes(R) bytes packed by deco_b200/denoiser_pixnerd.py.  Built for patch 16,
+ * hidden_size_x 64, nerf_mlpratio 2. */
+int deco_nerf_decoder_blob_bytes(int num_nerf_blocks);
+int deco_nerf_decoder(const float* x, const void* const* params, int num_nerf_blocks, const void* blob,
+                      void* out, int out_is_bf16, int B, int H, int W, int patch, int hidden_x, int mlp_ratio, void* stream);
+
 /* Training-step inputs (src/diffusion/flow_matching/training_repa_DeCo.py:222-237, src/diffusion/base/training.py:14-20).
  * The random draws stay the caller's (torch's CUDA generator, reference order); these fuse what follows them.
  * deco_train_timesteps: t = time_shift(where(u_select <= 0.9, sigmoid(nt), u_uniform)) (fp32 [B]); with

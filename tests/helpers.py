@@ -94,3 +94,22 @@ def build_baseline_module(cfg: O.BaselineCfg, device, seed=2468):
     m = m.to_empty(device=device)
     m.load_state_dict({k: v.to(device) for k, v in P.items()})
     return m.eval(), P
+
+
+def pixnerd_cfg_from_array(a) -> O.PixNerdCfg:
+    a = [int(v) for v in a]
+    return O.PixNerdCfg(in_channels=a[0], num_groups=a[1], hidden_size=a[2], hidden_size_x=a[3], nerf_mlpratio=a[4],
+                        num_blocks=a[5], num_cond_blocks=a[6], patch_size=a[7], num_classes=a[8])
+
+
+def build_pixnerd_module(cfg: O.PixNerdCfg, device, seed=1357):
+    """deco_b200 PixNerd PixNerDiT holding oracle.pixnerd_seeded_params(cfg)."""
+    from deco_b200.denoiser_pixnerd import PixNerDiT
+    with torch.device("meta"):
+        m = PixNerDiT(in_channels=cfg.in_channels, num_groups=cfg.num_groups, hidden_size=cfg.hidden_size,
+                      hidden_size_x=cfg.hidden_size_x, nerf_mlpratio=cfg.nerf_mlpratio, num_blocks=cfg.num_blocks,
+                      num_cond_blocks=cfg.num_cond_blocks, patch_size=cfg.patch_size, num_classes=cfg.num_classes)
+    P = O.pixnerd_seeded_params(cfg, seed)
+    m = m.to_empty(device=device)
+    m.load_state_dict({k: v.to(device) for k, v in P.items()})
+    return m.eval(), P

@@ -192,3 +192,52 @@ def test_non_square_images_both_denoisers(cuda_dev, hw):
     eb = rel_l2(mb(x, t, y).float(), refb)
     print(f"FlattenDiT {Hh}x{Ww}: rel-L2 vs fp32 oracle = {eb:.3e}")
     assert eb <= 1e-2
+
+
+def test_pixnerd_forward_vs_reference_golden_and_oracle(cuda_dev):
+    """dit_c2i_pixnerd.PixNerDiT (hyper-network NerfBlock decoder; configs_c2i/Baseline_PixNerd.yaml): the fixture produced by
+    the live reference (rel-L2 <= 1e-2, north_star forward tolerance), then the YAML's architecture (hidden 1024, 22 DiT + 2
+    NerfBlocks, hidden_size_x 64, ratio 2) at 256 px against the fp32 oracle; forward(s=...) isolates the decoder."""
+    from helpers import build_pixnerd_module, pixnerd_cfg_from_array
+    g = load_golden("pixnerd_d64.npz")
+    cfg = pixnerd_cfg_from_array(g["cfg"])
+    m, P = build_pixnerd_module(cfg, cuda_dev)
+    x, t, y = (torch.from_numpy(g[k]).to(cuda_dev) for k in ("x", "t", "y"))
+    out = m(x, t, y)
+    assert out.dtype == torch.bfloat16 and out.shape == x.shape
+    e = rel_l2(out.float(), torch.from_numpy(g["out"]))
+    print(f"pixnerd_d64: rel-L2 vs reference fp32 = {e:.3e}")
+    assert e <= 1e-2
+    # the decoder alone: same condition s for the kernel and the oracle (ragged token count: 3 images of 48 px = 27 tokens)
+    Pd = {k: v.to(cuda_dev) for k, v in P.items()}
+    gen = torch.Generator().manual_seed(4)
+    xs = torch.randn(3, 3, 48, 48, generator=gen).to(cuda_dev)
+    s = (torch.randn(3, 9, cfg.hidden_size, generator=gen) * 0.7).to(cuda_dev).to(torch.bfloat16)
+    tz, yz = torch.zeros(3, device=cuda_dev), torch.zeros(3, dtype=torch.long, device=cuda_dev)
+    h = O.F.linear(torch.cat([O.F.unfold(xs, 16, stride=16).transpose(1, 2).reshape(27, 3, 256).transpose(1, 2),
+                              O.nerf_pos_table(16).to(cuda_dev)[None].expand(27, -1, -1)], -1),
+                   Pd["x_embedder.embedder.0.weight"], Pd["x_embedder.embedder.0.bias"])
+    for i in range(cfg.num_cond_blocks, cfg.num_blocks):
+        h = O.nerf_block(Pd, f"blocks.{i}.", h, s.float().reshape(27, -1), cfg.nerf_mlpratio)
+    h = O.F.linear(O.rmsnorm(h, Pd["final_layer.norm.weight"]), Pd["final_layer.linear.weight"], Pd["final_layer.linear.bias"])
+    ref = O.F.fold(h.transpose(1, 2).reshape(3, 9, -1).transpose(1, 2).contiguous(), (48, 48), kernel_size=16, stride=16)
+    got = m(xs, tz, yz, s=s)
+    e = rel_l2(got.float(), ref)
+    print(f"pixnerd decoder alone: rel-L2 vs oracle = {e:.3e}")
+    assert e <= 8e-3
+    # the YAML's architecture
+    cfg = O.PixNerdCfg()
+    m, P = build_pixnerd_module(cfg, cuda_dev)
+    Pd = {k: v.to(cuda_dev) for k, v in P.items()}
+    xb = seeded_noise(2, (3, 256, 256), 17).to(cuda_dev)
+    tb = torch.tensor([0.2, 0.8], device=cuda_dev)
+    yb = torch.tensor([1000, 33], device=cuda_dev)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        ref = O.pixnerd_forward(Pd, cfg, xb, tb, yb)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    e = rel_l2(m(xb, tb, yb).float(), ref)
+    print(f"PixNerd-L/16 256px: rel-L2 vs fp32 oracle = {e:.3e}")
+    assert e <= 1e-2

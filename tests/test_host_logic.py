@@ -585,3 +585,19 @@ def test_checkpoint_layout_and_prefix_cleaning(tmp_path):
     assert torch.equal(net3.blocks[0].attn.qkv.weight, ema.blocks[0].attn.qkv.weight)
     with pytest.raises(RuntimeError):
         load_checkpoint(dict(state_dict={"denoiser.nope": torch.zeros(1)}), PixNerDiT(**kw))
+
+
+def test_pixnerd_state_dict_is_the_reference_checkpoint_contract():
+    """dit_c2i_pixnerd.PixNerDiT (configs_c2i/Baseline_PixNerd.yaml): DiT blocks and NerfBlocks share one `blocks` list; names
+    and shapes as instantiated from the reference (oracle.pixnerd_param_shapes, pinned by tests/golden/pixnerd_d64.npz)."""
+    from deco_b200 import config
+    from deco_b200.denoiser_pixnerd import PixNerDiT
+    assert config.resolve("src.models.transformer.dit_c2i_pixnerd.PixNerDiT") is PixNerDiT
+    cfg = O.PixNerdCfg()
+    with torch.device("meta"):
+        m = PixNerDiT(in_channels=3, patch_size=16, num_groups=16, hidden_size=1024, hidden_size_x=64, num_blocks=24,
+                      num_cond_blocks=22, nerf_mlpratio=2, num_classes=1000)
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == O.pixnerd_param_shapes(cfg)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        PixNerDiT(in_channels=3, patch_size=16, num_groups=2, hidden_size=128, hidden_size_x=64, num_blocks=2, num_cond_blocks=1,
+                  nerf_mlpratio=2, num_classes=10).eval()(torch.zeros(1, 3, 16, 16), torch.zeros(1), torch.zeros(1, dtype=torch.long))
