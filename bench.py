@@ -31,6 +31,8 @@ LARGE = dict(XL, hidden_size=1024, num_blocks=25, num_cond_blocks=22)
 XXL_T2I = dict(in_channels=3, patch_size=16, num_groups=24, hidden_size=1536, txt_embed_dim=2048, txt_max_length=128,
                num_text_blocks=4, decoder_hidden_size=32, num_encoder_blocks=16, num_decoder_blocks=3)
 BASELINE_JIT = dict(in_channels=3, patch_size=16, num_groups=16, hidden_size=1024, num_blocks=24, num_classes=1000)
+PIXNERD = dict(in_channels=3, patch_size=16, num_groups=16, hidden_size=1024, hidden_size_x=64, num_blocks=24,
+               num_cond_blocks=22, nerf_mlpratio=2, num_classes=1000)
 UNIT = "images/s"
 # BASELINE.json configs; "xl256" (configs[1]) is the one the headline metric is quoted on and the default.
 # gflop = algorithmic GFLOP per image-forward (2*MAC, no padding counted).
@@ -59,6 +61,15 @@ WORKLOADS = {
                           "steps x CFG, fixed NFE)",
                    name="FlattenDiT 1024 x 24 blocks /16 256px c2i (configs_c2i/Baseline_DiT_JiT.yaml denoiser and sampler "
                         "settings), EulerSamplerJiT 50 steps x CFG rows (guidance 1.0 as configured)"),
+    # the PixNerd baseline (hyper-network NerfBlock decoder); not a BASELINE.json config.  GFLOP per
+    # image-forward: 22 DiT blocks of the L/16 architecture 147.6 + parameter generators 2 x 2 x 1024 x 16384 x 256 tokens =
+    # 17.2 + per-pixel MLPs 2 x 2 x (2 x 64 x 128) x 65536 = 4.3 + embedders / final layer 0.6
+    "pixnerd256": dict(kind="pixnerd", model=PIXNERD, res=256, batch=256, sampler="euler", steps=50, guidance=1.0, gmin=0.1,
+                       gmax=1.0, timeshift=1.0, gflop=169.7,
+                       metric="PixNerd-L/16 (hyper-network pixel decoder) 256px sampling throughput (Euler 50 steps x CFG rows, "
+                              "fixed NFE)",
+                       name="PixNerDiT 1024 x (22 DiT + 2 NerfBlock) /16 256px c2i (configs_c2i/Baseline_PixNerd.yaml denoiser and "
+                            "sampler settings), Euler 50 steps x CFG rows (guidance 1.0 as configured)"),
     # BASELINE configs[3]: training step (forward + backward of denoiser and DCT/FM loss), 32 images PER GPU (weak scaling)
     "train256": dict(kind="train", model=XL, res=256, batch=32, gflop=3 * 244.9,
                      metric="DeCo-XL/16 256px training step throughput (denoiser + DCT/FM loss, forward + backward)",
@@ -229,6 +240,11 @@ def _oracle_forward(wl, net, dev):
                        num_decoder_blocks=m["num_decoder_blocks"], num_text_blocks=m["num_text_blocks"],
                        patch_size=m["patch_size"], txt_embed_dim=m["txt_embed_dim"], txt_max_length=m["txt_max_length"])
         return (lambda x, t, c: O.t2i_forward(P, cfg, x, t, c.float())), P
+    if wl["kind"] == "pixnerd":
+        cfg = O.PixNerdCfg(in_channels=m["in_channels"], num_groups=m["num_groups"], hidden_size=m["hidden_size"],
+                           hidden_size_x=m["hidden_size_x"], nerf_mlpratio=m["nerf_mlpratio"], num_blocks=m["num_blocks"],
+                           num_cond_blocks=m["num_cond_blocks"], patch_size=m["patch_size"], num_classes=m["num_classes"])
+        return (lambda x, t, c: O.pixnerd_forward(P, cfg, x, t, c)), P
     if wl["kind"] == "baseline":
         cfg = O.BaselineCfg(in_channels=m["in_channels"], num_groups=m["num_groups"], hidden_size=m["hidden_size"],
                             num_blocks=m["num_blocks"], patch_size=m["patch_size"], num_classes=m["num_classes"])
@@ -386,8 +402,19 @@ def hbm_kernel_rooflines(torch, ops, net, dev, B2, res, hbm_gbs):
     ycond = torch.randn(M, net.patch_size ** 2 * 32, device=dev).to(bf)
     xx = torch.randn(B2, 3, res, res, device=dev)
     nres = net.num_blocks - net.num_cond_blocks if hasattr(net, "num_cond_blocks") else net.num_decoder_blocks
+    if "blob_tc" in P:      # the decoder the sampling step runs: tcgen05 kernel, sampler update fused into its epilogue
+        xh = xx[:B].contiguous()
+        xo = torch.empty_like(xh)
+        ms = _time_kernel(lambda i: ops.pixel_decoder_tc_step(xh, ycond, P["blob_tc"], net.patch_size, 32, nres, g=3.2, dt=0.01,
+                                                              x_out=xo), 5, torch)
+        add("pixel_decoder_tc_kernel (CFG + Euler update fused)", ms, (64.0 * B2 + 8.0 * B) * res * res,
+            "64 B/pixel condition per CFG row + x fp32 read/write per image; tensor/issue-bound (DESIGN.md 4): tflops on "
+            "37.2 kFLOP/pixel", flops=37.2e3 * B2 * res * res)
+        ms = _time_kernel(lambda i: ops.pixel_decoder_tc(xx, ycond, P["blob_tc"], net.patch_size, 32, nres), 5, torch)
+        add("pixel_decoder_tc_kernel (plain)", ms, 82.0 * B2 * res * res, "82 B/pixel (64 condition + 12 x + 6 out)",
+            flops=37.2e3 * B2 * res * res)
     ms = _time_kernel(lambda i: ops.pixel_decoder(xx, ycond, P["blob"], P["postab"], net.patch_size, 32, nres), 5, torch)
-    add("pixel_decoder_kernel", ms, 82.0 * B2 * res * res,
+    add("pixel_decoder_kernel (legacy mma.sync, A/B)", ms, 82.0 * B2 * res * res,
         "82 B/pixel (64 condition + 12 x + 6 out); compute/issue-bound once fused (DESIGN.md): tflops on 37.2 kFLOP/pixel",
         flops=37.2e3 * B2 * res * res)
     del ycond, xx
@@ -452,6 +479,7 @@ def run_deco(args):
     from deco_b200 import distributed as D
     from deco_b200.data import rank_indices, seeded_noise
     from deco_b200.denoiser_t2i import PixNerDiT as PixNerDiTT2I
+    from deco_b200.denoiser_pixnerd import PixNerDiT as PixNerdDiT
     from deco_b200.utils import GemmProbe, randomize_
 
     wl = WORKLOADS[args.workload]
@@ -468,7 +496,7 @@ def run_deco(args):
     idx = rank_indices(gbatch, rank, world)          # DistributedSampler(shuffle=False) shard
     B = len(idx)
     with torch.device("meta"):
-        net = {"t2i": PixNerDiTT2I, "baseline": FlattenDiT}.get(wl["kind"], PixNerDiT)(**wl["model"])
+        net = {"t2i": PixNerDiTT2I, "baseline": FlattenDiT, "pixnerd": PixNerdDiT}.get(wl["kind"], PixNerDiT)(**wl["model"])
     net = randomize_(net.to_empty(device=dev), seed=0).eval()
     net.prepare(dev)
     sch = LinearScheduler()
@@ -624,7 +652,7 @@ def run_deco(args):
         del x
         torch.cuda.empty_cache()
         fn = baseline_head_rooflines if wl["kind"] == "baseline" else hbm_kernel_rooflines
-        hbm = fn(torch, ops, net, dev, 2 * B, res, peaks["hbm_gbs"])
+        hbm = fn(torch, ops, net, dev, 2 * B, res, peaks["hbm_gbs"]) if wl["kind"] != "pixnerd" else None
 
     tgb = None
     if args.torch_baseline != "none" and world == 1 and not args.profile:
