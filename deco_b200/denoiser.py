@@ -28,6 +28,9 @@ COMPOSITE_SHIFT = os.environ.get("DECO_B200_COMPOSITE_SHIFT", "1") != "0"
 # kept for A/B measurements and as the forward of the training path, whose backward consumes the pre-activation ycond)
 DECODER = os.environ.get("DECO_B200_DECODER", "tc")
 QKV_PITCH80 = os.environ.get("DECO_B200_QKV_PITCH80", "1") != "0"
+# training loops: re-preparation of the bf16 / packed / transposed weight copies after every optimizer step is ~300 small
+# copy / gather kernels -- captured ONCE into a CUDA graph and replayed (static buffers), instead of re-launched one by one
+PREP_GRAPH = os.environ.get("DECO_B200_PREP_GRAPH", "1") != "0"
 
 
 # ------------------------------------------------------------------------------------------------ parameter holders
@@ -473,10 +476,53 @@ class PixNerDiT(nn.Module):
 
     @torch.no_grad()
     def prepare(self, device) -> dict:
-        """bf16 copies / packed layouts of the fp32 master parameters; cached until a parameter changes."""
+        """bf16 copies / packed layouts of the fp32 master parameters; cached until a parameter changes.
+
+        In a training loop the parameters change after every optimizer step: from the second re-preparation on, the whole
+        sequence (prepare + autograd.prepare_train: casts, interleaves, transposes, decoder packing) is a CUDA graph replay
+        into static buffers -- same kernels, no per-kernel launch cost (DECO_B200_PREP_GRAPH=0: plain re-launch)."""
         key = self._weights_key(device)
         if self._prep is not None and self._prep_key == key:
             return self._prep
+        ptrs = (str(device),) + tuple(p.data_ptr() for p in self.parameters())
+        g = self.__dict__.get("_prep_graph")
+        if g is not None and g["ptrs"] == ptrs and self.training:
+            g["graph"].replay()                       # the static buffers of g["P"] now hold the new weights' copies
+            P = g["P"]
+            for k in ("wshift", "bshift"):            # lazily built inference extras: stale now, rebuilt on demand
+                P.pop(k, None)
+            self._prep, self._prep_key = P, key
+            return P
+        want_graph = (PREP_GRAPH and self.training and torch.device(device).type == "cuda"
+                      and not torch.cuda.is_current_stream_capturing())
+        n_prev = self.__dict__.get("_prep_count", 0)
+        self.__dict__["_prep_count"] = n_prev + 1
+        if want_graph and n_prev >= 1:                # second re-preparation in training mode: this is a loop, capture it
+            try:
+                P = self._capture_prepare(device, ptrs)
+                self._prep, self._prep_key = P, key
+                return P
+            except Exception as e:   # noqa: BLE001 -- the graph is an optimisation; the eager path computes the same copies
+                import logging
+                logging.getLogger(__name__).warning("CUDA-graph capture of the weight re-preparation failed (%s)", e)
+                self.__dict__["_prep_graph"] = None
+        P = self._prepare_eager(device)
+        self._prep, self._prep_key = P, key
+        return P
+
+    def _capture_prepare(self, device, ptrs):
+        from .autograd import prepare_train
+        prepare_train(self, self._prepare_eager(device), device)   # warm-up outside the capture: constant tables, index caches
+        torch.cuda.synchronize(device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            P = self._prepare_eager(device)
+            prepare_train(self, P, device)
+        graph.replay()
+        self.__dict__["_prep_graph"] = dict(graph=graph, P=P, ptrs=ptrs)
+        return P
+
+    def _prepare_eager(self, device) -> dict:
         H, Hx, p = self.hidden_size, self.hidden_size_x, self.patch_size
         if Hx != 32 or p != 16 or self.in_channels != 3:
             raise NotImplementedError("the fused pixel decoder is built for in_channels=3, patch_size=16, "
@@ -503,7 +549,6 @@ class PixNerDiT(nn.Module):
         P["blob"], P["postab"] = self._pack_decoder(device)
         P["blob_tc"] = pack_decoder_tc(self.x_embedder.embedder[0], self.dec_net, self.in_channels,
                                        self.precompute_pos[("nerf_tab", str(device))], device)
-        self._prep, self._prep_key = P, key
         return P
 
     @torch.no_grad()

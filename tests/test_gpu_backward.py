@@ -623,3 +623,42 @@ def test_training_pipeline_step_and_checkpoint_resume(dev, tmp_path):
     assert abs(la[1] - lb[1]) <= 1e-3 * abs(la[1])        # then up to the fp32 atomics of the weight gradients
     for (n, p), (_, q) in zip(a.ema_denoiser.state_dict().items(), b.ema_denoiser.state_dict().items()):
         assert rel_l2(q, p) < 1e-4, n
+
+
+def test_weight_reprep_graph_replay_matches_eager(dev):
+    """Training loop: from the second re-preparation on, prepare() + prepare_train() (bf16 casts, w1|w3 interleave, dgrad
+    transposes, decoder fragment / tcgen05 packing) are ONE CUDA-graph replay into static buffers; every prepared tensor
+    must equal what a fresh eager preparation of the updated weights produces."""
+    from deco_b200 import FusedAdamWEMA, LinearScheduler, REPATrainer
+    from deco_b200.autograd import prepare_train
+    cfg = O.DenoiserCfg(num_groups=2, hidden_size=144, num_blocks=4, num_cond_blocks=2, num_classes=10)
+    m, _ = build_module(cfg, dev)
+    m.train()
+    tr = REPATrainer(scheduler=LinearScheduler()).to(dev)
+    opt = FusedAdamWEMA(m.parameters(), lr=2e-3)
+    x = torch.tanh(torch.randn(4, 3, 64, 64, device=dev, generator=_g(1)))
+    y, unc = torch.tensor([1, 2, 3, 4], device=dev), torch.full((4,), 10, device=dev)
+    for _ in range(4):
+        opt.zero_grad()
+        tr(m, None, None, x, y, unc)["loss"].backward()
+        opt.step()
+    P = m.prepare(dev)
+    assert m.__dict__.get("_prep_graph") is not None and P is m._prep_graph["P"], "the re-preparation was not graph-replayed"
+    with torch.no_grad():
+        E = m._prepare_eager(dev)
+        prepare_train(m, E, dev)
+
+    def same(a, b, path):
+        if torch.is_tensor(a):
+            assert torch.equal(a, b), path
+        elif isinstance(a, dict):
+            assert set(a) == set(b), path
+            for k in a:
+                same(a[k], b[k], f"{path}.{k}")
+        elif isinstance(a, (list, tuple)):
+            assert len(a) == len(b), path
+            for i, (u, v) in enumerate(zip(a, b)):
+                same(u, v, f"{path}[{i}]")
+        else:
+            assert a == b, path
+    same(P, E, "P")
