@@ -258,6 +258,94 @@ class GraphedStepper:
         _lib.launch_count += self.launches_per_step
 
 
+class HeunGraphedStepper:
+    """HeunSampler (ODE steps) on a denoiser with the fused decoder-epilogue update, as CUDA-graph replays: the schedule
+    scalars live in a device table walked by csrc/sampler.cu::sampler_advance_kernel (one row per network evaluation or
+    element-wise predictor), so a trajectory is `num_steps` replays with no host work in between.  Three captured bodies:
+      full  (step 0, and every step when exact_henu)  predictor evaluation at t_cur (x_hat = x + dt pred, pred kept) +
+                                                       corrector evaluation at t_next (x += dt (pred + pred_hat) / 2)
+      mid   (re-use variant, steps 1 .. n-2)           predictor x_hat = x + dt v_hat (element-wise) + corrector evaluation
+      last                                             predictor only: x = x_hat (+ fp2uint8)
+    Same kernels, same order, same numerics as HeunSampler's eager loop."""
+
+    def __init__(self, sampler, net, batch, shape, cond_like, to_uint8):
+        dev = cond_like.device
+        self.sampler, self.net, self.B, self.n = sampler, net, batch, sampler.num_steps
+        ts = sampler.timesteps
+        rows, self.kinds = [], []
+        for i in range(self.n):
+            t_cur, t_next = ts[i], ts[i + 1]
+            dt = float(t_next - t_cur)
+            in_window = bool(t_cur > sampler.guidance_interval_min) and bool(t_cur <= sampler.guidance_interval_max)
+            g = float(sampler.guidance) if in_window else 1.0
+            last = i == self.n - 1
+            evaluates = i == 0 or sampler.exact_henu
+            if evaluates:
+                rows.append([g, dt, 1.0, 0.0, 0.0, 0.0, float(t_cur), 0.0])           # predictor from the network
+            else:
+                rows.append([1.0, dt, 0.0, 1.0, 0.0, 0.0, float(t_next), 0.0])        # predictor from the kept velocity
+            if not last:
+                rows.append([g, dt, 0.5, 0.5, 0.0, 0.0, float(t_next), 0.0])          # corrector
+            self.kinds.append(("full" if evaluates else "mid") if not last else ("last_eval" if evaluates else "last"))
+        self.table = torch.tensor(rows, dtype=torch.float32).to(dev)
+        self.counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.cur = torch.zeros(8, dtype=torch.float32, device=dev)
+        self.t = torch.zeros(2 * batch, dtype=torch.float32, device=dev)
+        self.x = torch.zeros((batch,) + tuple(shape), dtype=torch.float32, device=dev)
+        self.x_hat = torch.zeros_like(self.x)
+        self.v = torch.zeros_like(self.x)            # predictor velocity of the current step
+        self.v_hat = torch.zeros_like(self.x)        # corrector velocity, kept for the next predictor
+        self.cond = torch.zeros((2 * batch,) + tuple(cond_like.shape[1:]), dtype=cond_like.dtype, device=dev)
+        self.u8 = torch.zeros(self.x.shape, dtype=torch.uint8, device=dev) if to_uint8 else None
+        self.zero_net = _zero_net_like(self.x)
+        self.graphs, self.launches = {}, {}
+        cur_stream = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(dev)
+        for kind in sorted(set(self.kinds)):
+            side.wait_stream(cur_stream)
+            with torch.cuda.stream(side):       # eager warm-up: lazily-set function attributes, weight / table caches
+                self._body(kind)
+            cur_stream.wait_stream(side)
+            torch.cuda.synchronize(dev)
+            n0 = _lib.launch_count
+            g_ = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_):
+                self._body(kind)
+            self.graphs[kind], self.launches[kind] = g_, _lib.launch_count - n0
+        self.prep_ref = getattr(net, "_prep", None)
+
+    def _advance(self):
+        ops.sampler_advance(self.table, self.counter, self.cur, self.t)
+
+    def _body(self, kind):
+        if kind in ("full", "last_eval"):
+            self._advance()
+            self.net.cfg_step(self.x, self.t, self.cond, dev=self.cur, x_out=(self.x if kind == "last_eval" else self.x_hat),
+                              pred_out=self.v, u8_out=(self.u8 if kind == "last_eval" else None))
+            if kind == "last_eval":
+                return
+            p1 = self.v
+        elif kind in ("mid", "last"):
+            self._advance()                     # predictor from the velocity the last corrector left: x_hat = x + dt v_hat
+            ops.cfg_step_dev(self.x, self.zero_net, self.cur, self.x if kind == "last" else self.x_hat, p1=self.v_hat,
+                             u8_out=(self.u8 if kind == "last" else None))
+            if kind == "last":
+                return
+            p1 = self.v_hat                     # read as p1 and overwritten (pred_out) element by element
+        self._advance()
+        self.net.cfg_step(self.x_hat, self.t, self.cond, dev=self.cur, p1=p1, pred_out=self.v_hat, x_out=self.x, x_base=self.x)
+
+    def reset(self, x, cfg_condition):
+        self.x.copy_(x)
+        self.cond.copy_(cfg_condition)
+        self.counter.zero_()
+
+    def run(self):
+        for kind in self.kinds:
+            self.graphs[kind].replay()
+            _lib.launch_count += self.launches[kind]
+
+
 FUSED_STEP = os.environ.get("DECO_B200_FUSED_STEP", "1") != "0"
 
 
@@ -403,6 +491,12 @@ class HeunSampler(BaseSampler):
             return self._impl_sampling_sde(net, x, cfg_condition, B, keep_x, keep_v, to_uint8)
         v_hat = None  # fp32 guided velocity at (x_hat, t_next) of the previous step
         fused = not keep_v and _fused_step_ok(net)     # guidance + predictor / corrector update inside the decoder epilogue
+        if fused and not keep_x and GRAPH and getattr(net, "cuda_graph_safe", False) and isinstance(self.guidance, (int, float)):
+            st = self._heun_stepper(net, x, cfg_condition, to_uint8)
+            if st is not None:
+                st.reset(x, cfg_condition)
+                st.run()
+                return st.x.clone(), None, None, (st.u8.clone() if to_uint8 else None)
 
         def full(t_scalar):
             return torch.full((2 * B,), float(t_scalar), dtype=torch.float32, device=x.device)
@@ -448,6 +542,26 @@ class HeunSampler(BaseSampler):
             v_trajs.append(torch.zeros_like(x))
         return x, x_trajs, v_trajs, u8
 
+
+    def _heun_stepper(self, net, x, cfg_condition, to_uint8):
+        """HeunGraphedStepper for (net, batch shape), cached like BaseSampler.graphed_stepper; None on a capture failure."""
+        prep = net.prepare(x.device) if hasattr(net, "prepare") else None
+        slot = (id(net), tuple(x.shape), tuple(cfg_condition.shape), cfg_condition.dtype, bool(to_uint8), x.device.index)
+        version = (id(prep), float(self.guidance))
+        cache = self.__dict__.setdefault("_steppers", {})
+        hit = cache.get(slot)
+        if hit is not None and hit[0] == version:
+            return hit[1]
+        cache.pop(slot, None)
+        while len(cache) >= MAX_STEPPERS:
+            cache.pop(next(iter(cache)))
+        try:
+            st = HeunGraphedStepper(self, net, x.shape[0], x.shape[1:], cfg_condition[: x.shape[0]], to_uint8)
+        except Exception as e:   # noqa: BLE001 -- capture is an optimisation; the eager loop runs the same kernels
+            logger.warning("CUDA-graph capture of the Heun step failed (%s); using the eager loop", e)
+            st = None
+        cache[slot] = (version, st)
+        return st
 
     def _impl_sampling_sde(self, net, x, cfg_condition, B, keep_x, keep_v, to_uint8):
         """Heun with an SDE step function (sampling.py:266-293): velocities AND scores of the two evaluations are averaged

@@ -342,6 +342,34 @@ def test_graphed_sampling_step_equals_eager_loop(cuda_dev, monkeypatch):
     assert torch.equal(xg, xe) and torch.equal(ug, ue) and torch.equal(xg2, xe)
 
 
+@pytest.mark.parametrize("exact", [False, True])
+def test_graphed_heun_equals_eager_loop(cuda_dev, monkeypatch, exact):
+    """HeunSampler on the fused decoder-epilogue step: three captured bodies (full / mid / last) replayed over a device
+    schedule table vs the eager loop launching the same kernels: bit-identical, for the re-use and the exact variant;
+    and the eager fused loop agrees with the unfused one (bf16 network output + separate update kernel) to bf16 accuracy."""
+    from deco_b200 import HeunSampler, LinearScheduler, ode_step_fn, simple_guidance_fn
+    from deco_b200 import sampling as S
+    cfg = O.DenoiserCfg(num_groups=8, hidden_size=576, num_blocks=5, num_cond_blocks=3, num_classes=10)
+    m, _ = build_module(cfg, cuda_dev)
+    noise = seeded_noise(3, (3, 64, 64), 7).to(cuda_dev)
+    cond = torch.tensor([2, 5, 8], device=cuda_dev)
+    unc = torch.full((3,), 10, device=cuda_dev)
+    sch = LinearScheduler()
+    kw = dict(scheduler=sch, w_scheduler=sch, exact_henu=exact, guidance_fn=simple_guidance_fn, num_steps=5, guidance=2.5,
+              guidance_interval_min=0.2, guidance_interval_max=0.9, timeshift=1.5, step_fn=ode_step_fn)
+    monkeypatch.setattr(S, "GRAPH", True)
+    sg = HeunSampler(**kw)
+    xg, ug = sg.sample_uint8(m, noise, cond, unc)
+    assert any(v[1] is not None for v in sg._steppers.values()), "the Heun steps were not captured into CUDA graphs"
+    xg2 = sg(m, noise, cond, unc)
+    monkeypatch.setattr(S, "GRAPH", False)
+    xe, ue = HeunSampler(**kw).sample_uint8(m, noise, cond, unc)
+    assert torch.equal(xg, xe) and torch.equal(ug, ue) and torch.equal(xg2, xe)
+    monkeypatch.setattr(S, "FUSED_STEP", False)
+    xu, _ = HeunSampler(**kw).sample_uint8(m, noise, cond, unc)
+    assert rel_l2(xe, xu) < 1e-2
+
+
 def test_step_time_vs_pytorch_eager_on_the_same_gpu(cuda_dev):
     """Not a parity test: times one CFG-batched XL/16 denoiser step (64 rows of 256 x 256 = the 8-GPU shard of BASELINE
     configs[1]) through deco_b200 and through the oracle's plain PyTorch ops under bf16 autocast -- the numerics and library
