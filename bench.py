@@ -749,6 +749,52 @@ def run_train(args):
             D.all_reduce_gradients(params, world)      # one bucket after the backward
         return d["loss"].detach()
 
+    def train_parity():
+        """parameter gradients of 2 images on the bench architecture against autograd over the fp32 oracle (checker only).
+        north_star states no gradient tolerance; the bar of tests/test_gpu_backward.py (global rel-L2 <= 2e-2, worst tensor
+        <= 6e-2: bf16 GEMM operands in forward AND backward) is applied and the per-tensor maxima are reported.  Runs after
+        the timed regions, inside its own scope, so no autograd graph of it is alive while a step is captured or timed."""
+        if args.no_parity or args.profile:
+            return None
+        from oracle import deco_oracle as O
+        _, Pd = _oracle_forward(wl, net, dev)
+        xs = x_host[0][:2].to(dev)
+        ys = torch.tensor([17, 1000], device=dev)
+        tt = torch.tensor([0.35, 0.8], device=dev)
+        g2 = torch.Generator(device=dev).manual_seed(5)
+        x_t, v_t = O.make_xt_vt(xs, torch.randn(xs.shape, device=dev, generator=g2), tt)
+        for p in params:
+            p.grad = None
+        lo = trainer.loss(net(x_t, tt, ys), v_t)["loss"]
+        lo.backward()
+        Pr = {k: v.clone().requires_grad_(True) for k, v in Pd.items()}
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            lr_ = O.dct_fm_loss(O.denoiser_forward(Pr, O.CFG_XL, x_t, tt, ys), v_t)["loss"]
+            lr_.backward()
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
+        per = []
+        num = den = 0.0
+        for n_, p in net.named_parameters():
+            a, b = p.grad.double(), Pr[n_].grad.double()
+            dn, dd = float((a - b).pow(2).sum()), float(b.pow(2).sum())
+            num, den = num + dn, den + dd
+            per.append(((dn / max(dd, 1e-300)) ** 0.5, n_))
+        per.sort(reverse=True)
+        e = (num / den) ** 0.5
+        parity = dict(grad_rel_l2=e, worst_tensors=[dict(name=n_, rel_l2=v) for v, n_ in per[:3]],
+                      loss=float(lo), loss_oracle=float(lr_), tol=dict(global_rel_l2=2e-2, per_tensor=6e-2),
+                      rows="2 images of the bench architecture (XL/16 256px), fixed t = (0.35, 0.8), labels (17, null)",
+                      against="torch autograd over the fp32 oracle on the same GPU, same weights",
+                      ok=bool(e <= 2e-2 and per[0][0] <= 6e-2))
+        for p in params:
+            p.grad = None
+        if not parity["ok"]:
+            raise SystemExit(f"bench: training parity check failed: {parity}")
+        return parity
+
     overlap_check = None
     if overlap:       # same seeded step through both averaging paths: the gradients must agree (fp32 atomics aside)
         got = []
@@ -857,6 +903,7 @@ def run_train(args):
         e2e = dict(value=B * world / (ms * 1e-3), unit=UNIT, h2d_bytes_per_step=B * 3 * res * res * 4 + B * 8,
                    d2h_bytes_per_step=4, ms_per_step=ms, loss=float(loss_host),
                    note="trainer(net, ...) + backward per step with pinned host images/labels copied in and the loss read back")
+    parity = train_parity()
     # optimizer tail (not part of `value`: BASELINE configs[3] names forward + backward): the fused AdamW + EMA kernel
     # alone, and a full iteration = step + optimizer + re-preparation of the bf16 / packed weights the next forward needs
     from deco_b200 import FusedAdamWEMA
@@ -919,7 +966,7 @@ def run_train(args):
                               measured="second pass of the same steps with CUDA events around every GEMM launch",
                               per_gpu_step_tflops_algorithmic=flops_step / (ms_per_step * 1e-3) / 1e12,
                               step_frac_of_peak=flops_step / (ms_per_step * 1e-3) / 1e12 / peaks["tf_sustained"]),
-                hbm_kernels=None, cpu_baseline=None, optimizer=optimizer)
+                parity=parity, hbm_kernels=None, cpu_baseline=None, optimizer=optimizer)
     print(json.dumps(line), flush=True)
 
 

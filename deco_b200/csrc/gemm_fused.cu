@@ -156,6 +156,9 @@ gemm_fused_kernel(const __grid_constant__ Maps maps, const Params P)
     const int num_tiles = num_m * num_n;
     const int num_k = (P.K + kBK - 1) / kBK;
     const int tile0 = blockIdx.x / 2, tile_stride = gridDim.x / 2;
+    // columns of the last column tile (stream GEMMs only; a multiple of 32, else the full-width MMA runs on zero padding)
+    const int n_rem = P.N - (num_n - 1) * C::kTileN;
+    const int n_last = (C::kStream && n_rem < BN && n_rem % 32 == 0) ? n_rem : BN;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&maps.a);
@@ -184,7 +187,9 @@ gemm_fused_kernel(const __grid_constant__ Maps maps, const Params P)
             for (int tile = tile0; tile < num_tiles; tile += tile_stride) {
                 const int m_blk = tile / num_n, n_blk = tile % num_n;
                 const int arow = (m_blk * 2 + (int)cta_rank) * kBM;
-                const int brow = n_blk * C::kTileN + (int)cta_rank * (BN / 2);
+                // a ragged last column tile of the stream GEMMs runs a NARROWER MMA (N = what is left) instead of multiplying
+                // zero padding: each CTA of the pair then supplies n_last / 2 weight rows, at the head of its B tile
+                const int brow = n_blk * C::kTileN + (int)cta_rank * ((C::kStream && n_blk == num_n - 1) ? n_last / 2 : BN / 2);
                 for (int kb = 0; kb < num_k; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     const uint32_t sa = smem_base + stage * C::kStageBytes;
@@ -207,6 +212,7 @@ gemm_fused_kernel(const __grid_constant__ Maps maps, const Params P)
                 mbar_wait(tempty_bar(as), aphase ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+                const uint32_t idesc_t = (C::kStream && (tile % num_n) == num_n - 1) ? make_idesc(2 * kBM, n_last) : idesc;
                 for (int kb = 0; kb < num_k; ++kb) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
@@ -214,7 +220,7 @@ gemm_fused_kernel(const __grid_constant__ Maps maps, const Params P)
                     const uint64_t da = make_sw128_desc(sa), db = make_sw128_desc(sa + kBM * kBK * 2);
 #pragma unroll
                     for (int k = 0; k < kBK / kUmmaK; ++k)
-                        umma_bf16_2sm(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+                        umma_bf16_2sm(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_t, (kb | k) ? 1u : 0u);
                     umma_commit_2sm(empty_bar(stage));
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                 }

@@ -263,6 +263,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const int num_k = (P.K + kBK - 1) / kBK;
     const int k_per = (num_k + split_k - 1) / split_k;      // host guarantees every slice is non-empty
     const int tile0 = blockIdx.x / CG, tile_stride = gridDim.x / CG;
+    // a ragged last column tile runs a NARROWER MMA (N = the columns that are left, when a multiple of 32) instead of
+    // multiplying zero padding: under the board power cap wasted MMA work costs clock, not just tensor-pipe time
+    const int n_rem = P.N - (num_n - 1) * BN;
+    const int n_last = (!TN && n_rem < BN && n_rem % 32 == 0) ? n_rem : BN;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
@@ -292,7 +296,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 const int mn = tile % num_mn, ks = tile / num_mn;
                 const int m_blk = mn / num_n, n_blk = mn % num_n;
                 const int arow = (m_blk * CG + (int)cta_rank) * kBM;
-                const int brow = n_blk * BN + (int)cta_rank * (BN / CG);
+                const int brow = n_blk * BN + (int)cta_rank * ((n_blk == num_n - 1 ? n_last : BN) / CG);
                 const int kb0 = ks * k_per, kb1 = min(num_k, kb0 + k_per);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1);
@@ -337,6 +341,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 mbar_wait(tempty_bar(as), aphase ^ 1);   // epilogues (of both CTAs) have drained this accumulator stage
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+                const uint32_t idesc_t = (!TN && ((tile % num_mn) % num_n) == num_n - 1) ? make_idesc(kBM * CG, n_last) : idesc;
                 const int kb0 = (tile / num_mn) * k_per, kb1 = min(num_k, kb0 + k_per);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(full_bar(stage), phase);
@@ -349,8 +354,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     constexpr uint64_t kstep = TN ? 128 : 2;
 #pragma unroll
                     for (int k = 0; k < kBK / kUmmaK; ++k) {
-                        if (CG == 2) umma_bf16_2sm(tmem_d, da + kstep * k, db + kstep * k, idesc, ((kb - kb0) | k) ? 1u : 0u);
-                        else umma_bf16(tmem_d, da + kstep * k, db + kstep * k, idesc, ((kb - kb0) | k) ? 1u : 0u);
+                        if (CG == 2) umma_bf16_2sm(tmem_d, da + kstep * k, db + kstep * k, idesc_t, ((kb - kb0) | k) ? 1u : 0u);
+                        else umma_bf16(tmem_d, da + kstep * k, db + kstep * k, idesc_t, ((kb - kb0) | k) ? 1u : 0u);
                     }
                     // frees the smem stage (in both CTAs) once these MMAs retire
                     if (CG == 2) umma_commit_2sm(empty_bar(stage)); else umma_commit(empty_bar(stage));
