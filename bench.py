@@ -966,6 +966,10 @@ def run_train(args):
                               measured="second pass of the same steps with CUDA events around every GEMM launch",
                               per_gpu_step_tflops_algorithmic=flops_step / (ms_per_step * 1e-3) / 1e12,
                               step_frac_of_peak=flops_step / (ms_per_step * 1e-3) / 1e12 / peaks["tf_sustained"]),
+                full_iteration=dict(ms=full_ms, value=B * world / (full_ms * 1e-3), unit=UNIT,
+                                    note="forward + backward + fused AdamW/EMA step + weight re-preparation (eager launches; the "
+                                         "re-preparation is a CUDA-graph replay): what one optimisation step of a training run "
+                                         "costs; `value` above is forward + backward only, as BASELINE configs[3] names it"),
                 parity=parity, hbm_kernels=None, cpu_baseline=None, optimizer=optimizer)
     print(json.dumps(line), flush=True)
 
