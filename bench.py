@@ -785,7 +785,7 @@ def run_train(args):
         per.sort(reverse=True)
         e = (num / den) ** 0.5
         parity = dict(grad_rel_l2=e, worst_tensors=[dict(name=n_, rel_l2=v) for v, n_ in per[:3]],
-                      loss=float(lo), loss_oracle=float(lr_), tol=dict(global_rel_l2=2e-2, per_tensor=6e-2),
+                      loss=float(lo.detach()), loss_oracle=float(lr_.detach()), tol=dict(global_rel_l2=2e-2, per_tensor=6e-2),
                       rows="2 images of the bench architecture (XL/16 256px), fixed t = (0.35, 0.8), labels (17, null)",
                       against="torch autograd over the fp32 oracle on the same GPU, same weights",
                       ok=bool(e <= 2e-2 and per[0][0] <= 6e-2))
@@ -903,7 +903,6 @@ def run_train(args):
         e2e = dict(value=B * world / (ms * 1e-3), unit=UNIT, h2d_bytes_per_step=B * 3 * res * res * 4 + B * 8,
                    d2h_bytes_per_step=4, ms_per_step=ms, loss=float(loss_host),
                    note="trainer(net, ...) + backward per step with pinned host images/labels copied in and the loss read back")
-    parity = train_parity()
     # optimizer tail (not part of `value`: BASELINE configs[3] names forward + backward): the fused AdamW + EMA kernel
     # alone, and a full iteration = step + optimizer + re-preparation of the bf16 / packed weights the next forward needs
     from deco_b200 import FusedAdamWEMA
@@ -936,6 +935,7 @@ def run_train(args):
                      frac=36.0 * nparam / (opt_ms * 1e-3) / 1e9 / measured_peaks()["hbm_gbs"],
                      iteration_with_optimizer_ms=full_ms,
                      note="iteration = forward + backward + optimizer + weight re-preparation (bf16 / packed copies)")
+    parity = train_parity()         # last: it leaves no gradients behind and sees the weights the optimizer section produced
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
