@@ -78,6 +78,8 @@ SIGNATURES = {
     "deco_train_timesteps": (_i, [_vp, _vp, _vp, _f, _i, _vp, _vp, _i, _vp]),
     "deco_flow_pair": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _ll, _vp]),
     "deco_label_dropout": (_i, [_vp, _vp, _vp, _f, _vp, _i, _vp]),
+    "deco_attention_bwd_tc": (_i, [_vp, _ll, _vp, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _vp, _ll, _vp, _vp,
+                                   _i, _i, _i, _i, _i, _f, _vp]),
     "deco_decoder_train_blob_floats": (_i, [_i]),
     "deco_pixel_decoder_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "deco_decoder_bwd_blob_bytes": (_i, [_i]),

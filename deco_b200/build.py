@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_C")
 LIB = os.path.join(OUT_DIR, "libdeco_b200.so")
 SOURCES = ["api.cu", "dct_loss.cu", "sampler.cu", "elementwise.cu", "decoder.cu", "attention_tc.cu", "gemm_tcgen05.cu", "gemm_fused.cu",
-           "backward.cu", "attention_bwd.cu", "decoder_bwd.cu", "decoder_bwd_mma.cu", "optimizer.cu", "baseline_head.cu", "train_inputs.cu", "decoder_tc.cu", "nerf_decoder.cu"]
+           "backward.cu", "attention_bwd.cu", "decoder_bwd.cu", "decoder_bwd_mma.cu", "optimizer.cu", "baseline_head.cu", "train_inputs.cu", "decoder_tc.cu", "nerf_decoder.cu", "attention_bwd_tc.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC"]
@@ -45,7 +45,7 @@ def build(force: bool = False, verbose: bool = True) -> str:
         subprocess.run(cmd, check=True)
         return obj
 
-    with ThreadPoolExecutor(max_workers=min(18, len(SOURCES))) as ex:
+    with ThreadPoolExecutor(max_workers=min(19, len(SOURCES))) as ex:
         objs = list(ex.map(compile_one, SOURCES))
     cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-cudart", "shared", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
     if verbose:

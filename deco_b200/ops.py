@@ -15,6 +15,7 @@ from ._lib import call, ptr
 EPI_BIAS, EPI_BIAS_SILU, EPI_GATE_RESIDUAL, EPI_SWIGLU, EPI_BIAS_F32 = 0, 1, 2, 3, 4
 bf16 = torch.bfloat16
 gemm_probe = None   # set to a deco_b200.utils.GemmProbe to time every GEMM launch with CUDA events
+ATTN_BWD = __import__("os").environ.get("DECO_B200_ATTN_BWD", "tc")     # "tc" (tcgen05) | "legacy" (mma.sync)
 
 
 def _cuda(*ts):
@@ -721,6 +722,14 @@ def attention_bwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, o: torch.Te
     if lse is not None:
         assert lse.dtype == torch.float32 and lse.is_contiguous() and lse.numel() == n
     ws = torch.empty((2, n), dtype=torch.float32, device=q.device)
+    aligned = all(t.stride(0) % 8 == 0 and t.data_ptr() % 16 == 0 for t in (q, k, v, o, dout, dq, dk, dv))
+    if lse is not None and ATTN_BWD == "tc" and aligned:
+        # tcgen05 / TMEM kernels (csrc/attention_bwd_tc.cu); the mma.sync pair below stays as the A/B variant
+        # (DECO_B200_ATTN_BWD=legacy) and for callers without the forward's statistics
+        call("deco_attention_bwd_tc", ptr(q), q.stride(0), ptr(k), ptr(v), k.stride(0), ptr(o), o.stride(0), ptr(dout),
+             dout.stride(0), ptr(dq), dq.stride(0), ptr(dk), ptr(dv), dk.stride(0), ptr(lse), ptr(ws[1]), B, heads, Lq, Lk,
+             head_dim, float(head_dim) ** -0.5, _st(q))
+        return
     call("deco_attention_bwd", ptr(q), q.stride(0), ptr(k), ptr(v), k.stride(0), ptr(o), o.stride(0), ptr(dout),
          dout.stride(0), ptr(dq), dq.stride(0), ptr(dk), ptr(dv), dk.stride(0), ptr(lse if lse is not None else ws[0]),
          ptr(ws[1]), int(lse is not None), B, heads, Lq, Lk, head_dim, float(head_dim) ** -0.5, _st(q))

@@ -183,6 +183,15 @@ int deco_nerf_decoder_blob_bytes(int num_nerf_blocks);
 int deco_nerf_decoder(const float* x, const void* const* params, int num_nerf_blocks, const void* blob,
                       void* out, int out_is_bf16, int B, int H, int W, int patch, int hidden_x, int mlp_ratio, void* stream);
 
+/* deco_attention_bwd on tcgen05 / TMEM (csrc/attention_bwd_tc.cu): same two deterministic passes and outputs; needs the
+ * forward's statistics lse2 [B*heads*Lq] (deco_attention_fwd_lse); delta_ws [B*heads*Lq] fp32 is scratch filled by the first
+ * pass.  All row strides multiples of 8 elements, pointers 16-byte aligned. */
+int deco_attention_bwd_tc(const void* q, long long q_stride, const void* k, const void* v, long long kv_stride,
+                          const void* o, long long o_stride, const void* dout, long long do_stride,
+                          void* dq, long long dq_stride, void* dk, void* dv, long long dkv_stride,
+                          const float* lse2, float* delta_ws, int B, int heads, int Lq, int Lk, int head_dim,
+                          float scale, void* stream);
+
 /* Training-step inputs (src/diffusion/flow_matching/training_repa_DeCo.py:222-237, src/diffusion/base/training.py:14-20).
  * The random draws stay the caller's (torch's CUDA generator, reference order); these fuse what follows them.
  * deco_train_timesteps: t = time_shift(where(u_select <= 0.9, sigmoid(nt), u_uniform)) (fp32 [B]); with
