@@ -486,11 +486,15 @@ def test_extended_sampler_control_flow_matches_reference(monkeypatch):
     # the reference's GVP derivatives carry no pi/2 factor: dalpha/alpha = -tan(pi/4) = -1, sden = sin^2 + sin cos = 1
     assert abs(kd + 1.0) < 1e-6 and abs(sden - 1.0) < 1e-6
     assert abs(a_s - 0.25) < 1e-7 and abs(a_n - np.sqrt(0.5)) < 1e-6
-    # the reference's guards: an SDE step needs a w_scheduler (sampling.py:61); Heun / Adams stay ODE-only here
+    # the reference's guards: an SDE step needs a w_scheduler (sampling.py:61, :225); Heun takes the SDE step functions too
+    # (scores averaged, sampling.py:283-291), an unknown step function is refused
     with pytest.raises(AssertionError):
         EulerSampler(scheduler=sch, step_fn=sde_step_fn, num_steps=2)
+    with pytest.raises(AssertionError):
+        HeunSampler(scheduler=sch, step_fn=sde_step_fn, num_steps=2)
+    assert HeunSampler(scheduler=sch, w_scheduler=sch, step_fn=sde_step_fn, num_steps=2)._kinds == ("sde_step_fn", "ode_step_fn")
     with pytest.raises(NotImplementedError):
-        HeunSampler(scheduler=sch, w_scheduler=sch, step_fn=sde_step_fn, num_steps=2)
+        HeunSampler(scheduler=sch, w_scheduler=sch, step_fn=lambda x, v, dt, s, w: x, num_steps=2)
 
 
 BASELINE_JIT_YAML = """
