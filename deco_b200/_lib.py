@@ -59,11 +59,14 @@ SIGNATURES = {
     "deco_transpose_cast": (_i, [_vp, _i, _ll, _vp, _ll, _i, _i, _i, _vp]),
     "deco_colsum": (_i, [_vp, _i, _ll, _vp, _ll, _i, _vp]),
     "deco_gate_residual": (_i, [_vp, _vp, _vp, _ll, _vp, _i, _ll, _i, _vp]),
+    "deco_gate_residual_norm": (_i, [_vp, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _ll, _i, _vp, _ll, _i, _f, _vp]),
     "deco_gate_bwd": (_i, [_vp, _vp, _vp, _ll, _vp, _vp, _ll, _vp, _vp, _i, _ll, _i, _vp]),
     "deco_silu_add_rows_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _vp]),
     "deco_swiglu_fwd": (_i, [_vp, _vp, _ll, _i, _vp]),
     "deco_swiglu_bwd": (_i, [_vp, _vp, _vp, _ll, _i, _vp]),
     "deco_rmsnorm_modulate_bwd": (_i, [_vp, _vp, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _ll, _vp, _vp, _i, _ll, _i, _f, _vp]),
+    "deco_rmsnorm_modulate_bwd_gate": (_i, [_vp, _vp, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _ll, _vp, _vp, _i, _ll, _i, _f,
+                                            _vp, _vp, _ll, _vp, _vp, _ll, _vp, _vp, _vp]),
     "deco_headnorm_rope_bwd": (_i, [_vp, _ll, _vp, _ll, _i, _vp, _vp, _vp, _ll, _i, _i, _i, _f, _vp]),
     "deco_cond_combine_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "deco_silu_bwd": (_i, [_vp, _vp, _vp, _ll, _vp]),

@@ -24,6 +24,7 @@ bf16 = torch.bfloat16
 F32 = torch.float32
 WGRAD = os.environ.get("DECO_B200_WGRAD", "tn")                # "tn" (product path) | "transpose" (A/B check)
 DECODER_BWD = os.environ.get("DECO_B200_DECODER_BWD", "mma")   # "mma" (product path) | "scalar" (A/B check)
+FUSE_GATE_NORM = os.environ.get("DECO_B200_FUSE_GATE_NORM", "1") != "0"   # residual add + next norm in one kernel
 
 
 # Called with lists of gradient tensors the moment they are final (per DiT block, walking backwards, then the tail): lets a
@@ -168,23 +169,39 @@ def train_forward(module, x32, t, y):
     s = ops.gemm(xp, P["ws"], P["bs"], ops.EPI_BIAS_F32)
     S.update(xp=xp, tfreq=tfreq, z1=z1, h1t=h1t, temb=temb, c=c, mod=mod)
     blocks = []
-    for i, bp in enumerate(P["blocks"]):
+    nb = len(P["blocks"])
+
+    def mod6(i):
         m = mod[:, i * 6 * H:(i + 1) * 6 * H]
-        sh1, sc1, g1, sh2, sc2, g2 = (m[:, j * H:(j + 1) * H] for j in range(6))
-        h1 = ops.rmsnorm_modulate(s, bp["n1"], sh1, sc1, L)
+        return tuple(m[:, j * H:(j + 1) * H] for j in range(6))
+
+    h1 = None
+    for i, bp in enumerate(P["blocks"]):
+        sh1, sc1, g1, sh2, sc2, g2 = mod6(i)
+        if h1 is None:
+            h1 = ops.rmsnorm_modulate(s, bp["n1"], sh1, sc1, L)
         qkv_raw = ops.gemm(h1, bp["wqkv"], None, ops.EPI_BIAS)
         qkv = torch.empty_like(qkv_raw)          # q, k normalised + rotated here; v is read from the raw GEMM output
         ops.qknorm_rope_to(qkv_raw, qkv, bp["qn"], bp["kn"], pos, heads, d, L)
         o, lse = ops.attention_lse(qkv[:, :H], qkv[:, H:2 * H], qkv_raw[:, 2 * H:], B, heads, d)
         a1 = ops.gemm(o, bp["wproj"], bp["bproj"], ops.EPI_BIAS)
-        s_mid = ops.gate_residual(s, a1, g1, L)
-        h2 = ops.rmsnorm_modulate(s_mid, bp["n2"], sh2, sc2, L)
+        # residual add + the norm that feeds the next GEMM in one pass over the row (FUSE_GATE_NORM=0: the two kernels)
+        if FUSE_GATE_NORM:
+            s_mid, h2 = ops.gate_residual_norm(s, a1, g1, L, bp["n2"], sh2, sc2)
+        else:
+            s_mid = ops.gate_residual(s, a1, g1, L)
+            h2 = ops.rmsnorm_modulate(s_mid, bp["n2"], sh2, sc2, L)
         y13 = ops.gemm(h2, bp["w13"], None, ops.EPI_BIAS)
         u = ops.swiglu_fwd(y13)
         a2 = ops.gemm(u, bp["w2"], None, ops.EPI_BIAS)
-        s_out = ops.gate_residual(s_mid, a2, g2, L)
+        h1_next = None
+        if FUSE_GATE_NORM and i + 1 < nb:
+            nsh1, nsc1 = mod6(i + 1)[:2]
+            s_out, h1_next = ops.gate_residual_norm(s_mid, a2, g2, L, P["blocks"][i + 1]["n1"], nsh1, nsc1)
+        else:
+            s_out = ops.gate_residual(s_mid, a2, g2, L)
         blocks.append(dict(s_in=s, h1=h1, qkv_raw=qkv_raw, qkv=qkv, o=o, lse=lse, a1=a1, s_mid=s_mid, h2=h2, y13=y13, u=u, a2=a2))
-        s = s_out
+        s, h1 = s_out, h1_next
     s2 = ops.silu_add_rows(s, temb, L)
     ycond = ops.gemm(s2, P["wcond"], P["bcond"], ops.EPI_BIAS)
     R = module.num_blocks - module.num_cond_blocks
@@ -253,6 +270,7 @@ def train_backward(module, S: dict, dout: torch.Tensor) -> Dict[str, torch.Tenso
     dmod = z(B, nb * 6 * H)
     mod = S["mod"]
     zblk = z(max(nb, 1), 3 * H + 2 * d)       # one fill for the per-block vector gradients (norm1/2, proj bias, q/k-norm)
+    da2 = None
     for i in reversed(range(nb)):
         bp, bt, sv = P["blocks"][i], T["blocks"][i], S["blocks"][i]
         pre = f"blocks.{i}."
@@ -262,8 +280,10 @@ def train_backward(module, S: dict, dout: torch.Tensor) -> Dict[str, torch.Tenso
         dsh1, dsc1, dg1, dsh2, dsc2, dg2 = (dm[:, j * H:(j + 1) * H] for j in range(6))
         F_ = module.blocks[i].mlp.w1.weight.shape[0]
         Fp = P["ffn_pad"]
-        # MLP branch
-        da2 = ops.gate_bwd(ds, sv["a2"], g2, dg2, L)
+        # MLP branch (da2: gate_bwd of this block's second residual add -- computed by the fused kernel at the end of the
+        # previous iteration, or here for the last block)
+        if da2 is None:
+            da2 = ops.gate_bwd(ds, sv["a2"], g2, dg2, L)
         gw2 = _wgrad(da2, sv["u"])
         G[pre + "mlp.w2.weight"] = gw2 if F_ == Fp else gw2[:, :F_].contiguous()
         du = ops.gemm(da2, bt["w2T"], None, ops.EPI_BIAS)
@@ -273,11 +293,16 @@ def train_backward(module, S: dict, dout: torch.Tensor) -> Dict[str, torch.Tenso
         G[pre + "mlp.w3.weight"] = dw13[:, 1].reshape(Fp, H)[:F_]
         dh2 = ops.gemm(dy13, bt["w13T"], None, ops.EPI_BIAS)
         dn2, dn1, dbproj, dqn, dkn = zblk[i, :H], zblk[i, H:2 * H], zblk[i, 2 * H:3 * H], zblk[i, 3 * H:3 * H + d], zblk[i, 3 * H + d:]
-        ops.rmsnorm_modulate_bwd_(ds, dh2, sv["s_mid"], bp["n2"], sc2, dn2, dsh2, dsc2, L)
+        # norm2 backward + the gate backward of the attention branch's residual add, one pass over ds
+        if FUSE_GATE_NORM:
+            da1 = ops.rmsnorm_modulate_bwd_gate_(ds, dh2, sv["s_mid"], bp["n2"], sc2, dn2, dsh2, dsc2, L, sv["a1"], g1, dg1,
+                                                 dbias=dbproj)
+        else:
+            ops.rmsnorm_modulate_bwd_(ds, dh2, sv["s_mid"], bp["n2"], sc2, dn2, dsh2, dsc2, L)
+            da1 = ops.gate_bwd(ds, sv["a1"], g1, dg1, L, dbias=dbproj)
         G[pre + "norm2.weight"] = dn2
         del da2, du, dy13, dh2
         # attention branch
-        da1 = ops.gate_bwd(ds, sv["a1"], g1, dg1, L, dbias=dbproj)
         G[pre + "attn.proj.bias"] = dbproj
         G[pre + "attn.proj.weight"] = _wgrad(da1, sv["o"])
         do = ops.gemm(da1, bt["wprojT"], None, ops.EPI_BIAS)
@@ -290,7 +315,13 @@ def train_backward(module, S: dict, dout: torch.Tensor) -> Dict[str, torch.Tenso
         G[pre + "attn.q_norm.weight"], G[pre + "attn.k_norm.weight"] = dqn, dkn
         G[pre + "attn.qkv.weight"] = _wgrad(dqkv, sv["h1"])
         dh1 = ops.gemm(dqkv, bt["wqkvT"], None, ops.EPI_BIAS)
-        ops.rmsnorm_modulate_bwd_(ds, dh1, sv["s_in"], bp["n1"], sc1, dn1, dsh1, dsc1, L)
+        da2 = None
+        if FUSE_GATE_NORM and i > 0:      # norm1 backward + the gate backward of block i - 1's second residual add
+            mp, dmp = mod[:, (i - 1) * 6 * H:i * 6 * H], dmod[:, (i - 1) * 6 * H:i * 6 * H]
+            da2 = ops.rmsnorm_modulate_bwd_gate_(ds, dh1, sv["s_in"], bp["n1"], sc1, dn1, dsh1, dsc1, L, S["blocks"][i - 1]["a2"],
+                                                 mp[:, 5 * H:6 * H], dmp[:, 5 * H:6 * H])
+        else:
+            ops.rmsnorm_modulate_bwd_(ds, dh1, sv["s_in"], bp["n1"], sc1, dn1, dsh1, dsc1, L)
         G[pre + "norm1.weight"] = dn1
         del da1, do, dqkv, dh1
         S["blocks"][i] = None   # release the block's activations

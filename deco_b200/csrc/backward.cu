@@ -280,11 +280,25 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_rowstats_kernel(
     }
 }
 
+// kGate: the gate_bwd_kernel work of the branch that is differentiated NEXT (its residual add consumed the same stream
+// gradient) rides along: da = gate2 * ds_new, dgate2 += sum_rows ds_new * a, usum2 += sum_rows ds_new -- the updated
+// stream gradient is used while it is still in registers instead of being re-read by a second kernel.
+struct GateBwdArgs {
+    const __nv_bfloat16* a;
+    const __nv_bfloat16* gate;
+    long long gate_stride;
+    __nv_bfloat16* da;
+    float* dgate;
+    long long dgate_stride;
+    float* usum;
+};
+
+template <bool kGate>
 __global__ void __launch_bounds__(512) rmsnorm_modulate_bwd_kernel(
     const __nv_bfloat16* __restrict__ dh, const float* __restrict__ x, const float* __restrict__ w,
     const __nv_bfloat16* __restrict__ scale, long long mod_stride, const float2* __restrict__ stats, float* __restrict__ ds,
     float* __restrict__ tsum, float* __restrict__ dshift, long long dmod_stride,
-    int L, int RB, int Hd)
+    int L, int RB, int Hd, const GateBwdArgs G)
 {
     // tsum [B, Hd]: per-image sums T = sum_rows dh * xhat; d scale = w * T and d w = sum_b (1 + scale[b]) * T are formed
     // by rmsnorm_bwd_finalize_kernel (one atomic target per (image, column) instead of 1024 blocks hammering dw[Hd])
@@ -301,6 +315,12 @@ __global__ void __launch_bounds__(512) rmsnorm_modulate_bwd_kernel(
         sc1[0] = 1.0f + q0.x; sc1[1] = 1.0f + q0.y; sc1[2] = 1.0f + q1.x; sc1[3] = 1.0f + q1.y;
     }
     float a_sh[4] = {0.f, 0.f, 0.f, 0.f}, a_t[4] = {0.f, 0.f, 0.f, 0.f};
+    float g2[4] = {0.f, 0.f, 0.f, 0.f}, accg[4] = {0.f, 0.f, 0.f, 0.f}, accb[4] = {0.f, 0.f, 0.f, 0.f};
+    if (kGate) {
+        const uint2 q = *reinterpret_cast<const uint2*>(G.gate + b * G.gate_stride + c);
+        const float2 q0 = unpack_bf2(q.x), q1 = unpack_bf2(q.y);
+        g2[0] = q0.x; g2[1] = q0.y; g2[2] = q1.x; g2[3] = q1.y;
+    }
 #pragma unroll 4
     for (int i = 0; i < RB; ++i) {
         const long long r = r0 + i;
@@ -320,11 +340,23 @@ __global__ void __launch_bounds__(512) rmsnorm_modulate_bwd_kernel(
         }
         d4.x += o[0]; d4.y += o[1]; d4.z += o[2]; d4.w += o[3];
         *dp = d4;
+        if (kGate) {
+            const uint2 qa = *reinterpret_cast<const uint2*>(G.a + r * Hd + c);
+            const float2 a0 = unpack_bf2(qa.x), a1 = unpack_bf2(qa.y);
+            *reinterpret_cast<uint2*>(G.da + r * Hd + c) = make_uint2(pack_bf2(g2[0] * d4.x, g2[1] * d4.y), pack_bf2(g2[2] * d4.z, g2[3] * d4.w));
+            accg[0] = fmaf(d4.x, a0.x, accg[0]); accg[1] = fmaf(d4.y, a0.y, accg[1]);
+            accg[2] = fmaf(d4.z, a1.x, accg[2]); accg[3] = fmaf(d4.w, a1.y, accg[3]);
+            accb[0] += d4.x; accb[1] += d4.y; accb[2] += d4.z; accb[3] += d4.w;
+        }
     }
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         atomicAdd(dshift + b * dmod_stride + c + e, a_sh[e]);
         atomicAdd(tsum + b * Hd + c + e, a_t[e]);
+        if (kGate) {
+            atomicAdd(G.dgate + b * G.dgate_stride + c + e, accg[e]);
+            if (G.usum) atomicAdd(G.usum + b * Hd + c + e, accb[e]);
+        }
     }
 }
 
@@ -564,11 +596,11 @@ extern "C" int deco_swiglu_bwd(const void* y13_bf16, const void* du_bf16, void* 
     return DECO_OK;
 }
 
-extern "C" int deco_rmsnorm_modulate_bwd(const void* dh_bf16, const float* x, const float* weight, const void* scale_bf16,
-                                         long long mod_row_stride, float* ds_accum, float* dweight_accum,
-                                         float* dshift_accum, float* dscale_accum, long long dmod_row_stride,
-                                         float* row_ws, float* img_ws, int rows_per_image, long long M, int hidden, float eps,
-                                         void* stream)
+static int rmsnorm_modulate_bwd_impl(const void* dh_bf16, const float* x, const float* weight, const void* scale_bf16,
+                                     long long mod_row_stride, float* ds_accum, float* dweight_accum,
+                                     float* dshift_accum, float* dscale_accum, long long dmod_row_stride,
+                                     float* row_ws, float* img_ws, int rows_per_image, long long M, int hidden, float eps,
+                                     const deco::GateBwdArgs* gate, void* stream)
 {
     using namespace deco;
     DECO_CHECK_ARG(dh_bf16 && x && weight && scale_bf16 && ds_accum && dweight_accum && dshift_accum && dscale_accum && row_ws &&
@@ -587,13 +619,57 @@ extern "C" int deco_rmsnorm_modulate_bwd(const void* dh_bf16, const float* x, co
         rmsnorm_bwd_rowstats_kernel<16><<<g1, 256, 0, st>>>(dhp, x, weight, scp, mod_row_stride, stats, rows_per_image, M, hidden, eps);
     DECO_CHECK_LAUNCH("rmsnorm_bwd_rowstats_kernel");
     const int rb = rows_block(rows_per_image, M);
-    rmsnorm_modulate_bwd_kernel<<<(unsigned)(M / rb), ((hidden / 4) + 31) / 32 * 32, 0, st>>>(
-        dhp, x, weight, scp, mod_row_stride, stats, ds_accum, img_ws, dshift_accum, dmod_row_stride, rows_per_image, rb, hidden);
+    if (gate)
+        rmsnorm_modulate_bwd_kernel<true><<<(unsigned)(M / rb), ((hidden / 4) + 31) / 32 * 32, 0, st>>>(
+            dhp, x, weight, scp, mod_row_stride, stats, ds_accum, img_ws, dshift_accum, dmod_row_stride, rows_per_image, rb, hidden, *gate);
+    else
+        rmsnorm_modulate_bwd_kernel<false><<<(unsigned)(M / rb), ((hidden / 4) + 31) / 32 * 32, 0, st>>>(
+            dhp, x, weight, scp, mod_row_stride, stats, ds_accum, img_ws, dshift_accum, dmod_row_stride, rows_per_image, rb, hidden,
+            GateBwdArgs{});
     DECO_CHECK_LAUNCH("rmsnorm_modulate_bwd_kernel");
     rmsnorm_bwd_finalize_kernel<<<(hidden + 31) / 32, dim3(32, 32), 0, st>>>(img_ws, weight, scp, mod_row_stride, dscale_accum,
                                                                        dmod_row_stride, dweight_accum,
                                                                        (int)(M / rows_per_image), hidden);
     DECO_CHECK_LAUNCH("rmsnorm_bwd_finalize_kernel");
+    return DECO_OK;
+}
+
+extern "C" int deco_rmsnorm_modulate_bwd(const void* dh_bf16, const float* x, const float* weight, const void* scale_bf16,
+                                         long long mod_row_stride, float* ds_accum, float* dweight_accum,
+                                         float* dshift_accum, float* dscale_accum, long long dmod_row_stride,
+                                         float* row_ws, float* img_ws, int rows_per_image, long long M, int hidden, float eps,
+                                         void* stream)
+{
+    return rmsnorm_modulate_bwd_impl(dh_bf16, x, weight, scale_bf16, mod_row_stride, ds_accum, dweight_accum, dshift_accum,
+                                     dscale_accum, dmod_row_stride, row_ws, img_ws, rows_per_image, M, hidden, eps, nullptr, stream);
+}
+
+// deco_rmsnorm_modulate_bwd followed by deco_gate_bwd on the UPDATED stream gradient, in one pass over it: the backward of
+// "s_mid = s + gate * a; h = norm(s_mid)" seen from the norm's side (training backward; dit_c2i_DeCo.py:236-244 reversed).
+// gate_img_ws [B, hidden] zeroed fp32 is needed only with dbias_accum.
+extern "C" int deco_rmsnorm_modulate_bwd_gate(const void* dh_bf16, const float* x, const float* weight, const void* scale_bf16,
+                                              long long mod_row_stride, float* ds_accum, float* dweight_accum,
+                                              float* dshift_accum, float* dscale_accum, long long dmod_row_stride,
+                                              float* row_ws, float* img_ws, int rows_per_image, long long M, int hidden, float eps,
+                                              const void* a_bf16, const void* gate_bf16, long long gate_stride, void* da_bf16,
+                                              float* dgate_accum, long long dgate_stride, float* dbias_accum, float* gate_img_ws,
+                                              void* stream)
+{
+    using namespace deco;
+    DECO_CHECK_ARG(a_bf16 && gate_bf16 && da_bf16 && dgate_accum, "rmsnorm_modulate_bwd_gate: null pointer");
+    DECO_CHECK_ARG(!dbias_accum || gate_img_ws, "rmsnorm_modulate_bwd_gate: the bias gradient needs the zeroed [B, hidden] workspace");
+    DECO_CHECK_ARG(gate_stride % 4 == 0, "rmsnorm_modulate_bwd_gate: bad gate stride");
+    GateBwdArgs G;
+    G.a = (const __nv_bfloat16*)a_bf16; G.gate = (const __nv_bfloat16*)gate_bf16; G.gate_stride = gate_stride;
+    G.da = (__nv_bfloat16*)da_bf16; G.dgate = dgate_accum; G.dgate_stride = dgate_stride; G.usum = dbias_accum ? gate_img_ws : nullptr;
+    int rc = rmsnorm_modulate_bwd_impl(dh_bf16, x, weight, scale_bf16, mod_row_stride, ds_accum, dweight_accum, dshift_accum,
+                                       dscale_accum, dmod_row_stride, row_ws, img_ws, rows_per_image, M, hidden, eps, &G, stream);
+    if (rc) return rc;
+    if (dbias_accum) {
+        gate_bias_finalize_kernel<<<(hidden + 31) / 32, dim3(32, 32), 0, (cudaStream_t)stream>>>(
+            (const __nv_bfloat16*)gate_bf16, gate_stride, gate_img_ws, dbias_accum, (int)(M / rows_per_image), hidden);
+        DECO_CHECK_LAUNCH("gate_bias_finalize_kernel");
+    }
     return DECO_OK;
 }
 

@@ -133,6 +133,73 @@ __global__ void __launch_bounds__(256) rmsnorm_modulate_kernel(
     }
 }
 
+// ---------------------------------------------------------------- gated residual + the next RMSNorm / modulation in one pass
+//   s_out = s + gate[b] * a   (fp32 stream)   and   h = rms(s_out) * w * (1 + scale[b]) + shift[b]   (bf16)
+// (training forward: dit_c2i_DeCo.py:236-244, the residual add of one branch followed by the norm that feeds the next
+// GEMM).  A warp owns a row and keeps it in registers between the two halves, so s_out is written once and never re-read.
+// Same arithmetic, in the same order, as gate_residual_kernel followed by rmsnorm_modulate_kernel<float>.
+template <int kMaxChunks>
+__global__ void __launch_bounds__(256) gate_residual_norm_kernel(
+    const float* s, const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ gate, long long gate_stride,
+    float* s_out, const float* __restrict__ w, const __nv_bfloat16* __restrict__ shift, const __nv_bfloat16* __restrict__ scale,
+    long long mod_row_stride, int rows_per_mod, __nv_bfloat16* __restrict__ h_out, long long M, int Hd, float eps)
+{
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const int nch = Hd >> 3;
+    const long long mrow = row / rows_per_mod;
+    const uint4* grow = reinterpret_cast<const uint4*>(gate + mrow * gate_stride);
+    float v[kMaxChunks][8];
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < kMaxChunks; ++j) {
+        const int ch = lane + j * 32;
+        if (ch < nch) {
+            float av[8];
+            load8<float>(s + row * Hd + ch * 8, v[j]);
+            load8<__nv_bfloat16>(a + row * Hd + ch * 8, av);
+            const uint4 g4 = __ldg(grow + ch);
+            const uint32_t gw[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 g2 = unpack_bf2(gw[e]);
+                v[j][2 * e] = fmaf(g2.x, av[2 * e], v[j][2 * e]);
+                v[j][2 * e + 1] = fmaf(g2.y, av[2 * e + 1], v[j][2 * e + 1]);
+            }
+            float4* op = reinterpret_cast<float4*>(s_out + row * Hd + ch * 8);
+            op[0] = make_float4(v[j][0], v[j][1], v[j][2], v[j][3]);
+            op[1] = make_float4(v[j][4], v[j][5], v[j][6], v[j][7]);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) ss = fmaf(v[j][e], v[j][e], ss);
+        }
+    }
+    ss = warp_sum(ss);
+    const float rs = rsqrtf(ss / (float)Hd + eps);
+    const uint4* shr = reinterpret_cast<const uint4*>(shift + mrow * mod_row_stride);
+    const uint4* scr = reinterpret_cast<const uint4*>(scale + mrow * mod_row_stride);
+    uint4* orow = reinterpret_cast<uint4*>(h_out + row * Hd);
+#pragma unroll
+    for (int j = 0; j < kMaxChunks; ++j) {
+        const int ch = lane + j * 32;
+        if (ch < nch) {
+            const float4 w0 = __ldg(reinterpret_cast<const float4*>(w) + ch * 2);
+            const float4 w1 = __ldg(reinterpret_cast<const float4*>(w) + ch * 2 + 1);
+            const uint4 sh = __ldg(shr + ch), sc = __ldg(scr + ch);
+            const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+            const uint32_t shw[4] = {sh.x, sh.y, sh.z, sh.w}, scw[4] = {sc.x, sc.y, sc.z, sc.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 s2 = unpack_bf2(shw[e]), c2 = unpack_bf2(scw[e]);
+                const float n0 = v[j][2 * e] * rs, n1 = v[j][2 * e + 1] * rs;
+                o[e] = pack_bf2(fmaf(wv[2 * e] * n0, 1.0f + c2.x, s2.x), fmaf(wv[2 * e + 1] * n1, 1.0f + c2.y, s2.y));
+            }
+            orow[ch] = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+    }
+}
+
 // ---------------------------------------------------------------- per-head RMSNorm + 2-D RoPE, in place
 // buf: [M, row_stride]; segment 0 starts at column col0 (weights qw), optional segment 1 at col1 (weights kw); each
 // segment is heads x D.  One thread per (token, segment, head) vector of D elements.
@@ -325,6 +392,28 @@ extern "C" int deco_rmsnorm_modulate(const void* x, int x_is_f32, const float* w
     else { if (hidden <= 1280) RMS_LAUNCH(__nv_bfloat16, 5); else RMS_LAUNCH(__nv_bfloat16, 8); }
 #undef RMS_LAUNCH
     DECO_CHECK_LAUNCH("rmsnorm_modulate_kernel");
+    return DECO_OK;
+}
+
+extern "C" int deco_gate_residual_norm(const float* s, const void* a_bf16, const void* gate_bf16, long long gate_stride,
+                                       float* s_out, const float* weight, const void* shift_bf16, const void* scale_bf16,
+                                       long long mod_row_stride, int rows_per_image, void* h_out_bf16, long long M, int hidden,
+                                       float eps, void* stream) {
+    using namespace deco;
+    DECO_CHECK_ARG(s && a_bf16 && gate_bf16 && s_out && weight && shift_bf16 && scale_bf16 && h_out_bf16, "gate_residual_norm: null pointer");
+    DECO_CHECK_ARG(M > 0 && hidden % 8 == 0 && hidden <= 2048 && rows_per_image > 0 && mod_row_stride % 8 == 0 && gate_stride % 8 == 0,
+                   "gate_residual_norm: unsupported M=%lld hidden=%d", M, hidden);
+    DECO_CHECK_ARG((((uintptr_t)s | (uintptr_t)a_bf16 | (uintptr_t)gate_bf16 | (uintptr_t)s_out | (uintptr_t)weight | (uintptr_t)shift_bf16 |
+                     (uintptr_t)scale_bf16 | (uintptr_t)h_out_bf16) & 15) == 0, "gate_residual_norm: pointers must be 16-byte aligned");
+    const int warps = 8;
+    const unsigned grid = (unsigned)((M + warps - 1) / warps);
+    cudaStream_t st = (cudaStream_t)stream;
+#define GRN_LAUNCH(C) gate_residual_norm_kernel<C><<<grid, warps * 32, 0, st>>>( \
+        s, (const __nv_bfloat16*)a_bf16, (const __nv_bfloat16*)gate_bf16, gate_stride, s_out, weight, (const __nv_bfloat16*)shift_bf16, \
+        (const __nv_bfloat16*)scale_bf16, mod_row_stride, rows_per_image, (__nv_bfloat16*)h_out_bf16, M, hidden, eps)
+    if (hidden <= 1280) GRN_LAUNCH(5); else GRN_LAUNCH(8);
+#undef GRN_LAUNCH
+    DECO_CHECK_LAUNCH("gate_residual_norm_kernel");
     return DECO_OK;
 }
 

@@ -607,6 +607,21 @@ def gate_residual(s: torch.Tensor, a: torch.Tensor, gate: torch.Tensor, L: int,
     return out
 
 
+def gate_residual_norm(s: torch.Tensor, a: torch.Tensor, gate: torch.Tensor, L: int, weight: torch.Tensor, shift: torch.Tensor,
+                       scale: torch.Tensor, eps: float = 1e-6):
+    """(s_out, h): s_out = s + gate[row // L] * a (fp32) and h = rms(s_out) * weight * (1 + scale) + shift (bf16) in one
+    pass over the row -- gate_residual + rmsnorm_modulate without re-reading the stream."""
+    _cuda(s, a, gate, weight, shift, scale)
+    assert s.dtype == torch.float32 and s.is_contiguous() and a.dtype == bf16 and a.is_contiguous() and a.shape == s.shape
+    assert gate.dtype == bf16 and gate.stride(1) == 1 and gate.shape[1] == s.shape[1] and weight.dtype == torch.float32
+    assert shift.stride(0) == scale.stride(0) and shift.stride(1) == 1 and scale.stride(1) == 1
+    s_out = torch.empty_like(s)
+    h = torch.empty(s.shape, dtype=bf16, device=s.device)
+    call("deco_gate_residual_norm", ptr(s), ptr(a), ptr(gate), gate.stride(0), ptr(s_out), ptr(weight), ptr(shift), ptr(scale),
+         shift.stride(0), L, ptr(h), s.shape[0], s.shape[1], float(eps), _st(s))
+    return s_out, h
+
+
 def gate_bwd(ds: torch.Tensor, a: torch.Tensor, gate: torch.Tensor, dgate: torch.Tensor, L: int,
              dbias: Optional[torch.Tensor] = None) -> torch.Tensor:
     """da = gate * ds (returned, bf16); dgate (fp32 view [B, H], row stride free) += sum_rows ds * a; dbias += sum da."""
@@ -663,6 +678,29 @@ def rmsnorm_modulate_bwd_(ds: torch.Tensor, dh: torch.Tensor, x: torch.Tensor, w
     call("deco_rmsnorm_modulate_bwd", ptr(dh), ptr(x), ptr(weight), ptr(scale), scale.stride(0), ptr(ds), ptr(dweight),
          ptr(dshift), ptr(dscale), dshift.stride(0), ptr(ws), ptr(iws), L, x.shape[0], x.shape[1], float(eps), _st(x))
     return ds
+
+
+def rmsnorm_modulate_bwd_gate_(ds: torch.Tensor, dh: torch.Tensor, x: torch.Tensor, weight: torch.Tensor, scale: torch.Tensor,
+                               dweight: torch.Tensor, dshift: torch.Tensor, dscale: torch.Tensor, L: int,
+                               a: torch.Tensor, gate: torch.Tensor, dgate: torch.Tensor, dbias: Optional[torch.Tensor] = None,
+                               eps: float = 1e-6) -> torch.Tensor:
+    """rmsnorm_modulate_bwd_ followed by gate_bwd on the updated ds, in one pass over it; returns da (bf16)."""
+    _cuda(ds, dh, x, weight, scale, dweight, dshift, dscale, a, gate, dgate, dbias)
+    assert ds.dtype == torch.float32 and ds.is_contiguous() and x.dtype == torch.float32 and x.is_contiguous()
+    assert dh.dtype == bf16 and dh.is_contiguous() and dh.shape == x.shape == ds.shape
+    assert scale.dtype == bf16 and scale.stride(1) == 1
+    assert dshift.dtype == torch.float32 and dshift.stride(1) == 1 and dshift.stride(0) == dscale.stride(0)
+    assert a.dtype == bf16 and a.is_contiguous() and a.shape == ds.shape
+    assert gate.dtype == bf16 and gate.stride(1) == 1 and dgate.dtype == torch.float32 and dgate.stride(1) == 1
+    nimg = x.shape[0] // L
+    ws = torch.empty(2 * x.shape[0], dtype=torch.float32, device=x.device)
+    iws = torch.zeros((2 if dbias is not None else 1, nimg, x.shape[1]), dtype=torch.float32, device=x.device)
+    da = torch.empty_like(a)
+    call("deco_rmsnorm_modulate_bwd_gate", ptr(dh), ptr(x), ptr(weight), ptr(scale), scale.stride(0), ptr(ds), ptr(dweight),
+         ptr(dshift), ptr(dscale), dshift.stride(0), ptr(ws), ptr(iws[0]), L, x.shape[0], x.shape[1], float(eps),
+         ptr(a), ptr(gate), gate.stride(0), ptr(da), ptr(dgate), dgate.stride(0), ptr(dbias),
+         ptr(iws[1]) if dbias is not None else None, _st(x))
+    return da
 
 
 def headnorm_rope_bwd_(g: torch.Tensor, raw: torch.Tensor, col: int, weight: torch.Tensor, rope: Optional[torch.Tensor],

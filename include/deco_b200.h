@@ -298,6 +298,14 @@ int deco_transpose_cast(const void* src, int src_is_f32, long long lds, void* ds
 /* out_accum[c] += sum_r x[r][c]  (bias gradients of nn.Linear) */
 int deco_colsum(const void* x, int x_is_f32, long long ldx, float* out_accum, long long M, int N, void* stream);
 
+/* gate_residual followed by the next block-level RMSNorm + modulation in one pass (training forward,
+ * dit_c2i_DeCo.py:236-244): s_out = s + gate[row / L] * a (fp32) and h_out = rms(s_out) * weight * (1 + scale) + shift (bf16).
+ * Bit-identical to deco_gate_residual + deco_rmsnorm_modulate. */
+int deco_gate_residual_norm(const float* s, const void* a_bf16, const void* gate_bf16, long long gate_stride,
+                            float* s_out, const float* weight, const void* shift_bf16, const void* scale_bf16,
+                            long long mod_row_stride, int rows_per_image, void* h_out_bf16, long long M, int hidden,
+                            float eps, void* stream);
+
 /* out[m,:] = s[m,:] + gate[m / rows_per_image,:] * a[m,:]  (dit_c2i_DeCo.py:208-209 with the branch output a kept for
  * backward); out may alias s */
 int deco_gate_residual(const float* s, const void* a_bf16, const void* gate_bf16, long long gate_stride,
@@ -327,6 +335,17 @@ int deco_rmsnorm_modulate_bwd(const void* dh_bf16, const float* x, const float* 
                               float* dshift_accum, float* dscale_accum, long long dmod_row_stride,
                               float* row_ws, float* img_ws, int rows_per_image, long long M, int hidden, float eps,
                               void* stream);
+
+/* deco_rmsnorm_modulate_bwd followed by deco_gate_bwd on the updated stream gradient in ONE pass over it (the backward of
+ * "s_mid = s + gate * a; h = norm(s_mid)", dit_c2i_DeCo.py:236-244 reversed): da = gate * ds_new, dgate += sum_rows ds_new * a,
+ * dbias += sum_rows da (optional; gate_img_ws = zeroed fp32 [B, hidden]). */
+int deco_rmsnorm_modulate_bwd_gate(const void* dh_bf16, const float* x, const float* weight, const void* scale_bf16,
+                                   long long mod_row_stride, float* ds_accum, float* dweight_accum,
+                                   float* dshift_accum, float* dscale_accum, long long dmod_row_stride,
+                                   float* row_ws, float* img_ws, int rows_per_image, long long M, int hidden, float eps,
+                                   const void* a_bf16, const void* gate_bf16, long long gate_stride, void* da_bf16,
+                                   float* dgate_accum, long long dgate_stride, float* dbias_accum, float* gate_img_ws,
+                                   void* stream);
 
 /* backward of per-head RMSNorm (+ RoPE when rope_cos_sin != NULL) for one segment (dit_c2i_DeCo.py:178-180, :134-145):
  * g [M, g_stride] holds d(out) at columns [col, col + heads*head_dim) on entry and d(raw) on exit; raw = the QKV GEMM

@@ -91,6 +91,59 @@ def test_wgrad_dgrad_through_the_gemm(dev):
     assert rel_l2(_wgrad(dy2, x2), dy2.to(bf16).float().t() @ x2.float()) < 2e-3
 
 
+@pytest.mark.parametrize("B,L,H", [(2, 16, 576), (3, 64, 1152), (2, 5, 1536), (1, 3, 136)])
+def test_gate_residual_norm_equals_the_two_kernels(dev, B, L, H):
+    """The fused residual add + next norm of the training forward is bit-identical to gate_residual + rmsnorm_modulate."""
+    from deco_b200 import ops
+    M = B * L
+    s = torch.randn(M, H, device=dev, generator=_g(1))
+    a = torch.randn(M, H, device=dev, generator=_g(2)).to(bf16)
+    mod = torch.randn(B, 6 * H, device=dev, generator=_g(3)).to(bf16)
+    gate, shift, scale = mod[:, 2 * H:3 * H], mod[:, 3 * H:4 * H], mod[:, 4 * H:5 * H]
+    w = torch.randn(H, device=dev, generator=_g(4))
+    s_ref = ops.gate_residual(s, a, gate, L)
+    h_ref = ops.rmsnorm_modulate(s_ref, w, shift, scale, L)
+    s_out, h = ops.gate_residual_norm(s, a, gate, L, w, shift, scale)
+    assert torch.equal(s_out, s_ref) and torch.equal(h, h_ref)
+    x = s + gate.float().repeat_interleave(L, 0) * a.float()
+    ref = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-6) * w * (1 + scale.float().repeat_interleave(L, 0)) \
+        + shift.float().repeat_interleave(L, 0)
+    assert rel_l2(h.float(), ref) < 5e-3
+
+
+@pytest.mark.parametrize("B,L,H,with_bias", [(2, 16, 576, True), (3, 64, 1152, False), (2, 4, 144, True)])
+def test_rmsnorm_bwd_gate_equals_the_two_kernels(dev, B, L, H, with_bias):
+    """norm backward + the next gate backward fused == rmsnorm_modulate_bwd_ followed by gate_bwd."""
+    from deco_b200 import ops
+    M = B * L
+    g = lambda k: _g(100 + k)   # noqa: E731
+    ds0 = torch.randn(M, H, device=dev, generator=g(1))
+    dh = torch.randn(M, H, device=dev, generator=g(2)).to(bf16)
+    x = torch.randn(M, H, device=dev, generator=g(3))
+    w = torch.randn(H, device=dev, generator=g(4))
+    mod = torch.randn(B, 6 * H, device=dev, generator=g(5)).to(bf16)
+    scale, gate = mod[:, H:2 * H], mod[:, 5 * H:6 * H]
+    a = torch.randn(M, H, device=dev, generator=g(6)).to(bf16)
+
+    def run(fused):
+        ds, dw, dmod = ds0.clone(), torch.zeros(H, device=dev), torch.zeros(B, 6 * H, device=dev)
+        dbias = torch.zeros(H, device=dev) if with_bias else None
+        if fused:
+            da = ops.rmsnorm_modulate_bwd_gate_(ds, dh, x, w, scale, dw, dmod[:, :H], dmod[:, H:2 * H], L, a, gate,
+                                                dmod[:, 5 * H:6 * H], dbias=dbias)
+        else:
+            ops.rmsnorm_modulate_bwd_(ds, dh, x, w, scale, dw, dmod[:, :H], dmod[:, H:2 * H], L)
+            da = ops.gate_bwd(ds, a, gate, dmod[:, 5 * H:6 * H], L, dbias=dbias)
+        return ds, dw, dmod, da, dbias
+
+    r0, r1 = run(False), run(True)
+    assert torch.equal(r0[0], r1[0]) and torch.equal(r0[3], r1[3])         # ds and da: same arithmetic per element
+    for u, v in zip(r0[1:3], r1[1:3]):                                       # atomically reduced sums: order differs
+        assert rel_l2(v, u) < 1e-5
+    if with_bias:
+        assert rel_l2(r1[4], r0[4]) < 1e-5
+
+
 @pytest.mark.parametrize("B,L,H", [(2, 16, 576), (3, 64, 1152), (2, 4, 144)])
 def test_gate_and_silu_rows_backward(dev, B, L, H):
     from deco_b200 import ops
