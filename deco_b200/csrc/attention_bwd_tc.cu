@@ -1,41 +1,30 @@
 // Backward of non-causal softmax attention on the 5th-generation tensor cores (training step; autograd through
 // F.scaled_dot_product_attention at /root/reference/src/models/transformer/dit_c2i_DeCo.py:181-185).
 //
-// Same two deterministic passes as csrc/attention_bwd.cu (no atomics; S and dP are recomputed in each), every product a
-// tcgen05.mma with M = 128 and the accumulators in tensor memory; two threads share a row of the 128 x 128 score block
-// (warps w and w + 4 address the same 32 TMEM lanes; each takes 64 of the block's 128 keys):
-//   pass A  item = (image, head, 128 queries):  for every 128-key block   S = Q K^T, dP = dO V^T          (SS, N = 128)
-//           P = exp2(c S - lse2), dS = P (dP - delta) scale -> bf16 -> tensor memory;  dQ += dS K  (TS, B = K MN-major)
-//           delta = rowsum(dO . O) is formed here (thread-local) and left in the workspace for pass B
-//   pass B  item = (image, head, 128 keys):     for every 128-query tile  S, dP as above (rows = queries)
-//           P and dS -> bf16 -> SHARED memory as [query][key] tiles = the MN-major A operands of
-//           dV += P^T dO and dK += dS^T Q   (M = keys, K = queries; B = the dO / Q tiles read MN-major)
-// Q, K, V, dO tiles come straight from the strided [tokens, 3H] matrices through 4-D TMA maps (16-column boxes, 32-byte
-// swizzle = the operand layout; head dim 72 zero-padded to 80, ragged sequence tails zero-filled) -- one tile in shared
-// memory serves as K-major operand of the score products and as MN-major operand of the gradient products.
-// lse2 comes from the forward (deco_attention_fwd_lse).  The kernels are synchronous inside a CTA (load -> MMA -> row
-// math -> MMA); parallelism comes from one persistent CTA per SM over ~7 items each.  Operand forms not exercised by the
-// forward kernel (A MN-major from shared memory) are checked by tests/test_gpu_backward.py against autograd.
+// Two deterministic passes as in csrc/attention_bwd.cu (no atomics; S and dP are recomputed in each), every product a
+// tcgen05.mma with M = 128 and the accumulators in tensor memory; two threads share a score row (warps w and w + 4
+// address the same 32 TMEM lanes and take 32 of a block's 64 columns each):
+//   pass 0  item = (image, head, 128 queries), one step per 64-key block:  S = Q K^T, dP = dO V^T  (SS, N = 64)
+//           dS / scale = exp2(c S - lse2) (dP - delta) -> bf16 -> tensor memory;  dQ += dS K  (TS, B = K block MN-major)
+//   pass 1  item = (image, head, 128 keys), one step per 64-query block, on the TRANSPOSED scores (rows = keys):
+//           S^T = K Q^T, dP^T = V dO^T;  P^T -> bf16 -> tensor memory, dV += P^T dO (TS);
+//           dS^T / scale -> bf16 -> shared memory (K-major SW32 tile), dK += dS^T Q (SS)
+//   the softmax scale is applied once per output element when dQ / dK leave tensor memory.
+// delta = rowsum(dO . O) comes from attn_bwd_delta_kernel; lse2 from the forward (deco_attention_fwd_lse).
+// Q, K, V, dO tiles come straight from the strided [tokens, 3H] matrices through 4-D TMA maps (16-column x 64-row boxes,
+// 32-byte swizzle = the operand layout; head dim 72 zero-padded to 80, ragged sequence tails zero-filled) -- one tile in
+// shared memory serves as K-major operand of the score products and as MN-major operand of the gradient products.
+// How the steps are pipelined is described above attn_bwd_pipe_kernel.  History of this file (profiles/attn_bwd_bench_r2.txt):
+// mma.sync pair 219 us -> unpipelined tcgen05 pair (load -> MMA -> row math -> MMA in sequence) 143 us -> this kernel 95 us
+// per XL/16 layer of 32 images.  A cp.async gather in place of the TMA boxes measured slower (109 us): once the loads have
+// four issuing warps the row-math warps are the critical path (scripts/abt_trace.py), not the TMA unit.
 #include "tcgen05.cuh"
 #include "tma_host.cuh"
 
 namespace deco {
 namespace abt {
 
-template <int D> struct Cfg {
-    static constexpr int DP = (D + 15) / 16 * 16;
-    static constexpr int NCH = DP / 16;
-    static constexpr uint32_t CHUNK = 128 * 32;
-    static constexpr uint32_t TILE = NCH * CHUNK;             // [128 rows x DP] bf16, chunk-major SW32
-    static constexpr uint32_t PT = 8 * CHUNK;                 // [128 x 128] bf16 (P or dS as an MN-major A operand)
-    static constexpr uint32_t SMEM_A = 8 * TILE + 256 + 1024;             // 2 x (Q, dO), 2 x (K, V): loads run one step ahead
-    static constexpr uint32_t SMEM_B = 6 * TILE + 2 * PT + 256 + 1024;    // K, V, 2 x (Q, dO), P, dS
-};
-constexpr int kRows = 128, kThreads = 256;      // two threads per score row: each takes 64 of the 128 keys of a block
-constexpr uint32_t kColS = 0, kColDP = 128, kColA = 256, kColDQ = 320;      // pass A
-constexpr uint32_t kColDV = 256, kColDK = 336;                              // pass B
-
-struct Maps { CUtensorMap q, k, v, dout; };
+constexpr int kRows = 128;                      // rows of an item: one TMEM lane each
 
 struct Params {
     const __nv_bfloat16 *o, *dout;
@@ -58,332 +47,8 @@ __device__ __forceinline__ float ex2f(float x) {
     return y;
 }
 
-template <int D>
-__device__ __forceinline__ void load_tile(uint32_t dst, const CUtensorMap* map, uint32_t bar, int row, int h, int b) {
-#pragma unroll
-    for (int c = 0; c < Cfg<D>::NCH; ++c) tma_load_4d(dst + c * Cfg<D>::CHUNK, map, bar, 16 * c, row, h, b);
-}
-
-// D[128 x N] = A[128 x DP] . B[N x DP]^T, both K-major SW32 tiles (score products)
-template <int D>
-__device__ __forceinline__ void mma_scores(uint32_t dcol, uint32_t sa, uint32_t sb) {
-    constexpr uint32_t idesc = make_idesc_major(128, 128, 0, 0);
-    const uint64_t da = make_umma_desc(sa, 16, 256, 6), db = make_umma_desc(sb, 16, 256, 6);
-#pragma unroll
-    for (int kc = 0; kc < Cfg<D>::NCH; ++kc)
-        umma_bf16(dcol, da + (uint64_t)kc * (Cfg<D>::CHUNK >> 4), db + (uint64_t)kc * (Cfg<D>::CHUNK >> 4), idesc, kc ? 1u : 0u);
-}
-
-// ------------------------------------------------------------------------------------------------ pass A: dQ (+ delta)
-template <int D>
-__global__ void __launch_bounds__(kThreads, 1) attn_bwd_dq_tc_kernel(const __grid_constant__ Maps M, const Params P)
-{
-    using C = Cfg<D>;
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-    // [2 x (Q, dO)] per item parity, [2 x (K, V)] per step parity: the loads of step s + 1 are issued before step s computes
-    auto sQ = [&](int n) { return base + (uint32_t)(n & 1) * 2 * C::TILE; };
-    auto sdO = [&](int n) { return sQ(n) + C::TILE; };
-    auto sK = [&](int st) { return base + 4 * C::TILE + (uint32_t)(st & 1) * 2 * C::TILE; };
-    auto sV = [&](int st) { return sK(st) + C::TILE; };
-    const uint32_t bars = base + 8 * C::TILE;
-    auto bar_ld = [&](int st) { return bars + 8u * (st & 1); };
-    const uint32_t bar_mma = bars + 16, slot = bars + 24;
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const int r = tid & 127, half = tid >> 7;                      // score row of this thread, and which 64 keys of a block it takes
-    if (tid == 0) { mbar_init(bar_ld(0), 1); mbar_init(bar_ld(1), 1); mbar_init(bar_mma, 1); fence_barrier_init(); }
-    if (warp == 0) tmem_alloc(slot, 512);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen + (slot - base));
-    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    const int nq = (P.Lq + kRows - 1) / kRows, nk = (P.Lk + kRows - 1) / kRows;
-    const int nitems = P.B * P.heads * nq;
-    const int nlocal = (int)blockIdx.x < nitems ? (nitems - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-    const int nsteps = nlocal * nk;                                // flat (item, key block) sequence of this CTA
-    uint32_t ph_mma = 0;
-    constexpr uint32_t idesc_dq = make_idesc_major(128, C::DP, 0, 1);
-    auto decode = [&](int n, int& qi, int& h, int& b) {
-        const int item = blockIdx.x + n * gridDim.x;
-        qi = item % nq; h = (item / nq) % P.heads; b = item / (nq * P.heads);
-    };
-    auto issue_loads = [&](int st) {                               // thread 0 only
-        if (st >= nsteps) return;
-        const int n = st / nk, j = st - n * nk;
-        int qi, h, b;
-        decode(n, qi, h, b);
-        mbar_expect_tx(bar_ld(st), (j == 0 ? 4 : 2) * C::TILE);
-        if (j == 0) {
-            load_tile<D>(sQ(n), &M.q, bar_ld(st), qi * kRows, h, b);
-            load_tile<D>(sdO(n), &M.dout, bar_ld(st), qi * kRows, h, b);
-        }
-        load_tile<D>(sK(st), &M.k, bar_ld(st), j * kRows, h, b);
-        load_tile<D>(sV(st), &M.v, bar_ld(st), j * kRows, h, b);
-    };
-    if (tid == 0) issue_loads(0);
-
-    for (int n = 0; n < nlocal; ++n) {
-        int qi, h, b;
-        decode(n, qi, h, b);
-        const int row = qi * kRows + r;                            // query of this thread
-        const bool live = row < P.Lq;
-        // delta = rowsum(dO . O), thread-local from the two global rows (the tiles in shared memory are swizzled operands)
-        float delta = 0.f, lse = 0.f;
-        if (live) {
-            const uint4* orow = reinterpret_cast<const uint4*>(P.o + ((long long)b * P.Lq + row) * P.o_stride + (long long)h * D);
-            const uint4* drow = reinterpret_cast<const uint4*>(P.dout + ((long long)b * P.Lq + row) * P.do_stride + (long long)h * D);
-#pragma unroll
-            for (int c = 0; c < D / 8; ++c) {
-                const uint4 a = __ldg(orow + c), g = __ldg(drow + c);
-                const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, gw[4] = {g.x, g.y, g.z, g.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float2 x = unpack_bf2(aw[e]), y = unpack_bf2(gw[e]);
-                    delta = fmaf(x.x, y.x, fmaf(x.y, y.y, delta));
-                }
-            }
-            const long long si = ((long long)b * P.heads + h) * P.Lq + row;
-            lse = __ldg(P.lse2 + si);
-            if (half == 0) P.delta[si] = delta;
-        }
-        for (int j = 0; j < nk; ++j) {
-            const int st = n * nk + j;
-            if (tid == 0) issue_loads(st + 1);                     // its buffers were released by step st - 1's last MMA wait
-            mbar_wait(bar_ld(st), (uint32_t)((st >> 1) & 1));
-            if (tid == 0) {
-                tc_fence_after();
-                mma_scores<D>(tmem + kColS, sQ(n), sK(st));
-                mma_scores<D>(tmem + kColDP, sdO(n), sV(st));
-                umma_commit(bar_mma);
-            }
-            mbar_wait(bar_mma, ph_mma); ph_mma ^= 1;
-            tc_fence_after();
-            const int kvalid = P.Lk - j * kRows;                   // keys of this block that exist
-#pragma unroll 1
-            for (int ch = 2 * half; ch < 2 * half + 2; ++ch) {
-                uint32_t s[32], dp[32];
-                tmem_ld32(trow + kColS + (uint32_t)(ch * 32), s);
-                tmem_ld32(trow + kColDP + (uint32_t)(ch * 32), dp);
-                tmem_ld_wait();
-                uint32_t pk[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    float v[2];
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int key = ch * 32 + 2 * i + e;
-                        const float p = (live && key < kvalid) ? ex2f(fmaf(__uint_as_float(s[2 * i + e]), P.scale_log2, -lse)) : 0.f;
-                        v[e] = p * (__uint_as_float(dp[2 * i + e]) - delta) * P.scale;
-                    }
-                    pk[i] = pack_bf2(v[0], v[1]);
-                }
-                tmem_st16(trow + kColA + (uint32_t)(ch * 16), pk);
-            }
-            tmem_st_wait();
-            tc_fence_before();
-            __syncthreads();
-            if (tid == 0) {
-                tc_fence_after();
-                const uint64_t dk = make_umma_desc(sK(st), kRows * 32, 256, 6);   // K block read MN-major: [keys (K) x d (N)]
-#pragma unroll
-                for (int ks = 0; ks < kRows / 16; ++ks)
-                    umma_bf16_ts(tmem + kColDQ, tmem + kColA + (uint32_t)(ks * 8), dk + (uint64_t)ks * (512 >> 4), idesc_dq,
-                                 (j > 0 || ks > 0) ? 1u : 0u);
-                umma_commit(bar_mma);
-            }
-            mbar_wait(bar_mma, ph_mma); ph_mma ^= 1;               // this step's K / V tiles and the A columns are free again
-        }
-        tc_fence_after();
-        {
-            // (the loads are warp-wide .sync.aligned instructions: every lane executes them, only live rows store)
-            __nv_bfloat16* out = P.dq + ((long long)b * P.Lq + (live ? row : 0)) * P.dq_stride + (long long)h * D;
-            constexpr int kSplit = (D / 8 + 1) / 2 * 8;           // the two threads of a row split its D columns
-#pragma unroll
-            for (int cc = 0; cc < kSplit; cc += 8) {
-                const int c0 = half * kSplit + cc;
-                if (c0 >= D) continue;                             // (warp-uniform: half is per warp)
-                uint32_t r8[8];
-                tmem_ld8(trow + kColDQ + (uint32_t)c0, r8);
-                tmem_ld_wait();
-                if (live)
-                    *reinterpret_cast<uint4*>(out + c0) = make_uint4(pack_bf2(__uint_as_float(r8[0]), __uint_as_float(r8[1])),
-                                                                     pack_bf2(__uint_as_float(r8[2]), __uint_as_float(r8[3])),
-                                                                     pack_bf2(__uint_as_float(r8[4]), __uint_as_float(r8[5])),
-                                                                     pack_bf2(__uint_as_float(r8[6]), __uint_as_float(r8[7])));
-            }
-        }
-        tc_fence_before();
-        __syncthreads();                                           // the accumulators are read out before the next item's MMAs
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 512);
-}
-
-// ------------------------------------------------------------------------------------------------ pass B: dK, dV
-template <int D>
-__global__ void __launch_bounds__(kThreads, 1) attn_bwd_dkv_tc_kernel(const __grid_constant__ Maps M, const Params P)
-{
-    using C = Cfg<D>;
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-    // K, V of the item (single buffer: reloaded at the item boundary), [2 x (Q, dO)] per step parity (loaded one step ahead)
-    const uint32_t sK = base, sV = base + C::TILE;
-    auto sQ = [&](int st) { return base + 2 * C::TILE + (uint32_t)(st & 1) * 2 * C::TILE; };
-    auto sdO = [&](int st) { return sQ(st) + C::TILE; };
-    const uint32_t sP = base + 6 * C::TILE, sdS = sP + C::PT;
-    const uint32_t bars = sdS + C::PT;
-    auto bar_ld = [&](int st) { return bars + 8u * (st & 1); };
-    const uint32_t bar_kv = bars + 16, bar_mma = bars + 24, slot = bars + 32;
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const int r = tid & 127, half = tid >> 7;                      // score row of this thread, and which 64 keys of a block it takes
-    if (tid == 0) { mbar_init(bar_ld(0), 1); mbar_init(bar_ld(1), 1); mbar_init(bar_kv, 1); mbar_init(bar_mma, 1); fence_barrier_init(); }
-    if (warp == 0) tmem_alloc(slot, 512);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen + (slot - base));
-    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    const int nq = (P.Lq + kRows - 1) / kRows, nk = (P.Lk + kRows - 1) / kRows;
-    const int nitems = P.B * P.heads * nk;
-    const int nlocal = (int)blockIdx.x < nitems ? (nitems - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-    const int nsteps = nlocal * nq;                                // flat (item, query tile) sequence of this CTA
-    uint32_t ph_mma = 0, ph_kv = 0;
-    constexpr uint32_t idesc_g = make_idesc_major(128, C::DP, 1, 1);    // A = P / dS tile MN-major, B = dO / Q tile MN-major
-    auto decode = [&](int n, int& kj, int& h, int& b) {
-        const int item = blockIdx.x + n * gridDim.x;
-        kj = item % nk; h = (item / nk) % P.heads; b = item / (nk * P.heads);
-    };
-    auto issue_qo = [&](int st) {                                  // thread 0 only: query tile of step st
-        if (st >= nsteps) return;
-        const int n = st / nq, i = st - n * nq;
-        int kj, h, b;
-        decode(n, kj, h, b);
-        mbar_expect_tx(bar_ld(st), 2 * C::TILE);
-        load_tile<D>(sQ(st), &M.q, bar_ld(st), i * kRows, h, b);
-        load_tile<D>(sdO(st), &M.dout, bar_ld(st), i * kRows, h, b);
-    };
-    if (tid == 0) issue_qo(0);
-
-    for (int n = 0; n < nlocal; ++n) {
-        int kj, h, b;
-        decode(n, kj, h, b);
-        const int kvalid = P.Lk - kj * kRows;
-        if (tid == 0) {             // the previous item's last MMAs (the readers of K / V) were waited for
-            mbar_expect_tx(bar_kv, 2 * C::TILE);
-            load_tile<D>(sK, &M.k, bar_kv, kj * kRows, h, b);
-            load_tile<D>(sV, &M.v, bar_kv, kj * kRows, h, b);
-        }
-        for (int i = 0; i < nq; ++i) {
-            const int st = n * nq + i;
-            const int row = i * kRows + r;                         // query of this thread in tile i
-            const bool live = row < P.Lq;
-            float lse = 0.f, delta = 0.f;
-            if (live) {
-                const long long si = ((long long)b * P.heads + h) * P.Lq + row;
-                lse = __ldg(P.lse2 + si);
-                delta = P.delta[si];                               // written by pass A (an earlier kernel in the stream)
-            }
-            if (tid == 0) issue_qo(st + 1);                        // its buffers were released by step st - 1's MMA wait
-            if (i == 0) { mbar_wait(bar_kv, ph_kv); ph_kv ^= 1; }
-            mbar_wait(bar_ld(st), (uint32_t)((st >> 1) & 1));
-            if (tid == 0) {
-                tc_fence_after();
-                mma_scores<D>(tmem + kColS, sQ(st), sK);           // rows = queries, columns = keys
-                mma_scores<D>(tmem + kColDP, sdO(st), sV);
-                umma_commit(bar_mma);
-            }
-            mbar_wait(bar_mma, ph_mma); ph_mma ^= 1;
-            tc_fence_after();
-#pragma unroll 1
-            for (int ch = 2 * half; ch < 2 * half + 2; ++ch) {
-                uint32_t s[32], dp[32];
-                tmem_ld32(trow + kColS + (uint32_t)(ch * 32), s);
-                tmem_ld32(trow + kColDP + (uint32_t)(ch * 32), dp);
-                tmem_ld_wait();
-                uint32_t pp[16], pd[16];
-#pragma unroll
-                for (int k2 = 0; k2 < 16; ++k2) {
-                    float p[2], g[2];
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int key = ch * 32 + 2 * k2 + e;
-                        p[e] = (live && key < kvalid) ? ex2f(fmaf(__uint_as_float(s[2 * k2 + e]), P.scale_log2, -lse)) : 0.f;
-                        g[e] = p[e] * (__uint_as_float(dp[2 * k2 + e]) - delta) * P.scale;
-                    }
-                    pp[k2] = pack_bf2(p[0], p[1]);
-                    pd[k2] = pack_bf2(g[0], g[1]);
-                }
-                // element (row = query tid, col = key) of the [query][key] tile: 16-key chunks of 32 bytes per row
-#pragma unroll
-                for (int c16 = 0; c16 < 2; ++c16) {
-                    const int col = ch * 32 + c16 * 16;
-                    const uint32_t o0 = sw32_offset(r, col, kRows), o1 = sw32_offset(r, col + 8, kRows);
-                    *reinterpret_cast<uint4*>(gen + (sP - base) + o0) = make_uint4(pp[c16 * 8], pp[c16 * 8 + 1], pp[c16 * 8 + 2], pp[c16 * 8 + 3]);
-                    *reinterpret_cast<uint4*>(gen + (sP - base) + o1) = make_uint4(pp[c16 * 8 + 4], pp[c16 * 8 + 5], pp[c16 * 8 + 6], pp[c16 * 8 + 7]);
-                    *reinterpret_cast<uint4*>(gen + (sdS - base) + o0) = make_uint4(pd[c16 * 8], pd[c16 * 8 + 1], pd[c16 * 8 + 2], pd[c16 * 8 + 3]);
-                    *reinterpret_cast<uint4*>(gen + (sdS - base) + o1) = make_uint4(pd[c16 * 8 + 4], pd[c16 * 8 + 5], pd[c16 * 8 + 6], pd[c16 * 8 + 7]);
-                }
-            }
-            fence_proxy_async();                                   // generic-proxy stores -> tensor-core (async proxy) reads
-            tc_fence_before();
-            __syncthreads();
-            if (tid == 0) {
-                tc_fence_after();
-                const uint64_t dP_ = make_umma_desc(sP, kRows * 32, 256, 6), dS_ = make_umma_desc(sdS, kRows * 32, 256, 6);
-                const uint64_t ddo = make_umma_desc(sdO(st), kRows * 32, 256, 6), dq_ = make_umma_desc(sQ(st), kRows * 32, 256, 6);
-#pragma unroll
-                for (int ks = 0; ks < kRows / 16; ++ks) {          // K = 16 queries per instruction
-                    const uint64_t stp = (uint64_t)ks * (512 >> 4);
-                    umma_bf16(tmem + kColDV, dP_ + stp, ddo + stp, idesc_g, (i > 0 || ks > 0) ? 1u : 0u);
-                    umma_bf16(tmem + kColDK, dS_ + stp, dq_ + stp, idesc_g, (i > 0 || ks > 0) ? 1u : 0u);
-                }
-                umma_commit(bar_mma);
-            }
-            mbar_wait(bar_mma, ph_mma); ph_mma ^= 1;               // this step's Q / dO tiles and P / dS are free again
-        }
-        tc_fence_after();
-        {
-            const int key = kj * kRows + r;                        // key of this thread (accumulator row)
-            constexpr int kSplit = (D / 8 + 1) / 2 * 8;           // the two threads of a row split its D columns
-            const bool live = key < P.Lk;
-            __nv_bfloat16* okp = P.dk + ((long long)b * P.Lk + (live ? key : 0)) * P.dkv_stride + (long long)h * D;
-            __nv_bfloat16* ovp = P.dv + ((long long)b * P.Lk + (live ? key : 0)) * P.dkv_stride + (long long)h * D;
-#pragma unroll
-            for (int cc = 0; cc < kSplit; cc += 8) {
-                const int c0 = half * kSplit + cc;
-                if (c0 >= D) continue;
-                uint32_t a8[8], b8[8];
-                tmem_ld8(trow + kColDK + (uint32_t)c0, a8);
-                tmem_ld8(trow + kColDV + (uint32_t)c0, b8);
-                tmem_ld_wait();
-                if (live) {
-                    *reinterpret_cast<uint4*>(okp + c0) = make_uint4(pack_bf2(__uint_as_float(a8[0]), __uint_as_float(a8[1])),
-                                                                     pack_bf2(__uint_as_float(a8[2]), __uint_as_float(a8[3])),
-                                                                     pack_bf2(__uint_as_float(a8[4]), __uint_as_float(a8[5])),
-                                                                     pack_bf2(__uint_as_float(a8[6]), __uint_as_float(a8[7])));
-                    *reinterpret_cast<uint4*>(ovp + c0) = make_uint4(pack_bf2(__uint_as_float(b8[0]), __uint_as_float(b8[1])),
-                                                                     pack_bf2(__uint_as_float(b8[2]), __uint_as_float(b8[3])),
-                                                                     pack_bf2(__uint_as_float(b8[4]), __uint_as_float(b8[5])),
-                                                                     pack_bf2(__uint_as_float(b8[6]), __uint_as_float(b8[7])));
-                }
-            }
-        }
-        tc_fence_before();
-        __syncthreads();
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 512);
-}
-
-
 // ------------------------------------------------------------------------------------------------ pipelined kernels
-// The two kernels above run load -> MMA -> row math -> MMA in sequence inside a CTA.  The pipelined form below overlaps
-// the row math of step s with the gradient products of step s - 1 and the score products of step s + 1 / s + 2:
+// The row math of step s overlaps the gradient products of step s - 1 and the score products of step s + 1 / s + 2:
 //   * 64-column score blocks, two S / dP accumulator pairs in tensor memory (2 x 128 columns);
 //   * both passes keep the long dimension of the gradient products on the TMEM lanes: the dK / dV pass works on the
 //     TRANSPOSED block S^T = K Q^T (rows = keys), so P^T and dS^T are [keys x queries]; its per-query constants
@@ -406,11 +71,14 @@ namespace pipe {
 
 #ifdef ABT_TRACE
 __device__ unsigned long long g_trace[2][16];
+__device__ long long g_tl[2][6][64][4];      // [pass][role][step][event]: CTA 0's clock at the pipeline events
+#define TL(role, step, ev) do { if (blockIdx.x == 0 && (step) < 64) g_tl[PASS][role][step][ev] = clock64(); } while (0)
 #define TR_T(var) const long long var = clock64()
 #define TR_ADD(slot, t0) atomicAdd(&g_trace[PASS][slot], (unsigned long long)(clock64() - (t0)))
 #else
 #define TR_T(var)
 #define TR_ADD(slot, t0)
+#define TL(role, step, ev)
 #endif
 
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
@@ -555,7 +223,9 @@ __global__ void __launch_bounds__(kThreadsP, 1) attn_bwd_pipe_kernel(const __gri
             if (n + 1 < nlocal) decode(n + 1, ri1, h1, b1);
             for (int j = 0; j < spi; ++j) {
                 TR_T(p1);
+                if (lane == 0 && pw == 0) TL(4, n * spi + j, 0);
                 mbar_wait(ld_empty(s), eph);
+                if (lane == 0 && pw == 0) TL(4, n * spi + j, 1);
                 if (lane == 0 && pw == 0) { TR_ADD(12, p1); }
                 if (lane == 0) {
                     if (PASS == 1 && pw == 0) mbar_expect_tx_only(ld_full(s), C::CTILE);     // the arrival follows the vector stores
@@ -566,6 +236,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) attn_bwd_pipe_kernel(const __gri
                 if (lane < C::NCH)                // lane = chunk
                     tma_load_4d((pw ? sC2(s) : sC1(s)) + lane * C::CCHUNK, pw ? &M.c2 : &M.c1, ld_full(s), 16 * lane, j * kCols, h, b);
                 __syncwarp();
+                if (lane == 0 && pw == 0) TL(4, n * spi + j, 2);
                 if (lane == 0 && pw == 0) { TR_ADD(13, p2); }
                 if (PASS == 1 && pw == 0) {
 #pragma unroll
@@ -606,11 +277,14 @@ __global__ void __launch_bounds__(kThreadsP, 1) attn_bwd_pipe_kernel(const __gri
                 TR_T(t0);
                 if (j == 0) mbar_wait(row_full(n & 1), (uint32_t)((n >> 1) & 1));
                 if (which == 0) { TR_ADD(10, t0); }
+                TL(which, st, 0);
                 mbar_wait(ld_full(s), (uint32_t)((st / NS) & 1));
+                TL(which, st, 1);
                 if (which == 0) { TR_ADD(3, t0); }
                 TR_T(t1);
                 mbar_wait(math_done(b), (uint32_t)(((st >> 1) & 1) ^ 1));      // step st - 2 has read this buffer (free at first)
                 if (which == 0) { TR_ADD(0, t1); }
+                TL(which, st, 2);
                 TR_T(t2);
                 tc_fence_after();
                 const uint64_t da = make_umma_desc(which ? sR2(n) : sR1(n), 16, 256, 6);
@@ -622,6 +296,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) attn_bwd_pipe_kernel(const __gri
                 umma_commit(s_full(b));
                 umma_commit(ld_empty(s));
                 if (j == spi - 1) umma_commit(row_empty(n & 1));
+                TL(which, st, 3);
                 if (which == 0) { TR_ADD(4, t2); }
             }
         }
@@ -632,7 +307,9 @@ __global__ void __launch_bounds__(kThreadsP, 1) attn_bwd_pipe_kernel(const __gri
             for (int st = 0; st < nsteps; ++st) {
                 const int n = st / spi, j = st - n * spi, s = st % NS, b = st & 1;
                 TR_T(t0);
+                TL(2, st, 0);
                 mbar_wait(math_done(b), (uint32_t)((st >> 1) & 1));
+                TL(2, st, 1);
                 TR_ADD(1, t0);
                 if (j == 0 && n > 0) mbar_wait(acc_empty, (uint32_t)((n - 1) & 1));   // the previous item's accumulators were read out
                 TR_T(t2);
@@ -654,6 +331,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) attn_bwd_pipe_kernel(const __gri
                 umma_commit(g_done(b));
                 umma_commit(ld_empty(s));
                 if (j == spi - 1) umma_commit(acc_full);
+                TL(2, st, 3);
                 TR_ADD(2, t2);
             }
         }
@@ -683,6 +361,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) attn_bwd_pipe_kernel(const __gri
             mbar_wait(acc_full, (uint32_t)(n & 1));
             if (tid == 0) { TR_ADD(7, e0); }
             TR_T(e1);
+            if (tid == 0) TL(5, n, 0);
             tc_fence_after();
             constexpr int kSplit = (D / 8 + 1) / 2 * 8;               // 40 | 32 columns of 72 for the halves, 32 | 32 of 64
             constexpr int kPieces = 32 * (D / 8);                     // 16-byte pieces of the group's 32 rows
@@ -696,17 +375,22 @@ __global__ void __launch_bounds__(kThreadsP, 1) attn_bwd_pipe_kernel(const __gri
                 tmem_ld32(tacc, v);
                 if (kSplit > 32) tmem_ld8(tacc + 32, w);              // (half 1 reads the zero padding of columns 72..79 and drops it)
                 tmem_ld_wait();
+                if (tid == 0 && acc == 0) TL(5, n, 1);
+                const float sc = (PASS == 0 || acc == 1) ? P.scale : 1.0f;      // dQ and dK carry the softmax scale (dV does not)
                 const uint32_t srow = scr + (uint32_t)lane * D * 2 + (uint32_t)(half * kSplit) * 2;
 #pragma unroll
                 for (int c = 0; c < 32; c += 8)
-                    sts128u(srow + c * 2, pack_bf2(__uint_as_float(v[c]), __uint_as_float(v[c + 1])),
-                            pack_bf2(__uint_as_float(v[c + 2]), __uint_as_float(v[c + 3])),
-                            pack_bf2(__uint_as_float(v[c + 4]), __uint_as_float(v[c + 5])),
-                            pack_bf2(__uint_as_float(v[c + 6]), __uint_as_float(v[c + 7])));
+                    sts128u(srow + c * 2, pack_bf2(sc * __uint_as_float(v[c]), sc * __uint_as_float(v[c + 1])),
+                            pack_bf2(sc * __uint_as_float(v[c + 2]), sc * __uint_as_float(v[c + 3])),
+                            pack_bf2(sc * __uint_as_float(v[c + 4]), sc * __uint_as_float(v[c + 5])),
+                            pack_bf2(sc * __uint_as_float(v[c + 6]), sc * __uint_as_float(v[c + 7])));
                 if (kSplit > 32 && half == 0)
-                    sts128u(srow + 64, pack_bf2(__uint_as_float(w[0]), __uint_as_float(w[1])), pack_bf2(__uint_as_float(w[2]), __uint_as_float(w[3])),
-                            pack_bf2(__uint_as_float(w[4]), __uint_as_float(w[5])), pack_bf2(__uint_as_float(w[6]), __uint_as_float(w[7])));
+                    sts128u(srow + 64, pack_bf2(sc * __uint_as_float(w[0]), sc * __uint_as_float(w[1])),
+                            pack_bf2(sc * __uint_as_float(w[2]), sc * __uint_as_float(w[3])),
+                            pack_bf2(sc * __uint_as_float(w[4]), sc * __uint_as_float(w[5])),
+                            pack_bf2(sc * __uint_as_float(w[6]), sc * __uint_as_float(w[7])));
                 asm volatile("bar.sync %0, 64;" :: "r"(grp + 1) : "memory");
+                if (tid == 0 && acc == 0) TL(5, n, 2);
                 __nv_bfloat16* ob = (PASS == 0 ? P.dq : (acc == 0 ? P.dv : P.dk));
                 const long long ostr = PASS == 0 ? P.dq_stride : P.dkv_stride;
 #pragma unroll
@@ -722,6 +406,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) attn_bwd_pipe_kernel(const __gri
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty);
+            if (tid == 0) TL(5, n, 3);
             if (tid == 0) { TR_ADD(9, e1); }
         };
         fetch_row_consts(0);
@@ -731,6 +416,8 @@ __global__ void __launch_bounds__(kThreadsP, 1) attn_bwd_pipe_kernel(const __gri
             decode(n, ri, h, b);
             const int row = ri * kRows + r;
             const bool live = row < Lr;
+            const bool tile_full = (ri + 1) * kRows <= Lr;
+            const float lse_off = live ? 0.f : -__int_as_float(0x7f800000);
             const float lse = lse_n, delta = delta_n;
             fetch_row_consts(n + 1);               // one item ahead: the latency hides behind this item's steps
             for (int j = 0; j < spi; ++j) {
@@ -738,7 +425,9 @@ __global__ void __launch_bounds__(kThreadsP, 1) attn_bwd_pipe_kernel(const __gri
                 const uint32_t tS = trow + (uint32_t)bb * kBufCols + (uint32_t)(32 * half);
                 const uint32_t tA = trow + kColA + (uint32_t)bb * 32 + (uint32_t)(16 * half);
                 TR_T(m0);
+                if (tid == 0) TL(3, st, 0);
                 mbar_wait(s_full(bb), (uint32_t)((st >> 1) & 1));
+                if (tid == 0) TL(3, st, 1);
                 if (tid == 0) { TR_ADD(5, m0); }
                 TR_T(m1);
                 tc_fence_after();
@@ -747,17 +436,27 @@ __global__ void __launch_bounds__(kThreadsP, 1) attn_bwd_pipe_kernel(const __gri
                 tmem_ld32(tS + kCols, dp);
                 tmem_ld_wait();
                 if (PASS == 0) {
+                    // dS / scale = P (dP - delta): the softmax scale is applied once per output element at the read-out
                     const int cvalid = Lc - j * kCols - 32 * half;        // columns of this thread that exist
                     uint32_t pk[16];
+                    if (tile_full && cvalid >= 32) {                       // (uniform: no per-element masks)
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        float v[2];
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const float p = (live && 2 * i + e < cvalid) ? ex2f(fmaf(__uint_as_float(s[2 * i + e]), P.scale_log2, -lse)) : 0.f;
-                            v[e] = p * (__uint_as_float(dp[2 * i + e]) - delta) * P.scale;
+                        for (int i = 0; i < 16; ++i) {
+                            const float p0 = ex2f(fmaf(__uint_as_float(s[2 * i]), P.scale_log2, -lse));
+                            const float p1 = ex2f(fmaf(__uint_as_float(s[2 * i + 1]), P.scale_log2, -lse));
+                            pk[i] = pack_bf2(p0 * (__uint_as_float(dp[2 * i]) - delta), p1 * (__uint_as_float(dp[2 * i + 1]) - delta));
                         }
-                        pk[i] = pack_bf2(v[0], v[1]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            float v[2];
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const float p = (live && 2 * i + e < cvalid) ? ex2f(fmaf(__uint_as_float(s[2 * i + e]), P.scale_log2, -lse)) : 0.f;
+                                v[e] = p * (__uint_as_float(dp[2 * i + e]) - delta);
+                            }
+                            pk[i] = pack_bf2(v[0], v[1]);
+                        }
                     }
                     mbar_wait(g_done(bb), (uint32_t)(((st >> 1) & 1) ^ 1));   // the products of step st - 2 have read these columns
                     tc_fence_after();
@@ -768,10 +467,11 @@ __global__ void __launch_bounds__(kThreadsP, 1) attn_bwd_pipe_kernel(const __gri
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         const float4 c2 = lds128(vp + (uint32_t)i * 16);          // (lse2, delta) of columns 2i and 2i + 1
-                        const float p0 = live ? ex2f(fmaf(__uint_as_float(s[2 * i]), P.scale_log2, -c2.x)) : 0.f;
-                        const float p1 = live ? ex2f(fmaf(__uint_as_float(s[2 * i + 1]), P.scale_log2, -c2.z)) : 0.f;
+                        // (a key row past the end: lse_off = -inf sends its P to 0; dS^T / scale here, scale at the read-out)
+                        const float p0 = ex2f(fmaf(__uint_as_float(s[2 * i]), P.scale_log2, lse_off - c2.x));
+                        const float p1 = ex2f(fmaf(__uint_as_float(s[2 * i + 1]), P.scale_log2, lse_off - c2.z));
                         pp[i] = pack_bf2(p0, p1);
-                        pd[i] = pack_bf2(p0 * (__uint_as_float(dp[2 * i]) - c2.y) * P.scale, p1 * (__uint_as_float(dp[2 * i + 1]) - c2.w) * P.scale);
+                        pd[i] = pack_bf2(p0 * (__uint_as_float(dp[2 * i]) - c2.y), p1 * (__uint_as_float(dp[2 * i + 1]) - c2.w));
                     }
                     mbar_wait(g_done(bb), (uint32_t)(((st >> 1) & 1) ^ 1));
                     tc_fence_after();
@@ -790,6 +490,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) attn_bwd_pipe_kernel(const __gri
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(math_done(bb));
+                if (tid == 0) TL(3, st, 2);
                 if (tid == 0) { TR_ADD(6, m1); }
                 if (j == 0 && n > 0) read_out(n - 1);      // deferred: the issuers already have this item's first steps
             }
@@ -805,7 +506,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) attn_bwd_pipe_kernel(const __gri
 }  // namespace pipe
 
 // 4-D view (d, token, head, batch) of a strided [B*L, row_stride] bf16 matrix whose columns are [head][d]
-static int make_tmap(CUtensorMap* map, const void* ptr, int D, long long L, int heads, int B, long long row_stride, int box_rows = kRows) {
+static int make_tmap(CUtensorMap* map, const void* ptr, int D, long long L, int heads, int B, long long row_stride, int box_rows) {
     PFN_encodeTiled enc = get_tensormap_encoder();
     if (!enc) { deco_set_error("cuTensorMapEncodeTiled entry point not available"); return DECO_ERR_DRIVER; }
     cuuint64_t dims[4] = {(cuuint64_t)D, (cuuint64_t)L, (cuuint64_t)heads, (cuuint64_t)B};
@@ -817,32 +518,6 @@ static int make_tmap(CUtensorMap* map, const void* ptr, int D, long long L, int 
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) { deco_set_error("attention_bwd_tc: cuTensorMapEncodeTiled failed: %d", (int)rc); return DECO_ERR_DRIVER; }
     return DECO_OK;
-}
-
-template <int D>
-static int launch(const Maps& M, const Params& P, cudaStream_t st) {
-    using C = Cfg<D>;
-    static unsigned long long attr_done = 0;
-    if (!device_setup_done(attr_done)) {
-        cudaError_t e = cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_A);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_B);
-        if (e != cudaSuccess) { deco_set_error("attention_bwd_tc attr: %s", cudaGetErrorString(e)); return (int)e; }
-        mark_device_setup(attr_done);
-    }
-    const int sms = device_sm_count();
-    const int items_a = P.B * P.heads * ((P.Lq + kRows - 1) / kRows), items_b = P.B * P.heads * ((P.Lk + kRows - 1) / kRows);
-    attn_bwd_dq_tc_kernel<D><<<items_a < sms ? items_a : sms, kThreads, C::SMEM_A, st>>>(M, P);
-    DECO_CHECK_LAUNCH("attn_bwd_dq_tc_kernel");
-    attn_bwd_dkv_tc_kernel<D><<<items_b < sms ? items_b : sms, kThreads, C::SMEM_B, st>>>(M, P);
-    DECO_CHECK_LAUNCH("attn_bwd_dkv_tc_kernel");
-    return DECO_OK;
-}
-
-// DECO_ATTN_BWD_TC = "sync" selects the unpipelined kernel pair (A/B measurements); default = the pipelined kernels
-static bool use_pipelined() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("DECO_ATTN_BWD_TC"); v = (e && e[0] == 's') ? 0 : 1; }
-    return v == 1;
 }
 
 template <int D>
@@ -879,6 +554,10 @@ static int launch_pipe(const void* q, const void* k, const void* v, const void* 
 }  // namespace deco
 
 #ifdef ABT_TRACE
+extern "C" int deco_abt_timeline_read(long long* host) {
+    cudaMemcpyFromSymbol(host, deco::abt::pipe::g_tl, sizeof(long long) * 2 * 6 * 64 * 4);
+    return 0;
+}
 extern "C" int deco_abt_trace_read(unsigned long long* host32, int reset) {
     cudaMemcpyFromSymbol(host32, deco::abt::pipe::g_trace, sizeof(unsigned long long) * 32);
     if (reset) { unsigned long long z[32] = {}; cudaMemcpyToSymbol(deco::abt::pipe::g_trace, z, sizeof(z)); }
@@ -910,16 +589,6 @@ extern "C" int deco_attention_bwd_tc(const void* q, long long q_stride, const vo
     P.o_stride = o_stride; P.do_stride = do_stride; P.dq_stride = dq_stride; P.dkv_stride = dkv_stride;
     P.B = B; P.heads = heads; P.Lq = Lq; P.Lk = Lk;
     P.scale = scale; P.scale_log2 = scale * 1.4426950408889634f;
-    if (use_pipelined()) {
-        if (head_dim == 72) return launch_pipe<72>(q, k, v, dout, q_stride, kv_stride, do_stride, P, (cudaStream_t)stream);
-        return launch_pipe<64>(q, k, v, dout, q_stride, kv_stride, do_stride, P, (cudaStream_t)stream);
-    }
-    Maps M;
-    int rc;
-    if ((rc = make_tmap(&M.q, q, head_dim, Lq, heads, B, q_stride))) return rc;
-    if ((rc = make_tmap(&M.k, k, head_dim, Lk, heads, B, kv_stride))) return rc;
-    if ((rc = make_tmap(&M.v, v, head_dim, Lk, heads, B, kv_stride))) return rc;
-    if ((rc = make_tmap(&M.dout, dout, head_dim, Lq, heads, B, do_stride))) return rc;
-    if (head_dim == 72) return launch<72>(M, P, (cudaStream_t)stream);
-    return launch<64>(M, P, (cudaStream_t)stream);
+    if (head_dim == 72) return launch_pipe<72>(q, k, v, dout, q_stride, kv_stride, do_stride, P, (cudaStream_t)stream);
+    return launch_pipe<64>(q, k, v, dout, q_stride, kv_stride, do_stride, P, (cudaStream_t)stream);
 }

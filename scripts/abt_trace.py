@@ -1,6 +1,6 @@
-"""Where the pipelined attention-backward kernels spend their clocks (build csrc/attention_bwd_tc.cu with -DABT_TRACE into
-a scratch library first: see the command in the comment below).  python scripts/abt_trace.py
-  nvcc ... -DABT_TRACE  (scripts/abt_trace.sh builds deco_b200/_C/libdeco_trace.so and runs this with DECO_B200_LIB set)"""
+"""Where the pipelined attention-backward kernels (csrc/attention_bwd_tc.cu) spend their clocks: per-role totals and the
+timeline of CTA 0.  scripts/abt_trace.sh builds deco_b200/_C/libdeco_trace.so with -DABT_TRACE (here, nvcc cross-compiles);
+on the GPU: DECO_B200_LIB=$PWD/deco_b200/_C/libdeco_trace.so python scripts/abt_trace.py"""
 import ctypes
 import os
 import sys
@@ -39,3 +39,20 @@ for p in range(2):
     print(f"pass {p} ({'dQ' if p == 0 else 'dK/dV'}): clocks per CTA per launch")
     for i, nm in enumerate(names):
         print(f"   {nm:46s} {buf[p * 16 + i] / N / ctas:10.0f}")
+
+# timeline of CTA 0 (last launch): clocks relative to the first recorded event
+tl = (ctypes.c_longlong * (2 * 6 * 64 * 4))()
+lib.deco_abt_timeline_read(tl)
+import numpy as np
+T = np.array(tl, dtype=np.int64).reshape(2, 6, 64, 4)
+for p in range(2):
+    t0 = T[p][T[p] > 0].min()
+    R = np.where(T[p] > 0, T[p] - t0, -1)
+    print(f"pass {p}: step | S-issuer: enter, loads ready, math_done(st-2) ready, issued | G-issuer: enter, math_done ready, issued | "
+          f"math: enter, s_full ready, done | producer: enter, stage free, issued")
+    for st in range(20):
+        print(f"  {st:2d} | {R[0][st][0]:6d} {R[0][st][1]:6d} {R[0][st][2]:6d} {R[0][st][3]:6d} | {R[2][st][0]:6d} {R[2][st][1]:6d} {R[2][st][3]:6d} | "
+              f"{R[3][st][0]:6d} {R[3][st][1]:6d} {R[3][st][2]:6d} | {R[4][st][0]:6d} {R[4][st][1]:6d} {R[4][st][2]:6d}")
+    print("  read-out of item n: enter (accumulators complete), TMEM loaded, scratch written + pair barrier, done")
+    for n in range(5):
+        print(f"  {n:2d} | {R[5][n][0]:6d} {R[5][n][1]:6d} {R[5][n][2]:6d} {R[5][n][3]:6d}")
