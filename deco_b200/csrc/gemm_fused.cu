@@ -749,6 +749,9 @@ static int stream_tile_n(int N, int K) {
     if (ring_bn < 0) { const char* e = getenv("DECO_STREAM_RING_BN"); ring_bn = e ? atoi(e) : 0; }
     if (stream_uses_ring(K) && ring_bn > 0 && N % ring_bn == 0) return ring_bn;
     if (stream_uses_ring(K) && N >= 256) return 256;
+    static int plain_bn = -1;     // DECO_STREAM_BN = 128 / 192 overrides the whole-tile-staging variant's tile width (A/B measurements)
+    if (plain_bn < 0) { const char* e = getenv("DECO_STREAM_BN"); plain_bn = e ? atoi(e) : 0; }
+    if (!stream_uses_ring(K) && (plain_bn == 128 || (plain_bn == 192 && N % 192 == 0))) return plain_bn;
     return (N % 192 == 0) ? 192 : 128;
 }
 
