@@ -25,6 +25,10 @@ F32 = torch.float32
 WGRAD = os.environ.get("DECO_B200_WGRAD", "tn")                # "tn" (product path) | "transpose" (A/B check)
 DECODER_BWD = os.environ.get("DECO_B200_DECODER_BWD", "mma")   # "mma" (product path) | "scalar" (A/B check)
 FUSE_GATE_NORM = os.environ.get("DECO_B200_FUSE_GATE_NORM", "1") != "0"   # residual add + next norm in one kernel
+# SwiGLU inside GEMM epilogues: "fwd" = w13 GEMM leaves y13 and u; "1" = also the dgrad GEMM du -> dy13; "0" = stand-alone kernels
+_FS = os.environ.get("DECO_B200_FUSE_SWIGLU", "fwd")
+FUSE_SWIGLU, FUSE_SWIGLU_BWD = _FS != "0", _FS == "1"
+WGRAD_STREAM = os.environ.get("DECO_B200_WGRAD_STREAM", "1") != "0"       # weight-gradient GEMMs on a second stream
 
 
 # Called with lists of gradient tensors the moment they are final (per DiT block, walking backwards, then the tail): lets a
@@ -144,6 +148,58 @@ def _wgrad(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     return ops.gemm(ops.transpose_cast(dy), ops.transpose_cast(x), None, ops.EPI_BIAS_F32)
 
 
+_SIDE_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
+
+
+class WgradLane:
+    """The weight-gradient GEMMs of the DiT blocks on a SECOND stream.  Nothing on the backward's critical path reads a
+    dW (autograd only collects them at the end), while the chain dY -> dX -> norm / gate / SwiGLU / attention backward is
+    half memory-bound glue that leaves the tensor pipe idle: the wgrad GEMMs (a third of the backward's MMA work) fill
+    those holes instead of queueing behind them.  Works inside CUDA-graph capture (fork / join through events).
+
+    Allocation discipline: results are allocated on the MAIN stream before the fork and operands are kept referenced
+    until the main stream has waited for the GEMMs that read them (`sync(lag)`), so the caching allocator never hands a
+    block to one stream while the other still uses it."""
+
+    def __init__(self, dev: torch.device, enabled: bool):
+        self.main = torch.cuda.current_stream(dev)
+        self.side = None
+        if enabled:
+            key = dev.index if dev.index is not None else torch.cuda.current_device()
+            if key not in _SIDE_STREAMS:
+                _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
+            self.side = _SIDE_STREAMS[key]
+        self.pending: List[tuple] = []       # (event recorded on the side stream, tensors it covers)
+        self.batch: List[torch.Tensor] = []
+
+    def wgrad(self, dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+        """dW [N, K] fp32 = dy^T . x (both bf16, as they lie in memory), launched on the side stream behind everything the
+        main stream has enqueued so far."""
+        if self.side is None:
+            return _wgrad(dy, x)
+        out = torch.empty((dy.shape[1], x.shape[1]), dtype=F32, device=dy.device)
+        self.side.wait_stream(self.main)
+        with torch.cuda.stream(self.side):
+            ops.gemm_tn(dy, x, out=out)
+        self.batch += [dy, x, out]
+        return out
+
+    def mark(self) -> None:
+        """Close a batch (one DiT block): one event behind its GEMMs."""
+        if self.side is None or not self.batch:
+            return
+        ev = torch.cuda.Event()
+        ev.record(self.side)
+        self.pending.append((ev, self.batch))
+        self.batch = []
+
+    def sync(self, lag: int = 0) -> None:
+        """Main stream waits for all but the `lag` most recent batches; their operands may be released afterwards."""
+        while len(self.pending) > lag:
+            ev, _ = self.pending.pop(0)
+            self.main.wait_event(ev)
+
+
 def _colsum(x: torch.Tensor) -> torch.Tensor:
     return ops.colsum_(torch.zeros(x.shape[1], dtype=F32, device=x.device), x)
 
@@ -191,8 +247,12 @@ def train_forward(module, x32, t, y):
         else:
             s_mid = ops.gate_residual(s, a1, g1, L)
             h2 = ops.rmsnorm_modulate(s_mid, bp["n2"], sh2, sc2, L)
-        y13 = ops.gemm(h2, bp["w13"], None, ops.EPI_BIAS)
-        u = ops.swiglu_fwd(y13)
+        if FUSE_SWIGLU:     # one GEMM leaves both the pre-activation (for the backward) and u
+            y13 = torch.empty((h2.shape[0], bp["w13"].shape[0]), dtype=bf16, device=dev)
+            u = ops.gemm(h2, bp["w13"], None, ops.EPI_SWIGLU_DUAL, aux=y13)
+        else:
+            y13 = ops.gemm(h2, bp["w13"], None, ops.EPI_BIAS)
+            u = ops.swiglu_fwd(y13)
         a2 = ops.gemm(u, bp["w2"], None, ops.EPI_BIAS)
         h1_next = None
         if FUSE_GATE_NORM and i + 1 < nb:
@@ -223,6 +283,10 @@ def train_backward(module, S: dict, dout: torch.Tensor) -> Dict[str, torch.Tenso
     R = module.num_blocks - module.num_cond_blocks
     C = module.in_channels
     G: Dict[str, torch.Tensor] = {}
+    # wgrad GEMMs of the blocks on a second stream (not under the per-GEMM event probe of the bench's roofline pass, whose
+    # launch durations must not overlap other work, and not for the A/B transpose variant)
+    lane = WgradLane(dev, WGRAD_STREAM and WGRAD == "tn" and ops.gemm_probe is None)
+    ready: List[List[torch.Tensor]] = []     # per finished block: its matrix gradients, announced once the lane delivered
     z = lambda *shape: torch.zeros(shape, dtype=F32, device=dev)   # noqa: E731
 
     # ---- pixel decoder (+ NerfEmbedder)
@@ -284,13 +348,14 @@ def train_backward(module, S: dict, dout: torch.Tensor) -> Dict[str, torch.Tenso
         # previous iteration, or here for the last block)
         if da2 is None:
             da2 = ops.gate_bwd(ds, sv["a2"], g2, dg2, L)
-        gw2 = _wgrad(da2, sv["u"])
-        G[pre + "mlp.w2.weight"] = gw2 if F_ == Fp else gw2[:, :F_].contiguous()
-        du = ops.gemm(da2, bt["w2T"], None, ops.EPI_BIAS)
-        dy13 = ops.swiglu_bwd(sv["y13"], du)
-        dw13 = _wgrad(dy13, sv["h2"]).view(Fp // 16, 2, 16, H)
-        G[pre + "mlp.w1.weight"] = dw13[:, 0].reshape(Fp, H)[:F_]
-        G[pre + "mlp.w3.weight"] = dw13[:, 1].reshape(Fp, H)[:F_]
+        gw2 = lane.wgrad(da2, sv["u"])
+        if FUSE_SWIGLU_BWD:     # du never reaches memory: the dgrad GEMM's epilogue turns it into dy13
+            dy13 = ops.gemm(da2, bt["w2T"], None, ops.EPI_SWIGLU_BWD, aux=sv["y13"])
+            du = None
+        else:
+            du = ops.gemm(da2, bt["w2T"], None, ops.EPI_BIAS)
+            dy13 = ops.swiglu_bwd(sv["y13"], du)
+        gw13 = lane.wgrad(dy13, sv["h2"])
         dh2 = ops.gemm(dy13, bt["w13T"], None, ops.EPI_BIAS)
         dn2, dn1, dbproj, dqn, dkn = zblk[i, :H], zblk[i, H:2 * H], zblk[i, 2 * H:3 * H], zblk[i, 3 * H:3 * H + d], zblk[i, 3 * H + d:]
         # norm2 backward + the gate backward of the attention branch's residual add, one pass over ds
@@ -304,7 +369,7 @@ def train_backward(module, S: dict, dout: torch.Tensor) -> Dict[str, torch.Tenso
         del da2, du, dy13, dh2
         # attention branch
         G[pre + "attn.proj.bias"] = dbproj
-        G[pre + "attn.proj.weight"] = _wgrad(da1, sv["o"])
+        gwproj = lane.wgrad(da1, sv["o"])
         do = ops.gemm(da1, bt["wprojT"], None, ops.EPI_BIAS)
         qkv = sv["qkv"]
         dqkv = torch.empty_like(qkv)
@@ -313,7 +378,8 @@ def train_backward(module, S: dict, dout: torch.Tensor) -> Dict[str, torch.Tenso
         ops.headnorm_rope_bwd_(dqkv, sv["qkv_raw"], 0, bp["qn"], S["pos"], dqn, heads, d, L)
         ops.headnorm_rope_bwd_(dqkv, sv["qkv_raw"], H, bp["kn"], S["pos"], dkn, heads, d, L)
         G[pre + "attn.q_norm.weight"], G[pre + "attn.k_norm.weight"] = dqn, dkn
-        G[pre + "attn.qkv.weight"] = _wgrad(dqkv, sv["h1"])
+        gwqkv = lane.wgrad(dqkv, sv["h1"])
+        lane.mark()
         dh1 = ops.gemm(dqkv, bt["wqkvT"], None, ops.EPI_BIAS)
         da2 = None
         if FUSE_GATE_NORM and i > 0:      # norm1 backward + the gate backward of block i - 1's second residual add
@@ -324,10 +390,23 @@ def train_backward(module, S: dict, dout: torch.Tensor) -> Dict[str, torch.Tenso
             ops.rmsnorm_modulate_bwd_(ds, dh1, sv["s_in"], bp["n1"], sc1, dn1, dsh1, dsc1, L)
         G[pre + "norm1.weight"] = dn1
         del da1, do, dqkv, dh1
-        S["blocks"][i] = None   # release the block's activations
-        # the block's matrix gradients are final (the vector gradients live in zblk / dmod and follow with the tail)
-        _grads_ready([G[pre + k] for k in ("mlp.w2.weight", "mlp.w1.weight", "mlp.w3.weight", "attn.proj.weight",
-                                           "attn.qkv.weight")])
+        S["blocks"][i] = None   # release the block's activations (the lane keeps what its GEMMs still read)
+        # The main stream joins the lane one block late, so that a block's wgrad GEMMs overlap the next block's chain; the
+        # matrix gradients of a joined block are final (w1 / w3 de-interleaved on the main stream) and are announced; the
+        # vector gradients live in zblk / dmod and follow with the tail.
+        ready.append((i, F_, gw2, gw13, gwproj, gwqkv))
+        del gw2, gw13, gwproj, gwqkv
+        lane.sync(lag=1 if i > 0 else 0)
+        while len(ready) > (1 if (i > 0 and lane.side is not None) else 0):
+            j, Fj, w2g, w13g, wpg, wqg = ready.pop(0)
+            prej = f"blocks.{j}."
+            G[prej + "mlp.w2.weight"] = w2g if Fj == Fp else w2g[:, :Fj].contiguous()
+            w13g = w13g.view(Fp // 16, 2, 16, H)
+            G[prej + "mlp.w1.weight"] = w13g[:, 0].reshape(Fp, H)[:Fj]
+            G[prej + "mlp.w3.weight"] = w13g[:, 1].reshape(Fp, H)[:Fj]
+            G[prej + "attn.proj.weight"], G[prej + "attn.qkv.weight"] = wpg, wqg
+            _grads_ready([G[prej + k] for k in ("mlp.w2.weight", "mlp.w1.weight", "mlp.w3.weight", "attn.proj.weight",
+                                                "attn.qkv.weight")])
 
     # ---- s_embedder: s0 = xp . ws^T + bs
     G["s_embedder.proj.weight"] = _wgrad(ds, S["xp"])

@@ -33,13 +33,17 @@ enum GemmEpilogue : int {
     EPI_GATE_RESIDUAL = 2,  // out = resid + gate[row / rows_per_gate] * (acc + bias); resid / out are FP32
     EPI_SWIGLU = 3,         // columns interleaved in 16s: out[:, n/2 + i] = silu(acc[n + i]) * acc[n + 16 + i]
     EPI_BIAS_F32 = 4,       // out = acc + bias, FP32 output (starts the fp32 residual stream)
+    // training path: the SwiGLU passes live in the epilogues of the GEMMs next to them (row-per-thread form only)
+    EPI_SWIGLU_DUAL = 5,    // EPI_SWIGLU + the pre-activation acc itself as bf16 [M, N] into `resid` (what the backward reads)
+    EPI_SWIGLU_BWD = 6,     // acc = du [M, N]; `resid` = y13 bf16 [M, 2N] interleaved [16 a | 16 b]; out = dy13 bf16 [M, 2N]:
+                            //   dy[32 g + i] = du b silu'(a), dy[32 g + 16 + i] = du silu(a)   (N a multiple of 16)
 };
 
 struct GemmParams {
     void* out;                       // [M, ldo] bf16 (fp32 for EPI_GATE_RESIDUAL / EPI_BIAS_F32)
     long long ldo;
     const float* bias;               // [N] fp32 or null
-    const float* resid;              // [M, ldr] fp32 (EPI_GATE_RESIDUAL)
+    const float* resid;              // [M, ldr] fp32 (EPI_GATE_RESIDUAL); bf16 y13 (EPI_SWIGLU_DUAL: written, EPI_SWIGLU_BWD: read)
     long long ldr;
     const __nv_bfloat16* gate;       // [M / rows_per_gate, gate_stride]
     long long gate_stride;
@@ -49,11 +53,16 @@ struct GemmParams {
                                      // partial products are reduced with fp32 atomics into a pre-zeroed output
 };
 
-template <int BN, int CG> struct GemmCfg {
+// Epilogue warps: 4 (one per TMEM lane quarter), or 8 for the SwiGLU training epilogues -- two warps per quarter, each
+// draining half of the tile's columns: their per-element math and the pre-activation traffic (128 B in + 128 B out per
+// row and 32-column chunk) need more warps in flight than four to keep up with the main loop.
+__host__ __device__ constexpr int epi_warps(int epi) { return epi >= 5 ? 8 : 4; }
+
+template <int BN, int CG, int EW = 4> struct GemmCfg {
     static constexpr int kStageBytesA = kBM * kBK * 2;               // this CTA's 128 rows of A
     static constexpr int kStageBytesB = (BN / CG) * kBK * 2;         // this CTA's share of the W tile
     static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
-    static constexpr int kEpiStageBytes = 4 * 32 * 36 * 4;           // 4 epilogue warps x [32][36] fp32
+    static constexpr int kEpiStageBytes = EW * 32 * 36 * 4;          // EW epilogue warps x [32][36] fp32
     static constexpr int kBudget = 227 * 1024 - kEpiStageBytes - 1024 - 256;
     static constexpr int kStagesRaw = kBudget / kStageBytes;
     static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
@@ -164,6 +173,30 @@ __device__ __forceinline__ void epilogue_chunk_staged(const GemmParams& P, const
     __syncwarp();
 }
 
+// bf16 copy of a warp's 32 x 32 accumulator chunk to dst[row0 + r][n0 + c] through the warp's staging tile: a store
+// instruction covers 4 rows x 64 contiguous bytes (row-per-thread stores touch 32 lines per instruction).
+__device__ __forceinline__ void store_chunk_bf16_staged(const uint32_t (&acc)[32], float* stg, __nv_bfloat16* dst, long long ld,
+                                                        long long row0, int n0, int lane, int M, int N) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(stg + lane * kStageLd + 4 * j) =
+            make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]),
+                        __uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3]));
+    __syncwarp();
+    const int cg = lane & 7, rsub = lane >> 3;
+    const int n = n0 + 4 * cg;
+    if (n < N) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int r = it * 4 + rsub;
+            const long long row = row0 + r;
+            const float4 v = *reinterpret_cast<const float4*>(stg + r * kStageLd + 4 * cg);
+            if (row < M) *reinterpret_cast<uint2*>(dst + row * ld + n) = make_uint2(pack_bf2(v.x, v.y), pack_bf2(v.z, v.w));
+        }
+    }
+    __syncwarp();
+}
+
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk_direct(const GemmParams& P, const uint32_t (&acc)[32], long long row, int n0) {
     if (row >= P.M) return;
@@ -179,7 +212,7 @@ __device__ __forceinline__ void epilogue_chunk_direct(const GemmParams& P, const
             }
         }
     }
-    if (EPI == EPI_SWIGLU) {
+    if (EPI == EPI_SWIGLU || EPI == EPI_SWIGLU_DUAL) {
         __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(P.out) + row * P.ldo + (n0 >> 1);
         uint32_t w[8];
 #pragma unroll
@@ -229,6 +262,66 @@ __device__ __forceinline__ void epilogue_chunk_direct(const GemmParams& P, const
     }
 }
 
+// EPI_SWIGLU_BWD.  The 32 du columns [n0, n0 + 32) of a row are two groups of 16; their pre-activations are the 64 bf16
+// = 128 contiguous bytes y13[row][2 n0 ...] = [a0 | b0 | a1 | b1] (16 each), and dy13 goes to the same place of the output.
+// Global accesses are coalesced: in iteration `it` lane l owns the 16-byte piece (l & 7) of row 4 it + (l >> 3), so one
+// instruction covers 4 rows x 128 bytes; du comes from the warp's staging tile, the (a, b) partner piece by shuffle.
+struct SwigluPre { uint4 q[8]; };
+
+__device__ __forceinline__ void load_swiglu_pre(const GemmParams& P, SwigluPre& y, long long row0, int n0, int lane) {
+    const int pc = lane & 7, rsub = lane >> 3;
+    const bool col_ok = n0 + 16 * (pc >> 2) < P.N;
+    const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(P.resid) + 2 * n0 + 8 * pc;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const long long row = row0 + it * 4 + rsub;
+        y.q[it] = (col_ok && row < P.M) ? __ldg(reinterpret_cast<const uint4*>(src + row * P.ldr)) : make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+
+__device__ __forceinline__ void epilogue_chunk_swiglu_bwd(const GemmParams& P, const uint32_t (&acc)[32], float* stg,
+                                                          const SwigluPre& y, long long row0, int n0, int lane) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(stg + lane * kStageLd + 4 * j) =
+            make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]),
+                        __uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3]));
+    __syncwarp();
+    const int pc = lane & 7, rsub = lane >> 3;
+    const int grp = pc >> 2, is_b = (pc >> 1) & 1, half = pc & 1;     // piece = group, a / b part, elements 8 half .. + 7
+    const bool col_ok = n0 + 16 * grp < P.N;
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(P.out) + 2 * n0 + 8 * pc;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int r = it * 4 + rsub;
+        const long long row = row0 + r;
+        const uint4 mine = y.q[it];
+        uint4 other;                        // the partner's piece: b for an a-lane and vice versa (lane ^ 2)
+        other.x = __shfl_xor_sync(0xffffffffu, mine.x, 2); other.y = __shfl_xor_sync(0xffffffffu, mine.y, 2);
+        other.z = __shfl_xor_sync(0xffffffffu, mine.z, 2); other.w = __shfl_xor_sync(0xffffffffu, mine.w, 2);
+        const uint4 qa = is_b ? other : mine, qb = is_b ? mine : other;
+        const float* dp = stg + r * kStageLd + 16 * grp + 8 * half;
+        const float4 d0 = *reinterpret_cast<const float4*>(dp), d1 = *reinterpret_cast<const float4*>(dp + 4);
+        const float du[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+        const uint32_t wa[4] = {qa.x, qa.y, qa.z, qa.w}, wb[4] = {qb.x, qb.y, qb.z, qb.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 a = unpack_bf2(wa[e]), b = unpack_bf2(wb[e]);
+            // sigmoid(a) = 1/2 + 1/2 tanh(a/2): one MUFU op; silu = a s, silu' = s (1 + a (1 - s))
+            float t0, t1;
+            asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(0.5f * a.x));
+            asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(0.5f * a.y));
+            const float s0 = fmaf(0.5f, t0, 0.5f), s1 = fmaf(0.5f, t1, 0.5f);
+            const float f0 = is_b ? a.x * s0 : b.x * (s0 * fmaf(a.x, 1.0f - s0, 1.0f));
+            const float f1 = is_b ? a.y * s1 : b.y * (s1 * fmaf(a.y, 1.0f - s1, 1.0f));
+            o[e] = pack_bf2(du[2 * e] * f0, du[2 * e + 1] * f1);
+        }
+        if (col_ok && row < P.M) *reinterpret_cast<uint4*>(dst + row * P.ldo) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    __syncwarp();
+}
+
 // ------------------------------------------------------------------ kernel
 // CG = 1: one CTA per 128 x BN tile.   CG = 2: a 2-CTA cluster per 256 x BN tile (rank 0 = leader issues the MMAs).
 // TN = true: both operands are given TRANSPOSED in global memory -- At [K, M] and Wt [K, N], row-major -- and are staged
@@ -236,11 +329,12 @@ __device__ __forceinline__ void epilogue_chunk_direct(const GemmParams& P, const
 // 8 KB apart (LBO), 8-row K groups 1 KB apart (SBO); the instruction descriptor flags both operands MN-major.  This is
 // the wgrad contraction dW = dY^T . X read straight from the row-major activations (no transposed copies).
 template <int BN, int EPI, int CG, bool STAGED, bool TN = false>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(128 + 32 * epi_warps(EPI), 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const GemmParams P)
 {
-    using Cfg = GemmCfg<BN, CG>;
+    constexpr int kEW = epi_warps(EPI);
+    using Cfg = GemmCfg<BN, CG, kEW>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte alignment is required by the 128-byte swizzle atom (8 rows x 128 B); identical offsets in both CTAs
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -274,7 +368,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < kAccStages; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4 * CG); }
+        for (int s = 0; s < kAccStages; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), kEW * CG); }
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -368,8 +462,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     } else if (warp >= kEpiWarp0) {
         // ===================== epilogue (each CTA drains its own 128 accumulator rows) =====================
         const int q = warp & 3;                          // TMEM lane quarter this warp may access
+        // with 8 epilogue warps, warps 4-7 drain the first half of the tile's 32-column chunks and warps 8-11 the second
+        constexpr int kChunks = BN / 32 / (kEW / 4);
+        const int c_begin = ((warp - kEpiWarp0) >> 2) * kChunks, c_end = c_begin + kChunks;
         int as = 0; uint32_t aphase = 0;
-        float* stg = reinterpret_cast<float*>(smem_raw + (epi_stage_base - smem_u32(smem_raw))) + q * kStageFloatsPerWarp;
+        float* stg = reinterpret_cast<float*>(smem_raw + (epi_stage_base - smem_u32(smem_raw))) +
+                     (warp - kEpiWarp0) * kStageFloatsPerWarp;
         for (int tile = tile0; tile < num_tiles; tile += tile_stride) {
             const int m_blk = (tile % num_mn) / num_n, n_blk = (tile % num_mn) % num_n;
             const long long row0 = (long long)(m_blk * CG + (int)cta_rank) * kBM + q * 32;
@@ -397,16 +495,40 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     if (row0 < P.M && nbase + (c + 1) * 32 < P.N)
                         epilogue_chunk_staged<EPI>(P, acc, stg, row0, nbase + (c + 1) * 32, lane, rcB, ug);
                 }
+            } else if (EPI == EPI_SWIGLU_BWD) {
+                // the pre-activations of a chunk are fetched one chunk ahead (the first before the accumulator barrier)
+                SwigluPre yA, yB;
+                load_swiglu_pre(P, yA, row0, nbase + c_begin * 32, lane);
+                mbar_wait(tfull_bar(as), aphase);
+                tc_fence_after();
+#pragma unroll 1
+                for (int c = c_begin; c < c_end; c += 2) {
+                    uint32_t acc[32];
+                    if (c + 1 < c_end) load_swiglu_pre(P, yB, row0, nbase + (c + 1) * 32, lane);
+                    tmem_ld32(taddr + (uint32_t)(c * 32), acc);
+                    tmem_ld_wait();
+                    if (row0 < P.M && nbase + c * 32 < P.N) epilogue_chunk_swiglu_bwd(P, acc, stg, yA, row0, nbase + c * 32, lane);
+                    if (c + 1 < c_end) {
+                        if (c + 2 < c_end) load_swiglu_pre(P, yA, row0, nbase + (c + 2) * 32, lane);
+                        tmem_ld32(taddr + (uint32_t)((c + 1) * 32), acc);
+                        tmem_ld_wait();
+                        if (row0 < P.M && nbase + (c + 1) * 32 < P.N)
+                            epilogue_chunk_swiglu_bwd(P, acc, stg, yB, row0, nbase + (c + 1) * 32, lane);
+                    }
+                }
             } else {
                 mbar_wait(tfull_bar(as), aphase);
                 tc_fence_after();
 #pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
+                for (int c = c_begin; c < c_end; ++c) {
                     uint32_t acc[32];
                     tmem_ld32(taddr + (uint32_t)(c * 32), acc);
                     tmem_ld_wait();
                     const int n0 = nbase + c * 32;
                     if (row0 < P.M && n0 < P.N) {             // warp-uniform guard
+                        if (EPI == EPI_SWIGLU_DUAL)         // the pre-activation as the backward will read it
+                            store_chunk_bf16_staged(acc, stg, reinterpret_cast<__nv_bfloat16*>(const_cast<float*>(P.resid)), P.ldr,
+                                                    row0, n0, lane, P.M, P.N);
                         if (STAGED) { ResidChunk none; epilogue_chunk_staged<EPI>(P, acc, stg, row0, n0, lane, none, false); }
                         else epilogue_chunk_direct<EPI>(P, acc, row0 + lane, n0);
                     }
@@ -448,7 +570,7 @@ static int make_tmap(CUtensorMap* map, const void* ptr, long long rows, long lon
 
 template <int BN, int EPI, int CG, bool STAGED, bool TN = false>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& P, int max_ctas, cudaStream_t st) {
-    using Cfg = GemmCfg<BN, CG>;
+    using Cfg = GemmCfg<BN, CG, epi_warps(EPI)>;
     auto kern = gemm_bf16_tcgen05_kernel<BN, EPI, CG, STAGED, TN>;
     static unsigned long long attr_done = 0;   // per instantiation
     if (!device_setup_done(attr_done)) {
@@ -461,7 +583,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
     if (tiles < groups) groups = tiles;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(groups * CG);
-    cfg.blockDim = dim3(kGemmThreads);
+    cfg.blockDim = dim3(128 + 32 * epi_warps(EPI));
     cfg.dynamicSmemBytes = Cfg::kSmemBytes;
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
@@ -484,6 +606,8 @@ static int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, c
         case EPI_GATE_RESIDUAL: return launch_gemm<BN, EPI_GATE_RESIDUAL, CG, STAGED>(ta, tb, P, max_ctas, st);
         case EPI_SWIGLU: return launch_gemm<BN, EPI_SWIGLU, CG, STAGED>(ta, tb, P, max_ctas, st);
         case EPI_BIAS_F32: return launch_gemm<BN, EPI_BIAS_F32, CG, STAGED>(ta, tb, P, max_ctas, st);
+        case EPI_SWIGLU_DUAL: return launch_gemm<BN, EPI_SWIGLU_DUAL, CG, false>(ta, tb, P, max_ctas, st);   // row-per-thread only
+        case EPI_SWIGLU_BWD: return launch_gemm<BN, EPI_SWIGLU_BWD, CG, false>(ta, tb, P, max_ctas, st);
     }
     deco_set_error("gemm: unknown epilogue %d", epi);
     return DECO_ERR_ARG;
@@ -521,7 +645,10 @@ extern "C" int deco_gemm_bf16(const void* A, long long lda, const void* W, long 
     if (epilogue == EPI_GATE_RESIDUAL)
         DECO_CHECK_ARG(resid && gate && rows_per_gate > 0 && ldr % 8 == 0 && gate_stride % 8 == 0 &&
                        (((uintptr_t)resid | (uintptr_t)gate) & 15) == 0, "gemm: gate/residual arguments invalid");
-    if (epilogue == EPI_SWIGLU) DECO_CHECK_ARG(N % 32 == 0, "gemm: swiglu epilogue needs N %% 32 == 0");
+    if (epilogue == EPI_SWIGLU || epilogue == EPI_SWIGLU_DUAL) DECO_CHECK_ARG(N % 32 == 0, "gemm: swiglu epilogue needs N %% 32 == 0");
+    if (epilogue == EPI_SWIGLU_DUAL || epilogue == EPI_SWIGLU_BWD)
+        DECO_CHECK_ARG(resid && ldr % 8 == 0 && ((uintptr_t)resid & 15) == 0 && N % 16 == 0,
+                       "gemm: the SwiGLU training epilogues take the bf16 pre-activation matrix in resid / ldr (N %% 16 == 0)");
     // tile width: measured on the XL shapes (scripts/gemm_bench.py, profiles/gemm_bench_r1.txt): 256 where it divides N
     // (cond_embed 1315 TFLOP/s, SwiGLU 1554 with the direct epilogue), 192 for the 1152-multiples
     int bn = tile_n;
@@ -532,6 +659,7 @@ extern "C" int deco_gemm_bf16(const void* A, long long lda, const void* W, long 
     // staged (coalesced) epilogue everywhere except SwiGLU, whose output is half as wide as its accumulator tile and
     // is compute-heavy: the row-per-thread form keeps all 128 epilogue threads busy (1554 vs 1069 TFLOP/s at BN = 256)
     int staged = (g_force_staged >= 0) ? g_force_staged : (epilogue == EPI_SWIGLU ? 0 : 1);
+    if (epilogue == EPI_SWIGLU_DUAL || epilogue == EPI_SWIGLU_BWD) staged = 0;
     CUtensorMap ta, tb;
     int rc = make_tmap(&ta, A, M, K, lda, kBM);
     if (rc) return rc;

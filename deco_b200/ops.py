@@ -12,7 +12,7 @@ import torch
 from . import _lib
 from ._lib import call, ptr
 
-EPI_BIAS, EPI_BIAS_SILU, EPI_GATE_RESIDUAL, EPI_SWIGLU, EPI_BIAS_F32 = 0, 1, 2, 3, 4
+EPI_BIAS, EPI_BIAS_SILU, EPI_GATE_RESIDUAL, EPI_SWIGLU, EPI_BIAS_F32, EPI_SWIGLU_DUAL, EPI_SWIGLU_BWD = 0, 1, 2, 3, 4, 5, 6
 bf16 = torch.bfloat16
 gemm_probe = None   # set to a deco_b200.utils.GemmProbe to time every GEMM launch with CUDA events
 ATTN_BWD = __import__("os").environ.get("DECO_B200_ATTN_BWD", "tc")     # "tc" (tcgen05) | "legacy" (mma.sync)
@@ -30,17 +30,20 @@ def _st(t):
 
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, epilogue: int = EPI_BIAS,
          out: Optional[torch.Tensor] = None, resid: Optional[torch.Tensor] = None,
-         gate: Optional[torch.Tensor] = None, rows_per_gate: int = 1, tile_n: int = 0) -> torch.Tensor:
+         gate: Optional[torch.Tensor] = None, rows_per_gate: int = 1, tile_n: int = 0,
+         aux: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out = epilogue(a @ w.T): a [M,K] bf16 (row stride allowed), w [N,K] bf16, bias fp32 [N].
     gate: bf16 2-D view [M/rows_per_gate, N] with arbitrary row stride; resid fp32 [M,N].
-    Output is bf16 except for EPI_GATE_RESIDUAL / EPI_BIAS_F32 (the fp32 residual stream)."""
-    _cuda(a, w, bias, out, resid, gate)
+    Output is bf16 except for EPI_GATE_RESIDUAL / EPI_BIAS_F32 (the fp32 residual stream).
+    Training epilogues: EPI_SWIGLU_DUAL also WRITES the bf16 pre-activation [M,N] into `aux`; EPI_SWIGLU_BWD treats
+    a @ w.T as du [M,N], reads the pre-activation `aux` [M,2N] and returns dy13 [M,2N]."""
+    _cuda(a, w, bias, out, resid, gate, aux)
     assert a.dtype == bf16 and w.dtype == bf16 and a.dim() == 2 and w.dim() == 2
     assert a.stride(1) == 1 and w.stride(1) == 1
     M, K = a.shape
     N = w.shape[0]
     assert w.shape[1] == K, (a.shape, w.shape)
-    n_out = N // 2 if epilogue == EPI_SWIGLU else N
+    n_out = N // 2 if epilogue in (EPI_SWIGLU, EPI_SWIGLU_DUAL) else (2 * N if epilogue == EPI_SWIGLU_BWD else N)
     odt = torch.float32 if epilogue in (EPI_GATE_RESIDUAL, EPI_BIAS_F32) else bf16
     if out is None:
         out = torch.empty((M, n_out), dtype=odt, device=a.device)
@@ -54,6 +57,10 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
         assert gate.dtype == bf16 and gate.dim() == 2 and gate.shape[1] == N and gate.stride(1) == 1
         assert gate.shape[0] * rows_per_gate >= M
         ldr, gs = resid.stride(0), gate.stride(0)
+    if epilogue in (EPI_SWIGLU_DUAL, EPI_SWIGLU_BWD):
+        assert aux is not None and resid is None and aux.dtype == bf16 and aux.stride(1) == 1
+        assert aux.shape == (M, N if epilogue == EPI_SWIGLU_DUAL else 2 * N)
+        resid, ldr = aux, aux.stride(0)
     probe = gemm_probe
     ev = probe.before() if probe is not None else None
     call("deco_gemm_bf16", ptr(a), a.stride(0), ptr(w), w.stride(0), ptr(out), out.stride(0), M, N, K, epilogue,
@@ -823,15 +830,19 @@ def gemm_f32_splitk(a: torch.Tensor, w: torch.Tensor, split_k: int = 0) -> torch
     return out
 
 
-def gemm_tn(at: torch.Tensor, wt: torch.Tensor, tile_n: int = 0, split_k: int = 0) -> torch.Tensor:
+def gemm_tn(at: torch.Tensor, wt: torch.Tensor, tile_n: int = 0, split_k: int = 0,
+            out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out [M, N] fp32 = at^T @ wt for at [K, M], wt [K, N] bf16 row-major (wgrad: dW = dY^T . X, K = tokens); no
-    transposed copies -- the GEMM stages both operands MN-major."""
+    transposed copies -- the GEMM stages both operands MN-major.  `out` lets the caller allocate the result on another
+    stream than the one the GEMM is launched on."""
     _cuda(at, wt)
     assert at.dtype == bf16 and wt.dtype == bf16 and at.dim() == 2 and wt.dim() == 2
     assert at.stride(1) == 1 and wt.stride(1) == 1 and at.shape[0] == wt.shape[0]
     K, M = at.shape
     N = wt.shape[1]
-    out = torch.empty((M, N), dtype=torch.float32, device=at.device)
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=at.device)
+    assert out.dtype == torch.float32 and out.shape == (M, N) and out.stride(1) == 1
     probe = gemm_probe
     ev = probe.before() if probe is not None else None
     call("deco_gemm_bf16_tn", ptr(at), at.stride(0), ptr(wt), wt.stride(0), ptr(out), out.stride(0), M, N, K, tile_n, split_k,

@@ -34,6 +34,10 @@ int deco_abi_version(void);
 #define DECO_EPI_GATE_RESIDUAL 2  /* out = resid + gate[row / rows_per_gate] * (A.W^T + bias); resid, out FP32      */
 #define DECO_EPI_SWIGLU 3         /* W rows interleaved [16 x w1 | 16 x w3]: out[:, j] = silu(a_j) * b_j, N/2 cols */
 #define DECO_EPI_BIAS_F32 4       /* out = A.W^T + bias, FP32 output (head of the fp32 residual stream)           */
+/* training step: the SwiGLU passes of mlp (dit_c2i_DeCo.py:113) inside the GEMMs next to them; `resid` / `ldr` carry the
+ * bf16 pre-activation matrix y13 = [16 x w1 | 16 x w3]-interleaved instead of the fp32 residual */
+#define DECO_EPI_SWIGLU_DUAL 5    /* DECO_EPI_SWIGLU, and y13 = bf16(A.W^T) [M, N] is WRITTEN to resid (saved for backward) */
+#define DECO_EPI_SWIGLU_BWD 6     /* du = A.W^T [M, N]; y13 [M, 2N] READ from resid; out = dy13 bf16 [M, 2N]             */
 
 /* tcgen05 / TMEM / TMA bf16 GEMM: out[M, N(or N/2)] = epilogue(A[M,K] . W[N,K]^T), fp32 accumulate.
  * Replaces nn.Linear at src/models/transformer/dit_c2i_DeCo.py:496 (s_embedder), :55-57 (t_embedder.mlp),

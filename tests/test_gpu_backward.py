@@ -191,6 +191,37 @@ def test_swiglu_forward_backward(dev):
     assert rel_l2(dy.float(), yy.grad.reshape(M, 2 * Fp)) < 5e-3
 
 
+@pytest.mark.parametrize("M,K,Fp", [(300, 144, 688), (1024, 1152, 3072), (77, 64, 48)])
+def test_swiglu_gemm_epilogues_vs_autograd(dev, M, K, Fp):
+    """The training GEMMs that carry the SwiGLU passes (csrc/gemm_tcgen05.cu EPI_SWIGLU_DUAL / EPI_SWIGLU_BWD) against
+    autograd over the same bf16 operands: y13 = h W13^T, u = silu(a) b (dit_c2i_DeCo.py:113), dy13 from du = da W2."""
+    from deco_b200 import ops
+    h = torch.randn(M, K, device=dev, generator=_g(1)).to(bf16)
+    w13 = (torch.randn(2 * Fp, K, device=dev, generator=_g(2)) * K ** -0.5).to(bf16)     # rows interleaved [16 w1 | 16 w3]
+    if Fp % 16 == 0 and (2 * Fp) % 32 == 0:
+        y13 = torch.full((M + 1, 2 * Fp), 7.0, device=dev).to(bf16)      # one guard row
+        u = ops.gemm(h, w13, None, ops.EPI_SWIGLU_DUAL, aux=y13[:M])
+        y_ref = h.float() @ w13.float().t()
+        yy = y_ref.view(M, Fp // 16, 2, 16)
+        u_ref = (F.silu(yy[:, :, 0]) * yy[:, :, 1]).reshape(M, Fp)
+        assert rel_l2(y13[:M].float(), y_ref) < 5e-3 and rel_l2(u.float(), u_ref) < 5e-3
+        assert bool((y13[M] == 7.0).all())
+        assert torch.equal(y13[:M], ops.gemm(h, w13, None, ops.EPI_BIAS))       # the very bf16 the plain GEMM writes
+    # backward: du = da . W2 (the dgrad GEMM takes W2^T [Fp, H] as its weight operand), dy13 = SwiGLU'(y13) du
+    Hh = 96
+    da = torch.randn(M, Hh, device=dev, generator=_g(3)).to(bf16)
+    w2T = (torch.randn(Fp, Hh, device=dev, generator=_g(4)) * Hh ** -0.5).to(bf16)
+    y13 = torch.randn(M, 2 * Fp, device=dev, generator=_g(5)).to(bf16)
+    yy = y13.float().view(M, Fp // 16, 2, 16).clone().requires_grad_(True)
+    (F.silu(yy[:, :, 0]) * yy[:, :, 1]).reshape(M, Fp).backward(da.float() @ w2T.float().t())
+    dy = torch.full((M + 1, 2 * Fp), 7.0, device=dev).to(bf16)
+    ops.gemm(da, w2T, None, ops.EPI_SWIGLU_BWD, aux=y13, out=dy[:M])
+    assert rel_l2(dy[:M].float(), yy.grad.reshape(M, 2 * Fp)) < 5e-3
+    assert bool((dy[M] == 7.0).all())
+    two = ops.swiglu_bwd(y13, ops.gemm(da, w2T, None, ops.EPI_BIAS))            # the two-kernel form it replaces
+    assert rel_l2(dy[:M].float(), two.float()) < 6e-3
+
+
 @pytest.mark.parametrize("B,L,H", [(2, 16, 576), (2, 64, 1152), (1, 4, 1024)])
 def test_rmsnorm_modulate_backward(dev, B, L, H):
     from deco_b200 import ops
@@ -421,6 +452,55 @@ def test_training_step_gradients_d64_ragged_ffn(dev):
     # head_dim 64, hidden 256 -> FFN width int(2*1024/3) = 682 (padded to 688), 128 px -> 64 tokens
     cfg = O.DenoiserCfg(num_groups=4, hidden_size=256, num_blocks=6, num_cond_blocks=3, num_classes=10)
     _grad_check(dev, cfg, B=2, res=128, tol=2e-2)
+
+
+def test_wgrad_side_stream_matches_single_stream(dev, monkeypatch):
+    """The weight-gradient GEMMs on the second stream (autograd.WgradLane) leave the same gradients as the single-stream
+    backward -- eagerly, twice in a row (allocator reuse across the two streams), and captured into a CUDA graph."""
+    from deco_b200 import autograd as A
+    cfg = O.DenoiserCfg(num_groups=4, hidden_size=288, num_blocks=6, num_cond_blocks=4, num_classes=10)
+    m, _ = build_module(cfg, dev)
+    m.train()
+    x = torch.randn(4, 3, 128, 128, device=dev, generator=_g(21))
+    t = torch.rand(4, device=dev, generator=_g(22))
+    y = torch.tensor([1, 10, 3, 7], device=dev)
+    w = torch.randn(4, 3, 128, 128, device=dev, generator=_g(23))
+
+    def grads():
+        for p in m.parameters():
+            p.grad = None
+        (m(x, t, y) * w).sum().backward()
+        return {n: p.grad.clone() for n, p in m.named_parameters()}
+
+    monkeypatch.setattr(A, "WGRAD_STREAM", False)
+    g0 = grads()
+    monkeypatch.setattr(A, "WGRAD_STREAM", True)
+    g1, g2 = grads(), grads()
+    def same(a, b):     # fp32 atomics (split-K, per-image sums, decoder) make two runs equal up to summation order only
+        for n in b:
+            lane_out = n.startswith("blocks.") and n.endswith(".weight") and b[n].dim() == 2 and "adaLN" not in n
+            assert rel_l2(a[n], b[n]) < (1e-5 if lane_out else 2e-3), n
+
+    same(g1, g0)
+    same(g2, g0)
+    # graph capture: fork / join of the side stream inside the capture
+    static = {n: torch.zeros_like(p) for n, p in m.named_parameters()}
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        grads()
+    torch.cuda.current_stream().wait_stream(s)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        for p in m.parameters():
+            p.grad = None
+        (m(x, t, y) * w).sum().backward()
+        for n, p in m.named_parameters():
+            static[n].copy_(p.grad)
+    for _ in range(2):
+        graph.replay()
+    torch.cuda.synchronize()
+    same(static, g0)
 
 
 def test_optimizer_step_invalidates_weight_cache(dev):
