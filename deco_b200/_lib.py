@@ -19,6 +19,7 @@ SIGNATURES = {
     "deco_abi_version": (_i, []),
     "deco_gemm_bf16": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _vp, _vp, _ll, _vp, _ll, _i, _i, _vp]),
     "deco_gemm_bf16_tn": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _i, _vp]),
+    "deco_gemm_bf16_tn_deint16": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _i, _vp]),
     "deco_gemm_bf16_f32_splitk": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _vp]),
     "deco_gemm_stream_parts": (_i, [_i, _i]),
     "deco_gemm_stream": (_i, [_vp, _ll, _vp, _ll, _i, _i, _i, _vp, _vp, _ll, _vp, _ll, _vp, _ll, _i, _vp, _vp, _ll, _vp, _ll,

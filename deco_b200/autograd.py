@@ -138,14 +138,19 @@ def prepare_train(module, P: dict, device) -> dict:
     return T
 
 
-def _wgrad(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+def _wgrad(dy: torch.Tensor, x: torch.Tensor, deinterleave16: bool = False) -> torch.Tensor:
     """dW [N, K] fp32 = dy^T [N, M] . x [M, K], M = tokens.  WGRAD = "tn": the GEMM reads dy and x as they lie in memory
-    (MN-major operands); "transpose": both operands are first copied K-major (K = M padded to 8)."""
+    (MN-major operands); "transpose": both operands are first copied K-major (K = M padded to 8).  deinterleave16: the N
+    rows are the [16 x w1 | 16 x w3] rows of the SwiGLU weight and come back as (dW1 ; dW3) stacked."""
     if WGRAD == "tn":
         if dy.dtype != bf16:
             dy = ops.cast_bf16(dy.contiguous())
-        return ops.gemm_tn(dy, x)
-    return ops.gemm(ops.transpose_cast(dy), ops.transpose_cast(x), None, ops.EPI_BIAS_F32)
+        return ops.gemm_tn(dy, x, deinterleave16=deinterleave16)
+    dw = ops.gemm(ops.transpose_cast(dy), ops.transpose_cast(x), None, ops.EPI_BIAS_F32)
+    if deinterleave16:
+        n, k = dw.shape
+        dw = dw.view(n // 32, 2, 16, k).transpose(0, 1).reshape(n, k)
+    return dw
 
 
 _SIDE_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
@@ -172,15 +177,16 @@ class WgradLane:
         self.pending: List[tuple] = []       # (event recorded on the side stream, tensors it covers)
         self.batch: List[torch.Tensor] = []
 
-    def wgrad(self, dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    def wgrad(self, dy: torch.Tensor, x: torch.Tensor, deinterleave16: bool = False) -> torch.Tensor:
         """dW [N, K] fp32 = dy^T . x (both bf16, as they lie in memory), launched on the side stream behind everything the
-        main stream has enqueued so far."""
+        main stream has enqueued so far.  deinterleave16: dy's columns are the interleaved [16 x w1 | 16 x w3] SwiGLU
+        columns; the result is (dW1 ; dW3) stacked."""
         if self.side is None:
-            return _wgrad(dy, x)
+            return _wgrad(dy, x, deinterleave16)
         out = torch.empty((dy.shape[1], x.shape[1]), dtype=F32, device=dy.device)
         self.side.wait_stream(self.main)
         with torch.cuda.stream(self.side):
-            ops.gemm_tn(dy, x, out=out)
+            ops.gemm_tn(dy, x, out=out, deinterleave16=deinterleave16)
         self.batch += [dy, x, out]
         return out
 
@@ -355,7 +361,7 @@ def train_backward(module, S: dict, dout: torch.Tensor) -> Dict[str, torch.Tenso
         else:
             du = ops.gemm(da2, bt["w2T"], None, ops.EPI_BIAS)
             dy13 = ops.swiglu_bwd(sv["y13"], du)
-        gw13 = lane.wgrad(dy13, sv["h2"])
+        gw13 = lane.wgrad(dy13, sv["h2"], deinterleave16=True)      # (dW1 ; dW3) stacked: no copy to pull them apart
         dh2 = ops.gemm(dy13, bt["w13T"], None, ops.EPI_BIAS)
         dn2, dn1, dbproj, dqn, dkn = zblk[i, :H], zblk[i, H:2 * H], zblk[i, 2 * H:3 * H], zblk[i, 3 * H:3 * H + d], zblk[i, 3 * H + d:]
         # norm2 backward + the gate backward of the attention branch's residual add, one pass over ds
@@ -401,9 +407,7 @@ def train_backward(module, S: dict, dout: torch.Tensor) -> Dict[str, torch.Tenso
             j, Fj, w2g, w13g, wpg, wqg = ready.pop(0)
             prej = f"blocks.{j}."
             G[prej + "mlp.w2.weight"] = w2g if Fj == Fp else w2g[:, :Fj].contiguous()
-            w13g = w13g.view(Fp // 16, 2, 16, H)
-            G[prej + "mlp.w1.weight"] = w13g[:, 0].reshape(Fp, H)[:Fj]
-            G[prej + "mlp.w3.weight"] = w13g[:, 1].reshape(Fp, H)[:Fj]
+            G[prej + "mlp.w1.weight"], G[prej + "mlp.w3.weight"] = w13g[:Fj], w13g[Fp:Fp + Fj]
             G[prej + "attn.proj.weight"], G[prej + "attn.qkv.weight"] = wpg, wqg
             _grads_ready([G[prej + k] for k in ("mlp.w2.weight", "mlp.w1.weight", "mlp.w3.weight", "attn.proj.weight",
                                                 "attn.qkv.weight")])

@@ -7,6 +7,7 @@
 //   :11-12 modulate, :94-99 RMSNorm.forward, :112-114 FeedForward.forward, :134-145 apply_rotary_emb,
 //   :178-180 q_norm / k_norm, :206-210 FlattenDiTBlock.forward (gated residuals), :494 silu(t + y), :499 silu(t + s).
 #include "common.cuh"
+#include <cstdlib>
 
 namespace deco {
 
@@ -487,9 +488,14 @@ static inline unsigned bgrid(long long work, int threads) {
     return (unsigned)b;
 }
 
-// rows per block of the per-image reductions: a power of two <= 32 dividing L, halved until the grid has >= 4 CTAs per SM
-// (each block ends with one atomic per column, so fewer rows per block = more atomics but enough warps to hide latency)
-static inline int rows_block(int L, long long M, int ctas_per_sm = 4) {
+// rows per block of the per-image reductions: a power of two <= 32 dividing L, halved until the grid has >= 2 CTAs per SM.
+// Each block ends with one fp32 atomic per column and sum: fewer rows per block = more warps to hide latency but more
+// atomics, and a REDG costs the SM ~1.3 clocks per lane: at 8 rows per block (4 CTAs per SM, the first setting) the norm
+// backward issued 4.7 M of them per call, ~20 us of LSU time next to ~26 us of HBM time (train step 34.95 -> 34.73 ms).
+static inline int rows_block(int L, long long M, int ctas_per_sm = -1) {
+    static int env_ctas = -2;      // DECO_ROWS_BLOCK_CTAS overrides the target CTAs per SM (A/B measurements)
+    if (env_ctas == -2) { const char* e = getenv("DECO_ROWS_BLOCK_CTAS"); env_ctas = e ? atoi(e) : -1; }
+    if (ctas_per_sm < 0) ctas_per_sm = env_ctas > 0 ? env_ctas : 2;
     int rb = 32;
     while (rb > 1 && (L % rb || M / rb < (long long)ctas_per_sm * kNumSMs)) rb >>= 1;
     return rb;

@@ -51,6 +51,9 @@ struct GemmParams {
     int M, N, K;
     int split_k;                     // > 1 (EPI_BIAS_F32 only): the K loop is cut into split_k slices, one tile each, and the
                                      // partial products are reduced with fp32 atomics into a pre-zeroed output
+    int deint_rows;                  // > 0 (EPI_BIAS_F32, staged): output rows come in interleaved groups [16 x first | 16 x
+                                     // second] (the w1 / w3 row order of the SwiGLU weight); row r is stored at
+                                     // ((r >> 4) & 1) * deint_rows + (r >> 5) * 16 + (r & 15): two stacked plain matrices
 };
 
 // Epilogue warps: 4 (one per TMEM lane quarter), or 8 for the SwiGLU training epilogues -- two warps per quarter, each
@@ -155,7 +158,8 @@ __device__ __forceinline__ void epilogue_chunk_staged(const GemmParams& P, const
                     *reinterpret_cast<float4*>(reinterpret_cast<float*>(P.out) + row * P.ldo + n) =
                         make_float4(fmaf(g0.x, v.x, rv.x), fmaf(g0.y, v.y, rv.y), fmaf(g1.x, v.z, rv.z), fmaf(g1.y, v.w, rv.w));
                 } else if (EPI == EPI_BIAS_F32) {
-                    float* o = reinterpret_cast<float*>(P.out) + row * P.ldo + n;
+                    const long long orow = P.deint_rows > 0 ? ((row >> 4) & 1) * P.deint_rows + (row >> 5) * 16 + (row & 15) : row;
+                    float* o = reinterpret_cast<float*>(P.out) + orow * P.ldo + n;
                     if (P.split_k > 1) {        // partial product of one K slice (output zeroed by the launcher)
                         atomicAdd(o, v.x); atomicAdd(o + 1, v.y); atomicAdd(o + 2, v.z); atomicAdd(o + 3, v.w);
                     } else {
@@ -668,7 +672,7 @@ extern "C" int deco_gemm_bf16(const void* A, long long lda, const void* W, long 
     GemmParams P;
     P.out = out; P.ldo = ldo; P.bias = bias; P.resid = (const float*)resid; P.ldr = ldr;
     P.gate = (const __nv_bfloat16*)gate; P.gate_stride = gate_stride; P.rows_per_gate = rows_per_gate > 0 ? rows_per_gate : 1;
-    P.M = M; P.N = N; P.K = K; P.split_k = 1;
+    P.M = M; P.N = N; P.K = K; P.split_k = 1; P.deint_rows = 0;
     const int ctas = num_sms();
     cudaStream_t st = (cudaStream_t)stream;
     if (bn == 256) return dispatch_variant<256>(cg, staged, epilogue, ta, tb, P, ctas, st);
@@ -718,10 +722,11 @@ static int zero_output(float* out, long long ldo, int M, int N, cudaStream_t st)
 
 // out[M, N] fp32 = At^T . Wt with At [K, M] and Wt [K, N] row-major bf16 (the wgrad contraction dW = dY^T . X on the
 // activations as they lie in memory).  M, N, lda, ldw, ldo multiples of 8.
-extern "C" int deco_gemm_bf16_tn(const void* At, long long lda, const void* Wt, long long ldw, float* out, long long ldo,
-                                 int M, int N, int K, int tile_n, int split_k, void* stream)
+static int gemm_tn_impl(const void* At, long long lda, const void* Wt, long long ldw, float* out, long long ldo,
+                       int M, int N, int K, int tile_n, int split_k, int deinterleave16, void* stream)
 {
     using namespace deco;
+    DECO_CHECK_ARG(!deinterleave16 || M % 32 == 0, "gemm_tn: de-interleaved output needs M %% 32 == 0 (M=%d)", M);
     DECO_CHECK_ARG(At && Wt && out, "gemm_tn: null pointer");
     DECO_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm_tn: bad shape M=%d N=%d K=%d", M, N, K);
     DECO_CHECK_ARG(M % 8 == 0 && N % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldo % 4 == 0,
@@ -739,7 +744,7 @@ extern "C" int deco_gemm_bf16_tn(const void* At, long long lda, const void* Wt, 
     GemmParams P;
     P.out = out; P.ldo = ldo; P.bias = nullptr; P.resid = nullptr; P.ldr = 0;
     P.gate = nullptr; P.gate_stride = 0; P.rows_per_gate = 1;
-    P.M = M; P.N = N; P.K = K;
+    P.M = M; P.N = N; P.K = K; P.deint_rows = deinterleave16 ? M / 2 : 0;
     const int ctas = num_sms();
     cudaStream_t st = (cudaStream_t)stream;
     P.split_k = legal_split_k(split_k > 0 ? split_k : auto_split_k(M, N, K, bn, cg, ctas), K);
@@ -748,6 +753,20 @@ extern "C" int deco_gemm_bf16_tn(const void* At, long long lda, const void* Wt, 
                                   : launch_gemm<256, EPI_BIAS_F32, 1, true, true>(ta, tb, P, ctas, st);
     return cg == 2 ? launch_gemm<128, EPI_BIAS_F32, 2, true, true>(ta, tb, P, ctas, st)
                    : launch_gemm<128, EPI_BIAS_F32, 1, true, true>(ta, tb, P, ctas, st);
+}
+
+extern "C" int deco_gemm_bf16_tn(const void* At, long long lda, const void* Wt, long long ldw, float* out, long long ldo,
+                                 int M, int N, int K, int tile_n, int split_k, void* stream)
+{
+    return gemm_tn_impl(At, lda, Wt, ldw, out, ldo, M, N, K, tile_n, split_k, 0, stream);
+}
+
+// deco_gemm_bf16_tn whose M output rows are the [16 x w1 | 16 x w3] interleaved rows of the SwiGLU weight: they are stored
+// de-interleaved, out = [2][M / 2][ldo] = (dW1 ; dW3), so that no copy has to pull the two gradients apart afterwards.
+extern "C" int deco_gemm_bf16_tn_deint16(const void* At, long long lda, const void* Wt, long long ldw, float* out, long long ldo,
+                                         int M, int N, int K, int tile_n, int split_k, void* stream)
+{
+    return gemm_tn_impl(At, lda, Wt, ldw, out, ldo, M, N, K, tile_n, split_k, 1, stream);
 }
 
 // out[M, N] fp32 = A . W^T (K-major operands as deco_gemm_bf16 with DECO_EPI_BIAS_F32 and no bias) with the K loop split
@@ -771,7 +790,7 @@ extern "C" int deco_gemm_bf16_f32_splitk(const void* A, long long lda, const voi
     GemmParams P;
     P.out = out; P.ldo = ldo; P.bias = nullptr; P.resid = nullptr; P.ldr = 0;
     P.gate = nullptr; P.gate_stride = 0; P.rows_per_gate = 1;
-    P.M = M; P.N = N; P.K = K;
+    P.M = M; P.N = N; P.K = K; P.deint_rows = 0;
     const int ctas = num_sms();
     cudaStream_t st = (cudaStream_t)stream;
     P.split_k = legal_split_k(split_k > 0 ? split_k : auto_split_k(M, N, K, bn, cg, ctas), K);

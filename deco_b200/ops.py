@@ -831,10 +831,11 @@ def gemm_f32_splitk(a: torch.Tensor, w: torch.Tensor, split_k: int = 0) -> torch
 
 
 def gemm_tn(at: torch.Tensor, wt: torch.Tensor, tile_n: int = 0, split_k: int = 0,
-            out: Optional[torch.Tensor] = None) -> torch.Tensor:
+            out: Optional[torch.Tensor] = None, deinterleave16: bool = False) -> torch.Tensor:
     """out [M, N] fp32 = at^T @ wt for at [K, M], wt [K, N] bf16 row-major (wgrad: dW = dY^T . X, K = tokens); no
     transposed copies -- the GEMM stages both operands MN-major.  `out` lets the caller allocate the result on another
-    stream than the one the GEMM is launched on."""
+    stream than the one the GEMM is launched on.  deinterleave16: the M rows are [16 x w1 | 16 x w3] interleaved
+    (the SwiGLU weight); out [M, N] is then written as two stacked plain matrices (dW1 ; dW3) (M % 32 == 0)."""
     _cuda(at, wt)
     assert at.dtype == bf16 and wt.dtype == bf16 and at.dim() == 2 and wt.dim() == 2
     assert at.stride(1) == 1 and wt.stride(1) == 1 and at.shape[0] == wt.shape[0]
@@ -845,8 +846,8 @@ def gemm_tn(at: torch.Tensor, wt: torch.Tensor, tile_n: int = 0, split_k: int = 
     assert out.dtype == torch.float32 and out.shape == (M, N) and out.stride(1) == 1
     probe = gemm_probe
     ev = probe.before() if probe is not None else None
-    call("deco_gemm_bf16_tn", ptr(at), at.stride(0), ptr(wt), wt.stride(0), ptr(out), out.stride(0), M, N, K, tile_n, split_k,
-         _st(at))
+    call("deco_gemm_bf16_tn_deint16" if deinterleave16 else "deco_gemm_bf16_tn", ptr(at), at.stride(0), ptr(wt), wt.stride(0),
+         ptr(out), out.stride(0), M, N, K, tile_n, split_k, _st(at))
     if probe is not None:
         probe.after(ev, 2.0 * M * N * K)
     return out

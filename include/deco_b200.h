@@ -400,6 +400,11 @@ int deco_pixel_decoder_bwd_tc(const float* x, const void* ycond_bf16, const floa
  * of 8; tile_n in {0 (auto), 128, 256}. */
 int deco_gemm_bf16_tn(const void* At, long long lda, const void* Wt, long long ldw, float* out, long long ldo,
                       int M, int N, int K, int tile_n, int split_k, void* stream);
+/* The same contraction for the SwiGLU weight gradient: the M rows of dY^T are the [16 x w1 | 16 x w3]-interleaved rows of
+ * [w1 ; w3] (dit_c2i_DeCo.py:101-113 fused into one GEMM); they are stored de-interleaved, out = [2][M / 2][ldo] = (dW1 ; dW3).
+ * M a multiple of 32. */
+int deco_gemm_bf16_tn_deint16(const void* At, long long lda, const void* Wt, long long ldw, float* out, long long ldo,
+                              int M, int N, int K, int tile_n, int split_k, void* stream);
 
 /* Split-K: when the M x N tiles alone cannot fill the GPU (small weight matrices with a long token reduction; d c = d mod .
  * Wada with M = batch), the K loop is cut into split_k slices (0 = automatic, 1 = off) that run as separate tiles and are

@@ -191,6 +191,24 @@ def test_swiglu_forward_backward(dev):
     assert rel_l2(dy.float(), yy.grad.reshape(M, 2 * Fp)) < 5e-3
 
 
+@pytest.mark.parametrize("Fp,H,T", [(48, 64, 200), (688, 144, 1024), (3072, 1152, 2048)])
+def test_wgrad_deinterleaved_rows(dev, Fp, H, T):
+    """The SwiGLU weight gradient: dY's 2 Fp columns are the interleaved [16 x w1 | 16 x w3] columns; the TN GEMM with
+    de-interleaving leaves (dW1 ; dW3) stacked (deco_gemm_bf16_tn_deint16), equal to pulling the plain result apart."""
+    from deco_b200 import ops
+    dy = torch.randn(T, 2 * Fp, device=dev, generator=_g(1)).to(bf16)
+    x = torch.randn(T, H, device=dev, generator=_g(2)).to(bf16)
+    plain = ops.gemm_tn(dy, x, split_k=1).view(Fp // 16, 2, 16, H)
+    out = torch.full((2 * Fp + 8, H), 7.0, device=dev)
+    ops.gemm_tn(dy, x, out=out[:2 * Fp], deinterleave16=True, split_k=1)
+    assert torch.equal(out[:Fp], plain[:, 0].reshape(Fp, H)) and torch.equal(out[Fp:2 * Fp], plain[:, 1].reshape(Fp, H))
+    assert bool((out[2 * Fp:] == 7.0).all())
+    ref = dy.float().t() @ x.float()
+    assert rel_l2(plain.reshape(2 * Fp, H), ref) < 2e-3
+    auto = ops.gemm_tn(dy, x, deinterleave16=True)       # automatic split-K (atomics into the zeroed stacked output)
+    assert rel_l2(auto, out[:2 * Fp]) < 1e-5
+
+
 @pytest.mark.parametrize("M,K,Fp", [(300, 144, 688), (1024, 1152, 3072), (77, 64, 48)])
 def test_swiglu_gemm_epilogues_vs_autograd(dev, M, K, Fp):
     """The training GEMMs that carry the SwiGLU passes (csrc/gemm_tcgen05.cu EPI_SWIGLU_DUAL / EPI_SWIGLU_BWD) against
