@@ -53,6 +53,7 @@ SIGNATURES = {
                                 _ll, _vp]),
     "deco_layernorm_modulate": (_i, [_vp, _vp, _vp, _ll, _i, _vp, _ll, _i, _f, _vp]),
     "deco_unpatchify": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "deco_center_rows": (_i, [_vp, _vp, _ll, _i, _vp]),
     "deco_opt_chunk_elems": (_i, []),
     "deco_adamw_ema_step": (_i, [_vp, _vp, _i, _f, _f, _f, _f, _f, _f, _f, _f, _vp]),
     "deco_dct_scratch_doubles": (_i, []),

@@ -210,26 +210,24 @@ def _colsum(x: torch.Tensor) -> torch.Tensor:
     return ops.colsum_(torch.zeros(x.shape[1], dtype=F32, device=x.device), x)
 
 
-def train_forward(module, x32, t, y):
-    """Returns (out fp32 [B,3,H,W], saved dict)."""
-    P = module.prepare(x32.device)
-    T = prepare_train(module, P, x32.device)
-    B, _, Hh, Ww = x32.shape
-    p, H, heads = module.patch_size, module.hidden_size, module.num_groups
-    d = H // heads
-    L = (Hh // p) * (Ww // p)
-    dev = x32.device
-    pos = module.fetch_pos(Hh // p, Ww // p, dev)
-    S = dict(B=B, L=L, x32=x32, y=y, pos=pos)
-    xp = ops.patchify(x32, p)
+def _cond_forward(module, P: dict, t, y, S: dict):
+    """t sinusoid -> MLP -> + label embedding -> silu -> the adaLN GEMM of every block (+ whatever rows the model appended
+    to `wada`); keeps what `_cond_backward` needs.  Returns (temb, mod)."""
     tfreq = ops.timestep_freq(t, module.t_embedder.frequency_embedding_size)
     z1 = ops.gemm(tfreq, P["wt0"], P["bt0"], ops.EPI_BIAS)
     h1t = ops.gemm(tfreq, P["wt0"], P["bt0"], ops.EPI_BIAS_SILU)
     temb = ops.gemm(h1t, P["wt2"], P["bt2"], ops.EPI_BIAS)
     c = ops.cond_combine(temb, P["ytab"], y)
     mod = ops.gemm(c, P["wada"], P["bada"], ops.EPI_BIAS)
-    s = ops.gemm(xp, P["ws"], P["bs"], ops.EPI_BIAS_F32)
-    S.update(xp=xp, tfreq=tfreq, z1=z1, h1t=h1t, temb=temb, c=c, mod=mod)
+    S.update(tfreq=tfreq, z1=z1, h1t=h1t, temb=temb, c=c, mod=mod)
+    return temb, mod
+
+
+def _blocks_forward(P: dict, mod, s, B: int, L: int, H: int, heads: int, pos):
+    """The AdaLN DiT blocks (dit_c2i_DeCo.py:194-210 == dit_c2i_baseline.py:194-210) on the fp32 stream s [B*L, H], one
+    kernel per reference op, keeping per block what the backward reads.  Returns (s_out, saved blocks)."""
+    d = H // heads
+    dev = s.device
     blocks = []
     nb = len(P["blocks"])
 
@@ -268,6 +266,24 @@ def train_forward(module, x32, t, y):
             s_out = ops.gate_residual(s_mid, a2, g2, L)
         blocks.append(dict(s_in=s, h1=h1, qkv_raw=qkv_raw, qkv=qkv, o=o, lse=lse, a1=a1, s_mid=s_mid, h2=h2, y13=y13, u=u, a2=a2))
         s, h1 = s_out, h1_next
+    return s, blocks
+
+
+def train_forward(module, x32, t, y):
+    """Returns (out fp32 [B,3,H,W], saved dict)."""
+    P = module.prepare(x32.device)
+    prepare_train(module, P, x32.device)
+    B, _, Hh, Ww = x32.shape
+    p, H, heads = module.patch_size, module.hidden_size, module.num_groups
+    L = (Hh // p) * (Ww // p)
+    dev = x32.device
+    pos = module.fetch_pos(Hh // p, Ww // p, dev)
+    S = dict(B=B, L=L, x32=x32, y=y, pos=pos)
+    xp = ops.patchify(x32, p)
+    temb, mod = _cond_forward(module, P, t, y, S)
+    s = ops.gemm(xp, P["ws"], P["bs"], ops.EPI_BIAS_F32)
+    S.update(xp=xp)
+    s, blocks = _blocks_forward(P, mod, s, B, L, H, heads, pos)
     s2 = ops.silu_add_rows(s, temb, L)
     ycond = ops.gemm(s2, P["wcond"], P["bcond"], ops.EPI_BIAS)
     R = module.num_blocks - module.num_cond_blocks
@@ -276,69 +292,20 @@ def train_forward(module, x32, t, y):
     return out, S
 
 
-def train_backward(module, S: dict, dout: torch.Tensor) -> Dict[str, torch.Tensor]:
-    """Gradients of every parameter (by name) for upstream gradient dout [B,3,H,W]."""
-    x32 = S["x32"]
-    dev = x32.device
-    P = module.prepare(dev)
-    T = P["train"]
+def _blocks_backward(module, P: dict, T: dict, S: dict, ds: torch.Tensor, dmod: torch.Tensor, G: Dict[str, torch.Tensor]) -> None:
+    """Backward of `_blocks_forward`: walks the blocks in reverse, updates the stream gradient ds [B*L, H] fp32 in place,
+    accumulates the modulation gradients into dmod[:, :nb*6H] and leaves the blocks' parameter gradients in G."""
+    dev = ds.device
     B, L = S["B"], S["L"]
-    p, H, heads = module.patch_size, module.hidden_size, module.num_groups
+    H, heads = module.hidden_size, module.num_groups
     d = H // heads
     nb = len(P["blocks"])
-    R = module.num_blocks - module.num_cond_blocks
-    C = module.in_channels
-    G: Dict[str, torch.Tensor] = {}
+    mod = S["mod"]
+    z = lambda *shape: torch.zeros(shape, dtype=F32, device=dev)   # noqa: E731
     # wgrad GEMMs of the blocks on a second stream (not under the per-GEMM event probe of the bench's roofline pass, whose
     # launch durations must not overlap other work, and not for the A/B transpose variant)
     lane = WgradLane(dev, WGRAD_STREAM and WGRAD == "tn" and ops.gemm_probe is None)
-    ready: List[List[torch.Tensor]] = []     # per finished block: its matrix gradients, announced once the lane delivered
-    z = lambda *shape: torch.zeros(shape, dtype=F32, device=dev)   # noqa: E731
-
-    # ---- pixel decoder (+ NerfEmbedder)
-    if DECODER_BWD == "scalar":     # fp32 scalar kernel (csrc/decoder_bwd.cu): the check the MMA kernel is validated against
-        dycond, gdec = ops.pixel_decoder_bwd(x32, S["ycond"], dout.to(F32).contiguous(), T["dec_blob"], P["postab"], p,
-                                             module.hidden_size_x, R)
-    else:
-        dycond, gdec = ops.pixel_decoder_bwd_tc(x32, S["ycond"], dout.to(F32).contiguous(), P["blob"], T["dec_bwd_blob"],
-                                                P["postab"], p, module.hidden_size_x, R)
-    nW = T["dec_blob"].numel()
-    dpostab = gdec[nW:].view(p * p, 32)
-    gx = z(32, C + module.x_embedder.max_freqs ** 2)
-    gx[:, :C] = gdec[0:96].view(32, 3)[:, :C]
-    gx[:, C:] = ops.gemm(ops.transpose_cast(dpostab), T["tabT"], None, ops.EPI_BIAS_F32)      # [32, 64]
-    G["x_embedder.embedder.0.weight"] = gx
-    G["x_embedder.embedder.0.bias"] = _colsum(dpostab)
-    G["dec_net.input_proj.weight"] = gdec[96:1120].view(32, 32)
-    G["dec_net.input_proj.bias"] = gdec[1120:1152]
-    for j in range(R):
-        o0 = 1152 + j * 5344
-        pre = f"dec_net.res_blocks.{j}."
-        G[pre + "adaLN_modulation.1.weight"] = gdec[o0:o0 + 3072].view(96, 32)
-        G[pre + "adaLN_modulation.1.bias"] = gdec[o0 + 3072:o0 + 3168]
-        G[pre + "in_ln.weight"] = gdec[o0 + 3168:o0 + 3200]
-        G[pre + "in_ln.bias"] = gdec[o0 + 3200:o0 + 3232]
-        G[pre + "mlp.0.weight"] = gdec[o0 + 3232:o0 + 4256].view(32, 32)
-        G[pre + "mlp.0.bias"] = gdec[o0 + 4256:o0 + 4288]
-        G[pre + "mlp.2.weight"] = gdec[o0 + 4288:o0 + 5312].view(32, 32)
-        G[pre + "mlp.2.bias"] = gdec[o0 + 5312:o0 + 5344]
-    of = 1152 + R * 5344
-    G["dec_net.final_layer.linear.weight"] = gdec[of:of + 128].view(4, 32)[:C]
-    G["dec_net.final_layer.linear.bias"] = gdec[of + 128:of + 128 + C]
-
-    # ---- cond_embed: ycond = s2 . wcond^T + bcond
-    G["dec_net.cond_embed.weight"] = _wgrad(dycond, S["s2"])
-    G["dec_net.cond_embed.bias"] = _colsum(dycond)
-    ds2 = ops.gemm(dycond, T["wcondT"], None, ops.EPI_BIAS)
-    del dycond
-    # ---- s2 = silu(s + temb)
-    dtemb = z(B, H)
-    ds = ops.silu_add_rows_bwd(ds2, S["s_final"], S["temb"], dtemb, L)
-    del ds2
-
-    # ---- DiT blocks
-    dmod = z(B, nb * 6 * H)
-    mod = S["mod"]
+    ready: List[tuple] = []     # per finished block: its matrix gradients, announced once the lane delivered
     zblk = z(max(nb, 1), 3 * H + 2 * d)       # one fill for the per-block vector gradients (norm1/2, proj bias, q/k-norm)
     da2 = None
     for i in reversed(range(nb)):
@@ -412,16 +379,26 @@ def train_backward(module, S: dict, dout: torch.Tensor) -> Dict[str, torch.Tenso
             _grads_ready([G[prej + k] for k in ("mlp.w2.weight", "mlp.w1.weight", "mlp.w3.weight", "attn.proj.weight",
                                                 "attn.qkv.weight")])
 
-    # ---- s_embedder: s0 = xp . ws^T + bs
-    G["s_embedder.proj.weight"] = _wgrad(ds, S["xp"])
-    G["s_embedder.proj.bias"] = _colsum(ds)
+
+
+def _cond_backward(module, P: dict, T: dict, S: dict, dmod, dtemb, G: Dict[str, torch.Tensor], ada_names: List[str],
+                   ada_rows: int, extra_ada: tuple = ()) -> None:
+    """Backward of `_cond_forward`: the adaLN GEMM (rows of `wada`: `ada_rows` per name in `ada_names`, then the
+    (name, rows) pairs of `extra_ada`), c = silu(temb + table[y]), the timestep MLP.  dtemb [B, H] fp32 holds whatever the
+    rest of the model already sent to temb."""
+    B = S["B"]
+    H = module.hidden_size
+    nb = len(ada_names)
+    dev = dmod.device
+    z = lambda *shape: torch.zeros(shape, dtype=F32, device=dev)   # noqa: E731
     # ---- adaLN of all blocks: mod = c . wada^T + bada
-    if nb:
+    if dmod.shape[1]:
         dwada = _wgrad(dmod, S["c"])                            # [nb*6H, H]
         dbada = _colsum(dmod)
-        for i in range(nb):
-            G[f"blocks.{i}.adaLN_modulation.0.weight"] = dwada[i * 6 * H:(i + 1) * 6 * H]
-            G[f"blocks.{i}.adaLN_modulation.0.bias"] = dbada[i * 6 * H:(i + 1) * 6 * H]
+        r0 = 0
+        for name, rows in [(n, ada_rows) for n in ada_names] + list(extra_ada):
+            G[name + ".weight"], G[name + ".bias"] = dwada[r0:r0 + rows], dbada[r0:r0 + rows]
+            r0 += rows
         dc = ops.gemm_f32_splitk(ops.cast_bf16(dmod), T["wadaT"])          # M = batch, K = nb*6H: split-K
     else:
         dc = z(B, H)
@@ -436,17 +413,160 @@ def train_backward(module, S: dict, dout: torch.Tensor) -> Dict[str, torch.Tenso
     dz1 = ops.silu_bwd(S["z1"], dh1t)
     G["t_embedder.mlp.0.weight"] = _wgrad(dz1, S["tfreq"])
     G["t_embedder.mlp.0.bias"] = _colsum(dz1)
+
+
+def train_backward(module, S: dict, dout: torch.Tensor) -> Dict[str, torch.Tensor]:
+    """Gradients of every parameter (by name) for upstream gradient dout [B,3,H,W]."""
+    x32 = S["x32"]
+    dev = x32.device
+    P = module.prepare(dev)
+    T = P["train"]
+    B, L = S["B"], S["L"]
+    p, H, heads = module.patch_size, module.hidden_size, module.num_groups
+    d = H // heads
+    nb = len(P["blocks"])
+    R = module.num_blocks - module.num_cond_blocks
+    C = module.in_channels
+    G: Dict[str, torch.Tensor] = {}
+    z = lambda *shape: torch.zeros(shape, dtype=F32, device=dev)   # noqa: E731
+
+    # ---- pixel decoder (+ NerfEmbedder)
+    if DECODER_BWD == "scalar":     # fp32 scalar kernel (csrc/decoder_bwd.cu): the check the MMA kernel is validated against
+        dycond, gdec = ops.pixel_decoder_bwd(x32, S["ycond"], dout.to(F32).contiguous(), T["dec_blob"], P["postab"], p,
+                                             module.hidden_size_x, R)
+    else:
+        dycond, gdec = ops.pixel_decoder_bwd_tc(x32, S["ycond"], dout.to(F32).contiguous(), P["blob"], T["dec_bwd_blob"],
+                                                P["postab"], p, module.hidden_size_x, R)
+    nW = T["dec_blob"].numel()
+    dpostab = gdec[nW:].view(p * p, 32)
+    gx = z(32, C + module.x_embedder.max_freqs ** 2)
+    gx[:, :C] = gdec[0:96].view(32, 3)[:, :C]
+    gx[:, C:] = ops.gemm(ops.transpose_cast(dpostab), T["tabT"], None, ops.EPI_BIAS_F32)      # [32, 64]
+    G["x_embedder.embedder.0.weight"] = gx
+    G["x_embedder.embedder.0.bias"] = _colsum(dpostab)
+    G["dec_net.input_proj.weight"] = gdec[96:1120].view(32, 32)
+    G["dec_net.input_proj.bias"] = gdec[1120:1152]
+    for j in range(R):
+        o0 = 1152 + j * 5344
+        pre = f"dec_net.res_blocks.{j}."
+        G[pre + "adaLN_modulation.1.weight"] = gdec[o0:o0 + 3072].view(96, 32)
+        G[pre + "adaLN_modulation.1.bias"] = gdec[o0 + 3072:o0 + 3168]
+        G[pre + "in_ln.weight"] = gdec[o0 + 3168:o0 + 3200]
+        G[pre + "in_ln.bias"] = gdec[o0 + 3200:o0 + 3232]
+        G[pre + "mlp.0.weight"] = gdec[o0 + 3232:o0 + 4256].view(32, 32)
+        G[pre + "mlp.0.bias"] = gdec[o0 + 4256:o0 + 4288]
+        G[pre + "mlp.2.weight"] = gdec[o0 + 4288:o0 + 5312].view(32, 32)
+        G[pre + "mlp.2.bias"] = gdec[o0 + 5312:o0 + 5344]
+    of = 1152 + R * 5344
+    G["dec_net.final_layer.linear.weight"] = gdec[of:of + 128].view(4, 32)[:C]
+    G["dec_net.final_layer.linear.bias"] = gdec[of + 128:of + 128 + C]
+
+    # ---- cond_embed: ycond = s2 . wcond^T + bcond
+    G["dec_net.cond_embed.weight"] = _wgrad(dycond, S["s2"])
+    G["dec_net.cond_embed.bias"] = _colsum(dycond)
+    ds2 = ops.gemm(dycond, T["wcondT"], None, ops.EPI_BIAS)
+    del dycond
+    # ---- s2 = silu(s + temb)
+    dtemb = z(B, H)
+    ds = ops.silu_add_rows_bwd(ds2, S["s_final"], S["temb"], dtemb, L)
+    del ds2
+
+    # ---- DiT blocks
+    dmod = z(B, nb * 6 * H)
+    _blocks_backward(module, P, T, S, ds, dmod, G)
+    # ---- s_embedder: s0 = xp . ws^T + bs
+    G["s_embedder.proj.weight"] = _wgrad(ds, S["xp"])
+    G["s_embedder.proj.bias"] = _colsum(ds)
+    _cond_backward(module, P, T, S, dmod, dtemb, G, [f"blocks.{i}.adaLN_modulation.0" for i in range(nb)], 6 * H)
     _grads_ready(list(G.values()))      # the tail: everything not announced yet (the hook skips what it has seen)
     return G
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# Patch-linear baseline (`FlattenDiT`, dit_c2i_baseline.py:357-379): the same blocks between a patch-embedding head and the
+# AdaLN FinalLayer (:70-83) + Linear + fold tail.
+@torch.no_grad()
+def prepare_train_baseline(module, P: dict, device) -> dict:
+    if "train" in P:
+        return P["train"]
+
+    def tr(w):
+        return ops.transpose_cast(w, rows_pad=w.shape[0])
+
+    T = dict(wt2T=tr(P["wt2"]), wadaT=tr(P["wada"]), wfinT=tr(P["wfin"]))
+    T["blocks"] = [dict(wqkvT=tr(bp["wqkv"]), wprojT=tr(bp["wproj"]), w13T=tr(bp["w13"]), w2T=tr(bp["w2"]))
+                   for bp in P["blocks"]]
+    T["ones"] = torch.ones(module.hidden_size, dtype=F32, device=device)
+    P["train"] = T
+    return T
+
+
+def baseline_train_forward(module, x32, t, y):
+    """Returns (out bf16 [B,C,H,W] -- the reference's dtype under autocast --, saved dict)."""
+    dev = x32.device
+    P = module.prepare(dev)
+    T = prepare_train_baseline(module, P, dev)
+    B, Cc, Hh, Ww = x32.shape
+    p, H, heads = module.patch_size, module.hidden_size, module.num_groups
+    L = (Hh // p) * (Ww // p)
+    nb = len(P["blocks"])
+    pos = module.fetch_pos(Hh // p, Ww // p, dev)
+    S = dict(B=B, L=L, y=y, pos=pos, shape=(B, Cc, Hh, Ww))
+    xp = ops.patchify(x32, p)
+    _, mod = _cond_forward(module, P, t, y, S)
+    s = ops.gemm(xp, P["wx"], P["bx"], ops.EPI_BIAS_F32)
+    s, blocks = _blocks_forward(P, mod, s, B, L, H, heads, pos)
+    # FinalLayer: LayerNorm (no affine) = RMSNorm of the centred row, then modulate with the last 2H adaLN columns
+    shift, scale = mod[:, nb * 6 * H:nb * 6 * H + H], mod[:, nb * 6 * H + H:]
+    xc = ops.center_rows(s)
+    hf = ops.rmsnorm_modulate(xc, T["ones"], shift, scale, L)
+    tok = ops.gemm(hf, P["wfin"], P["bfin"], ops.EPI_BIAS)
+    out = ops.unpatchify(tok, B, Cc, Hh, Ww, p)
+    S.update(xp=xp, blocks=blocks, xc=xc, hf=hf)
+    return out, S
+
+
+def baseline_train_backward(module, S: dict, dout: torch.Tensor) -> Dict[str, torch.Tensor]:
+    dev = dout.device
+    P = module.prepare(dev)
+    T = P["train"]
+    B, L = S["B"], S["L"]
+    p, H = module.patch_size, module.hidden_size
+    nb = len(P["blocks"])
+    G: Dict[str, torch.Tensor] = {}
+    z = lambda *shape: torch.zeros(shape, dtype=F32, device=dev)   # noqa: E731
+    # ---- fold^T = unfold, then tok = hf . wfin^T + bfin
+    dtok = ops.patchify(dout.to(F32).contiguous(), p)
+    G["final_layer.linear.weight"] = _wgrad(dtok, S["hf"])
+    G["final_layer.linear.bias"] = _colsum(dtok)
+    dhf = ops.gemm(dtok, T["wfinT"], None, ops.EPI_BIAS)
+    # ---- hf = rmsnorm(xc) (1 + scale) + shift ; xc = s - mean(s)
+    dmod = z(B, nb * 6 * H + 2 * H)
+    scale = S["mod"][:, nb * 6 * H + H:]
+    ds = z(B * L, H)
+    ops.rmsnorm_modulate_bwd_(ds, dhf, S["xc"], T["ones"], scale, z(H), dmod[:, nb * 6 * H:nb * 6 * H + H],
+                              dmod[:, nb * 6 * H + H:], L)
+    ops.center_rows(ds, out=ds)
+    del dtok, dhf
+    S["xc"] = S["hf"] = None
+    _blocks_backward(module, P, T, S, ds, dmod, G)
+    G["x_embedder.proj.weight"] = _wgrad(ds, S["xp"])
+    G["x_embedder.proj.bias"] = _colsum(ds)
+    _cond_backward(module, P, T, S, dmod, z(B, H), G, [f"blocks.{i}.adaLN_modulation.0" for i in range(nb)], 6 * H,
+                   extra_ada=(("final_layer.adaLN_modulation.0", 2 * H),))
+    _grads_ready(list(G.values()))
+    return G
+
+
 class DenoiserFn(torch.autograd.Function):
-    """out = PixNerDiT(x, t, y) as one autograd node; *params only tell autograd which leaves receive gradients."""
+    """out = net(x, t, y) as one autograd node (PixNerDiT, or the patch-linear FlattenDiT); *params only tell autograd
+    which leaves receive gradients."""
 
     @staticmethod
     def forward(ctx, module, names: List[str], x, t, y, *params):
         x32 = x.detach().to(F32).contiguous()
-        out, S = train_forward(module, x32, t.detach().reshape(-1).to(F32), y.detach().reshape(-1))
+        fwd = baseline_train_forward if hasattr(module, "final_layer") else train_forward
+        out, S = fwd(module, x32, t.detach().reshape(-1).to(F32), y.detach().reshape(-1))
         ctx.module, ctx.names, ctx.S = module, names, S
         ctx.meta = [(p.requires_grad, p.shape, p.dtype) for p in params]
         return out
@@ -455,7 +575,8 @@ class DenoiserFn(torch.autograd.Function):
     def backward(ctx, dout):
         if ctx.S is None:
             raise RuntimeError("deco_b200 denoiser: backward called twice (activations are released after one pass)")
-        G = train_backward(ctx.module, ctx.S, dout)
+        bwd = baseline_train_backward if hasattr(ctx.module, "final_layer") else train_backward
+        G = bwd(ctx.module, ctx.S, dout)
         ctx.S = None
         # an overlapped gradient averager reduces G's buffers in place on another stream: order this stream behind it
         # before autograd reads (or clones) them

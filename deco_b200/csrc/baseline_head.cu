@@ -66,6 +66,33 @@ __global__ void __launch_bounds__(256) layernorm_modulate_kernel(
     }
 }
 
+// out = x - mean(x) per row (fp32, may run in place): LayerNorm without affine is RMSNorm of the centred row, so the
+// TRAINING path of the final layer is centre -> rmsnorm_modulate (unit weight), and its backward is rmsnorm_modulate_bwd ->
+// centre (the projection is symmetric).  One warp per row, the row kept in registers.
+template <int kMaxChunks>
+__global__ void __launch_bounds__(256) center_rows_kernel(const float* x, float* out, long long M, int Hd)
+{
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const int nch = Hd >> 2;
+    const float4* xr = reinterpret_cast<const float4*>(x + row * Hd);
+    float4 v[kMaxChunks];
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < kMaxChunks; ++j) {
+        const int ch = lane + j * 32;
+        if (ch < nch) { v[j] = xr[ch]; sum += (v[j].x + v[j].y) + (v[j].z + v[j].w); }
+    }
+    const float mean = warp_sum(sum) / (float)Hd;
+    float4* orow = reinterpret_cast<float4*>(out + row * Hd);
+#pragma unroll
+    for (int j = 0; j < kMaxChunks; ++j) {
+        const int ch = lane + j * 32;
+        if (ch < nch) orow[ch] = make_float4(v[j].x - mean, v[j].y - mean, v[j].z - mean, v[j].w - mean);
+    }
+}
+
 // out[b][c][py*p+ky][px*p+kx] = tok[(b*L + py*Wp + px)][c*p*p + ky*p + kx]; p % 8 == 0.  Thread i owns output chunk i (8
 // pixels of one image row): stores are fully coalesced, loads are 32-byte runs (p = 16) of a token row.
 __global__ void __launch_bounds__(256) unpatchify_kernel(const __nv_bfloat16* __restrict__ tok, __nv_bfloat16* __restrict__ out,
@@ -108,6 +135,17 @@ extern "C" int deco_layernorm_modulate(const float* x, const void* shift_bf16, c
         layernorm_modulate_kernel<8><<<grid, warps * 32, 0, st>>>(x, sh, sc, mod_row_stride, rows_per_mod,
                                                                   (__nv_bfloat16*)out_bf16, M, hidden, eps);
     DECO_CHECK_LAUNCH("layernorm_modulate_kernel");
+    return DECO_OK;
+}
+
+extern "C" int deco_center_rows(const float* x, float* out, long long M, int hidden, void* stream) {
+    using namespace deco;
+    DECO_CHECK_ARG(x && out && M > 0 && hidden > 0 && hidden % 4 == 0 && hidden <= 2048, "center_rows: unsupported M=%lld hidden=%d", M, hidden);
+    const int warps = 8;
+    const unsigned grid = (unsigned)((M + warps - 1) / warps);
+    if (hidden <= 1280) center_rows_kernel<10><<<grid, warps * 32, 0, (cudaStream_t)stream>>>(x, out, M, hidden);
+    else center_rows_kernel<16><<<grid, warps * 32, 0, (cudaStream_t)stream>>>(x, out, M, hidden);
+    DECO_CHECK_LAUNCH("center_rows_kernel");
     return DECO_OK;
 }
 

@@ -10,7 +10,9 @@ Linear(H -> C p^2) per patch, folded back to the image (:376-378).
 Per forward:  patchify -> [x_embedder GEMM -> blocks] (fused stream) ; t sinusoid -> 2 GEMMs -> cond_combine -> ONE adaLN
 GEMM for all blocks + the final layer -> layernorm_modulate -> final GEMM (+bias) -> unpatchify.
 With `EulerSamplerJiT` (sampling.py:109-188) the output is an x-prediction that the sampler's update kernel turns into a
-velocity.  Inference only: there is no hand-written backward for this head.
+velocity.  In `.train()` mode with grad enabled the forward is one autograd node with a hand-written backward
+(`deco_b200.autograd.baseline_train_forward / _backward`: the DeCo denoiser's block backward between the patch-embedding
+head and the FinalLayer / fold tail).
 """
 from __future__ import annotations
 
@@ -125,9 +127,14 @@ class FlattenDiT(nn.Module):
             raise NotImplementedError("attention masks are not supported (every config passes masks=None)")
         if not x.is_cuda:
             raise RuntimeError("deco_b200.FlattenDiT runs on CUDA (sm_100a) only; there is no CPU fallback")
-        if torch.is_grad_enabled() and (x.requires_grad or (self.training and any(p.requires_grad for p in self.parameters()))):
-            raise NotImplementedError("FlattenDiT is inference-only here (no hand-written backward for the patch-linear "
-                                      "head); call it under torch.no_grad() / .eval()")
+        if torch.is_grad_enabled() and x.requires_grad:
+            raise NotImplementedError("the denoiser backward yields parameter gradients only (the reference never "
+                                      "differentiates w.r.t. x_t); detach x")
+        if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
+            # training step (net(x_t, t, y) + loss.backward()): one autograd node with a hand-written backward -- the DiT
+            # blocks of deco_b200.autograd, the FinalLayer / fold tail next to them
+            from .autograd import denoiser_train_apply
+            return denoiser_train_apply(self, x, t, y), None
         B, Cc, Hh, Ww = x.shape
         p, H, heads = self.patch_size, self.hidden_size, self.num_groups
         assert Cc == self.in_channels and Hh % p == 0 and Ww % p == 0
@@ -162,6 +169,8 @@ class FlattenDiT(nn.Module):
     def forward_sx(self, x, t, y, masks=None):
         """dit_c2i_baseline.py:381-401: also returns the last block's stream as [B, H, sqrt(L), sqrt(L)]."""
         out, s = self._forward_impl(x, t, y, masks)
+        if s is None:
+            raise NotImplementedError("forward_sx is an inference entry point; the training path returns the output only")
         B, L, H = s.shape
         r = int(math.sqrt(L))
         return out, s.to(bf16).reshape(B, r, r, H).permute(0, 3, 1, 2)

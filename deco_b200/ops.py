@@ -493,6 +493,17 @@ def layernorm_modulate(x: torch.Tensor, shift: torch.Tensor, scale: torch.Tensor
     return out
 
 
+def center_rows(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = x - x.mean(1, keepdim=True) for the fp32 stream x [M, H] (out may be x)."""
+    _cuda(x, out)
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 2
+    if out is None:
+        out = torch.empty_like(x)
+    assert out.dtype == torch.float32 and out.is_contiguous() and out.shape == x.shape
+    call("deco_center_rows", ptr(x), ptr(out), x.shape[0], x.shape[1], _st(x))
+    return out
+
+
 def unpatchify(tok: torch.Tensor, B: int, C: int, H: int, W: int, p: int) -> torch.Tensor:
     """F.fold(kernel = stride = p) of bf16 tokens [B*L, C*p*p] -> [B, C, H, W] (dit_c2i_baseline.py:378)."""
     _cuda(tok)

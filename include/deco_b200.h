@@ -274,6 +274,9 @@ int deco_cfg_step_ex(const float* x, const void* net_out, int net_is_bf16,
 int deco_layernorm_modulate(const float* x, const void* shift_bf16, const void* scale_bf16, long long mod_row_stride,
                             int rows_per_mod, void* out_bf16, long long M, int hidden, float eps, void* stream);
 int deco_unpatchify(const void* tok_bf16, void* out_bf16, int B, int C, int H, int W, int p, void* stream);
+/* out = x - rowmean(x), fp32 [M, hidden], in place allowed: LayerNorm(no affine) = RMSNorm of the centred row, which is how the
+ * TRAINING path of the final layer (:76-82) reuses deco_rmsnorm_modulate and its backward (centre, norm; norm', centre). */
+int deco_center_rows(const float* x, float* out, long long M, int hidden, void* stream);
 
 /* Frequency-aware FM loss, forward and/or backward in one pass
  * (flow_matching/training_repa_DeCo.py:106-136 _rgb2ycbcr/_dct, :138-195 weights, :273-285 loss):

@@ -29,7 +29,7 @@ print(f"total {tot:.3f} ms over {sum(n for n, _ in agg.values())} launches")
 for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print(f"{t:9.3f} ms {100 * t / tot:5.1f}%  n={n:4d} avg={t / n:8.4f} ms  {k[:110]}")
 PY
-{ echo "# ncu launch list of one training step (round 2, eager launches: DECO_B200_GRAPH=0): python bench.py --workload train256 --steps 1 --warmup 2 --no-e2e --no-cpu-baseline --torch-baseline none --profile"; python $P/agg_launches.py $G/launches_train_r2.csv; } > $P/launches_r2_train256.txt
+{ echo "# ncu launch list of one training step (round 2, eager launches on ONE stream: DECO_B200_GRAPH=0 DECO_B200_WGRAD_STREAM=0): python bench.py --workload train256 --steps 1 --warmup 2 --no-e2e --no-cpu-baseline --torch-baseline none --profile"; python $P/agg_launches.py $G/launches_train_r2.csv; } > $P/launches_r2_train256.txt
 for n in decoder_tc attention gemm_qkv gemm_proj; do
   [ -f $G/full_r2_${n}_raw.csv ] && { echo "# ncu --set full --clock-control none --import-source on, one launch of the sampling step (round 2); profiles/summarize_full.py"; python $P/summarize_full.py $G/full_r2_${n}_raw.csv; } > $P/full_r2_$n.txt
 done

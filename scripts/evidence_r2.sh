@@ -19,8 +19,9 @@ if [[ $WHAT == *launches* ]]; then
   ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --profile-from-start off -c 400 --csv \
       --log-file $O/traffic_r2.csv $P > $O/ncu_traffic_r2.log 2>&1; echo "launch list + traffic rc=$?"
   PT="python bench.py --workload train256 --steps 1 --warmup 2 --no-e2e --no-cpu-baseline --torch-baseline none --profile"
-  DECO_B200_GRAPH=0 $PT > $O/plain_train_r2.log 2>&1 &&
-  DECO_B200_GRAPH=0 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 3000 --csv \
+  # one stream (DECO_B200_WGRAD_STREAM=0) so that every launch is timed alone
+  DECO_B200_GRAPH=0 DECO_B200_WGRAD_STREAM=0 $PT > $O/plain_train_r2.log 2>&1 &&
+  DECO_B200_GRAPH=0 DECO_B200_WGRAD_STREAM=0 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 3000 --csv \
       --log-file $O/launches_train_r2.csv $PT > $O/ncu_launches_train_r2.log 2>&1; echo "train launch list rc=$?"
 fi
 if [[ $WHAT == *full* ]]; then

@@ -521,6 +521,49 @@ def test_wgrad_side_stream_matches_single_stream(dev, monkeypatch):
     same(static, g0)
 
 
+@pytest.mark.parametrize("hidden,groups,blocks,res,B", [(288, 4, 4, 64, 3), (256, 4, 3, 128, 2)])
+def test_baseline_training_step_gradients(dev, hidden, groups, blocks, res, B):
+    """Patch-linear baseline (FlattenDiT, dit_c2i_baseline.py:357-379) in .train() mode: parameter gradients of the
+    hand-written backward (shared DiT blocks + FinalLayer / fold tail) against autograd over the fp32 oracle."""
+    from helpers import build_baseline_module
+    cfg = O.BaselineCfg(in_channels=3, num_groups=groups, hidden_size=hidden, num_blocks=blocks, patch_size=16, num_classes=10)
+    m, P = build_baseline_module(cfg, dev)
+    m.train()
+    x = torch.tanh(torch.randn(B, 3, res, res, device=dev, generator=_g(31)))
+    t = torch.rand(B, device=dev, generator=_g(32))
+    y = torch.randint(0, cfg.num_classes + 1, (B,), device=dev, generator=_g(33))
+    w = torch.randn(B, 3, res, res, device=dev, generator=_g(34))
+    out = m(x, t, y)
+    assert out.requires_grad
+    (out.float() * w).sum().backward()
+    Pr = {k: v.to(dev).clone().requires_grad_(True) for k, v in P.items()}
+    ref = O.baseline_forward(Pr, cfg, x, t, y)
+    (ref * w).sum().backward()
+    assert rel_l2(out.float(), ref) < 1e-2
+    worst, num, den = [], 0.0, 0.0
+    for name, prm in m.named_parameters():
+        assert prm.grad is not None, name
+        g, gr = prm.grad.double(), Pr[name].grad.double()
+        num += float((g - gr).pow(2).sum())
+        den += float(gr.pow(2).sum())
+        worst.append((rel_l2(g, gr), name))
+    worst.sort(reverse=True)
+    print("baseline global grad rel-L2 %.3e; worst tensors: %s" % (math.sqrt(num / den), worst[:6]))
+    assert math.sqrt(num / den) < 2e-2, worst[:6]
+    assert not [(e, n) for e, n in worst if e > 6e-2], worst[:6]
+
+
+def test_center_rows_kernel(dev):
+    from deco_b200 import ops
+    for M, H in ((70, 144), (513, 1152), (9, 2048)):
+        x = torch.randn(M, H, device=dev, generator=_g(M)) + 3.0
+        ref = x - x.mean(1, keepdim=True)
+        assert (ops.center_rows(x) - ref).abs().max() < 1e-5
+        y = x.clone()
+        ops.center_rows(y, out=y)
+        assert (y - ref).abs().max() < 1e-5
+
+
 def test_optimizer_step_invalidates_weight_cache(dev):
     """prepare() keys on parameter versions: after an optimizer step the next forward must see the new weights."""
     cfg = O.DenoiserCfg(num_groups=2, hidden_size=144, num_blocks=4, num_cond_blocks=1, num_classes=10)

@@ -48,8 +48,9 @@ def test_baseline_forward_vs_reference_golden(cuda_dev):
     assert rel_l2(O.baseline_forward(Pd, cfg, x, t, y), ref) < 1e-4
     out2, s_out = m.forward_sx(x, t, y)
     assert torch.equal(out2, out) and s_out.shape == (x.shape[0], cfg.hidden_size, 4, 4)
-    with pytest.raises(NotImplementedError):
-        m.train()(x, t, y)
+    with pytest.raises(NotImplementedError):     # parameter gradients only (tests/test_gpu_backward.py covers .train())
+        m.train()(x.clone().requires_grad_(True), t, y)
+    m.eval()
 
 
 def test_baseline_jit_config_shape_vs_oracle(cuda_dev):
