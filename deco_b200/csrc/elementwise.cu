@@ -202,49 +202,65 @@ __global__ void __launch_bounds__(256) gate_residual_norm_kernel(
 
 // ---------------------------------------------------------------- per-head RMSNorm + 2-D RoPE, in place
 // buf: [M, row_stride]; segment 0 starts at column col0 (weights qw), optional segment 1 at col1 (weights kw); each
-// segment is heads x D.  One thread per (token, segment, head) vector of D elements.
-// rope: [L, D/2] float2 (cos, sin) or NULL (norm only -- the t2i text keys); token position = row % L.
+// segment is heads x D.  rope: [L, D/2] float2 (cos, sin) or NULL (norm only -- the t2i text keys); token position = row % L.
+// G lanes share one (token, segment, head) vector (3 x 24 elements for D = 72, 4 x 16 for D = 64): a lane holds its 16-byte
+// chunks packed, the row's sum of squares is a G-lane shuffle reduction.  (The first version gave a thread the whole vector
+// in 72 fp32 registers: 0.53-0.57 of the HBM peak; with 3-4x the warps in flight the same traffic hides its latency.)
 template <int D>
-__global__ void __launch_bounds__(128) qknorm_rope_kernel(const __nv_bfloat16* src, __nv_bfloat16* qkv, long long row_stride,
+__global__ void __launch_bounds__(256) qknorm_rope_kernel(const __nv_bfloat16* src, __nv_bfloat16* qkv, long long row_stride,
                                                           int nseg, int col0, int col1, const float* __restrict__ qw,
                                                           const float* __restrict__ kw, const float2* __restrict__ rope,
                                                           long long M, int heads, int L, float eps)
 {
-    const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    constexpr int G = (D == 72) ? 3 : 4;
+    constexpr int CPL = D / 8 / G;            // 16-byte chunks per lane
+    constexpr int VPW = 32 / G;               // vectors per warp (D = 72: lanes 30, 31 idle)
+    static_assert(D % (8 * G) == 0, "head_dim must split into 16-byte chunks per lane");
+    __shared__ __align__(16) float sw[2][D];
+    for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) sw[i / D][i % D] = (i < D) ? qw[i] : (nseg > 1 ? kw[i - D] : 0.f);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int grp = lane / G, sub = lane % G, base = grp * G;
     const int per_tok = nseg * heads;
-    if (item >= M * per_tok) return;
-    const long long tok = item / per_tok;
-    const int r = (int)(item % per_tok);
+    const long long total = M * per_tok;
+    const long long item = ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * VPW + grp;
+    const bool live = grp < VPW && item < total;
+    const long long tok = live ? item / per_tok : 0;
+    const int r = live ? (int)(item % per_tok) : 0;
     const int is_k = r / heads, head = r % heads;
     const long long off = tok * row_stride + (is_k ? col1 : col0) + (long long)head * D;
-    __nv_bfloat16* p = qkv + off;
-    const __nv_bfloat16* sp = src + off;            // src == qkv: in place
-    const float* wv = is_k ? kw : qw;
     const float2* rp = rope ? rope + (long long)(tok % L) * (D / 2) : nullptr;
-    float v[D];
+    uint4 rq[CPL];
     float ss = 0.f;
 #pragma unroll
-    for (int c = 0; c < D / 8; ++c) {
-        const uint4 q = *reinterpret_cast<const uint4*>(sp + c * 8);
-        const float2 a = unpack_bf2(q.x), b = unpack_bf2(q.y), cc = unpack_bf2(q.z), d = unpack_bf2(q.w);
-        v[c * 8 + 0] = a.x; v[c * 8 + 1] = a.y; v[c * 8 + 2] = b.x; v[c * 8 + 3] = b.y;
-        v[c * 8 + 4] = cc.x; v[c * 8 + 5] = cc.y; v[c * 8 + 6] = d.x; v[c * 8 + 7] = d.y;
+    for (int k = 0; k < CPL; ++k) {
+        rq[k] = live ? *reinterpret_cast<const uint4*>(src + off + (sub + G * k) * 8) : make_uint4(0u, 0u, 0u, 0u);   // src == qkv: in place
+        const uint32_t w4[4] = {rq[k].x, rq[k].y, rq[k].z, rq[k].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { const float2 a = unpack_bf2(w4[e]); ss = fmaf(a.x, a.x, fmaf(a.y, a.y, ss)); }
     }
+    float tot = 0.f;
 #pragma unroll
-    for (int e = 0; e < D; ++e) ss = fmaf(v[e], v[e], ss);
-    const float rs = rsqrtf(ss / (float)D + eps);
+    for (int j = 0; j < G; ++j) tot += __shfl_sync(0xffffffffu, ss, (base + j) & 31);
+    const float rs = rsqrtf(tot / (float)D + eps);
+    if (!live) return;
 #pragma unroll
-    for (int c = 0; c < D / 8; ++c) {
+    for (int k = 0; k < CPL; ++k) {
+        const int ch = sub + G * k;
+        const uint32_t w4[4] = {rq[k].x, rq[k].y, rq[k].z, rq[k].w};
+        float4 t01 = make_float4(1.f, 0.f, 1.f, 0.f), t23 = t01;
+        if (rp) { t01 = __ldg(reinterpret_cast<const float4*>(rp + ch * 4)); t23 = __ldg(reinterpret_cast<const float4*>(rp + ch * 4 + 2)); }
+        const float4 w03 = *reinterpret_cast<const float4*>(&sw[is_k][ch * 8]), w47 = *reinterpret_cast<const float4*>(&sw[is_k][ch * 8 + 4]);
+        const float cc[4] = {t01.x, t01.z, t23.x, t23.z}, sn[4] = {t01.y, t01.w, t23.y, t23.w};
+        const float ww[8] = {w03.x, w03.y, w03.z, w03.w, w47.x, w47.y, w47.z, w47.w};
         uint32_t o[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            const int j = c * 4 + e;   // pair index
-            const float a = __ldg(wv + 2 * j) * round_bf(v[2 * j] * rs);
-            const float b = __ldg(wv + 2 * j + 1) * round_bf(v[2 * j + 1] * rs);
-            const float2 cs = rp ? __ldg(rp + j) : make_float2(1.f, 0.f);
-            o[e] = pack_bf2(a * cs.x - b * cs.y, a * cs.y + b * cs.x);
+            const float2 v = unpack_bf2(w4[e]);
+            const float a = ww[2 * e] * round_bf(v.x * rs), b = ww[2 * e + 1] * round_bf(v.y * rs);
+            o[e] = pack_bf2(a * cc[e] - b * sn[e], a * sn[e] + b * cc[e]);
         }
-        *reinterpret_cast<uint4*>(p + c * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<uint4*>(qkv + off + ch * 8) = make_uint4(o[0], o[1], o[2], o[3]);
     }
 }
 
@@ -425,13 +441,15 @@ static int headnorm_rope_launch(const void* src_bf16, void* buf_bf16, long long 
     DECO_CHECK_ARG(M > 0 && heads > 0 && L > 0 && row_stride % 8 == 0 && col0 % 8 == 0 && col1 % 8 == 0 && col0 >= 0 && col1 >= 0,
                    "headnorm_rope: bad shape");
     const long long items = M * nseg * heads;
-    const unsigned grid = (unsigned)((items + 127) / 128);
+    const int vpb = 8 * (32 / (head_dim == 72 ? 3 : 4));       // vectors per 256-thread block
+    const unsigned grid = (unsigned)((items + vpb - 1) / vpb);
+    DECO_CHECK_ARG(!rope_cos_sin || ((uintptr_t)rope_cos_sin & 15) == 0, "headnorm_rope: rope table must be 16-byte aligned");
     const __nv_bfloat16* sp = (const __nv_bfloat16*)src_bf16;
     if (head_dim == 72)
-        qknorm_rope_kernel<72><<<grid, 128, 0, (cudaStream_t)stream>>>(sp, (__nv_bfloat16*)buf_bf16, row_stride, nseg, col0, col1,
+        qknorm_rope_kernel<72><<<grid, 256, 0, (cudaStream_t)stream>>>(sp, (__nv_bfloat16*)buf_bf16, row_stride, nseg, col0, col1,
                                                                       w0, w1, (const float2*)rope_cos_sin, M, heads, L, eps);
     else if (head_dim == 64)
-        qknorm_rope_kernel<64><<<grid, 128, 0, (cudaStream_t)stream>>>(sp, (__nv_bfloat16*)buf_bf16, row_stride, nseg, col0, col1,
+        qknorm_rope_kernel<64><<<grid, 256, 0, (cudaStream_t)stream>>>(sp, (__nv_bfloat16*)buf_bf16, row_stride, nseg, col0, col1,
                                                                       w0, w1, (const float2*)rope_cos_sin, M, heads, L, eps);
     else {
         deco_set_error("headnorm_rope: head_dim %d not built (64, 72)", head_dim);
