@@ -294,70 +294,81 @@ struct GateBwdArgs {
     float* usum;
 };
 
+// Grid: ONE resident wave (the launcher asks the occupancy calculator), block i owns the contiguous rows
+// [M i / grid, M (i + 1) / grid) -- equal shares to within a row -- and walks them image by image, so the per-image column
+// sums stay in registers until the image changes (at most a couple of atomic flushes per block).  The first version gave
+// every block a fixed 8 / 16 rows: 512 blocks on 444 resident slots = 1.15 waves, the tail wave running a sixth full
+// (ncu: 36 % of DRAM throughput, 47 us for 171 MB).
 template <bool kGate>
 __global__ void __launch_bounds__(512) rmsnorm_modulate_bwd_kernel(
     const __nv_bfloat16* __restrict__ dh, const float* __restrict__ x, const float* __restrict__ w,
     const __nv_bfloat16* __restrict__ scale, long long mod_stride, const float2* __restrict__ stats, float* __restrict__ ds,
     float* __restrict__ tsum, float* __restrict__ dshift, long long dmod_stride,
-    int L, int RB, int Hd, const GateBwdArgs G)
+    int L, long long M, int Hd, const GateBwdArgs G)
 {
     // tsum [B, Hd]: per-image sums T = sum_rows dh * xhat; d scale = w * T and d w = sum_b (1 + scale[b]) * T are formed
     // by rmsnorm_bwd_finalize_kernel (one atomic target per (image, column) instead of 1024 blocks hammering dw[Hd])
     const int c = 4 * threadIdx.x;
     if (c >= Hd) return;
-    const long long r0 = (long long)blockIdx.x * RB;
-    const long long b = r0 / L;
-    float wv[4], sc1[4];
+    const long long r_begin = M * blockIdx.x / gridDim.x, r_end = M * (blockIdx.x + 1) / gridDim.x;
+    float wv[4];
     {
         const float4 w4 = __ldg(reinterpret_cast<const float4*>(w + c));
         wv[0] = w4.x; wv[1] = w4.y; wv[2] = w4.z; wv[3] = w4.w;
-        const uint2 q = *reinterpret_cast<const uint2*>(scale + b * mod_stride + c);
-        const float2 q0 = unpack_bf2(q.x), q1 = unpack_bf2(q.y);
-        sc1[0] = 1.0f + q0.x; sc1[1] = 1.0f + q0.y; sc1[2] = 1.0f + q1.x; sc1[3] = 1.0f + q1.y;
     }
-    float a_sh[4] = {0.f, 0.f, 0.f, 0.f}, a_t[4] = {0.f, 0.f, 0.f, 0.f};
-    float g2[4] = {0.f, 0.f, 0.f, 0.f}, accg[4] = {0.f, 0.f, 0.f, 0.f}, accb[4] = {0.f, 0.f, 0.f, 0.f};
-    if (kGate) {
-        const uint2 q = *reinterpret_cast<const uint2*>(G.gate + b * G.gate_stride + c);
-        const float2 q0 = unpack_bf2(q.x), q1 = unpack_bf2(q.y);
-        g2[0] = q0.x; g2[1] = q0.y; g2[2] = q1.x; g2[3] = q1.y;
-    }
+    for (long long seg = r_begin; seg < r_end;) {
+        const long long b = seg / L;
+        const long long seg_end = min(r_end, (b + 1) * L);
+        float sc1[4];
+        {
+            const uint2 q = *reinterpret_cast<const uint2*>(scale + b * mod_stride + c);
+            const float2 q0 = unpack_bf2(q.x), q1 = unpack_bf2(q.y);
+            sc1[0] = 1.0f + q0.x; sc1[1] = 1.0f + q0.y; sc1[2] = 1.0f + q1.x; sc1[3] = 1.0f + q1.y;
+        }
+        float a_sh[4] = {0.f, 0.f, 0.f, 0.f}, a_t[4] = {0.f, 0.f, 0.f, 0.f};
+        float g2[4] = {0.f, 0.f, 0.f, 0.f}, accg[4] = {0.f, 0.f, 0.f, 0.f}, accb[4] = {0.f, 0.f, 0.f, 0.f};
+        if (kGate) {
+            const uint2 q = *reinterpret_cast<const uint2*>(G.gate + b * G.gate_stride + c);
+            const float2 q0 = unpack_bf2(q.x), q1 = unpack_bf2(q.y);
+            g2[0] = q0.x; g2[1] = q0.y; g2[2] = q1.x; g2[3] = q1.y;
+        }
 #pragma unroll 4
-    for (int i = 0; i < RB; ++i) {
-        const long long r = r0 + i;
-        const float2 st = __ldg(stats + r);
-        const float4 x4 = *reinterpret_cast<const float4*>(x + r * Hd + c);
-        const uint2 d2 = *reinterpret_cast<const uint2*>(dh + r * Hd + c);
-        float4* dp = reinterpret_cast<float4*>(ds + r * Hd + c);
-        float4 d4 = *dp;
-        const float2 d0 = unpack_bf2(d2.x), d1 = unpack_bf2(d2.y);
-        const float xv[4] = {x4.x, x4.y, x4.z, x4.w}, dv[4] = {d0.x, d0.y, d1.x, d1.y};
-        float o[4];
+        for (long long r = seg; r < seg_end; ++r) {
+            const float2 st = __ldg(stats + r);
+            const float4 x4 = *reinterpret_cast<const float4*>(x + r * Hd + c);
+            const uint2 d2 = *reinterpret_cast<const uint2*>(dh + r * Hd + c);
+            float4* dp = reinterpret_cast<float4*>(ds + r * Hd + c);
+            float4 d4 = *dp;
+            const float2 d0 = unpack_bf2(d2.x), d1 = unpack_bf2(d2.y);
+            const float xv[4] = {x4.x, x4.y, x4.z, x4.w}, dv[4] = {d0.x, d0.y, d1.x, d1.y};
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                o[e] = st.x * dv[e] * wv[e] * sc1[e] - xv[e] * st.y;
+                a_sh[e] += dv[e];
+                a_t[e] = fmaf(dv[e] * xv[e], st.x, a_t[e]);
+            }
+            d4.x += o[0]; d4.y += o[1]; d4.z += o[2]; d4.w += o[3];
+            *dp = d4;
+            if (kGate) {
+                const uint2 qa = *reinterpret_cast<const uint2*>(G.a + r * Hd + c);
+                const float2 a0 = unpack_bf2(qa.x), a1 = unpack_bf2(qa.y);
+                *reinterpret_cast<uint2*>(G.da + r * Hd + c) = make_uint2(pack_bf2(g2[0] * d4.x, g2[1] * d4.y), pack_bf2(g2[2] * d4.z, g2[3] * d4.w));
+                accg[0] = fmaf(d4.x, a0.x, accg[0]); accg[1] = fmaf(d4.y, a0.y, accg[1]);
+                accg[2] = fmaf(d4.z, a1.x, accg[2]); accg[3] = fmaf(d4.w, a1.y, accg[3]);
+                accb[0] += d4.x; accb[1] += d4.y; accb[2] += d4.z; accb[3] += d4.w;
+            }
+        }
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-            o[e] = st.x * dv[e] * wv[e] * sc1[e] - xv[e] * st.y;
-            a_sh[e] += dv[e];
-            a_t[e] = fmaf(dv[e] * xv[e], st.x, a_t[e]);
+            atomicAdd(dshift + b * dmod_stride + c + e, a_sh[e]);
+            atomicAdd(tsum + b * Hd + c + e, a_t[e]);
+            if (kGate) {
+                atomicAdd(G.dgate + b * G.dgate_stride + c + e, accg[e]);
+                if (G.usum) atomicAdd(G.usum + b * Hd + c + e, accb[e]);
+            }
         }
-        d4.x += o[0]; d4.y += o[1]; d4.z += o[2]; d4.w += o[3];
-        *dp = d4;
-        if (kGate) {
-            const uint2 qa = *reinterpret_cast<const uint2*>(G.a + r * Hd + c);
-            const float2 a0 = unpack_bf2(qa.x), a1 = unpack_bf2(qa.y);
-            *reinterpret_cast<uint2*>(G.da + r * Hd + c) = make_uint2(pack_bf2(g2[0] * d4.x, g2[1] * d4.y), pack_bf2(g2[2] * d4.z, g2[3] * d4.w));
-            accg[0] = fmaf(d4.x, a0.x, accg[0]); accg[1] = fmaf(d4.y, a0.y, accg[1]);
-            accg[2] = fmaf(d4.z, a1.x, accg[2]); accg[3] = fmaf(d4.w, a1.y, accg[3]);
-            accb[0] += d4.x; accb[1] += d4.y; accb[2] += d4.z; accb[3] += d4.w;
-        }
-    }
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        atomicAdd(dshift + b * dmod_stride + c + e, a_sh[e]);
-        atomicAdd(tsum + b * Hd + c + e, a_t[e]);
-        if (kGate) {
-            atomicAdd(G.dgate + b * G.dgate_stride + c + e, accg[e]);
-            if (G.usum) atomicAdd(G.usum + b * Hd + c + e, accb[e]);
-        }
+        seg = seg_end;
     }
 }
 
@@ -670,13 +681,20 @@ static int rmsnorm_modulate_bwd_impl(const void* dh_bf16, const float* x, const 
     else
         rmsnorm_bwd_rowstats_kernel<16><<<g1, 256, 0, st>>>(dhp, x, weight, scp, mod_row_stride, stats, rows_per_image, M, hidden, eps);
     DECO_CHECK_LAUNCH("rmsnorm_bwd_rowstats_kernel");
-    const int rb = rows_block(rows_per_image, M);
+    // one resident wave of blocks, each with an equal share of contiguous rows
+    const int threads = ((hidden / 4) + 31) / 32 * 32;
+    int per_sm = 0;
+    cudaError_t oe = gate ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rmsnorm_modulate_bwd_kernel<true>, threads, 0)
+                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rmsnorm_modulate_bwd_kernel<false>, threads, 0);
+    if (oe != cudaSuccess || per_sm < 1) per_sm = 1;
+    long long nblk = (long long)per_sm * kNumSMs;
+    if (nblk > M) nblk = M;
     if (gate)
-        rmsnorm_modulate_bwd_kernel<true><<<(unsigned)(M / rb), ((hidden / 4) + 31) / 32 * 32, 0, st>>>(
-            dhp, x, weight, scp, mod_row_stride, stats, ds_accum, img_ws, dshift_accum, dmod_row_stride, rows_per_image, rb, hidden, *gate);
+        rmsnorm_modulate_bwd_kernel<true><<<(unsigned)nblk, threads, 0, st>>>(
+            dhp, x, weight, scp, mod_row_stride, stats, ds_accum, img_ws, dshift_accum, dmod_row_stride, rows_per_image, M, hidden, *gate);
     else
-        rmsnorm_modulate_bwd_kernel<false><<<(unsigned)(M / rb), ((hidden / 4) + 31) / 32 * 32, 0, st>>>(
-            dhp, x, weight, scp, mod_row_stride, stats, ds_accum, img_ws, dshift_accum, dmod_row_stride, rows_per_image, rb, hidden,
+        rmsnorm_modulate_bwd_kernel<false><<<(unsigned)nblk, threads, 0, st>>>(
+            dhp, x, weight, scp, mod_row_stride, stats, ds_accum, img_ws, dshift_accum, dmod_row_stride, rows_per_image, M, hidden,
             GateBwdArgs{});
     DECO_CHECK_LAUNCH("rmsnorm_modulate_bwd_kernel");
     rmsnorm_bwd_finalize_kernel<<<(hidden + 31) / 32, dim3(32, 32), 0, st>>>(img_ws, weight, scp, mod_row_stride, dscale_accum,
