@@ -326,6 +326,29 @@ __device__ __forceinline__ void epilogue_chunk_swiglu_bwd(const GemmParams& P, c
     __syncwarp();
 }
 
+// ------------------------------------------------------------------ tile schedule of the persistent CTA groups
+// Static, but balanced: (1) the tiles of a RAGGED last column (a narrower MMA, a fraction of a full tile's time) are
+// numbered after all full-width tiles, (2) successive rounds run over the CTA groups in alternating direction ("snake"),
+// so the groups that drew the extra tile of the last full round get the cheap tiles or none.  N = 1152 in 256-wide tiles on
+// 8192 rows = 128 full + 32 half tiles on 74 CTA pairs: every pair ends with exactly two tile-times of work (round robin in
+// row-major order: three), which is what lets the 1152-wide GEMMs of the training step use 256-wide tiles at all -- in
+// 192-wide tiles they are 192 tiles = 2.6 -> 3 rounds of a tile shape that feeds the tensor pipe a quarter slower.
+struct TileSchedule {
+    int num_n, num_mn, num_tiles, group, groups, full_mn;     // full_mn: tiles of the full-width columns (0 = no ragged column)
+    __device__ __forceinline__ int tile_of_round(int round) const {      // -1 = this group is done
+        const int t = round * groups + ((round & 1) ? groups - 1 - group : group);
+        return t < num_tiles ? t : -1;
+    }
+    __device__ __forceinline__ void coords(int tile, int& m_blk, int& n_blk, int& ks) const {
+        const int mn = tile % num_mn;
+        ks = tile / num_mn;
+        if (full_mn > 0) {
+            if (mn < full_mn) { m_blk = mn / (num_n - 1); n_blk = mn % (num_n - 1); }
+            else { m_blk = mn - full_mn; n_blk = num_n - 1; }
+        } else { m_blk = mn / num_n; n_blk = mn % num_n; }
+    }
+};
+
 // ------------------------------------------------------------------ kernel
 // CG = 1: one CTA per 128 x BN tile.   CG = 2: a 2-CTA cluster per 256 x BN tile (rank 0 = leader issues the MMAs).
 // TN = true: both operands are given TRANSPOSED in global memory -- At [K, M] and Wt [K, N], row-major -- and are staged
@@ -365,6 +388,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     // multiplying zero padding: under the board power cap wasted MMA work costs clock, not just tensor-pipe time
     const int n_rem = P.N - (num_n - 1) * BN;
     const int n_last = (!TN && n_rem < BN && n_rem % 32 == 0) ? n_rem : BN;
+    TileSchedule sched;
+    sched.num_n = num_n; sched.num_mn = num_mn; sched.num_tiles = num_tiles; sched.group = tile0; sched.groups = tile_stride;
+    sched.full_mn = (n_last < BN && num_n > 1) ? num_m * (num_n - 1) : 0;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
@@ -390,9 +416,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         // ===================== TMA producer (every CTA loads its own A rows and its share of W) =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int tile = tile0; tile < num_tiles; tile += tile_stride) {
-                const int mn = tile % num_mn, ks = tile / num_mn;
-                const int m_blk = mn / num_n, n_blk = mn % num_n;
+            for (int round = 0, tile; (tile = sched.tile_of_round(round)) >= 0; ++round) {
+                int m_blk, n_blk, ks;
+                sched.coords(tile, m_blk, n_blk, ks);
                 const int arow = (m_blk * CG + (int)cta_rank) * kBM;
                 const int brow = n_blk * BN + (int)cta_rank * ((n_blk == num_n - 1 ? n_last : BN) / CG);
                 const int kb0 = ks * k_per, kb1 = min(num_k, kb0 + k_per);
@@ -435,12 +461,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             constexpr uint32_t idesc = TN ? make_idesc_major(kBM * CG, BN, 1, 1) : make_idesc(kBM * CG, BN);
             int stage = 0; uint32_t phase = 0;
             int as = 0; uint32_t aphase = 0;
-            for (int tile = tile0; tile < num_tiles; tile += tile_stride) {
+            for (int round = 0, tile; (tile = sched.tile_of_round(round)) >= 0; ++round) {
+                int m_blk, n_blk, ks;
+                sched.coords(tile, m_blk, n_blk, ks);
                 mbar_wait(tempty_bar(as), aphase ^ 1);   // epilogues (of both CTAs) have drained this accumulator stage
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
-                const uint32_t idesc_t = (!TN && ((tile % num_mn) % num_n) == num_n - 1) ? make_idesc(kBM * CG, n_last) : idesc;
-                const int kb0 = (tile / num_mn) * k_per, kb1 = min(num_k, kb0 + k_per);
+                const uint32_t idesc_t = (!TN && n_blk == num_n - 1) ? make_idesc(kBM * CG, n_last) : idesc;
+                const int kb0 = ks * k_per, kb1 = min(num_k, kb0 + k_per);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
@@ -472,8 +500,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         int as = 0; uint32_t aphase = 0;
         float* stg = reinterpret_cast<float*>(smem_raw + (epi_stage_base - smem_u32(smem_raw))) +
                      (warp - kEpiWarp0) * kStageFloatsPerWarp;
-        for (int tile = tile0; tile < num_tiles; tile += tile_stride) {
-            const int m_blk = (tile % num_mn) / num_n, n_blk = (tile % num_mn) % num_n;
+        for (int round = 0, tile; (tile = sched.tile_of_round(round)) >= 0; ++round) {
+            int m_blk, n_blk, ks;
+            sched.coords(tile, m_blk, n_blk, ks);
             const long long row0 = (long long)(m_blk * CG + (int)cta_rank) * kBM + q * 32;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
             const int nbase = n_blk * BN;
@@ -653,13 +682,30 @@ extern "C" int deco_gemm_bf16(const void* A, long long lda, const void* W, long 
     if (epilogue == EPI_SWIGLU_DUAL || epilogue == EPI_SWIGLU_BWD)
         DECO_CHECK_ARG(resid && ldr % 8 == 0 && ((uintptr_t)resid & 15) == 0 && N % 16 == 0,
                        "gemm: the SwiGLU training epilogues take the bf16 pre-activation matrix in resid / ldr (N %% 16 == 0)");
-    // tile width: measured on the XL shapes (scripts/gemm_bench.py, profiles/gemm_bench_r1.txt): 256 where it divides N
-    // (cond_embed 1315 TFLOP/s, SwiGLU 1554 with the direct epilogue), 192 for the 1152-multiples
-    int bn = tile_n;
-    if (bn == 0) bn = (N % 256 == 0) ? 256 : ((N % 192 == 0) ? 192 : (N % 128 == 0 ? 128 : (N >= 1024 ? 256 : 128)));
-    DECO_CHECK_ARG(bn == 128 || bn == 192 || bn == 256, "gemm: tile_n must be 128, 192 or 256");
     // 2-CTA pairs for anything with at least one full 256-row pair tile; staged (coalesced) epilogue only there
     int cg = (g_force_cta_group > 0) ? g_force_cta_group : (M > kBM ? 2 : 1);
+    // Tile width.  Wide tiles feed the tensor pipe better (isolated: 850 / 1220 / 1590 TFLOP/s at 128 / 192 / 256 columns,
+    // profiles/gemm_bench_r1.txt); a ragged last column tile runs a narrower MMA and costs its fraction of a tile; the
+    // balanced schedule (TileSchedule) packs full and ragged tiles into ceil(units / CTA groups) rounds.  Pick the width with
+    // the smallest rounds x width / efficiency: N = 1152 on 8192 rows -> 256 (2 rounds) instead of 192 (3 rounds).
+    int bn = tile_n;
+    if (bn == 0) {
+        const int groups = num_sms() / cg;
+        const int num_m = (M + kBM * cg - 1) / (kBM * cg);
+        double best = 0.0;
+        for (int cand : {256, 192, 128}) {
+            if (cand == 192 && N % 192 != 0) continue;
+            const int nfull = N / cand, rem = N - nfull * cand;
+            const double frac = rem == 0 ? 0.0 : (rem % 32 == 0 ? (double)rem / cand : 1.0);
+            const double units = (double)num_m * (nfull + frac);
+            double rounds = units / groups;
+            rounds = (rounds <= 1.0) ? 1.0 : (double)(long long)(rounds + 0.999);
+            const double eff = cand == 256 ? 1.0 : (cand == 192 ? 0.78 : 0.55);
+            const double cost = rounds * cand / eff;
+            if (bn == 0 || cost < best) { bn = cand; best = cost; }
+        }
+    }
+    DECO_CHECK_ARG(bn == 128 || bn == 192 || bn == 256, "gemm: tile_n must be 128, 192 or 256");
     // staged (coalesced) epilogue everywhere except SwiGLU, whose output is half as wide as its accumulator tile and
     // is compute-heavy: the row-per-thread form keeps all 128 epilogue threads busy (1554 vs 1069 TFLOP/s at BN = 256)
     int staged = (g_force_staged >= 0) ? g_force_staged : (epilogue == EPI_SWIGLU ? 0 : 1);
