@@ -390,7 +390,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const int n_last = (!TN && n_rem < BN && n_rem % 32 == 0) ? n_rem : BN;
     TileSchedule sched;
     sched.num_n = num_n; sched.num_mn = num_mn; sched.num_tiles = num_tiles; sched.group = tile0; sched.groups = tile_stride;
-    sched.full_mn = (n_last < BN && num_n > 1) ? num_m * (num_n - 1) : 0;
+    // ragged tiles last only while A stays in L2 (126 MB): they re-read every row block of A long after the full-width tiles
+    // of that block ran.  On the 131072-row inference GEMMs the same order cost 1.2 % of the step in re-streamed A (measured
+    // in the fused kernels, profiles/tile_schedule_r2.txt); there the row-major order stays.
+    sched.full_mn = (n_last < BN && num_n > 1 && (long long)P.M * P.K * 2 <= (64ll << 20)) ? num_m * (num_n - 1) : 0;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
