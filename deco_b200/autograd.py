@@ -292,7 +292,14 @@ def train_forward(module, x32, t, y):
     return out, S
 
 
-def _blocks_backward(module, P: dict, T: dict, S: dict, ds: torch.Tensor, dmod: torch.Tensor, G: Dict[str, torch.Tensor]) -> None:
+def _make_lane(dev) -> "WgradLane":
+    # wgrad GEMMs on a second stream (not under the per-GEMM event probe of the bench's roofline pass, whose launch durations
+    # must not overlap other work, and not for the A/B transpose variant)
+    return WgradLane(dev, WGRAD_STREAM and WGRAD == "tn" and ops.gemm_probe is None)
+
+
+def _blocks_backward(module, P: dict, T: dict, S: dict, ds: torch.Tensor, dmod: torch.Tensor, G: Dict[str, torch.Tensor],
+                     lane: "WgradLane" = None) -> None:
     """Backward of `_blocks_forward`: walks the blocks in reverse, updates the stream gradient ds [B*L, H] fp32 in place,
     accumulates the modulation gradients into dmod[:, :nb*6H] and leaves the blocks' parameter gradients in G."""
     dev = ds.device
@@ -302,9 +309,8 @@ def _blocks_backward(module, P: dict, T: dict, S: dict, ds: torch.Tensor, dmod: 
     nb = len(P["blocks"])
     mod = S["mod"]
     z = lambda *shape: torch.zeros(shape, dtype=F32, device=dev)   # noqa: E731
-    # wgrad GEMMs of the blocks on a second stream (not under the per-GEMM event probe of the bench's roofline pass, whose
-    # launch durations must not overlap other work, and not for the A/B transpose variant)
-    lane = WgradLane(dev, WGRAD_STREAM and WGRAD == "tn" and ops.gemm_probe is None)
+    if lane is None:
+        lane = _make_lane(dev)
     ready: List[tuple] = []     # per finished block: its matrix gradients, announced once the lane delivered
     zblk = z(max(nb, 1), 3 * H + 2 * d)       # one fill for the per-block vector gradients (norm1/2, proj bias, q/k-norm)
     da2 = None
@@ -461,8 +467,11 @@ def train_backward(module, S: dict, dout: torch.Tensor) -> Dict[str, torch.Tenso
     G["dec_net.final_layer.linear.weight"] = gdec[of:of + 128].view(4, 32)[:C]
     G["dec_net.final_layer.linear.bias"] = gdec[of + 128:of + 128 + C]
 
-    # ---- cond_embed: ycond = s2 . wcond^T + bcond
-    G["dec_net.cond_embed.weight"] = _wgrad(dycond, S["s2"])
+    # ---- cond_embed: ycond = s2 . wcond^T + bcond (its weight gradient, the largest single wgrad GEMM of the step, rides on
+    # the second stream under the first blocks' chain)
+    lane = _make_lane(dev)
+    G["dec_net.cond_embed.weight"] = lane.wgrad(dycond, S["s2"])
+    lane.mark()
     G["dec_net.cond_embed.bias"] = _colsum(dycond)
     ds2 = ops.gemm(dycond, T["wcondT"], None, ops.EPI_BIAS)
     del dycond
@@ -473,7 +482,8 @@ def train_backward(module, S: dict, dout: torch.Tensor) -> Dict[str, torch.Tenso
 
     # ---- DiT blocks
     dmod = z(B, nb * 6 * H)
-    _blocks_backward(module, P, T, S, ds, dmod, G)
+    _blocks_backward(module, P, T, S, ds, dmod, G, lane)
+    lane.sync(0)
     # ---- s_embedder: s0 = xp . ws^T + bs
     G["s_embedder.proj.weight"] = _wgrad(ds, S["xp"])
     G["s_embedder.proj.bias"] = _colsum(ds)
