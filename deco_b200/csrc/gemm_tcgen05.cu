@@ -160,8 +160,12 @@ __device__ __forceinline__ void epilogue_chunk_staged(const GemmParams& P, const
                 } else if (EPI == EPI_BIAS_F32) {
                     const long long orow = P.deint_rows > 0 ? ((row >> 4) & 1) * P.deint_rows + (row >> 5) * 16 + (row & 15) : row;
                     float* o = reinterpret_cast<float*>(P.out) + orow * P.ldo + n;
-                    if (P.split_k > 1) {        // partial product of one K slice (output zeroed by the launcher)
-                        atomicAdd(o, v.x); atomicAdd(o + 1, v.y); atomicAdd(o + 2, v.z); atomicAdd(o + 3, v.w);
+                    if (P.split_k > 1) {        // partial product of one K slice (output zeroed by the launcher): ONE vector
+                        // reduction per 16 bytes -- a REDG costs the SM ~1.3 clocks per lane whatever its width, and
+                        // four scalar ones per float4 made the epilogue of a split tile (42 k clocks) longer than its
+                        // half-depth main loop
+                        asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                                     :: "l"(o), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
                     } else {
                         *reinterpret_cast<float4*>(o) = v;
                     }
@@ -417,7 +421,38 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 
     if (warp == 0) {
         // ===================== TMA producer (every CTA loads its own A rows and its share of W) =====================
-        if (lane == 0) {
+        if (TN) {
+            // MN-major staging: 64-wide MN blocks, each a {64 x 64} box at (MN coordinate, K row) -- kBM / 64 boxes of A and
+            // BN / CG / 64 of W per K block.  One thread gets a bulk tensor load out only every ~250 clocks whatever the box
+            // (profiles/tma_bench_r2.txt): four boxes from lane 0 were 1000 clocks per K block against 512 clocks of MMA, i.e.
+            // the weight-gradient GEMMs sat at half the tensor rate.  Each box is issued by its own lane instead.
+            constexpr int kBoxesA = kBM / 64, kBoxesB = (BN / CG) / 64;
+            int stage = 0; uint32_t phase = 0;
+            for (int round = 0, tile; (tile = sched.tile_of_round(round)) >= 0; ++round) {
+                int m_blk, n_blk, ks;
+                sched.coords(tile, m_blk, n_blk, ks);
+                const int arow = (m_blk * CG + (int)cta_rank) * kBM;
+                const int brow = n_blk * BN + (int)cta_rank * (BN / CG);
+                const int kb0 = ks * k_per, kb1 = min(num_k, kb0 + k_per);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+                    const uint32_t sb = sa + Cfg::kStageBytesA;
+                    if (lane == 0 && (CG == 1 || is_leader)) mbar_expect_tx(full_bar(stage), CG * Cfg::kStageBytes);
+                    __syncwarp();
+                    const uint32_t fb = CG == 2 ? mapa_shared(full_bar(stage), 0) : full_bar(stage);
+                    if (lane < kBoxesA) {
+                        if (CG == 2) tma_load_2d_2sm(sa + lane * 8192, &tmap_a, fb, arow + 64 * lane, kb * kBK);
+                        else tma_load_2d(sa + lane * 8192, &tmap_a, fb, arow + 64 * lane, kb * kBK);
+                    } else if (lane < kBoxesA + kBoxesB) {
+                        const int j = lane - kBoxesA;
+                        if (CG == 2) tma_load_2d_2sm(sb + j * 8192, &tmap_b, fb, brow + 64 * j, kb * kBK);
+                        else tma_load_2d(sb + j * 8192, &tmap_b, fb, brow + 64 * j, kb * kBK);
+                    }
+                    if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        } else if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int round = 0, tile; (tile = sched.tile_of_round(round)) >= 0; ++round) {
                 int m_blk, n_blk, ks;
@@ -429,21 +464,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
                     const uint32_t sb = sa + Cfg::kStageBytesA;
-                    if (TN) {
-                        // MN-major staging: 64-wide MN blocks, each a {64 x 64} box at (MN coordinate, K row)
-                        if (CG == 1 || is_leader) mbar_expect_tx(full_bar(stage), CG * Cfg::kStageBytes);
-                        const uint32_t fb = CG == 2 ? mapa_shared(full_bar(stage), 0) : full_bar(stage);
-#pragma unroll
-                        for (int j = 0; j < kBM / 64; ++j) {
-                            if (CG == 2) tma_load_2d_2sm(sa + j * 8192, &tmap_a, fb, arow + 64 * j, kb * kBK);
-                            else tma_load_2d(sa + j * 8192, &tmap_a, fb, arow + 64 * j, kb * kBK);
-                        }
-#pragma unroll
-                        for (int j = 0; j < (BN / CG) / 64; ++j) {
-                            if (CG == 2) tma_load_2d_2sm(sb + j * 8192, &tmap_b, fb, brow + 64 * j, kb * kBK);
-                            else tma_load_2d(sb + j * 8192, &tmap_b, fb, brow + 64 * j, kb * kBK);
-                        }
-                    } else if (CG == 1) {
+                    if (CG == 1) {
                         mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
                         tma_load_2d(sa, &tmap_a, full_bar(stage), kb * kBK, arow);
                         tma_load_2d(sb, &tmap_b, full_bar(stage), kb * kBK, brow);
@@ -745,6 +766,9 @@ static int auto_split_k(int M, int N, int K, int bn, int cg, int ctas) {
     const int tiles = ((M + kBM * cg - 1) / (kBM * cg)) * ((N + bn - 1) / bn);
     const int groups = ctas / cg;
     const int num_k = (K + kBK - 1) / kBK;
+    // Only when the tiles leave at least half of the CTA groups idle.  Splitting a GEMM that already fills a round to shave
+    // its last round was measured and is slower (dW13 = 120 tiles: 3 slices = 5 rounds of a third, 95.7 -> 100.5 us): every
+    // slice pays its own pipeline fill and a reduction epilogue.
     if (tiles * 2 > groups || num_k < 8) return 1;
     int s = groups / tiles;
     if (s > num_k / 4) s = num_k / 4;

@@ -1,0 +1,10 @@
+set -u
+O=gpurun_out; mkdir -p $O
+timeout 900 python -m pytest tests/test_gpu_backward.py tests/test_gpu_kernels.py -q -x > $O/tests_r2ap.log 2>&1; echo "tests rc=$?"; tail -3 $O/tests_r2ap.log
+python scripts/wgrad_bench.py 2>&1 | tee $O/wgrad_bench.txt
+python bench.py --workload train256 --no-cpu-baseline --torch-baseline none --steps 40 > $O/bench_train_ap.log 2>&1
+python - <<'PY'
+import json
+l=[x for x in open('gpurun_out/bench_train_ap.log') if x.startswith('{')]
+d=json.loads(l[-1]); print('train256', d['value'], d['ms_per_step'], d['parity']['grad_rel_l2'], d['full_iteration']['ms'], d['roofline']['frac'], d['roofline']['step_frac_of_peak'], d['clocks']['sm_mhz'])
+PY
