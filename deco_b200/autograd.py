@@ -428,8 +428,7 @@ def train_backward(module, S: dict, dout: torch.Tensor) -> Dict[str, torch.Tenso
     P = module.prepare(dev)
     T = P["train"]
     B, L = S["B"], S["L"]
-    p, H, heads = module.patch_size, module.hidden_size, module.num_groups
-    d = H // heads
+    p, H = module.patch_size, module.hidden_size
     nb = len(P["blocks"])
     R = module.num_blocks - module.num_cond_blocks
     C = module.in_channels
