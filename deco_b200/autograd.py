@@ -223,27 +223,43 @@ def _cond_forward(module, P: dict, t, y, S: dict):
     return temb, mod
 
 
-def _blocks_forward(P: dict, mod, s, B: int, L: int, H: int, heads: int, pos):
-    """The AdaLN DiT blocks (dit_c2i_DeCo.py:194-210 == dit_c2i_baseline.py:194-210) on the fp32 stream s [B*L, H], one
-    kernel per reference op, keeping per block what the backward reads.  Returns (s_out, saved blocks)."""
+def _blocks_forward(bps: list, mod, s, B: int, L: int, H: int, heads: int, pos, joint=None):
+    """The AdaLN DiT blocks (dit_c2i_DeCo.py:194-210 == dit_c2i_baseline.py:194-210; dit_t2i_pixnerd.py:65-81, :176-198) on
+    the fp32 stream s [B*L, H], one kernel per reference op, keeping per block what the backward reads.  bps = the prepared
+    weights of the blocks, mod = their [B, nb*6H] modulation columns, pos = RoPE table or None (the t2i text blocks).
+    joint = (ytxt bf16 [B*T, H], T): the t2i joint attention (dit_t2i_pixnerd.py:43-59) -- every block adds the keys / values
+    kv_y(ytxt) (k-normed, no RoPE) behind the image keys.  Returns (s_out, saved blocks)."""
     d = H // heads
     dev = s.device
     blocks = []
-    nb = len(P["blocks"])
+    nb = len(bps)
 
     def mod6(i):
         m = mod[:, i * 6 * H:(i + 1) * 6 * H]
         return tuple(m[:, j * H:(j + 1) * H] for j in range(6))
 
     h1 = None
-    for i, bp in enumerate(P["blocks"]):
+    for i, bp in enumerate(bps):
         sh1, sc1, g1, sh2, sc2, g2 = mod6(i)
         if h1 is None:
             h1 = ops.rmsnorm_modulate(s, bp["n1"], sh1, sc1, L)
         qkv_raw = ops.gemm(h1, bp["wqkv"], None, ops.EPI_BIAS)
         qkv = torch.empty_like(qkv_raw)          # q, k normalised + rotated here; v is read from the raw GEMM output
         ops.qknorm_rope_to(qkv_raw, qkv, bp["qn"], bp["kn"], pos, heads, d, L)
-        o, lse = ops.attention_lse(qkv[:, :H], qkv[:, H:2 * H], qkv_raw[:, 2 * H:], B, heads, d)
+        extra = {}
+        if joint is None:
+            o, lse = ops.attention_lse(qkv[:, :H], qkv[:, H:2 * H], qkv_raw[:, 2 * H:], B, heads, d)
+        else:
+            # keys / values = [image (L) || text (T)] per image, as one segment of L + T rows (copies: the backward kernels
+            # take one key segment)
+            ytxt, Tt = joint
+            kvy_raw = ops.gemm(ytxt, bp["wkvy"], None, ops.EPI_BIAS)                  # [B*T, 2H]
+            kvy = kvy_raw.clone()
+            ops.headnorm_rope_(kvy, 0, bp["kn"], heads, d, Tt)
+            kc = torch.cat([qkv.view(B, L, 3 * H)[:, :, H:2 * H], kvy.view(B, Tt, 2 * H)[:, :, :H]], 1).view(B * (L + Tt), H)
+            vc = torch.cat([qkv_raw.view(B, L, 3 * H)[:, :, 2 * H:], kvy.view(B, Tt, 2 * H)[:, :, H:]], 1).view(B * (L + Tt), H)
+            o, lse = ops.attention_lse(qkv[:, :H], kc, vc, B, heads, d)
+            extra = dict(kvy_raw=kvy_raw, kc=kc, vc=vc)
         a1 = ops.gemm(o, bp["wproj"], bp["bproj"], ops.EPI_BIAS)
         # residual add + the norm that feeds the next GEMM in one pass over the row (FUSE_GATE_NORM=0: the two kernels)
         if FUSE_GATE_NORM:
@@ -261,10 +277,11 @@ def _blocks_forward(P: dict, mod, s, B: int, L: int, H: int, heads: int, pos):
         h1_next = None
         if FUSE_GATE_NORM and i + 1 < nb:
             nsh1, nsc1 = mod6(i + 1)[:2]
-            s_out, h1_next = ops.gate_residual_norm(s_mid, a2, g2, L, P["blocks"][i + 1]["n1"], nsh1, nsc1)
+            s_out, h1_next = ops.gate_residual_norm(s_mid, a2, g2, L, bps[i + 1]["n1"], nsh1, nsc1)
         else:
             s_out = ops.gate_residual(s_mid, a2, g2, L)
-        blocks.append(dict(s_in=s, h1=h1, qkv_raw=qkv_raw, qkv=qkv, o=o, lse=lse, a1=a1, s_mid=s_mid, h2=h2, y13=y13, u=u, a2=a2))
+        blocks.append(dict(s_in=s, h1=h1, qkv_raw=qkv_raw, qkv=qkv, o=o, lse=lse, a1=a1, s_mid=s_mid, h2=h2, y13=y13, u=u, a2=a2,
+                           **extra))
         s, h1 = s_out, h1_next
     return s, blocks
 
@@ -283,7 +300,7 @@ def train_forward(module, x32, t, y):
     temb, mod = _cond_forward(module, P, t, y, S)
     s = ops.gemm(xp, P["ws"], P["bs"], ops.EPI_BIAS_F32)
     S.update(xp=xp)
-    s, blocks = _blocks_forward(P, mod, s, B, L, H, heads, pos)
+    s, blocks = _blocks_forward(P["blocks"], mod, s, B, L, H, heads, pos)
     s2 = ops.silu_add_rows(s, temb, L)
     ycond = ops.gemm(s2, P["wcond"], P["bcond"], ops.EPI_BIAS)
     R = module.num_blocks - module.num_cond_blocks
@@ -299,15 +316,23 @@ def _make_lane(dev) -> "WgradLane":
 
 
 def _blocks_backward(module, P: dict, T: dict, S: dict, ds: torch.Tensor, dmod: torch.Tensor, G: Dict[str, torch.Tensor],
-                     lane: "WgradLane" = None) -> None:
+                     lane: "WgradLane" = None, spec: dict = None) -> None:
     """Backward of `_blocks_forward`: walks the blocks in reverse, updates the stream gradient ds [B*L, H] fp32 in place,
-    accumulates the modulation gradients into dmod[:, :nb*6H] and leaves the blocks' parameter gradients in G."""
+    accumulates the modulation gradients into dmod[:, :nb*6H] and leaves the blocks' parameter gradients in G.
+    spec (t2i): which block list this is -- bps / bts (prepared weights and their transposes), saved (the forward's per-block
+    dicts), mod (the blocks' modulation columns; dmod is the matching view), L (rows per image), pos, prefix, t2i = True
+    (parameter names of dit_t2i_pixnerd.py: qkv_x / qkv, w12, w3), joint = dict(ytxt, T, dyt fp32 [B*T, H] accumulated, ones)."""
+    spec = spec or {}
     dev = ds.device
-    B, L = S["B"], S["L"]
+    B, L = S["B"], spec.get("L", S["L"])
     H, heads = module.hidden_size, module.num_groups
     d = H // heads
-    nb = len(P["blocks"])
-    mod = S["mod"]
+    bps, bts, saved = spec.get("bps", P.get("blocks")), spec.get("bts", T.get("blocks")), spec.get("saved", S.get("blocks"))
+    prefix, t2i, joint = spec.get("prefix", "blocks."), spec.get("t2i", False), spec.get("joint")
+    pos = spec["pos"] if "pos" in spec else S["pos"]
+    qkv_name = ("attn.qkv_x.weight" if joint is not None else "attn.qkv.weight")
+    nb = len(bps)
+    mod = spec.get("mod", S["mod"])
     z = lambda *shape: torch.zeros(shape, dtype=F32, device=dev)   # noqa: E731
     if lane is None:
         lane = _make_lane(dev)
@@ -315,14 +340,14 @@ def _blocks_backward(module, P: dict, T: dict, S: dict, ds: torch.Tensor, dmod: 
     zblk = z(max(nb, 1), 3 * H + 2 * d)       # one fill for the per-block vector gradients (norm1/2, proj bias, q/k-norm)
     da2 = None
     for i in reversed(range(nb)):
-        bp, bt, sv = P["blocks"][i], T["blocks"][i], S["blocks"][i]
-        pre = f"blocks.{i}."
+        bp, bt, sv = bps[i], bts[i], saved[i]
+        pre = f"{prefix}{i}."
         m = mod[:, i * 6 * H:(i + 1) * 6 * H]
         dm = dmod[:, i * 6 * H:(i + 1) * 6 * H]
         sc1, g1, sc2, g2 = m[:, H:2 * H], m[:, 2 * H:3 * H], m[:, 4 * H:5 * H], m[:, 5 * H:6 * H]
         dsh1, dsc1, dg1, dsh2, dsc2, dg2 = (dm[:, j * H:(j + 1) * H] for j in range(6))
-        F_ = module.blocks[i].mlp.w1.weight.shape[0]
-        Fp = P["ffn_pad"]
+        Fp = bp["w2"].shape[1]                       # SwiGLU width as prepared (padded to a multiple of 16)
+        F_ = Fp if t2i else module.blocks[i].mlp.w1.weight.shape[0]
         # MLP branch (da2: gate_bwd of this block's second residual add -- computed by the fused kernel at the end of the
         # previous iteration, or here for the last block)
         if da2 is None:
@@ -352,10 +377,29 @@ def _blocks_backward(module, P: dict, T: dict, S: dict, ds: torch.Tensor, dmod: 
         do = ops.gemm(da1, bt["wprojT"], None, ops.EPI_BIAS)
         qkv = sv["qkv"]
         dqkv = torch.empty_like(qkv)
-        ops.attention_bwd(qkv[:, :H], qkv[:, H:2 * H], sv["qkv_raw"][:, 2 * H:], sv["o"], do,
-                          dqkv[:, :H], dqkv[:, H:2 * H], dqkv[:, 2 * H:], B, heads, d, lse=sv["lse"])
-        ops.headnorm_rope_bwd_(dqkv, sv["qkv_raw"], 0, bp["qn"], S["pos"], dqn, heads, d, L)
-        ops.headnorm_rope_bwd_(dqkv, sv["qkv_raw"], H, bp["kn"], S["pos"], dkn, heads, d, L)
+        gwkvy = None
+        if joint is None:
+            ops.attention_bwd(qkv[:, :H], qkv[:, H:2 * H], sv["qkv_raw"][:, 2 * H:], sv["o"], do,
+                              dqkv[:, :H], dqkv[:, H:2 * H], dqkv[:, 2 * H:], B, heads, d, lse=sv["lse"])
+        else:
+            # one key segment [image || text]: its gradient is pulled apart again (copies); the text half goes back through
+            # the k-norm (the SAME k_norm weight as the image keys: both accumulate into dkn) and kv_y into the text stream
+            Tt = joint["T"]
+            dkc, dvc = torch.empty_like(sv["kc"]), torch.empty_like(sv["vc"])
+            ops.attention_bwd(qkv[:, :H], sv["kc"], sv["vc"], sv["o"], do, dqkv[:, :H], dkc, dvc, B, heads, d, lse=sv["lse"])
+            dq3, dk3, dv3 = dqkv.view(B, L, 3 * H), dkc.view(B, L + Tt, H), dvc.view(B, L + Tt, H)
+            dq3[:, :, H:2 * H].copy_(dk3[:, :L])
+            dq3[:, :, 2 * H:].copy_(dv3[:, :L])
+            dkvy = torch.empty((B * Tt, 2 * H), dtype=bf16, device=dev)
+            dkvy.view(B, Tt, 2 * H)[:, :, :H].copy_(dk3[:, L:])
+            dkvy.view(B, Tt, 2 * H)[:, :, H:].copy_(dv3[:, L:])
+            ops.headnorm_rope_bwd_(dkvy, sv["kvy_raw"], 0, bp["kn"], None, dkn, heads, d, Tt)
+            gwkvy = lane.wgrad(dkvy, joint["ytxt"])
+            ops.gemm(dkvy, bt["wkvyT"], None, ops.EPI_GATE_RESIDUAL, out=joint["dyt"], resid=joint["dyt"], gate=joint["ones"],
+                     rows_per_gate=B * Tt)            # dyt += dkvy . Wkvy, accumulated in fp32 over the blocks
+            del dkc, dvc, dkvy
+        ops.headnorm_rope_bwd_(dqkv, sv["qkv_raw"], 0, bp["qn"], pos, dqn, heads, d, L)
+        ops.headnorm_rope_bwd_(dqkv, sv["qkv_raw"], H, bp["kn"], pos, dkn, heads, d, L)
         G[pre + "attn.q_norm.weight"], G[pre + "attn.k_norm.weight"] = dqn, dkn
         gwqkv = lane.wgrad(dqkv, sv["h1"])
         lane.mark()
@@ -363,32 +407,39 @@ def _blocks_backward(module, P: dict, T: dict, S: dict, ds: torch.Tensor, dmod: 
         da2 = None
         if FUSE_GATE_NORM and i > 0:      # norm1 backward + the gate backward of block i - 1's second residual add
             mp, dmp = mod[:, (i - 1) * 6 * H:i * 6 * H], dmod[:, (i - 1) * 6 * H:i * 6 * H]
-            da2 = ops.rmsnorm_modulate_bwd_gate_(ds, dh1, sv["s_in"], bp["n1"], sc1, dn1, dsh1, dsc1, L, S["blocks"][i - 1]["a2"],
+            da2 = ops.rmsnorm_modulate_bwd_gate_(ds, dh1, sv["s_in"], bp["n1"], sc1, dn1, dsh1, dsc1, L, saved[i - 1]["a2"],
                                                  mp[:, 5 * H:6 * H], dmp[:, 5 * H:6 * H])
         else:
             ops.rmsnorm_modulate_bwd_(ds, dh1, sv["s_in"], bp["n1"], sc1, dn1, dsh1, dsc1, L)
         G[pre + "norm1.weight"] = dn1
         del da1, do, dqkv, dh1
-        S["blocks"][i] = None   # release the block's activations (the lane keeps what its GEMMs still read)
+        saved[i] = None   # release the block's activations (the lane keeps what its GEMMs still read)
         # The main stream joins the lane one block late, so that a block's wgrad GEMMs overlap the next block's chain; the
         # matrix gradients of a joined block are final (w1 / w3 de-interleaved on the main stream) and are announced; the
         # vector gradients live in zblk / dmod and follow with the tail.
-        ready.append((i, F_, gw2, gw13, gwproj, gwqkv))
-        del gw2, gw13, gwproj, gwqkv
+        ready.append((i, F_, gw2, gw13, gwproj, gwqkv, gwkvy))
+        del gw2, gw13, gwproj, gwqkv, gwkvy
         lane.sync(lag=1 if i > 0 else 0)
         while len(ready) > (1 if (i > 0 and lane.side is not None) else 0):
-            j, Fj, w2g, w13g, wpg, wqg = ready.pop(0)
-            prej = f"blocks.{j}."
-            G[prej + "mlp.w2.weight"] = w2g if Fj == Fp else w2g[:, :Fj].contiguous()
-            G[prej + "mlp.w1.weight"], G[prej + "mlp.w3.weight"] = w13g[:Fj], w13g[Fp:Fp + Fj]
-            G[prej + "attn.proj.weight"], G[prej + "attn.qkv.weight"] = wpg, wqg
-            _grads_ready([G[prej + k] for k in ("mlp.w2.weight", "mlp.w1.weight", "mlp.w3.weight", "attn.proj.weight",
-                                                "attn.qkv.weight")])
+            j, Fj, w2g, w13g, wpg, wqg, wkg = ready.pop(0)
+            prej = f"{prefix}{j}."
+            if t2i:     # layers/swiglu.py:4-17: w12 = (w1 ; w2) stacked, w3 = the down projection
+                names = ["mlp.w3.weight", "mlp.w12.weight", "attn.proj.weight", qkv_name]
+                G[prej + "mlp.w3.weight"], G[prej + "mlp.w12.weight"] = w2g, w13g
+                if wkg is not None:
+                    G[prej + "attn.kv_y.weight"] = wkg
+                    names.append("attn.kv_y.weight")
+            else:
+                names = ["mlp.w2.weight", "mlp.w1.weight", "mlp.w3.weight", "attn.proj.weight", qkv_name]
+                G[prej + "mlp.w2.weight"] = w2g if Fj == Fp else w2g[:, :Fj].contiguous()
+                G[prej + "mlp.w1.weight"], G[prej + "mlp.w3.weight"] = w13g[:Fj], w13g[Fp:Fp + Fj]
+            G[prej + "attn.proj.weight"], G[prej + qkv_name] = wpg, wqg
+            _grads_ready([G[prej + k] for k in names])
 
 
 
 def _cond_backward(module, P: dict, T: dict, S: dict, dmod, dtemb, G: Dict[str, torch.Tensor], ada_names: List[str],
-                   ada_rows: int, extra_ada: tuple = ()) -> None:
+                   ada_rows: int, extra_ada: tuple = (), label_table: bool = True) -> None:
     """Backward of `_cond_forward`: the adaLN GEMM (rows of `wada`: `ada_rows` per name in `ada_names`, then the
     (name, rows) pairs of `extra_ada`), c = silu(temb + table[y]), the timestep MLP.  dtemb [B, H] fp32 holds whatever the
     rest of the model already sent to temb."""
@@ -411,7 +462,8 @@ def _cond_backward(module, P: dict, T: dict, S: dict, dmod, dtemb, G: Dict[str, 
     # ---- c = silu(temb + table[y])
     dtab = torch.zeros_like(P["ytab"])
     ops.cond_combine_bwd_(dc, S["temb"], P["ytab"], S["y"], dtemb, dtab)
-    G["y_embedder.embedding_table.weight"] = dtab
+    if label_table:      # (the t2i model conditions on silu(temb) alone: its "table" is one zero row)
+        G["y_embedder.embedding_table.weight"] = dtab
     # ---- t_embedder: temb = silu(tfreq . wt0^T + bt0) . wt2^T + bt2
     G["t_embedder.mlp.2.weight"] = _wgrad(dtemb, S["h1t"])
     G["t_embedder.mlp.2.bias"] = _colsum(dtemb)
@@ -421,27 +473,22 @@ def _cond_backward(module, P: dict, T: dict, S: dict, dmod, dtemb, G: Dict[str, 
     G["t_embedder.mlp.0.bias"] = _colsum(dz1)
 
 
-def train_backward(module, S: dict, dout: torch.Tensor) -> Dict[str, torch.Tensor]:
-    """Gradients of every parameter (by name) for upstream gradient dout [B,3,H,W]."""
+def _decoder_backward(module, P: dict, T: dict, S: dict, dout: torch.Tensor, G: Dict[str, torch.Tensor], hidden_x: int,
+                      R: int) -> torch.Tensor:
+    """Backward of the pixel decoder + NerfEmbedder (dit_c2i_DeCo.py:212-248, :288-415): fills G with their parameter
+    gradients and returns dycond bf16 [B*L, p*p*32]."""
     x32 = S["x32"]
     dev = x32.device
-    P = module.prepare(dev)
-    T = P["train"]
-    B, L = S["B"], S["L"]
-    p, H = module.patch_size, module.hidden_size
-    nb = len(P["blocks"])
-    R = module.num_blocks - module.num_cond_blocks
+    p = module.patch_size
     C = module.in_channels
-    G: Dict[str, torch.Tensor] = {}
     z = lambda *shape: torch.zeros(shape, dtype=F32, device=dev)   # noqa: E731
-
     # ---- pixel decoder (+ NerfEmbedder)
     if DECODER_BWD == "scalar":     # fp32 scalar kernel (csrc/decoder_bwd.cu): the check the MMA kernel is validated against
         dycond, gdec = ops.pixel_decoder_bwd(x32, S["ycond"], dout.to(F32).contiguous(), T["dec_blob"], P["postab"], p,
-                                             module.hidden_size_x, R)
+                                             hidden_x, R)
     else:
         dycond, gdec = ops.pixel_decoder_bwd_tc(x32, S["ycond"], dout.to(F32).contiguous(), P["blob"], T["dec_bwd_blob"],
-                                                P["postab"], p, module.hidden_size_x, R)
+                                                P["postab"], p, hidden_x, R)
     nW = T["dec_blob"].numel()
     dpostab = gdec[nW:].view(p * p, 32)
     gx = z(32, C + module.x_embedder.max_freqs ** 2)
@@ -465,6 +512,25 @@ def train_backward(module, S: dict, dout: torch.Tensor) -> Dict[str, torch.Tenso
     of = 1152 + R * 5344
     G["dec_net.final_layer.linear.weight"] = gdec[of:of + 128].view(4, 32)[:C]
     G["dec_net.final_layer.linear.bias"] = gdec[of + 128:of + 128 + C]
+
+    return dycond
+
+
+def train_backward(module, S: dict, dout: torch.Tensor) -> Dict[str, torch.Tensor]:
+    """Gradients of every parameter (by name) for upstream gradient dout [B,3,H,W]."""
+    x32 = S["x32"]
+    dev = x32.device
+    P = module.prepare(dev)
+    T = P["train"]
+    B, L = S["B"], S["L"]
+    p, H = module.patch_size, module.hidden_size
+    nb = len(P["blocks"])
+    R = module.num_blocks - module.num_cond_blocks
+    C = module.in_channels
+    G: Dict[str, torch.Tensor] = {}
+    z = lambda *shape: torch.zeros(shape, dtype=F32, device=dev)   # noqa: E731
+
+    dycond = _decoder_backward(module, P, T, S, dout, G, module.hidden_size_x, R)
 
     # ---- cond_embed: ycond = s2 . wcond^T + bcond (its weight gradient, the largest single wgrad GEMM of the step, rides on
     # the second stream under the first blocks' chain)
@@ -524,7 +590,7 @@ def baseline_train_forward(module, x32, t, y):
     xp = ops.patchify(x32, p)
     _, mod = _cond_forward(module, P, t, y, S)
     s = ops.gemm(xp, P["wx"], P["bx"], ops.EPI_BIAS_F32)
-    s, blocks = _blocks_forward(P, mod, s, B, L, H, heads, pos)
+    s, blocks = _blocks_forward(P["blocks"], mod, s, B, L, H, heads, pos)
     # FinalLayer: LayerNorm (no affine) = RMSNorm of the centred row, then modulate with the last 2H adaLN columns
     shift, scale = mod[:, nb * 6 * H:nb * 6 * H + H], mod[:, nb * 6 * H + H:]
     xc = ops.center_rows(s)
@@ -567,6 +633,121 @@ def baseline_train_backward(module, S: dict, dout: torch.Tensor) -> Dict[str, to
     return G
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# Text-to-image denoiser (deco_b200/denoiser_t2i.py; dit_t2i_pixnerd.py:276-297 + SimpleMLPAdaLN): text embedding ->
+# text-refine blocks -> joint-attention image blocks -> the DeCo pixel decoder.
+@torch.no_grad()
+def prepare_train_t2i(module, P: dict, device) -> dict:
+    if "train" in P:
+        return P["train"]
+
+    def tr(w):
+        return ops.transpose_cast(w, rows_pad=w.shape[0])
+
+    T = dict(wt2T=tr(P["wt2"]), wadaT=tr(P["wada"]), wcondT=tr(P["wcond"]))
+    T["text"] = [dict(wqkvT=tr(bp["wqkv"]), wprojT=tr(bp["wproj"]), w13T=tr(bp["w13"]), w2T=tr(bp["w2"])) for bp in P["text"]]
+    T["blocks"] = [dict(wqkvT=tr(bp["wqkv"]), wprojT=tr(bp["wproj"]), w13T=tr(bp["w13"]), w2T=tr(bp["w2"]), wkvyT=tr(bp["wkvy"]))
+                   for bp in P["blocks"]]
+    T["dec_blob"] = pack_decoder_train(module, device)
+    T["dec_bwd_blob"] = pack_decoder_bwd(module, device)
+    from .denoiser_t2i import rope_cos_sin_ex2d
+    tab = rope_cos_sin_ex2d(module.x_embedder.max_freqs ** 2 * 2, module.patch_size, module.patch_size)[..., 0]
+    T["tabT"] = ops.transpose_cast(tab.to(device=device, dtype=F32).contiguous())
+    T["ones_row"] = torch.ones(1, module.hidden_size, dtype=bf16, device=device)
+    T["zero_mod"] = torch.zeros(1, module.hidden_size, dtype=bf16, device=device)
+    P["train"] = T
+    return T
+
+
+def t2i_train_forward(module, x32, t, y):
+    """Returns (out fp32 [B,3,H,W], saved dict); y = text-encoder states [B, T, txt_embed_dim]."""
+    dev = x32.device
+    P = module.prepare(dev)
+    prepare_train_t2i(module, P, dev)
+    B, _, Hh, Ww = x32.shape
+    p, H, heads = module.patch_size, module.hidden_size, module.num_groups
+    L = (Hh // p) * (Ww // p)
+    Tt = y.shape[1]
+    assert y.dim() == 3 and y.shape[0] == B and y.shape[2] == module.txt_embed_dim and Tt == module.txt_max_length
+    nt = len(P["text"])
+    pos = module.fetch_pos(Hh // p, Ww // p, dev)
+    S = dict(B=B, L=L, T=Tt, x32=x32, y=torch.zeros(B, dtype=torch.int64, device=dev), pos=pos)
+    Pc = dict(P, ytab=P["zero_row"])                       # c = silu(temb): the label table is one zero row
+    temb, mod = _cond_forward(module, Pc, t, S["y"], S)
+    # ---- text path: Linear -> RMSNorm -> + y_pos_embedding (fp32 stream), text-refine blocks (no RoPE)
+    y16 = y.detach().reshape(B * Tt, module.txt_embed_dim).to(bf16).contiguous()
+    yraw = ops.gemm(y16, P["wy"], P["by"], ops.EPI_BIAS_F32)
+    ys = ops.rmsnorm_addpos(yraw, P["yn"], P["ypos"])
+    ys, tblocks = _blocks_forward(P["text"], mod[:, :nt * 6 * H], ys, B, Tt, H, heads, None)
+    ytxt = ops.cast_bf16(ys)
+    # ---- image path: joint attention over [image || text] keys
+    xp = ops.patchify(x32, p)
+    s = ops.gemm(xp, P["ws"], P["bs"], ops.EPI_BIAS_F32)
+    s, blocks = _blocks_forward(P["blocks"], mod[:, nt * 6 * H:], s, B, L, H, heads, pos, joint=(ytxt, Tt))
+    s2 = ops.silu_add_rows(s, temb, L)
+    ycond = ops.gemm(s2, P["wcond"], P["bcond"], ops.EPI_BIAS)
+    out = ops.pixel_decoder(x32, ycond, P["blob"], P["postab"], p, module.decoder_hidden_size, module.num_decoder_blocks,
+                            out_dtype=F32)
+    S.update(y16=y16, yraw=yraw, tblocks=tblocks, ytxt=ytxt, xp=xp, blocks=blocks, s_final=s, s2=s2, ycond=ycond)
+    return out, S
+
+
+def t2i_train_backward(module, S: dict, dout: torch.Tensor) -> Dict[str, torch.Tensor]:
+    dev = dout.device
+    P = module.prepare(dev)
+    T = P["train"]
+    B, L, Tt = S["B"], S["L"], S["T"]
+    H = module.hidden_size
+    nt, ni = len(P["text"]), len(P["blocks"])
+    G: Dict[str, torch.Tensor] = {}
+    z = lambda *shape: torch.zeros(shape, dtype=F32, device=dev)   # noqa: E731
+    dycond = _decoder_backward(module, P, T, S, dout, G, module.decoder_hidden_size, module.num_decoder_blocks)
+    lane = _make_lane(dev)
+    G["dec_net.cond_embed.weight"] = lane.wgrad(dycond, S["s2"])
+    lane.mark()
+    G["dec_net.cond_embed.bias"] = _colsum(dycond)
+    ds2 = ops.gemm(dycond, T["wcondT"], None, ops.EPI_BIAS)
+    del dycond
+    dtemb = z(B, H)
+    ds = ops.silu_add_rows_bwd(ds2, S["s_final"], S["temb"], dtemb, L)
+    del ds2
+    dmod = z(B, (nt + ni) * 6 * H)
+    mod = S["mod"]
+    # ---- image blocks; the text stream's gradient collects every block's kv_y branch
+    dyt = z(B * Tt, H)
+    _blocks_backward(module, P, T, S, ds, dmod[:, nt * 6 * H:], G, lane,
+                     spec=dict(bps=P["blocks"], bts=T["blocks"], saved=S["blocks"], mod=mod[:, nt * 6 * H:], L=L, pos=S["pos"],
+                               prefix="blocks.", t2i=True, joint=dict(ytxt=S["ytxt"], T=Tt, dyt=dyt, ones=T["ones_row"])))
+    lane.sync(0)
+    G["s_embedder.proj.weight"] = _wgrad(ds, S["xp"])
+    G["s_embedder.proj.bias"] = _colsum(ds)
+    del ds
+    # ---- text-refine blocks (rows per image = T, no RoPE), then y_embedder: Linear -> RMSNorm (+ y_pos_embedding)
+    _blocks_backward(module, P, T, S, dyt, dmod[:, :nt * 6 * H], G, None,
+                     spec=dict(bps=P["text"], bts=T["text"], saved=S["tblocks"], mod=mod[:, :nt * 6 * H], L=Tt, pos=None,
+                               prefix="text_refine_blocks.", t2i=True))
+    G["y_pos_embedding"] = dyt.view(B, Tt, H).sum(0, keepdim=True)
+    dyn, dyraw = z(H), z(B * Tt, H)
+    zs = z(1, 2 * H)
+    ops.rmsnorm_modulate_bwd_(dyraw, ops.cast_bf16(dyt), S["yraw"], P["yn"], T["zero_mod"].expand(B, H), dyn,
+                              zs[:, :H].expand(B, H), zs[:, H:].expand(B, H), Tt)
+    G["y_embedder.norm.weight"] = dyn
+    G["y_embedder.proj.weight"] = _wgrad(dyraw, S["y16"])
+    G["y_embedder.proj.bias"] = _colsum(dyraw)
+    names = [f"text_refine_blocks.{i}.adaLN_modulation.0" for i in range(nt)] + [f"blocks.{i}.adaLN_modulation.0" for i in range(ni)]
+    _cond_backward(module, dict(P, ytab=P["zero_row"]), T, S, dmod, dtemb, G, names, 6 * H, label_table=False)
+    _grads_ready(list(G.values()))
+    return G
+
+
+def _train_fns(module):
+    if hasattr(module, "text_refine_blocks"):
+        return t2i_train_forward, t2i_train_backward
+    if hasattr(module, "final_layer"):
+        return baseline_train_forward, baseline_train_backward
+    return train_forward, train_backward
+
+
 class DenoiserFn(torch.autograd.Function):
     """out = net(x, t, y) as one autograd node (PixNerDiT, or the patch-linear FlattenDiT); *params only tell autograd
     which leaves receive gradients."""
@@ -574,8 +755,9 @@ class DenoiserFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, module, names: List[str], x, t, y, *params):
         x32 = x.detach().to(F32).contiguous()
-        fwd = baseline_train_forward if hasattr(module, "final_layer") else train_forward
-        out, S = fwd(module, x32, t.detach().reshape(-1).to(F32), y.detach().reshape(-1))
+        fwd = _train_fns(module)[0]
+        yy = y.detach() if hasattr(module, "text_refine_blocks") else y.detach().reshape(-1)
+        out, S = fwd(module, x32, t.detach().reshape(-1).to(F32), yy)
         ctx.module, ctx.names, ctx.S = module, names, S
         ctx.meta = [(p.requires_grad, p.shape, p.dtype) for p in params]
         return out
@@ -584,8 +766,7 @@ class DenoiserFn(torch.autograd.Function):
     def backward(ctx, dout):
         if ctx.S is None:
             raise RuntimeError("deco_b200 denoiser: backward called twice (activations are released after one pass)")
-        bwd = baseline_train_backward if hasattr(ctx.module, "final_layer") else train_backward
-        G = bwd(ctx.module, ctx.S, dout)
+        G = _train_fns(ctx.module)[1](ctx.module, ctx.S, dout)
         ctx.S = None
         # an overlapped gradient averager reduces G's buffers in place on another stream: order this stream behind it
         # before autograd reads (or clones) them

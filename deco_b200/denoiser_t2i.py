@@ -238,9 +238,14 @@ class PixNerDiT(nn.Module):
         """x [B,C,H,W], t [B] in [0,1], y [B, T, txt_embed_dim] text-encoder states -> velocity [B,C,H,W] (bf16)."""
         if not x.is_cuda:
             raise RuntimeError("deco_b200 t2i PixNerDiT runs on CUDA (sm_100a) only; there is no CPU fallback")
-        if torch.is_grad_enabled() and (x.requires_grad or (self.training and any(p.requires_grad for p in self.parameters()))):
-            raise NotImplementedError("the text-to-image denoiser has no backward yet (the class-conditional PixNerDiT does: "
-                                      "deco_b200/autograd.py); call under torch.no_grad() / .eval()")
+        if torch.is_grad_enabled() and (x.requires_grad or y.requires_grad):
+            raise NotImplementedError("the denoiser backward yields parameter gradients only (the reference never "
+                                      "differentiates w.r.t. x_t or the frozen text encoder's states); detach x and y")
+        if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
+            # training step: one autograd node with a hand-written backward (deco_b200/autograd.py::t2i_train_forward /
+            # _backward: the DeCo denoiser's block and decoder backward, joint attention over one [image || text] key segment)
+            from .autograd import denoiser_train_apply
+            return denoiser_train_apply(self, x, t, y)
         B, Cc, Hh, Ww = x.shape
         p = self.patch_size
         assert Cc == self.in_channels and Hh % p == 0 and Ww % p == 0

@@ -553,6 +553,51 @@ def test_baseline_training_step_gradients(dev, hidden, groups, blocks, res, B):
     assert not [(e, n) for e, n in worst if e > 6e-2], worst[:6]
 
 
+def test_t2i_training_step_gradients_xxl(dev):
+    """The configs_t2i/sft_res512.yaml architecture (DeCo-XXL: H 1536, 24 heads of 64, 4 text + 16 joint blocks, 128 text
+    tokens of 2048) at 256 px, 2 images."""
+    _t2i_grad_check(dev, O.CFG_XXL_T2I, 256, 2)
+
+
+@pytest.mark.parametrize("hidden,groups,res,B", [(256, 4, 64, 2), (288, 4, 128, 2)])
+def test_t2i_training_step_gradients(dev, hidden, groups, res, B):
+    """Text-to-image denoiser (dit_t2i_pixnerd.py:276-297 + SimpleMLPAdaLN) in .train() mode: parameter gradients of the
+    hand-written backward (text embedding, text-refine blocks, joint-attention image blocks with the kv_y branch into the
+    text stream, pixel decoder) against autograd over the fp32 oracle."""
+    cfg = O.T2ICfg(in_channels=3, num_groups=groups, hidden_size=hidden, decoder_hidden_size=32, num_encoder_blocks=3,
+                   num_decoder_blocks=2, num_text_blocks=2, patch_size=16, txt_embed_dim=64, txt_max_length=24)
+    _t2i_grad_check(dev, cfg, res, B)
+
+
+def _t2i_grad_check(dev, cfg, res, B):
+    from helpers import build_t2i_module
+    m, P = build_t2i_module(cfg, dev)
+    m.train()
+    x = torch.tanh(torch.randn(B, 3, res, res, device=dev, generator=_g(41)))
+    t = torch.rand(B, device=dev, generator=_g(42))
+    y = torch.randn(B, cfg.txt_max_length, cfg.txt_embed_dim, device=dev, generator=_g(43))
+    w = torch.randn(B, 3, res, res, device=dev, generator=_g(44))
+    out = m(x, t, y)
+    assert out.requires_grad and out.dtype == torch.float32
+    (out * w).sum().backward()
+    Pr = {k: v.to(dev).clone().requires_grad_(True) for k, v in P.items()}
+    ref = O.t2i_forward(Pr, cfg, x, t, y)
+    (ref * w).sum().backward()
+    assert rel_l2(out, ref) < 1e-2
+    worst, num, den = [], 0.0, 0.0
+    for name, prm in m.named_parameters():
+        assert prm.grad is not None, name
+        g, gr = prm.grad.double(), Pr[name].grad.double()
+        assert g.shape == gr.shape, name
+        num += float((g - gr).pow(2).sum())
+        den += float(gr.pow(2).sum())
+        worst.append((rel_l2(g, gr), name))
+    worst.sort(reverse=True)
+    print("t2i global grad rel-L2 %.3e; worst tensors: %s" % (math.sqrt(num / den), worst[:8]))
+    assert math.sqrt(num / den) < 2e-2, worst[:8]
+    assert not [(e, n) for e, n in worst if e > 6e-2], worst[:8]
+
+
 def test_center_rows_kernel(dev):
     from deco_b200 import ops
     for M, H in ((70, 144), (513, 1152), (9, 2048)):
