@@ -683,10 +683,14 @@ static int rmsnorm_modulate_bwd_impl(const void* dh_bf16, const float* x, const 
     DECO_CHECK_LAUNCH("rmsnorm_bwd_rowstats_kernel");
     // one resident wave of blocks, each with an equal share of contiguous rows
     const int threads = ((hidden / 4) + 31) / 32 * 32;
-    int per_sm = 0;
-    cudaError_t oe = gate ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rmsnorm_modulate_bwd_kernel<true>, threads, 0)
-                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rmsnorm_modulate_bwd_kernel<false>, threads, 0);
-    if (oe != cudaSuccess || per_sm < 1) per_sm = 1;
+    static int occ_cache[2][17] = {};           // resident blocks per SM by (gate variant, warps per block); 0 = not asked yet
+    int& per_sm = occ_cache[gate ? 1 : 0][threads / 32];
+    if (per_sm == 0) {
+        int v = 0;
+        cudaError_t oe = gate ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, rmsnorm_modulate_bwd_kernel<true>, threads, 0)
+                              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, rmsnorm_modulate_bwd_kernel<false>, threads, 0);
+        per_sm = (oe != cudaSuccess || v < 1) ? 1 : v;
+    }
     long long nblk = (long long)per_sm * kNumSMs;
     if (nblk > M) nblk = M;
     if (gate)
