@@ -1,3 +1,4 @@
+# ncu launch list of one training step on ONE stream (eager launches), aggregated per kernel: run under gpurun
 set -u
 O=gpurun_out; mkdir -p $O
 PT="python bench.py --workload train256 --steps 1 --warmup 2 --no-e2e --no-cpu-baseline --torch-baseline none --profile"
