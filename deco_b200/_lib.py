@@ -18,6 +18,7 @@ SIGNATURES = {
     "deco_last_error": (C.c_char_p, []),
     "deco_abi_version": (_i, []),
     "deco_gemm_bf16": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _vp, _vp, _ll, _vp, _ll, _i, _i, _vp]),
+    "deco_gemm_tile_plan": (_i, [_i, _i, _i, _i, _vp, _vp, _vp]),
     "deco_gemm_bf16_tn": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _i, _vp]),
     "deco_gemm_bf16_tn_deint16": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _i, _vp]),
     "deco_gemm_bf16_f32_splitk": (_i, [_vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _vp]),

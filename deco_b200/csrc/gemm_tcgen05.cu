@@ -18,6 +18,7 @@
 // warps 4-7 = epilogue (warp w owns TMEM lanes 32*(w%4)..+31 = tile rows).
 #include "tcgen05.cuh"
 #include "tma_host.cuh"
+#include <vector>
 
 namespace deco {
 
@@ -339,11 +340,11 @@ __device__ __forceinline__ void epilogue_chunk_swiglu_bwd(const GemmParams& P, c
 // 192-wide tiles they are 192 tiles = 2.6 -> 3 rounds of a tile shape that feeds the tensor pipe a quarter slower.
 struct TileSchedule {
     int num_n, num_mn, num_tiles, group, groups, full_mn;     // full_mn: tiles of the full-width columns (0 = no ragged column)
-    __device__ __forceinline__ int tile_of_round(int round) const {      // -1 = this group is done
+    __host__ __device__ __forceinline__ int tile_of_round(int round) const {      // -1 = this group is done
         const int t = round * groups + ((round & 1) ? groups - 1 - group : group);
         return t < num_tiles ? t : -1;
     }
-    __device__ __forceinline__ void coords(int tile, int& m_blk, int& n_blk, int& ks) const {
+    __host__ __device__ __forceinline__ void coords(int tile, int& m_blk, int& n_blk, int& ks) const {
         const int mn = tile % num_mn;
         ks = tile / num_mn;
         if (full_mn > 0) {
@@ -685,6 +686,26 @@ static int g_force_staged = -1;
 
 static int num_sms() { return device_sm_count() - deco_reserved_sms(); }
 
+// Tile width of an M x N problem on `groups` CTA groups of cg CTAs: the smallest rounds x width / efficiency (see
+// deco_gemm_bf16).  A ragged last column tile counts as its fraction of a tile when it can run a narrower MMA.
+static int pick_tile_n(int M, int N, int cg, int groups) {
+    const int num_m = (M + kBM * cg - 1) / (kBM * cg);
+    int bn = 0;
+    double best = 0.0;
+    for (int cand : {256, 192, 128}) {
+        if (cand == 192 && N % 192 != 0) continue;
+        const int nfull = N / cand, rem = N - nfull * cand;
+        const double frac = rem == 0 ? 0.0 : (rem % 32 == 0 ? (double)rem / cand : 1.0);
+        const double units = (double)num_m * (nfull + frac);
+        double rounds = units / groups;
+        rounds = (rounds <= 1.0) ? 1.0 : (double)(long long)(rounds + 0.999);
+        const double eff = cand == 256 ? 1.0 : (cand == 192 ? 0.78 : 0.55);
+        const double cost = rounds * cand / eff;
+        if (bn == 0 || cost < best) { bn = cand; best = cost; }
+    }
+    return bn;
+}
+
 }  // namespace deco
 
 extern "C" int deco_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, void* out, long long ldo,
@@ -712,23 +733,7 @@ extern "C" int deco_gemm_bf16(const void* A, long long lda, const void* W, long 
     // profiles/gemm_bench_r1.txt); a ragged last column tile runs a narrower MMA and costs its fraction of a tile; the
     // balanced schedule (TileSchedule) packs full and ragged tiles into ceil(units / CTA groups) rounds.  Pick the width with
     // the smallest rounds x width / efficiency: N = 1152 on 8192 rows -> 256 (2 rounds) instead of 192 (3 rounds).
-    int bn = tile_n;
-    if (bn == 0) {
-        const int groups = num_sms() / cg;
-        const int num_m = (M + kBM * cg - 1) / (kBM * cg);
-        double best = 0.0;
-        for (int cand : {256, 192, 128}) {
-            if (cand == 192 && N % 192 != 0) continue;
-            const int nfull = N / cand, rem = N - nfull * cand;
-            const double frac = rem == 0 ? 0.0 : (rem % 32 == 0 ? (double)rem / cand : 1.0);
-            const double units = (double)num_m * (nfull + frac);
-            double rounds = units / groups;
-            rounds = (rounds <= 1.0) ? 1.0 : (double)(long long)(rounds + 0.999);
-            const double eff = cand == 256 ? 1.0 : (cand == 192 ? 0.78 : 0.55);
-            const double cost = rounds * cand / eff;
-            if (bn == 0 || cost < best) { bn = cand; best = cost; }
-        }
-    }
+    const int bn = tile_n ? tile_n : pick_tile_n(M, N, cg, num_sms() / cg);
     DECO_CHECK_ARG(bn == 128 || bn == 192 || bn == 256, "gemm: tile_n must be 128, 192 or 256");
     // staged (coalesced) epilogue everywhere except SwiGLU, whose output is half as wide as its accumulator tile and
     // is compute-heavy: the row-per-thread form keeps all 128 epilogue threads busy (1554 vs 1069 TFLOP/s at BN = 256)
@@ -748,6 +753,45 @@ extern "C" int deco_gemm_bf16(const void* A, long long lda, const void* W, long 
     if (bn == 256) return dispatch_variant<256>(cg, staged, epilogue, ta, tb, P, ctas, st);
     if (bn == 192) return dispatch_variant<192>(cg, staged, epilogue, ta, tb, P, ctas, st);
     return dispatch_variant<128>(cg, staged, epilogue, ta, tb, P, ctas, st);
+}
+
+// Host-side view of what deco_gemm_bf16 would launch for an M x N x K problem on `ctas` CTAs (0 = this device's SM count):
+// the tile width it picks and, by walking the device code's own TileSchedule for every CTA group, the heaviest group's work in
+// 1/256ths of a full-width tile (a ragged last-column tile that runs a narrower MMA counts n_last / tile_n of one) and the
+// number of tiles nobody or more than one group visits (must be 0).  Needs no GPU: tests/test_abi.py checks the schedule.
+extern "C" int deco_gemm_tile_plan(int M, int N, int K, int ctas, int* tile_n_out, int* max_load_256ths, int* bad_tiles)
+{
+    using namespace deco;
+    DECO_CHECK_ARG(M > 0 && N > 0 && K > 0 && tile_n_out && max_load_256ths && bad_tiles, "gemm_tile_plan: bad arguments");
+    const int cg = M > kBM ? 2 : 1;
+    if (ctas <= 0) ctas = num_sms();
+    const int groups = ctas / cg;
+    DECO_CHECK_ARG(groups > 0, "gemm_tile_plan: no CTA group");
+    const int bn = pick_tile_n(M, N, cg, groups);
+    const int num_m = (M + kBM * cg - 1) / (kBM * cg), num_n = (N + bn - 1) / bn;
+    const int n_rem = N - (num_n - 1) * bn;
+    const int n_last = (n_rem < bn && n_rem % 32 == 0) ? n_rem : bn;
+    const int used = num_m * num_n < groups ? num_m * num_n : groups;
+    std::vector<int> visits((size_t)num_m * num_n, 0);
+    long long worst = 0;
+    for (int g = 0; g < used; ++g) {
+        TileSchedule sched;
+        sched.num_n = num_n; sched.num_mn = num_m * num_n; sched.num_tiles = num_m * num_n; sched.group = g; sched.groups = used;
+        sched.full_mn = (n_last < bn && num_n > 1 && (long long)M * K * 2 <= (64ll << 20)) ? num_m * (num_n - 1) : 0;
+        long long load = 0;
+        for (int round = 0, tile; (tile = sched.tile_of_round(round)) >= 0; ++round) {
+            int m_blk, n_blk, ks;
+            sched.coords(tile, m_blk, n_blk, ks);
+            if (m_blk < 0 || m_blk >= num_m || n_blk < 0 || n_blk >= num_n || ks != 0) { *bad_tiles = -1; return DECO_OK; }
+            ++visits[(size_t)m_blk * num_n + n_blk];
+            load += (n_blk == num_n - 1 ? n_last : bn) * 256 / bn;
+        }
+        if (load > worst) worst = load;
+    }
+    int bad = 0;
+    for (int v : visits) bad += (v != 1);
+    *tile_n_out = bn; *max_load_256ths = (int)worst; *bad_tiles = bad;
+    return DECO_OK;
 }
 
 extern "C" int deco_gemm_set_tuning(int cta_group, int staged_epilogue) {

@@ -49,6 +49,11 @@ int deco_gemm_bf16(const void* A, long long lda, const void* W, long long ldw, v
                    const void* resid, long long ldr, const void* gate, long long gate_stride, int rows_per_gate,
                    int tile_n, void* stream);
 
+/* Host-side view of the launch deco_gemm_bf16 would make (no GPU needed): the tile width it picks for M x N x K on `ctas`
+ * CTAs (0 = this device's SM count) and, walking the kernels' own static tile schedule, the heaviest CTA group's work in
+ * 1/256ths of a full-width tile plus the number of tiles not visited exactly once (0 for a correct schedule). */
+int deco_gemm_tile_plan(int M, int N, int K, int ctas, int* tile_n_out, int* max_load_256ths, int* bad_tiles);
+
 /* ---- GEMMs whose epilogues absorb the memory-bound neighbours of a DiT block (csrc/gemm_fused.cu) ----
  * RMSNorm commutes with the following Linear because its row factor is a scalar:
  *   Linear(modulate(RMSNorm(x))) = rstd[row] * ((x * w_norm * (1 + scale)) . W^T) + (shift . W^T)[image]

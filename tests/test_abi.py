@@ -73,3 +73,28 @@ def test_backward_entry_points_validate_arguments_without_a_gpu(lib):
     assert rc == -2 and b"head_dim" in lib.deco_last_error()
     rc = lib.deco_transpose_cast(p, 0, 8, p, 8, 4, 3, 4, None)               # odd column count
     assert rc == -1 and b"even" in lib.deco_last_error()
+
+
+def test_gemm_tile_plan_is_balanced_and_complete():
+    """Host-side walk of the GEMM kernels' static tile schedule (deco_gemm_tile_plan, no GPU): every tile is visited exactly
+    once, and at the training shapes (8192 tokens, 74 CTA pairs) the 1152-wide GEMMs take 256-wide tiles whose ragged last
+    column is dealt out so that every pair ends with exactly two tile-times of work (192-wide tiles: three rounds)."""
+    import ctypes
+    from deco_b200 import _lib
+    lib = _lib.load()
+
+    def plan(M, N, K, ctas=148):
+        a, b, c = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        assert lib.deco_gemm_tile_plan(M, N, K, ctas, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)) == 0
+        return a.value, b.value / 256.0, c.value
+
+    for shape in [(8192, 1152, 1152), (8192, 3456, 1152), (8192, 6144, 1152), (8192, 1152, 6144), (131072, 8192, 1152),
+                  (16384, 1152, 3072), (32, 1152, 256), (300, 688, 144), (77, 96, 64), (1024, 5472, 1024)]:
+        bn, load, bad = plan(*shape)
+        assert bn in (128, 192, 256) and bad == 0, (shape, bn, bad)
+    assert plan(8192, 1152, 1152) == (256, 2.0, 0)           # 128 full + 32 half tiles on 74 pairs
+    assert plan(8192, 1152, 3072) == (256, 2.0, 0)
+    assert plan(8192, 1152, 6144) == (256, 3.0, 0)           # A = 100 MB: row-major order (ragged tiles not deferred)
+    bn, load, _ = plan(8192, 3456, 1152)                     # 13.5 column tiles x 32 row tiles = 432 units on 74 pairs
+    assert bn == 256 and load == 6.0
+    assert lib.deco_gemm_tile_plan(0, 8, 8, 148, None, None, None) == -1
