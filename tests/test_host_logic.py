@@ -129,6 +129,29 @@ def test_no_cpu_fallback():
         ops.fp2uint8(x)
 
 
+def test_training_path_dispatch_and_no_cpu_fallback():
+    """Every trainable denoiser goes through the same autograd node with its own forward / backward pair, and in .train()
+    mode a CPU input still fails loudly (no fallback to PyTorch autograd)."""
+    from deco_b200 import PixNerDiT, autograd as A, ops
+    from deco_b200.denoiser_baseline import FlattenDiT
+    from deco_b200.denoiser_t2i import PixNerDiT as T2I
+    c2i = PixNerDiT(in_channels=3, num_groups=4, hidden_size=256, hidden_size_x=32, num_blocks=4, num_cond_blocks=1,
+                    patch_size=16, num_classes=10)
+    base = FlattenDiT(in_channels=3, num_groups=4, hidden_size=256, num_blocks=2, patch_size=16, num_classes=10)
+    t2i = T2I(in_channels=3, num_groups=4, hidden_size=256, decoder_hidden_size=32, num_encoder_blocks=2, num_decoder_blocks=1,
+              num_text_blocks=1, patch_size=16, txt_embed_dim=64, txt_max_length=8)
+    assert A._train_fns(c2i) == (A.train_forward, A.train_backward)
+    assert A._train_fns(base) == (A.baseline_train_forward, A.baseline_train_backward)
+    assert A._train_fns(t2i) == (A.t2i_train_forward, A.t2i_train_backward)
+    x = torch.zeros(1, 3, 32, 32)
+    for m, y in ((c2i, torch.zeros(1, dtype=torch.long)), (base, torch.zeros(1, dtype=torch.long)), (t2i, torch.zeros(1, 8, 64))):
+        m.train()
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            m(x, torch.zeros(1), y)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.center_rows(torch.zeros(4, 8))
+
+
 def _torch_cfg_step(x, net_out, g, dt, c0=1.0, prev=(), coeffs=(), x_out=None, want_pred=False, want_v=False,
                     want_u8=False):
     """Test-only torch statement of csrc/sampler.cu so the samplers' host control flow can be checked without a GPU."""
